@@ -197,6 +197,15 @@ struct SineInit {
     i64 nx, ny, nz; T u0;
 };
 
+// In the MPI build MultiBlockLattice3D::get() hands out a proxy cell (parallelism/parallelMultiBlockLattice3D.hh:69-87),
+// so raw cell data is reached through the single atomic block instead: local index = global index - getLocation().
+static plb::Cell<double, DESCRIPTOR>& raw_cell(MultiBlockLattice3D<double, DESCRIPTOR>& lattice, plint x, plint y, plint z) {
+    const plint id = lattice.getLocalInfo().getBlocks()[0];
+    BlockLattice3D<double, DESCRIPTOR>& b = lattice.getComponent(id);
+    const Dot3D loc = b.getLocation();
+    return b.get(x - loc.x, y - loc.y, z - loc.z);
+}
+
 static void dump_lattice(MultiBlockLattice3D<double, DESCRIPTOR>& lattice, const std::string& fname) {
     // Palabos serialised-cell layout: 19 fBar populations then the 4 external scalars (src/core/cell.hh:103-121),
     // cells in [x][y][z] order, z fastest (src/atomicBlock/blockLattice3D.hh:671-689).
@@ -204,7 +213,20 @@ static void dump_lattice(MultiBlockLattice3D<double, DESCRIPTOR>& lattice, const
     std::vector<double> v((size_t)nx * ny * nz * 23);
     size_t o = 0;
     for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
-        plb::Cell<double, DESCRIPTOR>& c = lattice.get(x, y, z);
+        plb::Cell<double, DESCRIPTOR>& c = raw_cell(lattice, x, y, z);
+        for (int i = 0; i < 19; ++i) v[o++] = c[i];
+        for (int i = 0; i < 4; ++i) v[o++] = *c.getExternal(i);
+    }
+    write_f64(fname, v);
+}
+// debugging aid: the whole atomic block including its envelope, local index order
+static void dump_block(MultiBlockLattice3D<double, DESCRIPTOR>& lattice, const std::string& fname) {
+    const plint id = lattice.getLocalInfo().getBlocks()[0];
+    BlockLattice3D<double, DESCRIPTOR>& b = lattice.getComponent(id);
+    std::vector<double> v((size_t)b.getNx() * b.getNy() * b.getNz() * 23);
+    size_t o = 0;
+    for (plint x = 0; x < b.getNx(); ++x) for (plint y = 0; y < b.getNy(); ++y) for (plint z = 0; z < b.getNz(); ++z) {
+        plb::Cell<double, DESCRIPTOR>& c = b.get(x, y, z);
         for (int i = 0; i < 19; ++i) v[o++] = c[i];
         for (int i = 0; i < 4; ++i) v[o++] = *c.getExternal(i);
     }
@@ -215,7 +237,10 @@ static void dump_velocity(MultiTensorField3D<double, 3>& vel, const std::string&
     std::vector<double> v((size_t)nx * ny * nz * 3);
     size_t o = 0;
     for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
-        Array<double, 3> const& u = vel.get(x, y, z);
+        const plint id = vel.getLocalInfo().getBlocks()[0];
+        TensorField3D<double, 3>& b = vel.getComponent(id);
+        const Dot3D loc = b.getLocation();
+        Array<double, 3> const& u = b.get(x - loc.x, y - loc.y, z - loc.z);
         v[o++] = u[0]; v[o++] = u[1]; v[o++] = u[2];
     }
     write_f64(fname, v);
@@ -272,7 +297,7 @@ static int run(const Config& cfg) {
         std::vector<double> ext = read_f64(cfg.str("externals"));
         size_t o = 0;
         for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
-            plb::Cell<double, DESCRIPTOR>& c = lattice.get(x, y, z);
+            plb::Cell<double, DESCRIPTOR>& c = raw_cell(lattice, x, y, z);
             for (int i = 0; i < 4; ++i) *c.getExternal(i) = ext[o++];
         }
         lattice.duplicateOverlaps(modif::staticVariables);
@@ -282,7 +307,7 @@ static int run(const Config& cfg) {
         std::vector<double> pop = read_f64(cfg.str("populations"));
         size_t o = 0;
         for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
-            plb::Cell<double, DESCRIPTOR>& c = lattice.get(x, y, z);
+            plb::Cell<double, DESCRIPTOR>& c = raw_cell(lattice, x, y, z);
             for (int i = 0; i < 19; ++i) c[i] = pop[o++];
             for (int i = 0; i < 4; ++i) *c.getExternal(i) = pop[o++];
         }
@@ -323,6 +348,7 @@ static int run(const Config& cfg) {
     std::auto_ptr<MultiTensorField3D<double, 3> > velocity = generateMultiTensorField<double, 3>(domain);
 
     dump_lattice(lattice, out + "/pop_init.f64");
+    if (cfg.integer("dump_block", 0)) dump_block(lattice, out + "/blk_init.f64");
     if (np > 0) dump_particles(*fsi, np, out + "/vert_init.f64", out + "/part_init.f64");
 
     double t_vel = 0, t_ext = 0, t_ib = 0, t_lbm = 0;
@@ -336,6 +362,15 @@ static int run(const Config& cfg) {
         double t2 = MPI_Wtime();
         if (!lbm_only) applyProcessingFunctional(wrap_ibm_dynamics3D(*fsi), domain, lattice, *velocity);
         double t3 = MPI_Wtime();
+        if (cfg.integer("debug_manual_cs", 0)) {
+            // debugging aid (fully periodic only): run the atomic-block step by hand and dump the block before the envelope refresh
+            const plint id = lattice.getLocalInfo().getBlocks()[0];
+            BlockLattice3D<double, DESCRIPTOR>& b = lattice.getComponent(id);
+            b.collideAndStream(b.getBoundingBox());
+            std::ostringstream s; s << (it + 1);
+            dump_block(lattice, out + "/pre_" + s.str() + ".f64");
+            lattice.duplicateOverlaps(modif::staticVariables);
+        } else
         lattice.collideAndStream();
         double t4 = MPI_Wtime();
         if (timed) { t_vel += t1 - t0; t_ext += t2 - t1; t_ib += t3 - t2; t_lbm += t4 - t3; }
@@ -343,6 +378,7 @@ static int run(const Config& cfg) {
         if (dump_every > 0 && (done % dump_every == 0 || done == steps)) {
             std::ostringstream s; s << done;
             dump_lattice(lattice, out + "/pop_" + s.str() + ".f64");
+            if (cfg.integer("dump_block", 0)) dump_block(lattice, out + "/blk_" + s.str() + ".f64");
             if (!lbm_only) dump_velocity(*velocity, out + "/vel_" + s.str() + ".f64");
             if (np > 0) dump_particles(*fsi, np, out + "/vert_" + s.str() + ".f64", out + "/part_" + s.str() + ".f64");
         }

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref/ref_harness, built by
+oracle/build_ref.sh from /root/reference). Run it in the build container (it needs /root/reference):
+
+    oracle/build_ref.sh && python tests/golden/make_golden.py
+
+Fixtures (all float64 unless noted, produced by the reference's own code paths):
+  rbc626.npz        the reference's sphere mesh (progs/rbc_in_shear/sphere_TRImesh_626n_1248el.msh) as arrays, the
+                    connectivity its ParticleShape builds (links, rest lengths, rest areas, pairs, rest angles), and the
+                    biconcave RBC produced by shrink_rbc_volume(0.59 V, 10000) with create_rbc_params (parameters as
+                    progs/rbcs_in_shear/rbcs_in_shear.cpp:44-71).
+  lbm_periodic.npz  12x10x14 fully periodic box, frozen synthetic force/phase field: populations after 0, 1, 10
+                    collideAndStream() calls.
+  lbm_walls.npz     same with y non-periodic (free bounce-back at the block faces).
+  ib_rbc1.npz       24x22x20 periodic box with one RBC + position regulator: vertex state after steps 1..5, and the
+                    lattice / velocity field of step 5 sampled at every 2nd cell (full driver sequence).
+  ib_rbc2_pfp.npz   36x22x20 box periodic in x,z, 2 RBCs one of which straddles the periodic x face, 3 steps.
+"""
+import pathlib
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+import kit  # noqa: E402
+
+MSH = "/root/reference/progs/rbc_in_shear/sphere_TRImesh_626n_1248el.msh"
+
+
+def harness(*args):
+    r = subprocess.run([str(kit.REF_HARNESS), *map(str, args)], capture_output=True, text=True, check=True)
+    return r.stdout
+
+
+def make_rbc_fixture():
+    with tempfile.TemporaryDirectory() as d:
+        d = pathlib.Path(d)
+        harness("mesh2bin", MSH, d / "s.mesh")
+        harness("shape", d / "s.mesh", d / "s")
+        raw = np.fromfile(d / "s.mesh", dtype=np.int64, count=2)
+        nv, nt = int(raw[0]), int(raw[1])
+        blob = open(d / "s.mesh", "rb").read()
+        verts = np.frombuffer(blob, dtype=np.float64, count=nv * 3, offset=16).reshape(nv, 3)
+        tris = np.frombuffer(blob, dtype=np.int64, count=nt * 3, offset=16 + nv * 24).reshape(nt, 3)
+        li = np.fromfile(d / "s.links.i64", dtype=np.int64).reshape(-1, 4)
+        lf = np.fromfile(d / "s.links.f64")
+        ti = np.fromfile(d / "s.tris.i64", dtype=np.int64).reshape(-1, 3)
+        tf = np.fromfile(d / "s.tris.f64").reshape(-1, 2)
+        pi = np.fromfile(d / "s.pairs.i64", dtype=np.int64).reshape(-1, 4)
+        pf = np.fromfile(d / "s.pairs.f64").reshape(-1, 2)
+        sc = np.fromfile(d / "s.scalars.f64")  # area, volume, radius, cx, cy, cz
+        assert np.array_equal(ti, tris)
+        # membrane parameters exactly as progs/rbcs_in_shear/rbcs_in_shear.cpp:44-71
+        a_lb, area = sc[2], sc[0]
+        tau, Re_p, Ca, k_bend_rel, poisson = 1.0, 0.1, 0.1, 0.006, 0.99
+        nu = (tau - 0.5) / 3.0
+        gamma = Re_p * nu / (a_lb * a_lb)
+        G = a_lb * gamma * nu / Ca
+        K_area = (poisson + 1) / (1 - poisson) * G
+        k_bend = k_bend_rel * G * area
+        harness("deflate", d / "s.mesh", d / "rbc.f64", repr(G), repr(K_area), repr(k_bend), 0.59, 10000)
+        r = np.fromfile(d / "rbc.f64")
+        np.savez_compressed(HERE / "rbc626.npz", verts=verts, tris=tris.astype(np.int32), tri_area=tf[:, 0], tri_lmean=tf[:, 1],
+                            links=li[:, :2].astype(np.int32), link_tri=li[:, 2:].astype(np.int32), link_len=lf,
+                            pairs=pi.astype(np.int32), pair_cs=pf, scalars=sc,
+                            rbc_params=r[:8], rbc_pos=r[8:8 + nv * 3].reshape(nv, 3), rbc_area_volume=r[8 + nv * 3:],
+                            membrane_inputs=np.array([G, K_area, k_bend]))
+        print("rbc626.npz: nv", nv, "nt", nt, "links", len(lf), "pairs", len(pf))
+
+
+def make_lbm(name, per):
+    nx, ny, nz = 12, 10, 14
+    ext = kit.synthetic_externals(nx, ny, nz, seed=3)
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=10, dump_every=1, lbm_only=1, periodicity=per,
+                                 omega=1.0 / 0.9, omega_inner=1.0 / 2.5), externals=ext)
+    np.savez_compressed(HERE / name, pop_init=out["pop_init"], pop_1=out["pop_1"], pop_2=out["pop_2"], pop_10=out["pop_10"],
+                        omega=1.0 / 0.9, omega_inner=1.0 / 2.5, per=np.array([c == "p" for c in per], dtype=np.int32))
+    print(name, "ok")
+
+
+def make_ib(name, dims, per, centers, steps, seed, regulator_p=0.0):
+    shape, params, rbc_pos, _ = kit.load_rbc_fixture()
+    nx, ny, nz = dims
+    pos = kit.place_particles(rbc_pos, centers, seed=seed)
+    cfg = dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=1, periodicity=per, omega=1.0, omega_inner=1.0 / 3.0,
+               body_x=1e-6, body_y=0.0, body_z=-2e-6, u0=0.02)
+    if regulator_p:
+        cfg.update(regulator_p=regulator_p, regulator_x=centers[0][0], regulator_y=centers[0][1], regulator_z=centers[0][2])
+    out = kit.run_reference(cfg, verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"],
+                pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(), vel_final_sample=out[f"vel_{steps}"][::2, ::2, ::2].copy(),
+                per=np.array([c == "p" for c in per], dtype=np.int32), body=np.array([1e-6, 0.0, -2e-6]),
+                omega=1.0, omega_inner=1.0 / 3.0, steps=steps, regulator_p=regulator_p, regulator_target=np.array(centers[0], dtype=np.float64))
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]
+        keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / name, **keep)
+    print(name, "ok")
+
+
+if __name__ == "__main__":
+    assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
+    make_rbc_fixture()
+    make_lbm("lbm_periodic.npz", "ppp")
+    make_lbm("lbm_walls.npz", "pfp")
+    make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)
+    make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -1,0 +1,131 @@
+"""Pins the CPU oracle (oracle/biblbm_oracle.c) to the reference: every check is BIT-EXACT against dumps that the
+unmodified reference produced (tests/golden/*.npz, made by tests/golden/make_golden.py) and, when the compiled
+reference is present (oracle/_ref/ref_harness), against live runs of it on fresh seeded inputs."""
+import numpy as np
+import pytest
+
+import kit
+
+
+def test_shape_connectivity_matches_reference(orc, rbc):
+    shape, _, _, z = rbc
+    s = orc.shape_build(shape.verts, shape.tris)
+    assert np.array_equal(s.links, z["links"]) and np.array_equal(s.link_tri, z["link_tri"])
+    assert np.array_equal(s.link_len, z["link_len"])
+    assert np.array_equal(s.tri_area, z["tri_area"])
+    assert np.array_equal(s.pairs, z["pairs"]) and np.array_equal(s.pair_cs, z["pair_cs"])
+    assert s.area == z["scalars"][0] and s.volume == z["scalars"][1]
+    assert np.array_equal(s.center, z["scalars"][3:6])
+    # Euler characteristic of a closed surface: V - E + F = 2
+    assert s.nv - s.nl + s.nt == 2 and s.npairs == s.nl
+
+
+@pytest.mark.parametrize("name", ["lbm_periodic", "lbm_walls"])
+def test_collide_and_stream_bit_exact(orc, name):
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    c = g["pop_init"].copy()
+    for s in range(1, 11):
+        c = orc.collide_and_stream(c, g["per"], float(g["omega"]), float(g["omega_inner"]))
+        if f"pop_{s}" in g:
+            assert np.array_equal(c, g[f"pop_{s}"]), f"{name}: step {s} differs from the reference"
+
+
+def test_envelope_swap_quirk(orc):
+    """The reference collides periodic-envelope copies with (omega, omega_inner) swapped (see biblbm_oracle.c). Without the
+    quirk only the cells fed through a periodic face differ; interior cells are identical."""
+    g = np.load(kit.GOLDEN / "lbm_periodic.npz")
+    c = orc.collide_and_stream(g["pop_1"].copy(), g["per"], float(g["omega"]), float(g["omega_inner"]), envelope_swap=False)
+    d = np.abs(c - g["pop_2"])[..., :19].max(-1)
+    assert d[1:-1, 1:-1, 1:-1].max() == 0.0
+    assert d.max() > 1e-6
+
+
+def test_mass_and_momentum_conservation(orc):
+    """Size-independent property: without force a periodic BGK step conserves sum(f) and sum(c f) to round-off
+    (with the reference's envelope quirk switched off: mixing two collisions of one cell breaks exact conservation)."""
+    g = np.load(kit.GOLDEN / "lbm_periodic.npz")
+    c = g["pop_init"].copy()
+    c[..., 19:22] = 0.0
+    m0 = c[..., :19].sum()
+    j0 = np.einsum("xyzi,id->d", c[..., :19] + kit.T19, kit.C19.astype(float))
+    for _ in range(5):
+        c = orc.collide_and_stream(c, [1, 1, 1], 1.1, 0.4, envelope_swap=False)
+    m1 = c[..., :19].sum()
+    j1 = np.einsum("xyzi,id->d", c[..., :19] + kit.T19, kit.C19.astype(float))
+    assert abs(m1 - m0) < 1e-12 and np.abs(j1 - j0).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ib_rbc1", "ib_rbc2_pfp"])
+def test_full_step_bit_exact(orc, rbc, name):
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    assert np.array_equal(orc.particle_update(shape, vert[0, :, :3].copy()), state[0])
+    vel = None
+    for s in range(1, int(g["steps"]) + 1):
+        vel = orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], shape, params, vert, state,
+                            regulator_p=float(g["regulator_p"]), regulator_target=g["regulator_target"])
+        assert np.array_equal(vert, g[f"vert_{s}"]), f"{name}: vertex state differs at step {s}"
+        assert np.array_equal(state, g[f"part_{s}"]), f"{name}: particle scalars differ at step {s}"
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+    assert np.array_equal(vel[::2, ::2, ::2], g["vel_final_sample"])
+
+
+def test_roma_kernel_properties(orc):
+    """Roma 3-point delta (fsi/Dirac.h:73-83): partition of unity and zero first moment on any stencil."""
+    rng = np.random.default_rng(0)
+    for x in rng.uniform(-3, 3, 200):
+        i0 = int(np.ceil(x - 1.5))
+        w = np.array([orc.roma(i0 + k - x) for k in range(3)])
+        assert abs(w.sum() - 1) < 1e-14
+        assert abs((w * (np.arange(3) + i0 - x)).sum()) < 1e-14
+        assert abs((w * w).sum() - 0.5) < 1e-14
+
+
+def test_interpolate_spread_adjoint(orc):
+    """<spread(F), u> == <F, interpolate(u)> on a periodic box (same weights both ways)."""
+    rng = np.random.default_rng(1)
+    dims = (10, 9, 11)
+    vel = rng.normal(size=dims + (3,))
+    pos = rng.uniform(-2, 13, size=(50, 3))
+    F = rng.normal(size=(50, 3))
+    cells = np.zeros(dims + (23,))
+    orc.spread(cells, [1, 1, 1], pos, F)
+    U = orc.interpolate(vel, [1, 1, 1], pos)
+    assert abs((cells[..., 19:22] * vel).sum() - (F * U).sum()) < 1e-11
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not kit.have_reference(), reason="compiled reference (oracle/_ref/ref_harness) not present")
+def test_live_reference_multi_rbc(orc, rbc):
+    """4 RBCs drifting across the periodic faces of a 40x36x34 box for 60 steps: oracle == live reference, bit for bit."""
+    shape, params, rbc_pos, _ = rbc
+    dims, per = (40, 36, 34), [1, 1, 1]
+    pos = kit.place_particles(rbc_pos, [(39.0, 10, 9), (19, 27.5, 9.3), (20.1, 9.0, 26.2), (1.0, 27.0, 33.0)], seed=5)
+    steps, body = 60, [2e-5, 1e-5, -1e-5]
+    ref = kit.run_reference(dict(nx=dims[0], ny=dims[1], nz=dims[2], steps=steps, dump_every=20, periodicity="ppp", omega=1.0,
+                                 omega_inner=1 / 3, body_x=body[0], body_y=body[1], body_z=body[2], u0=0.04),
+                            verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    cells, vert, state = ref["pop_init"].copy(), ref["vert_init"].copy(), ref["part_init"].copy()
+    for s in range(1, steps + 1):
+        orc.full_step(cells, per, 1.0, 1 / 3, body, shape, params, vert, state)
+        if s % 20 == 0:
+            assert np.array_equal(vert, ref[f"vert_{s}"]) and np.array_equal(cells, ref[f"pop_{s}"])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not kit.have_reference(), reason="compiled reference (oracle/_ref/ref_harness) not present")
+def test_live_reference_lbm_random_phase(orc):
+    """Random 0/1 phase field + random forces, x,z periodic, y walls (free bounce-back), 17x13x15, 6 steps."""
+    rng = np.random.default_rng(7)
+    nx, ny, nz = 17, 13, 15
+    ext = np.zeros((nx, ny, nz, 4))
+    ext[..., :3] = rng.normal(scale=1e-4, size=(nx, ny, nz, 3))
+    ext[..., 3] = rng.integers(0, 2, size=(nx, ny, nz))
+    ref = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=6, dump_every=3, lbm_only=1, periodicity="pfp", omega=1.7,
+                                 omega_inner=0.6, u0=0.08), externals=ext)
+    c = ref["pop_init"].copy()
+    for s in range(1, 7):
+        c = orc.collide_and_stream(c, [1, 0, 1], 1.7, 0.6)
+        if s % 3 == 0:
+            assert np.array_equal(c, ref[f"pop_{s}"])
