@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference interface over the C-ABI library (ctypes; no torch types cross the boundary).
+
+`Lattice` plays the role of the reference's ``MultiBlockLattice3D<double, ForcedPhaseD3Q19Descriptor>`` +
+``ImmersedBoundaryDynamics3D`` pair for the hot path (reference src/multiBlock/multiBlockLattice3D.hh:306-348,
+src/fsi/ImmersedBoundaryDynamics.h:50-217): the method names follow the reference's
+(``collideAndStream``, ``computeVelocity``, ``setExternalVector``, ``add_particle`` ...). Every call goes to
+libbiblbm_b200.so; there is no CPU fallback: on a machine without a CUDA device construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libbiblbm_b200.so"
+
+# every symbol include/biblbm_b200.h declares (tests check that the built library exports all of them)
+SYMBOLS = [
+    "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
+    "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_set_external_vector", "bib_compute_velocity",
+    "bib_velocity_download", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
+    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_count", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
+    "bib_ib_particle_scalars_download", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
+    "bib_kernel_launch_count", "bib_device_memory_bytes",
+]
+
+OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR = 1, 2, 3
+CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
+PARTICLE_RBC = 0
+
+_lib = None
+
+
+class BibError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the in-tree library (building it first if the sources are newer). Raises if it cannot be produced."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from . import build as _build
+    _build.build()
+    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    lib.bib_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+    _lib = lib
+    return lib
+
+
+def _check(ok):
+    if not ok:
+        raise BibError(load_library().bib_last_error().decode())
+
+
+def _box(b):
+    return (C.c_int * 6)(*[int(v) for v in b])
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    ok = load_library().bib_device_count(C.byref(n))
+    return n.value if ok else 0
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().bib_comm_unique_id(buf))
+    return buf.raw
+
+
+class Lattice:
+    """One x-slab of a D3Q19 ForcedPhase lattice + its immersed particles, resident on one GPU."""
+
+    def __init__(self, nx, ny, nz, omega, omega_inner, periodic=(True, True, True), device=0):
+        self.lib = load_library()
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.h = C.c_void_p()
+        per = (C.c_int * 3)(*[int(bool(p)) for p in periodic])
+        _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, 4, C.c_double(omega), C.c_double(omega_inner), per, int(device), C.byref(self.h)))
+        self.full = (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1)
+        self.shape_nv = {}
+
+    def close(self):
+        if self.h:
+            self.lib.bib_domain_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options
+    def set_option(self, key, value):
+        _check(self.lib.bib_domain_set_option(self.h, int(key), C.c_double(value)))
+
+    # ---- lattice data (Palabos serialised cells [x][y][z][23])
+    def upload(self, cells, box=None):
+        box = box or self.full
+        cells = np.ascontiguousarray(cells, dtype=np.float64)
+        assert cells.size == (box[1] - box[0] + 1) * (box[3] - box[2] + 1) * (box[5] - box[4] + 1) * 23
+        _check(self.lib.bib_domain_upload(self.h, _box(box), _dptr(cells)))
+
+    def download(self, box=None, out=None):
+        box = box or self.full
+        shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 23)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        _check(self.lib.bib_domain_download(self.h, _box(box), _dptr(out)))
+        return out
+
+    def defineDynamics(self, box, kind):
+        _check(self.lib.bib_domain_set_celltype(self.h, _box(box), int(kind)))
+
+    def initializeAtEquilibrium(self, rho, u, box=None):
+        _check(self.lib.bib_domain_init_equilibrium(self.h, _box(box or self.full), C.c_double(rho), C.c_double(u[0]), C.c_double(u[1]), C.c_double(u[2])))
+
+    def setExternalVector(self, F, box=None):
+        _check(self.lib.bib_set_external_vector(self.h, _box(box or self.full), C.c_double(F[0]), C.c_double(F[1]), C.c_double(F[2])))
+
+    def computeVelocity(self, box=None, download=True):
+        box = box or self.full
+        _check(self.lib.bib_compute_velocity(self.h, _box(box)))
+        if not download:
+            return None
+        out = np.empty((box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 3), dtype=np.float64)
+        _check(self.lib.bib_velocity_download(self.h, _box(box), _dptr(out)))
+        return out
+
+    def collideAndStream(self, n=1):
+        for _ in range(n):
+            _check(self.lib.bib_collide_and_stream(self.h))
+
+    # ---- immersed boundary
+    def register_shape(self, verts, tris) -> int:
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        tris = np.ascontiguousarray(tris, dtype=np.int32)
+        sid = C.c_int(-1)
+        _check(self.lib.bib_ib_shape_register(self.h, verts.shape[0], tris.shape[0], _dptr(verts), tris.ctypes.data_as(C.POINTER(C.c_int)), C.byref(sid)))
+        self.shape_nv[sid.value] = (verts.shape[0], tris.shape[0])
+        return sid.value
+
+    def shape_connectivity(self, sid):
+        nl, npair = C.c_int(0), C.c_int(0)
+        area, vol = C.c_double(0), C.c_double(0)
+        _check(self.lib.bib_ib_shape_info(self.h, sid, C.byref(nl), C.byref(npair), C.byref(area), C.byref(vol)))
+        nt = self.shape_nv[sid][1]
+        links = np.zeros((nl.value, 2), dtype=np.int32)
+        link_len = np.zeros(nl.value)
+        pairs = np.zeros((npair.value, 4), dtype=np.int32)
+        pair_cs = np.zeros((npair.value, 2))
+        tri_area = np.zeros(nt)
+        ip = C.POINTER(C.c_int)
+        _check(self.lib.bib_ib_shape_connectivity(self.h, sid, links.ctypes.data_as(ip), _dptr(link_len), pairs.ctypes.data_as(ip), _dptr(pair_cs), _dptr(tri_area)))
+        return dict(links=links, link_len=link_len, pairs=pairs, pair_cs=pair_cs, tri_area=tri_area, area=area.value, volume=vol.value)
+
+    def add_particles(self, sid, params, positions, kind=PARTICLE_RBC):
+        nv = self.shape_nv[sid][0]
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, nv, 3)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        assert params.size == 8
+        _check(self.lib.bib_ib_particles_add(self.h, int(kind), int(sid), _dptr(params), positions.shape[0], _dptr(positions)))
+
+    def set_regulator(self, p, target):
+        _check(self.lib.bib_ib_set_regulator(self.h, C.c_double(p), C.c_double(target[0]), C.c_double(target[1]), C.c_double(target[2])))
+
+    def count(self):
+        n_p, n_v = C.c_int(0), C.c_longlong(0)
+        _check(self.lib.bib_ib_count(self.h, C.byref(n_p), C.byref(n_v)))
+        return n_p.value, n_v.value
+
+    def interpolate_velocity(self):
+        _check(self.lib.bib_ib_interpolate_velocity(self.h))
+
+    def compute_and_spread_forces(self):
+        _check(self.lib.bib_ib_compute_and_spread_forces(self.h))
+
+    def move_vertices_and_revoxelize(self):
+        _check(self.lib.bib_ib_move_vertices_and_revoxelize(self.h))
+
+    def ib_step(self):
+        _check(self.lib.bib_ib_step(self.h))
+
+    def vertices(self, first=0, count=None):
+        if count is None:
+            count = self.count()[1] - first
+        out = np.empty((count, 9), dtype=np.float64)
+        _check(self.lib.bib_ib_vertices_download(self.h, C.c_longlong(first), C.c_longlong(count), _dptr(out)))
+        return out
+
+    def particle_scalars(self, first=0, count=None):
+        if count is None:
+            count = self.count()[0] - first
+        out = np.empty((count, 11), dtype=np.float64)
+        _check(self.lib.bib_ib_particle_scalars_download(self.h, int(first), int(count), _dptr(out)))
+        return out
+
+    # ---- whole driver steps
+    def step(self, body=(0.0, 0.0, 0.0), n=1):
+        _check(self.lib.bib_step(self.h, C.c_double(body[0]), C.c_double(body[1]), C.c_double(body[2]), int(n)))
+
+    # ---- multi-GPU ring
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        _check(self.lib.bib_comm_init(self.h, int(rank), int(n_ranks), C.c_char_p(unique_id)))
+
+    # ---- stream / timing
+    def sync(self):
+        _check(self.lib.bib_sync(self.h))
+
+    def time_begin(self):
+        _check(self.lib.bib_time_begin(self.h))
+
+    def time_end(self) -> float:
+        ms = C.c_float(0)
+        _check(self.lib.bib_time_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def launches(self) -> int:
+        n = C.c_longlong(0)
+        _check(self.lib.bib_kernel_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def device_bytes(self) -> int:
+        n = C.c_longlong(0)
+        _check(self.lib.bib_device_memory_bytes(self.h, C.byref(n)))
+        return n.value

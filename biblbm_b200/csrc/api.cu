@@ -1,0 +1,292 @@
+// api.cu -- the C-ABI of include/biblbm_b200.h: handle life cycle, argument checking, step sequencing.
+#include "../../include/biblbm_b200.h"
+#include "domain.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+static thread_local std::string g_last_error;
+
+void bib_set_error(const std::string& msg) { g_last_error = msg; }
+bool bib_cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+int ib_interpolate_dense(bib_domain* d);
+
+extern "C" {
+
+const char* bib_last_error(void) { return g_last_error.c_str(); }
+int bib_version(void) { return 100; }
+
+int bib_device_count(int* count) {
+    if (!count) { bib_set_error("device_count: null argument"); return 0; }
+    BIB_CHECK(cudaGetDeviceCount(count));
+    return 1;
+}
+
+int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3], int device,
+                      bib_domain** out) {
+    if (!out || !periodic) { bib_set_error("domain_create: null argument"); return 0; }
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || nz < 1) { bib_set_error("domain_create: empty lattice"); return 0; }
+    if (n_ext != 4) { bib_set_error("domain_create: only ForcedPhaseD3Q19Descriptor (4 external scalars) is implemented"); return 0; }
+    if (!(omega_outer > 0.0 && omega_outer < 2.0 && omega_inner > 0.0 && omega_inner < 2.0)) { bib_set_error("domain_create: omega must lie in (0,2)"); return 0; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        bib_set_error("domain_create: no CUDA device available (this library has no CPU fallback)");
+        return 0;
+    }
+    if (device < 0 || device >= ndev) { bib_set_error("domain_create: device index out of range"); return 0; }
+    BIB_CHECK(cudaSetDevice(device));
+    bib_domain* d = new (std::nothrow) bib_domain();
+    if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
+    d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
+    for (int k = 0; k < 3; ++k) d->per[k] = periodic[k] ? 1 : 0;
+    d->omega0 = omega_outer; d->omega1 = omega_inner;
+    d->plane = (size_t)ny * nz;
+    d->vol = (size_t)(nx + 2) * d->plane;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = d->vol * (2 * BIB_Q + 3) * sizeof(double) + d->vol + (size_t)(nx + 2) * ny + (64 << 20);
+    if (need > free_b) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "domain_create: lattice needs %.1f GB of HBM, %.1f GB free", need / 1e9, free_b / 1e9);
+        bib_set_error(buf); delete d; return 0;
+    }
+    bool ok = bib_cuda_ok(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              bib_cuda_ok(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              bib_cuda_ok(cudaEventCreate(&d->ev0), "cudaEventCreate") && bib_cuda_ok(cudaEventCreate(&d->ev1), "cudaEventCreate") &&
+              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming), "cudaEventCreate") &&
+              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_compute, cudaEventDisableTiming), "cudaEventCreate");
+    for (int b = 0; ok && b < 2; ++b) {
+        ok = bib_cuda_ok(cudaMalloc(&d->f[b], d->vol * BIB_Q * sizeof(double)), "cudaMalloc(populations)") &&
+             bib_cuda_ok(cudaMemsetAsync(d->f[b], 0, d->vol * BIB_Q * sizeof(double), d->stream), "cudaMemset");
+    }
+    ok = ok && bib_cuda_ok(cudaMalloc(&d->force, d->vol * 3 * sizeof(double)), "cudaMalloc(force)") &&
+         bib_cuda_ok(cudaMemsetAsync(d->force, 0, d->vol * 3 * sizeof(double), d->stream), "cudaMemset") &&
+         bib_cuda_ok(cudaMalloc(&d->phase, d->vol), "cudaMalloc(phase)") && bib_cuda_ok(cudaMemsetAsync(d->phase, 0, d->vol, d->stream), "cudaMemset") &&
+         bib_cuda_ok(cudaMalloc(&d->col_flags, (size_t)(nx + 2) * ny + 4), "cudaMalloc(col_flags)") &&
+         bib_cuda_ok(cudaMemsetAsync(d->col_flags, 0, (size_t)(nx + 2) * ny + 4, d->stream), "cudaMemset") &&
+         bib_cuda_ok(cudaStreamSynchronize(d->stream), "cudaStreamSynchronize");
+    if (!ok) { bib_domain_destroy(d); return 0; }
+    d->bytes = (long long)(d->vol * (2 * BIB_Q + 3) * sizeof(double) + d->vol);
+    *out = d;
+    return 1;
+}
+
+int bib_domain_destroy(bib_domain* d) {
+    if (!d) return 1;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    comm_destroy(d);
+    for (int b = 0; b < 2; ++b) if (d->f[b]) cudaFree(d->f[b]);
+    if (d->force) cudaFree(d->force);
+    if (d->phase) cudaFree(d->phase);
+    if (d->kind) cudaFree(d->kind);
+    if (d->vel) cudaFree(d->vel);
+    if (d->col_flags) cudaFree(d->col_flags);
+    if (d->scratch) cudaFree(d->scratch);
+    if (d->vpos) cudaFree(d->vpos);
+    if (d->vvel) cudaFree(d->vvel);
+    if (d->vfrc) cudaFree(d->vfrc);
+    if (d->pstate) cudaFree(d->pstate);
+    for (ShapeDev& s : d->shapes) {
+        void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair};
+        for (void* p : ptrs) if (p) cudaFree(p);
+    }
+    for (ParticleGroup& g : d->groups) { if (g.link_ks) cudaFree(g.link_ks); if (g.link_kp) cudaFree(g.link_kp); }
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->ev_halo) cudaEventDestroy(d->ev_halo);
+    if (d->ev_compute) cudaEventDestroy(d->ev_compute);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+    delete d;
+    return 1;
+}
+
+#define BIB_ENTER(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
+
+int bib_domain_set_option(bib_domain* d, int key, double value) {
+    BIB_ENTER(d);
+    switch (key) {
+        case BIB_OPT_ENVELOPE_SWAP: d->envelope_swap = value != 0.0; return 1;
+        case BIB_OPT_DETERMINISTIC_SPREAD: d->deterministic_spread = value != 0.0; return 1;
+        case BIB_OPT_REGULATOR: d->regulator_p = value; return 1;
+    }
+    bib_set_error("set_option: unknown key");
+    return 0;
+}
+
+int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
+    BIB_ENTER(d);
+    if (!box || !cells) { bib_set_error("upload: null argument"); return 0; }
+    if (!lbm_launch_upload(d, box, cells)) return 0;
+    return 1;
+}
+int bib_domain_download(bib_domain* d, const int box[6], double* cells) {
+    BIB_ENTER(d);
+    if (!box || !cells) { bib_set_error("download: null argument"); return 0; }
+    return lbm_launch_download(d, box, cells);
+}
+int bib_domain_set_celltype(bib_domain* d, const int box[6], int kind) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("set_celltype: null argument"); return 0; }
+    return lbm_set_celltype(d, box, kind);
+}
+int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("init_equilibrium: null argument"); return 0; }
+    if (!(rho > 0.0)) { bib_set_error("init_equilibrium: density must be positive"); return 0; }
+    return lbm_init_equilibrium(d, box, rho, ux, uy, uz);
+}
+int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("set_external_vector: null argument"); return 0; }
+    return lbm_launch_set_external(d, box, fx, fy, fz);
+}
+int bib_compute_velocity(bib_domain* d, const int box[6]) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("compute_velocity: null argument"); return 0; }
+    return lbm_launch_velocity(d, box);
+}
+int bib_velocity_download(bib_domain* d, const int box[6], double* velocity) {
+    BIB_ENTER(d);
+    if (!box || !velocity) { bib_set_error("velocity_download: null argument"); return 0; }
+    return lbm_velocity_download(d, box, velocity);
+}
+int bib_collide_and_stream(bib_domain* d) {
+    BIB_ENTER(d);
+    return lbm_launch_collide_stream(d);
+}
+
+int bib_ib_shape_register(bib_domain* d, int nv, int nt, const double* vertices, const int* triangles, int* shape_id) {
+    BIB_ENTER(d);
+    if (!shape_id) { bib_set_error("shape_register: null argument"); return 0; }
+    return ib_shape_register(d, nv, nt, vertices, triangles, shape_id);
+}
+int bib_ib_shape_info(bib_domain* d, int shape_id, int* n_links, int* n_pairs, double* area, double* volume) {
+    BIB_ENTER(d);
+    if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("shape_info: unknown shape"); return 0; }
+    const ShapeDev& s = d->shapes[shape_id];
+    if (n_links) *n_links = s.nl;
+    if (n_pairs) *n_pairs = s.np;
+    if (area) *area = s.area;
+    if (volume) *volume = s.volume;
+    return 1;
+}
+int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* link_len, int* pairs, double* pair_cos_sin, double* tri_area) {
+    BIB_ENTER(d);
+    if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("shape_connectivity: unknown shape"); return 0; }
+    const ShapeDev& s = d->shapes[shape_id];
+    if (links) std::memcpy(links, s.h_links.data(), s.h_links.size() * sizeof(int));
+    if (link_len) std::memcpy(link_len, s.h_link_len.data(), s.h_link_len.size() * sizeof(double));
+    if (pairs) std::memcpy(pairs, s.h_pairs.data(), s.h_pairs.size() * sizeof(int));
+    if (pair_cos_sin) std::memcpy(pair_cos_sin, s.h_pair_cs.data(), s.h_pair_cs.size() * sizeof(double));
+    if (tri_area) std::memcpy(tri_area, s.h_tri_area.data(), s.h_tri_area.size() * sizeof(double));
+    return 1;
+}
+int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
+    BIB_ENTER(d);
+    if (!params || (n > 0 && !positions)) { bib_set_error("particles_add: null argument"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("particles_add: immersed boundaries on multi-slab domains are not implemented yet"); return 0; }
+    return ib_particles_add(d, type, shape_id, params, n, positions);
+}
+int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz) {
+    BIB_ENTER(d);
+    d->regulator_p = p; d->regulator_target[0] = tx; d->regulator_target[1] = ty; d->regulator_target[2] = tz;
+    return 1;
+}
+int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
+    BIB_ENTER(d);
+    if (n_particles) *n_particles = d->n_particles;
+    if (n_vertices) *n_vertices = d->n_vertices;
+    return 1;
+}
+int bib_ib_interpolate_velocity(bib_domain* d) {
+    BIB_ENTER(d);
+    // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
+    return d->vel ? ib_interpolate_dense(d) : ib_interpolate(d);
+}
+int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); return ib_forces_and_spread(d); }
+int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib_move_and_voxelize(d); }
+int bib_ib_step(bib_domain* d) {
+    BIB_ENTER(d);
+    return (d->vel ? ib_interpolate_dense(d) : ib_interpolate(d)) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
+}
+int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
+    BIB_ENTER(d);
+    if (count > 0 && !vertices9) { bib_set_error("vertices_download: null argument"); return 0; }
+    return ib_vertices_download(d, first_vertex, count, vertices9);
+}
+int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9) {
+    BIB_ENTER(d);
+    if (count > 0 && !vertices9) { bib_set_error("vertices_upload: null argument"); return 0; }
+    return ib_vertices_upload(d, first_vertex, count, vertices9);
+}
+int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11) {
+    BIB_ENTER(d);
+    if (count > 0 && !scalars11) { bib_set_error("particle_scalars_download: null argument"); return 0; }
+    return ib_scalars_download(d, first_particle, count, scalars11);
+}
+
+// One driver step: the velocity the IB interpolates is u = j(f^t)/rho + F^{t-1}/2 evaluated on demand from the current
+// populations and the force field still holding last step's total force, so the dense
+// computeVelocity pass of the reference is not needed; then F := body, IB, collide-and-stream.
+int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
+    BIB_ENTER(d);
+    const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
+    for (int s = 0; s < n_steps; ++s) {
+        if (!ib_interpolate(d)) return 0;
+        if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
+        if (!ib_forces_and_spread(d)) return 0;
+        if (!ib_move_and_voxelize(d)) return 0;
+        if (!lbm_launch_collide_stream(d)) return 0;
+    }
+    return 1;
+}
+
+int bib_comm_unique_id(void* unique_id_128) {
+    if (!unique_id_128) { bib_set_error("comm_unique_id: null argument"); return 0; }
+    return comm_unique_id(unique_id_128);
+}
+int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128) {
+    BIB_ENTER(d);
+    if (!unique_id_128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) { bib_set_error("comm_init: bad arguments"); return 0; }
+    if (d->n_particles > 0) { bib_set_error("comm_init: immersed boundaries on multi-slab domains are not implemented yet"); return 0; }
+    return comm_init(d, rank, n_ranks, unique_id_128);
+}
+
+int bib_sync(bib_domain* d) {
+    BIB_ENTER(d);
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->comm_stream));
+    return 1;
+}
+int bib_time_begin(bib_domain* d) { BIB_ENTER(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
+int bib_time_end(bib_domain* d, float* milliseconds) {
+    BIB_ENTER(d);
+    if (!milliseconds) { bib_set_error("time_end: null argument"); return 0; }
+    BIB_CHECK(cudaEventRecord(d->ev1, d->stream));
+    BIB_CHECK(cudaEventSynchronize(d->ev1));
+    BIB_CHECK(cudaEventElapsedTime(milliseconds, d->ev0, d->ev1));
+    return 1;
+}
+int bib_kernel_launch_count(bib_domain* d, long long* launches) {
+    BIB_ENTER(d);
+    if (!launches) { bib_set_error("kernel_launch_count: null argument"); return 0; }
+    *launches = d->launches;
+    return 1;
+}
+int bib_device_memory_bytes(bib_domain* d, long long* bytes) {
+    BIB_ENTER(d);
+    if (!bytes) { bib_set_error("device_memory_bytes: null argument"); return 0; }
+    *bytes = d->bytes;
+    return 1;
+}
+
+}  // extern "C"

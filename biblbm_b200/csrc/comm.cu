@@ -1,0 +1,106 @@
+// comm.cu -- x-slab ring halo exchange over NCCL (NVLink 5 / NVSwitch).
+//
+// Replaces the reference's envelope exchange (src/parallelism/parallelBlockCommunicator3D.cpp:144-233, whole cells of
+// 184 B through MPI point-to-point) by the minimum a D3Q19 slab face needs: the 5 populations that cross it, 40 B per
+// face cell and direction. The push kernel deposits them in the slab's ghost planes; because every population is its own
+// [x][y][z] array, a ghost plane and its destination plane in the neighbour are contiguous ny*nz runs, so ncclSend /
+// ncclRecv work in place on the population buffers: no pack or unpack kernels.
+//
+// NCCL is resolved at run time (dlopen) so that the library has no link-time dependency on a particular libnccl and
+// shares the copy an embedding process (e.g. PyTorch) has already loaded.
+#include "domain.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.handle) break; }
+    if (!g_nccl.handle) { bib_set_error(std::string("cannot load libnccl: ") + dlerror()); return false; }
+#define LOAD(sym) g_nccl.sym = (decltype(g_nccl.sym))dlsym(g_nccl.handle, "nccl" #sym); if (!g_nccl.sym) { bib_set_error("libnccl lacks nccl" #sym); return false; }
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(GroupStart) LOAD(GroupEnd) LOAD(Send) LOAD(Recv) LOAD(GetErrorString)
+#undef LOAD
+    return true;
+}
+bool nccl_ok(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return true;
+    bib_set_error(std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+    return false;
+}
+#define NCCL_CHECK(call) do { if (!nccl_ok((call), #call)) return 0; } while (0)
+
+const int kPlusX[5] = {10, 13, 14, 15, 16};    // c_x = +1 (src/latticeBoltzmann/nearestNeighborLattices3D.hh:167-177)
+const int kMinusX[5] = {1, 4, 5, 6, 7};        // c_x = -1
+
+}  // namespace
+
+int comm_unique_id(void* out128) {
+    if (!load_nccl()) return 0;
+    ncclUniqueId id;
+    NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return 1;
+}
+
+int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128) {
+    d->rank = rank; d->n_ranks = n_ranks;
+    d->gnx = d->nx * n_ranks;           // equal slabs
+    d->x_offset = rank * d->nx;
+    if (n_ranks == 1) return 1;
+    if (!load_nccl()) return 0;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    NCCL_CHECK(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+    d->nccl_comm = comm;
+    return 1;
+}
+
+void comm_destroy(bib_domain* d) {
+    if (d->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)d->nccl_comm);
+    d->nccl_comm = nullptr;
+}
+
+// Runs on the compute stream right after the push kernel: ghost plane nx+1 (populations with c_x=+1) goes to the right
+// neighbour's plane 1, ghost plane 0 (c_x=-1) to the left neighbour's plane nx.
+int comm_halo_exchange(bib_domain* d) {
+    if (d->n_ranks == 1) return 1;
+    ncclComm_t comm = (ncclComm_t)d->nccl_comm;
+    if (!comm) { bib_set_error("halo exchange: bib_comm_init has not been called"); return 0; }
+    double* f = d->f[d->cur];           // the buffer just written
+    const size_t n = d->plane;
+    const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+    const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    const bool has_left = d->per[0] || d->rank > 0;
+    NCCL_CHECK(g_nccl.GroupStart());
+    for (int k = 0; k < 5; ++k) {
+        double* pop = f + (size_t)kPlusX[k] * d->vol;
+        if (has_right) NCCL_CHECK(g_nccl.Send(pop + (size_t)(d->nx + 1) * n, n, ncclDouble, right, comm, d->stream));
+        if (has_left) NCCL_CHECK(g_nccl.Recv(pop + (size_t)1 * n, n, ncclDouble, left, comm, d->stream));
+    }
+    for (int k = 0; k < 5; ++k) {
+        double* pop = f + (size_t)kMinusX[k] * d->vol;
+        if (has_left) NCCL_CHECK(g_nccl.Send(pop + (size_t)0 * n, n, ncclDouble, left, comm, d->stream));
+        if (has_right) NCCL_CHECK(g_nccl.Recv(pop + (size_t)d->nx * n, n, ncclDouble, right, comm, d->stream));
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    d->launches++;
+    return 1;
+}

@@ -1,0 +1,137 @@
+// domain.cuh -- device-resident state of one x-slab and shared device helpers.
+//
+// HBM layout (all fp64 unless stated; z fastest, then y, then x; x carries one ghost plane on each side so that a slab's
+// x-faces are contiguous ny*nz planes that can be sent/received without packing):
+//   f[2][19][nx+2][ny][nz]   population buffers A/B holding PRE-collision fBar (= what the reference's cells hold)
+//   force[3][nx+2][ny][nz]   total external force (body + spread IB force), the reference's external scalars 0..2
+//   phase[nx+2][ny][nz] u8   bit0 = inside/outside phase (reference external scalar 3, exactly 0.0/1.0), bit1 = voxelizer toggle mark
+//   kind[nx+2][ny][nz]  u8   optional cell kinds (allocated on first bib_domain_set_celltype)
+//   vel[3][nx+2][ny][nz]     optional dense velocity field (allocated on first bib_compute_velocity)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#define BIB_Q 19
+
+struct ShapeDev {
+    int nv = 0, nt = 0, nl = 0, np = 0;
+    double area = 0, volume = 0;
+    // connectivity (device)
+    int* tris = nullptr;          // [nt][3]
+    double* tri_area = nullptr;   // [nt]
+    int* links = nullptr;         // [nl][2]
+    double* link_len = nullptr;   // [nl]
+    int* pairs = nullptr;         // [np][4]
+    double* pair_cs = nullptr;    // [np][2]
+    // per-vertex incidence lists in the reference's accumulation order (CSR)
+    int* v_link_off = nullptr; int* v_link = nullptr;      // entry = link*2 + end
+    int* v_tri_off = nullptr;  int* v_tri = nullptr;       // entry = tri*3 + corner
+    int* v_pair_off = nullptr; int* v_pair = nullptr;      // entry = pair*4 + corner
+    // host copies
+    std::vector<int> h_tris, h_links, h_pairs;
+    std::vector<double> h_tri_area, h_link_len, h_pair_cs, h_verts;
+};
+
+struct ParticleGroup {            // particles of one (type, shape, params) added by one bib_ib_particles_add call
+    int type = 0, shape = 0;
+    int first_particle = 0, count = 0;
+    long long first_vertex = 0;
+    double params[8] = {0};
+    double* link_ks = nullptr;    // [nl] per-link WLC spring constant (host-computed with libm pow, like the reference)
+    double* link_kp = nullptr;    // [nl]
+};
+
+struct bib_domain {
+    int device = 0;
+    int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
+    int per[3] = {0, 0, 0};               // global periodicity
+    double omega0 = 1, omega1 = 1;        // outer, inner
+    size_t plane = 0;                     // ny*nz
+    size_t vol = 0;                       // (nx+2)*ny*nz  (storage incl. ghost planes)
+    int cur = 0;                          // which population buffer holds the current state
+    double* f[2] = {nullptr, nullptr};
+    double* force = nullptr;
+    uint8_t* phase = nullptr;
+    uint8_t* kind = nullptr;
+    double* vel = nullptr;
+    uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
+    long long launches = 0;
+    long long bytes = 0;
+    // options
+    int envelope_swap = 1;
+    int deterministic_spread = 0;
+    double regulator_p = 0, regulator_target[3] = {0, 0, 0};
+    // multi-GPU ring
+    int rank = 0, n_ranks = 1;
+    void* nccl_comm = nullptr;
+    int x_offset = 0;                     // global x of local plane 0
+    int gnx = 0;                          // global nx
+    // IB
+    std::vector<ShapeDev> shapes;
+    std::vector<ParticleGroup> groups;
+    int n_particles = 0;
+    long long n_vertices = 0;
+    long long cap_vertices = 0;
+    int cap_particles = 0;
+    double* vpos = nullptr;   // [3][cap_vertices]  SoA
+    double* vvel = nullptr;
+    double* vfrc = nullptr;
+    double* pstate = nullptr; // [cap_particles][11] area, volume, com[3], bbox[6]
+    int* p_first_vertex = nullptr;   // [cap_particles]
+    void* scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+void bib_set_error(const std::string& msg);
+bool bib_cuda_ok(cudaError_t e, const char* what);
+
+#define BIB_CHECK(call) do { if (!bib_cuda_ok((call), #call)) return 0; } while (0)
+
+// ---- kernels / host launchers implemented in the .cu files
+int lbm_launch_collide_stream(bib_domain* d);
+int lbm_launch_upload(bib_domain* d, const int box[6], const double* cells);
+int lbm_launch_download(bib_domain* d, const int box[6], double* cells);
+int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double fy, double fz);
+int lbm_launch_velocity(bib_domain* d, const int box[6]);
+int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity);
+int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
+int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz);
+
+int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const int* tris, int* shape_id);
+int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
+int ib_interpolate(bib_domain* d);
+int ib_forces_and_spread(bib_domain* d);
+int ib_move_and_voxelize(bib_domain* d);
+int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9);
+int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9);
+int ib_scalars_download(bib_domain* d, int first, int count, double* s11);
+
+int comm_unique_id(void* out128);
+int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);
+int comm_halo_exchange(bib_domain* d);
+void comm_destroy(bib_domain* d);
+
+// ---- device helpers shared by the LBM and IB kernels
+#ifdef __CUDACC__
+// Every arithmetic expression below mirrors the reference's evaluation order; the library is compiled with -fmad=false
+// so that no multiply-add is contracted and results are bit-identical to the reference's x86-64 (SSE2) build.
+
+// momentTemplates3D.h:351-373,411-423 of the reference (partial_rho + get_rhoBar_j)
+__device__ __forceinline__ void d_rhoBar_j(const double* f, double& rhoBar, double& jx, double& jy, double& jz) {
+    double surfX_M1 = f[1] + f[4] + f[5] + f[6] + f[7];
+    double surfX_P1 = f[10] + f[13] + f[14] + f[15] + f[16];
+    double surfY_M1 = f[2] + f[4] + f[8] + f[9] + f[14];
+    double surfY_P1 = f[5] + f[11] + f[13] + f[17] + f[18];
+    double surfZ_M1 = f[3] + f[6] + f[8] + f[16] + f[18];
+    double surfZ_P1 = f[7] + f[9] + f[12] + f[15] + f[17];
+    double surfX_0 = f[0] + f[2] + f[3] + f[8] + f[9] + f[11] + f[12] + f[17] + f[18];
+    rhoBar = surfX_M1 + surfX_0 + surfX_P1;
+    jx = surfX_P1 - surfX_M1;
+    jy = surfY_P1 - surfY_M1;
+    jz = surfZ_P1 - surfZ_M1;
+}
+#endif

@@ -1,0 +1,789 @@
+// ib_kernels.cu -- immersed-boundary coupling and membrane forces on SoA vertex arrays.
+//
+// Replaces (reference file:line):
+//   RomaDirac<T,3>::eval, get_dirac_compact_support_box      src/fsi/Dirac.h:73-83,131-139
+//   interpolate_bulk / interpolate (BulkInterpolator, GeneralInterpolator)
+//                                                            src/fsi/ImmersedBoundaryDynamics_interpolation.hh:43-153,236-276
+//   spread_forces_bulk / spread_forces                       src/fsi/ImmersedBoundaryDynamics_forces.hh:52-163,243-284
+//   RBCParticle::compute_forces, in_plane_ks_kp              src/fsi/RBCParticle.hh:27-44,140-247
+//   tri::triangle_area_and_gradient, grad_signed_volume, grad_angle_between_pair
+//                                                            src/fsi/TriangleUtils.h:57-164
+//   ParticleShape (connectivity)                             src/fsi/ParticleShape.hh:22-184
+//   DeformableParticle3D::move_vertices / update, map_center_of_mass_to_periodic_grid
+//                                                            src/fsi/DeformableParticle3D.hh:26-82, src/fsi/ParticleBase.hh:52-69,113-138
+//   RayTracer::find_intersections_z, ZBuffer, apply_voxelization
+//                                                            src/fsi/RayTracer.hh:19-108, src/fsi/ZBuffer.h:39-79,
+//                                                            src/fsi/ImmersedBoundaryDynamics_voxelization.hh:17-29,121-165
+//   ParticlePositionRegulator                                progs/common/particle_position_regulator.h:5-18
+//
+// All kernels are gathers over vertex/triangle arrays except the spread, which scatters with fp64 atomics (or, in
+// deterministic mode, in the reference's exact vertex order). Arithmetic mirrors the reference operation by operation
+// (library built with -fmad=false), so everything except the atomic spread is bit-identical to the reference.
+#include "domain.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ geometry helpers
+struct Geo {
+    int nx, ny, nz;          // GLOBAL lattice size (the reference's single block)
+    int per[3];
+    long long plane, vol;
+    int x_offset;            // global x of storage plane 1
+};
+
+__device__ __forceinline__ double d_roma(double x) {
+    const double dx = fabs(x);
+    return (1.0 / 6.0) * (dx > 0.5 ? (5.0 - 3 * dx - sqrt(-3 * (1 - dx) * (1 - dx) + 1)) : 2.0 * (1 + sqrt(1 - 3 * dx * dx)));
+}
+__device__ __forceinline__ double d_min_mod(double x, double N, double N_inv) { return x - floor(x * N_inv + 0.5) * N; }
+
+// Rect::contains(p, arithmetic), src/fsi/geometry.h:95-100, with Arithmetic3D::dist_* (src/fsi/Periodicity.h:24-32,99-102)
+__device__ __forceinline__ bool d_rect_contains(const Geo& g, double lo_enl, double hi_enl, const double* p) {
+    const int n[3] = {g.nx, g.ny, g.nz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double lo = 0.0, hi = (double)(n[d] - 1);
+        lo -= lo_enl; hi += hi_enl;
+        const double mid = 0.5 * (lo + hi);
+        const double L = (double)n[d];
+        const double dist = g.per[d] ? d_min_mod(mid - p[d], L, 1. / L) : mid - p[d];
+        if (!(fabs(dist) < 0.5 * (hi - lo))) return false;
+    }
+    return true;
+}
+// 0 = outside domain_with_fsi_envelope, 1 = bulk list, 2 = envelope list (src/fsi/ImmersedBoundaryDynamics.hh:46-65,346-358)
+__device__ __forceinline__ int d_classify(const Geo& g, const double* p) {
+    const double eps = 2.220446049250313e-16;
+    if (!d_rect_contains(g, 1.5, 1.5, p)) return 0;
+    const double d_bulk = 0.5 - 1.5 - eps;
+    if (d_rect_contains(g, d_bulk, d_bulk, p)) return 1;
+    return 2;
+}
+// local stencil index (block frame, envelope width 1) -> global lattice index
+__device__ __forceinline__ int d_remap(const Geo& g, int d, int i_local) {
+    const int n = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+    const int gi = i_local - 1;
+    if (!g.per[d]) return gi;
+    return (gi + 100 * n) % n;
+}
+__device__ __forceinline__ long long d_cell(const Geo& g, int gx, int gy, int gz) {
+    return (long long)(gx - g.x_offset + 1) * g.plane + (long long)gy * g.nz + gz;
+}
+
+// u = j/rho + F/2 from the current populations (ExternalForceDynamics::computeVelocity, externalForceDynamics.hh:59-74)
+__device__ __forceinline__ void d_cell_velocity(const double* __restrict__ f, const double* __restrict__ force, long long vol,
+                                                long long idx, double* u) {
+    double c[BIB_Q];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) c[i] = __ldg(f + (long long)i * vol + idx);
+    double rhoBar, jx, jy, jz;
+    d_rhoBar_j(c, rhoBar, jx, jy, jz);
+    const double invRho = 1.0 / (rhoBar + 1.0);
+    u[0] = jx * invRho + __ldg(force + idx) / 2.0;
+    u[1] = jy * invRho + __ldg(force + vol + idx) / 2.0;
+    u[2] = jz * invRho + __ldg(force + 2 * vol + idx) / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------------ I2: interpolation
+template <bool DENSE>
+__global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __restrict__ f, const double* __restrict__ force,
+                                                     const double* __restrict__ vel, long long nvert, long long cap,
+                                                     const double* __restrict__ vpos, double* __restrict__ vvel) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert) return;
+    const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    double o[3] = {0.0, 0.0, 0.0};
+    const int cls = d_classify(g, pp);
+    if (cls != 0) {
+        const double p[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};   // pos - getLocation()
+        const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
+        if (cls == 1) {
+            const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
+            const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
+            const double dz[3] = {d_roma((double)z0 - p[2]), d_roma((double)z0 + 1. - p[2]), d_roma((double)(z0 + 2) - p[2])};
+            const int i0 = d_remap(g, 0, x0), j0 = d_remap(g, 1, y0), k0 = d_remap(g, 2, z0);
+            double ax[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double ay[3][3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double u0[3], u1[3], u2[3];
+                    const long long c0 = d_cell(g, i0 + i, j0 + j, k0);
+                    if (DENSE) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { u0[c] = vel[c * g.vol + c0]; u1[c] = vel[c * g.vol + c0 + 1]; u2[c] = vel[c * g.vol + c0 + 2]; }
+                    } else {
+                        d_cell_velocity(f, force, g.vol, c0, u0);
+                        d_cell_velocity(f, force, g.vol, c0 + 1, u1);
+                        d_cell_velocity(f, force, g.vol, c0 + 2, u2);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) ay[j][c] = dy[j] * ((dz[0] * u0[c] + dz[1] * u1[c]) + dz[2] * u2[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ax[i][c] = dx[i] * ((ay[0][c] + ay[1][c]) + ay[2][c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = (ax[0][c] + ax[1][c]) + ax[2][c];
+        } else {
+            for (int i = x0; i <= x0 + 2; ++i) {
+                const int i2 = d_remap(g, 0, i);
+                if (i2 < 0 || i2 > g.nx - 1) continue;
+                const double dirac_x = d_roma((double)i - p[0]);
+                for (int j = y0; j <= y0 + 2; ++j) {
+                    const int j2 = d_remap(g, 1, j);
+                    if (j2 < 0 || j2 > g.ny - 1) continue;
+                    const double dirac_xy = dirac_x * d_roma((double)j - p[1]);
+                    for (int k = z0; k <= z0 + 2; ++k) {
+                        const int k2 = d_remap(g, 2, k);
+                        if (k2 < 0 || k2 > g.nz - 1) continue;
+                        const double dirac_xyz = dirac_xy * d_roma((double)k - p[2]);
+                        double u[3];
+                        const long long c0 = d_cell(g, i2, j2, k2);
+                        if (DENSE) { u[0] = vel[c0]; u[1] = vel[g.vol + c0]; u[2] = vel[2 * g.vol + c0]; }
+                        else d_cell_velocity(f, force, g.vol, c0, u);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) o[c] += dirac_xyz * u[c];
+                    }
+                }
+            }
+        }
+    }
+    vvel[v] = o[0]; vvel[cap + v] = o[1]; vvel[2 * cap + v] = o[2];
+}
+
+// ------------------------------------------------------------------------------------------------ I3: spreading
+__device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, const double* pp, const double* F, int cls, bool atomic) {
+    const double p[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};
+    const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
+    if (cls == 1) {
+        const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
+        const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
+        const double dz[3] = {d_roma((double)z0 - p[2]), d_roma((double)z0 + 1. - p[2]), d_roma((double)(z0 + 2) - p[2])};
+        const int i0 = d_remap(g, 0, x0), j0 = d_remap(g, 1, y0), k0 = d_remap(g, 2, z0);
+        for (int x = 0; x < 3; ++x) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+            const long long c0 = d_cell(g, i0 + x, j0 + j, k0 + k);
+            const double w = dx[x] * dy[j] * dz[k];
+            for (int c = 0; c < 3; ++c) {
+                const double val = w * F[c];
+                if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
+            }
+        }
+    } else {
+        for (int i = x0; i <= x0 + 2; ++i) {
+            const int i2 = d_remap(g, 0, i);
+            if (i2 < 0 || i2 > g.nx - 1) continue;
+            const double dirac_x = d_roma((double)i - p[0]);
+            for (int j = y0; j <= y0 + 2; ++j) {
+                const int j2 = d_remap(g, 1, j);
+                if (j2 < 0 || j2 > g.ny - 1) continue;
+                const double dirac_xy = dirac_x * d_roma((double)j - p[1]);
+                for (int k = z0; k <= z0 + 2; ++k) {
+                    const int k2 = d_remap(g, 2, k);
+                    if (k2 < 0 || k2 > g.nz - 1) continue;
+                    const double dirac_xyz = dirac_xy * d_roma((double)k - p[2]);
+                    const long long c0 = d_cell(g, i2, j2, k2);
+                    for (int c = 0; c < 3; ++c) {
+                        const double val = dirac_xyz * F[c];
+                        if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_spread_atomic(Geo g, double* force, long long nvert, long long cap,
+                                                       const double* __restrict__ vpos, const double* __restrict__ vfrc) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert) return;
+    const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
+    const int cls = d_classify(g, pp);
+    if (cls != 0) d_spread_vertex(g, force, pp, F, cls, true);
+}
+// Deterministic mode: the reference's own order (all bulk-list vertices, then all envelope-list vertices), one thread.
+__global__ void k_spread_sequential(Geo g, double* force, long long nvert, long long cap, const double* vpos, const double* vfrc) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int pass = 1; pass <= 2; ++pass)
+        for (long long v = 0; v < nvert; ++v) {
+            const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+            const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
+            if (d_classify(g, pp) == pass) d_spread_vertex(g, force, pp, F, pass, false);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ M1: RBC forces
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 ld3(const double* a, long long cap, long long i) { return {a[i], a[cap + i], a[2 * cap + i]}; }
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 crs(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double nrm(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ V3 divs(V3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+
+// tri::triangle_area_and_gradient (TriangleUtils.h:57-103); returns the gradient w.r.t. corner `k`
+__device__ __forceinline__ V3 d_area_grad(V3 v0, V3 v1, V3 v2, int k, double& area) {
+    const double v01v11 = v0.y - v1.y, v02v22 = v0.z - v2.z, v02v12 = v0.z - v1.z;
+    const double v01v21 = v0.y - v2.y, v00v20 = v0.x - v2.x, v00v10 = v0.x - v1.x;
+    const double a = v01v11 * v02v22 - v02v12 * v01v21;
+    const double b = v02v12 * v00v20 - (v0.x - v1.x) * v02v22;
+    const double c = v00v10 * v01v21 - v01v11 * v00v20;
+    area = 0.5 * sqrt(a * a + b * b + c * c);
+    const double denom = 1. / (4. * area);
+    V3 g;
+    if (k == 0) {
+        g.x = (b * (v2.z - v1.z) + c * (v1.y - v2.y)) * denom;
+        g.y = (a * (v1.z - v2.z) + c * (v2.x - v1.x)) * denom;
+        g.z = (a * (v2.y - v1.y) + b * (v1.x - v2.x)) * denom;
+    } else if (k == 1) {
+        g.x = (b * v02v22 + c * (v2.y - v0.y)) * denom;
+        g.y = (a * (v2.z - v0.z) + c * v00v20) * denom;
+        g.z = (a * v01v21 + b * (v2.x - v0.x)) * denom;
+    } else {
+        g.x = (b * (v1.z - v0.z) + c * v01v11) * denom;
+        g.y = (a * (v02v12) + c * (v1.x - v0.x)) * denom;
+        g.z = (a * (v1.y - v0.y) + b * v00v10) * denom;
+    }
+    return g;
+}
+
+// tri::grad_angle_between_pair (TriangleUtils.h:138-164); gradient w.r.t. corner k
+__device__ __forceinline__ V3 d_angle_grad(V3 v0, V3 v1, V3 v2, V3 v3, int k, double& cs, double& sn) {
+    const V3 e0 = sub(v1, v0), e1 = sub(v2, v0), e2 = sub(v3, v0);
+    const double e1_norm = nrm(e1);
+    const V3 e1u = divs(e1, e1_norm);
+    const V3 n1 = crs(e0, e1), n2 = crs(e1, e2);
+    const double n1_norm = nrm(n1), n2_norm = nrm(n2);
+    const V3 n1u = divs(n1, n1_norm), n2u = divs(n2, n2_norm);
+    cs = dot(n1u, n2u);
+    sn = ((dot(sub(n1, n2), sub(v1, v3)) > 0) ? 1. : -1.) * nrm(crs(n1u, n2u));
+    V3 g;
+    if (k == 0) {
+        const double a = dot(e1u, sub(e1, e2)) / n2_norm, b = dot(e1u, sub(e1, e0)) / n1_norm;
+        g = {a * n2u.x + b * n1u.x, a * n2u.y + b * n1u.y, a * n2u.z + b * n1u.z};
+    } else if (k == 1) {
+        const double a = -e1_norm / n1_norm;
+        g = {a * n1u.x, a * n1u.y, a * n1u.z};
+    } else if (k == 2) {
+        const double a = dot(e1u, e2) / n2_norm, b = dot(e1u, e0) / n1_norm;
+        g = {a * n2u.x + b * n1u.x, a * n2u.y + b * n1u.y, a * n2u.z + b * n1u.z};
+    } else {
+        const double a = -e1_norm / n2_norm;
+        g = {a * n2u.x, a * n2u.y, a * n2u.z};
+    }
+    return g;
+}
+
+struct RbcParams {
+    int nv;
+    long long first_vertex, cap;
+    int first_particle, count;
+    const int* tris; const double* tri_area;
+    const int* links; const double* link_len; const double* link_ks; const double* link_kp;
+    const int* pairs; const double* pair_cs;
+    const int* v_link_off; const int* v_link;
+    const int* v_tri_off; const int* v_tri;
+    const int* v_pair_off; const int* v_pair;
+    double shape_area, k_ag, k_al, k_v, vol_desired, k_b;
+    double reg_p, reg_t[3];
+};
+
+// One thread per vertex: gathers the contributions of its incident links, triangles and pairs in the order in which
+// RBCParticle::compute_forces adds them to that vertex (decorator, links, triangles [area, volume], pairs).
+__global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
+                                                    const double* __restrict__ pstate) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)q.count * q.nv) return;
+    const int pl = (int)(t / q.nv), v = (int)(t % q.nv);
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    const double* st = pstate + (long long)(q.first_particle + pl) * 11;
+    const double area = st[0], volume = st[1];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (q.reg_p != 0.0) {
+        fx += (q.reg_p * (q.reg_t[0] - st[2])) / (double)q.nv;
+        fy += (q.reg_p * (q.reg_t[1] - st[3])) / (double)q.nv;
+        fz += (q.reg_p * (q.reg_t[2] - st[4])) / (double)q.nv;
+    }
+    for (int e = q.v_link_off[v]; e < q.v_link_off[v + 1]; ++e) {
+        const int code = q.v_link[e], l = code >> 1, end = code & 1;
+        const V3 a = ld3(vpos, q.cap, base + q.links[2 * l]), b = ld3(vpos, q.cap, base + q.links[2 * l + 1]);
+        const V3 dv = sub(a, b);
+        const double L = nrm(dv);
+        const double x = L / (q.link_len[l] * 2.2);
+        const double df = -0.25 * q.link_ks[l] * (6. * x + (3. * x * x - 2. * x * x * x) / ((1 - x) * (1 - x))) + q.link_kp[l] / (L * L);
+        const double tx = df * dv.x / L, ty = df * dv.y / L, tz = df * dv.z / L;
+        if (end == 0) { fx += tx; fy += ty; fz += tz; } else { fx -= tx; fy -= ty; fz -= tz; }
+    }
+    const double df_vol = q.k_v * (q.vol_desired - volume) / q.vol_desired;
+    for (int e = q.v_tri_off[v]; e < q.v_tri_off[v + 1]; ++e) {
+        const int code = q.v_tri[e], tr = code / 3, k = code % 3;
+        const V3 v0 = ld3(vpos, q.cap, base + q.tris[3 * tr]), v1 = ld3(vpos, q.cap, base + q.tris[3 * tr + 1]), v2 = ld3(vpos, q.cap, base + q.tris[3 * tr + 2]);
+        double local_area;
+        const V3 g = d_area_grad(v0, v1, v2, k, local_area);
+        double df_area = 0.;
+        df_area += q.k_ag * (q.shape_area - area) / q.shape_area;
+        df_area += q.k_al * (q.tri_area[tr] - local_area) / q.tri_area[tr];
+        fx += df_area * g.x; fy += df_area * g.y; fz += df_area * g.z;
+        const V3 gv = k == 0 ? crs(v1, v2) : (k == 1 ? crs(v2, v0) : crs(v0, v1));   // grad_signed_volume, TriangleUtils.h:112-120
+        fx += df_vol * (gv.x / 6.); fy += df_vol * (gv.y / 6.); fz += df_vol * (gv.z / 6.);
+    }
+    for (int e = q.v_pair_off[v]; e < q.v_pair_off[v + 1]; ++e) {
+        const int code = q.v_pair[e], pr = code >> 2, k = code & 3;
+        const V3 v0 = ld3(vpos, q.cap, base + q.pairs[4 * pr]), v1 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 1]);
+        const V3 v2 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 2]), v3 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 3]);
+        double cs, sn;
+        const V3 g = d_angle_grad(v0, v1, v2, v3, k, cs, sn);
+        const double prefactor = q.k_b * (-q.pair_cs[2 * pr] * sn + q.pair_cs[2 * pr + 1] * cs);
+        fx += prefactor * g.x; fy += prefactor * g.y; fz += prefactor * g.z;
+    }
+    vfrc[base + v] = fx; vfrc[q.cap + base + v] = fy; vfrc[2 * q.cap + base + v] = fz;
+}
+
+// ------------------------------------------------------------------------------------------------ I4: move + update
+// One CTA per particle. Triangle terms are computed in parallel in chunks and accumulated by one thread in triangle
+// order, so area / volume / centre of mass carry exactly the reference's sequential rounding.
+#define UPD_CHUNK 512
+__global__ void __launch_bounds__(256) k_move_update(Geo g, int nv, int nt, const int* __restrict__ tris, long long first_vertex, long long cap,
+                                                     int first_particle, double* vpos, const double* __restrict__ vvel, double* pstate, int do_move) {
+    __shared__ double s_dA[UPD_CHUNK], s_vol[UPD_CHUNK], s_cx[UPD_CHUNK], s_cy[UPD_CHUNK], s_cz[UPD_CHUNK];
+    __shared__ double s_acc[5];
+    __shared__ double s_red[6][8];
+    __shared__ double s_delta[3];
+    const int pl = blockIdx.x;
+    const long long base = first_vertex + (long long)pl * nv;
+    double* st = pstate + (long long)(first_particle + pl) * 11;
+    double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
+    double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double x = vpos[d * cap + base + v];
+            if (do_move) { x += vvel[d * cap + base + v]; vpos[d * cap + base + v] = x; }
+            mn[d] = fmin(mn[d], x); mx[d] = fmax(mx[d], x);
+        }
+    }
+    // bounding box: order-independent min/max
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o)); }
+        if ((threadIdx.x & 31) == 0) { s_red[2 * d][threadIdx.x >> 5] = mn[d]; s_red[2 * d + 1][threadIdx.x >> 5] = mx[d]; }
+    }
+    if (threadIdx.x == 0) { for (int k = 0; k < 5; ++k) s_acc[k] = 0.0; }
+    __syncthreads();
+    for (int t0 = 0; t0 < nt; t0 += UPD_CHUNK) {
+        const int cn = min(UPD_CHUNK, nt - t0);
+        for (int k = threadIdx.x; k < cn; k += blockDim.x) {
+            const int t = t0 + k;
+            const V3 v0 = ld3(vpos, cap, base + tris[3 * t]), v1 = ld3(vpos, cap, base + tris[3 * t + 1]), v2 = ld3(vpos, cap, base + tris[3 * t + 2]);
+            const V3 centroid = {(v0.x + v1.x + v2.x) / 3.0, (v0.y + v1.y + v2.y) / 3.0, (v0.z + v1.z + v2.z) / 3.0};
+            const V3 n = crs(sub(v1, v0), sub(v2, v0));
+            double dA = nrm(n);
+            dA *= 0.5;                                            // tri::normal_and_area, TriangleUtils.h:27-34
+            s_dA[k] = dA;
+            s_vol[k] = dot(v0, crs(v1, v2)) / 6.;                 // tri::signed_volume, TriangleUtils.h:105-110
+            s_cx[k] = centroid.x * dA; s_cy[k] = centroid.y * dA; s_cz[k] = centroid.z * dA;
+        }
+        __syncthreads();
+        if (threadIdx.x < 5) {
+            const double* src = threadIdx.x == 0 ? s_dA : threadIdx.x == 1 ? s_vol : threadIdx.x == 2 ? s_cx : threadIdx.x == 3 ? s_cy : s_cz;
+            double acc = s_acc[threadIdx.x];
+            for (int k = 0; k < cn; ++k) acc += src[k];
+            s_acc[threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) / 32;
+        double bb[6];
+        for (int k = 0; k < 6; ++k) {
+            double r = s_red[k][0];
+            for (int w = 1; w < nw; ++w) r = (k & 1) ? fmax(r, s_red[k][w]) : fmin(r, s_red[k][w]);
+            bb[k] = r;
+        }
+        const double area = s_acc[0];
+        double com[3] = {s_acc[2] / area, s_acc[3] / area, s_acc[4] / area};
+        // map_center_of_mass_to_periodic_grid: remap_pos (Periodicity.h:83-87) then set_center_of_mass (ParticleBase.hh:122-138)
+        const int n[3] = {g.nx, g.ny, g.nz};
+        for (int d = 0; d < 3; ++d) {
+            double x = com[d];
+            if (g.per[d]) { const double L = (double)n[d], Linv = 1. / L; x = x - L * floor((x - (0.0 - 0.5)) * Linv); }
+            s_delta[d] = x - com[d];
+            com[d] = x;
+            bb[2 * d] += s_delta[d]; bb[2 * d + 1] += s_delta[d];
+        }
+        st[0] = area; st[1] = s_acc[1]; st[2] = com[0]; st[3] = com[1]; st[4] = com[2];
+        for (int k = 0; k < 6; ++k) st[5 + k] = bb[k];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) vpos[d * cap + base + v] += s_delta[d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ V1: voxelization
+__device__ __forceinline__ void d_toggle_mark(uint8_t* phase, long long idx) {
+    const unsigned long long addr = (unsigned long long)(phase + idx);
+    unsigned int* word = (unsigned int*)(addr & ~3ull);
+    atomicXor(word, 2u << (8 * (unsigned)(addr & 3ull)));
+}
+// One thread per (particle, triangle): Moeller-Trumbore against the +z rays through the integer (x,y) of the triangle's
+// bounding box (RayTracer.hh:19-39,80-108). A hit at height h toggles the mark bit of cell ceil(h) in column (x,y).
+__global__ void __launch_bounds__(128) k_raycast(Geo g, int nv, int nt, const int* __restrict__ tris, long long first_vertex, long long cap,
+                                                 int count, const double* __restrict__ vpos, uint8_t* phase, uint8_t* col_flags) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)count * nt) return;
+    const int pl = (int)(t / nt), tr = (int)(t % nt);
+    const long long base = first_vertex + (long long)pl * nv;
+    const V3 p0 = ld3(vpos, cap, base + tris[3 * tr]), p1 = ld3(vpos, cap, base + tris[3 * tr + 1]), p2 = ld3(vpos, cap, base + tris[3 * tr + 2]);
+    const int iXmin = (int)ceil(fmin(p0.x, fmin(p1.x, p2.x))), iXmax = (int)floor(fmax(p0.x, fmax(p1.x, p2.x)));
+    const int iYmin = (int)ceil(fmin(p0.y, fmin(p1.y, p2.y))), iYmax = (int)floor(fmax(p0.y, fmax(p1.y, p2.y)));
+    const V3 dir = {0., 0., 1.};
+    const V3 e1 = sub(p1, p0), e2 = sub(p2, p0);
+    const V3 q = crs(dir, e2);
+    const double a = dot(e1, q);
+    if (fabs(a) < 2.220446049250313e-16) return;
+    const double f = 1 / a;
+    const int z1 = g.nz - 1;
+    for (int i = iXmin; i <= iXmax; ++i) for (int j = iYmin; j <= iYmax; ++j) {
+        const V3 pos = {(double)i, (double)j, 0.};
+        const V3 s = sub(pos, p0);
+        const double u = f * dot(s, q);
+        if (u < 0.0) continue;
+        const V3 r = crs(s, e1);
+        const double v = f * dot(dir, r);
+        if (v < 0.0 || u + v > 1.0) continue;
+        double z = f * dot(e2, r);
+        if (g.per[2]) { const double L = (double)g.nz, Linv = 1. / L; z = z - L * floor((z - (-0.5)) * Linv); }   // ZBuffer::put, ZBuffer.h:39-50
+        const int ci = g.per[0] ? ((i + 100 * g.nx) % g.nx) : i;
+        const int cj = g.per[1] ? ((j + 100 * g.ny) % g.ny) : j;
+        if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
+        const int lx = ci - g.x_offset;
+        if (lx < 0 || lx >= (int)(g.vol / g.plane) - 2) continue;          // column belongs to another slab
+        const double zc_d = ceil(z);
+        uint8_t* flag = col_flags + (long long)(lx + 1) * g.ny + cj;
+        unsigned bits = 0;
+        if (zc_d > (double)z1) bits = 4;
+        else {
+            int zc = (int)zc_d; if (zc < 0) zc = 0;
+            d_toggle_mark(phase, (long long)(lx + 1) * g.plane + (long long)cj * g.nz + zc);
+            if (zc == z1) bits = (z == (double)z1) ? 2 : 1;
+        }
+        if (bits) {
+            const unsigned long long addr = (unsigned long long)flag;
+            atomicOr((unsigned int*)(addr & ~3ull), bits << (8 * (unsigned)(addr & 3ull)));
+        }
+    }
+}
+
+// One warp per (x,y) column: phase(z) = parity of the number of hits <= z = prefix XOR of the toggle marks
+// (apply_voxelization, ImmersedBoundaryDynamics_voxelization.hh:121-165, incl. its z1 corner case).
+__global__ void __launch_bounds__(256) k_phase_scan(int nx, int ny, int nz, long long plane, uint8_t* phase, uint8_t* col_flags) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nx * ny) return;
+    const int x = warp / ny, y = warp % ny;
+    uint8_t* col = phase + (long long)(x + 1) * plane + (long long)y * nz;
+    const int chunk = (nz + 31) / 32;
+    const int zb = lane * chunk, ze = min(nz, zb + chunk);
+    unsigned par = 0;
+    for (int z = zb; z < ze; ++z) par ^= (col[z] >> 1) & 1u;
+    unsigned incl = par;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl ^= t; }
+    unsigned run = incl ^ par;   // exclusive prefix
+    const unsigned flags = col_flags[(long long)(x + 1) * ny + y];
+    for (int z = zb; z < ze; ++z) {
+        const uint8_t b = col[z];
+        run ^= (b >> 1) & 1u;
+        unsigned val = run;
+        if (z == nz - 1 && !(flags & 4u) && (flags & 3u)) val = (flags & 2u) ? (run ^ 1u) : (b & 1u);
+        col[z] = (uint8_t)val;
+    }
+    __syncwarp();
+    if (lane == 0 && flags) col_flags[(long long)(x + 1) * ny + y] = 0;
+}
+
+Geo make_geo(const bib_domain* d) {
+    Geo g;
+    g.nx = d->gnx; g.ny = d->ny; g.nz = d->nz;
+    g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
+    g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
+    return g;
+}
+
+template <class T>
+bool to_device(T** dst, const std::vector<T>& src) {
+    if (!bib_cuda_ok(cudaMalloc((void**)dst, std::max<size_t>(1, src.size()) * sizeof(T)), "cudaMalloc(shape)")) return false;
+    if (!src.empty() && !bib_cuda_ok(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(shape)")) return false;
+    return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host: shapes
+// ParticleShape constructor + compute_connectivity (src/fsi/ParticleShape.hh:22-57,90-184): links in std::set<(i0,i1)>
+// order, t1 = first triangle naming the edge, t2 = last other triangle; one pair per interior link, in link order.
+int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const int* tris, int* shape_id) {
+    if (nv <= 0 || nt <= 0 || !verts || !tris) { bib_set_error("shape_register: empty mesh"); return 0; }
+    for (int i = 0; i < 3 * nt; ++i) if (tris[i] < 0 || tris[i] >= nv) { bib_set_error("shape_register: triangle index out of range"); return 0; }
+    ShapeDev s;
+    s.nv = nv; s.nt = nt;
+    s.h_verts.assign(verts, verts + 3 * (size_t)nv);
+    s.h_tris.assign(tris, tris + 3 * (size_t)nt);
+    auto V = [&](int i) { return verts + 3 * (size_t)i; };
+    auto cross3 = [](const double* a, const double* b, double* r) { r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0]; };
+    auto norm3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+    s.h_tri_area.resize(nt);
+    double area = 0, volume = 0;
+    for (int t = 0; t < nt; ++t) {
+        const double *v0 = V(tris[3 * t]), *v1 = V(tris[3 * t + 1]), *v2 = V(tris[3 * t + 2]);
+        double e1[3], e2[3], n[3], c[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+        cross3(e1, e2, n);
+        double a = norm3(n);
+        a *= 0.5;
+        s.h_tri_area[t] = a;
+        area += a;
+        cross3(v1, v2, c);
+        volume += (v0[0] * c[0] + v0[1] * c[1] + v0[2] * c[2]) / 6.;
+    }
+    s.area = area; s.volume = volume;
+    struct Key { int i0, i1, order; };
+    std::vector<Key> keys(3 * (size_t)nt);
+    for (int t = 0; t < nt; ++t) for (int j = 0; j < 3; ++j) {
+        const int a = tris[3 * t + j], b = tris[3 * t + (j + 1) % 3];
+        keys[3 * t + j] = {std::min(a, b), std::max(a, b), 3 * t + j};
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.i0 != b.i0 ? a.i0 < b.i0 : (a.i1 != b.i1 ? a.i1 < b.i1 : a.order < b.order); });
+    std::vector<int> link_tri;
+    for (size_t i = 0; i < keys.size();) {
+        size_t j = i;
+        const int t1 = keys[i].order / 3; int t2 = -1;
+        while (j < keys.size() && keys[j].i0 == keys[i].i0 && keys[j].i1 == keys[i].i1) { const int t = keys[j].order / 3; if (t != t1) t2 = t; ++j; }
+        s.h_links.push_back(keys[i].i0); s.h_links.push_back(keys[i].i1);
+        link_tri.push_back(t1); link_tri.push_back(t2);
+        const double* a = V(keys[i].i0); const double* b = V(keys[i].i1);
+        const double dd[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+        s.h_link_len.push_back(norm3(dd));
+        i = j;
+    }
+    s.nl = (int)s.h_link_len.size();
+    auto unit_normal = [&](const double* v0, const double* v1, const double* v2, double* n) {
+        double e1[3], e2[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+        cross3(e1, e2, n);
+        const double nn = norm3(n);
+        n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    };
+    for (int l = 0; l < s.nl; ++l) {
+        if (link_tri[2 * l] == -1 || link_tri[2 * l + 1] == -1) continue;
+        int a[3] = {tris[3 * link_tri[2 * l]], tris[3 * link_tri[2 * l] + 1], tris[3 * link_tri[2 * l] + 2]};
+        int b[3] = {tris[3 * link_tri[2 * l + 1]], tris[3 * link_tri[2 * l + 1] + 1], tris[3 * link_tri[2 * l + 1] + 2]};
+        const int i0 = s.h_links[2 * l], i1 = s.h_links[2 * l + 1];
+        while (!((a[0] == i0 && a[2] == i1) || (a[0] == i1 && a[2] == i0))) { const int tmp = a[0]; a[0] = a[2]; a[2] = a[1]; a[1] = tmp; }
+        while (!((b[0] == i0 && b[1] == i1) || (b[0] == i1 && b[1] == i0))) { const int tmp = b[0]; b[0] = b[2]; b[2] = b[1]; b[1] = tmp; }
+        const int q[4] = {a[0], a[1], a[2], b[2]};
+        for (int k = 0; k < 4; ++k) s.h_pairs.push_back(q[k]);
+        // tri::cos_sin_of_angle_between_pair on the REST mesh (TriangleUtils.h:124-136)
+        double n1[3], n2[3], dn[3], dv[3], cr[3];
+        unit_normal(V(q[0]), V(q[1]), V(q[2]), n1);
+        unit_normal(V(q[0]), V(q[2]), V(q[3]), n2);
+        const double cs = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
+        for (int k = 0; k < 3; ++k) { dn[k] = n1[k] - n2[k]; dv[k] = V(q[1])[k] - V(q[3])[k]; }
+        cross3(n1, n2, cr);
+        const double sn = ((dn[0] * dv[0] + dn[1] * dv[1] + dn[2] * dv[2] > 0) ? 1. : -1.) * norm3(cr);
+        s.h_pair_cs.push_back(cs); s.h_pair_cs.push_back(sn);
+    }
+    s.np = (int)s.h_pairs.size() / 4;
+    // per-vertex incidence lists, element index ascending
+    auto build_csr = [&](int n_elem, int arity, const std::vector<int>& elems, std::vector<int>& off, std::vector<int>& lst, int mul) {
+        off.assign(nv + 1, 0);
+        for (int e = 0; e < n_elem; ++e) for (int k = 0; k < arity; ++k) off[elems[arity * e + k] + 1]++;
+        for (int v = 0; v < nv; ++v) off[v + 1] += off[v];
+        lst.assign(off[nv], 0);
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int e = 0; e < n_elem; ++e) for (int k = 0; k < arity; ++k) lst[cur[elems[arity * e + k]]++] = e * mul + k;
+    };
+    std::vector<int> lo, ll, to, tl, po, pl;
+    build_csr(s.nl, 2, s.h_links, lo, ll, 2);
+    build_csr(s.nt, 3, s.h_tris, to, tl, 3);
+    build_csr(s.np, 4, s.h_pairs, po, pl, 4);
+    BIB_CHECK(cudaSetDevice(d->device));
+    if (!to_device(&s.tris, s.h_tris) || !to_device(&s.tri_area, s.h_tri_area) || !to_device(&s.links, s.h_links) ||
+        !to_device(&s.link_len, s.h_link_len) || !to_device(&s.pairs, s.h_pairs) || !to_device(&s.pair_cs, s.h_pair_cs) ||
+        !to_device(&s.v_link_off, lo) || !to_device(&s.v_link, ll) || !to_device(&s.v_tri_off, to) || !to_device(&s.v_tri, tl) ||
+        !to_device(&s.v_pair_off, po) || !to_device(&s.v_pair, pl)) return 0;
+    d->shapes.push_back(s);
+    *shape_id = (int)d->shapes.size() - 1;
+    return 1;
+}
+
+// RBCParameters::in_plane_ks_kp (src/fsi/RBCParticle.hh:27-44), evaluated on the host with libm pow like the reference
+static void rbc_ks_kp(double l0, double G, double& ks, double& kp) {
+    const double x0 = 1. / 2.2, m = 2;
+    const double ks_coeff1 = 0.25 * (6. * x0 + (3 * x0 * x0 - 2 * x0 * x0 * x0) / ((1 - x0) * (1 - x0)));
+    const double ks_coeff2 = x0 / (2. * (1 - x0) * (1 - x0) * (1 - x0)) + 0.25 * (1. - 1. / ((1 - x0) * (1 - x0)));
+    const double kp_coeff1 = -1. / std::pow(l0, m);
+    const double kp_coeff2 = (m + 1) / std::pow(l0, m);
+    const double G_lhs = 4. * l0 * G / std::sqrt(3);
+    ks = -kp_coeff1 * G_lhs / (ks_coeff1 * kp_coeff2 - ks_coeff2 * kp_coeff1);
+    kp = ks_coeff1 * G_lhs / (ks_coeff1 * kp_coeff2 - ks_coeff2 * kp_coeff1);
+}
+
+static int grow_particles(bib_domain* d, long long need_v, int need_p) {
+    if (need_v > d->cap_vertices) {
+        long long cap = std::max<long long>(need_v, d->cap_vertices * 2);
+        double* np[3];
+        double** old[3] = {&d->vpos, &d->vvel, &d->vfrc};
+        for (int k = 0; k < 3; ++k) {
+            BIB_CHECK(cudaMalloc(&np[k], (size_t)cap * 3 * sizeof(double)));
+            BIB_CHECK(cudaMemsetAsync(np[k], 0, (size_t)cap * 3 * sizeof(double), d->stream));
+            if (*old[k]) {
+                for (int c = 0; c < 3; ++c)
+                    BIB_CHECK(cudaMemcpyAsync(np[k] + c * cap, *old[k] + c * d->cap_vertices, (size_t)d->n_vertices * sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
+            }
+        }
+        BIB_CHECK(cudaStreamSynchronize(d->stream));
+        for (int k = 0; k < 3; ++k) { if (*old[k]) cudaFree(*old[k]); *old[k] = np[k]; }
+        d->bytes += (cap - d->cap_vertices) * 9 * 8;
+        d->cap_vertices = cap;
+    }
+    if (need_p > d->cap_particles) {
+        int cap = std::max(need_p, d->cap_particles * 2);
+        double* ns;
+        BIB_CHECK(cudaMalloc(&ns, (size_t)cap * 11 * sizeof(double)));
+        BIB_CHECK(cudaMemsetAsync(ns, 0, (size_t)cap * 11 * sizeof(double), d->stream));
+        if (d->pstate) BIB_CHECK(cudaMemcpyAsync(ns, d->pstate, (size_t)d->n_particles * 11 * sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
+        BIB_CHECK(cudaStreamSynchronize(d->stream));
+        if (d->pstate) cudaFree(d->pstate);
+        d->pstate = ns; d->cap_particles = cap;
+    }
+    return 1;
+}
+
+static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move) {
+    const ShapeDev& s = d->shapes[gr.shape];
+    k_move_update<<<gr.count, 256, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.first_particle,
+                                                 d->vpos, d->vvel, d->pstate, do_move);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
+    if (type != 0) { bib_set_error("particles_add: only BIB_PARTICLE_RBC is implemented"); return 0; }
+    if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("particles_add: unknown shape"); return 0; }
+    if (n <= 0) return 1;
+    const ShapeDev& s = d->shapes[shape_id];
+    const long long nvtot = (long long)n * s.nv;
+    if (!grow_particles(d, d->n_vertices + nvtot, d->n_particles + n)) return 0;
+    ParticleGroup gr;
+    gr.type = type; gr.shape = shape_id; gr.first_particle = d->n_particles; gr.count = n; gr.first_vertex = d->n_vertices;
+    std::memcpy(gr.params, params, 8 * sizeof(double));
+    std::vector<double> ks(s.nl), kp(s.nl);
+    for (int l = 0; l < s.nl; ++l) rbc_ks_kp(s.h_link_len[l], params[0], ks[l], kp[l]);
+    if (!to_device(&gr.link_ks, ks) || !to_device(&gr.link_kp, kp)) return 0;
+    // AoS [n][nv][3] -> SoA
+    std::vector<double> soa((size_t)nvtot * 3);
+    for (long long v = 0; v < nvtot; ++v) for (int c = 0; c < 3; ++c) soa[(size_t)c * nvtot + v] = positions[(size_t)v * 3 + c];
+    for (int c = 0; c < 3; ++c)
+        BIB_CHECK(cudaMemcpyAsync(d->vpos + (size_t)c * d->cap_vertices + gr.first_vertex, soa.data() + (size_t)c * nvtot, (size_t)nvtot * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    d->groups.push_back(gr);
+    d->n_particles += n; d->n_vertices += nvtot;
+    // ParticleBase3D::update() at construction + add_particle's map_center_of_mass_to_periodic_grid (ImmersedBoundaryDynamics.hh:500-525)
+    return launch_update(d, gr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ host: IB phases
+int ib_interpolate(bib_domain* d) {
+    if (d->n_vertices == 0) return 1;
+    const int bs = 128;
+    const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
+    k_interpolate<false><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, nullptr, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+int ib_interpolate_dense(bib_domain* d) {
+    if (d->n_vertices == 0) return 1;
+    const int bs = 128;
+    const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
+    k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int ib_forces_and_spread(bib_domain* d) {
+    if (d->n_vertices == 0) return 1;
+    for (const ParticleGroup& gr : d->groups) {
+        const ShapeDev& s = d->shapes[gr.shape];
+        RbcParams q;
+        q.nv = s.nv; q.first_vertex = gr.first_vertex; q.cap = d->cap_vertices; q.first_particle = gr.first_particle; q.count = gr.count;
+        q.tris = s.tris; q.tri_area = s.tri_area; q.links = s.links; q.link_len = s.link_len; q.link_ks = gr.link_ks; q.link_kp = gr.link_kp;
+        q.pairs = s.pairs; q.pair_cs = s.pair_cs;
+        q.v_link_off = s.v_link_off; q.v_link = s.v_link; q.v_tri_off = s.v_tri_off; q.v_tri = s.v_tri; q.v_pair_off = s.v_pair_off; q.v_pair = s.v_pair;
+        q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
+        q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
+        const long long n = (long long)gr.count * s.nv;
+        k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+        d->launches++;
+    }
+    if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+    else k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int ib_move_and_voxelize(bib_domain* d) {
+    for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;
+    for (const ParticleGroup& gr : d->groups) {
+        const ShapeDev& s = d->shapes[gr.shape];
+        const long long n = (long long)gr.count * s.nt;
+        k_raycast<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.count, d->vpos, d->phase, d->col_flags);
+        d->launches++;
+    }
+    // apply_voxelization rewrites the phase of every cell of the block each step, also without any particle
+    const long long warps = (long long)d->nx * d->ny;
+    k_phase_scan<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, d->stream>>>(d->nx, d->ny, d->nz, (long long)d->plane, d->phase, d->col_flags);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9) {
+    if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_download: range"); return 0; }
+    if (count == 0) return 1;
+    std::vector<double> tmp((size_t)count * 9);
+    const double* src[3] = {d->vpos, d->vvel, d->vfrc};
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
+        BIB_CHECK(cudaMemcpyAsync(tmp.data() + (size_t)(a * 3 + c) * count, src[a] + (size_t)c * d->cap_vertices + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    for (long long v = 0; v < count; ++v) for (int k = 0; k < 9; ++k) v9[(size_t)v * 9 + k] = tmp[(size_t)k * count + v];
+    return 1;
+}
+int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {
+    if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_upload: range"); return 0; }
+    if (count == 0) return 1;
+    std::vector<double> tmp((size_t)count * 9);
+    for (long long v = 0; v < count; ++v) for (int k = 0; k < 9; ++k) tmp[(size_t)k * count + v] = v9[(size_t)v * 9 + k];
+    double* dst[3] = {d->vpos, d->vvel, d->vfrc};
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
+        BIB_CHECK(cudaMemcpyAsync(dst[a] + (size_t)c * d->cap_vertices + first, tmp.data() + (size_t)(a * 3 + c) * count, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}
+int ib_scalars_download(bib_domain* d, int first, int count, double* s11) {
+    if (first < 0 || count < 0 || first + count > d->n_particles) { bib_set_error("particle_scalars_download: range"); return 0; }
+    if (count == 0) return 1;
+    BIB_CHECK(cudaMemcpyAsync(s11, d->pstate + (size_t)first * 11, (size_t)count * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}

@@ -1,0 +1,501 @@
+// lbm_kernels.cu -- fused D3Q19 collide-and-stream (one-step push, A/B buffers, SoA fp64) and the lattice side passes.
+//
+// Replaces (reference file:line):
+//   GuoExternalForceVOFDynamics::collide            src/fsi/VariableViscosityDynamics.hh:151-172
+//   bgk_ma2_collision_base (D3Q19)                  src/latticeBoltzmann/dynamicsTemplates3D.h:759-838
+//   vofTemplatesImpl::addGuoForce / computeOmega    src/fsi/VariableViscosityDynamics.hh:47-141
+//   BlockLattice3D::collideAndStream + periodic envelope copy
+//                                                   src/atomicBlock/blockLattice3D.hh:252-312,402-427,500-551
+//   BoxVelocityFunctional3D / SetExternalVectorFunctional3D
+//                                                   src/dataProcessors/dataAnalysisFunctional3D.hh:772-784,
+//                                                   src/dataProcessors/dataInitializerFunctional3D.hh:1144-1154
+//
+// Kernel design: one thread per cell, z (the contiguous axis) along threadIdx.x, so the 19 loads of
+// a warp are 256-byte contiguous and aligned; the thread collides in registers and PUSHES the 19 post-collision values
+// to its neighbours in the other buffer (stores shifted by 0/+-1 element in z, +-1 row in y, +-1 plane in x). The buffers
+// hold pre-collision populations, exactly the state the reference keeps, so upload/download/velocity need no gather.
+// Bound: HBM. Algorithmic traffic 19*8*2 = 304 B/cell (+24 B force +1 B phase actually read).
+#include "domain.cuh"
+
+namespace {
+
+struct LbmParams {
+    const double* __restrict__ fin;
+    double* __restrict__ fout;
+    const double* __restrict__ force;
+    const uint8_t* __restrict__ phase;
+    const uint8_t* __restrict__ kind;
+    int nx, ny, nz;
+    long long plane, vol;
+    double omega0, omega1;
+    int per_y, per_z;
+    // x handling: 0 = write into the ghost plane (neighbour slab or periodic image handled by the halo exchange),
+    //             1 = wrap inside this slab (single slab, periodic x), 2 = wall face (non-periodic: free bounce-back)
+    int x_lo_mode, x_hi_mode;
+};
+
+__constant__ int c_cx[BIB_Q] = {0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0};
+__constant__ int c_cy[BIB_Q] = {0, 0, -1, 0, -1, 1, 0, 0, -1, -1, 0, 1, 0, 1, -1, 0, 0, 1, 1};
+__constant__ int c_cz[BIB_Q] = {0, 0, 0, -1, 0, 0, -1, 1, -1, 1, 0, 0, 1, 0, 0, 1, -1, 1, -1};
+
+__device__ __forceinline__ int d_opp(int i) { return i == 0 ? 0 : (i <= 9 ? i + 9 : i - 9); }
+
+// GuoExternalForceVOFDynamics::collide, operation order as in the reference (see oracle/biblbm_oracle.c for the
+// line-by-line citations). f: 19 fBar values in/out; F: force; c: phase; (w0, w1) = (omega, omega2_) of the dynamics object.
+__device__ __forceinline__ void d_collide(double* f, double Fx, double Fy, double Fz, double c, double w0, double w1) {
+    // computeRhoBar: plain left-to-right sum (momentTemplates3D.h:375-382)
+    double rhoBar = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8] + f[9] + f[10] + f[11] + f[12] + f[13] + f[14] +
+                    f[15] + f[16] + f[17] + f[18];
+    // computeVelocity: grouped sums, u = j/rho + F/2 (externalForceDynamics.hh:59-74)
+    double rhoBar2, jx, jy, jz;
+    d_rhoBar_j(f, rhoBar2, jx, jy, jz);
+    const double invRho2 = 1.0 / (rhoBar2 + 1.0);
+    const double ux = jx * invRho2 + Fx / 2.0;
+    const double uy = jy * invRho2 + Fy / 2.0;
+    const double uz = jz * invRho2 + Fz / 2.0;
+    const double rho = rhoBar + 1.0;
+    jx = rho * ux; jy = rho * uy; jz = rho * uz;
+    const double omega = w0 * w1 / (c * w0 + (1. - c) * w1);
+
+    // bgk_ma2_collision_base
+    const double invRho = 1.0 / (rhoBar + 1.0);
+    const double one_m_omega = 1.0 - omega;
+    const double t0_omega = (1.0 / 3.0) * omega;
+    const double t1_omega = (1.0 / 18.0) * omega;
+    const double t4_omega = (1.0 / 36.0) * omega;
+    const double jSqr = jx * jx + jy * jy + jz * jz;
+    const double kx = 3.0 * jx, ky = 3.0 * jy, kz = 3.0 * jz;
+    const double kxSqr_ = invRho / 2.0 * kx * kx;
+    const double kySqr_ = invRho / 2.0 * ky * ky;
+    const double kzSqr_ = invRho / 2.0 * kz * kz;
+    const double kxky_ = invRho * kx * ky;
+    const double kxkz_ = invRho * kx * kz;
+    const double kykz_ = invRho * ky * kz;
+    const double C1 = rhoBar + invRho * 3.0 * jSqr;
+    double C2, C3;
+    C3 = -kxSqr_ - kySqr_ - kzSqr_;
+    f[0] *= one_m_omega; f[0] += t0_omega * (C1 + C3);
+    C2 = -kx; C3 = -kySqr_ - kzSqr_;
+    f[1] *= one_m_omega; f[1] += t1_omega * (C1 + C2 + C3);
+    f[10] *= one_m_omega; f[10] += t1_omega * (C1 - C2 + C3);
+    C2 = -ky; C3 = -kxSqr_ - kzSqr_;
+    f[2] *= one_m_omega; f[2] += t1_omega * (C1 + C2 + C3);
+    f[11] *= one_m_omega; f[11] += t1_omega * (C1 - C2 + C3);
+    C2 = -kz; C3 = -kxSqr_ - kySqr_;
+    f[3] *= one_m_omega; f[3] += t1_omega * (C1 + C2 + C3);
+    f[12] *= one_m_omega; f[12] += t1_omega * (C1 - C2 + C3);
+    C2 = -kx - ky; C3 = kxky_ - kzSqr_;
+    f[4] *= one_m_omega; f[4] += t4_omega * (C1 + C2 + C3);
+    f[13] *= one_m_omega; f[13] += t4_omega * (C1 - C2 + C3);
+    C2 = -kx + ky; C3 = -kxky_ - kzSqr_;
+    f[5] *= one_m_omega; f[5] += t4_omega * (C1 + C2 + C3);
+    f[14] *= one_m_omega; f[14] += t4_omega * (C1 - C2 + C3);
+    C2 = -kx - kz; C3 = kxkz_ - kySqr_;
+    f[6] *= one_m_omega; f[6] += t4_omega * (C1 + C2 + C3);
+    f[15] *= one_m_omega; f[15] += t4_omega * (C1 - C2 + C3);
+    C2 = -kx + kz; C3 = -kxkz_ - kySqr_;
+    f[7] *= one_m_omega; f[7] += t4_omega * (C1 + C2 + C3);
+    f[16] *= one_m_omega; f[16] += t4_omega * (C1 - C2 + C3);
+    C2 = -ky - kz; C3 = kykz_ - kxSqr_;
+    f[8] *= one_m_omega; f[8] += t4_omega * (C1 + C2 + C3);
+    f[17] *= one_m_omega; f[17] += t4_omega * (C1 - C2 + C3);
+    C2 = -ky + kz; C3 = -kykz_ - kxSqr_;
+    f[9] *= one_m_omega; f[9] += t4_omega * (C1 + C2 + C3);
+    f[18] *= one_m_omega; f[18] += t4_omega * (C1 - C2 + C3);
+
+    // addGuoForce (amplitude 1)
+    const double mu = 1.0 * (1.0 - omega / 2.0);
+    const double oneOver6 = 1.0 / 6.0;
+    const double oneOver12 = 1.0 / 12.0;
+    f[0] += -mu * (Fx * ux + Fy * uy + Fz * uz);
+    f[1] += oneOver6 * mu * (Fx * (-1.0 + 2 * ux) - Fy * uy - Fz * uz);
+    f[2] += -oneOver6 * mu * (Fx * ux + Fy * (1.0 - 2 * uy) + Fz * uz);
+    f[3] += -oneOver6 * mu * (Fx * ux + Fy * uy + Fz * (1.0 - 2 * uz));
+    f[4] += oneOver12 * mu * (Fx * (-1.0 + 2 * ux + 3 * uy) + Fy * (-1.0 + 2 * uy + 3 * ux) - Fz * uz);
+    f[5] += oneOver12 * mu * (Fx * (-1.0 + 2 * ux - 3 * uy) + Fy * (1.0 + 2 * uy - 3 * ux) - Fz * uz);
+    f[6] += oneOver12 * mu * (Fx * (-1.0 + 2 * ux + 3 * uz) - Fy * uy + Fz * (-1.0 + 2 * uz + 3 * ux));
+    f[7] += oneOver12 * mu * (Fx * (-1.0 + 2 * ux - 3 * uz) - Fy * uy + Fz * (1.0 + 2 * uz - 3 * ux));
+    f[8] += -oneOver12 * mu * (Fx * ux + Fy * (1.0 - 2 * uy - 3 * uz) + Fz * (1.0 - 2 * uz - 3 * uy));
+    f[9] += -oneOver12 * mu * (Fx * ux + Fy * (1.0 - 2 * uy + 3 * uz) + Fz * (-1.0 - 2 * uz + 3 * uy));
+    f[10] += oneOver6 * mu * (Fx * (1.0 + 2 * ux) - Fy * uy - Fz * uz);
+    f[11] += -oneOver6 * mu * (Fx * ux + Fy * (-1.0 - 2 * uy) + Fz * uz);
+    f[12] += -oneOver6 * mu * (Fx * ux + Fy * uy + Fz * (-1.0 - 2 * uz));
+    f[13] += oneOver12 * mu * (Fx * (1.0 + 2 * ux + 3 * uy) + Fy * (1.0 + 2 * uy + 3 * ux) - Fz * uz);
+    f[14] += oneOver12 * mu * (Fx * (1.0 + 2 * ux - 3 * uy) + Fy * (-1.0 + 2 * uy - 3 * ux) - Fz * uz);
+    f[15] += oneOver12 * mu * (Fx * (1.0 + 2 * ux + 3 * uz) - Fy * uy + Fz * (1.0 + 2 * uz + 3 * ux));
+    f[16] += oneOver12 * mu * (Fx * (1.0 + 2 * ux - 3 * uz) - Fy * uy + Fz * (-1.0 + 2 * uz - 3 * ux));
+    f[17] += -oneOver12 * mu * (Fx * ux + Fy * (-1.0 - 2 * uy - 3 * uz) + Fz * (-1.0 - 2 * uz - 3 * uy));
+    f[18] += -oneOver12 * mu * (Fx * ux + Fy * (-1.0 - 2 * uy + 3 * uz) + Fz * (1.0 - 2 * uz + 3 * uy));
+}
+
+__device__ __forceinline__ void d_apply_kind(double* f, int kind, double Fx, double Fy, double Fz, double c, double w0, double w1) {
+    if (kind == 0) {
+        d_collide(f, Fx, Fy, Fz, c, w0, w1);
+    } else if (kind == 2) {   // BounceBack::collide = swap i <-> i+9 (core/dynamics.hh:763-770)
+#pragma unroll
+        for (int i = 1; i <= 9; ++i) { double t = f[i]; f[i] = f[i + 9]; f[i + 9] = t; }
+    }                         // NoDynamics: populations are streamed untouched (core/dynamics.hh:940-943)
+}
+
+// Destination of population i pushed from (x,y,z) [x,y,z slab-local, storage plane = x+1]; returns false when the
+// population leaves through a non-periodic face (it then stays in the cell's own opposite slot), sets `crossed` when it
+// goes through a periodic face handled inside this slab.
+__device__ __forceinline__ bool d_dest(const LbmParams& p, int i, int x, int y, int z, long long& dst) {
+    int tx = x + c_cx[i], ty = y + c_cy[i], tz = z + c_cz[i];
+    if (tx < 0) { if (p.x_lo_mode == 1) tx = p.nx - 1; else if (p.x_lo_mode == 2) return false; }
+    else if (tx >= p.nx) { if (p.x_hi_mode == 1) tx = 0; else if (p.x_hi_mode == 2) return false; }
+    if (ty < 0) { if (p.per_y) ty = p.ny - 1; else return false; }
+    else if (ty >= p.ny) { if (p.per_y) ty = 0; else return false; }
+    if (tz < 0) { if (p.per_z) tz = p.nz - 1; else return false; }
+    else if (tz >= p.nz) { if (p.per_z) tz = 0; else return false; }
+    dst = (long long)(tx + 1) * p.plane + (long long)ty * p.nz + tz;
+    return true;
+}
+
+template <bool HAS_KIND>
+__global__ void __launch_bounds__(256) k_collide_stream(const LbmParams p) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= p.nz) return;
+    const int y = blockIdx.y, x = blockIdx.z;
+    const long long idx = (long long)(x + 1) * p.plane + (long long)y * p.nz + z;
+
+    double f[BIB_Q];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) f[i] = __ldg(p.fin + (long long)i * p.vol + idx);
+    const double Fx = __ldg(p.force + idx), Fy = __ldg(p.force + p.vol + idx), Fz = __ldg(p.force + 2 * p.vol + idx);
+    const double c = (double)(__ldg(p.phase + idx) & 1);
+    const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
+    d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega0, p.omega1);
+
+    const bool interior = (y > 0) & (y < p.ny - 1) & (z > 0) & (z < p.nz - 1) &
+                          ((x > 0) | (p.x_lo_mode == 0)) & ((x < p.nx - 1) | (p.x_hi_mode == 0));
+    if (interior) {
+#pragma unroll
+        for (int i = 0; i < BIB_Q; ++i) {
+            const long long dst = idx + (long long)c_cx[i] * p.plane + (long long)c_cy[i] * p.nz + c_cz[i];
+            p.fout[(long long)i * p.vol + dst] = f[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < BIB_Q; ++i) {
+            long long dst;
+            if (d_dest(p, i, x, y, z, dst)) p.fout[(long long)i * p.vol + dst] = f[i];
+            else p.fout[(long long)d_opp(i) * p.vol + idx] = f[i];
+        }
+    }
+}
+
+// Envelope quirk: populations that cross a periodic face come from a collision with (omega, omega_inner) swapped
+// (DESIGN.md "reference quirks"; core/dynamicsIdentifiers.h:131-141 of the reference). Runs after k_collide_stream over the
+// cells of the periodic faces only and overwrites just the crossing populations.
+struct FaceParams {
+    LbmParams p;
+    int face_dim;     // 0,1,2
+    int face_side;    // 0 = low, 1 = high
+    int swap_x_lo, swap_x_hi;   // is this slab's x face a GLOBAL periodic face
+};
+
+template <bool HAS_KIND>
+__global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
+    const LbmParams& p = q.p;
+    // enumerate the cells of one face: (a, b) over the two other dimensions
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    int x, y, z;
+    if (q.face_dim == 0) { x = q.face_side ? p.nx - 1 : 0; y = b; z = a; if (a >= p.nz) return; }
+    else if (q.face_dim == 1) { y = q.face_side ? p.ny - 1 : 0; x = b; z = a; if (a >= p.nz) return; }
+    else { z = q.face_side ? p.nz - 1 : 0; x = b; y = a; if (a >= p.ny) return; }
+    // a cell on several periodic faces is handled once, by the first (dim, side) that contains it
+    const bool on_xlo = (x == 0) && q.swap_x_lo, on_xhi = (x == p.nx - 1) && q.swap_x_hi;
+    const bool on_ylo = (y == 0) && p.per_y, on_yhi = (y == p.ny - 1) && p.per_y;
+    const bool on_zlo = (z == 0) && p.per_z, on_zhi = (z == p.nz - 1) && p.per_z;
+    if (q.face_dim == 0 && q.face_side == 1 && on_xlo) return;
+    if (q.face_dim == 1 && (on_xlo || on_xhi || (q.face_side == 1 && on_ylo))) return;
+    if (q.face_dim == 2 && (on_xlo || on_xhi || on_ylo || on_yhi || (q.face_side == 1 && on_zlo))) return;
+
+    const long long idx = (long long)(x + 1) * p.plane + (long long)y * p.nz + z;
+    double f[BIB_Q];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) f[i] = __ldg(p.fin + (long long)i * p.vol + idx);
+    const double Fx = __ldg(p.force + idx), Fy = __ldg(p.force + p.vol + idx), Fz = __ldg(p.force + 2 * p.vol + idx);
+    const double c = (double)(__ldg(p.phase + idx) & 1);
+    const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
+    d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega1, p.omega0);   // swapped
+#pragma unroll
+    for (int i = 1; i < BIB_Q; ++i) {
+        const int tx = x + c_cx[i], ty = y + c_cy[i], tz = z + c_cz[i];
+        const bool cross = (tx < 0 && q.swap_x_lo) || (tx >= p.nx && q.swap_x_hi) ||
+                           ((ty < 0 || ty >= p.ny) && p.per_y) || ((tz < 0 || tz >= p.nz) && p.per_z);
+        if (!cross) continue;
+        long long dst;
+        if (d_dest(p, i, x, y, z, dst)) p.fout[(long long)i * p.vol + dst] = f[i];
+        // (a population that also leaves through a non-periodic face is bounced from the bulk collision: untouched)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- transposes & side passes
+// host AoS [x][y][z][23] (staged in device memory) <-> device SoA. One thread per (cell, component).
+__global__ void k_unpack_cells(const double* __restrict__ aos, double* f, double* force, uint8_t* phase, int* bad_phase,
+                               int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        const double* c = aos + t * 23;
+        for (int i = 0; i < BIB_Q; ++i) f[(long long)i * vol + idx] = c[i];
+        for (int k = 0; k < 3; ++k) force[(long long)k * vol + idx] = c[BIB_Q + k];
+        const double ph = c[BIB_Q + 3];
+        if (ph != 0.0 && ph != 1.0) atomicAdd(bad_phase, 1);
+        phase[idx] = (ph != 0.0) ? 1 : 0;
+    }
+}
+__global__ void k_pack_cells(double* __restrict__ aos, const double* f, const double* force, const uint8_t* phase,
+                             int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        double* c = aos + t * 23;
+        for (int i = 0; i < BIB_Q; ++i) c[i] = f[(long long)i * vol + idx];
+        for (int k = 0; k < 3; ++k) c[BIB_Q + k] = force[(long long)k * vol + idx];
+        c[BIB_Q + 3] = (double)(phase[idx] & 1);
+    }
+}
+__global__ void k_set_external(double* force, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz,
+                               double fx, double fy, double fz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        force[idx] = fx; force[vol + idx] = fy; force[2 * vol + idx] = fz;
+    }
+}
+__global__ void k_velocity(const double* __restrict__ f, const double* __restrict__ force, double* vel,
+                           int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        double c[BIB_Q];
+#pragma unroll
+        for (int i = 0; i < BIB_Q; ++i) c[i] = f[(long long)i * vol + idx];
+        double rhoBar, jx, jy, jz;
+        d_rhoBar_j(c, rhoBar, jx, jy, jz);
+        const double invRho = 1.0 / (rhoBar + 1.0);
+        vel[idx] = jx * invRho + force[idx] / 2.0;
+        vel[vol + idx] = jy * invRho + force[vol + idx] / 2.0;
+        vel[2 * vol + idx] = jz * invRho + force[2 * vol + idx] / 2.0;
+    }
+}
+__global__ void k_pack_velocity(double* __restrict__ out, const double* vel, int bx0, int by0, int bz0, int bnx, int bny, int bnz,
+                                long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        out[t * 3] = vel[idx]; out[t * 3 + 1] = vel[vol + idx]; out[t * 3 + 2] = vel[2 * vol + idx];
+    }
+}
+__global__ void k_set_kind(uint8_t* kind, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, int nz, uint8_t v) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        kind[(long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0)] = v;
+    }
+}
+
+struct Eq19 { double v[BIB_Q]; };
+__global__ void k_fill_populations(double* f, Eq19 eq, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+#pragma unroll
+        for (int i = 0; i < BIB_Q; ++i) f[(long long)i * vol + idx] = eq.v[i];
+    }
+}
+
+bool box_ok(const bib_domain* d, const int box[6]) {
+    return box[0] >= 0 && box[1] < d->nx && box[0] <= box[1] && box[2] >= 0 && box[3] < d->ny && box[2] <= box[3] &&
+           box[4] >= 0 && box[5] < d->nz && box[4] <= box[5];
+}
+int grid_for(long long n, int bs) {
+    long long g = (n + bs - 1) / bs;
+    const long long cap = 148LL * 16;   // grid-stride loops: a few waves over the 148 SMs
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+bool ensure_scratch(bib_domain* d, size_t bytes) {
+    if (d->scratch_bytes >= bytes) return true;
+    if (d->scratch) cudaFree(d->scratch);
+    d->scratch = nullptr; d->scratch_bytes = 0;
+    if (!bib_cuda_ok(cudaMalloc(&d->scratch, bytes), "cudaMalloc(scratch)")) return false;
+    d->scratch_bytes = bytes;
+    return true;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------- host launchers
+static LbmParams make_params(bib_domain* d) {
+    LbmParams p;
+    p.fin = d->f[d->cur]; p.fout = d->f[1 - d->cur];
+    p.force = d->force; p.phase = d->phase; p.kind = d->kind;
+    p.nx = d->nx; p.ny = d->ny; p.nz = d->nz;
+    p.plane = (long long)d->plane; p.vol = (long long)d->vol;
+    p.omega0 = d->omega0; p.omega1 = d->omega1;
+    p.per_y = d->per[1]; p.per_z = d->per[2];
+    const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
+    if (d->n_ranks == 1) { p.x_lo_mode = p.x_hi_mode = d->per[0] ? 1 : 2; }
+    else {
+        p.x_lo_mode = (first && !d->per[0]) ? 2 : 0;
+        p.x_hi_mode = (last && !d->per[0]) ? 2 : 0;
+    }
+    return p;
+}
+
+int lbm_launch_collide_stream(bib_domain* d) {
+    LbmParams p = make_params(d);
+    int bs = d->nz >= 256 ? 256 : ((d->nz + 31) / 32) * 32;
+    dim3 grid((d->nz + bs - 1) / bs, d->ny, d->nx);
+    if (d->kind) k_collide_stream<true><<<grid, bs, 0, d->stream>>>(p);
+    else k_collide_stream<false><<<grid, bs, 0, d->stream>>>(p);
+    d->launches++;
+    if (d->envelope_swap) {
+        FaceParams q; q.p = p;
+        const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
+        q.swap_x_lo = d->per[0] && first; q.swap_x_hi = d->per[0] && last;
+        for (int dim = 0; dim < 3; ++dim) for (int side = 0; side < 2; ++side) {
+            bool active = dim == 0 ? (side == 0 ? q.swap_x_lo : q.swap_x_hi) : (dim == 1 ? d->per[1] : d->per[2]);
+            if (!active) continue;
+            q.face_dim = dim; q.face_side = side;
+            const int na = dim == 2 ? d->ny : d->nz, nb = dim == 0 ? d->ny : d->nx;
+            dim3 g((na + 127) / 128, nb);
+            if (d->kind) k_face_swap<true><<<g, 128, 0, d->stream>>>(q);
+            else k_face_swap<false><<<g, 128, 0, d->stream>>>(q);
+            d->launches++;
+        }
+    }
+    BIB_CHECK(cudaGetLastError());
+    d->cur = 1 - d->cur;
+    if (d->n_ranks > 1) return comm_halo_exchange(d);
+    return 1;
+}
+
+int lbm_launch_upload(bib_domain* d, const int box[6], const double* cells) {
+    if (!box_ok(d, box)) { bib_set_error("upload: box outside the slab"); return 0; }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    const long long n = (long long)bnx * bny * bnz;
+    // staged in chunks of x-planes so that very large slabs do not need a second full copy in HBM
+    const long long per_plane = (long long)bny * bnz;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * 23 * 8) + 1));
+    if (!ensure_scratch(d, (size_t)chunk * per_plane * 23 * 8 + 16)) return 0;
+    int* bad = (int*)((char*)d->scratch + (size_t)chunk * per_plane * 23 * 8);
+    BIB_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), d->stream));
+    for (int x0 = 0; x0 < bnx; x0 += chunk) {
+        const int cn = std::min(chunk, bnx - x0);
+        BIB_CHECK(cudaMemcpyAsync(d->scratch, cells + (size_t)x0 * per_plane * 23, (size_t)cn * per_plane * 23 * 8, cudaMemcpyHostToDevice, d->stream));
+        k_unpack_cells<<<grid_for(cn * per_plane, 256), 256, 0, d->stream>>>((const double*)d->scratch, d->f[d->cur], d->force, d->phase, bad,
+                                                                          box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz);
+        d->launches++;
+    }
+    int h_bad = 0;
+    BIB_CHECK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    (void)n;
+    if (h_bad) { bib_set_error("upload: phase scalar must be exactly 0.0 or 1.0 (it is stored as one byte)"); return 0; }
+    return 1;
+}
+
+int lbm_launch_download(bib_domain* d, const int box[6], double* cells) {
+    if (!box_ok(d, box)) { bib_set_error("download: box outside the slab"); return 0; }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    const long long per_plane = (long long)bny * bnz;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * 23 * 8) + 1));
+    if (!ensure_scratch(d, (size_t)chunk * per_plane * 23 * 8 + 16)) return 0;
+    for (int x0 = 0; x0 < bnx; x0 += chunk) {
+        const int cn = std::min(chunk, bnx - x0);
+        k_pack_cells<<<grid_for(cn * per_plane, 256), 256, 0, d->stream>>>((double*)d->scratch, d->f[d->cur], d->force, d->phase,
+                                                                        box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz);
+        d->launches++;
+        BIB_CHECK(cudaMemcpyAsync(cells + (size_t)x0 * per_plane * 23, d->scratch, (size_t)cn * per_plane * 23 * 8, cudaMemcpyDeviceToHost, d->stream));
+    }
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}
+
+int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double fy, double fz) {
+    if (!box_ok(d, box)) { bib_set_error("set_external_vector: box outside the slab"); return 0; }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    k_set_external<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->force, box[0], box[2], box[4], bnx, bny, bnz,
+                                                                                  (long long)d->plane, (long long)d->vol, d->nz, fx, fy, fz);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int lbm_launch_velocity(bib_domain* d, const int box[6]) {
+    if (!box_ok(d, box)) { bib_set_error("compute_velocity: box outside the slab"); return 0; }
+    if (!d->vel) {
+        BIB_CHECK(cudaMalloc(&d->vel, d->vol * 3 * sizeof(double)));
+        BIB_CHECK(cudaMemsetAsync(d->vel, 0, d->vol * 3 * sizeof(double), d->stream));
+        d->bytes += (long long)d->vol * 3 * 8;
+    }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    k_velocity<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->f[d->cur], d->force, d->vel, box[0], box[2], box[4], bnx, bny, bnz,
+                                                                              (long long)d->plane, (long long)d->vol, d->nz);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity) {
+    if (!box_ok(d, box)) { bib_set_error("velocity_download: box outside the slab"); return 0; }
+    if (!d->vel) { bib_set_error("velocity_download: call bib_compute_velocity first"); return 0; }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    const long long n = (long long)bnx * bny * bnz;
+    if (!ensure_scratch(d, (size_t)n * 3 * 8)) return 0;
+    k_pack_velocity<<<grid_for(n, 256), 256, 0, d->stream>>>((double*)d->scratch, d->vel, box[0], box[2], box[4], bnx, bny, bnz,
+                                                          (long long)d->plane, (long long)d->vol, d->nz);
+    d->launches++;
+    BIB_CHECK(cudaMemcpyAsync(velocity, d->scratch, (size_t)n * 3 * 8, cudaMemcpyDeviceToHost, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}
+
+int lbm_set_celltype(bib_domain* d, const int box[6], int kind) {
+    if (!box_ok(d, box)) { bib_set_error("set_celltype: box outside the slab"); return 0; }
+    if (kind < 0 || kind > 2) { bib_set_error("set_celltype: unknown kind"); return 0; }
+    if (!d->kind) {
+        BIB_CHECK(cudaMalloc(&d->kind, d->vol));
+        BIB_CHECK(cudaMemsetAsync(d->kind, 0, d->vol, d->stream));
+        d->bytes += (long long)d->vol;
+    }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    k_set_kind<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->kind, box[0], box[2], box[4], bnx, bny, bnz, (long long)d->plane, d->nz, (uint8_t)kind);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// bgk_ma2_equilibrium (src/latticeBoltzmann/dynamicsTemplates3D.h:675-678) for constant (rho, u), evaluated once on the host
+int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz) {
+    if (!box_ok(d, box)) { bib_set_error("init_equilibrium: box outside the slab"); return 0; }
+    static const int c[BIB_Q][3] = {{0, 0, 0}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {0, -1, -1}, {0, -1, 1},
+                                    {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, -1, 0}, {1, 0, 1}, {1, 0, -1}, {0, 1, 1}, {0, 1, -1}};
+    static const double t[BIB_Q] = {1. / 3, 1. / 18, 1. / 18, 1. / 18, 1. / 36, 1. / 36, 1. / 36, 1. / 36, 1. / 36, 1. / 36,
+                                    1. / 18, 1. / 18, 1. / 18, 1. / 36, 1. / 36, 1. / 36, 1. / 36, 1. / 36, 1. / 36};
+    const double j[3] = {rho * ux, rho * uy, rho * uz};
+    const double jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+    const double rhoBar = rho - 1.0, invRho = 1.0 / (rhoBar + 1.0);
+    Eq19 eq;
+    for (int i = 0; i < BIB_Q; ++i) {
+        const double c_j = c[i][0] * j[0] + c[i][1] * j[1] + c[i][2] * j[2];
+        eq.v[i] = t[i] * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
+    }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    k_fill_populations<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->f[d->cur], eq, box[0], box[2], box[4], bnx, bny, bnz,
+                                                                                       (long long)d->plane, (long long)d->vol, d->nz);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}

@@ -1,0 +1,114 @@
+/* biblbm_b200.h -- C-ABI of the B200-native hot path of niclasberg/biblbm.
+ *
+ * One handle = one x-slab of the global lattice resident on one GPU (a single GPU holds the whole lattice).
+ * Every entry point returns 1 on success and 0 on failure, like the reference's own accelerator seam
+ * plb::CoProcessor3D<T> (reference src/coProcessors/coProcessor3D.h:57-115, "return 1 = success, 0 = failure" :74,79,95);
+ * bib_last_error() describes the last failure of the calling thread. Nothing here throws, owns host memory passed in,
+ * or falls back to a CPU path: without a CUDA device bib_domain_create fails.
+ *
+ * Host data layouts are the reference's own:
+ *   cells   : Palabos serialised cells, C order [x][y][z], per cell 19 fBar populations (f_i - t_i) in D3Q19Constants
+ *             order followed by the descriptor's external scalars {Fx,Fy,Fz,phase}
+ *             (reference src/atomicBlock/blockLattice3D.hh:671-689, src/core/cell.hh:103-121,
+ *              src/fsi/VariableViscosityDynamics.h:25-42) = what BlockLatticeDataTransfer3D::send(staticVariables) and
+ *             CoProcessor3D::send/receive carry (src/coProcessors/coProcessorCommunication3D.hh:46-50,84-90);
+ *   velocity: TensorField3D<T,3>, [x][y][z][3] (reference src/atomicBlock/dataField3D.hh:272-281);
+ *   vertices: fsi::Vertex<T> = {pos[3], vel[3], force[3]} (reference src/fsi/ParticleBase.h:32-37).
+ * Boxes are inclusive {x0,x1,y0,y1,z0,z1} like plb::Box3D, in slab-local coordinates (x0 = 0 is the slab's first plane).
+ */
+#ifndef BIBLBM_B200_H
+#define BIBLBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bib_domain bib_domain;   /* opaque */
+
+/* cell kinds for bib_domain_set_celltype (reference: background dynamics / plb::NoDynamics / plb::BounceBack,
+ * src/core/dynamics.hh:763-770,940-943) */
+enum { BIB_CELL_BULK = 0, BIB_CELL_NODYNAMICS = 1, BIB_CELL_BOUNCEBACK = 2 };
+
+/* particle types for bib_ib_particles_add (reference: fsi::RBCParticle, src/fsi/RBCParticle.h:68-100) */
+enum { BIB_PARTICLE_RBC = 0 };
+
+/* bib_domain_set_option keys */
+enum {
+    BIB_OPT_ENVELOPE_SWAP = 1,       /* 1 (default): reproduce the reference's periodic-envelope (omega,omega_inner) swap, see DESIGN.md */
+    BIB_OPT_DETERMINISTIC_SPREAD = 2,/* 1: spread forces in the reference's vertex order (slow, bit-exact); 0 (default): fp64 atomics */
+    BIB_OPT_REGULATOR = 3            /* enable ParticlePositionRegulator (value = p, then target x,y,z via bib_ib_set_regulator) */
+};
+
+const char* bib_last_error(void);
+int bib_version(void);
+int bib_device_count(int* count);
+
+/* ---- lattice (replaces CoProcessor3D::addDomain / send / receive / collideAndStream, coProcessor3D.h:71-109, and
+ *      MultiBlockLattice3D<double,ForcedPhaseD3Q19Descriptor>::collideAndStream, src/multiBlock/multiBlockLattice3D.hh:306-348)
+ * nx,ny,nz: size of THIS slab (x is the slab direction); periodic[3]: global periodicity (x periodicity of a multi-slab
+ * domain is realised by the halo exchange, see bib_comm_*). n_ext must be 4 (ForcedPhaseD3Q19Descriptor). */
+int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner,
+                      const int periodic[3], int device, bib_domain** out);
+int bib_domain_destroy(bib_domain* d);
+int bib_domain_set_option(bib_domain* d, int key, double value);
+int bib_domain_upload(bib_domain* d, const int box[6], const double* cells);
+int bib_domain_download(bib_domain* d, const int box[6], double* cells);
+int bib_domain_set_celltype(bib_domain* d, const int box[6], int kind);
+/* initializeAtEquilibrium(lattice, domain, rho, velocity): constant density/velocity equilibrium fill on the device
+ * (reference src/dataProcessors/dataInitializerWrapper3D.hh:327-329, dataInitializerFunctional3D.hh:847-866) */
+int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz);
+
+/* F7: setExternalVector(lattice, domain, forceBeginsAt, F)   (src/dataProcessors/dataInitializerFunctional3D.hh:1144-1154) */
+int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz);
+/* F6: computeVelocity(lattice, velocity, domain)             (src/dataProcessors/dataAnalysisFunctional3D.hh:772-784) */
+int bib_compute_velocity(bib_domain* d, const int box[6]);
+int bib_velocity_download(bib_domain* d, const int box[6], double* velocity);
+/* F1-F5: one lattice.collideAndStream() */
+int bib_collide_and_stream(bib_domain* d);
+
+/* ---- immersed boundary (replaces ImmersedBoundaryDynamics3D::{add_particle, init, interpolate_velocity,
+ *      compute_and_spread_forces, move_vertices_and_revoxelize}, src/fsi/ImmersedBoundaryDynamics.h:83-85, driven through
+ *      ImmersedBoundaryWrapperFunctional3D::process, src/fsi/DataProcessors.hh:94-108) */
+/* builds links / rest lengths / adjacent-triangle pairs / rest angles exactly like ParticleShape (src/fsi/ParticleShape.hh:22-184) */
+int bib_ib_shape_register(bib_domain* d, int nv, int nt, const double* vertices, const int* triangles, int* shape_id);
+int bib_ib_shape_info(bib_domain* d, int shape_id, int* n_links, int* n_pairs, double* area, double* volume);
+int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* link_len, int* pairs, double* pair_cos_sin, double* tri_area);
+/* params for BIB_PARTICLE_RBC: {shear_modulus, L0, k_area_global, k_area_local, k_volume, vol_desired, k_bend, theta0}
+ * (RBCParameters, src/fsi/RBCParticle.h:23-60). positions: [n][nv][3]. Particles get ids in order of addition. */
+int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
+int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz);
+int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices);
+/* the three phases of the wrapper functional, in its order, and all three at once */
+int bib_ib_interpolate_velocity(bib_domain* d);
+int bib_ib_compute_and_spread_forces(bib_domain* d);
+int bib_ib_move_vertices_and_revoxelize(bib_domain* d);
+int bib_ib_step(bib_domain* d);
+int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9);
+int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
+/* per particle {area, volume, com[3], bbox x0,x1,y0,y1,z0,z1} (ParticleBase3D::area/volume/center_of_mass/bounding_box) */
+int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11);
+
+/* ---- one whole driver time step, in the order every reference driver issues it
+ *      (progs/rbc_in_shear/rbc_in_shear.cpp:154-186): computeVelocity -> setExternalVector(body) -> IB wrapper ->
+ *      collideAndStream, repeated n_steps times without host synchronisation. */
+int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps);
+
+/* ---- multi-GPU: x-slab ring over NCCL (replaces ParallelBlockCommunicator3D::duplicateOverlaps,
+ *      src/parallelism/parallelBlockCommunicator3D.cpp:144-233). unique_id: the 128 bytes of an ncclUniqueId. */
+int bib_comm_unique_id(void* unique_id_128);
+int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128);
+
+/* ---- stream / timing */
+int bib_sync(bib_domain* d);
+int bib_time_begin(bib_domain* d);                 /* records a CUDA event on the domain's stream */
+int bib_time_end(bib_domain* d, float* milliseconds);  /* records a second event, waits, returns elapsed device time */
+int bib_kernel_launch_count(bib_domain* d, long long* launches);   /* kernels launched by this library on this domain so far */
+int bib_device_memory_bytes(bib_domain* d, long long* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

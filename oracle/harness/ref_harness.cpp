@@ -288,7 +288,10 @@ static int run(const Config& cfg) {
         lattice.periodicity().toggle(0, Periodicity::get_x());
         lattice.periodicity().toggle(1, Periodicity::get_y());
         lattice.periodicity().toggle(2, Periodicity::get_z());
-        initializeAtEquilibrium(lattice, domain, SineInit<double>(nx, ny, nz, cfg.num("u0", 0.05)));
+        if (cfg.str("init", "sine") == "uniform")
+            initializeAtEquilibrium(lattice, domain, cfg.num("rho", 1.0), Array<double, 3>(cfg.num("ux", 0), cfg.num("uy", 0), cfg.num("uz", 0)));
+        else
+            initializeAtEquilibrium(lattice, domain, SineInit<double>(nx, ny, nz, cfg.num("u0", 0.05)));
         lattice.initialize();
     }
 

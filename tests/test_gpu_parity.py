@@ -1,0 +1,234 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against (a) the committed golden dumps of the
+unmodified reference, (b) the CPU oracle on fresh seeded inputs, (c) size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): per-step populations <= 1e-12 relative, velocity field / vertex positions after
+1000 steps <= 1e-9 relative. Everything that does not involve the atomic force spread is in fact required to be
+BIT-EXACT here (the library is built without FMA contraction and mirrors the reference's operation order)."""
+import numpy as np
+import pytest
+
+import biblbm_b200 as bib
+import kit
+
+pytestmark = pytest.mark.gpu
+
+TOL_POP = 1e-12
+TOL_1000 = 1e-9
+
+
+def make_lattice(cells, per, omega, omega_inner, **opts):
+    nx, ny, nz, _ = cells.shape
+    lat = bib.Lattice(nx, ny, nz, omega, omega_inner, periodic=tuple(bool(p) for p in per))
+    for k, v in opts.items():
+        lat.set_option(k, v)
+    lat.upload(cells)
+    return lat
+
+
+def test_upload_download_roundtrip():
+    rng = np.random.default_rng(0)
+    cells = rng.normal(size=(7, 5, 9, 23))
+    cells[..., 22] = rng.integers(0, 2, size=(7, 5, 9))
+    lat = make_lattice(cells, (1, 1, 1), 1.0, 0.5)
+    assert np.array_equal(lat.download(), cells)
+    sub = (2, 4, 1, 3, 0, 8)
+    assert np.array_equal(lat.download(sub), cells[2:5, 1:4, 0:9])
+    patch = rng.normal(size=(3, 3, 9, 23)); patch[..., 22] = 1.0
+    lat.upload(patch, sub)
+    cells[2:5, 1:4, 0:9] = patch
+    assert np.array_equal(lat.download(), cells)
+    bad = cells.copy(); bad[0, 0, 0, 22] = 0.5
+    with pytest.raises(bib.BibError, match="phase"):
+        lat.upload(bad)
+
+
+@pytest.mark.parametrize("name", ["lbm_periodic", "lbm_walls"])
+def test_collide_and_stream_vs_golden(name):
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]))
+    for s in range(1, 11):
+        lat.collideAndStream()
+        if f"pop_{s}" in g:
+            got = lat.download()
+            assert kit.rel_err(got[..., :19], g[f"pop_{s}"][..., :19]) <= TOL_POP
+            assert np.array_equal(got, g[f"pop_{s}"]), f"{name} step {s}: not bit-identical to the reference"
+
+
+@pytest.mark.parametrize("per", [(1, 1, 1), (1, 0, 1), (0, 0, 0), (0, 1, 0)])
+@pytest.mark.parametrize("swap", [True, False])
+def test_collide_and_stream_vs_oracle(orc, per, swap):
+    rng = np.random.default_rng(11)
+    nx, ny, nz = 19, 9, 37            # ragged sizes: nz not a multiple of the warp size
+    cells = np.zeros((nx, ny, nz, 23))
+    cells[..., :19] = 0.01 * rng.normal(size=(nx, ny, nz, 19))
+    cells[..., 19:22] = 1e-4 * rng.normal(size=(nx, ny, nz, 3))
+    cells[..., 22] = rng.integers(0, 2, size=(nx, ny, nz))
+    lat = make_lattice(cells, per, 1.6, 0.7, **{bib.OPT_ENVELOPE_SWAP: float(swap)})
+    ref = cells
+    for _ in range(4):
+        lat.collideAndStream()
+        ref = orc.collide_and_stream(ref, per, 1.6, 0.7, envelope_swap=swap)
+    assert np.array_equal(lat.download(), ref)
+
+
+def test_cell_kinds_vs_oracle(orc):
+    rng = np.random.default_rng(12)
+    nx, ny, nz = 10, 12, 33
+    cells = np.zeros((nx, ny, nz, 23))
+    cells[..., :19] = 0.01 * rng.normal(size=(nx, ny, nz, 19))
+    cells[..., 22] = rng.integers(0, 2, size=(nx, ny, nz))
+    kind = np.zeros((nx, ny, nz), dtype=np.uint8)
+    kind[:, 0, :] = bib.CELL_BOUNCEBACK
+    kind[:, -1, :] = bib.CELL_NODYNAMICS
+    kind[3:5, 4:7, 10:20] = bib.CELL_BOUNCEBACK
+    lat = make_lattice(cells, (1, 0, 1), 1.2, 0.9)
+    lat.defineDynamics((0, nx - 1, 0, 0, 0, nz - 1), bib.CELL_BOUNCEBACK)
+    lat.defineDynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), bib.CELL_NODYNAMICS)
+    lat.defineDynamics((3, 4, 4, 6, 10, 19), bib.CELL_BOUNCEBACK)
+    ref = cells
+    for _ in range(3):
+        lat.collideAndStream()
+        ref = orc.collide_and_stream(ref, (1, 0, 1), 1.2, 0.9, kind=kind)
+    assert np.array_equal(lat.download(), ref)
+
+
+def test_velocity_and_external_vector(orc):
+    g = np.load(kit.GOLDEN / "lbm_periodic.npz")
+    lat = make_lattice(g["pop_1"], g["per"], 1.0, 0.5)
+    assert np.array_equal(lat.computeVelocity(), orc.compute_velocity(g["pop_1"].copy()))
+    lat.setExternalVector((1e-5, -2e-5, 3e-5), box=(1, 3, 0, 9, 2, 5))
+    ref = g["pop_1"].copy()
+    ref[1:4, :, 2:6, 19:22] = (1e-5, -2e-5, 3e-5)
+    assert np.array_equal(lat.download(), ref)
+
+
+def test_shape_connectivity_matches_reference(rbc):
+    shape, _, _, z = rbc
+    lat = bib.Lattice(4, 4, 4, 1.0, 1.0)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    c = lat.shape_connectivity(sid)
+    assert np.array_equal(c["links"], z["links"]) and np.array_equal(c["link_len"], z["link_len"])
+    assert np.array_equal(c["pairs"], z["pairs"]) and np.array_equal(c["pair_cs"], z["pair_cs"])
+    assert np.array_equal(c["tri_area"], z["tri_area"])
+    assert c["area"] == z["scalars"][0] and c["volume"] == z["scalars"][1]
+
+
+def run_ib_case(g, shape, params, deterministic):
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]),
+                       **{bib.OPT_DETERMINISTIC_SPREAD: float(deterministic)})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, g["vert_init"][..., :3])
+    if float(g["regulator_p"]) != 0.0:
+        lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
+    return lat
+
+
+@pytest.mark.parametrize("name", ["ib_rbc1", "ib_rbc2_pfp"])
+def test_full_step_deterministic_bit_exact(rbc, name):
+    """Whole driver step with the spread done in the reference's vertex order: every dumped quantity is bit-identical."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    lat = run_ib_case(g, shape, params, deterministic=True)
+    n_p, nv = g["vert_init"].shape[:2]
+    assert np.array_equal(lat.particle_scalars(), g["part_init"])
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step(g["body"])
+        assert np.array_equal(lat.vertices().reshape(n_p, nv, 9), g[f"vert_{s}"]), f"{name}: vertices differ at step {s}"
+        assert np.array_equal(lat.particle_scalars(), g[f"part_{s}"])
+    assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
+
+
+@pytest.mark.parametrize("name", ["ib_rbc1", "ib_rbc2_pfp"])
+def test_full_step_atomic_spread(rbc, name):
+    """Production path (fp64 atomics reorder the force sums): parity within the per-step tolerance."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    lat = run_ib_case(g, shape, params, deterministic=False)
+    n_p, nv = g["vert_init"].shape[:2]
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step(g["body"])
+        v = lat.vertices().reshape(n_p, nv, 9)
+        assert kit.rel_err(v[..., :3], g[f"vert_{s}"][..., :3]) <= TOL_POP
+        assert kit.rel_err(v[..., 3:6], g[f"vert_{s}"][..., 3:6]) <= 1e-11
+        assert kit.rel_err(v[..., 6:], g[f"vert_{s}"][..., 6:]) <= 1e-10
+    got = lat.download()[::2, ::2, ::2]
+    assert kit.rel_err(got[..., :19], g["pop_final_sample"][..., :19]) <= TOL_POP
+    assert np.array_equal(got[..., 22], g["pop_final_sample"][..., 22])
+
+
+def test_ib_phases_through_reference_call_sequence(orc, rbc):
+    """The four separate driver calls (computeVelocity, setExternalVector, the three IB phases, collideAndStream) give
+    the same state as bib_step and as the oracle."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc1.npz")
+    lat = run_ib_case(g, shape, params, deterministic=True)
+    for s in range(1, 3):
+        lat.computeVelocity(download=False)
+        lat.interpolate_velocity()
+        lat.setExternalVector(g["body"])
+        lat.compute_and_spread_forces()
+        lat.move_vertices_and_revoxelize()
+        lat.collideAndStream()
+        assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"])
+
+
+def test_1000_steps_vs_oracle(orc, rbc):
+    """north_star: velocity field and membrane vertex positions after 1000 steps within 1e-9 relative (atomic spread)."""
+    shape, params, rbc_pos, _ = rbc
+    dims, per = (32, 30, 28), (1, 1, 1)
+    pos = kit.place_particles(rbc_pos, [(15.5, 14.2, 13.1)], seed=4)
+    body = (3e-6, 0.0, 1e-6)
+    rng = np.random.default_rng(5)
+    cells = np.zeros(dims + (23,))
+    x, y, z = np.meshgrid(*[np.arange(n) for n in dims], indexing="ij")
+    u = 0.02 * np.stack([np.sin(2 * np.pi * y / dims[1]), np.sin(2 * np.pi * z / dims[2]), np.sin(2 * np.pi * x / dims[0])], -1)
+    cu = np.einsum("xyzd,id->xyzi", u, kit.C19.astype(float))
+    cells[..., :19] = kit.T19 * (3 * cu + 4.5 * cu ** 2 - 1.5 * (u ** 2).sum(-1, keepdims=True))
+    del rng
+    lat = make_lattice(cells, per, 1.0, 1 / 3)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    vert = np.zeros((1, shape.nv, 9)); vert[..., :3] = pos
+    state = np.array([orc.particle_update(shape, pos[0])])
+    ref = cells.copy()
+    for _ in range(1000):
+        orc.full_step(ref, per, 1.0, 1 / 3, body, shape, params, vert, state)
+    lat.step(body, n=1000)
+    got_v = lat.vertices().reshape(1, shape.nv, 9)
+    assert kit.rel_err(got_v[..., :3], vert[..., :3]) <= TOL_1000
+    got = lat.download()
+    assert kit.rel_err(lat.computeVelocity(), orc.compute_velocity(ref)) <= TOL_1000
+    assert kit.rel_err(got[..., :19], ref[..., :19]) <= TOL_1000
+    assert np.array_equal(got[..., 22], ref[..., 22])
+
+
+def test_mass_conservation_large():
+    """Size-independent property at a size the oracle is not run at: 192^3 periodic, no force, quirk off => sum(f) and
+    sum(c f) conserved to round-off over 20 steps."""
+    n = 192
+    rng = np.random.default_rng(3)
+    cells = np.zeros((n, n, n, 23))
+    cells[..., :19] = 1e-3 * rng.standard_normal((n, n, n, 19))
+    cells[..., 22] = (rng.random((n, n, n)) < 0.3)
+    m0 = cells[..., :19].sum()
+    j0 = np.einsum("xyzi,id->d", cells[..., :19], kit.C19.astype(float))
+    lat = make_lattice(cells, (1, 1, 1), 1.3, 0.5, **{bib.OPT_ENVELOPE_SWAP: 0.0})
+    lat.collideAndStream(20)
+    out = lat.download()
+    m1 = out[..., :19].sum()
+    j1 = np.einsum("xyzi,id->d", out[..., :19], kit.C19.astype(float))
+    assert abs(m1 - m0) <= 1e-9 * max(1.0, abs(m0)) and np.abs(j1 - j0).max() <= 1e-9 * max(1.0, np.abs(j0).max())
+
+
+def test_translation_invariance():
+    """Periodic box: stepping a state shifted by (3,5,7) cells equals shifting the stepped state (quirk off)."""
+    rng = np.random.default_rng(8)
+    dims = (24, 20, 40)
+    cells = np.zeros(dims + (23,))
+    cells[..., :19] = 1e-2 * rng.standard_normal(dims + (19,))
+    cells[..., 19:22] = 1e-5 * rng.standard_normal(dims + (3,))
+    cells[..., 22] = (rng.random(dims) < 0.5)
+    a = make_lattice(cells, (1, 1, 1), 1.1, 0.6, **{bib.OPT_ENVELOPE_SWAP: 0.0})
+    b = make_lattice(np.roll(cells, (3, 5, 7), axis=(0, 1, 2)), (1, 1, 1), 1.1, 0.6, **{bib.OPT_ENVELOPE_SWAP: 0.0})
+    a.collideAndStream(5); b.collideAndStream(5)
+    assert np.array_equal(np.roll(a.download(), (3, 5, 7), axis=(0, 1, 2)), b.download())
