@@ -152,8 +152,44 @@ __device__ __forceinline__ bool d_dest(const LbmParams& p, int i, int x, int y, 
     return true;
 }
 
-template <bool HAS_KIND>
-__global__ void __launch_bounds__(256) k_collide_stream(const LbmParams p) {
+// Per-thread neighbour offsets (relative to the cell's own index, in elements) with periodic wrap applied, plus wall
+// flags for faces through which nothing streams (non-periodic block faces: the population stays in the cell's opposite slot).
+struct Nbr {
+    int oxm, oxp, oym, oyp, ozm, ozp;
+    bool wxm, wxp, wym, wyp, wzm, wzp;
+};
+template <bool HAS_WALLS>
+__device__ __forceinline__ Nbr d_neighbours(const LbmParams& p, int x, int y, int z) {
+    Nbr n;
+    const int plane = (int)p.plane;
+    n.oxm = -plane; n.oxp = plane; n.oym = -p.nz; n.oyp = p.nz; n.ozm = -1; n.ozp = 1;
+    n.wxm = n.wxp = n.wym = n.wyp = n.wzm = n.wzp = false;
+    if (x == 0) { if (p.x_lo_mode == 1) n.oxm = (p.nx - 1) * plane; else if (HAS_WALLS && p.x_lo_mode == 2) n.wxm = true; }
+    if (x == p.nx - 1) { if (p.x_hi_mode == 1) n.oxp = -(p.nx - 1) * plane; else if (HAS_WALLS && p.x_hi_mode == 2) n.wxp = true; }
+    if (y == 0) { if (p.per_y) n.oym = (p.ny - 1) * p.nz; else if (HAS_WALLS) n.wym = true; }
+    if (y == p.ny - 1) { if (p.per_y) n.oyp = -(p.ny - 1) * p.nz; else if (HAS_WALLS) n.wyp = true; }
+    if (z == 0) { if (p.per_z) n.ozm = p.nz - 1; else if (HAS_WALLS) n.wzm = true; }
+    if (z == p.nz - 1) { if (p.per_z) n.ozp = -(p.nz - 1); else if (HAS_WALLS) n.wzp = true; }
+    return n;
+}
+
+// push population I (compile-time direction) of the cell at idx
+template <int I, bool HAS_WALLS>
+__device__ __forceinline__ void d_push(const LbmParams& p, const Nbr& n, long long idx, double v) {
+    constexpr int cx = (I == 1 || I == 4 || I == 5 || I == 6 || I == 7) ? -1 : ((I == 10 || I == 13 || I == 14 || I == 15 || I == 16) ? 1 : 0);
+    constexpr int cy = (I == 2 || I == 4 || I == 8 || I == 9 || I == 14) ? -1 : ((I == 5 || I == 11 || I == 13 || I == 17 || I == 18) ? 1 : 0);
+    constexpr int cz = (I == 3 || I == 6 || I == 8 || I == 16 || I == 18) ? -1 : ((I == 7 || I == 9 || I == 12 || I == 15 || I == 17) ? 1 : 0);
+    constexpr int OPP = I == 0 ? 0 : (I <= 9 ? I + 9 : I - 9);
+    if (HAS_WALLS) {
+        const bool blocked = (cx < 0 && n.wxm) || (cx > 0 && n.wxp) || (cy < 0 && n.wym) || (cy > 0 && n.wyp) || (cz < 0 && n.wzm) || (cz > 0 && n.wzp);
+        if (blocked) { p.fout[(long long)OPP * p.vol + idx] = v; return; }
+    }
+    const int off = (cx < 0 ? n.oxm : (cx > 0 ? n.oxp : 0)) + (cy < 0 ? n.oym : (cy > 0 ? n.oyp : 0)) + (cz < 0 ? n.ozm : (cz > 0 ? n.ozp : 0));
+    p.fout[(long long)I * p.vol + idx + off] = v;
+}
+
+template <bool HAS_KIND, bool HAS_WALLS>
+__global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nz) return;
     const int y = blockIdx.y, x = blockIdx.z;
@@ -167,22 +203,17 @@ __global__ void __launch_bounds__(256) k_collide_stream(const LbmParams p) {
     const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
     d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega0, p.omega1);
 
-    const bool interior = (y > 0) & (y < p.ny - 1) & (z > 0) & (z < p.nz - 1) &
-                          ((x > 0) | (p.x_lo_mode == 0)) & ((x < p.nx - 1) | (p.x_hi_mode == 0));
-    if (interior) {
-#pragma unroll
-        for (int i = 0; i < BIB_Q; ++i) {
-            const long long dst = idx + (long long)c_cx[i] * p.plane + (long long)c_cy[i] * p.nz + c_cz[i];
-            p.fout[(long long)i * p.vol + dst] = f[i];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < BIB_Q; ++i) {
-            long long dst;
-            if (d_dest(p, i, x, y, z, dst)) p.fout[(long long)i * p.vol + dst] = f[i];
-            else p.fout[(long long)d_opp(i) * p.vol + idx] = f[i];
-        }
-    }
+    const Nbr n = d_neighbours<HAS_WALLS>(p, x, y, z);
+    d_push<0, HAS_WALLS>(p, n, idx, f[0]);
+    d_push<1, HAS_WALLS>(p, n, idx, f[1]);   d_push<10, HAS_WALLS>(p, n, idx, f[10]);
+    d_push<2, HAS_WALLS>(p, n, idx, f[2]);   d_push<11, HAS_WALLS>(p, n, idx, f[11]);
+    d_push<3, HAS_WALLS>(p, n, idx, f[3]);   d_push<12, HAS_WALLS>(p, n, idx, f[12]);
+    d_push<4, HAS_WALLS>(p, n, idx, f[4]);   d_push<13, HAS_WALLS>(p, n, idx, f[13]);
+    d_push<5, HAS_WALLS>(p, n, idx, f[5]);   d_push<14, HAS_WALLS>(p, n, idx, f[14]);
+    d_push<6, HAS_WALLS>(p, n, idx, f[6]);   d_push<15, HAS_WALLS>(p, n, idx, f[15]);
+    d_push<7, HAS_WALLS>(p, n, idx, f[7]);   d_push<16, HAS_WALLS>(p, n, idx, f[16]);
+    d_push<8, HAS_WALLS>(p, n, idx, f[8]);   d_push<17, HAS_WALLS>(p, n, idx, f[17]);
+    d_push<9, HAS_WALLS>(p, n, idx, f[9]);   d_push<18, HAS_WALLS>(p, n, idx, f[18]);
 }
 
 // Envelope quirk: populations that cross a periodic face come from a collision with (omega, omega_inner) swapped
@@ -355,10 +386,11 @@ static LbmParams make_params(bib_domain* d) {
 
 int lbm_launch_collide_stream(bib_domain* d) {
     LbmParams p = make_params(d);
-    int bs = d->nz >= 256 ? 256 : ((d->nz + 31) / 32) * 32;
+    int bs = d->nz >= 128 ? 128 : ((d->nz + 31) / 32) * 32;
     dim3 grid((d->nz + bs - 1) / bs, d->ny, d->nx);
-    if (d->kind) k_collide_stream<true><<<grid, bs, 0, d->stream>>>(p);
-    else k_collide_stream<false><<<grid, bs, 0, d->stream>>>(p);
+    const bool walls = p.x_lo_mode == 2 || p.x_hi_mode == 2 || !p.per_y || !p.per_z;
+    if (d->kind) { if (walls) k_collide_stream<true, true><<<grid, bs, 0, d->stream>>>(p); else k_collide_stream<true, false><<<grid, bs, 0, d->stream>>>(p); }
+    else { if (walls) k_collide_stream<false, true><<<grid, bs, 0, d->stream>>>(p); else k_collide_stream<false, false><<<grid, bs, 0, d->stream>>>(p); }
     d->launches++;
     if (d->envelope_swap) {
         FaceParams q; q.p = p;

@@ -16,10 +16,10 @@ TOL_POP = 1e-12
 TOL_1000 = 1e-9
 
 
-def make_lattice(cells, per, omega, omega_inner, **opts):
+def make_lattice(cells, per, omega, omega_inner, opts=None):
     nx, ny, nz, _ = cells.shape
     lat = bib.Lattice(nx, ny, nz, omega, omega_inner, periodic=tuple(bool(p) for p in per))
-    for k, v in opts.items():
+    for k, v in (opts or {}).items():
         lat.set_option(k, v)
     lat.upload(cells)
     return lat
@@ -63,7 +63,7 @@ def test_collide_and_stream_vs_oracle(orc, per, swap):
     cells[..., :19] = 0.01 * rng.normal(size=(nx, ny, nz, 19))
     cells[..., 19:22] = 1e-4 * rng.normal(size=(nx, ny, nz, 3))
     cells[..., 22] = rng.integers(0, 2, size=(nx, ny, nz))
-    lat = make_lattice(cells, per, 1.6, 0.7, **{bib.OPT_ENVELOPE_SWAP: float(swap)})
+    lat = make_lattice(cells, per, 1.6, 0.7, {bib.OPT_ENVELOPE_SWAP: float(swap)})
     ref = cells
     for _ in range(4):
         lat.collideAndStream()
@@ -115,7 +115,7 @@ def test_shape_connectivity_matches_reference(rbc):
 
 def run_ib_case(g, shape, params, deterministic):
     lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]),
-                       **{bib.OPT_DETERMINISTIC_SPREAD: float(deterministic)})
+                       {bib.OPT_DETERMINISTIC_SPREAD: float(deterministic)})
     sid = lat.register_shape(shape.verts, shape.tris)
     lat.add_particles(sid, params, g["vert_init"][..., :3])
     if float(g["regulator_p"]) != 0.0:
@@ -212,7 +212,7 @@ def test_mass_conservation_large():
     cells[..., 22] = (rng.random((n, n, n)) < 0.3)
     m0 = cells[..., :19].sum()
     j0 = np.einsum("xyzi,id->d", cells[..., :19], kit.C19.astype(float))
-    lat = make_lattice(cells, (1, 1, 1), 1.3, 0.5, **{bib.OPT_ENVELOPE_SWAP: 0.0})
+    lat = make_lattice(cells, (1, 1, 1), 1.3, 0.5, {bib.OPT_ENVELOPE_SWAP: 0.0})
     lat.collideAndStream(20)
     out = lat.download()
     m1 = out[..., :19].sum()
@@ -228,7 +228,7 @@ def test_translation_invariance():
     cells[..., :19] = 1e-2 * rng.standard_normal(dims + (19,))
     cells[..., 19:22] = 1e-5 * rng.standard_normal(dims + (3,))
     cells[..., 22] = (rng.random(dims) < 0.5)
-    a = make_lattice(cells, (1, 1, 1), 1.1, 0.6, **{bib.OPT_ENVELOPE_SWAP: 0.0})
-    b = make_lattice(np.roll(cells, (3, 5, 7), axis=(0, 1, 2)), (1, 1, 1), 1.1, 0.6, **{bib.OPT_ENVELOPE_SWAP: 0.0})
+    a = make_lattice(cells, (1, 1, 1), 1.1, 0.6, {bib.OPT_ENVELOPE_SWAP: 0.0})
+    b = make_lattice(np.roll(cells, (3, 5, 7), axis=(0, 1, 2)), (1, 1, 1), 1.1, 0.6, {bib.OPT_ENVELOPE_SWAP: 0.0})
     a.collideAndStream(5); b.collideAndStream(5)
     assert np.array_equal(np.roll(a.download(), (3, 5, 7), axis=(0, 1, 2)), b.download())
