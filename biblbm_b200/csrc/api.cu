@@ -15,7 +15,6 @@ bool bib_cuda_ok(cudaError_t e, const char* what) {
     return false;
 }
 
-int ib_interpolate_dense(bib_domain* d);
 
 extern "C" {
 
@@ -125,6 +124,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
 int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
     BIB_ENTER(d);
     if (!box || !cells) { bib_set_error("upload: null argument"); return 0; }
+    d->vel_full_valid = false; d->force_is_body = false;
     if (!lbm_launch_upload(d, box, cells)) return 0;
     return 1;
 }
@@ -147,12 +147,17 @@ int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, dou
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
     BIB_ENTER(d);
     if (!box) { bib_set_error("set_external_vector: null argument"); return 0; }
+    const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    d->force_is_body = full;
+    if (full) { d->force_body[0] = fx; d->force_body[1] = fy; d->force_body[2] = fz; }
     return lbm_launch_set_external(d, box, fx, fy, fz);
 }
 int bib_compute_velocity(bib_domain* d, const int box[6]) {
     BIB_ENTER(d);
     if (!box) { bib_set_error("compute_velocity: null argument"); return 0; }
-    return lbm_launch_velocity(d, box);
+    if (!lbm_launch_velocity(d, box)) return 0;
+    d->vel_full_valid = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    return 1;
 }
 int bib_velocity_download(bib_domain* d, const int box[6], double* velocity) {
     BIB_ENTER(d);
@@ -161,6 +166,7 @@ int bib_velocity_download(bib_domain* d, const int box[6], double* velocity) {
 }
 int bib_collide_and_stream(bib_domain* d) {
     BIB_ENTER(d);
+    d->vel_full_valid = false;
     return lbm_launch_collide_stream(d);
 }
 
@@ -210,13 +216,13 @@ int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
 int bib_ib_interpolate_velocity(bib_domain* d) {
     BIB_ENTER(d);
     // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
-    return d->vel ? ib_interpolate_dense(d) : ib_interpolate(d);
+    return ib_interpolate(d);
 }
 int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); return ib_forces_and_spread(d); }
 int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib_move_and_voxelize(d); }
 int bib_ib_step(bib_domain* d) {
     BIB_ENTER(d);
-    return (d->vel ? ib_interpolate_dense(d) : ib_interpolate(d)) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
+    return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
     BIB_ENTER(d);
@@ -242,9 +248,16 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
     const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
     for (int s = 0; s < n_steps; ++s) {
         if (!ib_interpolate(d)) return 0;
-        if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
+        // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
+        if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {
+            if (!ib_band_reset(d, body_fx, body_fy, body_fz)) return 0;
+        } else {
+            if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
+            d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
+        }
         if (!ib_forces_and_spread(d)) return 0;
         if (!ib_move_and_voxelize(d)) return 0;
+        d->vel_full_valid = false;
         if (!lbm_launch_collide_stream(d)) return 0;
     }
     return 1;

@@ -56,6 +56,9 @@ struct bib_domain {
     uint8_t* phase = nullptr;
     uint8_t* kind = nullptr;
     double* vel = nullptr;
+    bool vel_full_valid = false;          // vel holds the full field of the CURRENT populations (bib_compute_velocity)
+    bool force_is_body = false;           // every cell outside the particle bands holds force_body
+    double force_body[3] = {0, 0, 0};
     uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
@@ -104,6 +107,7 @@ int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux,
 int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const int* tris, int* shape_id);
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
 int ib_interpolate(bib_domain* d);
+int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
 int ib_forces_and_spread(bib_domain* d);
 int ib_move_and_voxelize(bib_domain* d);
 int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9);

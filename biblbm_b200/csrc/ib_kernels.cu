@@ -294,15 +294,10 @@ struct RbcParams {
     double reg_p, reg_t[3];
 };
 
-// One thread per vertex: gathers the contributions of its incident links, triangles and pairs in the order in which
-// RBCParticle::compute_forces adds them to that vertex (decorator, links, triangles [area, volume], pairs).
-__global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
-                                                    const double* __restrict__ pstate) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= (long long)q.count * q.nv) return;
-    const int pl = (int)(t / q.nv), v = (int)(t % q.nv);
-    const long long base = q.first_vertex + (long long)pl * q.nv;
-    const double* st = pstate + (long long)(q.first_particle + pl) * 11;
+// Force on vertex v of one particle: gathers the contributions of its incident links, triangles and pairs in the order in
+// which RBCParticle::compute_forces adds them to that vertex (decorator, links, triangles [area, volume], pairs).
+// P/capP/baseP address the particle's vertex positions (global SoA arrays or a shared-memory copy).
+__device__ __forceinline__ V3 d_rbc_vertex_force(const RbcParams& q, const double* P, long long capP, long long baseP, int v, const double* st) {
     const double area = st[0], volume = st[1];
     double fx = 0.0, fy = 0.0, fz = 0.0;
     if (q.reg_p != 0.0) {
@@ -312,7 +307,7 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     }
     for (int e = q.v_link_off[v]; e < q.v_link_off[v + 1]; ++e) {
         const int code = q.v_link[e], l = code >> 1, end = code & 1;
-        const V3 a = ld3(vpos, q.cap, base + q.links[2 * l]), b = ld3(vpos, q.cap, base + q.links[2 * l + 1]);
+        const V3 a = ld3(P, capP, baseP + q.links[2 * l]), b = ld3(P, capP, baseP + q.links[2 * l + 1]);
         const V3 dv = sub(a, b);
         const double L = nrm(dv);
         const double x = L / (q.link_len[l] * 2.2);
@@ -323,7 +318,7 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     const double df_vol = q.k_v * (q.vol_desired - volume) / q.vol_desired;
     for (int e = q.v_tri_off[v]; e < q.v_tri_off[v + 1]; ++e) {
         const int code = q.v_tri[e], tr = code / 3, k = code % 3;
-        const V3 v0 = ld3(vpos, q.cap, base + q.tris[3 * tr]), v1 = ld3(vpos, q.cap, base + q.tris[3 * tr + 1]), v2 = ld3(vpos, q.cap, base + q.tris[3 * tr + 2]);
+        const V3 v0 = ld3(P, capP, baseP + q.tris[3 * tr]), v1 = ld3(P, capP, baseP + q.tris[3 * tr + 1]), v2 = ld3(P, capP, baseP + q.tris[3 * tr + 2]);
         double local_area;
         const V3 g = d_area_grad(v0, v1, v2, k, local_area);
         double df_area = 0.;
@@ -335,14 +330,42 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     }
     for (int e = q.v_pair_off[v]; e < q.v_pair_off[v + 1]; ++e) {
         const int code = q.v_pair[e], pr = code >> 2, k = code & 3;
-        const V3 v0 = ld3(vpos, q.cap, base + q.pairs[4 * pr]), v1 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 1]);
-        const V3 v2 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 2]), v3 = ld3(vpos, q.cap, base + q.pairs[4 * pr + 3]);
+        const V3 v0 = ld3(P, capP, baseP + q.pairs[4 * pr]), v1 = ld3(P, capP, baseP + q.pairs[4 * pr + 1]);
+        const V3 v2 = ld3(P, capP, baseP + q.pairs[4 * pr + 2]), v3 = ld3(P, capP, baseP + q.pairs[4 * pr + 3]);
         double cs, sn;
         const V3 g = d_angle_grad(v0, v1, v2, v3, k, cs, sn);
         const double prefactor = q.k_b * (-q.pair_cs[2 * pr] * sn + q.pair_cs[2 * pr + 1] * cs);
         fx += prefactor * g.x; fy += prefactor * g.y; fz += prefactor * g.z;
     }
-    vfrc[base + v] = fx; vfrc[q.cap + base + v] = fy; vfrc[2 * q.cap + base + v] = fz;
+    return {fx, fy, fz};
+}
+
+// One CTA per particle: the particle's vertex positions are staged in shared memory once (nv*24 B), every thread then
+// gathers from there; the connectivity arrays are shared by all particles of the shape and stay in L1/L2.
+__global__ void __launch_bounds__(256) k_rbc_forces_cta(RbcParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
+                                                        const double* __restrict__ pstate) {
+    extern __shared__ double s_pos[];
+    const int pl = blockIdx.x;
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        s_pos[v] = vpos[base + v]; s_pos[q.nv + v] = vpos[q.cap + base + v]; s_pos[2 * q.nv + v] = vpos[2 * q.cap + base + v];
+    }
+    __syncthreads();
+    const double* st = pstate + (long long)(q.first_particle + pl) * 11;
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        const V3 f = d_rbc_vertex_force(q, s_pos, q.nv, 0, v, st);
+        vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
+    }
+}
+// Fallback for meshes whose vertices do not fit in shared memory: one thread per vertex, positions gathered from HBM/L2.
+__global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
+                                                    const double* __restrict__ pstate) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)q.count * q.nv) return;
+    const int pl = (int)(t / q.nv), v = (int)(t % q.nv);
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    const V3 f = d_rbc_vertex_force(q, vpos, q.cap, base, v, pstate + (long long)(q.first_particle + pl) * 11);
+    vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
 }
 
 // ------------------------------------------------------------------------------------------------ I4: move + update
@@ -506,6 +529,104 @@ __global__ void __launch_bounds__(256) k_phase_scan(int nx, int ny, int nz, long
     }
     __syncwarp();
     if (lane == 0 && flags) col_flags[(long long)(x + 1) * ny + y] = 0;
+}
+
+// Word-parallel version of k_phase_scan for nz % (4*W) == 0: a lane handles W consecutive 32-bit words (4 cells each),
+// so a warp reads and writes 128*W contiguous bytes per iteration.
+template <int W>
+__global__ void __launch_bounds__(256) k_phase_scan_words(int nx, int ny, int nz, long long plane, uint8_t* phase, uint8_t* col_flags) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nx * ny) return;
+    const int x = warp / ny, y = warp % ny;
+    uint32_t* col = (uint32_t*)(phase + (long long)(x + 1) * plane + (long long)y * nz);
+    const int nw = nz / 4;
+    const unsigned flags = col_flags[(long long)(x + 1) * ny + y];
+    unsigned carry = 0;
+    for (int w0 = 0; w0 < nw; w0 += 32 * W) {
+        const int w = w0 + lane * W;
+        uint32_t v[W], p[W];
+        if (W == 4) { if (w < nw) { const uint4 q = *(const uint4*)(col + w); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; } else { v[0] = v[1] = v[2] = v[3] = 0; } }
+        else { v[0] = (w < nw) ? col[w] : 0u; }
+        unsigned lane_par = 0;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const uint32_t m = (v[k] >> 1) & 0x01010101u;
+            uint32_t q = m ^ (m << 8); q ^= (q << 16);           // inclusive prefix parity per byte within the word
+            p[k] = q ^ (lane_par ? 0x01010101u : 0u);
+            lane_par ^= (q >> 24) & 1u;
+        }
+        unsigned incl = lane_par;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl ^= t; }
+        const unsigned before = incl ^ lane_par ^ carry;
+        if (w < nw) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                uint32_t out = p[k] ^ (before ? 0x01010101u : 0u);
+                if (w + k == nw - 1 && !(flags & 4u) && (flags & 3u)) {
+                    const unsigned val = (flags & 2u) ? (((out >> 24) & 1u) ^ 1u) : ((v[k] >> 24) & 1u);
+                    out = (out & 0x00ffffffu) | (val << 24);
+                }
+                v[k] = out;
+            }
+            if (W == 4) *(uint4*)(col + w) = make_uint4(v[0], v[1], v[2], v[3]); else col[w] = v[0];
+        }
+        carry ^= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0 && flags) col_flags[(long long)(x + 1) * ny + y] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ band passes
+// The reference recomputes the velocity field and resets the force field over the WHOLE lattice every step
+// (computeVelocity / setExternalVector, 48 B/cell of extra traffic). Only cells inside some vertex stencil are ever read
+// by the interpolation or changed by the spread, so both passes run over the particles' bounding boxes only:
+// one CTA per particle, cells of bbox +- margin, periodic wrap per cell. Overlapping boxes write identical values.
+struct Band { int lo[3], n[3]; };
+__device__ __forceinline__ Band d_band(const double* st, int margin) {
+    Band b;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        b.lo[d] = (int)floor(st[5 + 2 * d]) - margin;
+        b.n[d] = (int)ceil(st[5 + 2 * d + 1]) + margin - b.lo[d] + 1;
+    }
+    return b;
+}
+__device__ __forceinline__ bool d_band_cell(const Geo& g, const Band& b, int t, long long& idx) {
+    const int kz = t % b.n[2], ky = (t / b.n[2]) % b.n[1], kx = t / (b.n[2] * b.n[1]);
+    int c[3] = {b.lo[0] + kx, b.lo[1] + ky, b.lo[2] + kz};
+    const int n[3] = {g.nx, g.ny, g.nz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (c[d] < 0 || c[d] >= n[d]) {
+            if (!g.per[d]) return false;
+            c[d] = ((c[d] % n[d]) + n[d]) % n[d];
+        }
+    }
+    const int lx = c[0] - g.x_offset;
+    if (lx < 0 || lx >= (int)(g.vol / g.plane) - 2) return false;
+    idx = (long long)(lx + 1) * g.plane + (long long)c[1] * g.nz + c[2];
+    return true;
+}
+__global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __restrict__ f, const double* __restrict__ force, double* vel,
+                                                       const double* __restrict__ pstate) {
+    const Band b = d_band(pstate + (long long)blockIdx.x * 11, 2);
+    const int total = b.n[0] * b.n[1] * b.n[2];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        long long idx;
+        if (!d_band_cell(g, b, t, idx)) continue;
+        double u[3];
+        d_cell_velocity(f, force, g.vol, idx, u);
+        vel[idx] = u[0]; vel[g.vol + idx] = u[1]; vel[2 * g.vol + idx] = u[2];
+    }
+}
+__global__ void __launch_bounds__(256) k_band_reset(Geo g, double* force, const double* __restrict__ pstate, double fx, double fy, double fz) {
+    const Band b = d_band(pstate + (long long)blockIdx.x * 11, 3);
+    const int total = b.n[0] * b.n[1] * b.n[2];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        long long idx;
+        if (!d_band_cell(g, b, t, idx)) continue;
+        force[idx] = fx; force[g.vol + idx] = fy; force[2 * g.vol + idx] = fz;
+    }
 }
 
 Geo make_geo(const bib_domain* d) {
@@ -701,20 +822,35 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
 }
 
 // ------------------------------------------------------------------------------------------------ host: IB phases
+static int ensure_velocity_field(bib_domain* d) {
+    if (d->vel) return 1;
+    BIB_CHECK(cudaMalloc(&d->vel, d->vol * 3 * sizeof(double)));
+    BIB_CHECK(cudaMemsetAsync(d->vel, 0, d->vol * 3 * sizeof(double), d->stream));
+    d->bytes += (long long)d->vol * 3 * 8;
+    return 1;
+}
+
+// interpolate_velocity: velocity u = j/rho + F/2 is evaluated in the particles' bands unless the caller has just computed
+// the full field with bib_compute_velocity (the reference's calling sequence), then gathered with the Roma kernel.
 int ib_interpolate(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
+    if (!ensure_velocity_field(d)) return 0;
+    if (!d->vel_full_valid) {
+        k_band_velocity<<<d->n_particles, 256, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->pstate);
+        d->launches++;
+    }
     const int bs = 128;
     const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
-    k_interpolate<false><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, nullptr, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
+    k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     return 1;
 }
-int ib_interpolate_dense(bib_domain* d) {
-    if (d->n_vertices == 0) return 1;
-    const int bs = 128;
-    const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
-    k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
+
+// F := body inside the particles' bands (everywhere else the force already equals the body force)
+int ib_band_reset(bib_domain* d, double fx, double fy, double fz) {
+    if (d->n_particles == 0) return 1;
+    k_band_reset<<<d->n_particles, 256, 0, d->stream>>>(make_geo(d), d->force, d->pstate, fx, fy, fz);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     return 1;
@@ -731,8 +867,14 @@ int ib_forces_and_spread(bib_domain* d) {
         q.v_link_off = s.v_link_off; q.v_link = s.v_link; q.v_tri_off = s.v_tri_off; q.v_tri = s.v_tri; q.v_pair_off = s.v_pair_off; q.v_pair = s.v_pair;
         q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
         q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
-        const long long n = (long long)gr.count * s.nv;
-        k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+        const size_t smem = (size_t)s.nv * 3 * sizeof(double);
+        if (smem <= 200 * 1024) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_rbc_forces_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_rbc_forces_cta<<<gr.count, 256, smem, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+        } else {
+            const long long n = (long long)gr.count * s.nv;
+            k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+        }
         d->launches++;
     }
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
@@ -752,7 +894,10 @@ int ib_move_and_voxelize(bib_domain* d) {
     }
     // apply_voxelization rewrites the phase of every cell of the block each step, also without any particle
     const long long warps = (long long)d->nx * d->ny;
-    k_phase_scan<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, d->stream>>>(d->nx, d->ny, d->nz, (long long)d->plane, d->phase, d->col_flags);
+    const unsigned scan_grid = (unsigned)((warps * 32 + 255) / 256);
+    if (d->nz % 16 == 0) k_phase_scan_words<4><<<scan_grid, 256, 0, d->stream>>>(d->nx, d->ny, d->nz, (long long)d->plane, d->phase, d->col_flags);
+    else if (d->nz % 4 == 0) k_phase_scan_words<1><<<scan_grid, 256, 0, d->stream>>>(d->nx, d->ny, d->nz, (long long)d->plane, d->phase, d->col_flags);
+    else k_phase_scan<<<scan_grid, 256, 0, d->stream>>>(d->nx, d->ny, d->nz, (long long)d->plane, d->phase, d->col_flags);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     return 1;

@@ -232,3 +232,47 @@ def test_translation_invariance():
     b = make_lattice(np.roll(cells, (3, 5, 7), axis=(0, 1, 2)), (1, 1, 1), 1.1, 0.6, {bib.OPT_ENVELOPE_SWAP: 0.0})
     a.collideAndStream(5); b.collideAndStream(5)
     assert np.array_equal(np.roll(a.download(), (3, 5, 7), axis=(0, 1, 2)), b.download())
+
+
+@pytest.mark.parametrize("nz", [32, 20, 23])
+@pytest.mark.parametrize("per_z", [1, 0])
+def test_voxelizer_vs_oracle(orc, rbc, nz, per_z):
+    """Phase field after move_vertices_and_revoxelize (zero velocity) == oracle voxelizer, for the three scan code paths
+    (nz % 16 == 0, nz % 4 == 0, ragged), with particles hugging / straddling the z faces (the reference's z1 corner case
+    and its periodic z-remap quirk) and a second call that must reproduce cells the reference leaves untouched."""
+    shape, params, rbc_pos, _ = rbc
+    nx, ny = 40, 22
+    per = (1, 1, per_z)
+    base = rbc_pos - rbc_pos.mean(0)      # flat RBC: |z| <= 6.7
+    zc = [nz - 7.2, 0.3 if per_z else 7.4]
+    pos = np.array([base + (10.3, 11.2, zc[0]), base + (29.6, 10.7, zc[1])])
+    cells = np.zeros((nx, ny, nz, 23))
+    cells[..., 22] = (np.random.default_rng(2).random((nx, ny, nz)) < 0.5)   # stale phase that must be overwritten (or kept at z1)
+    lat = make_lattice(cells, per, 1.0, 0.5)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    ref = cells.copy()
+    for _ in range(2):
+        lat.move_vertices_and_revoxelize()
+        orc.voxelize(ref, per, shape, lat.vertices().reshape(2, shape.nv, 9)[..., :3].copy())
+        got = lat.download()
+        assert np.array_equal(got[..., 22], ref[..., 22])
+        assert got[..., 22].sum() > 500
+
+
+def test_band_passes_equal_full_passes(rbc):
+    """bib_step (band velocity / band force reset) == the reference's call sequence with full-lattice passes."""
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    a = run_ib_case(g, shape, params, deterministic=True)
+    b = run_ib_case(g, shape, params, deterministic=True)
+    for _ in range(6):
+        a.step(g["body"])
+        b.computeVelocity(download=False)
+        b.interpolate_velocity()
+        b.setExternalVector(g["body"])
+        b.compute_and_spread_forces()
+        b.move_vertices_and_revoxelize()
+        b.collideAndStream()
+    assert np.array_equal(a.vertices(), b.vertices())
+    assert np.array_equal(a.download(), b.download())
