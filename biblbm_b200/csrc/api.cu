@@ -88,6 +88,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->kind) cudaFree(d->kind);
     if (d->vel) cudaFree(d->vel);
     if (d->col_flags) cudaFree(d->col_flags);
+    if (d->halo_stage) cudaFree(d->halo_stage);
     if (d->scratch) cudaFree(d->scratch);
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);

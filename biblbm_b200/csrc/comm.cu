@@ -10,6 +10,7 @@
 // shares the copy an embedding process (e.g. PyTorch) has already loaded.
 #include "domain.cuh"
 
+#include <algorithm>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -47,6 +48,21 @@ bool nccl_ok(ncclResult_t r, const char* what) {
 
 const int kPlusX[5] = {10, 13, 14, 15, 16};    // c_x = +1 (src/latticeBoltzmann/nearestNeighborLattices3D.hh:167-177)
 const int kMinusX[5] = {1, 4, 5, 6, 7};        // c_x = -1
+const int kCy[19] = {0, 0, -1, 0, -1, 1, 0, 0, -1, -1, 0, 1, 0, 1, -1, 0, 0, 1, 1};
+const int kCz[19] = {0, 0, 0, -1, 0, 0, -1, 1, -1, 1, 0, 0, 1, 0, 0, 1, -1, 1, -1};
+
+// With a non-periodic y or z face the neighbour's ghost plane has holes: an entry whose source row lies outside the
+// lattice was never pushed by the sender, and the receiving cell has already filled that slot itself with its bounced
+// population. Received planes are therefore staged and merged, skipping those entries.
+__global__ void k_halo_merge(double* __restrict__ dst, const double* __restrict__ src, int ny, int nz, int cy, int cz, int per_y, int per_z) {
+    const long long n = (long long)ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % nz), y = (int)(t / nz);
+        const int sy = y - cy, sz = z - cz;
+        if ((!per_y && (sy < 0 || sy >= ny)) || (!per_z && (sz < 0 || sz >= nz))) continue;
+        dst[t] = src[t];
+    }
+}
 
 }  // namespace
 
@@ -89,18 +105,31 @@ int comm_halo_exchange(bib_domain* d) {
     const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
     const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
     const bool has_left = d->per[0] || d->rank > 0;
+    const bool staged = !d->per[1] || !d->per[2];
+    if (staged && !d->halo_stage) {
+        BIB_CHECK(cudaMalloc(&d->halo_stage, 10 * n * sizeof(double)));
+        d->bytes += (long long)(10 * n * sizeof(double));
+    }
     NCCL_CHECK(g_nccl.GroupStart());
     for (int k = 0; k < 5; ++k) {
         double* pop = f + (size_t)kPlusX[k] * d->vol;
         if (has_right) NCCL_CHECK(g_nccl.Send(pop + (size_t)(d->nx + 1) * n, n, ncclDouble, right, comm, d->stream));
-        if (has_left) NCCL_CHECK(g_nccl.Recv(pop + (size_t)1 * n, n, ncclDouble, left, comm, d->stream));
+        if (has_left) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)k * n : pop + (size_t)1 * n, n, ncclDouble, left, comm, d->stream));
     }
     for (int k = 0; k < 5; ++k) {
         double* pop = f + (size_t)kMinusX[k] * d->vol;
         if (has_left) NCCL_CHECK(g_nccl.Send(pop + (size_t)0 * n, n, ncclDouble, left, comm, d->stream));
-        if (has_right) NCCL_CHECK(g_nccl.Recv(pop + (size_t)d->nx * n, n, ncclDouble, right, comm, d->stream));
+        if (has_right) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)(5 + k) * n : pop + (size_t)d->nx * n, n, ncclDouble, right, comm, d->stream));
     }
     NCCL_CHECK(g_nccl.GroupEnd());
     d->launches++;
+    if (staged) {
+        const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+        for (int k = 0; k < 5; ++k) {
+            if (has_left) { k_halo_merge<<<grid, 256, 0, d->stream>>>(f + (size_t)kPlusX[k] * d->vol + (size_t)1 * n, d->halo_stage + (size_t)k * n, d->ny, d->nz, kCy[kPlusX[k]], kCz[kPlusX[k]], d->per[1], d->per[2]); d->launches++; }
+            if (has_right) { k_halo_merge<<<grid, 256, 0, d->stream>>>(f + (size_t)kMinusX[k] * d->vol + (size_t)d->nx * n, d->halo_stage + (size_t)(5 + k) * n, d->ny, d->nz, kCy[kMinusX[k]], kCz[kMinusX[k]], d->per[1], d->per[2]); d->launches++; }
+        }
+        BIB_CHECK(cudaGetLastError());
+    }
     return 1;
 }

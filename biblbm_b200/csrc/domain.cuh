@@ -72,6 +72,7 @@ struct bib_domain {
     // multi-GPU ring
     int rank = 0, n_ranks = 1;
     void* nccl_comm = nullptr;
+    double* halo_stage = nullptr;         // [10][ny*nz] received ghost planes when y or z has walls
     int x_offset = 0;                     // global x of local plane 0
     int gnx = 0;                          // global nx
     // IB

@@ -1,0 +1,21 @@
+"""Multi-GPU (x-slab ring over NCCL) parity: needs >= 2 visible GPUs, otherwise skipped (the 1-GPU box runs the rest)."""
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+import biblbm_b200 as bib
+
+pytestmark = pytest.mark.gpu
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_ring_bit_identical_to_single_domain(world):
+    if bib.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(ROOT / "tests" / "mgpu" / "slab_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("bit-identical=True") == 3
