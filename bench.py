@@ -263,9 +263,15 @@ def ours(args):
     ms_kernel = max_over_ranks(lat.time_end()) / args.steps
     lat.set_option(bib.OPT_ENVELOPE_SWAP, 1.0)
     peak, peak_kind = measured_peaks()
+    traffic = None
+    tj = ROOT / "profiles" / "r1_k_collide_stream_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text())
+        if t["workload"] == [nx, ny, nz]:
+            traffic = t["dram_bytes_per_launch"]
     achieved = LBM_BYTES_PER_CELL * cells_local / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_collide_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}; burst figure, kernel timed alone)",
+                "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}; burst figure, kernel timed alone)",
                 "ms_per_launch": ms_kernel, "lbm_only_mlups": cells_local * world / (ms_kernel * 1e-3) / 1e6,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "algorithmic_bytes_per_cell": LBM_BYTES_PER_CELL, "true_bytes_per_cell": 329.0}
