@@ -21,7 +21,7 @@ SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
-    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_count", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
@@ -179,6 +179,15 @@ class Lattice:
         n_p, n_v = C.c_int(0), C.c_longlong(0)
         _check(self.lib.bib_ib_count(self.h, C.byref(n_p), C.byref(n_v)))
         return n_p.value, n_v.value
+
+    def local_slots(self):
+        """(global ids, roles) of the particle slots on this slab (roles: 0 dead, 1 owned, 2/3 ghost)."""
+        cap = max(1, self.count()[0])
+        gids = np.zeros(cap, dtype=np.int32); roles = np.zeros(cap, dtype=np.int32)
+        n = C.c_int(0)
+        ip = C.POINTER(C.c_int)
+        _check(self.lib.bib_ib_local_slots(self.h, gids.ctypes.data_as(ip), roles.ctypes.data_as(ip), cap, C.byref(n)))
+        return gids[:n.value], roles[:n.value]
 
     def interpolate_velocity(self):
         _check(self.lib.bib_ib_interpolate_velocity(self.h))

@@ -14,7 +14,7 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbiblbm_b200.so"
-SOURCES = ["api.cu", "lbm_kernels.cu", "ib_kernels.cu", "comm.cu"]
+SOURCES = ["api.cu", "lbm_kernels.cu", "ib_kernels.cu", "ib_multislab.cu", "comm.cu"]
 HEADERS = [CSRC / "domain.cuh", HERE.parent / "include" / "biblbm_b200.h"]
 
 

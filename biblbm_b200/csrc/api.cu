@@ -16,6 +16,9 @@ bool bib_cuda_ok(cudaError_t e, const char* what) {
 }
 
 
+void ms_destroy(bib_domain* d);
+int ms_check_overflow(bib_domain* d);
+
 extern "C" {
 
 const char* bib_last_error(void) { return g_last_error.c_str(); }
@@ -82,6 +85,7 @@ int bib_domain_destroy(bib_domain* d) {
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     comm_destroy(d);
+    ms_destroy(d);
     for (int b = 0; b < 2; ++b) if (d->f[b]) cudaFree(d->f[b]);
     if (d->force) cudaFree(d->force);
     if (d->phase) cudaFree(d->phase);
@@ -200,7 +204,6 @@ int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* l
 int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
     BIB_ENTER(d);
     if (!params || (n > 0 && !positions)) { bib_set_error("particles_add: null argument"); return 0; }
-    if (d->n_ranks > 1) { bib_set_error("particles_add: immersed boundaries on multi-slab domains are not implemented yet"); return 0; }
     return ib_particles_add(d, type, shape_id, params, n, positions);
 }
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz) {
@@ -234,6 +237,11 @@ int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long coun
     BIB_ENTER(d);
     if (count > 0 && !vertices9) { bib_set_error("vertices_upload: null argument"); return 0; }
     return ib_vertices_upload(d, first_vertex, count, vertices9);
+}
+int bib_ib_local_slots(bib_domain* d, int* global_ids, int* roles, int capacity, int* n_slots) {
+    BIB_ENTER(d);
+    if (!global_ids || !roles || !n_slots) { bib_set_error("local_slots: null argument"); return 0; }
+    return ib_local_slots(d, global_ids, roles, capacity, n_slots);
 }
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11) {
     BIB_ENTER(d);
@@ -271,7 +279,7 @@ int bib_comm_unique_id(void* unique_id_128) {
 int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128) {
     BIB_ENTER(d);
     if (!unique_id_128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) { bib_set_error("comm_init: bad arguments"); return 0; }
-    if (d->n_particles > 0) { bib_set_error("comm_init: immersed boundaries on multi-slab domains are not implemented yet"); return 0; }
+    if (d->n_particles > 0) { bib_set_error("comm_init: call bib_comm_init before adding particles"); return 0; }
     return comm_init(d, rank, n_ranks, unique_id_128);
 }
 
@@ -279,7 +287,7 @@ int bib_sync(bib_domain* d) {
     BIB_ENTER(d);
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->comm_stream));
-    return 1;
+    return ms_check_overflow(d);
 }
 int bib_time_begin(bib_domain* d) { BIB_ENTER(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
 int bib_time_end(bib_domain* d, float* milliseconds) {

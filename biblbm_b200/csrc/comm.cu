@@ -133,3 +133,20 @@ int comm_halo_exchange(bib_domain* d) {
     }
     return 1;
 }
+
+// Symmetric neighbour exchange of two fixed-size buffers (used by the multi-slab immersed-boundary protocol).
+int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles) {
+    ncclComm_t comm = (ncclComm_t)d->nccl_comm;
+    if (!comm) { bib_set_error("exchange: bib_comm_init has not been called"); return 0; }
+    const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+    const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    const bool has_left = d->per[0] || d->rank > 0;
+    if (!has_left) BIB_CHECK(cudaMemsetAsync(recv_left, 0, sizeof(double), d->stream));
+    if (!has_right) BIB_CHECK(cudaMemsetAsync(recv_right, 0, sizeof(double), d->stream));
+    NCCL_CHECK(g_nccl.GroupStart());
+    if (has_left) { NCCL_CHECK(g_nccl.Send(send_left, n_doubles, ncclDouble, left, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(recv_left, n_doubles, ncclDouble, left, comm, d->stream)); }
+    if (has_right) { NCCL_CHECK(g_nccl.Send(send_right, n_doubles, ncclDouble, right, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(recv_right, n_doubles, ncclDouble, right, comm, d->stream)); }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    d->launches++;
+    return 1;
+}

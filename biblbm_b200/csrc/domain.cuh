@@ -43,6 +43,25 @@ struct ParticleGroup {            // particles of one (type, shape, params) adde
     double* link_kp = nullptr;    // [nl]
 };
 
+// Immersed boundaries on several slabs: every rank keeps a slot array holding the particles it OWNS (centre of mass inside
+// its x-range, the reference's ownership rule, src/fsi/ImmersedBoundaryDynamics.hh:232-246) plus GHOST copies of neighbours'
+// particles that reach into its slab. Per step three fixed-capacity neighbour exchanges keyed by global particle id:
+// positions (owner -> ghost holders, carries ownership hand-off), partial interpolated velocities (ghost holder -> owner,
+// summed there) and vertex forces (owner -> ghost holders, each slab spreads into its own cells only).
+struct MultiSlabIB {
+    int nv = 0, cap = 0, n_global = 0, xcap = 0;
+    size_t entry = 0;                      // doubles per exchanged particle: gid, flag, 3*nv payload
+    int* role = nullptr;                   // [cap] 0 dead, 1 owned, 2 ghost (owner = left neighbour), 3 ghost (owner = right)
+    int* gid_of = nullptr;                 // [cap]
+    int* slot_of = nullptr;                // [n_global] -1 when not resident
+    int* free_stack = nullptr;             // [cap]
+    int* counters = nullptr;               // [0] free_top, [1] overflow flag
+    uint8_t* seen = nullptr;               // [cap]
+    double* send[2] = {nullptr, nullptr};  // [1 + xcap*entry]; element 0 holds the entry count (uint64)
+    double* recv[2] = {nullptr, nullptr};
+    bool ghosts_dirty = true;
+};
+
 struct bib_domain {
     int device = 0;
     int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
@@ -88,6 +107,7 @@ struct bib_domain {
     double* pstate = nullptr; // [cap_particles][11] area, volume, com[3], bbox[6]
     int* p_first_vertex = nullptr;   // [cap_particles]
     void* scratch = nullptr; size_t scratch_bytes = 0;
+    MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 
 void bib_set_error(const std::string& msg);
@@ -119,6 +139,8 @@ int comm_unique_id(void* out128);
 int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);
 int comm_halo_exchange(bib_domain* d);
 void comm_destroy(bib_domain* d);
+int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles);
+int ib_local_slots(bib_domain* d, int* gids, int* roles, int capacity, int* n_slots);
 
 // ---- device helpers shared by the LBM and IB kernels
 #ifdef __CUDACC__

@@ -33,7 +33,12 @@ struct Geo {
     int per[3];
     long long plane, vol;
     int x_offset;            // global x of storage plane 1
+    int nxl;                 // planes owned by this slab (== nx on a single slab)
+    const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
+    int nv_slot;             // vertices per slot when role != NULL
 };
+// slab-local plane index of global x, or -1 when another slab owns it
+__device__ __forceinline__ bool d_in_slab(const Geo& g, int gx) { const int lx = gx - g.x_offset; return lx >= 0 && lx < g.nxl; }
 
 __device__ __forceinline__ double d_roma(double x) {
     const double dx = fabs(x);
@@ -95,12 +100,15 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
                                                      const double* __restrict__ vpos, double* __restrict__ vvel) {
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= nvert) return;
+    if (g.role && g.role[v / g.nv_slot] == 0) return;
     const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     double o[3] = {0.0, 0.0, 0.0};
-    const int cls = d_classify(g, pp);
+    int cls = d_classify(g, pp);
     if (cls != 0) {
         const double p[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};   // pos - getLocation()
         const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
+        // a stencil that reaches into a neighbouring slab is summed cell by cell; the neighbour adds its part (multi-slab only)
+        if (cls == 1 && !(d_in_slab(g, d_remap(g, 0, x0)) && d_in_slab(g, d_remap(g, 0, x0) + 2))) cls = 2;
         if (cls == 1) {
             const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
             const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
         } else {
             for (int i = x0; i <= x0 + 2; ++i) {
                 const int i2 = d_remap(g, 0, i);
-                if (i2 < 0 || i2 > g.nx - 1) continue;
+                if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2)) continue;
                 const double dirac_x = d_roma((double)i - p[0]);
                 for (int j = y0; j <= y0 + 2; ++j) {
                     const int j2 = d_remap(g, 1, j);
@@ -159,8 +167,10 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
 
 // ------------------------------------------------------------------------------------------------ I3: spreading
 __device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, const double* pp, const double* F, int cls, bool atomic) {
+    // (multi-slab: cells owned by a neighbouring slab are skipped here and spread there from the ghost copy of the vertex)
     const double p[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};
     const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
+    if (cls == 1 && !(d_in_slab(g, d_remap(g, 0, x0)) && d_in_slab(g, d_remap(g, 0, x0) + 2))) cls = 2;
     if (cls == 1) {
         const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
         const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
@@ -177,7 +187,7 @@ __device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, con
     } else {
         for (int i = x0; i <= x0 + 2; ++i) {
             const int i2 = d_remap(g, 0, i);
-            if (i2 < 0 || i2 > g.nx - 1) continue;
+            if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2)) continue;
             const double dirac_x = d_roma((double)i - p[0]);
             for (int j = y0; j <= y0 + 2; ++j) {
                 const int j2 = d_remap(g, 1, j);
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(128) k_spread_atomic(Geo g, double* force, lon
                                                        const double* __restrict__ vpos, const double* __restrict__ vfrc) {
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= nvert) return;
+    if (g.role && g.role[v / g.nv_slot] == 0) return;
     const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
     const int cls = d_classify(g, pp);
@@ -214,6 +225,7 @@ __global__ void k_spread_sequential(Geo g, double* force, long long nvert, long 
         for (long long v = 0; v < nvert; ++v) {
             const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
             const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
+            if (g.role && g.role[v / g.nv_slot] == 0) continue;
             if (d_classify(g, pp) == pass) d_spread_vertex(g, force, pp, F, pass, false);
         }
 }
@@ -292,6 +304,7 @@ struct RbcParams {
     const int* v_pair_off; const int* v_pair;
     double shape_area, k_ag, k_al, k_v, vol_desired, k_b;
     double reg_p, reg_t[3];
+    const int* role;
 };
 
 // Force on vertex v of one particle: gathers the contributions of its incident links, triangles and pairs in the order in
@@ -346,6 +359,7 @@ __global__ void __launch_bounds__(256) k_rbc_forces_cta(RbcParams q, const doubl
                                                         const double* __restrict__ pstate) {
     extern __shared__ double s_pos[];
     const int pl = blockIdx.x;
+    if (q.role && q.role[q.first_particle + pl] != 1) return;      // only the owner evaluates membrane forces
     const long long base = q.first_vertex + (long long)pl * q.nv;
     for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
         s_pos[v] = vpos[base + v]; s_pos[q.nv + v] = vpos[q.cap + base + v]; s_pos[2 * q.nv + v] = vpos[2 * q.cap + base + v];
@@ -363,6 +377,7 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= (long long)q.count * q.nv) return;
     const int pl = (int)(t / q.nv), v = (int)(t % q.nv);
+    if (q.role && q.role[q.first_particle + pl] != 1) return;
     const long long base = q.first_vertex + (long long)pl * q.nv;
     const V3 f = d_rbc_vertex_force(q, vpos, q.cap, base, v, pstate + (long long)(q.first_particle + pl) * 11);
     vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
@@ -373,12 +388,19 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
 // order, so area / volume / centre of mass carry exactly the reference's sequential rounding.
 #define UPD_CHUNK 512
 __global__ void __launch_bounds__(256) k_move_update(Geo g, int nv, int nt, const int* __restrict__ tris, long long first_vertex, long long cap,
-                                                     int first_particle, double* vpos, const double* __restrict__ vvel, double* pstate, int do_move) {
+                                                     int first_particle, double* vpos, const double* __restrict__ vvel, double* pstate, int do_move,
+                                                     const uint8_t* __restrict__ skip_mask) {
     __shared__ double s_dA[UPD_CHUNK], s_vol[UPD_CHUNK], s_cx[UPD_CHUNK], s_cy[UPD_CHUNK], s_cz[UPD_CHUNK];
     __shared__ double s_acc[5];
     __shared__ double s_red[6][8];
     __shared__ double s_delta[3];
     const int pl = blockIdx.x;
+    if (skip_mask && skip_mask[first_particle + pl]) return;
+    if (g.role) {
+        const int r = g.role[first_particle + pl];
+        if (r == 0) return;
+        if (r != 1) do_move = 0;            // ghost copies are advected by their owner
+    }
     const long long base = first_vertex + (long long)pl * nv;
     double* st = pstate + (long long)(first_particle + pl) * 11;
     double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
@@ -463,6 +485,7 @@ __global__ void __launch_bounds__(128) k_raycast(Geo g, int nv, int nt, const in
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= (long long)count * nt) return;
     const int pl = (int)(t / nt), tr = (int)(t % nt);
+    if (g.role && g.role[pl] == 0) return;
     const long long base = first_vertex + (long long)pl * nv;
     const V3 p0 = ld3(vpos, cap, base + tris[3 * tr]), p1 = ld3(vpos, cap, base + tris[3 * tr + 1]), p2 = ld3(vpos, cap, base + tris[3 * tr + 2]);
     const int iXmin = (int)ceil(fmin(p0.x, fmin(p1.x, p2.x))), iXmax = (int)floor(fmax(p0.x, fmax(p1.x, p2.x)));
@@ -488,7 +511,7 @@ __global__ void __launch_bounds__(128) k_raycast(Geo g, int nv, int nt, const in
         const int cj = g.per[1] ? ((j + 100 * g.ny) % g.ny) : j;
         if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
         const int lx = ci - g.x_offset;
-        if (lx < 0 || lx >= (int)(g.vol / g.plane) - 2) continue;          // column belongs to another slab
+        if (lx < 0 || lx >= g.nxl) continue;                               // column belongs to another slab
         const double zc_d = ceil(z);
         uint8_t* flag = col_flags + (long long)(lx + 1) * g.ny + cj;
         unsigned bits = 0;
@@ -603,12 +626,13 @@ __device__ __forceinline__ bool d_band_cell(const Geo& g, const Band& b, int t, 
         }
     }
     const int lx = c[0] - g.x_offset;
-    if (lx < 0 || lx >= (int)(g.vol / g.plane) - 2) return false;
+    if (lx < 0 || lx >= g.nxl) return false;
     idx = (long long)(lx + 1) * g.plane + (long long)c[1] * g.nz + c[2];
     return true;
 }
 __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __restrict__ f, const double* __restrict__ force, double* vel,
                                                        const double* __restrict__ pstate) {
+    if (g.role && g.role[blockIdx.x] == 0) return;
     const Band b = d_band(pstate + (long long)blockIdx.x * 11, 2);
     const int total = b.n[0] * b.n[1] * b.n[2];
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
@@ -620,6 +644,7 @@ __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __re
     }
 }
 __global__ void __launch_bounds__(256) k_band_reset(Geo g, double* force, const double* __restrict__ pstate, double fx, double fy, double fz) {
+    if (g.role && g.role[blockIdx.x] == 0) return;
     const Band b = d_band(pstate + (long long)blockIdx.x * 11, 3);
     const int total = b.n[0] * b.n[1] * b.n[2];
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
@@ -634,6 +659,7 @@ Geo make_geo(const bib_domain* d) {
     g.nx = d->gnx; g.ny = d->ny; g.nz = d->nz;
     g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
+    g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
     return g;
 }
 
@@ -787,19 +813,80 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
     return 1;
 }
 
-static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move) {
+static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move, const uint8_t* skip_mask = nullptr) {
     const ShapeDev& s = d->shapes[gr.shape];
     k_move_update<<<gr.count, 256, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.first_particle,
-                                                 d->vpos, d->vvel, d->pstate, do_move);
+                                                 d->vpos, d->vvel, d->pstate, do_move, skip_mask);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     return 1;
+}
+
+int ms_create(bib_domain* d, int nv, int n_global);
+int ms_set_initial(bib_domain* d, const std::vector<int>& owned_gids);
+int ms_exchange_positions(bib_domain* d);
+int ms_exchange_velocities(bib_domain* d);
+int ms_exchange_forces(bib_domain* d);
+
+// update (and optionally advect) every live particle slot; skip_mask[slot] != 0 leaves a slot alone
+int ib_update_all(bib_domain* d, int do_move) {
+    const uint8_t* skip = (d->ms && do_move == 0) ? d->ms->seen + d->ms->cap : nullptr;   // POS exchange: owners keep their cached scalars
+    for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, do_move, skip)) return 0;
+    return 1;
+}
+
+// Multi-slab domains: every rank is given the same global particle list (like the reference's add_particle, which keeps
+// only what it owns, src/fsi/ImmersedBoundaryDynamics.hh:500-525); ownership = slab containing the centre of mass.
+static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
+    if (!d->groups.empty()) { bib_set_error("particles_add: multi-slab domains take one particle group (one call)"); return 0; }
+    const ShapeDev& s = d->shapes[shape_id];
+    if (!ms_create(d, s.nv, n)) return 0;
+    MultiSlabIB* m = d->ms;
+    if (!grow_particles(d, (long long)m->cap * s.nv, m->cap)) return 0;
+    // centre of mass exactly as DeformableParticle3D::update computes it (sequential, area weighted), then the periodic remap
+    std::vector<int> owned;
+    for (int p = 0; p < n; ++p) {
+        const double* P = positions + (size_t)p * s.nv * 3;
+        double area = 0, cx = 0;
+        for (int t = 0; t < s.nt; ++t) {
+            const double *v0 = P + 3 * s.h_tris[3 * t], *v1 = P + 3 * s.h_tris[3 * t + 1], *v2 = P + 3 * s.h_tris[3 * t + 2];
+            const double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+            const double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            double dA = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+            dA *= 0.5;
+            area += dA;
+            cx += ((v0[0] + v1[0] + v2[0]) / 3.0) * dA;
+        }
+        double x = cx / area;
+        if (d->per[0]) { const double L = (double)d->gnx; x = x - L * std::floor((x - (0.0 - 0.5)) * (1. / L)); }
+        if (x >= (double)d->x_offset - 0.5 && x < (double)(d->x_offset + d->nx) - 0.5) owned.push_back(p);
+    }
+    if ((int)owned.size() > m->cap) { bib_set_error("particles_add: more owned particles than slots"); return 0; }
+    const long long capv = d->cap_vertices;
+    std::vector<double> soa((size_t)owned.size() * s.nv * 3);
+    const size_t no = owned.size() * (size_t)s.nv;
+    for (size_t k = 0; k < owned.size(); ++k) for (int v = 0; v < s.nv; ++v) for (int c = 0; c < 3; ++c)
+        soa[(size_t)c * no + k * s.nv + v] = positions[((size_t)owned[k] * s.nv + v) * 3 + c];
+    for (int c = 0; c < 3 && no > 0; ++c)
+        BIB_CHECK(cudaMemcpyAsync(d->vpos + (size_t)c * capv, soa.data() + (size_t)c * no, no * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    if (!ms_set_initial(d, owned)) return 0;
+    ParticleGroup gr;
+    gr.type = type; gr.shape = shape_id; gr.first_particle = 0; gr.count = m->cap; gr.first_vertex = 0;
+    std::memcpy(gr.params, params, 8 * sizeof(double));
+    std::vector<double> ks(s.nl), kp(s.nl);
+    for (int l = 0; l < s.nl; ++l) rbc_ks_kp(s.h_link_len[l], params[0], ks[l], kp[l]);
+    if (!to_device(&gr.link_ks, ks) || !to_device(&gr.link_kp, kp)) return 0;
+    d->groups.push_back(gr);
+    d->n_particles = m->cap; d->n_vertices = (long long)m->cap * s.nv;
+    return launch_update(d, gr, 0);
 }
 
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
     if (type != 0) { bib_set_error("particles_add: only BIB_PARTICLE_RBC is implemented"); return 0; }
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("particles_add: unknown shape"); return 0; }
     if (n <= 0) return 1;
+    if (d->n_ranks > 1) return ib_particles_add_multislab(d, type, shape_id, params, n, positions);
     const ShapeDev& s = d->shapes[shape_id];
     const long long nvtot = (long long)n * s.nv;
     if (!grow_particles(d, d->n_vertices + nvtot, d->n_particles + n)) return 0;
@@ -835,6 +922,7 @@ static int ensure_velocity_field(bib_domain* d) {
 int ib_interpolate(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
     if (!ensure_velocity_field(d)) return 0;
+    if (d->ms && d->ms->ghosts_dirty && !ms_exchange_positions(d)) return 0;
     if (!d->vel_full_valid) {
         k_band_velocity<<<d->n_particles, 256, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->pstate);
         d->launches++;
@@ -844,6 +932,7 @@ int ib_interpolate(bib_domain* d) {
     k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
+    if (d->ms && !ms_exchange_velocities(d)) return 0;     // owners add the partial sums of the neighbouring slabs
     return 1;
 }
 
@@ -867,6 +956,7 @@ int ib_forces_and_spread(bib_domain* d) {
         q.v_link_off = s.v_link_off; q.v_link = s.v_link; q.v_tri_off = s.v_tri_off; q.v_tri = s.v_tri; q.v_pair_off = s.v_pair_off; q.v_pair = s.v_pair;
         q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
         q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
+        q.role = d->ms ? d->ms->role : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
         if (smem <= 200 * 1024) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_rbc_forces_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -877,6 +967,7 @@ int ib_forces_and_spread(bib_domain* d) {
         }
         d->launches++;
     }
+    if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     d->launches++;
@@ -886,6 +977,7 @@ int ib_forces_and_spread(bib_domain* d) {
 
 int ib_move_and_voxelize(bib_domain* d) {
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;
+    if (d->ms && !ms_exchange_positions(d)) return 0;      // refresh ghosts / hand particles over before voxelizing
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
         const long long n = (long long)gr.count * s.nt;

@@ -81,6 +81,11 @@ int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* l
 int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz);
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices);
+/* Multi-slab domains keep particles in slots (owned + ghost copies of neighbours' particles): global id and role
+ * (0 dead, 1 owned, 2/3 ghost of the left/right neighbour) of each slot; vertex/scalar downloads index by slot. On a single
+ * slab slot == particle index, all owned. bib_ib_particles_add must then be given the SAME global particle list on every
+ * rank (after bib_comm_init); each rank keeps what it owns, like the reference's add_particle. */
+int bib_ib_local_slots(bib_domain* d, int* global_ids, int* roles, int capacity, int* n_slots);
 /* the three phases of the wrapper functional, in its order, and all three at once */
 int bib_ib_interpolate_velocity(bib_domain* d);
 int bib_ib_compute_and_spread_forces(bib_domain* d);

@@ -19,3 +19,14 @@ def test_slab_ring_bit_identical_to_single_domain(world):
                         "--master-port", "29611", str(ROOT / "tests" / "mgpu" / "slab_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("bit-identical=True") == 3
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multislab_immersed_boundary(world):
+    """Ghost particles, partial-sum exchange and ownership hand-off across slab faces and the periodic seam."""
+    if bib.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", str(ROOT / "tests" / "mgpu" / "ib_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "phase_equal=True" in r.stdout
