@@ -93,6 +93,8 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->vel) cudaFree(d->vel);
     if (d->col_flags) cudaFree(d->col_flags);
     if (d->halo_stage) cudaFree(d->halo_stage);
+    if (d->band_mask) cudaFree(d->band_mask);
+    if (d->band_box) cudaFree(d->band_box);
     if (d->scratch) cudaFree(d->scratch);
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);
@@ -222,10 +224,11 @@ int bib_ib_interpolate_velocity(bib_domain* d) {
     // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
     return ib_interpolate(d);
 }
-int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); return ib_forces_and_spread(d); }
+int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); d->force_is_body = false; return ib_forces_and_spread(d); }
 int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib_move_and_voxelize(d); }
 int bib_ib_step(bib_domain* d) {
     BIB_ENTER(d);
+    d->force_is_body = false;      // the caller resets the force field itself (setExternalVector) in this calling sequence
     return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {

@@ -76,6 +76,10 @@ struct bib_domain {
     uint8_t* kind = nullptr;
     double* vel = nullptr;
     bool vel_full_valid = false;          // vel holds the full field of the CURRENT populations (bib_compute_velocity)
+    unsigned* band_mask = nullptr;        // [2][band_cap][512] touched-cell bitmasks of the particle bands (double buffered)
+    int* band_box = nullptr;              // [2][band_cap][6] box origin / extent the masks refer to
+    int band_cap = 0, band_cur = 0;
+    bool band_valid[2] = {false, false};
     bool force_is_body = false;           // every cell outside the particle bands holds force_body
     double force_body[3] = {0, 0, 0};
     uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags

@@ -229,20 +229,28 @@ struct FaceParams {
 template <bool HAS_KIND>
 __global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
     const LbmParams& p = q.p;
-    // enumerate the cells of one face: (a, b) over the two other dimensions
+    // all six faces in one launch: blockIdx.z = 2*dim + side; (a, b) enumerate the two other dimensions
+    FaceParams qq = q;
+    qq.face_dim = blockIdx.z >> 1; qq.face_side = blockIdx.z & 1;
+    {
+        const bool active = qq.face_dim == 0 ? (qq.face_side == 0 ? q.swap_x_lo : q.swap_x_hi) : (qq.face_dim == 1 ? p.per_y : p.per_z);
+        if (!active) return;
+    }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
+    if (b >= (qq.face_dim == 0 ? p.ny : p.nx)) return;
     int x, y, z;
-    if (q.face_dim == 0) { x = q.face_side ? p.nx - 1 : 0; y = b; z = a; if (a >= p.nz) return; }
-    else if (q.face_dim == 1) { y = q.face_side ? p.ny - 1 : 0; x = b; z = a; if (a >= p.nz) return; }
-    else { z = q.face_side ? p.nz - 1 : 0; x = b; y = a; if (a >= p.ny) return; }
+    if (q.face_dim == -1) return;
+    if (qq.face_dim == 0) { x = qq.face_side ? p.nx - 1 : 0; y = b; z = a; if (a >= p.nz) return; }
+    else if (qq.face_dim == 1) { y = qq.face_side ? p.ny - 1 : 0; x = b; z = a; if (a >= p.nz) return; }
+    else { z = qq.face_side ? p.nz - 1 : 0; x = b; y = a; if (a >= p.ny) return; }
     // a cell on several periodic faces is handled once, by the first (dim, side) that contains it
     const bool on_xlo = (x == 0) && q.swap_x_lo, on_xhi = (x == p.nx - 1) && q.swap_x_hi;
     const bool on_ylo = (y == 0) && p.per_y, on_yhi = (y == p.ny - 1) && p.per_y;
     const bool on_zlo = (z == 0) && p.per_z, on_zhi = (z == p.nz - 1) && p.per_z;
-    if (q.face_dim == 0 && q.face_side == 1 && on_xlo) return;
-    if (q.face_dim == 1 && (on_xlo || on_xhi || (q.face_side == 1 && on_ylo))) return;
-    if (q.face_dim == 2 && (on_xlo || on_xhi || on_ylo || on_yhi || (q.face_side == 1 && on_zlo))) return;
+    if (qq.face_dim == 0 && qq.face_side == 1 && on_xlo) return;
+    if (qq.face_dim == 1 && (on_xlo || on_xhi || (qq.face_side == 1 && on_ylo))) return;
+    if (qq.face_dim == 2 && (on_xlo || on_xhi || on_ylo || on_yhi || (qq.face_side == 1 && on_zlo))) return;
 
     const long long idx = (long long)(x + 1) * p.plane + (long long)y * p.nz + z;
     double f[BIB_Q];
@@ -396,12 +404,10 @@ int lbm_launch_collide_stream(bib_domain* d) {
         FaceParams q; q.p = p;
         const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
         q.swap_x_lo = d->per[0] && first; q.swap_x_hi = d->per[0] && last;
-        for (int dim = 0; dim < 3; ++dim) for (int side = 0; side < 2; ++side) {
-            bool active = dim == 0 ? (side == 0 ? q.swap_x_lo : q.swap_x_hi) : (dim == 1 ? d->per[1] : d->per[2]);
-            if (!active) continue;
-            q.face_dim = dim; q.face_side = side;
-            const int na = dim == 2 ? d->ny : d->nz, nb = dim == 0 ? d->ny : d->nx;
-            dim3 g((na + 127) / 128, nb);
+        if (q.swap_x_lo || q.swap_x_hi || d->per[1] || d->per[2]) {
+            q.face_dim = 0; q.face_side = 0;
+            const int na = std::max(d->ny, d->nz), nb = std::max(d->nx, d->ny);
+            dim3 g((na + 127) / 128, nb, 6);
             if (d->kind) k_face_swap<true><<<g, 128, 0, d->stream>>>(q);
             else k_face_swap<false><<<g, 128, 0, d->stream>>>(q);
             d->launches++;
