@@ -1,0 +1,95 @@
+"""CPU model of the multi-slab algorithm (run by tests/test_dist_cpu.py under torch.distributed with the gloo backend,
+world_size 2): every rank owns an x-slab with one ghost plane per side, collides its cells with the oracle, PUSHES the
+post-collision populations (numpy) exactly like k_collide_stream does -- periodic wrap in y/z, ghost planes in x, the
+envelope quirk only at the GLOBAL periodic faces -- and exchanges just the 5 populations that cross each face, received
+in place into the boundary planes (the NCCL halo exchange of biblbm_b200/csrc/comm.cu). The gathered result must be
+bit-identical to the oracle stepping the undivided lattice."""
+import os
+import sys
+import pathlib
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent))
+import kit  # noqa: E402
+
+PLUS_X = [10, 13, 14, 15, 16]
+MINUS_X = [1, 4, 5, 6, 7]
+
+
+def push_step(orc, slab, omega0, omega1, rank, world, per):
+    """slab: [nx][ny][nz][23] -> (new slab, ghost_lo[5][ny][nz], ghost_hi[5][ny][nz]) before the halo exchange."""
+    import ctypes as C
+    nx, ny, nz, _ = slab.shape
+    post = slab.copy()
+    orc.lib.orc_collide_cells(post.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(nx * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(0))
+    env = slab.copy()
+    orc.lib.orc_collide_cells(env.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(nx * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(1))
+    f = np.zeros((19, nx + 2, ny, nz))            # destination buffer with ghost planes
+    first, last = rank == 0, rank == world - 1
+    for i in range(19):
+        cx, cy, cz = kit.C19[i]
+        src_n = post[..., i]
+        src_e = env[..., i]
+        val = src_n.copy()
+        # populations crossing a GLOBAL periodic face come from the swapped (envelope) collision
+        if per[1]:
+            if cy == 1: val[:, -1, :] = src_e[:, -1, :]
+            if cy == -1: val[:, 0, :] = src_e[:, 0, :]
+        if per[2]:
+            if cz == 1: val[:, :, -1] = src_e[:, :, -1]
+            if cz == -1: val[:, :, 0] = src_e[:, :, 0]
+        if per[0]:
+            if cx == 1 and last: val[-1] = src_e[-1]
+            if cx == -1 and first: val[0] = src_e[0]
+        assert per[1] and per[2], "model covers periodic y/z"
+        shifted = np.roll(val, (cy, cz), axis=(1, 2))
+        f[i, 1 + cx:1 + cx + nx] = shifted        # x: into the ghost planes, no wrap
+    return f
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    orc = kit.oracle()
+    nxl, ny, nz = 5, 6, 7
+    per = (1, 1, 1)
+    rng = np.random.default_rng(5)
+    gx = nxl * world
+    cells = np.zeros((gx, ny, nz, 23))
+    cells[..., :19] = 0.01 * rng.normal(size=(gx, ny, nz, 19))
+    cells[..., 19:22] = 1e-4 * rng.normal(size=(gx, ny, nz, 3))
+    cells[..., 22] = rng.integers(0, 2, size=(gx, ny, nz))
+    slab = cells[rank * nxl:(rank + 1) * nxl].copy()
+    right, left = (rank + 1) % world, (rank - 1) % world
+    steps = 4
+    for _ in range(steps):
+        f = push_step(orc, slab, 1.5, 0.6, rank, world, per)
+        # halo: ghost plane nx+1 (c_x=+1 pops) -> right neighbour's plane 1; ghost plane 0 (c_x=-1) -> left neighbour's plane nx
+        send_r = torch.from_numpy(np.ascontiguousarray(f[PLUS_X, nxl + 1]))
+        send_l = torch.from_numpy(np.ascontiguousarray(f[MINUS_X, 0]))
+        recv_l = torch.empty_like(send_r); recv_r = torch.empty_like(send_l)
+        reqs = [dist.isend(send_r, right), dist.isend(send_l, left), dist.irecv(recv_l, left), dist.irecv(recv_r, right)]
+        for r in reqs:
+            r.wait()
+        f[PLUS_X, 1] = recv_l.numpy()
+        f[MINUS_X, nxl] = recv_r.numpy()
+        slab[..., :19] = np.moveaxis(f[:, 1:nxl + 1], 0, -1)
+    parts = [torch.empty(slab.shape, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(slab))
+    ok = True
+    if rank == 0:
+        got = torch.cat(parts, 0).numpy()
+        ref = cells
+        for _ in range(steps):
+            ref = orc.collide_and_stream(ref, per, 1.5, 0.6)
+        ok = bool(np.array_equal(got, ref))
+        print(f"gloo slab model world={world}: bit-identical={ok}")
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
