@@ -19,7 +19,7 @@ LIB_PATH = _HERE / "libbiblbm_b200.so"
 # every symbol include/biblbm_b200.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
-    "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_set_external_vector", "bib_compute_velocity",
+    "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
@@ -125,6 +125,16 @@ class Lattice:
 
     def initializeAtEquilibrium(self, rho, u, box=None):
         _check(self.lib.bib_domain_init_equilibrium(self.h, _box(box or self.full), C.c_double(rho), C.c_double(u[0]), C.c_double(u[1]), C.c_double(u[2])))
+
+    def addVelocityBoundary(self, box, direction, orientation, velocities=None):
+        """boundaryCondition.addVelocityBoundary{dir}{N|P}(box, lattice) [+ setBoundaryVelocity(lattice, box, velocities)]."""
+        _check(self.lib.bib_add_velocity_boundary(self.h, _box(box), int(direction), int(orientation)))
+        if velocities is not None:
+            self.setBoundaryVelocity(box, velocities)
+
+    def setBoundaryVelocity(self, box, velocities):
+        v = np.ascontiguousarray(velocities, dtype=np.float64)
+        _check(self.lib.bib_set_boundary_velocity(self.h, _box(box), _dptr(v)))
 
     def setExternalVector(self, F, box=None):
         _check(self.lib.bib_set_external_vector(self.h, _box(box or self.full), C.c_double(F[0]), C.c_double(F[1]), C.c_double(F[2])))

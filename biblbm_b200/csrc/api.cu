@@ -104,6 +104,7 @@ int bib_domain_destroy(bib_domain* d) {
         void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
+    for (WallPlane& w : d->walls) if (w.vel) cudaFree(w.vel);
     for (ParticleGroup& g : d->groups) { if (g.link_ks) cudaFree(g.link_ks); if (g.link_kp) cudaFree(g.link_kp); }
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -150,6 +151,16 @@ int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, dou
     if (!box) { bib_set_error("init_equilibrium: null argument"); return 0; }
     if (!(rho > 0.0)) { bib_set_error("init_equilibrium: density must be positive"); return 0; }
     return lbm_init_equilibrium(d, box, rho, ux, uy, uz);
+}
+int bib_add_velocity_boundary(bib_domain* d, const int box[6], int direction, int orientation) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("add_velocity_boundary: null argument"); return 0; }
+    return lbm_add_wall(d, box, direction, orientation);
+}
+int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* velocities) {
+    BIB_ENTER(d);
+    if (!box || !velocities) { bib_set_error("set_boundary_velocity: null argument"); return 0; }
+    return lbm_set_wall_velocity(d, box, velocities);
 }
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
     BIB_ENTER(d);

@@ -62,6 +62,12 @@ struct MultiSlabIB {
     bool ghosts_dirty = true;
 };
 
+struct WallPlane {                 // one velocity boundary plane (VelocityDirichlet + PlaneFd)
+    int dir = 1, orient = -1, coord = 0;
+    int na = 0, nb = 0;            // extent along the two in-plane axes (x,y,z order)
+    double* vel = nullptr;         // device [na][nb][3] stored boundary velocities
+};
+
 struct bib_domain {
     int device = 0;
     int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
@@ -99,6 +105,7 @@ struct bib_domain {
     int x_offset = 0;                     // global x of local plane 0
     int gnx = 0;                          // global nx
     // IB
+    std::vector<WallPlane> walls;
     std::vector<ShapeDev> shapes;
     std::vector<ParticleGroup> groups;
     int n_particles = 0;
@@ -127,6 +134,10 @@ int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double f
 int lbm_launch_velocity(bib_domain* d, const int box[6]);
 int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity);
 int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
+int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient);
+int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel);
+int lbm_apply_walls(bib_domain* d);
+int lbm_wall_velocity_fill(bib_domain* d);
 int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz);
 
 int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const int* tris, int* shape_id);

@@ -1136,6 +1136,7 @@ int ib_interpolate(bib_domain* d) {
             d->launches++;
         }
         d->band_valid[d->band_cur] = true;
+        if (!lbm_wall_velocity_fill(d)) return 0;      // wall cells report their stored boundary velocity
     } else {
         d->band_valid[0] = d->band_valid[1] = false;
     }

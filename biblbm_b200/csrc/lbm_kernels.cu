@@ -354,6 +354,95 @@ __global__ void k_fill_populations(double* f, Eq19 eq, int bx0, int by0, int bz0
     }
 }
 
+// PlaneFdBoundaryFunctional3D::processCell + VelocityDirichletBoundaryDynamics::computeRhoBar on one plane (citations and the
+// operation order: oracle/biblbm_oracle.c, orc_wall_plane). One thread per plane cell; reads the post-stream populations of
+// the wall cell and of its fluid neighbour, writes the regularised populations of the wall cell.
+struct WallParams {
+    double* f; const double* force; const double* wallvel;
+    int nx, ny, nz; long long plane, vol;
+    int dir, orient, coord, na, nb;
+    double omega;
+};
+__global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= w.nb) return;
+    const int ta = w.dir == 0 ? 1 : 0, tb = w.dir == 2 ? 1 : 2;
+    int c[3]; c[w.dir] = w.coord; c[ta] = a; c[tb] = b;
+    const long long idx = (long long)(c[0] + 1) * w.plane + (long long)c[1] * w.nz + c[2];
+    double f[BIB_Q];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) f[i] = w.f[(long long)i * w.vol + idx];
+    const double* vel = w.wallvel + ((long long)a * w.nb + b) * 3;
+    const double v[3] = {vel[0], vel[1], vel[2]};
+    const double Fd = w.force[(long long)w.dir * w.vol + idx];
+    double rhoOnWall = 0.0, rhoNormal = 0.0;
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) { const int ci = w.dir == 0 ? c_cx[i] : (w.dir == 1 ? c_cy[i] : c_cz[i]); if (ci == 0) rhoOnWall += f[i]; }
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) { const int ci = w.dir == 0 ? c_cx[i] : (w.dir == 1 ? c_cy[i] : c_cz[i]); if (ci == w.orient) rhoNormal += f[i]; }
+    const double velNormal = (double)w.orient * (v[w.dir] - 0.5 * Fd);
+    const double rhoBarW = (2.0 * rhoNormal + rhoOnWall - 1 * velNormal) / (1.0 + velNormal);
+    const double rho = rhoBarW + 1.0;
+    const int n[3] = {w.nx, w.ny, w.nz};
+    double grad[3][3];
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        if (dd == w.dir) {
+            int m[3] = {c[0], c[1], c[2]}; m[w.dir] = w.coord - w.orient;
+            const long long mi = (long long)(m[0] + 1) * w.plane + (long long)m[1] * w.nz + m[2];
+            double g[BIB_Q];
+#pragma unroll
+            for (int i = 0; i < BIB_Q; ++i) g[i] = w.f[(long long)i * w.vol + mi];
+            double rb, jx, jy, jz;
+            d_rhoBar_j(g, rb, jx, jy, jz);
+            const double invRho = 1.0 / (rb + 1.0);
+            const double u1[3] = {jx * invRho + w.force[mi] / 2.0, jy * invRho + w.force[w.vol + mi] / 2.0, jz * invRho + w.force[2 * w.vol + mi] / 2.0};
+            for (int k = 0; k < 3; ++k) grad[dd][k] = -w.orient * (-v[k] + u1[k]);
+        } else {
+            int p[3] = {c[0], c[1], c[2]}, q[3] = {c[0], c[1], c[2]};
+            p[dd] = (c[dd] + 1) % n[dd]; q[dd] = (c[dd] + n[dd] - 1) % n[dd];
+            const double* up = w.wallvel + ((long long)p[ta] * w.nb + p[tb]) * 3;
+            const double* um = w.wallvel + ((long long)q[ta] * w.nb + q[tb]) * 3;
+            for (int k = 0; k < 3; ++k) grad[dd][k] = (up[k] - um[k]) / 2.0;
+        }
+    }
+    const double sToPi = -rho / 3.0 / w.omega;
+    double pi[6];
+    pi[0] = 2.0 * grad[0][0] * sToPi; pi[3] = 2.0 * grad[1][1] * sToPi; pi[5] = 2.0 * grad[2][2] * sToPi;
+    pi[1] = (grad[0][1] + grad[1][0]) * sToPi; pi[2] = (grad[0][2] + grad[2][0]) * sToPi; pi[4] = (grad[1][2] + grad[2][1]) * sToPi;
+    const double j[3] = {rho * v[0], rho * v[1], rho * v[2]};
+    const double jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+    const double rhoBar = rho - 1.0;
+    const double invRho = 1.0 / (rhoBar + 1.0);
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) {
+        const int cc[3] = {c_cx[i], c_cy[i], c_cz[i]};
+        const double ti = i == 0 ? 1. / 3 : ((i >= 1 && i <= 3) || (i >= 10 && i <= 12) ? 1. / 18 : 1. / 36);
+        const double c_j = cc[0] * j[0] + cc[1] * j[1] + cc[2] * j[2];
+        const double eq = ti * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
+        double fNeq = 0.0; int iPi = 0;
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+            fNeq += pi[iPi] * (cc[al] * cc[al] - 1.0 / 3.0);
+            ++iPi;
+#pragma unroll
+            for (int be = al + 1; be < 3; ++be) { fNeq += pi[iPi] * 2.0 * cc[al] * cc[be]; ++iPi; }
+        }
+        fNeq *= ti * 3.0 * 3.0 / 2.0;
+        w.f[(long long)i * w.vol + idx] = eq + fNeq;
+    }
+}
+// computeVelocity on a wall cell returns the stored boundary velocity (StoreVelocityDynamics::computeVelocity)
+__global__ void k_wall_velocity_fill(double* vel, const double* __restrict__ wallvel, int dir, int coord, int na, int nb, long long plane, long long vol, int nz) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= nb) return;
+    const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+    int c[3]; c[dir] = coord; c[ta] = a; c[tb] = b;
+    const long long idx = (long long)(c[0] + 1) * plane + (long long)c[1] * nz + c[2];
+    const double* v = wallvel + ((long long)a * nb + b) * 3;
+    vel[idx] = v[0]; vel[vol + idx] = v[1]; vel[2 * vol + idx] = v[2];
+}
+
 bool box_ok(const bib_domain* d, const int box[6]) {
     return box[0] >= 0 && box[1] < d->nx && box[0] <= box[1] && box[2] >= 0 && box[3] < d->ny && box[2] <= box[3] &&
            box[4] >= 0 && box[5] < d->nz && box[4] <= box[5];
@@ -415,7 +504,55 @@ int lbm_launch_collide_stream(bib_domain* d) {
     }
     BIB_CHECK(cudaGetLastError());
     d->cur = 1 - d->cur;
-    if (d->n_ranks > 1) return comm_halo_exchange(d);
+    if (d->n_ranks > 1 && !comm_halo_exchange(d)) return 0;
+    return lbm_apply_walls(d);      // level-0 internal processors run after streaming (and after the halo is in place)
+}
+
+static bool wall_box(const bib_domain* d, const int box[6], int dir) {
+    return box_ok(d, box) && dir >= 0 && dir <= 2 && box[2 * dir] == box[2 * dir + 1];
+}
+int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient) {
+    if (!wall_box(d, box, dir) || (orient != 1 && orient != -1)) { bib_set_error("add_velocity_boundary: box must be one plane normal to direction; orientation +-1"); return 0; }
+    const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+    const int n[3] = {d->nx, d->ny, d->nz};
+    if (box[2 * ta] != 0 || box[2 * ta + 1] != n[ta] - 1 || box[2 * tb] != 0 || box[2 * tb + 1] != n[tb] - 1) {
+        bib_set_error("add_velocity_boundary: the plane must span the whole slab face"); return 0; }
+    if (!d->per[ta] || !d->per[tb]) { bib_set_error("add_velocity_boundary: in-plane directions must be periodic (edge/corner conditions are not implemented)"); return 0; }
+    WallPlane w; w.dir = dir; w.orient = orient; w.coord = box[2 * dir]; w.na = n[ta]; w.nb = n[tb];
+    BIB_CHECK(cudaMalloc(&w.vel, (size_t)w.na * w.nb * 3 * sizeof(double)));
+    BIB_CHECK(cudaMemsetAsync(w.vel, 0, (size_t)w.na * w.nb * 3 * sizeof(double), d->stream));
+    d->walls.push_back(w);
+    return 1;
+}
+int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
+    for (WallPlane& w : d->walls) {
+        if (box[2 * w.dir] == w.coord && box[2 * w.dir + 1] == w.coord) {
+            BIB_CHECK(cudaMemcpyAsync(w.vel, vel, (size_t)w.na * w.nb * 3 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+            BIB_CHECK(cudaStreamSynchronize(d->stream));
+            return 1;
+        }
+    }
+    bib_set_error("set_boundary_velocity: no velocity boundary registered on this plane");
+    return 0;
+}
+int lbm_apply_walls(bib_domain* d) {
+    for (const WallPlane& wp : d->walls) {
+        WallParams w;
+        w.f = d->f[d->cur]; w.force = d->force; w.wallvel = wp.vel; w.nx = d->nx; w.ny = d->ny; w.nz = d->nz;
+        w.plane = (long long)d->plane; w.vol = (long long)d->vol; w.dir = wp.dir; w.orient = wp.orient; w.coord = wp.coord; w.na = wp.na; w.nb = wp.nb;
+        w.omega = d->omega0;
+        k_wall_plane<<<dim3((wp.nb + 127) / 128, wp.na), 128, 0, d->stream>>>(w);
+        d->launches++;
+    }
+    if (!d->walls.empty()) BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+int lbm_wall_velocity_fill(bib_domain* d) {
+    if (!d->vel) return 1;
+    for (const WallPlane& wp : d->walls) {
+        k_wall_velocity_fill<<<dim3((wp.nb + 127) / 128, wp.na), 128, 0, d->stream>>>(d->vel, wp.vel, wp.dir, wp.coord, wp.na, wp.nb, (long long)d->plane, (long long)d->vol, d->nz);
+        d->launches++;
+    }
     return 1;
 }
 
@@ -483,7 +620,7 @@ int lbm_launch_velocity(bib_domain* d, const int box[6]) {
                                                                               (long long)d->plane, (long long)d->vol, d->nz);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
-    return 1;
+    return lbm_wall_velocity_fill(d);
 }
 
 int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity) {

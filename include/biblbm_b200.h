@@ -61,6 +61,15 @@ int bib_domain_set_celltype(bib_domain* d, const int box[6], int kind);
  * (reference src/dataProcessors/dataInitializerWrapper3D.hh:327-329, dataInitializerFunctional3D.hh:847-866) */
 int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz);
 
+/* Velocity wall planes = OnLatticeBoundaryCondition3D::addVelocityBoundary{0,1,2}{N,P} of createInterpBoundaryCondition3D
+ * (reference src/boundaryCondition/boundaryInstantiator3D.h:1017-1069: VelocityDirichletBoundaryDynamics + the level-0
+ * PlaneFdBoundaryFunctional3D executed after streaming, src/boundaryCondition/finiteDifferenceBoundaryProcessor3D.hh:52-115)
+ * and setBoundaryVelocity (src/dataProcessors/dataInitializerWrapper3D.hh:317-319). box must be one plane of thickness 1
+ * normal to `direction` (0,1,2), orientation = -1 / +1 (outward normal). velocities: [cells of box in x,y,z order][3], or NULL
+ * to keep the current values (initially 0). The two in-plane directions must be periodic. */
+int bib_add_velocity_boundary(bib_domain* d, const int box[6], int direction, int orientation);
+int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* velocities);
+
 /* F7: setExternalVector(lattice, domain, forceBeginsAt, F)   (src/dataProcessors/dataInitializerFunctional3D.hh:1144-1154) */
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz);
 /* F6: computeVelocity(lattice, velocity, domain)             (src/dataProcessors/dataAnalysisFunctional3D.hh:772-784) */

@@ -101,10 +101,39 @@ def make_ib(name, dims, per, centers, steps, seed, regulator_p=0.0):
     print(name, "ok")
 
 
+def make_shear():
+    """Couette cell with velocity planes (VelocityDirichlet + PlaneFd, the rbc_in_shear set-up) : LBM only with a frozen
+    random force/phase field, and a miniature rbc_in_shear (one RBC + position regulator)."""
+    nx, ny, nz, uw = 10, 12, 9, 0.03
+    rng = np.random.default_rng(17)
+    ext = np.zeros((nx, ny, nz, 4))
+    ext[..., :3] = 1e-5 * rng.normal(size=(nx, ny, nz, 3))
+    ext[..., 3] = rng.integers(0, 2, size=(nx, ny, nz))
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=10, dump_every=1, lbm_only=1, walls="shear", u_wall=uw, omega=1 / 0.8, omega_inner=0.5),
+                            externals=ext)
+    np.savez_compressed(HERE / "lbm_shear.npz", pop_init=out["pop_init"], pop_1=out["pop_1"], pop_2=out["pop_2"], pop_10=out["pop_10"],
+                        omega=1 / 0.8, omega_inner=0.5, u_wall=uw)
+    shape, params, rbc_pos, _ = kit.load_rbc_fixture()
+    nx, ny, nz, uw, steps = 26, 24, 22, 0.02, 4
+    c = (0.5 * (nx - 1), 0.5 * (ny - 1), 0.5 * (nz - 1))
+    pos = kit.place_particles(rbc_pos, [c], seed=3)
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=1, walls="shear", u_wall=uw, omega=1.0, omega_inner=1 / (0.5 + 8.48 * 0.5),
+                                 regulator_p=1e-2, regulator_x=c[0], regulator_y=c[1], regulator_z=c[2]),
+                            verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                vel_final_sample=out[f"vel_{steps}"][::2, ::2, ::2].copy(), omega=1.0, omega_inner=1 / (0.5 + 8.48 * 0.5), u_wall=uw, steps=steps,
+                regulator_p=1e-2, regulator_target=np.array(c))
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_rbc_in_shear.npz", **keep)
+    print("shear goldens ok")
+
+
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
     make_lbm("lbm_periodic.npz", "ppp")
     make_lbm("lbm_walls.npz", "pfp")
     make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)
+    make_shear()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -168,6 +168,46 @@ class Oracle:
         self.lib.orc_voxelize(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(pr), C.c_int(pos.shape[0]),
                               C.c_int(shape.nv), C.c_int(shape.nt), _i(shape.tris), _d(pos))
 
+    def wall_plane(self, cells, direction, orient, coord, wallvel, omega):
+        nx, ny, nz, _ = cells.shape
+        wallvel = np.ascontiguousarray(wallvel, dtype=np.float64)
+        self.lib.orc_wall_plane(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(direction), C.c_int(orient), C.c_int(coord),
+                                _d(wallvel), C.c_double(omega))
+
+    def wall_velocity_fill(self, vel, direction, coord, wallvel):
+        nx, ny, nz, _ = vel.shape
+        wallvel = np.ascontiguousarray(wallvel, dtype=np.float64)
+        self.lib.orc_wall_velocity_fill(_d(vel), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(direction), C.c_int(coord), _d(wallvel))
+
+    def ib_step(self, cells, vel, per, shape: Shape, params, vert, state, regulator_p=0.0, regulator_target=(0, 0, 0)):
+        nx, ny, nz, _ = cells.shape
+        pr = np.asarray(per, dtype=np.int32)
+        tgt = np.asarray(regulator_target, dtype=np.float64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self.lib.orc_ib_step(_d(cells), _d(vel), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(pr), C.c_int(vert.shape[0]), C.c_int(shape.nv),
+                             C.c_int(shape.nt), C.c_int(shape.nl), C.c_int(shape.npairs), _i(shape.tris), _d(shape.tri_area), _i(shape.links),
+                             _d(shape.link_len), _i(shape.pairs), _d(shape.pair_cs), C.c_double(shape.area), _d(params), _d(vert), _d(state),
+                             C.c_double(regulator_p), _d(tgt))
+
+    def shear_step(self, cells, omega0, omega1, body, u_wall_lo, u_wall_hi, shape=None, params=None, vert=None, state=None,
+                   regulator_p=0.0, regulator_target=(0, 0, 0)):
+        """One driver step of a Couette cell (x,z periodic, velocity planes at y=0 and y=ny-1: progs/common/shear_flow_setup.h:50-97),
+        in the reference's order incl. the level-0 wall functionals after streaming. Returns (new cells, velocity field)."""
+        nx, ny, nz, _ = cells.shape
+        per = (1, 0, 1)
+        vel = self.compute_velocity(cells)
+        self.wall_velocity_fill(vel, 1, 0, u_wall_lo)
+        self.wall_velocity_fill(vel, 1, ny - 1, u_wall_hi)
+        self.set_external_vector(cells, body)
+        if vert is not None and vert.shape[0] > 0:
+            self.ib_step(cells, vel, per, shape, params, vert, state, regulator_p, regulator_target)
+        else:
+            cells[..., 22] = 0.0
+        out = self.collide_and_stream(cells, per, omega0, omega1)
+        self.wall_plane(out, 1, -1, 0, u_wall_lo, omega0)
+        self.wall_plane(out, 1, 1, ny - 1, u_wall_hi, omega0)
+        return out, vel
+
     def full_step(self, cells, per, omega0, omega1, body, shape: Shape | None, params, vert, state,
                   regulator_p=0.0, regulator_target=(0, 0, 0), kind=None, envelope_swap=True):
         """One driver step in place. vert: [np][nv][9], state: [np][11]. Returns the velocity field used."""

@@ -276,3 +276,64 @@ def test_band_passes_equal_full_passes(rbc):
         b.collideAndStream()
     assert np.array_equal(a.vertices(), b.vertices())
     assert np.array_equal(a.download(), b.download())
+
+
+def _shear_lattice(g, opts=None):
+    nx, ny, nz, _ = g["pop_init"].shape
+    uw = float(g["u_wall"])
+    lo = np.zeros((nx, nz, 3)); hi = np.zeros((nx, nz, 3))
+    lo[..., 0] = -uw; hi[..., 0] = uw
+    lat = make_lattice(g["pop_init"], (1, 0, 1), float(g["omega"]), float(g["omega_inner"]), opts)
+    lat.addVelocityBoundary((0, nx - 1, 0, 0, 0, nz - 1), 1, -1, lo)             # addVelocityBoundary1N(bottomSurface)
+    lat.addVelocityBoundary((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), 1, +1, hi)   # addVelocityBoundary1P(topSurface)
+    return lat
+
+
+def test_wall_planes_vs_golden():
+    g = np.load(kit.GOLDEN / "lbm_shear.npz")
+    lat = _shear_lattice(g)
+    for s in range(1, 11):
+        lat.collideAndStream()
+        if f"pop_{s}" in g:
+            assert np.array_equal(lat.download(), g[f"pop_{s}"]), f"step {s}"
+
+
+def test_rbc_in_shear_vs_golden(rbc):
+    """BASELINE.json configs[0] (progs/rbc_in_shear) in miniature, deterministic spread: bit-identical to the reference."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_in_shear.npz")
+    lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, g["vert_init"][..., :3])
+    lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step((0.0, 0.0, 0.0))
+        assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"]), f"vertices differ at step {s}"
+        assert np.array_equal(lat.particle_scalars(), g[f"part_{s}"])
+    assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
+
+
+@pytest.mark.skipif(not kit.have_reference(), reason="compiled reference (oracle/_ref/ref_harness) not present")
+def test_rbc_in_shear_full_size_vs_live_reference(rbc):
+    """progs/rbc_in_shear at the driver's own size (97^3 lattice, deflated 626-vertex RBC in the centre, position regulator,
+    lambda = 8.48, Couette walls) against the UNMODIFIED reference run live on the host: 25 steps, production (atomic) spread."""
+    shape, params, rbc_pos, _ = rbc
+    n, uw, steps = 97, 0.0085, 25
+    c = (48.0, 48.0, 48.0)
+    pos = kit.place_particles(rbc_pos, [c], seed=1)
+    om_in = 1 / (0.5 + 8.48 * 0.5)
+    ref = kit.run_reference(dict(nx=n, ny=n, nz=n, steps=steps, dump_every=steps, walls="shear", u_wall=uw, omega=1.0, omega_inner=om_in,
+                                 regulator_p=1e-2, regulator_x=c[0], regulator_y=c[1], regulator_z=c[2]),
+                            verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    g = dict(pop_init=ref["pop_init"], omega=1.0, omega_inner=om_in, u_wall=uw)
+    lat = _shear_lattice(g)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    lat.set_regulator(1e-2, c)
+    lat.step((0.0, 0.0, 0.0), n=steps)
+    v = lat.vertices().reshape(1, -1, 9)
+    assert kit.rel_err(v[..., :3], ref[f"vert_{steps}"][..., :3]) <= TOL_POP
+    assert kit.rel_err(v[..., 6:], ref[f"vert_{steps}"][..., 6:]) <= 1e-9
+    got = lat.download()
+    assert kit.rel_err(got[..., :19], ref[f"pop_{steps}"][..., :19]) <= TOL_POP
+    assert np.array_equal(got[..., 22], ref[f"pop_{steps}"][..., 22])

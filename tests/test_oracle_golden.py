@@ -129,3 +129,40 @@ def test_live_reference_lbm_random_phase(orc):
         c = orc.collide_and_stream(c, [1, 0, 1], 1.7, 0.6)
         if s % 3 == 0:
             assert np.array_equal(c, ref[f"pop_{s}"])
+
+
+def _shear_walls(g):
+    nx, ny, nz, _ = g["pop_init"].shape
+    uw = float(g["u_wall"])
+    lo = np.zeros((nx, nz, 3)); hi = np.zeros((nx, nz, 3))
+    lo[..., 0] = -uw; hi[..., 0] = uw       # SimpleShearVelocity, progs/common/shear_flow_setup.h:5-30
+    return lo, hi
+
+
+def test_wall_planes_bit_exact(orc):
+    """VelocityDirichlet + PlaneFd velocity planes of the shear drivers, frozen random force / phase field."""
+    g = np.load(kit.GOLDEN / "lbm_shear.npz")
+    lo, hi = _shear_walls(g)
+    ny = g["pop_init"].shape[1]
+    c = g["pop_init"].copy()
+    for s in range(1, 11):
+        c = orc.collide_and_stream(c, [1, 0, 1], float(g["omega"]), float(g["omega_inner"]))
+        orc.wall_plane(c, 1, -1, 0, lo, float(g["omega"]))
+        orc.wall_plane(c, 1, 1, ny - 1, hi, float(g["omega"]))
+        if f"pop_{s}" in g:
+            assert np.array_equal(c, g[f"pop_{s}"]), f"step {s}"
+
+
+def test_rbc_in_shear_bit_exact(orc, rbc):
+    """Miniature progs/rbc_in_shear (BASELINE.json configs[0]): Couette walls, one RBC, position regulator, lambda = 8.48."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_in_shear.npz")
+    lo, hi = _shear_walls(g)
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    vel = None
+    for s in range(1, int(g["steps"]) + 1):
+        cells, vel = orc.shear_step(cells, float(g["omega"]), float(g["omega_inner"]), (0, 0, 0), lo, hi, shape, params, vert, state,
+                                    float(g["regulator_p"]), g["regulator_target"])
+        assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"])
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+    assert np.array_equal(vel[::2, ::2, ::2], g["vel_final_sample"])
