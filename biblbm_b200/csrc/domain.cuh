@@ -21,6 +21,7 @@ struct ShapeDev {
     // connectivity (device)
     int* tris = nullptr;          // [nt][3]
     double* tri_area = nullptr;   // [nt]
+    double* verts = nullptr;      // [nv][3] rest configuration (capsule FEM reference state)
     int* links = nullptr;         // [nl][2]
     double* link_len = nullptr;   // [nl]
     int* pairs = nullptr;         // [np][4]

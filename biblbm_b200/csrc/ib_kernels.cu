@@ -530,6 +530,81 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
 }
 
+// ------------------------------------------------------------------------------------------------ M2: capsule forces
+// DeformableCapsuleParticle::compute_forces (src/fsi/DeformableCapsule.hh:60-150), neo-Hookean membrane FEM; see
+// oracle/biblbm_oracle.c orc_capsule_forces for the line-by-line restatement (incl. the reference's `c` quirk). Returns
+// the contribution of triangle (v0,v1,v2) with rest corners (r0,r1,r2) and rest area A0 to its corner `i`.
+__device__ __forceinline__ V3 d_capsule_corner(V3 v0, V3 v1, V3 v2, V3 r0, V3 r1, V3 r2, double A0, double G, int i) {
+    const V3 e0 = sub(v1, v0), e1 = sub(v2, v0), e0_0 = sub(r1, r0), e1_0 = sub(r2, r0);
+    const double l = nrm(e0), lprime = nrm(e1), l0 = nrm(e0_0), l0prime = nrm(e1_0);
+    const double e0_dot_e1 = dot(e0, e1);
+    const double sin_phi = nrm(crs(e0, e1)) / (l * lprime);
+    const double cos_phi = e0_dot_e1 / (l * lprime);
+    const double sin_phi_0 = nrm(crs(e0_0, e1_0)) / (l0 * l0prime);
+    const double cos_phi_0 = dot(e0_0, e1_0) / (l0 * l0prime);
+    const double a = l / l0;
+    const double b = (lprime * cos_phi / l0prime - l * cos_phi_0 / l0) / sin_phi_0;
+    const double c = lprime * sin_phi / (lprime * sin_phi_0);
+    const double D11 = (a * a - 1.) / 2.;
+    const double D22 = (b * b + c * c - 1) / 2.;
+    const double D12 = a * b / 2.;
+    const double I1 = 2. * (D11 + D22);
+    const double I2 = I1 + 4 * (D11 * D22 - D12 * D12);
+    const double E0[3] = {e0.x, e0.y, e0.z}, E1[3] = {e1.x, e1.y, e1.z};
+    double out[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double gl = i == 0 ? E0[d] / (-l) : (i == 1 ? E0[d] / l : 0.0);
+        const double glp = i == 0 ? E1[d] / (-lprime) : (i == 1 ? 0.0 : E1[d] / lprime);
+        double gc;
+        if (i == 0) gc = (-1. / (l * lprime) + e0_dot_e1 / (l * l * l * lprime)) * E0[d] + (-1. / (l * lprime) + e0_dot_e1 / (l * lprime * lprime * lprime)) * E1[d];
+        else if (i == 1) gc = (1. / (l * lprime)) * E1[d] - (e0_dot_e1 / (l * l * l * lprime)) * E0[d];
+        else gc = (1. / (l * lprime)) * E0[d] - (e0_dot_e1 / (l * lprime * lprime * lprime)) * E1[d];
+        const double grad_D11 = (l / (l0 * l0)) * gl;
+        const double grad_D22 = (1. / (sin_phi_0 * sin_phi_0)) * (
+                (lprime / (l0prime * l0prime) - l * cos_phi * cos_phi_0 / (l0 * l0prime)) * glp +
+                (l * (cos_phi_0 * cos_phi_0) / (l0 * l0) - lprime * cos_phi * cos_phi_0 / (l0prime * l0)) * gl -
+                (l * lprime * cos_phi_0 / (l0 * l0prime)) * gc);
+        const double grad_D12 = (1. / (2. * l0prime * sin_phi_0)) * (
+                (lprime * cos_phi / l0prime - 2. * l * cos_phi_0 / l0) * gl + (l * cos_phi / l0prime) * glp + (l * lprime / l0prime) * gc);
+        const double grad_I1 = 2. * (grad_D11 + grad_D22);
+        const double grad_I2 = (2. + 4. * D22) * grad_D11 + (2. + 4. * D11) * grad_D22 - 8. * D12 * grad_D12;
+        out[d] = -G / 2. * A0 * (grad_I1 - (1. / ((1 + I2) * (1 + I2))) * grad_I2);
+    }
+    return {out[0], out[1], out[2]};
+}
+struct CapParams {
+    int nv; long long first_vertex, cap; int first_particle, count;
+    const int* tris; const double* tri_area; const double* rest;   // rest: [nv][3]
+    const int* v_tri_off; const int* v_tri;
+    double G; const int* role; int use_smem;
+};
+// One CTA per particle, per-vertex gather over incident triangles in ascending order (= the reference's accumulation order).
+__global__ void __launch_bounds__(256) k_capsule_forces(CapParams q, const double* __restrict__ vpos, double* __restrict__ vfrc) {
+    extern __shared__ double s_cp[];
+    const int pl = blockIdx.x;
+    if (q.role && q.role[q.first_particle + pl] != 1) return;
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    const double* P = vpos; long long capP = q.cap, baseP = base;
+    if (q.use_smem) {
+        for (int v = threadIdx.x; v < q.nv; v += blockDim.x) { s_cp[v] = vpos[base + v]; s_cp[q.nv + v] = vpos[q.cap + base + v]; s_cp[2 * q.nv + v] = vpos[2 * q.cap + base + v]; }
+        __syncthreads();
+        P = s_cp; capP = q.nv; baseP = 0;
+    }
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        for (int e = q.v_tri_off[v]; e < q.v_tri_off[v + 1]; ++e) {
+            const int code = q.v_tri[e], tr = code / 3, k = code % 3;
+            const int i0 = q.tris[3 * tr], i1 = q.tris[3 * tr + 1], i2 = q.tris[3 * tr + 2];
+            const V3 r0 = {q.rest[3 * i0], q.rest[3 * i0 + 1], q.rest[3 * i0 + 2]}, r1 = {q.rest[3 * i1], q.rest[3 * i1 + 1], q.rest[3 * i1 + 2]};
+            const V3 r2 = {q.rest[3 * i2], q.rest[3 * i2 + 1], q.rest[3 * i2 + 2]};
+            const V3 f = d_capsule_corner(ld3(P, capP, baseP + i0), ld3(P, capP, baseP + i1), ld3(P, capP, baseP + i2), r0, r1, r2, q.tri_area[tr], q.G, k);
+            fx += f.x; fy += f.y; fz += f.z;
+        }
+        vfrc[base + v] = fx; vfrc[q.cap + base + v] = fy; vfrc[2 * q.cap + base + v] = fz;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ I4: move + update
 // One CTA per particle. Triangle terms are computed in parallel in chunks and accumulated by one thread in triangle
 // order, so area / volume / centre of mass carry exactly the reference's sequential rounding.
@@ -954,7 +1029,7 @@ int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const 
     if (!to_device(&s.tris, s.h_tris) || !to_device(&s.tri_area, s.h_tri_area) || !to_device(&s.links, s.h_links) ||
         !to_device(&s.link_len, s.h_link_len) || !to_device(&s.pairs, s.h_pairs) || !to_device(&s.pair_cs, s.h_pair_cs) ||
         !to_device(&s.v_link_off, lo) || !to_device(&s.v_link, ll) || !to_device(&s.v_tri_off, to) || !to_device(&s.v_tri, tl) ||
-        !to_device(&s.v_pair_off, po) || !to_device(&s.v_pair, pl)) return 0;
+        !to_device(&s.v_pair_off, po) || !to_device(&s.v_pair, pl) || !to_device(&s.verts, s.h_verts)) return 0;
     d->shapes.push_back(s);
     *shape_id = (int)d->shapes.size() - 1;
     return 1;
@@ -1073,7 +1148,7 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
 }
 
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
-    if (type != 0) { bib_set_error("particles_add: only BIB_PARTICLE_RBC is implemented"); return 0; }
+    if (type != 0 && type != 1) { bib_set_error("particles_add: unknown particle type (BIB_PARTICLE_RBC, BIB_PARTICLE_CAPSULE)"); return 0; }
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("particles_add: unknown shape"); return 0; }
     if (n <= 0) return 1;
     if (d->n_ranks > 1) return ib_particles_add_multislab(d, type, shape_id, params, n, positions);
@@ -1167,6 +1242,18 @@ int ib_forces_and_spread(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
+        if (gr.type == 1) {      // BIB_PARTICLE_CAPSULE
+            CapParams c;
+            c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle; c.count = gr.count;
+            c.tris = s.tris; c.tri_area = s.tri_area; c.rest = s.verts; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri;
+            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr;
+            const size_t smem = (size_t)s.nv * 3 * sizeof(double);
+            c.use_smem = smem <= 200 * 1024;
+            if (c.use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_capsule_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_capsule_forces<<<gr.count, 256, c.use_smem ? smem : 0, d->stream>>>(c, d->vpos, d->vfrc);
+            d->launches++;
+            continue;
+        }
         RbcParams q;
         q.nv = s.nv; q.first_vertex = gr.first_vertex; q.cap = d->cap_vertices; q.first_particle = gr.first_particle; q.count = gr.count;
         q.tris = s.tris; q.tri_area = s.tri_area; q.links = s.links; q.link_len = s.link_len; q.link_ks = gr.link_ks; q.link_kp = gr.link_kp;

@@ -33,7 +33,9 @@ typedef struct bib_domain bib_domain;   /* opaque */
 enum { BIB_CELL_BULK = 0, BIB_CELL_NODYNAMICS = 1, BIB_CELL_BOUNCEBACK = 2 };
 
 /* particle types for bib_ib_particles_add (reference: fsi::RBCParticle, src/fsi/RBCParticle.h:68-100) */
-enum { BIB_PARTICLE_RBC = 0 };
+enum { BIB_PARTICLE_RBC = 0,        /* params: RBCParameters, see bib_ib_particles_add */
+       BIB_PARTICLE_CAPSULE = 1 };  /* fsi::DeformableCapsuleParticle (src/fsi/DeformableCapsule.hh:47-150, neo-Hookean FEM; the shape's
+                                       vertices are the stress-free state); params: {G, C, nu_s, kb, 0, 0, 0, 0} (CapsuleParameters) */
 
 /* bib_domain_set_option keys */
 enum {

@@ -334,11 +334,20 @@ static int run(const Config& cfg) {
         const i64 nv = mesh.nv;
         np = (i64)(pf.size() - 8) / (nv * 3);
         const ParticleShape<double>* shape = shape_library.get_by_tag("RBC");
+        const bool capsule = cfg.str("particle_type", "rbc") == "capsule";     // params = {G, C, nu_s, kb, 0, 0, 0, 0}
         for (i64 p = 0; p < np; ++p) {
-            RBCParticle<double> rbc(shape, params);
-            for (i64 n = 0; n < nv; ++n) for (int d = 0; d < 3; ++d) rbc.get_node(n).pos[d] = pf[8 + (p * nv + n) * 3 + d];
-            rbc.update();
-            fsi->add_particle(&rbc);
+            if (capsule) {
+                CapsuleParameters<double> cp; cp.G = pf[0]; cp.C = pf[1]; cp.nu_s = pf[2]; cp.kb = pf[3];
+                DeformableCapsuleParticle<double> cap(shape, cp);
+                for (i64 n = 0; n < nv; ++n) for (int d = 0; d < 3; ++d) cap.get_node(n).pos[d] = pf[8 + (p * nv + n) * 3 + d];
+                cap.update();
+                fsi->add_particle(&cap);
+            } else {
+                RBCParticle<double> rbc(shape, params);
+                for (i64 n = 0; n < nv; ++n) for (int d = 0; d < 3; ++d) rbc.get_node(n).pos[d] = pf[8 + (p * nv + n) * 3 + d];
+                rbc.update();
+                fsi->add_particle(&rbc);
+            }
         }
         if (regulator_p != 0.0) {
             regulator = new ParticlePositionRegulator<double>(

@@ -129,6 +129,24 @@ def make_shear():
     print("shear goldens ok")
 
 
+def make_capsule():
+    """Miniature progs/capsule_in_shear: Couette walls + one neo-Hookean capsule (DeformableCapsuleParticle) whose stress-free
+    state is the sphere mesh, started from an affinely pre-deformed shape so that the membrane forces are non-zero at once."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    nx, ny, nz, uw, steps = 26, 24, 22, 0.02, 4
+    c = np.array([0.5 * (nx - 1) + 0.3, 0.5 * (ny - 1) - 0.2, 0.5 * (nz - 1) + 0.1])
+    pos = (shape.verts * np.array([1.12, 0.93, 0.97]))[None] + c
+    cp = np.array([0.004, 1.0, 0.5, 0.0, 0, 0, 0, 0])           # G, C, nu_s, kb
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=1, walls="shear", u_wall=uw, omega=1.0, omega_inner=0.5,
+                                 particle_type="capsule"), verts=shape.verts, tris=shape.tris, params=cp, particle_pos=pos)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                omega=1.0, omega_inner=0.5, u_wall=uw, steps=steps, cparams=cp)
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_capsule_in_shear.npz", **keep)
+    print("capsule golden ok")
+
+
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
@@ -136,4 +154,5 @@ if __name__ == "__main__":
     make_lbm("lbm_walls.npz", "pfp")
     make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)
     make_shear()
+    make_capsule()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -168,6 +168,18 @@ class Oracle:
         self.lib.orc_voxelize(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(pr), C.c_int(pos.shape[0]),
                               C.c_int(shape.nv), C.c_int(shape.nt), _i(shape.tris), _d(pos))
 
+    def set_particle_model(self, ptype, rest_mesh=None):
+        """0 = RBC (default), 1 = neo-Hookean capsule whose rest configuration is rest_mesh [nv][3]."""
+        self._rest = None if rest_mesh is None else np.ascontiguousarray(rest_mesh, dtype=np.float64)
+        self.lib.orc_set_particle_model(C.c_int(ptype), None if self._rest is None else _d(self._rest))
+
+    def capsule_forces(self, shape: Shape, cparams, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        f = np.zeros_like(pos)
+        cp = np.ascontiguousarray(cparams, dtype=np.float64)
+        self.lib.orc_capsule_forces(C.c_int(shape.nv), C.c_int(shape.nt), _i(shape.tris), _d(shape.tri_area), _d(shape.verts), _d(cp), _d(pos), _d(f))
+        return f
+
     def wall_plane(self, cells, direction, orient, coord, wallvel, omega):
         nx, ny, nz, _ = cells.shape
         wallvel = np.ascontiguousarray(wallvel, dtype=np.float64)

@@ -337,3 +337,16 @@ def test_rbc_in_shear_full_size_vs_live_reference(rbc):
     got = lat.download()
     assert kit.rel_err(got[..., :19], ref[f"pop_{steps}"][..., :19]) <= TOL_POP
     assert np.array_equal(got[..., 22], ref[f"pop_{steps}"][..., 22])
+
+
+def test_capsule_in_shear_vs_golden(rbc):
+    """BASELINE.json configs[1] (progs/capsule_in_shear) in miniature: neo-Hookean FEM membrane, bit-identical (deterministic spread)."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_capsule_in_shear.npz")
+    lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, g["cparams"], g["vert_init"][..., :3], kind=bib.PARTICLE_CAPSULE)
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step((0.0, 0.0, 0.0))
+        assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"]), f"vertices differ at step {s}"
+    assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])

@@ -166,3 +166,20 @@ def test_rbc_in_shear_bit_exact(orc, rbc):
         assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"])
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
     assert np.array_equal(vel[::2, ::2, ::2], g["vel_final_sample"])
+
+
+def test_capsule_in_shear_bit_exact(orc, rbc):
+    """Miniature progs/capsule_in_shear (BASELINE.json configs[1]): neo-Hookean capsule between Couette walls."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_capsule_in_shear.npz")
+    lo, hi = _shear_walls(g)
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    orc.set_particle_model(1, shape.verts)
+    try:
+        for s in range(1, int(g["steps"]) + 1):
+            cells, _ = orc.shear_step(cells, float(g["omega"]), float(g["omega_inner"]), (0, 0, 0), lo, hi, shape, g["cparams"], vert, state)
+            assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"])
+            assert np.abs(vert[..., 6:]).max() > 1e-4
+    finally:
+        orc.set_particle_model(0)
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
