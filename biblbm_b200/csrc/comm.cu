@@ -96,7 +96,7 @@ void comm_destroy(bib_domain* d) {
 
 // Runs on the compute stream right after the push kernel: ghost plane nx+1 (populations with c_x=+1) goes to the right
 // neighbour's plane 1, ghost plane 0 (c_x=-1) to the left neighbour's plane nx.
-int comm_halo_exchange(bib_domain* d) {
+int comm_halo_exchange(bib_domain* d, cudaStream_t st) {
     if (d->n_ranks == 1) return 1;
     ncclComm_t comm = (ncclComm_t)d->nccl_comm;
     if (!comm) { bib_set_error("halo exchange: bib_comm_init has not been called"); return 0; }
@@ -113,21 +113,21 @@ int comm_halo_exchange(bib_domain* d) {
     NCCL_CHECK(g_nccl.GroupStart());
     for (int k = 0; k < 5; ++k) {
         double* pop = f + (size_t)kPlusX[k] * d->vol;
-        if (has_right) NCCL_CHECK(g_nccl.Send(pop + (size_t)(d->nx + 1) * n, n, ncclDouble, right, comm, d->stream));
-        if (has_left) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)k * n : pop + (size_t)1 * n, n, ncclDouble, left, comm, d->stream));
+        if (has_right) NCCL_CHECK(g_nccl.Send(pop + (size_t)(d->nx + 1) * n, n, ncclDouble, right, comm, st));
+        if (has_left) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)k * n : pop + (size_t)1 * n, n, ncclDouble, left, comm, st));
     }
     for (int k = 0; k < 5; ++k) {
         double* pop = f + (size_t)kMinusX[k] * d->vol;
-        if (has_left) NCCL_CHECK(g_nccl.Send(pop + (size_t)0 * n, n, ncclDouble, left, comm, d->stream));
-        if (has_right) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)(5 + k) * n : pop + (size_t)d->nx * n, n, ncclDouble, right, comm, d->stream));
+        if (has_left) NCCL_CHECK(g_nccl.Send(pop + (size_t)0 * n, n, ncclDouble, left, comm, st));
+        if (has_right) NCCL_CHECK(g_nccl.Recv(staged ? d->halo_stage + (size_t)(5 + k) * n : pop + (size_t)d->nx * n, n, ncclDouble, right, comm, st));
     }
     NCCL_CHECK(g_nccl.GroupEnd());
     d->launches++;
     if (staged) {
         const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
         for (int k = 0; k < 5; ++k) {
-            if (has_left) { k_halo_merge<<<grid, 256, 0, d->stream>>>(f + (size_t)kPlusX[k] * d->vol + (size_t)1 * n, d->halo_stage + (size_t)k * n, d->ny, d->nz, kCy[kPlusX[k]], kCz[kPlusX[k]], d->per[1], d->per[2]); d->launches++; }
-            if (has_right) { k_halo_merge<<<grid, 256, 0, d->stream>>>(f + (size_t)kMinusX[k] * d->vol + (size_t)d->nx * n, d->halo_stage + (size_t)(5 + k) * n, d->ny, d->nz, kCy[kMinusX[k]], kCz[kMinusX[k]], d->per[1], d->per[2]); d->launches++; }
+            if (has_left) { k_halo_merge<<<grid, 256, 0, st>>>(f + (size_t)kPlusX[k] * d->vol + (size_t)1 * n, d->halo_stage + (size_t)k * n, d->ny, d->nz, kCy[kPlusX[k]], kCz[kPlusX[k]], d->per[1], d->per[2]); d->launches++; }
+            if (has_right) { k_halo_merge<<<grid, 256, 0, st>>>(f + (size_t)kMinusX[k] * d->vol + (size_t)d->nx * n, d->halo_stage + (size_t)(5 + k) * n, d->ny, d->nz, kCy[kMinusX[k]], kCz[kMinusX[k]], d->per[1], d->per[2]); d->launches++; }
         }
         BIB_CHECK(cudaGetLastError());
     }

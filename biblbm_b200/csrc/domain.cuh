@@ -153,7 +153,7 @@ int ib_scalars_download(bib_domain* d, int first, int count, double* s11);
 
 int comm_unique_id(void* out128);
 int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);
-int comm_halo_exchange(bib_domain* d);
+int comm_halo_exchange(bib_domain* d, cudaStream_t st);
 void comm_destroy(bib_domain* d);
 int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles);
 int ib_local_slots(bib_domain* d, int* gids, int* roles, int capacity, int* n_slots);

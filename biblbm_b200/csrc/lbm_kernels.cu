@@ -32,6 +32,8 @@ struct LbmParams {
     // x handling: 0 = write into the ghost plane (neighbour slab or periodic image handled by the halo exchange),
     //             1 = wrap inside this slab (single slab, periodic x), 2 = wall face (non-periodic: free bounce-back)
     int x_lo_mode, x_hi_mode;
+    // planes handled by this launch: x = x_first + blockIdx.z * x_stride (boundary launch: planes 0 and nx-1; interior: 1..nx-2)
+    int x_first, x_stride;
 };
 
 __constant__ int c_cx[BIB_Q] = {0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0};
@@ -192,7 +194,7 @@ template <bool HAS_KIND, bool HAS_WALLS>
 __global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nz) return;
-    const int y = blockIdx.y, x = blockIdx.z;
+    const int y = blockIdx.y, x = p.x_first + (int)blockIdx.z * p.x_stride;
     const long long idx = (long long)(x + 1) * p.plane + (long long)y * p.nz + z;
 
     double f[BIB_Q];
@@ -224,6 +226,8 @@ struct FaceParams {
     int face_dim;     // 0,1,2
     int face_side;    // 0 = low, 1 = high
     int swap_x_lo, swap_x_hi;   // is this slab's x face a GLOBAL periodic face
+    int face_mask;              // bit (2*dim + side): faces handled by this launch
+    int x_select;               // 0: every plane, 1: only the slab's boundary planes x = 0 / nx-1, 2: only the interior planes
 };
 
 template <bool HAS_KIND>
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
     qq.face_dim = blockIdx.z >> 1; qq.face_side = blockIdx.z & 1;
     {
         const bool active = qq.face_dim == 0 ? (qq.face_side == 0 ? q.swap_x_lo : q.swap_x_hi) : (qq.face_dim == 1 ? p.per_y : p.per_z);
-        if (!active) return;
+        if (!active || !((q.face_mask >> blockIdx.z) & 1)) return;
     }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -244,6 +248,8 @@ __global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
     if (qq.face_dim == 0) { x = qq.face_side ? p.nx - 1 : 0; y = b; z = a; if (a >= p.nz) return; }
     else if (qq.face_dim == 1) { y = qq.face_side ? p.ny - 1 : 0; x = b; z = a; if (a >= p.nz) return; }
     else { z = qq.face_side ? p.nz - 1 : 0; x = b; y = a; if (a >= p.ny) return; }
+    if (q.x_select == 1 && x != 0 && x != p.nx - 1) return;
+    if (q.x_select == 2 && (x == 0 || x == p.nx - 1)) return;
     // a cell on several periodic faces is handled once, by the first (dim, side) that contains it
     const bool on_xlo = (x == 0) && q.swap_x_lo, on_xhi = (x == p.nx - 1) && q.swap_x_hi;
     const bool on_ylo = (y == 0) && p.per_y, on_yhi = (y == p.ny - 1) && p.per_y;
@@ -478,34 +484,65 @@ static LbmParams make_params(bib_domain* d) {
         p.x_lo_mode = (first && !d->per[0]) ? 2 : 0;
         p.x_hi_mode = (last && !d->per[0]) ? 2 : 0;
     }
+    p.x_first = 0; p.x_stride = 1;
     return p;
 }
 
+static void launch_main(bib_domain* d, const LbmParams& p, int n_planes, cudaStream_t st) {
+    if (n_planes <= 0) return;
+    int bs = d->nz >= 128 ? 128 : ((d->nz + 31) / 32) * 32;
+    dim3 grid((d->nz + bs - 1) / bs, d->ny, n_planes);
+    const bool walls = p.x_lo_mode == 2 || p.x_hi_mode == 2 || !p.per_y || !p.per_z;
+    if (d->kind) { if (walls) k_collide_stream<true, true><<<grid, bs, 0, st>>>(p); else k_collide_stream<true, false><<<grid, bs, 0, st>>>(p); }
+    else { if (walls) k_collide_stream<false, true><<<grid, bs, 0, st>>>(p); else k_collide_stream<false, false><<<grid, bs, 0, st>>>(p); }
+    d->launches++;
+}
+static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x_select, cudaStream_t st) {
+    if (!d->envelope_swap) return;
+    FaceParams q; q.p = p; q.x_select = x_select;
+    const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
+    q.swap_x_lo = d->per[0] && first; q.swap_x_hi = d->per[0] && last;
+    int active = (q.swap_x_lo ? 1 : 0) | (q.swap_x_hi ? 2 : 0) | (d->per[1] ? 12 : 0) | (d->per[2] ? 48 : 0);
+    q.face_mask = face_mask & active;
+    if (!q.face_mask) return;
+    q.face_dim = 0; q.face_side = 0;
+    const int na = std::max(d->ny, d->nz), nb = std::max(d->nx, d->ny);
+    dim3 g((na + 127) / 128, nb, 6);
+    if (d->kind) k_face_swap<true><<<g, 128, 0, st>>>(q);
+    else k_face_swap<false><<<g, 128, 0, st>>>(q);
+    d->launches++;
+}
+
+// One lattice step. Single slab: one launch over all planes (+ the periodic-face fix-up). Several slabs: the two boundary
+// planes go first, their ghost planes are exchanged over NCCL on the communication stream WHILE the interior planes are
+// processed on the compute stream (the exchange writes populations c_x=+-1 of planes 1 / nx, the interior launch writes
+// the other populations of those planes: disjoint arrays).
 int lbm_launch_collide_stream(bib_domain* d) {
     LbmParams p = make_params(d);
-    int bs = d->nz >= 128 ? 128 : ((d->nz + 31) / 32) * 32;
-    dim3 grid((d->nz + bs - 1) / bs, d->ny, d->nx);
-    const bool walls = p.x_lo_mode == 2 || p.x_hi_mode == 2 || !p.per_y || !p.per_z;
-    if (d->kind) { if (walls) k_collide_stream<true, true><<<grid, bs, 0, d->stream>>>(p); else k_collide_stream<true, false><<<grid, bs, 0, d->stream>>>(p); }
-    else { if (walls) k_collide_stream<false, true><<<grid, bs, 0, d->stream>>>(p); else k_collide_stream<false, false><<<grid, bs, 0, d->stream>>>(p); }
-    d->launches++;
-    if (d->envelope_swap) {
-        FaceParams q; q.p = p;
-        const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
-        q.swap_x_lo = d->per[0] && first; q.swap_x_hi = d->per[0] && last;
-        if (q.swap_x_lo || q.swap_x_hi || d->per[1] || d->per[2]) {
-            q.face_dim = 0; q.face_side = 0;
-            const int na = std::max(d->ny, d->nz), nb = std::max(d->nx, d->ny);
-            dim3 g((na + 127) / 128, nb, 6);
-            if (d->kind) k_face_swap<true><<<g, 128, 0, d->stream>>>(q);
-            else k_face_swap<false><<<g, 128, 0, d->stream>>>(q);
-            d->launches++;
-        }
+    if (d->n_ranks == 1 || d->nx < 3) {
+        launch_main(d, p, d->nx, d->stream);
+        launch_faces(d, p, 63, 0, d->stream);
+        BIB_CHECK(cudaGetLastError());
+        d->cur = 1 - d->cur;
+        if (d->n_ranks > 1 && !comm_halo_exchange(d, d->stream)) return 0;
+        return lbm_apply_walls(d);      // level-0 internal processors run after streaming (and after the halo is in place)
     }
+    LbmParams pb = p; pb.x_first = 0; pb.x_stride = d->nx - 1;
+    launch_main(d, pb, 2, d->stream);
+    launch_faces(d, p, 63, 1, d->stream);                   // every periodic-face fix-up of the boundary planes precedes the exchange
+    BIB_CHECK(cudaEventRecord(d->ev_compute, d->stream));
+    BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_compute, 0));
+    d->cur = 1 - d->cur;
+    if (!comm_halo_exchange(d, d->comm_stream)) return 0;
+    BIB_CHECK(cudaEventRecord(d->ev_halo, d->comm_stream));
+    d->cur = 1 - d->cur;
+    LbmParams pi = p; pi.x_first = 1; pi.x_stride = 1;
+    launch_main(d, pi, d->nx - 2, d->stream);
+    launch_faces(d, p, 60, 2, d->stream);                   // y and z faces of the interior planes
     BIB_CHECK(cudaGetLastError());
     d->cur = 1 - d->cur;
-    if (d->n_ranks > 1 && !comm_halo_exchange(d)) return 0;
-    return lbm_apply_walls(d);      // level-0 internal processors run after streaming (and after the halo is in place)
+    BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_halo, 0));
+    return lbm_apply_walls(d);
 }
 
 static bool wall_box(const bib_domain* d, const int box[6], int dir) {
