@@ -1040,8 +1040,12 @@ static void rbc_ks_kp(double l0, double G, double& ks, double& kp) {
     const double x0 = 1. / 2.2, m = 2;
     const double ks_coeff1 = 0.25 * (6. * x0 + (3 * x0 * x0 - 2 * x0 * x0 * x0) / ((1 - x0) * (1 - x0)));
     const double ks_coeff2 = x0 / (2. * (1 - x0) * (1 - x0) * (1 - x0)) + 0.25 * (1. - 1. / ((1 - x0) * (1 - x0)));
-    const double kp_coeff1 = -1. / std::pow(l0, m);
-    const double kp_coeff2 = (m + 1) / std::pow(l0, m);
+    // a genuine libm pow() call, as in the reference (m is a run-time argument there): glibc's pow(x, 2.0) differs from x*x
+    // by one ulp for a few rest lengths, so the exponent is hidden from the compiler's pow(x,2) -> x*x folding
+    static volatile double m_runtime = 2.0;
+    const double p_l0 = std::pow(l0, (double)m_runtime);
+    const double kp_coeff1 = -1. / p_l0;
+    const double kp_coeff2 = (m + 1) / p_l0;
     const double G_lhs = 4. * l0 * G / std::sqrt(3);
     ks = -kp_coeff1 * G_lhs / (ks_coeff1 * kp_coeff2 - ks_coeff2 * kp_coeff1);
     kp = ks_coeff1 * G_lhs / (ks_coeff1 * kp_coeff2 - ks_coeff2 * kp_coeff1);

@@ -355,6 +355,11 @@ static int run(const Config& cfg) {
             fsi->add_force_decorator(regulator);
         }
     }
+    ParallelPlatesBoundary<double>* plates = 0;
+    if (cfg.has("plate_y0")) {                                   // rbcs_in_shear.cpp:122-123
+        plates = new ParallelPlatesBoundary<double>(cfg.num("plate_y0", 0), cfg.num("plate_y1", ny - 1));
+        fsi->set_boundary(plates);
+    }
     fsi->init();
 
     std::auto_ptr<MultiTensorField3D<double, 3> > velocity = generateMultiTensorField<double, 3>(domain);

@@ -61,8 +61,9 @@ def make_rbc_fixture():
         G = a_lb * gamma * nu / Ca
         K_area = (poisson + 1) / (1 - poisson) * G
         k_bend = k_bend_rel * G * area
-        harness("deflate", d / "s.mesh", d / "rbc.f64", repr(G), repr(K_area), repr(k_bend), 0.59, 10000)
+        harness("deflate", d / "s.mesh", d / "rbc.f64", repr(float(G)), repr(float(K_area)), repr(float(k_bend)), 0.59, 10000)
         r = np.fromfile(d / "rbc.f64")
+        assert r[0] > 0 and r[8 + nv * 3 + 1] < 0.7 * sc[1], "deflation did not run with the intended membrane parameters"
         np.savez_compressed(HERE / "rbc626.npz", verts=verts, tris=tris.astype(np.int32), tri_area=tf[:, 0], tri_lmean=tf[:, 1],
                             links=li[:, :2].astype(np.int32), link_tri=li[:, 2:].astype(np.int32), link_len=lf,
                             pairs=pi.astype(np.int32), pair_cs=pf, scalars=sc,

@@ -173,6 +173,9 @@ class Oracle:
         self._rest = None if rest_mesh is None else np.ascontiguousarray(rest_mesh, dtype=np.float64)
         self.lib.orc_set_particle_model(C.c_int(ptype), None if self._rest is None else _d(self._rest))
 
+    def set_parallel_plates(self, on, y0=0.0, y1=0.0):
+        self.lib.orc_set_parallel_plates(C.c_int(int(on)), C.c_double(y0), C.c_double(y1))
+
     def capsule_forces(self, shape: Shape, cparams, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         f = np.zeros_like(pos)
