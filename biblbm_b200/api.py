@@ -21,7 +21,7 @@ SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
-    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
@@ -184,6 +184,10 @@ class Lattice:
 
     def set_regulator(self, p, target):
         _check(self.lib.bib_ib_set_regulator(self.h, C.c_double(p), C.c_double(target[0]), C.c_double(target[1]), C.c_double(target[2])))
+
+    def set_boundary(self, y0, y1, enabled=True):
+        """fsi.set_boundary(&ParallelPlatesBoundary(y0, y1))"""
+        _check(self.lib.bib_ib_set_parallel_plates(self.h, int(enabled), C.c_double(y0), C.c_double(y1)))
 
     def count(self):
         n_p, n_v = C.c_int(0), C.c_longlong(0)

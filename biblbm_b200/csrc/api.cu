@@ -224,6 +224,12 @@ int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double t
     d->regulator_p = p; d->regulator_target[0] = tx; d->regulator_target[1] = ty; d->regulator_target[2] = tz;
     return 1;
 }
+int bib_ib_set_parallel_plates(bib_domain* d, int enabled, double y0, double y1) {
+    BIB_ENTER(d);
+    if (enabled && !(y1 > y0)) { bib_set_error("set_parallel_plates: need y1 > y0"); return 0; }
+    d->plates = enabled ? 1 : 0; d->plate_y0 = y0; d->plate_y1 = y1;
+    return 1;
+}
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
     BIB_ENTER(d);
     if (n_particles) *n_particles = d->n_particles;

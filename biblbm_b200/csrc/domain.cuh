@@ -99,6 +99,7 @@ struct bib_domain {
     int envelope_swap = 1;
     int deterministic_spread = 0;
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
+    int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary(ParallelPlatesBoundary)
     // multi-GPU ring
     int rank = 0, n_ranks = 1;
     void* nccl_comm = nullptr;

@@ -36,6 +36,7 @@ struct Geo {
     int nxl;                 // planes owned by this slab (== nx on a single slab)
     const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
     int nv_slot;             // vertices per slot when role != NULL
+    int plates; double py0, py1;   // fsi::ParallelPlatesBoundary (walls at y = py0, py1), src/fsi/Boundary.h:300-365
 };
 // slab-local plane index of global x, or -1 when another slab owns it
 __device__ __forceinline__ bool d_in_slab(const Geo& g, int gx) { const int lx = gx - g.x_offset; return lx >= 0 && lx < g.nxl; }
@@ -64,6 +65,7 @@ __device__ __forceinline__ bool d_rect_contains(const Geo& g, double lo_enl, dou
 __device__ __forceinline__ int d_classify(const Geo& g, const double* p) {
     const double eps = 2.220446049250313e-16;
     if (!d_rect_contains(g, 1.5, 1.5, p)) return 0;
+    if (g.plates && ((p[1] + (1.5 + 1.)) > g.py1 || (p[1] - (1.5 + 1.)) < g.py0)) return 3;   // near-boundary list (ImmersedBoundaryDynamics.hh:349-350)
     const double d_bulk = 0.5 - 1.5 - eps;
     if (d_rect_contains(g, d_bulk, d_bulk, p)) return 1;
     return 2;
@@ -94,6 +96,32 @@ __device__ __forceinline__ void d_cell_velocity(const double* __restrict__ f, co
 }
 
 // ------------------------------------------------------------------------------------------------ I2: interpolation
+__device__ __forceinline__ double d_tophat(double x) { return 1. - fabs(x); }        // TopHatDirac, src/fsi/Dirac.h:55-58
+__device__ __forceinline__ double d_plates_distance(const Geo& g, const double* r) { return (r[1] < 0.5 * (g.py0 + g.py1)) ? r[1] - g.py0 : g.py1 - r[1]; }
+// GeneralInterpolator::interpolate_node for the Roma (3-point) or top-hat (2-point) kernel, from the dense velocity field
+__device__ __forceinline__ void d_general_interp(const Geo& g, const double* __restrict__ vel, const double* p, bool th, double* o) {
+    const int sup = th ? 2 : 3;
+    const double hs = th ? 1.0 : 1.5;
+    const int x0 = (int)ceil(p[0] - hs), y0 = (int)ceil(p[1] - hs), z0 = (int)ceil(p[2] - hs);
+    for (int i = x0; i <= x0 + sup - 1; ++i) {
+        const int i2 = d_remap(g, 0, i);
+        if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2)) continue;
+        const double dirac_x = th ? d_tophat((double)i - p[0]) : d_roma((double)i - p[0]);
+        for (int j = y0; j <= y0 + sup - 1; ++j) {
+            const int j2 = d_remap(g, 1, j);
+            if (j2 < 0 || j2 > g.ny - 1) continue;
+            const double dirac_xy = dirac_x * (th ? d_tophat((double)j - p[1]) : d_roma((double)j - p[1]));
+            for (int k = z0; k <= z0 + sup - 1; ++k) {
+                const int k2 = d_remap(g, 2, k);
+                if (k2 < 0 || k2 > g.nz - 1) continue;
+                const double dirac_xyz = dirac_xy * (th ? d_tophat((double)k - p[2]) : d_roma((double)k - p[2]));
+                const long long c0 = d_cell(g, i2, j2, k2);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o[c] += dirac_xyz * vel[c * g.vol + c0];
+            }
+        }
+    }
+}
 template <bool DENSE>
 __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __restrict__ f, const double* __restrict__ force,
                                                      const double* __restrict__ vel, long long nvert, long long cap,
@@ -109,7 +137,19 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
         const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
         // a stencil that reaches into a neighbouring slab is summed cell by cell; the neighbour adds its part (multi-slab only)
         if (cls == 1 && !(d_in_slab(g, d_remap(g, 0, x0)) && d_in_slab(g, d_remap(g, 0, x0) + 2))) cls = 2;
-        if (cls == 1) {
+        if (cls == 3) {
+            // interpolate_near_boundary (_interpolation.hh:181-230): blend to the 2-point kernel within 1.5..2.5 of the wall
+            const double weight = d_plates_distance(g, pp) - 1.5;
+            if (weight >= 1) d_general_interp(g, vel, p, false, o);
+            else if (weight <= 0) d_general_interp(g, vel, p, true, o);
+            else {
+                double sup[3] = {0, 0, 0}, th[3] = {0, 0, 0};
+                d_general_interp(g, vel, p, false, sup);
+                d_general_interp(g, vel, p, true, th);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o[c] = (1. - weight) * th[c] + weight * sup[c];
+            }
+        } else if (cls == 1) {
             const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
             const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
             const double dz[3] = {d_roma((double)z0 - p[2]), d_roma((double)z0 + 1. - p[2]), d_roma((double)(z0 + 2) - p[2])};
@@ -166,11 +206,49 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ I3: spreading
+__device__ __forceinline__ void d_general_spread(const Geo& g, double* force, const double* p, bool th, const double* F, bool atomic) {
+    const int sup = th ? 2 : 3;
+    const double hs = th ? 1.0 : 1.5;
+    const int x0 = (int)ceil(p[0] - hs), y0 = (int)ceil(p[1] - hs), z0 = (int)ceil(p[2] - hs);
+    for (int i = x0; i <= x0 + sup - 1; ++i) {
+        const int i2 = d_remap(g, 0, i);
+        if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2)) continue;
+        const double dirac_x = th ? d_tophat((double)i - p[0]) : d_roma((double)i - p[0]);
+        for (int j = y0; j <= y0 + sup - 1; ++j) {
+            const int j2 = d_remap(g, 1, j);
+            if (j2 < 0 || j2 > g.ny - 1) continue;
+            const double dirac_xy = dirac_x * (th ? d_tophat((double)j - p[1]) : d_roma((double)j - p[1]));
+            for (int k = z0; k <= z0 + sup - 1; ++k) {
+                const int k2 = d_remap(g, 2, k);
+                if (k2 < 0 || k2 > g.nz - 1) continue;
+                const double dirac_xyz = dirac_xy * (th ? d_tophat((double)k - p[2]) : d_roma((double)k - p[2]));
+                const long long c0 = d_cell(g, i2, j2, k2);
+                for (int c = 0; c < 3; ++c) {
+                    const double val = dirac_xyz * F[c];
+                    if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
+                }
+            }
+        }
+    }
+}
 __device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, const double* pp, const double* F, int cls, bool atomic) {
     // (multi-slab: cells owned by a neighbouring slab are skipped here and spread there from the ghost copy of the vertex)
     const double p[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};
     const int x0 = (int)ceil(p[0] - 1.5), y0 = (int)ceil(p[1] - 1.5), z0 = (int)ceil(p[2] - 1.5);
     if (cls == 1 && !(d_in_slab(g, d_remap(g, 0, x0)) && d_in_slab(g, d_remap(g, 0, x0) + 2))) cls = 2;
+    if (cls == 3) {
+        // spread_forces_near_boundary (_forces.hh:192-237)
+        const double weight = d_plates_distance(g, pp) - 1.5;
+        if (weight >= 1) d_general_spread(g, force, p, false, F, atomic);
+        else if (weight <= 0) d_general_spread(g, force, p, true, F, atomic);
+        else {
+            const double Fw[3] = {F[0] * weight, F[1] * weight, F[2] * weight};
+            const double Ft[3] = {F[0] * (1. - weight), F[1] * (1. - weight), F[2] * (1. - weight)};
+            d_general_spread(g, force, p, false, Fw, atomic);
+            d_general_spread(g, force, p, true, Ft, atomic);
+        }
+        return;
+    }
     if (cls == 1) {
         const double dx[3] = {d_roma((double)x0 - p[0]), d_roma((double)x0 + 1. - p[0]), d_roma((double)(x0 + 2) - p[0])};
         const double dy[3] = {d_roma((double)y0 - p[1]), d_roma((double)y0 + 1. - p[1]), d_roma((double)(y0 + 2) - p[1])};
@@ -221,7 +299,7 @@ __global__ void __launch_bounds__(128) k_spread_atomic(Geo g, double* force, lon
 // Deterministic mode: the reference's own order (all bulk-list vertices, then all envelope-list vertices), one thread.
 __global__ void k_spread_sequential(Geo g, double* force, long long nvert, long long cap, const double* vpos, const double* vfrc) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    for (int pass = 1; pass <= 2; ++pass)
+    for (int pass = 1; pass <= 3; ++pass)
         for (long long v = 0; v < nvert; ++v) {
             const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
             const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
@@ -629,11 +707,30 @@ __global__ void __launch_bounds__(256) k_move_update(Geo g, int nv, int nt, cons
     double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
     for (int v = threadIdx.x; v < nv; v += blockDim.x) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            double x = vpos[d * cap + base + v];
-            if (do_move) { x += vvel[d * cap + base + v]; vpos[d * cap + base + v] = x; }
-            mn[d] = fmin(mn[d], x); mx[d] = fmax(mx[d], x);
+        double x[3] = {vpos[base + v], vpos[cap + base + v], vpos[2 * cap + base + v]};
+        if (do_move) {
+            const double u[3] = {vvel[base + v], vvel[cap + base + v], vvel[2 * cap + base + v]};
+            const double old[3] = {x[0], x[1], x[2]};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) x[d] += u[d];
+            if (g.plates) {   // specular reflection (DeformableParticle3D.hh:33-50; ParallelPlatesBoundary::trace_ray / get_normal)
+                double t = (g.py1 - old[1]) / (x[1] - old[1]);
+                bool hit = (t > 0 && t < 1);
+                if (!hit) { t = (g.py0 - old[1]) / (x[1] - old[1]); hit = (t > 0 && t < 1); }
+                if (hit) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) x[d] = old[d] + t * u[d];
+                    const double n[3] = {0, (x[1] < 0.5 * (g.py0 + g.py1)) ? -1.0 : 1.0, 0};
+                    const double un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { const double vpc = u[d] - 2. * un * n[d]; x[d] += vpc * (1. - t); }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) vpos[d * cap + base + v] = x[d];
         }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], x[d]); mx[d] = fmax(mx[d], x[d]); }
     }
     // bounding box: order-independent min/max
 #pragma unroll
@@ -925,6 +1022,7 @@ Geo make_geo(const bib_domain* d) {
     g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
     g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
+    g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1;
     return g;
 }
 

@@ -91,6 +91,11 @@ int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* l
  * (RBCParameters, src/fsi/RBCParticle.h:23-60). positions: [n][nv][3]. Particles get ids in order of addition. */
 int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz);
+/* fsi.set_boundary(&ParallelPlatesBoundary(y0, y1)) (src/fsi/Boundary.h:300-365, progs/rbcs_in_shear/rbcs_in_shear.cpp:122-123): vertices
+ * within 2.5 cells of a plate interpolate / spread with the Roma kernel blended into the 2-point kernel
+ * (src/fsi/ImmersedBoundaryDynamics_interpolation.hh:181-230, _forces.hh:192-237) and are reflected specularly at the plates when
+ * advected (src/fsi/DeformableParticle3D.hh:33-50). */
+int bib_ib_set_parallel_plates(bib_domain* d, int enabled, double y0, double y1);
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices);
 /* Multi-slab domains keep particles in slots (owned + ghost copies of neighbours' particles): global id and role
  * (0 dead, 1 owned, 2/3 ghost of the left/right neighbour) of each slot; vertex/scalar downloads index by slot. On a single

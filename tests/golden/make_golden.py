@@ -148,6 +148,26 @@ def make_capsule():
     print("capsule golden ok")
 
 
+def make_plates():
+    """RBC pressed against the lower plate of a Couette cell by a body force, fsi.set_boundary(ParallelPlatesBoundary) active
+    (rbcs_in_shear set-up): exercises the near-wall vertex list, the Roma/top-hat blending and the wall reflection."""
+    shape, params, rbc_pos, _ = kit.load_rbc_fixture()
+    nx, ny, nz, uw, steps = 26, 24, 22, 0.02, 40
+    base = rbc_pos - rbc_pos.mean(0)
+    flat = np.stack([-base[:, 1], base[:, 0], base[:, 2]], 1)   # proper rotation (a plain axis swap would mirror the mesh)
+    pos = (flat + np.array([12.3, -flat[:, 1].min() + 0.004, 10.8]))[None]
+    body = (0.0, -1e-4, 0.0)
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=10, walls="shear", u_wall=uw, omega=1.0, omega_inner=0.5,
+                                 plate_y0=0, plate_y1=ny - 1, body_x=body[0], body_y=body[1], body_z=body[2]),
+                            verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                omega=1.0, omega_inner=0.5, u_wall=uw, steps=steps, body=np.array(body), plates=np.array([0.0, ny - 1.0]))
+    for s in range(10, steps + 1, 10):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_rbc_plates.npz", **keep)
+    print("plates golden ok")
+
+
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
@@ -156,4 +176,5 @@ if __name__ == "__main__":
     make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)
     make_shear()
     make_capsule()
+    make_plates()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -350,3 +350,50 @@ def test_capsule_in_shear_vs_golden(rbc):
         lat.step((0.0, 0.0, 0.0))
         assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"]), f"vertices differ at step {s}"
     assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
+
+
+def test_parallel_plates_boundary_vs_golden(rbc):
+    """rbcs_in_shear-type set-up: ParallelPlatesBoundary active, RBC pressed onto the lower plate (deterministic spread, bit-identical)."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_plates.npz")
+    lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, g["vert_init"][..., :3])
+    lat.set_boundary(float(g["plates"][0]), float(g["plates"][1]))
+    for s in range(10, int(g["steps"]) + 1, 10):
+        lat.step(g["body"], n=10)
+        assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"]), f"vertices differ at step {s}"
+    assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
+
+
+def test_wall_reflection_of_vertices_vs_oracle(orc, rbc):
+    """move_vertices with a ParallelPlatesBoundary: vertices given a velocity that carries them through a plate are reflected
+    specularly (DeformableParticle3D.hh:33-50); CUDA == oracle bit for bit, incl. the particle scalars recomputed afterwards."""
+    import ctypes as C
+    shape, params, rbc_pos, _ = rbc
+    nx, ny, nz = 26, 24, 22
+    pos = (rbc_pos - rbc_pos.mean(0) + (12.0, 7.2, 11.0))[None].copy()
+    rng = np.random.default_rng(4)
+    vel = 0.3 * rng.normal(size=pos.shape); vel[..., 1] -= 3.0          # many vertices cross y = 0 in one step
+    cells = np.zeros((nx, ny, nz, 23))
+    lat = make_lattice(cells, (1, 0, 1), 1.0, 0.5)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    lat.set_boundary(0.0, ny - 1.0)
+    v9 = lat.vertices(); v9[:, 3:6] = vel[0]
+    _check = lat.lib.bib_ib_vertices_upload(lat.h, C.c_longlong(0), C.c_longlong(v9.shape[0]), v9.ctypes.data_as(C.POINTER(C.c_double)))
+    assert _check == 1
+    lat.move_vertices_and_revoxelize()
+    got = lat.vertices()
+    p = pos[0].copy(); state = np.zeros(11)
+    orc.set_parallel_plates(1, 0.0, ny - 1.0)
+    try:
+        tr = shape.tris
+        orc.lib.orc_particle_move(C.c_int(shape.nv), C.c_int(shape.nt), tr.ctypes.data_as(C.POINTER(C.c_int)), p.ctypes.data_as(C.POINTER(C.c_double)),
+                                  np.ascontiguousarray(vel[0]).ctypes.data_as(C.POINTER(C.c_double)), C.c_int(nx), C.c_int(ny), C.c_int(nz),
+                                  np.array([1, 0, 1], dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int)), state.ctypes.data_as(C.POINTER(C.c_double)))
+    finally:
+        orc.set_parallel_plates(0)
+    assert (pos[0][:, 1] + vel[0][:, 1] < 0).sum() > 50 and p[:, 1].min() >= 0.0
+    assert np.array_equal(got[:, :3], p)
+    assert np.array_equal(lat.particle_scalars()[0], state)

@@ -183,3 +183,32 @@ def test_capsule_in_shear_bit_exact(orc, rbc):
     finally:
         orc.set_particle_model(0)
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+
+
+def test_parallel_plates_boundary_bit_exact(orc, rbc):
+    """fsi.set_boundary(ParallelPlatesBoundary): near-wall list, Roma/top-hat blending, specular reflection (40 steps)."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_plates.npz")
+    lo, hi = _shear_walls(g)
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    orc.set_parallel_plates(1, float(g["plates"][0]), float(g["plates"][1]))
+    try:
+        classes = {orc.classify(p, cells.shape[:3], (1, 0, 1)) for p in vert[0, :, :3]}
+        assert classes == {1, 3}
+        for s in range(1, int(g["steps"]) + 1):
+            cells, _ = orc.shear_step(cells, float(g["omega"]), float(g["omega_inner"]), g["body"], lo, hi, shape, params, vert, state)
+            if s % 10 == 0:
+                assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"]), f"step {s}"
+    finally:
+        orc.set_parallel_plates(0)
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+
+
+def test_golden_membrane_forces_are_not_trivial():
+    """Guards the fixtures themselves: the RBC goldens must carry real membrane stiffness and non-zero vertex forces."""
+    z = np.load(kit.GOLDEN / "rbc626.npz")
+    assert z["rbc_params"][0] > 1e-3 and z["rbc_params"][6] > 1e-3 and z["rbc_area_volume"][1] < 0.7 * z["scalars"][1]
+    for name in ["ib_rbc1", "ib_rbc2_pfp", "ib_rbc_in_shear", "ib_rbc_plates"]:
+        g = np.load(kit.GOLDEN / f"{name}.npz")
+        last = max(int(k.split("_")[1]) for k in g.files if k.startswith("vert_") and k.split("_")[1].isdigit())
+        assert np.abs(g[f"vert_{last}"][..., 6:]).max() > 1e-8, name
