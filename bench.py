@@ -293,13 +293,15 @@ def ours(args):
     #      (vertex state for write_lightweight_particle_data / VTK, particle scalars for the volume diagnostics)
     n_slots = lat.count()[0]
     d2h = lat.count()[1] * 72 + n_slots * 88
+    host_v = torch.empty((max(1, lat.count()[1]), 9), dtype=torch.float64, pin_memory=True).numpy()     # page-locked result buffers
+    host_s = torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy()
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
         step(1)
         if n_rbc > 0:
-            lat.vertices()
-            lat.particle_scalars()
+            lat.vertices(out=host_v)
+            lat.particle_scalars(out=host_s)
         else:
             lat.sync()
     barrier()

@@ -215,17 +215,21 @@ class Lattice:
     def ib_step(self):
         _check(self.lib.bib_ib_step(self.h))
 
-    def vertices(self, first=0, count=None):
+    def vertices(self, first=0, count=None, out=None):
+        """fsi::Vertex records {pos, vel, force}; `out` may be a preallocated (ideally page-locked) float64 array."""
         if count is None:
             count = self.count()[1] - first
-        out = np.empty((count, 9), dtype=np.float64)
+        if out is None:
+            out = np.empty((count, 9), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size >= count * 9 and out.flags["C_CONTIGUOUS"]
         _check(self.lib.bib_ib_vertices_download(self.h, C.c_longlong(first), C.c_longlong(count), _dptr(out)))
         return out
 
-    def particle_scalars(self, first=0, count=None):
+    def particle_scalars(self, first=0, count=None, out=None):
         if count is None:
             count = self.count()[0] - first
-        out = np.empty((count, 11), dtype=np.float64)
+        if out is None:
+            out = np.empty((count, 11), dtype=np.float64)
         _check(self.lib.bib_ib_particle_scalars_download(self.h, int(first), int(count), _dptr(out)))
         return out
 

@@ -96,6 +96,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->band_mask) cudaFree(d->band_mask);
     if (d->band_box) cudaFree(d->band_box);
     if (d->scratch) cudaFree(d->scratch);
+    if (d->pinned) cudaFreeHost(d->pinned);
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);
     if (d->vfrc) cudaFree(d->vfrc);

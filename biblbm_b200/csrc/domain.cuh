@@ -120,6 +120,7 @@ struct bib_domain {
     double* pstate = nullptr; // [cap_particles][11] area, volume, com[3], bbox[6]
     int* p_first_vertex = nullptr;   // [cap_particles]
     void* scratch = nullptr; size_t scratch_bytes = 0;
+    void* pinned = nullptr; size_t pinned_bytes = 0;      // pinned host staging for device->host result reads
     MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 

@@ -1406,15 +1406,52 @@ int ib_move_and_voxelize(bib_domain* d) {
     return 1;
 }
 
+// SoA device arrays -> fsi::Vertex AoS {pos, vel, force}: packed on the device, one D2H copy into a pinned staging buffer
+__global__ void k_pack_vertices(double* __restrict__ out, const double* __restrict__ vpos, const double* __restrict__ vvel,
+                                const double* __restrict__ vfrc, long long cap, long long first, long long count) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count * 9; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = t / 9; const int k = (int)(t % 9);
+        const double* src = k < 3 ? vpos : (k < 6 ? vvel : vfrc);
+        out[t] = src[(long long)(k % 3) * cap + first + v];
+    }
+}
+static bool ensure_pinned(bib_domain* d, size_t bytes) {
+    if (d->pinned_bytes >= bytes) return true;
+    if (d->pinned) cudaFreeHost(d->pinned);
+    d->pinned = nullptr; d->pinned_bytes = 0;
+    if (!bib_cuda_ok(cudaHostAlloc(&d->pinned, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+    d->pinned_bytes = bytes;
+    return true;
+}
+static bool ensure_ib_scratch(bib_domain* d, size_t bytes) {
+    if (d->scratch_bytes >= bytes) return true;
+    if (d->scratch) cudaFree(d->scratch);
+    d->scratch = nullptr; d->scratch_bytes = 0;
+    if (!bib_cuda_ok(cudaMalloc(&d->scratch, bytes), "cudaMalloc(scratch)")) return false;
+    d->scratch_bytes = bytes;
+    return true;
+}
 int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9) {
     if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_download: range"); return 0; }
     if (count == 0) return 1;
-    std::vector<double> tmp((size_t)count * 9);
-    const double* src[3] = {d->vpos, d->vvel, d->vfrc};
-    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
-        BIB_CHECK(cudaMemcpyAsync(tmp.data() + (size_t)(a * 3 + c) * count, src[a] + (size_t)c * d->cap_vertices + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    const size_t bytes = (size_t)count * 9 * sizeof(double);
+    if (!ensure_ib_scratch(d, bytes)) return 0;
+    const int grid = (int)std::min<long long>((count * 9 + 255) / 256, 148 * 16);
+    k_pack_vertices<<<grid, 256, 0, d->stream>>>((double*)d->scratch, d->vpos, d->vvel, d->vfrc, d->cap_vertices, first, count);
+    d->launches++;
+    // a caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister) receives the DMA directly
+    cudaPointerAttributes attr;
+    const bool user_pinned = cudaPointerGetAttributes(&attr, v9) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (user_pinned) {
+        BIB_CHECK(cudaMemcpyAsync(v9, d->scratch, bytes, cudaMemcpyDeviceToHost, d->stream));
+        BIB_CHECK(cudaStreamSynchronize(d->stream));
+        return 1;
+    }
+    if (!ensure_pinned(d, bytes)) return 0;
+    BIB_CHECK(cudaMemcpyAsync(d->pinned, d->scratch, bytes, cudaMemcpyDeviceToHost, d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->stream));
-    for (long long v = 0; v < count; ++v) for (int k = 0; k < 9; ++k) v9[(size_t)v * 9 + k] = tmp[(size_t)k * count + v];
+    std::memcpy(v9, d->pinned, bytes);
     return 1;
 }
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {
