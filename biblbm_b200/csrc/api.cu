@@ -167,6 +167,12 @@ int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double f
     BIB_ENTER(d);
     if (!box) { bib_set_error("set_external_vector: null argument"); return 0; }
     const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    // Every cell outside the bands the last spread touched still holds the same body force: reset the bands only. Needs this
+    // step's interpolation to have run already (it rotates the band masks), i.e. the calling order of bib_step.
+    if (full && d->force_is_body && d->force_body[0] == fx && d->force_body[1] == fy && d->force_body[2] == fz) {
+        if (d->n_particles == 0) return 1;
+        if (d->interp_since_spread) return ib_band_reset(d, fx, fy, fz);
+    }
     d->force_is_body = full;
     if (full) { d->force_body[0] = fx; d->force_body[1] = fy; d->force_body[2] = fz; }
     return lbm_launch_set_external(d, box, fx, fy, fz);
@@ -182,6 +188,13 @@ int bib_velocity_download(bib_domain* d, const int box[6], double* velocity) {
     BIB_ENTER(d);
     if (!box || !velocity) { bib_set_error("velocity_download: null argument"); return 0; }
     return lbm_velocity_download(d, box, velocity);
+}
+int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity) {
+    BIB_ENTER(d);
+    if (!box || !velocity) { bib_set_error("velocity_upload: null argument"); return 0; }
+    if (!lbm_velocity_upload(d, box, velocity)) return 0;
+    d->vel_full_valid = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    return 1;
 }
 int bib_collide_and_stream(bib_domain* d) {
     BIB_ENTER(d);
@@ -242,11 +255,10 @@ int bib_ib_interpolate_velocity(bib_domain* d) {
     // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
     return ib_interpolate(d);
 }
-int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); d->force_is_body = false; return ib_forces_and_spread(d); }
+int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); return ib_forces_and_spread(d); }
 int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib_move_and_voxelize(d); }
 int bib_ib_step(bib_domain* d) {
     BIB_ENTER(d);
-    d->force_is_body = false;      // the caller resets the force field itself (setExternalVector) in this calling sequence
     return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
@@ -268,6 +280,12 @@ int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int coun
     BIB_ENTER(d);
     if (count > 0 && !scalars11) { bib_set_error("particle_scalars_download: null argument"); return 0; }
     return ib_scalars_download(d, first_particle, count, scalars11);
+}
+int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count, const double* scalars11) {
+    BIB_ENTER(d);
+    if (count > 0 && !scalars11) { bib_set_error("particle_scalars_upload: null argument"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("particle_scalars_upload: single-slab domains only"); return 0; }
+    return ib_scalars_upload(d, first_particle, count, scalars11);
 }
 
 // One driver step: the velocity the IB interpolates is u = j(f^t)/rho + F^{t-1}/2 evaluated on demand from the current

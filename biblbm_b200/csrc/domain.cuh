@@ -88,6 +88,7 @@ struct bib_domain {
     int band_cap = 0, band_cur = 0;
     bool band_valid[2] = {false, false};
     bool force_is_body = false;           // every cell outside the particle bands holds force_body
+    bool interp_since_spread = false;     // the band masks of the last spread are in buffer 1 - band_cur (ib_interpolate ran since)
     double force_body[3] = {0, 0, 0};
     uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags
     cudaStream_t stream = nullptr;
@@ -136,6 +137,7 @@ int lbm_launch_download(bib_domain* d, const int box[6], double* cells);
 int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double fy, double fz);
 int lbm_launch_velocity(bib_domain* d, const int box[6]);
 int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity);
+int lbm_velocity_upload(bib_domain* d, const int box[6], const double* velocity);
 int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
 int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient);
 int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel);
@@ -151,7 +153,9 @@ int ib_forces_and_spread(bib_domain* d);
 int ib_move_and_voxelize(bib_domain* d);
 int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9);
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9);
+int ib_update_all(bib_domain* d, int do_move);
 int ib_scalars_download(bib_domain* d, int first, int count, double* s11);
+int ib_scalars_upload(bib_domain* d, int first, int count, const double* s11);
 
 int comm_unique_id(void* out128);
 int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);

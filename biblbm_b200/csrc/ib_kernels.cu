@@ -1317,6 +1317,7 @@ int ib_interpolate(bib_domain* d) {
     } else {
         d->band_valid[0] = d->band_valid[1] = false;
     }
+    d->interp_since_spread = true;
     const int bs = 128;
     const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
     k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
@@ -1342,6 +1343,7 @@ int ib_band_reset(bib_domain* d, double fx, double fy, double fz) {
 
 int ib_forces_and_spread(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
+    d->interp_since_spread = false;
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
         if (gr.type == 1) {      // BIB_PARTICLE_CAPSULE
@@ -1462,6 +1464,14 @@ int ib_vertices_upload(bib_domain* d, long long first, long long count, const do
     double* dst[3] = {d->vpos, d->vvel, d->vfrc};
     for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
         BIB_CHECK(cudaMemcpyAsync(dst[a] + (size_t)c * d->cap_vertices + first, tmp.data() + (size_t)(a * 3 + c) * count, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    if (d->ms) d->ms->ghosts_dirty = true;
+    return ib_update_all(d, 0);        // area, volume, centre of mass, bounding box follow the new positions (ParticleBase3D::update)
+}
+int ib_scalars_upload(bib_domain* d, int first, int count, const double* s11) {
+    if (first < 0 || count < 0 || first + count > d->n_particles) { bib_set_error("particle_scalars_upload: range"); return 0; }
+    if (count == 0) return 1;
+    BIB_CHECK(cudaMemcpyAsync(d->pstate + (size_t)first * 11, s11, (size_t)count * 11 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     return 1;
 }

@@ -341,6 +341,15 @@ __global__ void k_pack_velocity(double* __restrict__ out, const double* vel, int
         out[t * 3] = vel[idx]; out[t * 3 + 1] = vel[vol + idx]; out[t * 3 + 2] = vel[2 * vol + idx];
     }
 }
+__global__ void k_unpack_velocity(const double* __restrict__ in, double* vel, int bx0, int by0, int bz0, int bnx, int bny, int bnz,
+                                  long long plane, long long vol, int nz) {
+    const long long n = (long long)bnx * bny * bnz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
+        const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        vel[idx] = in[t * 3]; vel[vol + idx] = in[t * 3 + 1]; vel[2 * vol + idx] = in[t * 3 + 2];
+    }
+}
 __global__ void k_set_kind(uint8_t* kind, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, int nz, uint8_t v) {
     const long long n = (long long)bnx * bny * bnz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -670,6 +679,25 @@ int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity) {
                                                           (long long)d->plane, (long long)d->vol, d->nz);
     d->launches++;
     BIB_CHECK(cudaMemcpyAsync(velocity, d->scratch, (size_t)n * 3 * 8, cudaMemcpyDeviceToHost, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}
+
+// the driver's (possibly host-edited) TensorField3D becomes the field the IB interpolates from
+int lbm_velocity_upload(bib_domain* d, const int box[6], const double* velocity) {
+    if (!box_ok(d, box)) { bib_set_error("velocity_upload: box outside the slab"); return 0; }
+    if (!d->vel) {
+        BIB_CHECK(cudaMalloc(&d->vel, d->vol * 3 * sizeof(double)));
+        BIB_CHECK(cudaMemsetAsync(d->vel, 0, d->vol * 3 * sizeof(double), d->stream));
+        d->bytes += (long long)d->vol * 3 * 8;
+    }
+    const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
+    const long long n = (long long)bnx * bny * bnz;
+    if (!ensure_scratch(d, (size_t)n * 3 * 8)) return 0;
+    BIB_CHECK(cudaMemcpyAsync(d->scratch, velocity, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, d->stream));
+    k_unpack_velocity<<<grid_for(n, 256), 256, 0, d->stream>>>((const double*)d->scratch, d->vel, box[0], box[2], box[4], bnx, bny, bnz,
+                                                            (long long)d->plane, (long long)d->vol, d->nz);
+    d->launches++;
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     return 1;
 }

@@ -77,6 +77,10 @@ int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double f
 /* F6: computeVelocity(lattice, velocity, domain)             (src/dataProcessors/dataAnalysisFunctional3D.hh:772-784) */
 int bib_compute_velocity(bib_domain* d, const int box[6]);
 int bib_velocity_download(bib_domain* d, const int box[6], double* velocity);
+/* the IB interpolates from the TensorField3D the driver passes (ImmersedBoundaryDynamics3D::interpolate_velocity(domain, velocity),
+ * src/fsi/ImmersedBoundaryDynamics_interpolation.hh:236-276); a driver that edits the field on the host after computeVelocity
+ * (CouetteVelocityExtrapolator, progs/common/shear_flow_setup.h:121-183) hands the edited field back with this call */
+int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity);
 /* F1-F5: one lattice.collideAndStream() */
 int bib_collide_and_stream(bib_domain* d);
 
@@ -111,6 +115,11 @@ int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long co
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
 /* per particle {area, volume, com[3], bbox x0,x1,y0,y1,z0,z1} (ParticleBase3D::area/volume/center_of_mass/bounding_box) */
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11);
+/* The reference caches these per particle and refreshes them only in update() (after a move); a particle that was translated
+ * or rotated on the host keeps the values computed before (ParticleBase3D::set_center_of_mass, src/fsi/ParticleBase.hh). A host
+ * mirror hands its cached values over with this call so that the first force evaluation sees exactly what the reference sees;
+ * bib_ib_particles_add / bib_ib_vertices_upload recompute them from the positions. Single-slab domains. */
+int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count, const double* scalars11);
 
 /* ---- one whole driver time step, in the order every reference driver issues it
  *      (progs/rbc_in_shear/rbc_in_shear.cpp:154-186): computeVelocity -> setExternalVector(body) -> IB wrapper ->

@@ -1,0 +1,55 @@
+#!/usr/bin/env bash
+# Compiles the reference's own drivers (progs/*) against the B200 binding: the overlay include directory comes before the
+# reference's src/ so that "fsi/headers.h" / "fsi/headers.hh" resolve to overlay/fsi/*, which include the reference headers
+# unchanged (#include_next) and add the bindings of overlay/biblbm_overlay/. Nothing of the reference is copied into this
+# repository: sources are compiled where they lie under /root/reference; binaries land in overlay/_build/ (git-ignored).
+#
+#   overlay/build_drivers.sh                 # every supported driver, unchanged source  -> overlay/_build/<driver>
+#   plus, for the parity tests, a parameter-patched copy (step count / mesh file / output cadence read from the environment;
+#   the time loop and all calls are untouched) built twice: against the binding (-> overlay/_build/<driver>_short_b200) and
+#   against the pure reference (-> oracle/_ref/<driver>_short_cpu).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(dirname "$HERE")"
+REF="${BIBLBM_REFERENCE:-/root/reference}"
+OUT="$HERE/_build"
+REFOUT="$ROOT/oracle/_ref"
+if [ ! -d "$REF/src" ]; then echo "reference not present at $REF (prebuilt binaries in overlay/_build are used)"; exit 0; fi
+[ -f "$REFOUT/libplb_ref.a" ] || "$ROOT/oracle/build_ref.sh" >/dev/null
+[ -f "$ROOT/biblbm_b200/libbiblbm_b200.so" ] || python "$ROOT/biblbm_b200/build.py" >/dev/null
+mkdir -p "$OUT/src"
+BASE="-std=gnu++98 -fpermissive -w -O2 -DPLB_MPI_PARALLEL -I$ROOT/oracle/mpi_shim"
+REFINC="-I$REF/src -I$REF/externalLibraries -I$REF/progs"
+B200="-I$HERE -I$ROOT/include"
+LINK_B200="$REFOUT/libplb_ref.a -L$ROOT/biblbm_b200 -lbiblbm_b200 -Wl,-rpath,\$ORIGIN/../../biblbm_b200"
+
+build() {   # build <out> <src> <driver dir> <b200|cpu>
+  local out="$1" src="$2" dir="$3" kind="$4"
+  if [ -f "$out" ] && [ "$out" -nt "$src" ] && [ "$out" -nt "$HERE/biblbm_overlay/impl.hh" ] && [ "$out" -nt "$HERE/biblbm_overlay/decl.h" ] \
+     && [ "$out" -nt "$ROOT/include/biblbm_b200.h" ]; then return; fi
+  echo "building $out"
+  if [ "$kind" = b200 ]; then g++ $BASE $B200 $REFINC -I"$dir" "$src" $LINK_B200 -o "$out"
+  else g++ $BASE $REFINC -I"$dir" "$src" "$REFOUT/libplb_ref.a" -o "$out"; fi
+}
+
+# parameter patch: literal values -> environment (defaults = the driver's own values)
+patch_params() {  # patch_params <driver.cpp> <out.cpp>
+  sed -E \
+    -e 's|^(\s*)plint Nt = ([0-9]+);|\1plint Nt = getenv("BIB_NT") ? atol(getenv("BIB_NT")) : \2;|' \
+    -e 's|^(\s*)plint output_interval = ([0-9]+);|\1plint output_interval = getenv("BIB_OUTPUT_INTERVAL") ? atol(getenv("BIB_OUTPUT_INTERVAL")) : \2;|' \
+    -e 's|for\(int i = 0; i < 13; \+\+i\) \{|for(int i = 0; i < (getenv("BIB_NCASES") ? atoi(getenv("BIB_NCASES")) : 13); ++i) {|' \
+    -e 's|^(\s*)const char \* mesh_file = "sphere_dx0_33.msh";|\1const char * mesh_file = getenv("BIB_MESH") ? getenv("BIB_MESH") : "sphere_dx0_33.msh";|' \
+    -e 's|shrink_volume\(0.59, 40000\)|shrink_volume(0.59, getenv("BIB_SHRINK_ITERS") ? atol(getenv("BIB_SHRINK_ITERS")) : 40000)|' \
+    "$1" > "$2"
+}
+
+DRIVERS="${@:-rbc_in_shear}"
+for drv in $DRIVERS; do
+  dir="$REF/progs/$drv"
+  src="$(ls "$dir"/*.cpp | head -1)"
+  build "$OUT/$drv" "$src" "$dir" b200                       # the unchanged driver
+  patch_params "$src" "$OUT/src/${drv}_short.cpp.new"
+  if ! cmp -s "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp" 2>/dev/null; then mv "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp"; else rm "$OUT/src/${drv}_short.cpp.new"; fi
+  build "$OUT/${drv}_short_b200" "$OUT/src/${drv}_short.cpp" "$dir" b200
+  build "$REFOUT/${drv}_short_cpu" "$OUT/src/${drv}_short.cpp" "$dir" cpu
+done

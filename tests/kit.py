@@ -383,3 +383,16 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     s = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (s if s > 0 else 1.0))
+
+
+def write_gmsh(path, verts, tris):
+    """gmsh 2.1 ASCII triangle mesh, the format ParticleShapeLibrary::read_and_store_mesh reads (reference
+    src/fsi/ParticleShapeFactory.hh:105-117); %.17g keeps the doubles exact."""
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.1 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(verts))
+        for i, v in enumerate(verts):
+            f.write("%d %.17g %.17g %.17g\n" % (i + 1, v[0], v[1], v[2]))
+        f.write("$EndNodes\n$Elements\n%d\n" % len(tris))
+        for i, t in enumerate(tris):
+            f.write("%d 2 3 0 1 0 %d %d %d\n" % (i + 1, t[0] + 1, t[1] + 1, t[2] + 1))
+        f.write("$EndElements\n")
