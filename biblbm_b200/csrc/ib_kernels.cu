@@ -36,6 +36,7 @@ struct Geo {
     int nxl;                 // planes owned by this slab (== nx on a single slab)
     const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
     int nv_slot;             // vertices per slot when role != NULL
+    const uint8_t* kind;     // cell kinds (NULL = all bulk)
     int plates; double py0, py1;   // fsi::ParallelPlatesBoundary (walls at y = py0, py1), src/fsi/Boundary.h:300-365
 };
 // slab-local plane index of global x, or -1 when another slab owns it
@@ -987,7 +988,8 @@ __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __re
         long long idx;
         if (!d_band_cell(g, b, t, idx)) continue;
         double u[3];
-        d_cell_velocity(f, force, g.vol, idx, u);
+        if (g.kind && g.kind[idx] != 0) u[0] = u[1] = u[2] = 0.0;       // NoDynamics / BounceBack: computeVelocity gives 0
+        else d_cell_velocity(f, force, g.vol, idx, u);
         vel[idx] = u[0]; vel[g.vol + idx] = u[1]; vel[2 * g.vol + idx] = u[2];
     }
 }
@@ -1022,7 +1024,7 @@ Geo make_geo(const bib_domain* d) {
     g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
     g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
-    g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1;
+    g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1; g.kind = d->kind;
     return g;
 }
 

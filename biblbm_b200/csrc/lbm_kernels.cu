@@ -315,12 +315,14 @@ __global__ void k_set_external(double* force, int bx0, int by0, int bz0, int bnx
         force[idx] = fx; force[vol + idx] = fy; force[2 * vol + idx] = fz;
     }
 }
-__global__ void k_velocity(const double* __restrict__ f, const double* __restrict__ force, double* vel,
+// NoDynamics / BounceBack cells report zero velocity (their computeVelocity, src/core/dynamics.hh:763-770,940-943)
+__global__ void k_velocity(const double* __restrict__ f, const double* __restrict__ force, double* vel, const uint8_t* __restrict__ kind,
                            int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
     const long long n = (long long)bnx * bny * bnz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
         const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
+        if (kind && kind[idx] != 0) { vel[idx] = 0.0; vel[vol + idx] = 0.0; vel[2 * vol + idx] = 0.0; continue; }
         double c[BIB_Q];
 #pragma unroll
         for (int i = 0; i < BIB_Q; ++i) c[i] = f[(long long)i * vol + idx];
@@ -662,7 +664,7 @@ int lbm_launch_velocity(bib_domain* d, const int box[6]) {
         d->bytes += (long long)d->vol * 3 * 8;
     }
     const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
-    k_velocity<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->f[d->cur], d->force, d->vel, box[0], box[2], box[4], bnx, bny, bnz,
+    k_velocity<<<grid_for((long long)bnx * bny * bnz, 256), 256, 0, d->stream>>>(d->f[d->cur], d->force, d->vel, d->kind, box[0], box[2], box[4], bnx, bny, bnz,
                                                                               (long long)d->plane, (long long)d->vol, d->nz);
     d->launches++;
     BIB_CHECK(cudaGetLastError());

@@ -256,7 +256,12 @@ inline void before_host_access(const Lattice& lattice, bool may_write) {
     Twin* t = find_twin(lattice);
     if (!t) return;
     sync_to_host(*t);
-    if (may_write) { t->device_valid = false; t->velocity_evaluable = false; }
+    if (may_write) {
+        // the host may change populations / externals: materialise a pending computeVelocity result first, it refers to the state as it is now
+        if (t->velocity && t->velocity_pending && !t->velocity_host_valid && t->velocity_evaluable
+            && multiBlockRegistration3D().find(t->velocity_id) == t->velocity) velocity_to_host(*t);
+        t->device_valid = false; t->velocity_evaluable = false;
+    }
 }
 
 inline void before_host_access(const VelocityField& field, bool may_write) {

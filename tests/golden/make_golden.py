@@ -72,6 +72,19 @@ def make_rbc_fixture():
         print("rbc626.npz: nv", nv, "nt", nt, "links", len(lf), "pairs", len(pf))
 
 
+def make_mesh_fixture(msh, out):
+    """A reference mesh file as arrays (vertices, triangles), read by the reference's own gmsh reader."""
+    with tempfile.TemporaryDirectory() as d:
+        d = pathlib.Path(d)
+        harness("mesh2bin", msh, d / "s.mesh")
+        blob = open(d / "s.mesh", "rb").read()
+        nv, nt = (int(v) for v in np.frombuffer(blob, dtype=np.int64, count=2))
+        verts = np.frombuffer(blob, dtype=np.float64, count=nv * 3, offset=16).reshape(nv, 3)
+        tris = np.frombuffer(blob, dtype=np.int64, count=nt * 3, offset=16 + nv * 24).reshape(nt, 3)
+        np.savez_compressed(HERE / out, verts=verts, tris=tris.astype(np.int32))
+        print(out, "nv", nv, "nt", nt)
+
+
 def make_lbm(name, per):
     nx, ny, nz = 12, 10, 14
     ext = kit.synthetic_externals(nx, ny, nz, seed=3)
@@ -171,6 +184,7 @@ def make_plates():
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
+    make_mesh_fixture("/root/reference/progs/capsule_in_shear/sphere_r6_TRImesh_1046n_2088el.msh", "sphere1046.npz")
     make_lbm("lbm_periodic.npz", "ppp")
     make_lbm("lbm_walls.npz", "pfp")
     make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)

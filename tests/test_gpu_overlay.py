@@ -23,10 +23,10 @@ CPU = ROOT / "oracle" / "_ref"
 pytestmark = pytest.mark.gpu
 
 
-def run_driver(exe, cwd, env_extra, timeout=900):
+def run_driver(exe, cwd, env_extra, args=(), timeout=900):
     env = dict(os.environ)
     env.update(env_extra)
-    r = subprocess.run([str(exe)], cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run([str(exe), *args], cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -83,3 +83,37 @@ def test_rbc_in_shear_driver_atomic_spread(tmp_path, mesh):
         a, b = numbers((d_cpu / f).read_text()), numbers((d_gpu / f).read_text())
         assert a.shape == b.shape
         assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(a))), f
+
+
+def _compare_runs(tmp_path, driver, env, args=(), meshes=(), min_files=4):
+    _need(B200 / f"{driver}_short_b200", CPU / f"{driver}_short_cpu")
+    d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
+    for d in (d_cpu, d_gpu):
+        d.mkdir()
+        for name, (verts, tris) in meshes:
+            kit.write_gmsh(d / name, verts, tris)
+    out_cpu = run_driver(CPU / f"{driver}_short_cpu", d_cpu, env, args)
+    out_gpu = run_driver(B200 / f"{driver}_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1"), args)
+    assert out_gpu == out_cpu
+    files = all_files(d_cpu)
+    assert files == all_files(d_gpu) and len(files) >= min_files, files
+    for f in files:
+        if f.endswith(".msh") or "profile" in f:      # inputs; wall-clock timer report
+            continue
+        assert filecmp.cmp(d_cpu / f, d_gpu / f, shallow=False), f"{f} differs"
+    return files
+
+
+def test_capsule_in_shear_driver_bit_identical(tmp_path):
+    """progs/capsule_in_shear -N 60 (BASELINE.json configs[1]): neo-Hookean capsule (1046 vertices) in a 61^3 Couette cell."""
+    z = np.load(kit.GOLDEN / "sphere1046.npz")
+    _compare_runs(tmp_path, "capsule_in_shear", dict(BIB_NT="40", BIB_OUTPUT_INTERVAL="20"), args=("-N", "60"),
+                  meshes=[("sphere_r6_TRImesh_1046n_2088el.msh", (z["verts"], z["tris"]))])
+
+
+def test_rbcs_in_shear_driver_bit_identical(tmp_path):
+    """progs/rbcs_in_shear: 28 RBCs between parallel plates (ParallelPlatesBoundary, NoDynamics margin, velocity wall planes
+    inside the box, CouetteVelocityExtrapolator applied to the velocity field on the host every step)."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    _compare_runs(tmp_path, "rbcs_in_shear", dict(BIB_NT="20", BIB_OUTPUT_INTERVAL="10", BIB_SHRINK_ITERS="2000"),
+                  meshes=[("sphere_TRImesh_626n_1248el.msh", (shape.verts, shape.tris))])
