@@ -23,7 +23,7 @@ SYMBOLS = [
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
-    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
+    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
 ]
 
@@ -224,6 +224,13 @@ class Lattice:
         assert out.dtype == np.float64 and out.size >= count * 9 and out.flags["C_CONTIGUOUS"]
         _check(self.lib.bib_ib_vertices_download(self.h, C.c_longlong(first), C.c_longlong(count), _dptr(out)))
         return out
+
+    def results_download_async(self, out_vertices, out_scalars):
+        """Non-blocking read-back of all vertex records and particle scalars into page-locked arrays; see results_wait()."""
+        _check(self.lib.bib_ib_results_download_async(self.h, _dptr(out_vertices), _dptr(out_scalars)))
+
+    def results_wait(self):
+        _check(self.lib.bib_ib_results_wait(self.h))
 
     def particle_scalars(self, first=0, count=None, out=None):
         if count is None:

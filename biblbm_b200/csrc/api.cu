@@ -97,6 +97,10 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->band_box) cudaFree(d->band_box);
     if (d->scratch) cudaFree(d->scratch);
     if (d->pinned) cudaFreeHost(d->pinned);
+    if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
+    if (d->results_dev) cudaFree(d->results_dev);
+    if (d->ev_packed) cudaEventDestroy(d->ev_packed);
+    if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);
     if (d->vfrc) cudaFree(d->vfrc);
@@ -287,6 +291,12 @@ int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count,
     if (d->n_ranks > 1) { bib_set_error("particle_scalars_upload: single-slab domains only"); return 0; }
     return ib_scalars_upload(d, first_particle, count, scalars11);
 }
+int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11) {
+    BIB_ENTER(d);
+    if (!vertices9 || !scalars11) { bib_set_error("results_download_async: null argument"); return 0; }
+    return ib_results_download_async(d, vertices9, scalars11);
+}
+int bib_ib_results_wait(bib_domain* d) { BIB_ENTER(d); return ib_results_wait(d); }
 
 // One driver step: the velocity the IB interpolates is u = j(f^t)/rho + F^{t-1}/2 evaluated on demand from the current
 // populations and the force field still holding last step's total force, so the dense

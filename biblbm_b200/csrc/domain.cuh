@@ -122,6 +122,11 @@ struct bib_domain {
     int* p_first_vertex = nullptr;   // [cap_particles]
     void* scratch = nullptr; size_t scratch_bytes = 0;
     void* pinned = nullptr; size_t pinned_bytes = 0;      // pinned host staging for device->host result reads
+    // asynchronous result read-back (bib_ib_results_download_async): packed on the compute stream, copied on copy_stream
+    void* results_dev = nullptr; size_t results_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
+    bool copy_in_flight = false;
     MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 
@@ -155,6 +160,8 @@ int ib_vertices_download(bib_domain* d, long long first, long long count, double
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9);
 int ib_update_all(bib_domain* d, int do_move);
 int ib_scalars_download(bib_domain* d, int first, int count, double* s11);
+int ib_results_download_async(bib_domain* d, double* v9, double* s11);
+int ib_results_wait(bib_domain* d);
 int ib_scalars_upload(bib_domain* d, int first, int count, const double* s11);
 
 int comm_unique_id(void* out128);

@@ -1458,6 +1458,50 @@ int ib_vertices_download(bib_domain* d, long long first, long long count, double
     std::memcpy(v9, d->pinned, bytes);
     return 1;
 }
+// Read-back that overlaps the following steps: the fsi::Vertex records of every slot and the particle scalars are packed on
+// the compute stream into a dedicated staging buffer; a second stream copies them to the caller's page-locked buffers while
+// the compute stream carries on. The next pack waits (on the device) for the previous copy, the host only in ib_results_wait.
+int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
+    cudaPointerAttributes a0, a1;
+    const bool pinned = cudaPointerGetAttributes(&a0, v9) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&a1, s11) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) { bib_set_error("results_download_async: both host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)"); return 0; }
+    if (!d->copy_stream) {
+        BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        BIB_CHECK(cudaEventCreateWithFlags(&d->ev_packed, cudaEventDisableTiming));
+        BIB_CHECK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
+    }
+    const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double), sb = (size_t)d->n_particles * 11 * sizeof(double);
+    if (vb + sb == 0) return 1;
+    if (d->results_bytes < vb + sb) {
+        if (d->copy_in_flight) BIB_CHECK(cudaEventSynchronize(d->ev_copied));
+        if (d->results_dev) cudaFree(d->results_dev);
+        d->results_dev = nullptr; d->results_bytes = 0;
+        BIB_CHECK(cudaMalloc(&d->results_dev, vb + sb));
+        d->results_bytes = vb + sb; d->bytes += (long long)(vb + sb);
+    }
+    if (d->copy_in_flight) BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));      // staging buffer free again
+    if (vb) {
+        const int grid = (int)std::min<long long>((d->n_vertices * 9 + 255) / 256, 148 * 16);
+        k_pack_vertices<<<grid, 256, 0, d->stream>>>((double*)d->results_dev, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
+        d->launches++;
+    }
+    if (sb) BIB_CHECK(cudaMemcpyAsync((char*)d->results_dev + vb, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
+    BIB_CHECK(cudaEventRecord(d->ev_packed, d->stream));
+    BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_packed, 0));
+    if (vb) BIB_CHECK(cudaMemcpyAsync(v9, d->results_dev, vb, cudaMemcpyDeviceToHost, d->copy_stream));
+    if (sb) BIB_CHECK(cudaMemcpyAsync(s11, (char*)d->results_dev + vb, sb, cudaMemcpyDeviceToHost, d->copy_stream));
+    BIB_CHECK(cudaEventRecord(d->ev_copied, d->copy_stream));
+    d->copy_in_flight = true;
+    return 1;
+}
+int ib_results_wait(bib_domain* d) {
+    if (!d->copy_in_flight) return 1;
+    BIB_CHECK(cudaEventSynchronize(d->ev_copied));
+    d->copy_in_flight = false;
+    return 1;
+}
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {
     if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_upload: range"); return 0; }
     if (count == 0) return 1;

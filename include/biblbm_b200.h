@@ -115,6 +115,12 @@ int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long co
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
 /* per particle {area, volume, com[3], bbox x0,x1,y0,y1,z0,z1} (ParticleBase3D::area/volume/center_of_mass/bounding_box) */
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11);
+/* Non-blocking read-back of ALL vertex records and particle scalars of this slab (what write_lightweight_particle_data /
+ * write_particles_as_vtk / the volume diagnostics of the drivers consume) into page-locked host buffers: the device->host copy
+ * runs on its own stream while later steps execute. The buffers may be read after bib_ib_results_wait(); a second call
+ * before the wait is allowed with different buffers (the device serialises them). */
+int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11);
+int bib_ib_results_wait(bib_domain* d);
 /* The reference caches these per particle and refreshes them only in update() (after a move); a particle that was translated
  * or rotated on the host keeps the values computed before (ParticleBase3D::set_center_of_mass, src/fsi/ParticleBase.hh). A host
  * mirror hands its cached values over with this call so that the first force evaluation sees exactly what the reference sees;

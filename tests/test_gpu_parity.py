@@ -138,6 +138,34 @@ def test_full_step_deterministic_bit_exact(rbc, name):
     assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_async_result_readback_matches_golden(rbc):
+    """bib_ib_results_download_async: the read-back of step s overlaps step s+1 and still delivers step s, bit for bit."""
+    import torch
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    lat = run_ib_case(g, shape, params, deterministic=True)
+    n_p, nv = g["vert_init"].shape[:2]
+    hv = [torch.empty((n_p * nv, 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+    hs = [torch.empty((n_p, 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+    steps = int(g["steps"])
+    for s in range(1, steps + 1):
+        lat.step(g["body"])
+        lat.results_download_async(hv[s % 2], hs[s % 2])
+        if s > 1:        # step s is already queued behind the copy of step s-1
+            pass
+        lat.results_wait()
+        assert np.array_equal(hv[s % 2].reshape(n_p, nv, 9), g[f"vert_{s}"]), s
+        assert np.array_equal(hs[s % 2], g[f"part_{s}"])
+    # issue without waiting in between: both copies must land in order
+    lat2 = run_ib_case(g, shape, params, deterministic=True)
+    lat2.step(g["body"]); lat2.results_download_async(hv[0], hs[0])
+    lat2.step(g["body"]); lat2.results_download_async(hv[1], hs[1])
+    lat2.results_wait()
+    assert np.array_equal(hv[0].reshape(n_p, nv, 9), g["vert_1"]) and np.array_equal(hv[1].reshape(n_p, nv, 9), g["vert_2"])
+    with pytest.raises(bib.BibError, match="page-locked"):
+        lat2.results_download_async(np.empty((n_p * nv, 9)), np.empty((n_p, 11)))
+
+
 @pytest.mark.parametrize("name", ["ib_rbc1", "ib_rbc2_pfp"])
 def test_full_step_atomic_spread(rbc, name):
     """Production path (fp64 atomics reorder the force sums): parity within the per-step tolerance."""
