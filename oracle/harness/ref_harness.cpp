@@ -355,10 +355,31 @@ static int run(const Config& cfg) {
             fsi->add_force_decorator(regulator);
         }
     }
-    ParallelPlatesBoundary<double>* plates = 0;
+    Boundary<double>* boundary = 0;
     if (cfg.has("plate_y0")) {                                   // rbcs_in_shear.cpp:122-123
-        plates = new ParallelPlatesBoundary<double>(cfg.num("plate_y0", 0), cfg.num("plate_y1", ny - 1));
-        fsi->set_boundary(plates);
+        boundary = new ParallelPlatesBoundary<double>(cfg.num("plate_y0", 0), cfg.num("plate_y1", ny - 1));
+        fsi->set_boundary(boundary);
+    } else if (cfg.has("pipe_radius")) {                         // rbc_in_pipe.cpp:42,304,733 (PipeBoundary(y0, z0, radius, length))
+        boundary = new PipeBoundary<double>(cfg.num("pipe_y0", 0.5 * (ny - 1)), cfg.num("pipe_z0", 0.5 * (nz - 1)), cfg.num("pipe_radius", 0),
+                                            cfg.num("pipe_length", nx - 1));
+        fsi->set_boundary(boundary);
+    }
+    // rbc_in_pipe.cpp:150-178,736-741: wall interaction (ForceDecorator) and particle-particle interaction (PPInteractionForce)
+    if (cfg.has("wall_morse") && boundary) {
+        std::istringstream is(cfg.str("wall_morse")); double r_min, beta, strength; is >> r_min >> beta >> strength;
+        fsi->add_force_decorator(new WallInteraction<double, MorsePotential<double> >(*boundary, MorsePotential<double>(r_min, beta, strength)));
+    }
+    if (cfg.has("wall_spring") && boundary) {
+        std::istringstream is(cfg.str("wall_spring")); double r_min, strength; is >> r_min >> strength;
+        fsi->add_force_decorator(new WallInteraction<double, SpringPotential<double> >(*boundary, SpringPotential<double>(r_min, strength)));
+    }
+    if (cfg.has("pp_morse")) {
+        std::istringstream is(cfg.str("pp_morse")); double r_min, beta, strength; is >> r_min >> beta >> strength;
+        fsi->add_pp_force(new PPPotentialForce<double, MorsePotential<double> >(MorsePotential<double>(r_min, beta, strength)));
+    }
+    if (cfg.has("pp_spring")) {
+        std::istringstream is(cfg.str("pp_spring")); double r_min, strength; is >> r_min >> strength;
+        fsi->add_pp_force(new PPPotentialForce<double, SpringPotential<double> >(SpringPotential<double>(r_min, strength)));
     }
     fsi->init();
 
@@ -416,6 +437,7 @@ static int cmd_run(int argc, char** argv) {
     if (cfg.str("walls", "none") == "shear") per = "pfp";
     if (per == "ppp") return run<Periodicity3D<double, true, true, true> >(cfg);
     if (per == "pfp") return run<Periodicity3D<double, true, false, true> >(cfg);
+    if (per == "pff") return run<Periodicity3D<double, true, false, false> >(cfg);
     std::fprintf(stderr, "unsupported periodicity %s\n", per.c_str());
     return 1;
 }

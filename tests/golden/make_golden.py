@@ -181,6 +181,58 @@ def make_plates():
     print("plates golden ok")
 
 
+def pipe_case():
+    """rbc_in_pipe-type set-up in miniature (x periodic; PipeBoundary; Morse wall interaction and Morse particle-particle
+    interaction with the parameters of progs/rbc_in_pipe/input.xml): RBC A almost touching the pipe wall with the fluid initially
+    moving towards the wall (vertices get reflected), RBC B 0.5 below A (vertex-vertex repulsion), RBC C across the periodic x face."""
+    shape, params, rbc_pos, _ = kit.load_rbc_fixture()
+    nx, ny, nz = 30, 28, 28
+    y0 = z0 = 13.5; radius = 12.2
+    base = rbc_pos - rbc_pos.mean(0)
+    _, _, vt = np.linalg.svd(base, full_matrices=False)       # principal axes, minor axis last
+    R = vt if np.linalg.det(vt) > 0 else vt * np.array([[1], [1], [-1]])
+    flat = base @ R.T                                         # minor axis along z, a proper rotation
+    def max_r(c):
+        p = flat + c
+        return np.sqrt((p[:, 1] - y0) ** 2 + (p[:, 2] - z0) ** 2).max()
+    lo, hi = 0.0, radius
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        if max_r(np.array([10.2, y0 + 0.3, z0 + mid])) < radius - 0.004: lo = mid
+        else: hi = mid
+    ca = np.array([10.2, y0 + 0.3, z0 + lo])
+    A = flat + ca
+    def gap(dz):
+        Bp = flat + ca - np.array([0.4, 0.2, dz])
+        d = np.sqrt(((A[:, None, :] - Bp[None, :, :]) ** 2).sum(-1))
+        return d.min()
+    lo, hi = 0.5, 8.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if gap(mid) < 0.5: lo = mid
+        else: hi = mid
+    Bp = flat + ca - np.array([0.4, 0.2, hi])
+    Cc = kit.place_particles(rbc_pos, [(29.2, 12.8, 9.0)], seed=5)[0]
+    pos = np.stack([A, Bp, Cc])
+    cfg = dict(nx=nx, ny=ny, nz=nz, steps=20, dump_every=5, periodicity="pff", omega=1.0, omega_inner=0.5, init="uniform", rho=1.0,
+               ux=0.01, uy=0.0, uz=0.04, body_x=1e-5, body_y=0, body_z=0, pipe_y0=y0, pipe_z0=z0, pipe_radius=radius, pipe_length=nx - 1,
+               wall_morse="2 2 1e-4", pp_morse="1 1 1e-3")
+    return shape, params, pos, cfg
+
+
+def make_pipe():
+    shape, params, pos, cfg = pipe_case()
+    out = kit.run_reference(cfg, verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    steps = cfg["steps"]
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                omega=1.0, omega_inner=0.5, steps=steps, body=np.array([1e-5, 0.0, 0.0]), per=np.array([1, 0, 0], dtype=np.int32),
+                pipe=np.array([cfg["pipe_y0"], cfg["pipe_z0"], cfg["pipe_radius"]]), wall_morse=np.array([2.0, 2.0, 1e-4]), pp_morse=np.array([1.0, 1.0, 1e-3]))
+    for s in range(5, steps + 1, 5):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_pipe_pp.npz", **keep)
+    print("pipe golden ok")
+
+
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
@@ -191,4 +243,5 @@ if __name__ == "__main__":
     make_shear()
     make_capsule()
     make_plates()
+    make_pipe()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -176,6 +176,29 @@ class Oracle:
     def set_parallel_plates(self, on, y0=0.0, y1=0.0):
         self.lib.orc_set_parallel_plates(C.c_int(int(on)), C.c_double(y0), C.c_double(y1))
 
+    def set_pipe(self, on, y0=0.0, z0=0.0, radius=0.0):
+        """fsi.set_boundary(&PipeBoundary(y0, z0, radius, length))"""
+        self.lib.orc_set_pipe(C.c_int(int(on)), C.c_double(y0), C.c_double(z0), C.c_double(radius))
+
+    def set_wall_interaction(self, kind, r_min=0.0, beta=0.0, strength=0.0):
+        """WallInteraction force decorator: kind 0 none, 1 MorsePotential(r_min, beta, strength), 2 SpringPotential(r_min, strength)"""
+        self.lib.orc_set_wall_interaction(C.c_int(kind), C.c_double(r_min), C.c_double(beta), C.c_double(strength))
+
+    def set_pp_interaction(self, kind, r_min=0.0, beta=0.0, strength=0.0):
+        """fsi.add_pp_force(PPPotentialForce<...>): same kinds as set_wall_interaction"""
+        self.lib.orc_set_pp_interaction(C.c_int(kind), C.c_double(r_min), C.c_double(beta), C.c_double(strength))
+
+    def pp_forces(self, dims, per, pos, obj):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        obj = np.ascontiguousarray(obj, dtype=np.int32)
+        f = np.zeros_like(pos)
+        pr = np.asarray(per, dtype=np.int32)
+        self.lib.orc_pp_forces(C.c_int(dims[0]), C.c_int(dims[1]), C.c_int(dims[2]), _i(pr), C.c_long(pos.shape[0]), _d(pos), _i(obj), _d(f))
+        return f
+
+    def reset_modes(self):
+        self.set_parallel_plates(0); self.set_wall_interaction(0); self.set_pp_interaction(0); self.set_particle_model(0)
+
     def capsule_forces(self, shape: Shape, cparams, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         f = np.zeros_like(pos)

@@ -204,6 +204,30 @@ def test_parallel_plates_boundary_bit_exact(orc, rbc):
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_pipe_wall_and_particle_interactions_bit_exact(orc, rbc):
+    """rbc_in_pipe-type set-up (tests/golden/make_golden.py:pipe_case): PipeBoundary near-wall blending and reflection, Morse
+    WallInteraction decorator and the cell-list particle-particle Morse force, 20 steps; oracle == reference bit for bit."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_pipe_pp.npz")
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    orc.set_pipe(1, *[float(v) for v in g["pipe"]])
+    orc.set_wall_interaction(1, *[float(v) for v in g["wall_morse"]])
+    orc.set_pp_interaction(1, *[float(v) for v in g["pp_morse"]])
+    try:
+        classes = {orc.classify(p, cells.shape[:3], g["per"]) for p in vert[:, :, :3].reshape(-1, 3)}
+        assert {1, 2, 3} <= classes
+        # the fixture must exercise both interactions at the start
+        f_pp = orc.pp_forces(cells.shape[:3], g["per"], vert[..., :3], np.repeat(np.arange(3), shape.nv))
+        assert np.abs(f_pp).max() > 1e-6 and abs(f_pp.sum()) < 1e-12
+        for s in range(1, int(g["steps"]) + 1):
+            orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], shape, params, vert, state)
+            if s % 5 == 0:
+                assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"]), f"step {s}"
+    finally:
+        orc.reset_modes()
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+
+
 def test_golden_membrane_forces_are_not_trivial():
     """Guards the fixtures themselves: the RBC goldens must carry real membrane stiffness and non-zero vertex forces."""
     z = np.load(kit.GOLDEN / "rbc626.npz")
