@@ -21,7 +21,7 @@ SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
-    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
@@ -30,6 +30,7 @@ SYMBOLS = [
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR = 1, 2, 3
 CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
 PARTICLE_RBC, PARTICLE_CAPSULE = 0, 1
+POTENTIAL_NONE, POTENTIAL_MORSE, POTENTIAL_SPRING = 0, 1, 2
 
 _lib = None
 
@@ -188,6 +189,16 @@ class Lattice:
     def set_boundary(self, y0, y1, enabled=True):
         """fsi.set_boundary(&ParallelPlatesBoundary(y0, y1))"""
         _check(self.lib.bib_ib_set_parallel_plates(self.h, int(enabled), C.c_double(y0), C.c_double(y1)))
+
+    def set_pipe(self, y0, z0, radius, enabled=True):
+        """fsi.set_boundary(&PipeBoundary(y0, z0, radius, length))"""
+        _check(self.lib.bib_ib_set_pipe(self.h, int(enabled), C.c_double(y0), C.c_double(z0), C.c_double(radius)))
+
+    def set_wall_interaction(self, kind, r_min=0.0, beta=0.0, strength=0.0):
+        _check(self.lib.bib_ib_set_wall_interaction(self.h, int(kind), C.c_double(r_min), C.c_double(beta), C.c_double(strength)))
+
+    def set_pp_interaction(self, kind, r_min=0.0, beta=0.0, strength=0.0):
+        _check(self.lib.bib_ib_set_pp_interaction(self.h, int(kind), C.c_double(r_min), C.c_double(beta), C.c_double(strength)))
 
     def count(self):
         n_p, n_v = C.c_int(0), C.c_longlong(0)

@@ -99,6 +99,9 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     if (d->results_dev) cudaFree(d->results_dev);
+    if (d->pp_head) cudaFree(d->pp_head);
+    if (d->pp_next) cudaFree(d->pp_next);
+    if (d->pp_vobj) cudaFree(d->pp_vobj);
     if (d->ev_packed) cudaEventDestroy(d->ev_packed);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->vpos) cudaFree(d->vpos);
@@ -247,6 +250,25 @@ int bib_ib_set_parallel_plates(bib_domain* d, int enabled, double y0, double y1)
     if (enabled && !(y1 > y0)) { bib_set_error("set_parallel_plates: need y1 > y0"); return 0; }
     d->plates = enabled ? 1 : 0; d->plate_y0 = y0; d->plate_y1 = y1;
     return 1;
+}
+int bib_ib_set_pipe(bib_domain* d, int enabled, double y0, double z0, double radius) {
+    BIB_ENTER(d);
+    if (enabled && !(radius > 0)) { bib_set_error("set_pipe: need radius > 0"); return 0; }
+    d->plates = enabled ? 2 : 0; d->plate_y0 = y0; d->plate_y1 = z0; d->pipe_radius = radius;
+    return 1;
+}
+static int set_potential(PotentialDev& q, int type, double r_min, double beta, double strength, const char* who) {
+    if (type != BIB_POTENTIAL_NONE && type != BIB_POTENTIAL_MORSE && type != BIB_POTENTIAL_SPRING) { bib_set_error(std::string(who) + ": unknown potential type"); return 0; }
+    q.type = type; q.r_min = r_min; q.beta = beta; q.strength = strength;
+    return 1;
+}
+int bib_ib_set_wall_interaction(bib_domain* d, int type, double r_min, double beta, double strength) {
+    BIB_ENTER(d);
+    return set_potential(d->wall_pot, type, r_min, beta, strength, "set_wall_interaction");
+}
+int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta, double strength) {
+    BIB_ENTER(d);
+    return set_potential(d->pp_pot, type, r_min, beta, strength, "set_pp_interaction");
 }
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
     BIB_ENTER(d);

@@ -63,6 +63,8 @@ struct MultiSlabIB {
     bool ghosts_dirty = true;
 };
 
+struct PotentialDev { int type = 0; double r_min = 0, beta = 0, strength = 0; };   // fsi/Potentials.h: 1 Morse, 2 spring
+
 struct WallPlane {                 // one velocity boundary plane (VelocityDirichlet + PlaneFd)
     int dir = 1, orient = -1, coord = 0;
     int na = 0, nb = 0;            // extent along the two in-plane axes (x,y,z order)
@@ -100,7 +102,10 @@ struct bib_domain {
     int envelope_swap = 1;
     int deterministic_spread = 0;
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
-    int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary(ParallelPlatesBoundary)
+    int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),
+    double pipe_radius = 0;                                 //   2 PipeBoundary (axis y = plate_y0, z = plate_y1, radius)
+    PotentialDev wall_pot, pp_pot;                          // WallInteraction decorator / PPPotentialForce
+    int* pp_head = nullptr; int* pp_next = nullptr; int* pp_vobj = nullptr; long long pp_cap = 0; int pp_groups = 0;
     // multi-GPU ring
     int rank = 0, n_ranks = 1;
     void* nccl_comm = nullptr;

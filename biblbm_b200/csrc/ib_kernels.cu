@@ -37,7 +37,8 @@ struct Geo {
     const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
     int nv_slot;             // vertices per slot when role != NULL
     const uint8_t* kind;     // cell kinds (NULL = all bulk)
-    int plates; double py0, py1;   // fsi::ParallelPlatesBoundary (walls at y = py0, py1), src/fsi/Boundary.h:300-365
+    int plates;              // fsi::Boundary kind: 0 none, 1 ParallelPlatesBoundary (walls at y = py0, py1; src/fsi/Boundary.h:300-365),
+    double py0, py1, prad;   //   2 PipeBoundary along x with axis (y, z) = (py0, py1) and radius prad (src/fsi/Boundary.h:131-253)
 };
 // slab-local plane index of global x, or -1 when another slab owns it
 __device__ __forceinline__ bool d_in_slab(const Geo& g, int gx) { const int lx = gx - g.x_offset; return lx >= 0 && lx < g.nxl; }
@@ -62,11 +63,48 @@ __device__ __forceinline__ bool d_rect_contains(const Geo& g, double lo_enl, dou
     }
     return true;
 }
+// Boundary::distance_to_boundary_less_than / distance_to_boundary / get_normal / trace_ray of the two boundary classes
+__device__ __forceinline__ double d_sqr(double x) { return x * x; }
+__device__ __forceinline__ bool d_boundary_closer_than(const Geo& g, const double* p, double dist) {
+    if (g.plates == 2) return (d_sqr(p[1] - g.py0) + d_sqr(p[2] - g.py1)) > d_sqr(g.prad - dist);
+    return (p[1] + dist) > g.py1 || (p[1] - dist) < g.py0;
+}
+__device__ __forceinline__ double d_plates_distance(const Geo& g, const double* r) {
+    if (g.plates == 2) return g.prad - sqrt(d_sqr(r[1] - g.py0) + d_sqr(r[2] - g.py1));
+    return (r[1] < 0.5 * (g.py0 + g.py1)) ? r[1] - g.py0 : g.py1 - r[1];
+}
+__device__ __forceinline__ void d_boundary_normal(const Geo& g, const double* r, double* n) {
+    if (g.plates == 2) {
+        const double dy = r[1] - g.py0, dz = r[2] - g.py1;
+        const double nrm = sqrt((0.0 * 0.0 + dy * dy) + dz * dz);
+        n[0] = 0.0 / nrm; n[1] = dy / nrm; n[2] = dz / nrm;
+    } else { n[0] = 0; n[1] = (r[1] < 0.5 * (g.py0 + g.py1)) ? -1.0 : 1.0; n[2] = 0; }
+}
+__device__ __forceinline__ bool d_boundary_trace_ray(const Geo& g, const double* x0, const double* x1, double& t) {
+    if (g.plates == 2) {
+        const double y1 = x0[1] - g.py0, y2 = x1[1] - g.py0, z1 = x0[2] - g.py1, z2 = x1[2] - g.py1;
+        const double a = (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+        const double b = y1 * (y2 - y1) + z1 * (z2 - z1);
+        const double c = y1 * y1 + z1 * z1 - g.prad * g.prad;
+        const double disc = b * b - c * a;
+        if (disc < 0. || fabs(a) < 10 * 2.220446049250313e-16) return false;
+        const double bOverA = -b / a;
+        const double sqrtDisc = sqrt(disc) / a;
+        t = bOverA - sqrtDisc;
+        if (t >= 0. && t <= 1.) return true;
+        t = bOverA + sqrtDisc;
+        return t >= 0. && t <= 1.;
+    }
+    t = (g.py1 - x0[1]) / (x1[1] - x0[1]);
+    if (t > 0 && t < 1) return true;
+    t = (g.py0 - x0[1]) / (x1[1] - x0[1]);
+    return t > 0 && t < 1;
+}
 // 0 = outside domain_with_fsi_envelope, 1 = bulk list, 2 = envelope list (src/fsi/ImmersedBoundaryDynamics.hh:46-65,346-358)
 __device__ __forceinline__ int d_classify(const Geo& g, const double* p) {
     const double eps = 2.220446049250313e-16;
     if (!d_rect_contains(g, 1.5, 1.5, p)) return 0;
-    if (g.plates && ((p[1] + (1.5 + 1.)) > g.py1 || (p[1] - (1.5 + 1.)) < g.py0)) return 3;   // near-boundary list (ImmersedBoundaryDynamics.hh:349-350)
+    if (g.plates && d_boundary_closer_than(g, p, 1.5 + 1.)) return 3;   // near-boundary list (ImmersedBoundaryDynamics.hh:349-350)
     const double d_bulk = 0.5 - 1.5 - eps;
     if (d_rect_contains(g, d_bulk, d_bulk, p)) return 1;
     return 2;
@@ -98,7 +136,6 @@ __device__ __forceinline__ void d_cell_velocity(const double* __restrict__ f, co
 
 // ------------------------------------------------------------------------------------------------ I2: interpolation
 __device__ __forceinline__ double d_tophat(double x) { return 1. - fabs(x); }        // TopHatDirac, src/fsi/Dirac.h:55-58
-__device__ __forceinline__ double d_plates_distance(const Geo& g, const double* r) { return (r[1] < 0.5 * (g.py0 + g.py1)) ? r[1] - g.py0 : g.py1 - r[1]; }
 // GeneralInterpolator::interpolate_node for the Roma (3-point) or top-hat (2-point) kernel, from the dense velocity field
 __device__ __forceinline__ void d_general_interp(const Geo& g, const double* __restrict__ vel, const double* p, bool th, double* o) {
     const int sup = th ? 2 : 3;
@@ -384,14 +421,17 @@ struct RbcParams {
     double shape_area, k_ag, k_al, k_v, vol_desired, k_b;
     double reg_p, reg_t[3];
     const int* role;
+    const double* f_init;     // non-NULL: vertex forces start from the values a decorator pass left in vfrc (wall interaction)
 };
 
 // Force on vertex v of one particle: gathers the contributions of its incident links, triangles and pairs in the order in
 // which RBCParticle::compute_forces adds them to that vertex (decorator, links, triangles [area, volume], pairs).
 // P/capP/baseP address the particle's vertex positions (global SoA arrays or a shared-memory copy).
-__device__ __forceinline__ V3 d_rbc_vertex_force(const RbcParams& q, const double* P, long long capP, long long baseP, int v, const double* st) {
+__device__ __forceinline__ V3 d_rbc_vertex_force(const RbcParams& q, const double* P, long long capP, long long baseP, int v, const double* st,
+                                                  long long gv) {
     const double area = st[0], volume = st[1];
     double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (q.f_init) { fx = q.f_init[gv]; fy = q.f_init[q.cap + gv]; fz = q.f_init[2 * q.cap + gv]; }
     if (q.reg_p != 0.0) {
         fx += (q.reg_p * (q.reg_t[0] - st[2])) / (double)q.nv;
         fy += (q.reg_p * (q.reg_t[1] - st[3])) / (double)q.nv;
@@ -446,7 +486,7 @@ __global__ void __launch_bounds__(256) k_rbc_forces_cta(RbcParams q, const doubl
     __syncthreads();
     const double* st = pstate + (long long)(q.first_particle + pl) * 11;
     for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
-        const V3 f = d_rbc_vertex_force(q, s_pos, q.nv, 0, v, st);
+        const V3 f = d_rbc_vertex_force(q, s_pos, q.nv, 0, v, st, base + v);
         vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
     }
 }
@@ -477,6 +517,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_rbc_forces_elem(RbcParams q, con
         fx[k] = fy[k] = fz[k] = 0.0;
         const int v = threadIdx.x + k * RF_THREADS;
         if (v < q.nv) {
+            if (q.f_init) { fx[k] = q.f_init[base + v]; fy[k] = q.f_init[q.cap + base + v]; fz[k] = q.f_init[2 * q.cap + base + v]; }
             if (q.reg_p != 0.0) {
                 fx[k] += (q.reg_p * (q.reg_t[0] - st[2])) / (double)q.nv;
                 fy[k] += (q.reg_p * (q.reg_t[1] - st[3])) / (double)q.nv;
@@ -605,7 +646,7 @@ __global__ void __launch_bounds__(128) k_rbc_forces(RbcParams q, const double* _
     const int pl = (int)(t / q.nv), v = (int)(t % q.nv);
     if (q.role && q.role[q.first_particle + pl] != 1) return;
     const long long base = q.first_vertex + (long long)pl * q.nv;
-    const V3 f = d_rbc_vertex_force(q, vpos, q.cap, base, v, pstate + (long long)(q.first_particle + pl) * 11);
+    const V3 f = d_rbc_vertex_force(q, vpos, q.cap, base, v, pstate + (long long)(q.first_particle + pl) * 11, base + v);
     vfrc[base + v] = f.x; vfrc[q.cap + base + v] = f.y; vfrc[2 * q.cap + base + v] = f.z;
 }
 
@@ -656,7 +697,7 @@ struct CapParams {
     int nv; long long first_vertex, cap; int first_particle, count;
     const int* tris; const double* tri_area; const double* rest;   // rest: [nv][3]
     const int* v_tri_off; const int* v_tri;
-    double G; const int* role; int use_smem;
+    double G; const int* role; int use_smem; int f_init;
 };
 // One CTA per particle, per-vertex gather over incident triangles in ascending order (= the reference's accumulation order).
 __global__ void __launch_bounds__(256) k_capsule_forces(CapParams q, const double* __restrict__ vpos, double* __restrict__ vfrc) {
@@ -672,6 +713,7 @@ __global__ void __launch_bounds__(256) k_capsule_forces(CapParams q, const doubl
     }
     for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
         double fx = 0.0, fy = 0.0, fz = 0.0;
+        if (q.f_init) { fx = vfrc[base + v]; fy = vfrc[q.cap + base + v]; fz = vfrc[2 * q.cap + base + v]; }
         for (int e = q.v_tri_off[v]; e < q.v_tri_off[v + 1]; ++e) {
             const int code = q.v_tri[e], tr = code / 3, k = code % 3;
             const int i0 = q.tris[3 * tr], i1 = q.tris[3 * tr + 1], i2 = q.tris[3 * tr + 2];
@@ -682,6 +724,137 @@ __global__ void __launch_bounds__(256) k_capsule_forces(CapParams q, const doubl
         }
         vfrc[base + v] = fx; vfrc[q.cap + base + v] = fy; vfrc[2 * q.cap + base + v] = fz;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ M4: wall / particle-particle forces
+// fsi/Potentials.h:29-71: type 1 = MorsePotential(r_min, beta, strength), 2 = SpringPotential(min_dist, strength); cutoff = r_min
+__device__ __forceinline__ double d_potential(const PotentialDev& q, double dist) {
+    if (q.type == 1) {
+        if (dist < 0) dist = 0;
+        const double x = exp(q.beta * (q.r_min - dist));
+        return ((2 * q.beta) * q.strength) * x * (x - 1);
+    }
+    return (q.r_min - dist) * q.strength;
+}
+// WallInteraction::apply_force (src/fsi/ForceDecorator.hh:25-33), run BEFORE the membrane force kernels, which then start
+// from these values (decorators act first: src/fsi/ImmersedBoundaryDynamics_forces.hh:293-297). One thread per vertex.
+__global__ void __launch_bounds__(256) k_wall_interaction(Geo g, PotentialDev pot, long long nvert, long long cap, const double* __restrict__ vpos,
+                                                          double* __restrict__ vfrc) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert) return;
+    const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    double f[3] = {0.0, 0.0, 0.0};
+    const double dist = d_plates_distance(g, p);
+    if (dist <= pot.r_min) {
+        double n[3]; d_boundary_normal(g, p, n);
+        const double I = d_potential(pot, dist);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[d] -= I * n[d];
+    }
+    vfrc[v] = f[0]; vfrc[cap + v] = f[1]; vfrc[2 * cap + v] = f[2];
+}
+
+// Particle-particle interaction (compute_particle_particle_interaction_impl, src/fsi/ImmersedBoundaryDynamics_forces.hh:336-381;
+// collision::CollisionHandler, src/fsi/CollisionForces.h:62-217; Grid, src/fsi/Grid.hh:36-103). The reference bins the
+// vertices into a uniform grid and walks it once, applying +df / -df to both members of each pair. Here every vertex
+// GATHERS its own force from exactly the same set of pairs (no atomics on forces): the cells the reference would have
+// paired with the vertex's cell, including what the reference leaves out -- only the 7 neighbours with non-negative
+// offsets are visited from a bulk cell (so a pair is seen iff its cell offset is one of those 7 or their negatives), and
+// periodic images are only paired between directly opposite boundary cells.
+struct PPGrid { int nc[3]; double g0[3], cs[3], lo[3], hi[3]; int per[3]; double L[3]; };
+__device__ __forceinline__ bool d_pp_cell(const PPGrid& G, const double* p, int* c) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (!(p[d] > G.lo[d] && p[d] < G.hi[d])) return false;          // coll_domain.contains(pos)
+        c[d] = (int)floor((p[d] - G.g0[d]) / G.cs[d]);
+    }
+    return true;
+}
+__global__ void __launch_bounds__(256) k_pp_build(PPGrid G, long long nvert, long long cap, const double* __restrict__ vpos, int* head, int* next) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert) return;
+    const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    int c[3];
+    if (!d_pp_cell(G, p, c)) { next[v] = -2; return; }
+    const long long cell = (long long)c[2] + (long long)G.nc[2] * ((long long)c[1] + (long long)G.nc[1] * c[0]);
+    next[v] = atomicExch(&head[cell], (int)v);
+}
+__global__ void __launch_bounds__(256) k_pp_clear(PPGrid G, long long nvert, long long cap, const double* __restrict__ vpos, int* head) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert) return;
+    const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    int c[3];
+    if (!d_pp_cell(G, p, c)) return;
+    head[(long long)c[2] + (long long)G.nc[2] * ((long long)c[1] + (long long)G.nc[1] * c[0])] = -1;
+}
+__device__ __forceinline__ void d_pp_cell_sum(const PPGrid& G, const PotentialDev& pot, double cut_sqr, const int* __restrict__ head, const int* __restrict__ next,
+                                              const double* __restrict__ vpos, long long cap, const int* __restrict__ vobj, int ci, int cj, int ck,
+                                              long long self, int obj, const double* p, double* f) {
+    for (int b = head[(long long)ck + (long long)G.nc[2] * ((long long)cj + (long long)G.nc[1] * ci)]; b >= 0; b = next[b]) {
+        if (b == self || vobj[b] == obj) continue;
+        double dr[3] = {vpos[b] - p[0], vpos[cap + b] - p[1], vpos[2 * cap + b] - p[2]};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) if (G.per[d]) dr[d] = d_min_mod(dr[d], G.L[d], 1. / G.L[d]);
+        const double dist_sqr = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
+        if (dist_sqr <= cut_sqr) {
+            const double dist = sqrt(dist_sqr);
+            const double k = -d_potential(pot, dist) / dist;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) f[d] += k * dr[d];
+        }
+    }
+}
+__global__ void __launch_bounds__(128) k_pp_forces(PPGrid G, PotentialDev pot, long long nvert, long long cap, const double* __restrict__ vpos,
+                                                   const int* __restrict__ vobj, const int* __restrict__ head, const int* __restrict__ next,
+                                                   double* __restrict__ vfrc) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert || next[v] == -2) return;
+    const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    int c[3];
+    d_pp_cell(G, p, c);
+    const int obj = vobj[v];
+    const double cut_sqr = pot.r_min * pot.r_min;
+    const int lo[3] = {1, 1, 1}, hi[3] = {G.nc[0] - 2, G.nc[1] - 2, G.nc[2] - 2};
+    const bool bulk = c[0] >= lo[0] && c[0] <= hi[0] && c[1] >= lo[1] && c[1] <= hi[1] && c[2] >= lo[2] && c[2] <= hi[2];
+    double f[3] = {0.0, 0.0, 0.0};
+    const int off[7][3] = {{0, 1, 0}, {0, 1, 1}, {0, 0, 1}, {1, 0, 0}, {1, 1, 0}, {1, 1, 1}, {1, 0, 1}};
+    if (bulk) {
+        d_pp_cell_sum(G, pot, cut_sqr, head, next, vpos, cap, vobj, c[0], c[1], c[2], v, obj, p, f);            // same cell
+        for (int o = 0; o < 7; ++o)                                                                               // this vertex is the pair's first member
+            d_pp_cell_sum(G, pot, cut_sqr, head, next, vpos, cap, vobj, c[0] + off[o][0], c[1] + off[o][1], c[2] + off[o][2], v, obj, p, f);
+    }
+    for (int o = 0; o < 7; ++o) {                                                                                 // ... or its second member
+        const int b[3] = {c[0] - off[o][0], c[1] - off[o][1], c[2] - off[o][2]};
+        if (b[0] >= lo[0] && b[0] <= hi[0] && b[1] >= lo[1] && b[1] <= hi[1] && b[2] >= lo[2] && b[2] <= hi[2])
+            d_pp_cell_sum(G, pot, cut_sqr, head, next, vpos, cap, vobj, b[0], b[1], b[2], v, obj, p, f);
+    }
+    if (bulk) {
+        // periodic faces / edges / corner: the cell at the low end of every direction in D is paired with the cell at the high end of all of them
+        for (int mask = 1; mask < 8; ++mask) {
+            bool ok = true, all_lo = true, all_hi = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) if (mask & (1 << d)) {
+                if (!G.per[d]) ok = false;
+                if (c[d] != lo[d]) all_lo = false;
+                if (c[d] != hi[d]) all_hi = false;
+            }
+            if (!ok) continue;
+            int q[3] = {c[0], c[1], c[2]};
+            if (all_lo) {
+                for (int d = 0; d < 3; ++d) if (mask & (1 << d)) q[d] = hi[d];
+                d_pp_cell_sum(G, pot, cut_sqr, head, next, vpos, cap, vobj, q[0], q[1], q[2], v, obj, p, f);
+            }
+            if (all_hi) {
+                for (int d = 0; d < 3; ++d) if (mask & (1 << d)) q[d] = lo[d];
+                d_pp_cell_sum(G, pot, cut_sqr, head, next, vpos, cap, vobj, q[0], q[1], q[2], v, obj, p, f);
+            }
+        }
+    }
+    vfrc[v] += f[0]; vfrc[cap + v] += f[1]; vfrc[2 * cap + v] += f[2];
+}
+__global__ void k_fill_vobj(int* vobj, long long first_vertex, int nv, int first_particle, long long n) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) vobj[first_vertex + t] = first_particle + (int)(t / nv);
 }
 
 // ------------------------------------------------------------------------------------------------ I4: move + update
@@ -714,14 +887,12 @@ __global__ void __launch_bounds__(256) k_move_update(Geo g, int nv, int nt, cons
             const double old[3] = {x[0], x[1], x[2]};
 #pragma unroll
             for (int d = 0; d < 3; ++d) x[d] += u[d];
-            if (g.plates) {   // specular reflection (DeformableParticle3D.hh:33-50; ParallelPlatesBoundary::trace_ray / get_normal)
-                double t = (g.py1 - old[1]) / (x[1] - old[1]);
-                bool hit = (t > 0 && t < 1);
-                if (!hit) { t = (g.py0 - old[1]) / (x[1] - old[1]); hit = (t > 0 && t < 1); }
-                if (hit) {
+            if (g.plates) {   // specular reflection (DeformableParticle3D.hh:33-50; Boundary::trace_ray / get_normal)
+                double t;
+                if (d_boundary_trace_ray(g, old, x, t)) {
 #pragma unroll
                     for (int d = 0; d < 3; ++d) x[d] = old[d] + t * u[d];
-                    const double n[3] = {0, (x[1] < 0.5 * (g.py0 + g.py1)) ? -1.0 : 1.0, 0};
+                    double n[3]; d_boundary_normal(g, x, n);
                     const double un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) { const double vpc = u[d] - 2. * un * n[d]; x[d] += vpc * (1. - t); }
@@ -1024,7 +1195,7 @@ Geo make_geo(const bib_domain* d) {
     g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
     g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
-    g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1; g.kind = d->kind;
+    g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1; g.prad = d->pipe_radius; g.kind = d->kind;
     return g;
 }
 
@@ -1343,16 +1514,72 @@ int ib_band_reset(bib_domain* d, double fx, double fy, double fz) {
     return 1;
 }
 
+static PPGrid make_pp_grid(const bib_domain* d) {
+    PPGrid G;
+    const double eps = 2.220446049250313e-16;
+    const int n[3] = {d->gnx, d->ny, d->nz};
+    for (int k = 0; k < 3; ++k) {
+        const double dom0 = 0 - 0.5, dom1 = (double)(n[k] - 1) + 0.5 - eps;
+        G.nc[k] = (int)std::floor((dom1 - dom0) / 1.);
+        G.cs[k] = (dom1 - dom0) / (double)G.nc[k];
+        G.nc[k] += 2;
+        G.g0[k] = dom0 - G.cs[k];
+        G.lo[k] = dom0 - d->pp_pot.r_min; G.hi[k] = dom1 + d->pp_pot.r_min;
+        G.per[k] = d->per[k]; G.L[k] = (double)n[k];
+    }
+    return G;
+}
+static int ib_pp_forces(bib_domain* d) {
+    if (d->n_ranks > 1) { bib_set_error("particle-particle interaction forces: single-slab domains only (round 1)"); return 0; }
+    if (d->pp_pot.r_min > 1.0) { bib_set_error("The interaction distance cannot be greater than the lattice spacing (1)"); return 0; }   // _forces.hh:347-350
+    const PPGrid G = make_pp_grid(d);
+    const size_t ncell = (size_t)G.nc[0] * G.nc[1] * G.nc[2];
+    if (!d->pp_head) {
+        BIB_CHECK(cudaMalloc(&d->pp_head, ncell * sizeof(int)));
+        BIB_CHECK(cudaMemsetAsync(d->pp_head, 0xff, ncell * sizeof(int), d->stream));
+        d->bytes += (long long)(ncell * sizeof(int));
+    }
+    if (d->pp_cap < d->cap_vertices) {
+        if (d->pp_next) cudaFree(d->pp_next);
+        if (d->pp_vobj) cudaFree(d->pp_vobj);
+        BIB_CHECK(cudaMalloc(&d->pp_next, (size_t)d->cap_vertices * sizeof(int)));
+        BIB_CHECK(cudaMalloc(&d->pp_vobj, (size_t)d->cap_vertices * sizeof(int)));
+        d->pp_cap = d->cap_vertices; d->pp_groups = 0;
+    }
+    if (d->pp_groups != (int)d->groups.size()) {
+        for (const ParticleGroup& gr : d->groups) {
+            const long long n = (long long)gr.count * d->shapes[gr.shape].nv;
+            k_fill_vobj<<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>(d->pp_vobj, gr.first_vertex, d->shapes[gr.shape].nv, gr.first_particle, n);
+            d->launches++;
+        }
+        d->pp_groups = (int)d->groups.size();
+    }
+    const unsigned grid = (unsigned)((d->n_vertices + 255) / 256);
+    k_pp_build<<<grid, 256, 0, d->stream>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head, d->pp_next);
+    k_pp_forces<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(G, d->pp_pot, d->n_vertices, d->cap_vertices, d->vpos, d->pp_vobj,
+                                                                            d->pp_head, d->pp_next, d->vfrc);
+    k_pp_clear<<<grid, 256, 0, d->stream>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head);
+    d->launches += 3;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int ib_forces_and_spread(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
     d->interp_since_spread = false;
+    const bool wall = d->wall_pot.type != 0 && d->plates != 0;
+    if (wall) {
+        if (d->n_ranks > 1) { bib_set_error("wall interaction forces: single-slab domains only (round 1)"); return 0; }
+        k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, d->stream>>>(make_geo(d), d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+        d->launches++;
+    }
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
         if (gr.type == 1) {      // BIB_PARTICLE_CAPSULE
             CapParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle; c.count = gr.count;
             c.tris = s.tris; c.tri_area = s.tri_area; c.rest = s.verts; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri;
-            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr;
+            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
             const size_t smem = (size_t)s.nv * 3 * sizeof(double);
             c.use_smem = smem <= 200 * 1024;
             if (c.use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_capsule_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1368,6 +1595,7 @@ int ib_forces_and_spread(bib_domain* d) {
         q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
         q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
         q.role = d->ms ? d->ms->role : nullptr;
+        q.f_init = wall ? d->vfrc : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
         if (s.nv <= RF_THREADS * RF_VPT) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
@@ -1382,6 +1610,7 @@ int ib_forces_and_spread(bib_domain* d) {
         }
         d->launches++;
     }
+    if (d->pp_pot.type != 0 && !ib_pp_forces(d)) return 0;   // after every particle's own forces (_forces.hh:300-302)
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);

@@ -100,6 +100,17 @@ int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double t
  * (src/fsi/ImmersedBoundaryDynamics_interpolation.hh:181-230, _forces.hh:192-237) and are reflected specularly at the plates when
  * advected (src/fsi/DeformableParticle3D.hh:33-50). */
 int bib_ib_set_parallel_plates(bib_domain* d, int enabled, double y0, double y1);
+/* fsi.set_boundary(&PipeBoundary(y0, z0, radius, length)) (src/fsi/Boundary.h:131-253; progs/rbc_in_pipe/rbc_in_pipe.cpp:42,733): cylinder
+ * along x. Same near-wall blending / reflection rules as the plates, with the pipe's distance, normal and ray-trace functions. */
+int bib_ib_set_pipe(bib_domain* d, int enabled, double y0, double z0, double radius);
+/* interaction potentials of src/fsi/Potentials.h:29-71 (cut-off = r_min for both) */
+enum { BIB_POTENTIAL_NONE = 0, BIB_POTENTIAL_MORSE = 1 /* (r_min, beta, strength) */, BIB_POTENTIAL_SPRING = 2 /* (r_min, -, strength) */ };
+/* fsi.add_force_decorator(new WallInteraction<T, Potential>(boundary, potential)) (src/fsi/ForceDecorator.hh:25-33): every vertex closer
+ * than r_min to the boundary set above gets f -= potential(dist) * normal, before the membrane forces are added. */
+int bib_ib_set_wall_interaction(bib_domain* d, int type, double r_min, double beta, double strength);
+/* fsi.add_pp_force(new PPPotentialForce<T, Potential>(potential)) (src/fsi/ParticleParticleInteraction.h:28-44): short-range repulsion
+ * between vertices of DIFFERENT particles, evaluated over the reference's collision grid (src/fsi/CollisionForces.h:62-217; r_min <= 1). */
+int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta, double strength);
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices);
 /* Multi-slab domains keep particles in slots (owned + ghost copies of neighbours' particles): global id and role
  * (0 dead, 1 owned, 2/3 ghost of the left/right neighbour) of each slot; vertex/scalar downloads index by slot. On a single

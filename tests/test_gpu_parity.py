@@ -138,6 +138,69 @@ def test_full_step_deterministic_bit_exact(rbc, name):
     assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def _pipe_lattice(g, shape, params, deterministic=True):
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]), {bib.OPT_DETERMINISTIC_SPREAD: float(deterministic)})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, g["vert_init"][..., :3])
+    lat.set_pipe(*[float(v) for v in g["pipe"]])
+    lat.set_wall_interaction(bib.POTENTIAL_MORSE, *[float(v) for v in g["wall_morse"]])
+    lat.set_pp_interaction(bib.POTENTIAL_MORSE, *[float(v) for v in g["pp_morse"]])
+    return lat
+
+
+def test_pipe_wall_and_particle_interactions_vs_golden(rbc):
+    """rbc_in_pipe-type set-up against the reference (tests/golden/make_golden.py:pipe_case): PipeBoundary (near-wall Roma/top-hat
+    blending, reflection), Morse WallInteraction, cell-list particle-particle Morse force. exp() and the order in which a vertex
+    sums its partners differ from the host in the last bits, hence tolerances instead of bit equality: positions 1e-12, forces 1e-9."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_pipe_pp.npz")
+    lat = _pipe_lattice(g, shape, params)
+    n_p, nv = g["vert_init"].shape[:2]
+    for s in range(5, int(g["steps"]) + 1, 5):
+        lat.step(g["body"], n=5)
+        v = lat.vertices().reshape(n_p, nv, 9)
+        assert kit.rel_err(v[..., :3], g[f"vert_{s}"][..., :3]) <= 1e-12, s
+        assert kit.rel_err(v[..., 3:6], g[f"vert_{s}"][..., 3:6]) <= 1e-9, s
+        assert kit.rel_err(v[..., 6:], g[f"vert_{s}"][..., 6:]) <= 1e-9, s
+        assert kit.rel_err(lat.particle_scalars(), g[f"part_{s}"]) <= 1e-12
+    got = lat.download()[::2, ::2, ::2]
+    assert kit.rel_err(got[..., :19], g["pop_final_sample"][..., :19]) <= 1e-11
+    assert np.array_equal(got[..., 22], g["pop_final_sample"][..., 22])
+
+
+def test_particle_particle_force_vs_oracle(orc, rbc):
+    """The gather form of the collision handler against the oracle's restatement of the reference's grid walk, on a dense random cloud
+    of 'particles' in a fully periodic box (every periodic face / edge / corner pairing is hit), Morse and spring potentials."""
+    shape, params, rbc_pos, _ = rbc
+    dims, per = (14, 12, 10), (1, 1, 1)
+    rng = np.random.default_rng(11)
+    n_p = 40
+    centers = rng.uniform(-0.4, 1.0, size=(n_p, 3)) * np.array(dims)
+    centers = np.mod(centers + 0.5, dims) - 0.5
+    pos = kit.place_particles(rbc_pos * 0.35, centers, seed=3)           # small blobs, many close contacts, some across the periodic faces
+    cells = np.zeros(dims + (23,))
+    SOFT = np.array([1e-30, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0])
+    for kind, args in ((bib.POTENTIAL_MORSE, (1.0, 1.0, 1e-3)), (bib.POTENTIAL_SPRING, (0.8, 0.0, 5e-2))):
+        lat = make_lattice(cells, per, 1.0, 1.0)
+        sid = lat.register_shape(shape.verts * 0.35, shape.tris)
+        lat.add_particles(sid, SOFT, pos)                 # (almost) no membrane stiffness: the force is the pp force
+        lat.set_pp_interaction(kind, *args)
+        lat.compute_and_spread_forces()
+        got = lat.vertices()[:, 6:]
+        lat0 = make_lattice(cells, per, 1.0, 1.0)
+        sid = lat0.register_shape(shape.verts * 0.35, shape.tris)
+        lat0.add_particles(sid, SOFT, pos)
+        lat0.compute_and_spread_forces()
+        base = lat0.vertices()[:, 6:]
+        orc.set_pp_interaction(kind, *args)
+        try:
+            want = orc.pp_forces(dims, per, pos, np.repeat(np.arange(n_p), shape.nv))
+        finally:
+            orc.reset_modes()
+        assert np.abs(want).max() > 1e-6 and np.count_nonzero(np.abs(want).sum(1)) > 200
+        assert np.abs((got - base) - want).max() <= 1e-12 * np.abs(want).max()
+
+
 def test_async_result_readback_matches_golden(rbc):
     """bib_ib_results_download_async: the read-back of step s overlaps step s+1 and still delivers step s, bit for bit."""
     import torch
