@@ -19,7 +19,7 @@ LIB_PATH = _HERE / "libbiblbm_b200.so"
 # every symbol include/biblbm_b200.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
-    "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_external_vector", "bib_compute_velocity",
+    "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
@@ -136,6 +136,14 @@ class Lattice:
     def setBoundaryVelocity(self, box, velocities):
         v = np.ascontiguousarray(velocities, dtype=np.float64)
         _check(self.lib.bib_set_boundary_velocity(self.h, _box(box), _dptr(v)))
+
+    def set_guo_wall_nodes(self, nodes, wall_velocity=None):
+        """GuoRigidWallBoundary: nodes [n][7] = {x, y, z, dir_x, dir_y, dir_z, delta} (kit.Oracle.guo_build / the host instantiator)."""
+        nodes = np.asarray(nodes, dtype=np.float64).reshape(-1, 7)
+        ld = np.ascontiguousarray(nodes[:, :6], dtype=np.int32)
+        delta = np.ascontiguousarray(nodes[:, 6], dtype=np.float64)
+        wv = None if wall_velocity is None else np.ascontiguousarray(wall_velocity, dtype=np.float64)
+        _check(self.lib.bib_set_guo_wall_nodes(self.h, ld.shape[0], ld.ctypes.data_as(C.POINTER(C.c_int)), _dptr(delta), None if wv is None else _dptr(wv)))
 
     def setExternalVector(self, F, box=None):
         _check(self.lib.bib_set_external_vector(self.h, _box(box or self.full), C.c_double(F[0]), C.c_double(F[1]), C.c_double(F[2])))

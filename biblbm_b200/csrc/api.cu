@@ -99,6 +99,9 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     if (d->results_dev) cudaFree(d->results_dev);
+    if (d->guo_nodes) cudaFree(d->guo_nodes);
+    if (d->guo_delta) cudaFree(d->guo_delta);
+    if (d->guo_vel) cudaFree(d->guo_vel);
     if (d->pp_head) cudaFree(d->pp_head);
     if (d->pp_next) cudaFree(d->pp_next);
     if (d->pp_vobj) cudaFree(d->pp_vobj);
@@ -169,6 +172,11 @@ int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* vel
     BIB_ENTER(d);
     if (!box || !velocities) { bib_set_error("set_boundary_velocity: null argument"); return 0; }
     return lbm_set_wall_velocity(d, box, velocities);
+}
+int bib_set_guo_wall_nodes(bib_domain* d, int n, const int* location_direction6, const double* delta, const double* wall_velocity3) {
+    BIB_ENTER(d);
+    if (n > 0 && (!location_direction6 || !delta)) { bib_set_error("set_guo_wall_nodes: null argument"); return 0; }
+    return lbm_set_guo_nodes(d, n, location_direction6, delta, wall_velocity3);
 }
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
     BIB_ENTER(d);

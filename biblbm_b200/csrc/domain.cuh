@@ -114,6 +114,7 @@ struct bib_domain {
     int gnx = 0;                          // global nx
     // IB
     std::vector<WallPlane> walls;
+    int n_guo = 0; int* guo_nodes = nullptr; double* guo_delta = nullptr; double* guo_vel = nullptr;   // Guo off-lattice wall nodes
     std::vector<ShapeDev> shapes;
     std::vector<ParticleGroup> groups;
     int n_particles = 0;
@@ -152,6 +153,8 @@ int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
 int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient);
 int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel);
 int lbm_apply_walls(bib_domain* d);
+int lbm_set_guo_nodes(bib_domain* d, int n, const int* loc_dir, const double* delta, const double* wall_velocity);
+int lbm_apply_guo(bib_domain* d);
 int lbm_wall_velocity_fill(bib_domain* d);
 int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz);
 

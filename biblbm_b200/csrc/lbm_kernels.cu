@@ -536,7 +536,7 @@ int lbm_launch_collide_stream(bib_domain* d) {
         BIB_CHECK(cudaGetLastError());
         d->cur = 1 - d->cur;
         if (d->n_ranks > 1 && !comm_halo_exchange(d, d->stream)) return 0;
-        return lbm_apply_walls(d);      // level-0 internal processors run after streaming (and after the halo is in place)
+        return lbm_apply_walls(d) && lbm_apply_guo(d);      // level-0, then level-1 internal processors run after streaming (and after the halo is in place)
     }
     LbmParams pb = p; pb.x_first = 0; pb.x_stride = d->nx - 1;
     launch_main(d, pb, 2, d->stream);
@@ -553,7 +553,7 @@ int lbm_launch_collide_stream(bib_domain* d) {
     BIB_CHECK(cudaGetLastError());
     d->cur = 1 - d->cur;
     BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_halo, 0));
-    return lbm_apply_walls(d);
+    return lbm_apply_walls(d) && lbm_apply_guo(d);
 }
 
 static bool wall_box(const bib_domain* d, const int box[6], int dir) {
@@ -593,6 +593,94 @@ int lbm_apply_walls(bib_domain* d) {
         d->launches++;
     }
     if (!d->walls.empty()) BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+// GuoRigidWallBoundaryFunctional::process (src/fsi/GuoBoundaryCondition.hh:133-198, depth 2): one thread per wall node. The node's
+// 19 populations are rebuilt from the equilibrium at the extrapolated wall momentum plus the extrapolated non-equilibrium part
+// of the two fluid nodes behind it (loc + dir, loc + 2 dir). Nodes whose own dynamics is NoDynamics / BounceBack get no
+// equilibrium part (their computeEquilibrium returns 0; see oracle/biblbm_oracle.c orc_guo_apply for where that happens).
+__device__ __forceinline__ double d_ma2_equilibrium(int i, double rhoBar, double invRho, const double* j, double jSqr) {
+    const double t = i == 0 ? 1. / 3 : ((i >= 1 && i <= 3) || (i >= 10 && i <= 12) ? 1. / 18 : 1. / 36);
+    const double c_j = c_cx[i] * j[0] + c_cy[i] * j[1] + c_cz[i] * j[2];
+    return t * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
+}
+__global__ void __launch_bounds__(128) k_guo_wall(double* __restrict__ f, const uint8_t* __restrict__ kind, const int* __restrict__ nodes,
+                                                  const double* __restrict__ delta_arr, const double* __restrict__ wall_vel, int n_nodes,
+                                                  int nxl, int gnx, int ny, int nz, int x_offset, int per_x, int per_y, int per_z,
+                                                  long long plane, long long vol) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_nodes) return;
+    const int* nd = nodes + 6 * w;
+    const int lx = nd[0] - x_offset;
+    if (lx < 0 || lx >= nxl) return;                       // another slab owns this node
+    int c1[3] = {nd[0] + nd[3], nd[1] + nd[4], nd[2] + nd[5]}, c2[3] = {nd[0] + 2 * nd[3], nd[1] + 2 * nd[4], nd[2] + 2 * nd[5]};
+    if (per_x) { c1[0] = (c1[0] + gnx) % gnx; c2[0] = (c2[0] + 2 * gnx) % gnx; }
+    if (per_y) { c1[1] = (c1[1] + ny) % ny; c2[1] = (c2[1] + 2 * ny) % ny; }
+    if (per_z) { c1[2] = (c1[2] + nz) % nz; c2[2] = (c2[2] + 2 * nz) % nz; }
+    const long long i0 = (long long)(lx + 1) * plane + (long long)nd[1] * nz + nd[2];
+    const long long i1 = (long long)(c1[0] - x_offset + 1) * plane + (long long)c1[1] * nz + c1[2];
+    const long long i2 = (long long)(c2[0] - x_offset + 1) * plane + (long long)c2[1] * nz + c2[2];
+    double f1[BIB_Q], f2[BIB_Q];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) { f1[i] = f[(long long)i * vol + i1]; f2[i] = f[(long long)i * vol + i2]; }
+    double rhoBar1, rhoBar2, j1[3], j2[3];
+    d_rhoBar_j(f1, rhoBar1, j1[0], j1[1], j1[2]);
+    d_rhoBar_j(f2, rhoBar2, j2[0], j2[1], j2[2]);
+    const double j1sqr = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
+    const double j2sqr = j2[0] * j2[0] + j2[1] * j2[1] + j2[2] * j2[2];
+    const double inv1 = 1. / (rhoBar1 + 1.), inv2 = 1. / (rhoBar2 + 1.);
+    const double delta = delta_arr[w];
+    const double rhoBar_w = rhoBar1;
+    double wall_j[3], j_w[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) wall_j[d] = (rhoBar_w + 1.) * (wall_vel ? wall_vel[3 * w + d] : 0.0);
+    const bool near = delta < 0.75;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        j_w[d] = near ? (wall_j[d] + (delta - 1.) * j1[d]) + ((1. - delta) / (1. + delta)) * (2. * wall_j[d] + (delta - 1.) * j2[d])
+                      : (1. / delta) * (wall_j[d] + (delta - 1.) * j1[d]);
+    const double jSqr_w = j_w[0] * j_w[0] + j_w[1] * j_w[1] + j_w[2] * j_w[2];
+    const bool no_eq = kind && kind[i0] != 0;
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) {
+        const double n1 = f1[i] - d_ma2_equilibrium(i, rhoBar1, inv1, j1, j1sqr);
+        const double n2 = f2[i] - d_ma2_equilibrium(i, rhoBar2, inv2, j2, j2sqr);
+        const double neq = near ? delta * n1 + (1. - delta) * n2 : n1;
+        f[(long long)i * vol + i0] = (no_eq ? 0.0 : d_ma2_equilibrium(i, rhoBar_w, 1. / (rhoBar_w + 1.), j_w, jSqr_w)) + neq;
+    }
+}
+int lbm_set_guo_nodes(bib_domain* d, int n, const int* loc_dir, const double* delta, const double* wall_velocity) {
+    if (d->guo_nodes) { cudaFree(d->guo_nodes); cudaFree(d->guo_delta); if (d->guo_vel) cudaFree(d->guo_vel); d->guo_nodes = nullptr; d->guo_delta = nullptr; d->guo_vel = nullptr; }
+    d->n_guo = 0;
+    if (n <= 0) return 1;
+    for (int w = 0; w < n; ++w) {
+        const int* q = loc_dir + 6 * w;
+        bool ok = q[0] >= 0 && q[0] < d->gnx && q[1] >= 0 && q[1] < d->ny && q[2] >= 0 && q[2] < d->nz;
+        const int nn[3] = {d->gnx, d->ny, d->nz};
+        for (int k = 0; ok && k < 3; ++k) {
+            const int far = q[k] + 2 * q[3 + k];
+            if (!d->per[k] && (far < 0 || far >= nn[k])) ok = false;
+        }
+        if (!ok) { bib_set_error("set_guo_wall_nodes: node or its two fluid neighbours outside the lattice"); return 0; }
+        if (d->n_ranks > 1 && q[3] != 0) { bib_set_error("set_guo_wall_nodes: on multi-slab domains the node direction must not have an x component"); return 0; }
+    }
+    BIB_CHECK(cudaMalloc(&d->guo_nodes, (size_t)n * 6 * sizeof(int)));
+    BIB_CHECK(cudaMalloc(&d->guo_delta, (size_t)n * sizeof(double)));
+    BIB_CHECK(cudaMemcpy(d->guo_nodes, loc_dir, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice));
+    BIB_CHECK(cudaMemcpy(d->guo_delta, delta, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    if (wall_velocity) {
+        BIB_CHECK(cudaMalloc(&d->guo_vel, (size_t)n * 3 * sizeof(double)));
+        BIB_CHECK(cudaMemcpy(d->guo_vel, wall_velocity, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    d->n_guo = n;
+    return 1;
+}
+int lbm_apply_guo(bib_domain* d) {
+    if (d->n_guo == 0) return 1;
+    k_guo_wall<<<(d->n_guo + 127) / 128, 128, 0, d->stream>>>(d->f[d->cur], d->kind, d->guo_nodes, d->guo_delta, d->guo_vel, d->n_guo, d->nx, d->gnx, d->ny, d->nz,
+                                                           d->x_offset, d->n_ranks == 1 ? d->per[0] : 0, d->per[1], d->per[2], (long long)d->plane, (long long)d->vol);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
     return 1;
 }
 int lbm_wall_velocity_fill(bib_domain* d) {

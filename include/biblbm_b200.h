@@ -72,6 +72,13 @@ int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, dou
 int bib_add_velocity_boundary(bib_domain* d, const int box[6], int direction, int orientation);
 int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* velocities);
 
+/* Off-lattice (curved) no-slip / moving wall = fsi::GuoRigidWallBoundary (src/fsi/GuoBoundaryCondition.hh:25-198; rbc_in_pipe.cpp:303-306):
+ * a list of wall nodes {location x,y,z (global lattice coordinates), inward lattice direction dx,dy,dz}, the fraction `delta` of the link
+ * between the wall and the first fluid node, and the wall velocity per node (NULL = at rest). Applied after every
+ * bib_collide_and_stream like the reference's level-1 internal processor. A second call replaces the list; n = 0 removes it.
+ * (The list itself is geometry: GuoRigidWallBoundaryInstantiator::process builds it on the host at set-up time.) */
+int bib_set_guo_wall_nodes(bib_domain* d, int n, const int* location_direction6, const double* delta, const double* wall_velocity3);
+
 /* F7: setExternalVector(lattice, domain, forceBeginsAt, F)   (src/dataProcessors/dataInitializerFunctional3D.hh:1144-1154) */
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz);
 /* F6: computeVelocity(lattice, velocity, domain)             (src/dataProcessors/dataAnalysisFunctional3D.hh:772-784) */

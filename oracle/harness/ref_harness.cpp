@@ -14,6 +14,8 @@
 #include "palabos3D.hh"
 #include "fsi/headers.h"
 #include "fsi/headers.hh"
+#include "fsi/GuoBoundaryCondition.h"
+#include "fsi/GuoBoundaryCondition.hh"
 #include "common/calibrate_rbc_shape.h"
 #include "common/shear_flow_setup.h"
 #include "common/particle_position_regulator.h"
@@ -293,6 +295,28 @@ static int run(const Config& cfg) {
         else
             initializeAtEquilibrium(lattice, domain, SineInit<double>(nx, ny, nz, cfg.num("u0", 0.05)));
         lattice.initialize();
+    }
+
+    // rbc_in_pipe.cpp:285-343 (setup_flow): Guo off-lattice wall condition on the pipe surface + NoDynamics outside of it
+    PipeBoundary<double>* guo_pipe = 0;
+    GuoRigidWallBoundary<double, DESCRIPTOR>* guo = 0;
+    if (cfg.integer("guo_pipe", 0) != 0 && cfg.has("pipe_radius")) {
+        guo_pipe = new PipeBoundary<double>(cfg.num("pipe_y0", 0.5 * (ny - 1)), cfg.num("pipe_z0", 0.5 * (nz - 1)), cfg.num("pipe_radius", 0), cfg.num("pipe_length", nx - 1));
+        guo = new GuoRigidWallBoundary<double, DESCRIPTOR>(*guo_pipe, lattice);
+        guo->insert();
+        defineDynamics<double, DESCRIPTOR>(lattice, lattice.getBoundingBox(), new BoundaryOutside<double>(*guo_pipe, std::sqrt(2)),
+                                           new plb::NoDynamics<double, DESCRIPTOR>());
+        if (cfg.has("guo_wall_ux")) guo->set_wall_velocity(Array<double, 3>(cfg.num("guo_wall_ux", 0), cfg.num("guo_wall_uy", 0), cfg.num("guo_wall_uz", 0)));
+        lattice.initialize();
+        if (cfg.has("guo_dump")) {
+            std::vector<double> nd;
+            for (GuoRigidWallBoundary<double, DESCRIPTOR>::iterator it = guo->begin(); it != guo->end(); ++it) {
+                nd.push_back(it->location.x); nd.push_back(it->location.y); nd.push_back(it->location.z);
+                nd.push_back(it->direction.x); nd.push_back(it->direction.y); nd.push_back(it->direction.z);
+                nd.push_back(it->delta);
+            }
+            write_f64(out + "/guo_nodes.f64", nd);
+        }
     }
 
     // Optional frozen synthetic external field (force + phase), read from a file in serialised-cell order [x][y][z][4]

@@ -72,15 +72,11 @@ inline int classify_dynamics(const Dynamics<double, descriptors::ForcedPhaseD3Q1
 }
 
 inline void read_omegas(const Dynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>& dyn, double& omega, double& omega_inner) {
-    if (!dynamic_cast<const GuoExternalForceVOFDynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>*>(&dyn))
-        die("the background dynamics must be GuoExternalForceVOFDynamics (src/fsi/VariableViscosityDynamics.h:45-77)");
-    // the inner relaxation rate has no accessor; its serialised form is (omega, omega_inner) (VariableViscosityDynamics.hh:197-201)
-    std::vector<char> data;
-    HierarchicSerializer serializer(data, dyn.getId());
-    dyn.serialize(serializer);
-    HierarchicUnserializer unserializer(data, 0);
-    omega = unserializer.readValue<double>();
-    omega_inner = unserializer.readValue<double>();
+    const GuoExternalForceVOFDynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>* vof =
+        dynamic_cast<const GuoExternalForceVOFDynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>*>(&dyn);
+    if (!vof) die("the background dynamics must be GuoExternalForceVOFDynamics (src/fsi/VariableViscosityDynamics.h:45-77)");
+    omega = vof->getOmega();
+    omega_inner = vof->omega2_;           // no accessor in the reference; see overlay/fsi/headers.h
 }
 
 inline void upload_state(Twin& t) {
@@ -404,25 +400,40 @@ BIB_IBD_TEMPLATE void BIB_IBD::drop_device_particles() {
 
 BIB_IBD_TEMPLATE void BIB_IBD::configure_decorators_and_boundary(bibglue::Twin& t) {
     for (pluint i = 0; i < decorators_.size(); ++i) {
-        if (ParticlePositionRegulator<T>* r = dynamic_cast<ParticlePositionRegulator<T>*>(decorators_[i])) {
+        ForceDecorator<T>* dec = decorators_[i];
+        if (ParticlePositionRegulator<T>* r = dynamic_cast<ParticlePositionRegulator<T>*>(dec)) {
             BIBGLUE_OK(bib_ib_set_regulator(t.d, r->p, r->position[0], r->position[1], r->position[2]));
+        } else if (WallInteraction<T, MorsePotential<T> >* w = dynamic_cast<WallInteraction<T, MorsePotential<T> >*>(dec)) {
+            if (w->boundary_ != boundary_) bibglue::die("WallInteraction must refer to the boundary passed to fsi.set_boundary()");
+            BIBGLUE_OK(bib_ib_set_wall_interaction(t.d, BIB_POTENTIAL_MORSE, w->interaction_.r_min, w->interaction_.beta, w->interaction_.strength));
+        } else if (WallInteraction<T, SpringPotential<T> >* w2 = dynamic_cast<WallInteraction<T, SpringPotential<T> >*>(dec)) {
+            if (w2->boundary_ != boundary_) bibglue::die("WallInteraction must refer to the boundary passed to fsi.set_boundary()");
+            BIBGLUE_OK(bib_ib_set_wall_interaction(t.d, BIB_POTENTIAL_SPRING, w2->interaction_.min_dist, 0., w2->interaction_.strength));
         } else {
-            pcerr << "biblbm_b200 binding: unsupported ForceDecorator " << typeid(*decorators_[i]).name() << std::endl;
+            pcerr << "biblbm_b200 binding: unsupported ForceDecorator " << typeid(*dec).name() << std::endl;
             exit(-1);
         }
     }
-    if (!pp_forces_.empty()) bibglue::die("particle-particle interaction forces (add_pp_force) are not supported yet");
+    if (pp_forces_.size() > 1) bibglue::die("only one particle-particle interaction force is supported");
+    if (pp_forces_.size() == 1) {
+        if (PPPotentialForce<T, MorsePotential<T> >* m = dynamic_cast<PPPotentialForce<T, MorsePotential<T> >*>(pp_forces_[0])) {
+            BIBGLUE_OK(bib_ib_set_pp_interaction(t.d, BIB_POTENTIAL_MORSE, m->potential_.r_min, m->potential_.beta, m->potential_.strength));
+        } else if (PPPotentialForce<T, SpringPotential<T> >* sp = dynamic_cast<PPPotentialForce<T, SpringPotential<T> >*>(pp_forces_[0])) {
+            BIBGLUE_OK(bib_ib_set_pp_interaction(t.d, BIB_POTENTIAL_SPRING, sp->potential_.min_dist, 0., sp->potential_.strength));
+        } else {
+            pcerr << "biblbm_b200 binding: unsupported PPInteractionForce " << typeid(*pp_forces_[0]).name() << std::endl;
+            exit(-1);
+        }
+    }
     if (boundary_) {
-        ParallelPlatesBoundary<T>* plates = dynamic_cast<ParallelPlatesBoundary<T>*>(boundary_);
-        if (!plates) bibglue::die("only ParallelPlatesBoundary is supported by fsi.set_boundary() so far");
-        // y0/y1 are private; recover them exactly from the public interface (src/fsi/Boundary.h:327-330,362-365)
-        const Box3D bb = plates->get_bounding_box(0);
-        const double yl = (double)bb.y0, yh = (double)bb.y1;
-        const double y0 = yl - plates->distance_to_boundary(Array<T, 3>(0., yl, 0.));
-        const double y1 = yh + plates->distance_to_boundary(Array<T, 3>(0., yh, 0.));
-        if (!(y1 > y0) || plates->distance_to_boundary(Array<T, 3>(0., y0, 0.)) != 0. || plates->distance_to_boundary(Array<T, 3>(0., y1, 0.)) != 0.)
-            bibglue::die("could not recover the plate positions of the ParallelPlatesBoundary");
-        BIBGLUE_OK(bib_ib_set_parallel_plates(t.d, 1, y0, y1));
+        if (ParallelPlatesBoundary<T>* plates = dynamic_cast<ParallelPlatesBoundary<T>*>(boundary_)) {
+            BIBGLUE_OK(bib_ib_set_parallel_plates(t.d, 1, plates->y0, plates->y1));
+        } else if (PipeBoundary<T>* pipe = dynamic_cast<PipeBoundary<T>*>(boundary_)) {
+            BIBGLUE_OK(bib_ib_set_pipe(t.d, 1, pipe->y0, pipe->z0, pipe->radius));
+        } else {
+            pcerr << "biblbm_b200 binding: unsupported Boundary " << typeid(*boundary_).name() << std::endl;
+            exit(-1);
+        }
     }
 }
 

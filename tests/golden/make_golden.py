@@ -233,6 +233,33 @@ def make_pipe():
     print("pipe golden ok")
 
 
+def make_guo():
+    """Guo off-lattice wall on a pipe (rbc_in_pipe.cpp:285-343: GuoRigidWallBoundary + NoDynamics outside), body-force driven flow
+    starting from rest, tau = 0.55 as in progs/rbc_in_pipe/input.xml: LBM only, and the whole rbc_in_pipe set-up in miniature
+    (pipe_case + Guo wall)."""
+    nx, ny, nz = 12, 24, 24
+    y0 = z0 = 11.5; R = 9.3
+    cfg = dict(nx=nx, ny=ny, nz=nz, steps=6, dump_every=1, periodicity="pff", omega=1 / 0.55, omega_inner=0.5, init="uniform", rho=1.0,
+               ux=0.0, uy=0.0, uz=0.0, body_x=2e-5, body_y=0, body_z=0, pipe_y0=y0, pipe_z0=z0, pipe_radius=R, pipe_length=nx - 1,
+               guo_pipe=1, guo_dump=1)
+    out = kit.run_reference(cfg)
+    np.savez_compressed(HERE / "lbm_guo_pipe.npz", pop_init=out["pop_init"], pop_1=out["pop_1"], pop_2=out["pop_2"], pop_6=out["pop_6"],
+                        nodes=out["guo_nodes"].reshape(-1, 7), pipe=np.array([y0, z0, R]), omega=1 / 0.55, omega_inner=0.5, body=np.array([2e-5, 0.0, 0.0]),
+                        per=np.array([1, 0, 0], dtype=np.int32))
+    shape, params, pos, cfg = pipe_case()
+    cfg.update(guo_pipe=1, guo_dump=1, omega=1 / 0.55)
+    out = kit.run_reference(cfg, verts=shape.verts, tris=shape.tris, params=params, particle_pos=pos)
+    steps = cfg["steps"]
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                nodes=out["guo_nodes"].reshape(-1, 7), omega=1 / 0.55, omega_inner=0.5, steps=steps, body=np.array([1e-5, 0.0, 0.0]),
+                per=np.array([1, 0, 0], dtype=np.int32), pipe=np.array([cfg["pipe_y0"], cfg["pipe_z0"], cfg["pipe_radius"]]),
+                wall_morse=np.array([2.0, 2.0, 1e-4]), pp_morse=np.array([1.0, 1.0, 1e-3]))
+    for s in range(5, steps + 1, 5):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_pipe_guo.npz", **keep)
+    print("guo goldens ok")
+
+
 if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
@@ -244,4 +271,5 @@ if __name__ == "__main__":
     make_capsule()
     make_plates()
     make_pipe()
+    make_guo()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -196,6 +196,23 @@ class Oracle:
         self.lib.orc_pp_forces(C.c_int(dims[0]), C.c_int(dims[1]), C.c_int(dims[2]), _i(pr), C.c_long(pos.shape[0]), _d(pos), _i(obj), _d(f))
         return f
 
+    def guo_build(self, dims):
+        """Wall nodes of the Guo off-lattice condition for the boundary set with set_pipe / set_parallel_plates: [n][7]
+        {x, y, z, dir_x, dir_y, dir_z, delta}."""
+        self.lib.orc_guo_build.restype = C.c_long
+        n = self.lib.orc_guo_build(C.c_int(dims[0]), C.c_int(dims[1]), C.c_int(dims[2]), None, C.c_long(0))
+        nodes = np.zeros((n, 7))
+        self.lib.orc_guo_build(C.c_int(dims[0]), C.c_int(dims[1]), C.c_int(dims[2]), _d(nodes), C.c_long(n))
+        return nodes
+
+    def guo_apply(self, cells, per, nodes, wall_velocity=None, kind=None):
+        nx, ny, nz, _ = cells.shape
+        pr = np.asarray(per, dtype=np.int32)
+        wv = None if wall_velocity is None else np.ascontiguousarray(wall_velocity, dtype=np.float64)
+        self.lib.orc_guo_apply(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(pr), C.c_long(nodes.shape[0]), _d(nodes),
+                               None if wv is None else _d(wv),
+                               None if kind is None else np.ascontiguousarray(kind, dtype=np.uint8).ctypes.data_as(_u8p))
+
     def reset_modes(self):
         self.set_parallel_plates(0); self.set_wall_interaction(0); self.set_pp_interaction(0); self.set_particle_model(0)
 
@@ -406,6 +423,15 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     s = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (s if s > 0 else 1.0))
+
+
+def pipe_outside_kind(dims, y0, z0, radius):
+    """Cell kinds of rbc_in_pipe.cpp:314-318: NoDynamics where BoundaryOutside(pipe, std::sqrt(2)) holds -- its margin is truncated
+    to plint 1 (reference src/fsi/Boundary.h:113-128), i.e. where (y-y0)^2 + (z-z0)^2 >= (radius + 1)^2."""
+    nx, ny, nz = dims
+    yy, zz = np.meshgrid(np.arange(ny, dtype=np.float64), np.arange(nz, dtype=np.float64), indexing="ij")
+    inside = ((yy - y0) * (yy - y0) + (zz - z0) * (zz - z0)) < (radius - (-1.0)) * (radius - (-1.0))
+    return np.ascontiguousarray(np.where(inside, 0, 1).astype(np.uint8)[None].repeat(nx, 0))
 
 
 def write_gmsh(path, verts, tris):

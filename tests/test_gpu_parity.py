@@ -168,6 +168,56 @@ def test_pipe_wall_and_particle_interactions_vs_golden(rbc):
     assert np.array_equal(got[..., 22], g["pop_final_sample"][..., 22])
 
 
+def test_guo_pipe_wall_vs_golden():
+    """GuoRigidWallBoundary (off-lattice pipe wall) + NoDynamics outside, LBM only: bit-identical to the reference."""
+    g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]))
+    dims = g["pop_init"].shape[:3]
+    kind = kit.pipe_outside_kind(dims, *[float(v) for v in g["pipe"]])
+    _set_kinds(lat, kind)
+    lat.set_guo_wall_nodes(g["nodes"])
+    for s in range(1, 7):
+        lat.setExternalVector(g["body"])
+        lat.collideAndStream()
+        if f"pop_{s}" in g:
+            got = lat.download()
+            assert np.array_equal(got[..., :19], g[f"pop_{s}"][..., :19]), s
+
+
+def _set_kinds(lat, kind):
+    nx, ny, nz = kind.shape
+    for y in range(ny):
+        z = 0
+        while z < nz:
+            if kind[0, y, z]:
+                z1 = z
+                while z1 + 1 < nz and kind[0, y, z1 + 1] == kind[0, y, z]:
+                    z1 += 1
+                lat.defineDynamics((0, nx - 1, y, y, z, z1), int(kind[0, y, z]))
+                z = z1 + 1
+            else:
+                z += 1
+
+
+def test_rbc_in_pipe_miniature_vs_golden(rbc):
+    """BASELINE.json configs[2] (progs/rbc_in_pipe) in miniature: Guo wall, NoDynamics outside, PipeBoundary, Morse wall / particle
+    interactions, 3 RBCs, 20 steps against the reference."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_pipe_guo.npz")
+    lat = _pipe_lattice(g, shape, params)
+    _set_kinds(lat, kit.pipe_outside_kind(g["pop_init"].shape[:3], *[float(v) for v in g["pipe"]]))
+    lat.set_guo_wall_nodes(g["nodes"])
+    n_p, nv = g["vert_init"].shape[:2]
+    for s in range(5, int(g["steps"]) + 1, 5):
+        lat.step(g["body"], n=5)
+        v = lat.vertices().reshape(n_p, nv, 9)
+        assert kit.rel_err(v[..., :3], g[f"vert_{s}"][..., :3]) <= 1e-12, s
+        assert kit.rel_err(v[..., 6:], g[f"vert_{s}"][..., 6:]) <= 1e-9, s
+    got = lat.download()[::2, ::2, ::2]
+    assert kit.rel_err(got[..., :19], g["pop_final_sample"][..., :19]) <= 1e-11
+    assert np.array_equal(got[..., 22], g["pop_final_sample"][..., 22])
+
+
 def test_particle_particle_force_vs_oracle(orc, rbc):
     """The gather form of the collision handler against the oracle's restatement of the reference's grid walk, on a dense random cloud
     of 'particles' in a fully periodic box (every periodic face / edge / corner pairing is hit), Morse and spring potentials."""

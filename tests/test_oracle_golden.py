@@ -228,6 +228,50 @@ def test_pipe_wall_and_particle_interactions_bit_exact(orc, rbc):
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_guo_pipe_wall_bit_exact(orc):
+    """GuoRigidWallBoundary on a pipe + NoDynamics outside (rbc_in_pipe.cpp:285-343), LBM only: the wall-node list and 6 steps."""
+    g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
+    cells = g["pop_init"].copy()
+    dims = cells.shape[:3]
+    orc.set_pipe(1, *[float(v) for v in g["pipe"]])
+    try:
+        nodes = orc.guo_build(dims)
+        assert np.array_equal(nodes, g["nodes"]) and len(nodes) > 500
+        kind = kit.pipe_outside_kind(dims, *[float(v) for v in g["pipe"]])
+        assert kind[0][tuple(nodes[:, 1:3].astype(int).T)].any(), "some wall nodes must be NoDynamics cells (the margin-truncation quirk)"
+        for s in range(1, 7):
+            orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], None, None, None, None, kind=kind)
+            orc.guo_apply(cells, g["per"], nodes, kind=kind)
+            if f"pop_{s}" in g:
+                assert np.array_equal(cells, g[f"pop_{s}"]), s
+    finally:
+        orc.reset_modes()
+
+
+def test_rbc_in_pipe_miniature_bit_exact(orc, rbc):
+    """The whole rbc_in_pipe set-up in miniature: Guo wall + NoDynamics outside, PipeBoundary for the particles, Morse wall and
+    particle-particle interaction, 3 RBCs, 20 steps."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_pipe_guo.npz")
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    dims = cells.shape[:3]
+    orc.set_pipe(1, *[float(v) for v in g["pipe"]])
+    orc.set_wall_interaction(1, *[float(v) for v in g["wall_morse"]])
+    orc.set_pp_interaction(1, *[float(v) for v in g["pp_morse"]])
+    try:
+        nodes = orc.guo_build(dims)
+        assert np.array_equal(nodes, g["nodes"])
+        kind = kit.pipe_outside_kind(dims, *[float(v) for v in g["pipe"]])
+        for s in range(1, int(g["steps"]) + 1):
+            orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], shape, params, vert, state, kind=kind)
+            orc.guo_apply(cells, g["per"], nodes, kind=kind)
+            if s % 5 == 0:
+                assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"]), f"step {s}"
+    finally:
+        orc.reset_modes()
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+
+
 def test_golden_membrane_forces_are_not_trivial():
     """Guards the fixtures themselves: the RBC goldens must carry real membrane stiffness and non-zero vertex forces."""
     z = np.load(kit.GOLDEN / "rbc626.npz")
