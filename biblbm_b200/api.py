@@ -29,7 +29,7 @@ SYMBOLS = [
 
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR = 1, 2, 3
 CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
-PARTICLE_RBC, PARTICLE_CAPSULE = 0, 1
+PARTICLE_RBC, PARTICLE_CAPSULE, PARTICLE_SEMIRIGID = 0, 1, 2
 POTENTIAL_NONE, POTENTIAL_MORSE, POTENTIAL_SPRING = 0, 1, 2
 
 _lib = None

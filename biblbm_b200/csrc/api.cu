@@ -112,7 +112,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->vfrc) cudaFree(d->vfrc);
     if (d->pstate) cudaFree(d->pstate);
     for (ShapeDev& s : d->shapes) {
-        void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts};
+        void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts, s.rest_radial};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
     for (WallPlane& w : d->walls) if (w.vel) cudaFree(w.vel);

@@ -22,6 +22,7 @@ struct ShapeDev {
     int* tris = nullptr;          // [nt][3]
     double* tri_area = nullptr;   // [nt]
     double* verts = nullptr;      // [nv][3] rest configuration (capsule FEM reference state)
+    double* rest_radial = nullptr; // [nv] |vertex - shape centre| (semi-rigid particles)
     int* links = nullptr;         // [nl][2]
     double* link_len = nullptr;   // [nl]
     int* pairs = nullptr;         // [np][4]

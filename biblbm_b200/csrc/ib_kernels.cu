@@ -726,6 +726,60 @@ __global__ void __launch_bounds__(256) k_capsule_forces(CapParams q, const doubl
     }
 }
 
+// ------------------------------------------------------------------------------------------------ platelets: SemiRigidParticle3D
+// SemiRigidParticle3D::compute_forces (src/fsi/SemiRigidParticle.hh:56-96). One CTA per particle; the radial spring terms are
+// computed in parallel, their reaction is accumulated by one thread in vertex order (the reference's sequential sum), and each
+// thread then adds radial term, reaction share and its incident link springs in link order.
+struct SemiParams {
+    int nv; long long first_vertex, cap; int first_particle;
+    const int* links; const double* link_len; const int* v_link_off; const int* v_link;
+    const double* rest_radial;      // [nv] |shape vertex - shape centre|
+    double k_in, k_out; const int* role; int f_init;
+};
+__global__ void __launch_bounds__(256) k_semirigid_forces(SemiParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
+                                                          const double* __restrict__ pstate) {
+    extern __shared__ double s_sr[];
+    double* s_pos = s_sr;               // [3][nv]
+    double* s_df = s_sr + 3 * q.nv;     // [3][nv]
+    __shared__ double s_com[3];
+    const int pl = blockIdx.x;
+    if (q.role && q.role[q.first_particle + pl] != 1) return;
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    const double* st = pstate + (long long)(q.first_particle + pl) * 11;
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        const double x = vpos[base + v], y = vpos[q.cap + base + v], z = vpos[2 * q.cap + base + v];
+        s_pos[v] = x; s_pos[q.nv + v] = y; s_pos[2 * q.nv + v] = z;
+        const double dx = x - st[2], dy = y - st[3], dz = z - st[4];
+        const double l = sqrt(dx * dx + dy * dy + dz * dz);
+        const double l0 = q.rest_radial[v];
+        const double k = -q.k_out * (l - l0) / (l0 * l);
+        s_df[v] = k * dx; s_df[q.nv + v] = k * dy; s_df[2 * q.nv + v] = k * dz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double acc = 0.0;
+        for (int v = 0; v < q.nv; ++v) acc -= s_df[threadIdx.x * q.nv + v];
+        s_com[threadIdx.x] = acc / (double)q.nv;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        if (q.f_init) { f[0] = vfrc[base + v]; f[1] = vfrc[q.cap + base + v]; f[2] = vfrc[2 * q.cap + base + v]; }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { f[d] += s_df[d * q.nv + v]; f[d] += s_com[d]; }
+        for (int e = q.v_link_off[v]; e < q.v_link_off[v + 1]; ++e) {
+            const int code = q.v_link[e], l = code >> 1, end = code & 1;
+            const int i0 = q.links[2 * l], i1 = q.links[2 * l + 1];
+            const double dv[3] = {s_pos[i0] - s_pos[i1], s_pos[q.nv + i0] - s_pos[q.nv + i1], s_pos[2 * q.nv + i0] - s_pos[2 * q.nv + i1]};
+            const double L = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+            const double df = -q.k_in * (L - q.link_len[l]) / (L * q.link_len[l]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { if (end == 0) f[d] += df * dv[d]; else f[d] -= df * dv[d]; }
+        }
+        vfrc[base + v] = f[0]; vfrc[q.cap + base + v] = f[1]; vfrc[2 * q.cap + base + v] = f[2];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ M4: wall / particle-particle forces
 // fsi/Potentials.h:29-71: type 1 = MorsePotential(r_min, beta, strength), 2 = SpringPotential(min_dist, strength); cutoff = r_min
 __device__ __forceinline__ double d_potential(const PotentialDev& q, double dist) {
@@ -1236,6 +1290,20 @@ int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const 
         volume += (v0[0] * c[0] + v0[1] * c[1] + v0[2] * c[2]) / 6.;
     }
     s.area = area; s.volume = volume;
+    {   // ParticleShape centre (src/fsi/ParticleShape.hh:36-50) and the rest length of the semi-rigid model's radial springs
+        double center[3] = {0, 0, 0};
+        for (int t = 0; t < nt; ++t) {
+            const double *v0 = V(tris[3 * t]), *v1 = V(tris[3 * t + 1]), *v2 = V(tris[3 * t + 2]);
+            for (int k = 0; k < 3; ++k) center[k] += ((v0[k] + v1[k] + v2[k]) / 3.0) * s.h_tri_area[t];
+        }
+        for (int k = 0; k < 3; ++k) center[k] /= area;
+        std::vector<double> rr(nv);
+        for (int i = 0; i < nv; ++i) {
+            const double r0[3] = {V(i)[0] - center[0], V(i)[1] - center[1], V(i)[2] - center[2]};
+            rr[i] = std::sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+        }
+        if (!to_device(&s.rest_radial, rr)) return 0;
+    }
     struct Key { int i0, i1, order; };
     std::vector<Key> keys(3 * (size_t)nt);
     for (int t = 0; t < nt; ++t) for (int j = 0; j < 3; ++j) {
@@ -1423,7 +1491,7 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
 }
 
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
-    if (type != 0 && type != 1) { bib_set_error("particles_add: unknown particle type (BIB_PARTICLE_RBC, BIB_PARTICLE_CAPSULE)"); return 0; }
+    if (type < 0 || type > 2) { bib_set_error("particles_add: unknown particle type (BIB_PARTICLE_RBC, BIB_PARTICLE_CAPSULE, BIB_PARTICLE_SEMIRIGID)"); return 0; }
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("particles_add: unknown shape"); return 0; }
     if (n <= 0) return 1;
     if (d->n_ranks > 1) return ib_particles_add_multislab(d, type, shape_id, params, n, positions);
@@ -1575,6 +1643,18 @@ int ib_forces_and_spread(bib_domain* d) {
     }
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
+        if (gr.type == 2) {
+            SemiParams c;
+            c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
+            c.links = s.links; c.link_len = s.link_len; c.v_link_off = s.v_link_off; c.v_link = s.v_link; c.rest_radial = s.rest_radial;
+            c.k_in = gr.params[1]; c.k_out = gr.params[2]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
+            const size_t smem = (size_t)s.nv * 6 * sizeof(double);
+            if (smem > 200 * 1024) { bib_set_error("semi-rigid particles: mesh too large for the shared-memory kernel"); return 0; }
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_semirigid_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_semirigid_forces<<<gr.count, 256, smem, d->stream>>>(c, d->vpos, d->vfrc, d->pstate);
+            d->launches++;
+            continue;
+        }
         if (gr.type == 1) {      // BIB_PARTICLE_CAPSULE
             CapParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle; c.count = gr.count;

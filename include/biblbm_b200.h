@@ -34,8 +34,10 @@ enum { BIB_CELL_BULK = 0, BIB_CELL_NODYNAMICS = 1, BIB_CELL_BOUNCEBACK = 2 };
 
 /* particle types for bib_ib_particles_add (reference: fsi::RBCParticle, src/fsi/RBCParticle.h:68-100) */
 enum { BIB_PARTICLE_RBC = 0,        /* params: RBCParameters, see bib_ib_particles_add */
-       BIB_PARTICLE_CAPSULE = 1 };  /* fsi::DeformableCapsuleParticle (src/fsi/DeformableCapsule.hh:47-150, neo-Hookean FEM; the shape's
+       BIB_PARTICLE_CAPSULE = 1,  /* fsi::DeformableCapsuleParticle (src/fsi/DeformableCapsule.hh:47-150, neo-Hookean FEM; the shape's
                                        vertices are the stress-free state); params: {G, C, nu_s, kb, 0, 0, 0, 0} (CapsuleParameters) */
+       BIB_PARTICLE_SEMIRIGID = 2 };/* fsi::SemiRigidParticle3D (src/fsi/SemiRigidParticle.hh:56-96; the platelets of rbc_in_pipe): radial springs to the
+                                       centre of mass + link springs; params: {l0, k_in_plane, k_out_of_plane, k_bend, 0, 0, 0, 0} */
 
 /* bib_domain_set_option keys */
 enum {

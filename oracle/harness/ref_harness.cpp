@@ -359,8 +359,15 @@ static int run(const Config& cfg) {
         np = (i64)(pf.size() - 8) / (nv * 3);
         const ParticleShape<double>* shape = shape_library.get_by_tag("RBC");
         const bool capsule = cfg.str("particle_type", "rbc") == "capsule";     // params = {G, C, nu_s, kb, 0, 0, 0, 0}
+        const bool semirigid = cfg.str("particle_type", "rbc") == "semirigid";  // params = {l0, k_in_plane, k_out_of_plane, k_bend, 0, 0, 0, 0}
         for (i64 p = 0; p < np; ++p) {
-            if (capsule) {
+            if (semirigid) {
+                SemiRigidParticleParams<double> sp; sp.l0 = pf[0]; sp.k_in_plane = pf[1]; sp.k_out_of_plane = pf[2]; sp.k_bend = pf[3];
+                SemiRigidParticle3D<double> plt(shape, sp);
+                for (i64 n = 0; n < nv; ++n) for (int d = 0; d < 3; ++d) plt.get_node(n).pos[d] = pf[8 + (p * nv + n) * 3 + d];
+                plt.update();
+                fsi->add_particle(&plt);
+            } else if (capsule) {
                 CapsuleParameters<double> cp; cp.G = pf[0]; cp.C = pf[1]; cp.nu_s = pf[2]; cp.kb = pf[3];
                 DeformableCapsuleParticle<double> cap(shape, cp);
                 for (i64 n = 0; n < nv; ++n) for (int d = 0; d < 3; ++d) cap.get_node(n).pos[d] = pf[8 + (p * nv + n) * 3 + d];

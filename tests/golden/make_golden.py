@@ -181,6 +181,25 @@ def make_plates():
     print("plates golden ok")
 
 
+def make_semirigid():
+    """SemiRigidParticle3D (the platelets of rbc_in_pipe) in a periodic box: sphere mesh as rest shape, started from an affinely
+    deformed configuration so that radial and link springs are loaded."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    nx, ny, nz, steps = 24, 22, 20, 4
+    c = np.array([11.3, 10.2, 9.6])
+    pos = (shape.verts * np.array([1.1, 0.92, 0.98]))[None] + c
+    sp = np.array([float(shape.link_len.mean()), 0.01, 0.02, 0.0, 0, 0, 0, 0])      # l0, k_in_plane, k_out_of_plane, k_bend
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=1, periodicity="ppp", omega=1.0, omega_inner=0.5, u0=0.02,
+                                 particle_type="semirigid"), verts=shape.verts, tris=shape.tris, params=sp, particle_pos=pos)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(),
+                omega=1.0, omega_inner=0.5, steps=steps, sparams=sp, per=np.array([1, 1, 1], dtype=np.int32), body=np.zeros(3), regulator_p=0.0,
+                regulator_target=np.zeros(3))
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]
+    np.savez_compressed(HERE / "ib_semirigid.npz", **keep)
+    print("semirigid golden ok, max |F| =", np.abs(out[f"vert_{steps}"][..., 6:]).max())
+
+
 def pipe_case():
     """rbc_in_pipe-type set-up in miniature (x periodic; PipeBoundary; Morse wall interaction and Morse particle-particle
     interaction with the parameters of progs/rbc_in_pipe/input.xml): RBC A almost touching the pipe wall with the fluid initially
@@ -270,6 +289,7 @@ if __name__ == "__main__":
     make_shear()
     make_capsule()
     make_plates()
+    make_semirigid()
     make_pipe()
     make_guo()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

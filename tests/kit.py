@@ -169,7 +169,7 @@ class Oracle:
                               C.c_int(shape.nv), C.c_int(shape.nt), _i(shape.tris), _d(pos))
 
     def set_particle_model(self, ptype, rest_mesh=None):
-        """0 = RBC (default), 1 = neo-Hookean capsule whose rest configuration is rest_mesh [nv][3]."""
+        """0 = RBC (default), 1 = neo-Hookean capsule / 2 = semi-rigid particle whose rest configuration is rest_mesh [nv][3]."""
         self._rest = None if rest_mesh is None else np.ascontiguousarray(rest_mesh, dtype=np.float64)
         self.lib.orc_set_particle_model(C.c_int(ptype), None if self._rest is None else _d(self._rest))
 

@@ -168,6 +168,20 @@ def test_pipe_wall_and_particle_interactions_vs_golden(rbc):
     assert np.array_equal(got[..., 22], g["pop_final_sample"][..., 22])
 
 
+def test_semirigid_particle_vs_golden(rbc):
+    """SemiRigidParticle3D (the platelets of rbc_in_pipe): bit-identical to the reference with the deterministic spread."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_semirigid.npz")
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]), {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, g["sparams"], g["vert_init"][..., :3], kind=bib.PARTICLE_SEMIRIGID)
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step(g["body"])
+        assert np.array_equal(lat.vertices().reshape(1, -1, 9), g[f"vert_{s}"]), f"vertices differ at step {s}"
+        assert np.array_equal(lat.particle_scalars(), g[f"part_{s}"])
+    assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
+
+
 def test_guo_pipe_wall_vs_golden():
     """GuoRigidWallBoundary (off-lattice pipe wall) + NoDynamics outside, LBM only: bit-identical to the reference."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")

@@ -228,6 +228,22 @@ def test_pipe_wall_and_particle_interactions_bit_exact(orc, rbc):
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_semirigid_particle_bit_exact(orc, rbc):
+    """SemiRigidParticle3D (platelets): radial + link springs, 4 coupled steps."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_semirigid.npz")
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    orc.set_particle_model(2, shape.verts)
+    try:
+        for s in range(1, int(g["steps"]) + 1):
+            orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], shape, g["sparams"], vert, state)
+            assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"]), f"step {s}"
+    finally:
+        orc.reset_modes()
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+    assert np.abs(vert[..., 6:]).max() > 1e-5
+
+
 def test_guo_pipe_wall_bit_exact(orc):
     """GuoRigidWallBoundary on a pipe + NoDynamics outside (rbc_in_pipe.cpp:285-343), LBM only: the wall-node list and 6 steps."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
