@@ -274,6 +274,12 @@ int bib_ib_set_wall_interaction(bib_domain* d, int type, double r_min, double be
     BIB_ENTER(d);
     return set_potential(d->wall_pot, type, r_min, beta, strength, "set_wall_interaction");
 }
+int bib_ib_set_wall_interaction_boundary(bib_domain* d, int kind, double p0, double p1, double p2) {
+    BIB_ENTER(d);
+    if (kind < -1 || kind > 2) { bib_set_error("set_wall_interaction_boundary: kind must be -1 (boundary of set_boundary), 0, 1 (plates y0,y1) or 2 (pipe y0,z0,radius)"); return 0; }
+    d->wall_bkind = kind; d->wall_b[0] = p0; d->wall_b[1] = p1; d->wall_b[2] = p2;
+    return 1;
+}
 int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta, double strength) {
     BIB_ENTER(d);
     return set_potential(d->pp_pot, type, r_min, beta, strength, "set_pp_interaction");

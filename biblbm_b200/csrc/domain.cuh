@@ -106,6 +106,7 @@ struct bib_domain {
     int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),
     double pipe_radius = 0;                                 //   2 PipeBoundary (axis y = plate_y0, z = plate_y1, radius)
     PotentialDev wall_pot, pp_pot;                          // WallInteraction decorator / PPPotentialForce
+    int wall_bkind = -1; double wall_b[3] = {0, 0, 0};      // boundary the WallInteraction refers to (-1: the one of set_boundary)
     int* pp_head = nullptr; int* pp_next = nullptr; int* pp_vobj = nullptr; long long pp_cap = 0; int pp_groups = 0;
     // multi-GPU ring
     int rank = 0, n_ranks = 1;

@@ -1635,10 +1635,12 @@ static int ib_pp_forces(bib_domain* d) {
 int ib_forces_and_spread(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
     d->interp_since_spread = false;
-    const bool wall = d->wall_pot.type != 0 && d->plates != 0;
+    Geo wg = make_geo(d);
+    if (d->wall_bkind >= 0) { wg.plates = d->wall_bkind; wg.py0 = d->wall_b[0]; wg.py1 = d->wall_b[1]; wg.prad = d->wall_b[2]; }
+    const bool wall = d->wall_pot.type != 0 && wg.plates != 0;
     if (wall) {
         if (d->n_ranks > 1) { bib_set_error("wall interaction forces: single-slab domains only (round 1)"); return 0; }
-        k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, d->stream>>>(make_geo(d), d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+        k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, d->stream>>>(wg, d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
         d->launches++;
     }
     for (const ParticleGroup& gr : d->groups) {

@@ -117,6 +117,10 @@ enum { BIB_POTENTIAL_NONE = 0, BIB_POTENTIAL_MORSE = 1 /* (r_min, beta, strength
 /* fsi.add_force_decorator(new WallInteraction<T, Potential>(boundary, potential)) (src/fsi/ForceDecorator.hh:25-33): every vertex closer
  * than r_min to the boundary set above gets f -= potential(dist) * normal, before the membrane forces are added. */
 int bib_ib_set_wall_interaction(bib_domain* d, int type, double r_min, double beta, double strength);
+/* The WallInteraction decorator carries its own Boundary reference, independent of fsi.set_boundary() (rbc_in_pipe uses the wall
+ * force WITHOUT the near-wall kernel blending): kind -1 = the boundary of bib_ib_set_parallel_plates / bib_ib_set_pipe (default),
+ * 1 = plates (p0 = y0, p1 = y1), 2 = pipe (p0 = y0, p1 = z0, p2 = radius). */
+int bib_ib_set_wall_interaction_boundary(bib_domain* d, int kind, double p0, double p1, double p2);
 /* fsi.add_pp_force(new PPPotentialForce<T, Potential>(potential)) (src/fsi/ParticleParticleInteraction.h:28-44): short-range repulsion
  * between vertices of DIFFERENT particles, evaluated over the reference's collision grid (src/fsi/CollisionForces.h:62-217; r_min <= 1). */
 int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta, double strength);

@@ -56,6 +56,8 @@ struct Twin {
     Block* block;
     bib_domain* d;
     int nx, ny, nz, env;
+    plint ox, oy, oz;           // origin of the lattice's bounding box (rbc_in_pipe centres its pipe at y = z = 0): device index = global - origin
+    plint ex, ey, ez;           // global index - this = index inside the atomic block (block location incl. envelope)
     bool device_valid;          // the device holds the current populations / externals
     bool host_valid;            // the host lattice holds the current populations / externals
     VelocityField* velocity;    // the driver's velocity field (bound by computeVelocity)
@@ -68,7 +70,7 @@ struct Twin {
     bool velocity_host_modified;// host code wrote to the velocity field after computeVelocity (e.g. CouetteVelocityExtrapolator)
     ParticleClient* particles;  // IB binding attached to this twin (or 0)
     long long steps;
-    Twin() : lattice(0), lattice_id(0), block_id(0), block(0), d(0), nx(0), ny(0), nz(0), env(0), device_valid(false), host_valid(true),
+    Twin() : lattice(0), lattice_id(0), block_id(0), block(0), d(0), nx(0), ny(0), nz(0), env(0), ox(0), oy(0), oz(0), ex(0), ey(0), ez(0), device_valid(false), host_valid(true),
              velocity(0), velocity_id(0), velocity_pending(false), velocity_host_valid(true), velocity_evaluable(false),
              interpolated(false), velocity_host_modified(false), particles(0), steps(0) { }
 };
@@ -85,6 +87,7 @@ void release(Lattice& lattice);                  // drop the twin (device memory
 int& hooks_suspended();
 struct SuspendHooks { SuspendHooks() { ++hooks_suspended(); } ~SuspendHooks() { --hooks_suspended(); } };
 void interpolate_if_pending(Twin& t);
+void register_guo_wall(const Lattice& lattice, void* guo_boundary);
 
 }  // namespace bibglue
 
@@ -102,6 +105,9 @@ void computeVelocity(bibglue::Lattice& lattice, bibglue::VelocityField& velocity
 void setExternalVector(bibglue::Lattice& lattice, Box3D domain, int vectorStartsAt, Array<double, 3> externalVector);
 
 namespace fsi {
+
+// GuoRigidWallBoundary::insert() (src/fsi/GuoBoundaryCondition.hh:25-29) additionally announces the wall-node list to the binding
+template<> void GuoRigidWallBoundary<double, descriptors::ForcedPhaseD3Q19Descriptor>::insert();
 
 // tagged periodicity: same arithmetic, distinct type, so that ImmersedBoundaryDynamics3D<..., BibHostPeriodicity<P>> is the
 // reference's unmodified primary template (used as the host mirror) while <..., P> is the binding below

@@ -25,7 +25,13 @@ inline bool env_flag(const char* name) { const char* v = std::getenv(name); retu
 inline void box_to_int6(const Box3D& b, int out[6]) {
     out[0] = (int)b.x0; out[1] = (int)b.x1; out[2] = (int)b.y0; out[3] = (int)b.y1; out[4] = (int)b.z0; out[5] = (int)b.z1;
 }
-inline Box3D full_box(const Twin& t) { return Box3D(0, t.nx - 1, 0, t.ny - 1, 0, t.nz - 1); }
+inline Box3D full_box(const Twin& t) { return Box3D(0, t.nx - 1, 0, t.ny - 1, 0, t.nz - 1); }      // device index space
+inline Box3D to_device_box(const Twin& t, const Box3D& global) { return global.shift(-t.ox, -t.oy, -t.oz); }
+inline Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& host_cell(const Twin& t, plint x, plint y, plint z) {   // device index -> host cell
+    return t.block->get(x + t.ox - t.ex, y + t.oy - t.ey, z + t.oz - t.ez);
+}
+inline std::map<const void*, void*>& guo_walls() { static std::map<const void*, void*> m; return m; }
+inline void register_guo_wall(const Lattice& lattice, void* guo_boundary) { guo_walls()[&lattice] = guo_boundary; }
 
 inline void destroy_twin(Twin* t) {
     if (t->particles) t->particles->on_twin_destroyed();
@@ -80,11 +86,10 @@ inline void read_omegas(const Dynamics<double, descriptors::ForcedPhaseD3Q19Desc
 }
 
 inline void upload_state(Twin& t) {
-    const plint e = t.env;
     std::vector<double> cells((size_t)t.nx * t.ny * t.nz * 23);
     size_t k = 0;
     for (plint x = 0; x < t.nx; ++x) for (plint y = 0; y < t.ny; ++y) for (plint z = 0; z < t.nz; ++z) {
-        Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = t.block->get(x + e, y + e, z + e);
+        Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = host_cell(t, x, y, z);
         for (int i = 0; i < 19; ++i) cells[k++] = c[i];
         for (int i = 0; i < 4; ++i) cells[k++] = *c.getExternal(i);
     }
@@ -95,7 +100,6 @@ inline void upload_state(Twin& t) {
 }
 
 inline void configure_dynamics(Twin& t) {
-    const plint e = t.env;
     std::map<int, int> kind_of_id;                 // Dynamics::getId() -> kind
     Box3D wall_box[6]; long long wall_cells[6] = {0, 0, 0, 0, 0, 0};
     int box[6];
@@ -104,7 +108,7 @@ inline void configure_dynamics(Twin& t) {
         for (plint z = 0; z <= t.nz; ++z) {
             int kind = BIB_CELL_BULK;
             if (z < t.nz) {
-                const Dynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>& dyn = t.block->get(x + e, y + e, z + e).getDynamics();
+                const Dynamics<double, descriptors::ForcedPhaseD3Q19Descriptor>& dyn = host_cell(t, x, y, z).getDynamics();
                 std::map<int, int>::iterator it = kind_of_id.find(dyn.getId());
                 if (it == kind_of_id.end()) {
                     kind = classify_dynamics(dyn);
@@ -147,13 +151,29 @@ inline void configure_dynamics(Twin& t) {
         std::vector<double> vel((size_t)b.nCells() * 3);
         size_t k = 0;
         for (plint x = b.x0; x <= b.x1; ++x) for (plint y = b.y0; y <= b.y1; ++y) for (plint z = b.z0; z <= b.z1; ++z) {
-            Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = t.block->get(x + e, y + e, z + e);
+            Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = host_cell(t, x, y, z);
             Array<double, 3> u;
             c.getDynamics().computeVelocity(c, u);          // StoreVelocityDynamics: the stored boundary velocity
             vel[k++] = u[0]; vel[k++] = u[1]; vel[k++] = u[2];
         }
         BIBGLUE_OK(bib_set_boundary_velocity(t.d, box, &vel[0]));
     }
+}
+
+// Guo off-lattice wall nodes announced by GuoRigidWallBoundary::insert() (see the specialisation below)
+inline void configure_guo_wall(Twin& t) {
+    std::map<const void*, void*>::iterator it = guo_walls().find(t.lattice);
+    if (it == guo_walls().end()) return;
+    typedef fsi::GuoRigidWallBoundary<double, descriptors::ForcedPhaseD3Q19Descriptor> Guo;
+    Guo* guo = static_cast<Guo*>(it->second);
+    std::vector<int> ld; std::vector<double> delta, vel;
+    for (Guo::iterator n = guo->begin(); n != guo->end(); ++n) {
+        ld.push_back((int)(n->location.x - t.ox)); ld.push_back((int)(n->location.y - t.oy)); ld.push_back((int)(n->location.z - t.oz));
+        ld.push_back((int)n->direction.x); ld.push_back((int)n->direction.y); ld.push_back((int)n->direction.z);
+        delta.push_back(n->delta);
+        for (int c = 0; c < 3; ++c) vel.push_back(n->velocity[c]);
+    }
+    if (!delta.empty()) BIBGLUE_OK(bib_set_guo_wall_nodes(t.d, (int)delta.size(), &ld[0], &delta[0], &vel[0]));
 }
 
 inline Twin* create_twin(Lattice& lattice) {
@@ -168,7 +188,9 @@ inline Twin* create_twin(Lattice& lattice) {
     t->block = lattice.getBlockLattices().find(t->block_id)->second;
     t->env = (int)management.getEnvelopeWidth();
     const Box3D bb = lattice.getBoundingBox();
-    if (bb.x0 != 0 || bb.y0 != 0 || bb.z0 != 0) die("lattice bounding box must start at the origin");
+    t->ox = bb.x0; t->oy = bb.y0; t->oz = bb.z0;
+    const Dot3D loc = t->block->getLocation();
+    t->ex = loc.x; t->ey = loc.y; t->ez = loc.z;
     t->nx = (int)bb.getNx(); t->ny = (int)bb.getNy(); t->nz = (int)bb.getNz();
     double omega = 1., omega_inner = 1.;
     read_omegas(lattice.getBackgroundDynamics(), omega, omega_inner);
@@ -177,6 +199,7 @@ inline Twin* create_twin(Lattice& lattice) {
     if (!bib_domain_create(t->nx, t->ny, t->nz, 4, omega, omega_inner, per, dev ? std::atoi(dev) : 0, &t->d)) { delete t; die("bib_domain_create"); }
     if (env_flag("BIB_DETERMINISTIC_SPREAD")) BIBGLUE_OK(bib_domain_set_option(t->d, BIB_OPT_DETERMINISTIC_SPREAD, 1.0));
     configure_dynamics(*t);
+    configure_guo_wall(*t);
     upload_state(*t);
     t->host_valid = true;
     twins()[&lattice] = t;
@@ -197,10 +220,9 @@ inline void sync_to_host(Twin& t) {
     std::vector<double> cells((size_t)t.nx * t.ny * t.nz * 23);
     int box[6]; box_to_int6(full_box(t), box);
     BIBGLUE_OK(bib_domain_download(t.d, box, &cells[0]));
-    const plint e = t.env;
     size_t k = 0;
     for (plint x = 0; x < t.nx; ++x) for (plint y = 0; y < t.ny; ++y) for (plint z = 0; z < t.nz; ++z) {
-        Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = t.block->get(x + e, y + e, z + e);
+        Cell<double, descriptors::ForcedPhaseD3Q19Descriptor>& c = host_cell(t, x, y, z);
         for (int i = 0; i < 19; ++i) c[i] = cells[k++];
         for (int i = 0; i < 4; ++i) *c.getExternal(i) = cells[k++];
     }
@@ -214,9 +236,9 @@ inline void velocity_to_host(Twin& t) {
     if (!t.velocity_evaluable)
         die("the velocity field was read on the host after the force field or the populations changed; "
             "read it between computeVelocity and setExternalVector (as the reference drivers do) or set BIB_EAGER_VELOCITY=1");
-    int box[6]; box_to_int6(t.velocity_domain, box);
+    const Box3D b = to_device_box(t, t.velocity_domain);
+    int box[6]; box_to_int6(b, box);
     if (!env_flag("BIB_EAGER_VELOCITY")) BIBGLUE_OK(bib_compute_velocity(t.d, box));
-    const Box3D& b = t.velocity_domain;
     std::vector<double> vel((size_t)b.nCells() * 3);
     BIBGLUE_OK(bib_velocity_download(t.d, box, &vel[0]));
     SuspendHooks guard;
@@ -224,7 +246,7 @@ inline void velocity_to_host(Twin& t) {
     const Dot3D loc = vb.getLocation();
     size_t k = 0;
     for (plint x = b.x0; x <= b.x1; ++x) for (plint y = b.y0; y <= b.y1; ++y) for (plint z = b.z0; z <= b.z1; ++z) {
-        Array<double, 3>& u = vb.get(x - loc.x, y - loc.y, z - loc.z);
+        Array<double, 3>& u = vb.get(x + t.ox - loc.x, y + t.oy - loc.y, z + t.oz - loc.z);
         u[0] = vel[k++]; u[1] = vel[k++]; u[2] = vel[k++];
     }
     t.velocity_host_valid = true;
@@ -240,7 +262,7 @@ inline void velocity_to_device(Twin& t) {
     const Dot3D loc = vb.getLocation();
     size_t k = 0;
     for (plint x = b.x0; x <= b.x1; ++x) for (plint y = b.y0; y <= b.y1; ++y) for (plint z = b.z0; z <= b.z1; ++z) {
-        const Array<double, 3>& u = vb.get(x - loc.x, y - loc.y, z - loc.z);
+        const Array<double, 3>& u = vb.get(x + t.ox - loc.x, y + t.oy - loc.y, z + t.oz - loc.z);
         vel[k++] = u[0]; vel[k++] = u[1]; vel[k++] = u[2];
     }
     int box[6]; box_to_int6(b, box);
@@ -341,7 +363,7 @@ inline void computeVelocity(bibglue::Lattice& lattice, bibglue::VelocityField& v
     t.velocity_pending = true; t.velocity_host_valid = false; t.velocity_evaluable = true; t.interpolated = false;
     t.velocity_host_modified = false;
     if (bibglue::env_flag("BIB_EAGER_VELOCITY")) {      // dense pass like the reference; default: band-limited, on demand
-        int box[6]; bibglue::box_to_int6(domain, box);
+        int box[6]; bibglue::box_to_int6(bibglue::to_device_box(t, domain), box);
         BIBGLUE_OK(bib_compute_velocity(t.d, box));
     }
 }
@@ -355,13 +377,21 @@ inline void setExternalVector(bibglue::Lattice& lattice, Box3D domain, int vecto
         return;
     }
     bibglue::interpolate_if_pending(*t);       // the IB sees u = j/rho + F/2 with the force field as it is BEFORE this reset
-    int box[6]; bibglue::box_to_int6(domain, box);
+    int box[6]; bibglue::box_to_int6(bibglue::to_device_box(*t, domain), box);
     BIBGLUE_OK(bib_set_external_vector(t->d, box, externalVector[0], externalVector[1], externalVector[2]));
     t->host_valid = false; t->velocity_evaluable = false;
 }
 
 // ================================================================================================ (3) immersed boundary
 namespace fsi {
+
+template<>
+inline void GuoRigidWallBoundary<double, descriptors::ForcedPhaseD3Q19Descriptor>::insert() {
+    // the reference's own body (the host lattice keeps its level-1 processor: lattice.initialize() runs it once at set-up) ...
+    integrateProcessingFunctional(new GuoRigidWallBoundaryFunctional<double, descriptors::ForcedPhaseD3Q19Descriptor>(*this), lattice_.getBoundingBox(), lattice_, 1);
+    // ... plus: the device twin applies the same wall-node list after every collideAndStream
+    bibglue::register_guo_wall(lattice_, this);
+}
 
 #define BIB_IBD_TEMPLATE template<bool pX, bool pY, bool pZ>
 #define BIB_IBD ImmersedBoundaryDynamics3D<double, descriptors::ForcedPhaseD3Q19Descriptor, Periodicity3D<double, pX, pY, pZ> >
@@ -374,9 +404,15 @@ BIB_IBD::ImmersedBoundaryDynamics3D(const bibglue::Lattice& lattice, const Parti
 BIB_IBD_TEMPLATE
 BIB_IBD::~ImmersedBoundaryDynamics3D() {
     if (twin_ && twin_->particles == this) {
-        // the device domain keeps this module's particles; a lattice that outlives its fsi module gets a fresh twin
-        bibglue::Twin* t = bibglue::find_twin(*lattice_);
-        if (t == twin_) { t->particles = 0; bibglue::release(*lattice_); }
+        // The device domain holds this module's particles: drop the twin (a lattice that outlives its fsi module gets a fresh one on
+        // its next device call). The lattice may already be gone (rbc_in_pipe deletes it first): it is only touched if still registered.
+        twin_->particles = 0;
+        std::map<const void*, bibglue::Twin*>::iterator it = bibglue::twins().find(lattice_);
+        if (it != bibglue::twins().end() && it->second == twin_) {
+            if (multiBlockRegistration3D().find(twin_->lattice_id)) bibglue::sync_to_host(*twin_);
+            bibglue::twins().erase(it);
+            bibglue::destroy_twin(twin_);
+        }
     }
 }
 
@@ -398,16 +434,25 @@ BIB_IBD_TEMPLATE void BIB_IBD::drop_device_particles() {
     if (uploaded_) bibglue::die("removing or reloading particles after they were moved to the device is not supported yet");
 }
 
+// the Boundary a WallInteraction decorator refers to (it need not be the one given to fsi.set_boundary)
+inline void set_wall_boundary(bibglue::Twin& t, const Boundary<double>* b) {
+    if (const ParallelPlatesBoundary<double>* plates = dynamic_cast<const ParallelPlatesBoundary<double>*>(b)) {
+        BIBGLUE_OK(bib_ib_set_wall_interaction_boundary(t.d, 1, plates->y0 - (double)t.oy, plates->y1 - (double)t.oy, 0.));
+    } else if (const PipeBoundary<double>* pipe = dynamic_cast<const PipeBoundary<double>*>(b)) {
+        BIBGLUE_OK(bib_ib_set_wall_interaction_boundary(t.d, 2, pipe->y0 - (double)t.oy, pipe->z0 - (double)t.oz, pipe->radius));
+    } else bibglue::die("WallInteraction: unsupported Boundary type");
+}
+
 BIB_IBD_TEMPLATE void BIB_IBD::configure_decorators_and_boundary(bibglue::Twin& t) {
     for (pluint i = 0; i < decorators_.size(); ++i) {
         ForceDecorator<T>* dec = decorators_[i];
         if (ParticlePositionRegulator<T>* r = dynamic_cast<ParticlePositionRegulator<T>*>(dec)) {
-            BIBGLUE_OK(bib_ib_set_regulator(t.d, r->p, r->position[0], r->position[1], r->position[2]));
+            BIBGLUE_OK(bib_ib_set_regulator(t.d, r->p, r->position[0] - (T)t.ox, r->position[1] - (T)t.oy, r->position[2] - (T)t.oz));
         } else if (WallInteraction<T, MorsePotential<T> >* w = dynamic_cast<WallInteraction<T, MorsePotential<T> >*>(dec)) {
-            if (w->boundary_ != boundary_) bibglue::die("WallInteraction must refer to the boundary passed to fsi.set_boundary()");
+            set_wall_boundary(t, w->boundary_);
             BIBGLUE_OK(bib_ib_set_wall_interaction(t.d, BIB_POTENTIAL_MORSE, w->interaction_.r_min, w->interaction_.beta, w->interaction_.strength));
         } else if (WallInteraction<T, SpringPotential<T> >* w2 = dynamic_cast<WallInteraction<T, SpringPotential<T> >*>(dec)) {
-            if (w2->boundary_ != boundary_) bibglue::die("WallInteraction must refer to the boundary passed to fsi.set_boundary()");
+            set_wall_boundary(t, w2->boundary_);
             BIBGLUE_OK(bib_ib_set_wall_interaction(t.d, BIB_POTENTIAL_SPRING, w2->interaction_.min_dist, 0., w2->interaction_.strength));
         } else {
             pcerr << "biblbm_b200 binding: unsupported ForceDecorator " << typeid(*dec).name() << std::endl;
@@ -427,9 +472,9 @@ BIB_IBD_TEMPLATE void BIB_IBD::configure_decorators_and_boundary(bibglue::Twin& 
     }
     if (boundary_) {
         if (ParallelPlatesBoundary<T>* plates = dynamic_cast<ParallelPlatesBoundary<T>*>(boundary_)) {
-            BIBGLUE_OK(bib_ib_set_parallel_plates(t.d, 1, plates->y0, plates->y1));
+            BIBGLUE_OK(bib_ib_set_parallel_plates(t.d, 1, plates->y0 - (T)t.oy, plates->y1 - (T)t.oy));
         } else if (PipeBoundary<T>* pipe = dynamic_cast<PipeBoundary<T>*>(boundary_)) {
-            BIBGLUE_OK(bib_ib_set_pipe(t.d, 1, pipe->y0, pipe->z0, pipe->radius));
+            BIBGLUE_OK(bib_ib_set_pipe(t.d, 1, pipe->y0 - (T)t.oy, pipe->z0 - (T)t.oz, pipe->radius));
         } else {
             pcerr << "biblbm_b200 binding: unsupported Boundary " << typeid(*boundary_).name() << std::endl;
             exit(-1);
@@ -439,6 +484,7 @@ BIB_IBD_TEMPLATE void BIB_IBD::configure_decorators_and_boundary(bibglue::Twin& 
 
 BIB_IBD_TEMPLATE void BIB_IBD::push() {
     bibglue::Twin& t = *twin_;
+    const T org[3] = { (T)t.ox, (T)t.oy, (T)t.oz };          // device coordinates = global - origin (exact no-op for origin 0)
     if (!uploaded_) {
         // particles in id order (std::map), consecutive particles with equal (type, shape, parameters) form one device group
         std::vector<double> positions;
@@ -458,6 +504,9 @@ BIB_IBD_TEMPLATE void BIB_IBD::push() {
                 } else if (DeformableCapsuleParticle<T>* cap = dynamic_cast<DeformableCapsuleParticle<T>*>(p)) {
                     type = BIB_PARTICLE_CAPSULE;
                     params[0] = cap->params().G; params[1] = cap->params().C; params[2] = cap->params().nu_s; params[3] = cap->params().kb;
+                } else if (SemiRigidParticle3D<T>* sr = dynamic_cast<SemiRigidParticle3D<T>*>(p)) {
+                    type = BIB_PARTICLE_SEMIRIGID;
+                    params[0] = sr->params().l0; params[1] = sr->params().k_in_plane; params[2] = sr->params().k_out_of_plane; params[3] = sr->params().k_bend;
                 } else {
                     pcerr << "biblbm_b200 binding: unsupported particle type " << typeid(*p).name() << std::endl;
                     exit(-1);
@@ -483,7 +532,7 @@ BIB_IBD_TEMPLATE void BIB_IBD::push() {
             if (end) break;
             cur_type = type; cur_shape = shape_id; std::memcpy(cur_params, params, sizeof(params)); ++cur_n;
             ParticleType* p = it->second;
-            for (plint i = 0; i < p->count_nodes(); ++i) for (int c = 0; c < 3; ++c) positions.push_back(p->get_node(i).pos[c]);
+            for (plint i = 0; i < p->count_nodes(); ++i) for (int c = 0; c < 3; ++c) positions.push_back(p->get_node(i).pos[c] - org[c]);
         }
         configure_decorators_and_boundary(t);
         uploaded_ = true;
@@ -495,7 +544,7 @@ BIB_IBD_TEMPLATE void BIB_IBD::push() {
             ParticleType* p = it->second;
             for (plint i = 0; i < p->count_nodes(); ++i) {
                 const Vertex<T>& n = p->get_node(i);
-                for (int c = 0; c < 3; ++c) v9.push_back(n.pos[c]);
+                for (int c = 0; c < 3; ++c) v9.push_back(n.pos[c] - org[c]);
                 for (int c = 0; c < 3; ++c) v9.push_back(n.vel[c]);
                 for (int c = 0; c < 3; ++c) v9.push_back(n.force[c]);
             }
@@ -508,8 +557,9 @@ BIB_IBD_TEMPLATE void BIB_IBD::push() {
         const ParticleType* p = it->second;
         const geo::Rect<T> bb = p->bounding_box();
         s11.push_back(p->area()); s11.push_back(p->volume());
-        for (int c = 0; c < 3; ++c) s11.push_back(p->center_of_mass()[c]);
-        s11.push_back(bb.x0); s11.push_back(bb.x1); s11.push_back(bb.y0); s11.push_back(bb.y1); s11.push_back(bb.z0); s11.push_back(bb.z1);
+        for (int c = 0; c < 3; ++c) s11.push_back(p->center_of_mass()[c] - org[c]);
+        s11.push_back(bb.x0 - org[0]); s11.push_back(bb.x1 - org[0]); s11.push_back(bb.y0 - org[1]); s11.push_back(bb.y1 - org[1]);
+        s11.push_back(bb.z0 - org[2]); s11.push_back(bb.z1 - org[2]);
     }
     if (!s11.empty()) BIBGLUE_OK(bib_ib_particle_scalars_upload(t.d, 0, (int)(s11.size() / 11), &s11[0]));
     host_modified_ = false; device_ahead_ = false;
@@ -521,12 +571,13 @@ BIB_IBD_TEMPLATE void BIB_IBD::pull() const {
     BIBGLUE_OK(bib_ib_count(twin_->d, &np, &nv));
     std::vector<double> v9((size_t)nv * 9);
     if (nv > 0) BIBGLUE_OK(bib_ib_vertices_download(twin_->d, 0, nv, &v9[0]));
+    const T org[3] = { (T)twin_->ox, (T)twin_->oy, (T)twin_->oz };
     size_t k = 0;
     for (ObjMapIterator it = host_.particles_begin(); it != host_.particles_end(); ++it) {
         ParticleType* p = it->second;
         for (plint i = 0; i < p->count_nodes(); ++i) {
             Vertex<T>& n = p->get_node(i);
-            for (int c = 0; c < 3; ++c) n.pos[c] = v9[k++];
+            for (int c = 0; c < 3; ++c) n.pos[c] = v9[k++] + org[c];
             for (int c = 0; c < 3; ++c) n.vel[c] = v9[k++];
             for (int c = 0; c < 3; ++c) n.force[c] = v9[k++];
         }
@@ -571,7 +622,7 @@ void bib_apply_ib(ImmersedBoundaryWrapperFunctional3D<double, descriptors::Force
     bibglue::Block& block = *t.block;
     bibglue::VelocityBlock& vb = velocity.getComponent(t.block_id);
     const Dot3D loc = block.getLocation();
-    functional->process(domain.shift(-loc.x, -loc.y, -loc.z), block, vb);    // -> the three methods above
+    functional->process(domain.shift(-loc.x, -loc.y, -loc.z), block, vb);    // global -> block-local box, like the multi-block machinery; -> the three methods above
     delete functional;
 }
 

@@ -42,11 +42,13 @@ patch_params() {  # patch_params <driver.cpp> <out.cpp>
     -e 's|^(\s*)plint Nt = std::ceil\(20 / gamma_lb\);|\1plint Nt = getenv("BIB_NT") ? atol(getenv("BIB_NT")) : (plint) std::ceil(20 / gamma_lb);|' \
     -e 's|^(\s*)plint output_interval = std::ceil\(1 /gamma_lb / 20\);|\1plint output_interval = getenv("BIB_OUTPUT_INTERVAL") ? atol(getenv("BIB_OUTPUT_INTERVAL")) : (plint) std::ceil(1 /gamma_lb / 20);|' \
     -e 's|get_volume\(\), 10000\);|get_volume(), getenv("BIB_SHRINK_ITERS") ? atol(getenv("BIB_SHRINK_ITERS")) : 10000);|' \
+    -e 's|get_volume\(\), 100000\);|get_volume(), getenv("BIB_SHRINK_ITERS") ? atol(getenv("BIB_SHRINK_ITERS")) : 100000);|' \
+    -e 's|^(\s*)plint Nit = 40000;|\1plint Nit = getenv("BIB_GROW_ITERS") ? atol(getenv("BIB_GROW_ITERS")) : 40000;|' \
     -e 's|shrink_volume\(0.59, 40000\)|shrink_volume(0.59, getenv("BIB_SHRINK_ITERS") ? atol(getenv("BIB_SHRINK_ITERS")) : 40000)|' \
     "$1" > "$2"
 }
 
-DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear}"
+DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe}"
 for drv in $DRIVERS; do
   dir="$REF/progs/$drv"
   src="$(ls "$dir"/*.cpp | head -1)"

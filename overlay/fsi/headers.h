@@ -24,6 +24,7 @@
 #define private public
 #define protected public
 #include_next "fsi/headers.h"
+#include "fsi/GuoBoundaryCondition.h"      // not part of fsi/headers.h; rbc_in_pipe includes it itself (include-guarded)
 #undef private
 #undef protected
 #include "biblbm_overlay/decl.h"

@@ -5,6 +5,7 @@
 #define private public
 #define protected public
 #include_next "fsi/headers.hh"
+#include "fsi/GuoBoundaryCondition.hh"
 #undef private
 #undef protected
 #include "biblbm_overlay/impl.hh"

@@ -283,6 +283,7 @@ if __name__ == "__main__":
     assert kit.have_reference(), "build the reference first: oracle/build_ref.sh"
     make_rbc_fixture()
     make_mesh_fixture("/root/reference/progs/capsule_in_shear/sphere_r6_TRImesh_1046n_2088el.msh", "sphere1046.npz")
+    make_mesh_fixture("/root/reference/progs/rbc_in_pipe/sphere_2_2_2_TRImesh_54n_104el.msh", "platelet54.npz")
     make_lbm("lbm_periodic.npz", "ppp")
     make_lbm("lbm_walls.npz", "pfp")
     make_ib("ib_rbc1.npz", (24, 22, 20), "ppp", [(11.3, 10.1, 9.7)], steps=5, seed=1, regulator_p=1e-2)

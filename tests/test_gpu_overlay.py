@@ -35,6 +35,23 @@ def all_files(root):
     return sorted(str(p.relative_to(root)) for p in pathlib.Path(root).rglob("*") if p.is_file())
 
 
+def same_file(a, b):
+    """Byte equality, except for Palabos' XML block descriptions (*.plb): their <DynamicsDict> maps dynamics NAMES to the numeric
+    ids the writing binary happened to assign at static-initialisation time (src/core/dynamicsIdentifiers.h), which differ between
+    any two executables; names and everything else must still agree."""
+    if filecmp.cmp(a, b, shallow=False):
+        return True
+    if not str(a).endswith(".plb"):
+        return False
+    try:
+        ta, tb = a.read_text(), b.read_text()
+    except UnicodeDecodeError:
+        return False
+    def norm(t):
+        return re.sub(r"(<DynamicsDict>)(.*?)(</DynamicsDict>)", lambda m: m.group(1) + re.sub(r"> \d+ <", "> # <", m.group(2)) + m.group(3), t, flags=re.S)
+    return "<DynamicsDict>" in ta and norm(ta) == norm(tb)
+
+
 def numbers(text):
     return np.array([float(x) for x in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", text)])
 
@@ -66,7 +83,7 @@ def test_rbc_in_shear_driver_bit_identical(tmp_path, mesh):
     files = all_files(d_cpu)
     assert files == all_files(d_gpu) and len(files) >= 8
     for f in files:
-        assert filecmp.cmp(d_cpu / f, d_gpu / f, shallow=False), f"{f} differs"
+        assert same_file(d_cpu / f, d_gpu / f), f"{f} differs"
 
 
 def test_rbc_in_shear_driver_atomic_spread(tmp_path, mesh):
@@ -100,7 +117,7 @@ def _compare_runs(tmp_path, driver, env, args=(), meshes=(), min_files=4):
     for f in files:
         if f.endswith(".msh") or "profile" in f:      # inputs; wall-clock timer report
             continue
-        assert filecmp.cmp(d_cpu / f, d_gpu / f, shallow=False), f"{f} differs"
+        assert same_file(d_cpu / f, d_gpu / f), f"{f} differs"
     return files
 
 
@@ -117,3 +134,71 @@ def test_rbcs_in_shear_driver_bit_identical(tmp_path):
     shape, _, _, _ = kit.load_rbc_fixture()
     _compare_runs(tmp_path, "rbcs_in_shear", dict(BIB_NT="20", BIB_OUTPUT_INTERVAL="10", BIB_SHRINK_ITERS="2000"),
                   meshes=[("sphere_TRImesh_626n_1248el.msh", (shape.verts, shape.tris))])
+
+
+PIPE_XML = """<?xml version="1.0" ?>
+<geometry><diameter>30</diameter><length>24</length></geometry>
+<physics><Re_d>1</Re_d></physics>
+<particles>
+  <rbc><mesh>sphere_TRImesh_626n_1248el.msh</mesh><concentration>0.12</concentration><poisson_ratio>0.995</poisson_ratio>
+       <Xi_b>0.006</Xi_b><lambda>1</lambda><Ca>0.1</Ca></rbc>
+  <platelet><mesh>sphere_2_2_2_TRImesh_54n_104el.msh</mesh><Ca>0.01</Ca><concentration>0.004</concentration></platelet>
+  <wall_interaction><type>morse</type><r_min>2</r_min><beta>2</beta><strength>1e-4</strength></wall_interaction>
+  <particle_interaction><type>morse</type><r_min>1</r_min><beta>1</beta><strength>1e-3</strength></particle_interaction>
+</particles>
+<numerics><max_iterations>40</max_iterations><tau>0.55</tau></numerics>
+<checkpoints><folder>chk</folder><start_from_checkpoint>false</start_from_checkpoint><write_interval>40</write_interval></checkpoints>
+<output><folder>out</folder><flow_vtk_interval>20</flow_vtk_interval><particle_vtk_interval>20</particle_vtk_interval>
+        <particle_lw_interval>10</particle_lw_interval></output>
+"""
+
+
+def test_rbc_in_pipe_driver(tmp_path):
+    """progs/rbc_in_pipe (BASELINE.json configs[2]) with its own input format, reduced to a 30-diameter pipe: RBCs + platelets
+    (SemiRigidParticle3D) packed by the driver's own host-side growth procedure, Guo off-lattice wall, NoDynamics outside, pipe
+    centred at y = z = 0 (negative lattice coordinates, envelope width 2), Morse wall and particle-particle forces. Morse exp() and
+    the particle-particle summation order differ from the host in the last bits, so outputs are compared numerically:
+    particle data 1e-9, fields 1e-9 absolute (|u| ~ 1e-3)."""
+    import base64
+    _need(B200 / "rbc_in_pipe_short_b200", CPU / "rbc_in_pipe_short_cpu")
+    shape, _, _, _ = kit.load_rbc_fixture()
+    plt = np.load(kit.GOLDEN / "platelet54.npz")
+    env = dict(BIB_SHRINK_ITERS="2000", BIB_GROW_ITERS="2000")
+    dirs = {}
+    for name, exe, extra in (("cpu", CPU / "rbc_in_pipe_short_cpu", {}), ("gpu", B200 / "rbc_in_pipe_short_b200", {"BIB_DETERMINISTIC_SPREAD": "1"})):
+        d = tmp_path / name
+        d.mkdir()
+        kit.write_gmsh(d / "sphere_TRImesh_626n_1248el.msh", shape.verts, shape.tris)
+        kit.write_gmsh(d / "sphere_2_2_2_TRImesh_54n_104el.msh", plt["verts"], plt["tris"])
+        (d / "input.xml").write_text(PIPE_XML)
+        run_driver(exe, d, dict(env, **extra), args=("input.xml",))
+        dirs[name] = d
+    files = [f for f in all_files(dirs["cpu"] / "out")]
+    assert files == all_files(dirs["gpu"] / "out") and len(files) >= 20
+    checked = 0
+    for f in files:
+        a, b = dirs["cpu"] / "out" / f, dirs["gpu"] / "out" / f
+        if "objsP" in f:
+            x, y = numbers(a.read_text()), numbers(b.read_text())
+            assert x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x))), f
+            checked += 1
+        elif f.endswith("checkpoint_lbm.dat"):
+            x, y = np.fromfile(a), np.fromfile(b)
+            assert x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9, f
+            checked += 1
+        elif f.endswith("checkpoint_fsi/0.plb"):
+            assert a.stat().st_size == b.stat().st_size
+        elif f.endswith(".vti"):
+            def arrays(path):
+                out = {}
+                for m in re.finditer(r'<DataArray type="(\w+)" Name="(\w+)"[^>]*>\n([^<]*)\n</DataArray>', path.read_text()):
+                    raw = m.group(3).strip()
+                    n = np.frombuffer(base64.b64decode(raw[:8]), dtype=np.uint32)[0]
+                    out[m.group(2)] = np.frombuffer(base64.b64decode(raw[8:])[:n], dtype=np.float32)
+                return out
+            xa, ya = arrays(a), arrays(b)
+            assert set(xa) == set(ya) and "velocity" in xa
+            for k in xa:
+                assert xa[k].shape == ya[k].shape and np.max(np.abs(xa[k] - ya[k])) <= 1e-7, (f, k)
+            checked += 1
+    assert checked >= 8
