@@ -135,6 +135,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_ENVELOPE_SWAP: d->envelope_swap = value != 0.0; return 1;
         case BIB_OPT_DETERMINISTIC_SPREAD: d->deterministic_spread = value != 0.0; return 1;
         case BIB_OPT_REGULATOR: d->regulator_p = value; return 1;
+        case BIB_OPT_SPREAD_MODE: d->spread_mode = value != 0.0 ? 1 : 0; return 1;
     }
     bib_set_error("set_option: unknown key");
     return 0;

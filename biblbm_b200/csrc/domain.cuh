@@ -102,6 +102,7 @@ struct bib_domain {
     // options
     int envelope_swap = 1;
     int deterministic_spread = 0;
+    int spread_mode = 0;                  // 0 shared-memory tile staging (default), 1 one global atomic per stencil point
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
     int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),
     double pipe_radius = 0;                                 //   2 PipeBoundary (axis y = plate_y0, z = plate_y1, radius)

@@ -1243,6 +1243,118 @@ __global__ void __launch_bounds__(256) k_band_reset(Geo g, double* force, const 
     }
 }
 
+// Production spread (north-star: shared-memory tile staging): one CTA per particle. The particle's vertex forces are first
+// accumulated into a shared-memory tile covering its bounding box + 2 cells (the box k_band_velocity uses; a deflated RBC
+// touches ~1.6k cells, every one of them ~30 times), then each touched cell is added to the lattice force field ONCE with a
+// global fp64 reduction: 81 global atomics per vertex become ~8.
+// sm_100 has no native 64-bit shared-memory atomic add (fp64 and u64 both compile to ATOMS.CAST.SPIN loops, and a returning
+// atomic per stencil point makes the kernel latency-bound), so the tile accumulates in FIXED POINT spread over three 32-bit
+// limbs of 22 + 22 + 18 bits, each updated with a fire-and-forget native ATOMS.ADD; the limbs are summed independently (no
+// carries: |limb| < 2^21, at most 2^9 contributions per cell) and recombined in 64-bit integer arithmetic at flush time.
+// Integer addition commutes, so the per-particle sums do not depend on the order (deterministic). The scale is a power of
+// two chosen per particle from its largest force component (one unit = 2^-52 of it, i.e. fp64 resolution), so converting
+// back is exact.
+// Cells are addressed unwrapped inside the tile; periodic wrap, walls and slab ownership are applied at flush time
+// (d_band_cell), which is exactly where the reference's general kernel drops or wraps them. Boxes larger than the tile, or
+// stencil points outside it, fall back to direct global atomics.
+#define TILE_CELLS 2048
+__device__ __forceinline__ void d_tile_add(int* limb0, int* limb1, int* limb2, long long q) {
+    const long long b0 = ((q + (1LL << 21)) & ((1LL << 22) - 1)) - (1LL << 21);
+    const long long q1 = (q - b0) >> 22;
+    const long long b1 = ((q1 + (1LL << 21)) & ((1LL << 22) - 1)) - (1LL << 21);
+    const long long b2 = (q1 - b1) >> 22;
+    atomicAdd(limb0, (int)b0);
+    if (b1) atomicAdd(limb1, (int)b1);
+    if (b2) atomicAdd(limb2, (int)b2);
+}
+__device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int total, int* s_limb, double scale, double* force,
+                                            const double* p, bool th, const double* F) {
+    const int sup = th ? 2 : 3;
+    const double hs = th ? 1.0 : 1.5;
+    const int x0 = (int)ceil(p[0] - hs), y0 = (int)ceil(p[1] - hs), z0 = (int)ceil(p[2] - hs);
+    for (int i = x0; i <= x0 + sup - 1; ++i) {
+        const double wx = th ? d_tophat((double)i - p[0]) : d_roma((double)i - p[0]);
+        const int tx = i - 1 - b.lo[0];
+        for (int j = y0; j <= y0 + sup - 1; ++j) {
+            const double wxy = wx * (th ? d_tophat((double)j - p[1]) : d_roma((double)j - p[1]));
+            const int ty = j - 1 - b.lo[1];
+            for (int k = z0; k <= z0 + sup - 1; ++k) {
+                const double w = wxy * (th ? d_tophat((double)k - p[2]) : d_roma((double)k - p[2]));
+                const int tz = k - 1 - b.lo[2];
+                if (tx >= 0 && tx < b.n[0] && ty >= 0 && ty < b.n[1] && tz >= 0 && tz < b.n[2]) {
+                    const int t = (tx * b.n[1] + ty) * b.n[2] + tz;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d_tile_add(&s_limb[c * total + t], &s_limb[(3 + c) * total + t], &s_limb[(6 + c) * total + t], __double2ll_rn((w * F[c]) * scale));
+                } else {
+                    const int i2 = d_remap(g, 0, i), j2 = d_remap(g, 1, j), k2 = d_remap(g, 2, k);
+                    if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2) || j2 < 0 || j2 > g.ny - 1 || k2 < 0 || k2 > g.nz - 1) continue;
+                    const long long c0 = d_cell(g, i2, j2, k2);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(force + c * g.vol + c0, w * F[c]);
+                }
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const double* __restrict__ pstate, const double* __restrict__ vpos,
+                                                     const double* __restrict__ vfrc, long long cap, int nv, long long first_vertex, int first_particle) {
+    extern __shared__ int s_tile[];
+    __shared__ double s_max[8];
+    const int p = first_particle + blockIdx.x;
+    if (g.role && g.role[p] == 0) return;
+    const Band b = d_band(pstate + (long long)p * 11, 2);
+    const long long total_ll = (long long)b.n[0] * b.n[1] * b.n[2];
+    const long long base = first_vertex + (long long)blockIdx.x * nv;
+    // largest force component of the particle -> power-of-two fixed-point scale
+    double m = 0.0;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x)
+        m = fmax(m, fmax(fabs(vfrc[base + v]), fmax(fabs(vfrc[cap + base + v]), fabs(vfrc[2 * cap + base + v]))));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, s_max[w]);
+    if (m == 0.0) return;                                       // nothing to spread (uniform across the CTA)
+    const bool finite = m <= 1.7976931348623157e308;            // false for inf / nan
+    const bool tiled = finite && total_ll > 0 && total_ll <= TILE_CELLS;
+    const int total = tiled ? (int)total_ll : 0;
+    const int e = tiled ? ilogb(m) : 0;
+    const double scale = scalbn(1.0, 52 - e), inv_scale = scalbn(1.0, e - 52);       // |w F| < 2^(e+1)  ->  |q| < 2^53, sums of 2^9 stay below 2^62
+    for (int t = threadIdx.x; t < 9 * total; t += blockDim.x) s_tile[t] = 0;
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const double pp[3] = {vpos[base + v], vpos[cap + base + v], vpos[2 * cap + base + v]};
+        const double F[3] = {vfrc[base + v], vfrc[cap + base + v], vfrc[2 * cap + base + v]};
+        const int cls = d_classify(g, pp);
+        if (cls == 0) continue;
+        if (!tiled) { d_spread_vertex(g, force, pp, F, cls, true); continue; }
+        const double pr[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};
+        if (cls == 3) {
+            const double weight = d_plates_distance(g, pp) - 1.5;
+            if (weight >= 1) d_tile_pass(g, b, total, s_tile, scale, force, pr, false, F);
+            else if (weight <= 0) d_tile_pass(g, b, total, s_tile, scale, force, pr, true, F);
+            else {
+                const double Fw[3] = {F[0] * weight, F[1] * weight, F[2] * weight};
+                const double Ft[3] = {F[0] * (1. - weight), F[1] * (1. - weight), F[2] * (1. - weight)};
+                d_tile_pass(g, b, total, s_tile, scale, force, pr, false, Fw);
+                d_tile_pass(g, b, total, s_tile, scale, force, pr, true, Ft);
+            }
+        } else d_tile_pass(g, b, total, s_tile, scale, force, pr, false, F);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        long long q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            q[c] = (((long long)s_tile[(6 + c) * total + t] << 22) + (long long)s_tile[(3 + c) * total + t]) * (1LL << 22) + (long long)s_tile[c * total + t];
+        if (q[0] == 0 && q[1] == 0 && q[2] == 0) continue;
+        long long idx;
+        if (!d_band_cell(g, b, t, idx)) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) if (q[c] != 0) atomicAdd(force + c * g.vol + idx, (double)q[c] * inv_scale);
+    }
+}
+
 Geo make_geo(const bib_domain* d) {
     Geo g;
     g.nx = d->gnx; g.ny = d->ny; g.nz = d->nz;
@@ -1695,7 +1807,18 @@ int ib_forces_and_spread(bib_domain* d) {
     if (d->pp_pot.type != 0 && !ib_pp_forces(d)) return 0;   // after every particle's own forces (_forces.hh:300-302)
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
-    else k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+    else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
+    else {
+        const size_t smem = (size_t)TILE_CELLS * 9 * sizeof(int);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k_spread_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+        for (const ParticleGroup& gr : d->groups) {
+            k_spread_tile<<<gr.count, 256, smem, d->stream>>>(make_geo(d), d->force, d->pstate, d->vpos, d->vfrc, d->cap_vertices, d->shapes[gr.shape].nv,
+                                                         gr.first_vertex, gr.first_particle);
+            d->launches++;
+        }
+        d->launches--;
+    }
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     return 1;

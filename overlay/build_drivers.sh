@@ -48,7 +48,7 @@ patch_params() {  # patch_params <driver.cpp> <out.cpp>
     "$1" > "$2"
 }
 
-DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe}"
+DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe rigid_particle_in_shear}"
 for drv in $DRIVERS; do
   dir="$REF/progs/$drv"
   src="$(ls "$dir"/*.cpp | head -1)"

@@ -136,6 +136,20 @@ def test_rbcs_in_shear_driver_bit_identical(tmp_path):
                   meshes=[("sphere_TRImesh_626n_1248el.msh", (shape.verts, shape.tris))])
 
 
+def test_rigid_particle_in_shear_driver_bit_identical(tmp_path):
+    """progs/rigid_particle_in_shear/ellipsoid_in_shear.cpp: three stiff particles (RBC membrane model with create_platelet_params)
+    in a 33^3 Couette cell, one run per mesh. The driver's ellipsoid meshes are not in the reference repository; any closed
+    triangulated surface will do, the platelet / RBC / capsule sphere meshes are written under the names it expects."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    plt = np.load(kit.GOLDEN / "platelet54.npz")
+    big = np.load(kit.GOLDEN / "sphere1046.npz")
+    meshes = [("ellipsoid_1.5_3_3_TRImesh_74n_144el.msh", (plt["verts"] * np.array([0.75, 1.5, 1.5]), plt["tris"])),
+              ("ellipsoid_1.5_3_3_TRImesh_166n_328el.msh", (shape.verts * np.array([0.25, 0.5, 0.5]), shape.tris)),
+              ("ellipsoid_1.5_3_3_TRImesh_374n_744el.msh", (big["verts"] * np.array([0.25, 0.5, 0.5]), big["tris"]))]
+    files = _compare_runs(tmp_path, "rigid_particle_in_shear", dict(BIB_NT="25"), meshes=meshes, min_files=12)
+    assert sum("checkpoint_lbm.dat" in f for f in files) == 3
+
+
 PIPE_XML = """<?xml version="1.0" ?>
 <geometry><diameter>30</diameter><length>24</length></geometry>
 <physics><Re_d>1</Re_d></physics>
