@@ -21,7 +21,7 @@ SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
-    "bib_ib_particles_add", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
@@ -190,6 +190,19 @@ class Lattice:
         params = np.ascontiguousarray(params, dtype=np.float64)
         assert params.size == 8
         _check(self.lib.bib_ib_particles_add(self.h, int(kind), int(sid), _dptr(params), positions.shape[0], _dptr(positions)))
+
+    def add_rigid_particles(self, sid, inertia, shape_volume, state17):
+        """RigidParticle3D: state17 [n][17] = com, velocity, angular velocity, quaternion, density, damping, relaxation, scale."""
+        st = np.ascontiguousarray(state17, dtype=np.float64).reshape(-1, 17)
+        I = np.ascontiguousarray(inertia, dtype=np.float64).reshape(9)
+        _check(self.lib.bib_ib_rigid_particles_add(self.h, int(sid), _dptr(I), C.c_double(shape_volume), st.shape[0], _dptr(st)))
+
+    def rigid_state(self, first=0, count=None):
+        if count is None:
+            count = self.count()[0] - first
+        out = np.empty((count, 19), dtype=np.float64)
+        _check(self.lib.bib_ib_rigid_state_download(self.h, int(first), int(count), _dptr(out)))
+        return out
 
     def set_regulator(self, p, target):
         _check(self.lib.bib_ib_set_regulator(self.h, C.c_double(p), C.c_double(target[0]), C.c_double(target[1]), C.c_double(target[2])))

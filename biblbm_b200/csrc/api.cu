@@ -116,7 +116,7 @@ int bib_domain_destroy(bib_domain* d) {
         for (void* p : ptrs) if (p) cudaFree(p);
     }
     for (WallPlane& w : d->walls) if (w.vel) cudaFree(w.vel);
-    for (ParticleGroup& g : d->groups) { if (g.link_ks) cudaFree(g.link_ks); if (g.link_kp) cudaFree(g.link_kp); }
+    for (ParticleGroup& g : d->groups) { if (g.link_ks) cudaFree(g.link_ks); if (g.link_kp) cudaFree(g.link_kp); if (g.rigid) cudaFree(g.rigid); }
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
@@ -248,6 +248,16 @@ int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* pa
     BIB_ENTER(d);
     if (!params || (n > 0 && !positions)) { bib_set_error("particles_add: null argument"); return 0; }
     return ib_particles_add(d, type, shape_id, params, n, positions);
+}
+int bib_ib_rigid_particles_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17) {
+    BIB_ENTER(d);
+    if (!inertia9 || (n > 0 && !state17)) { bib_set_error("rigid_particles_add: null argument"); return 0; }
+    return ib_rigid_add(d, shape_id, inertia9, shape_volume, n, state17);
+}
+int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, double* state19) {
+    BIB_ENTER(d);
+    if (count > 0 && !state19) { bib_set_error("rigid_state_download: null argument"); return 0; }
+    return ib_rigid_download(d, first_particle, count, state19);
 }
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz) {
     BIB_ENTER(d);

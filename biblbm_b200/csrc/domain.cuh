@@ -43,6 +43,8 @@ struct ParticleGroup {            // particles of one (type, shape, params) adde
     double params[8] = {0};
     double* link_ks = nullptr;    // [nl] per-link WLC spring constant (host-computed with libm pow, like the reference)
     double* link_kp = nullptr;    // [nl]
+    double* rigid = nullptr;      // type 3 (RigidParticle3D): [count][24] com, vel, angvel, quat, force, torque, density, damping, relax, scale
+    double inertia[9] = {0}; double shape_volume = 0;   // body-frame moment of inertia and volume of the (unscaled) shape
 };
 
 // Immersed boundaries on several slabs: every rank keeps a slot array holding the particles it OWNS (centre of mass inside
@@ -163,6 +165,8 @@ int lbm_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux,
 
 int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const int* tris, int* shape_id);
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
+int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
+int ib_rigid_download(bib_domain* d, int first, int count, double* state19);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
 int ib_forces_and_spread(bib_domain* d);

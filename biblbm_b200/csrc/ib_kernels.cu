@@ -780,6 +780,153 @@ __global__ void __launch_bounds__(256) k_semirigid_forces(SemiParams q, const do
     }
 }
 
+// ------------------------------------------------------------------------------------------------ M3: RigidParticle3D
+// src/fsi/RigidParticle.hh:31-120 (update, move_vertices, compute_forces), Quaternion.h, Matrix3.h:129-144. One CTA per particle;
+// rigid state RS = 24 doubles: com[3], velocity[3], angular velocity[3], quaternion[4], force[3], torque[3], density, damping,
+// relaxation factor, scale, pad. Sums over vertices run sequentially in one thread (the reference's order).
+#define RS 24
+__device__ __forceinline__ void d_quat_rot(const double* q, const double* v, double* r) {
+    r[0] = (1 - 2 * (q[2] * q[2] + q[3] * q[3])) * v[0] + 2 * (q[1] * q[2] - q[0] * q[3]) * v[1] + 2 * (q[0] * q[2] + q[1] * q[3]) * v[2];
+    r[1] = 2 * (q[1] * q[2] + q[0] * q[3]) * v[0] + (1 - 2 * (q[1] * q[1] + q[3] * q[3])) * v[1] + 2 * (q[2] * q[3] - q[0] * q[1]) * v[2];
+    r[2] = 2 * (q[1] * q[3] - q[0] * q[2]) * v[0] + 2 * (q[0] * q[1] + q[2] * q[3]) * v[1] + (1 - 2 * (q[1] * q[1] + q[2] * q[2])) * v[2];
+}
+__device__ __forceinline__ void d_quat_inv_rot(const double* q, const double* v, double* r) {
+    r[0] = (1 - 2 * (q[2] * q[2] + q[3] * q[3])) * v[0] + 2 * (q[1] * q[2] + q[0] * q[3]) * v[1] + 2 * (q[1] * q[3] - q[0] * q[2]) * v[2];
+    r[1] = 2 * (q[1] * q[2] - q[0] * q[3]) * v[0] + (1 - 2 * (q[1] * q[1] + q[3] * q[3])) * v[1] + 2 * (q[0] * q[1] + q[2] * q[3]) * v[2];
+    r[2] = 2 * (q[0] * q[2] + q[1] * q[3]) * v[0] + 2 * (q[2] * q[3] - q[0] * q[1]) * v[1] + (1 - 2 * (q[1] * q[1] + q[2] * q[2])) * v[2];
+}
+__device__ __forceinline__ void d_mat_vec(const double* m, const double* v, double* r) {
+    r[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2]; r[1] = m[3] * v[0] + m[4] * v[1] + m[5] * v[2]; r[2] = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+}
+struct RigidParams {
+    int nv, nt; long long first_vertex, cap; int first_particle;
+    const int* tris; const int* v_tri_off; const int* v_tri; const double* rest;   // rest: [nv][3] shape vertices
+    double* rigid; double inertia[9]; double shape_volume; const int* role; int f_init;
+};
+// compute_forces: f_i += relaxation * M_i * (V + W x (x_i - X) - u_i), M_i = sum of a third of the incident triangle areas
+__global__ void __launch_bounds__(256) k_rigid_forces(RigidParams q, const double* __restrict__ vpos, const double* __restrict__ vvel, double* __restrict__ vfrc) {
+    const int pl = blockIdx.x;
+    if (q.role && q.role[q.first_particle + pl] != 1) return;
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    const double* rs = q.rigid + (long long)pl * RS;
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        double M = 0.0;
+        for (int e = q.v_tri_off[v]; e < q.v_tri_off[v + 1]; ++e) {
+            const int tr = q.v_tri[e] / 3;
+            const V3 v0 = ld3(vpos, q.cap, base + q.tris[3 * tr]), v1 = ld3(vpos, q.cap, base + q.tris[3 * tr + 1]), v2 = ld3(vpos, q.cap, base + q.tris[3 * tr + 2]);
+            const double local_area = 0.5 * nrm(crs(sub(v1, v0), sub(v2, v0)));
+            M += local_area / 3.;
+        }
+        const double p[3] = {vpos[base + v], vpos[q.cap + base + v], vpos[2 * q.cap + base + v]};
+        const double r[3] = {p[0] - rs[0], p[1] - rs[1], p[2] - rs[2]};
+        const double w[3] = {rs[7] * r[2] - rs[8] * r[1], rs[8] * r[0] - rs[6] * r[2], rs[6] * r[1] - rs[7] * r[0]};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double f = q.f_init ? vfrc[d * q.cap + base + v] : 0.0;
+            f += rs[21] * M * ((rs[3 + d] + w[d]) - vvel[d * q.cap + base + v]);
+            vfrc[d * q.cap + base + v] = f;
+        }
+    }
+}
+// move_vertices + update + map_center_of_mass_to_periodic_grid (do_move = 0: only place the nodes and refresh the bounding box)
+__global__ void __launch_bounds__(256) k_rigid_move(Geo g, RigidParams q, double* __restrict__ vpos, const double* __restrict__ vfrc,
+                                                    double* __restrict__ pstate, int do_move) {
+    __shared__ double s_rs[RS];
+    __shared__ double s_R[9];
+    __shared__ double s_red[6][8];
+    const int pl = blockIdx.x;
+    if (q.role && q.role[q.first_particle + pl] == 0) return;
+    const long long base = q.first_vertex + (long long)pl * q.nv;
+    double* rsg = q.rigid + (long long)pl * RS;
+    if (threadIdx.x < RS) s_rs[threadIdx.x] = rsg[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* com = s_rs; double* vel = s_rs + 3; double* om = s_rs + 6; double* qt = s_rs + 9; double* F = s_rs + 13; double* Tq = s_rs + 16;
+        if (do_move) {
+            const double density = s_rs[19], damping = s_rs[20], scale = s_rs[22];
+            for (int d = 0; d < 3; ++d) F[d] = Tq[d] = 0.0;
+            for (int i = 0; i < q.nv; ++i) {
+                const double f[3] = {vfrc[base + i], vfrc[q.cap + base + i], vfrc[2 * q.cap + base + i]};
+                const double r[3] = {vpos[base + i] - com[0], vpos[q.cap + base + i] - com[1], vpos[2 * q.cap + base + i] - com[2]};
+                for (int d = 0; d < 3; ++d) F[d] += f[d];
+                Tq[0] += r[1] * f[2] - r[2] * f[1]; Tq[1] += r[2] * f[0] - r[0] * f[2]; Tq[2] += r[0] * f[1] - r[1] * f[0];
+            }
+            double om_body[3]; d_quat_inv_rot(qt, om, om_body);
+            const double sI = density * ((((scale * scale) * scale) * scale) * scale);      // std::pow(scale_, 5) as the reference build evaluates it
+            double I[9];
+            for (int k = 0; k < 9; ++k) I[k] = sI * q.inertia[k];
+            const double mass = (scale * scale * scale) * q.shape_volume * density;
+            double v_dot[3], tq_body[3], Iw[3], rhs[3], sol[3], rot[3];
+            for (int d = 0; d < 3; ++d) v_dot[d] = F[d] / mass - damping * vel[d];
+            d_quat_inv_rot(qt, Tq, tq_body);
+            d_mat_vec(I, om_body, Iw);
+            const double cr[3] = {om_body[1] * Iw[2] - om_body[2] * Iw[1], om_body[2] * Iw[0] - om_body[0] * Iw[2], om_body[0] * Iw[1] - om_body[1] * Iw[0]};
+            for (int d = 0; d < 3; ++d) rhs[d] = tq_body[d] - cr[d];
+            const double* a = I;
+            const double det = a[0] * a[4] * a[8] - a[0] * a[5] * a[7] - a[1] * a[3] * a[8] + a[1] * a[5] * a[6] + a[2] * a[3] * a[7] - a[2] * a[4] * a[6];
+            sol[0] = (rhs[2] * (a[1] * a[5] - a[2] * a[4]) + rhs[1] * (a[2] * a[7] - a[1] * a[8]) + rhs[0] * (a[4] * a[8] - a[5] * a[7])) / det;
+            sol[1] = (rhs[2] * (a[2] * a[3] - a[0] * a[5]) + rhs[1] * (a[0] * a[8] - a[2] * a[6]) + rhs[0] * (a[5] * a[6] - a[3] * a[8])) / det;
+            sol[2] = (rhs[2] * (a[0] * a[4] - a[1] * a[3]) + rhs[1] * (a[1] * a[6] - a[0] * a[7]) + rhs[0] * (a[3] * a[7] - a[4] * a[6])) / det;
+            d_quat_rot(qt, sol, rot);
+            for (int d = 0; d < 3; ++d) { vel[d] += v_dot[d]; om[d] += rot[d] - damping * om[d]; }
+            for (int d = 0; d < 3; ++d) com[d] += vel[d];
+            const double om_norm = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+            if (om_norm >= 10 * 2.220446049250313e-16) {        // exponential map (sin / cos: last-bit differences vs the host libm are possible)
+                const double ax[3] = {om[0] / om_norm, om[1] / om_norm, om[2] / om_norm};
+                const double sh = sin(om_norm / 2);
+                const double p[4] = {cos(om_norm / 2), sh * ax[0], sh * ax[1], sh * ax[2]};
+                const double r4[4] = {p[0] * qt[0] - (p[1] * qt[1] + p[2] * qt[2] + p[3] * qt[3]),
+                                      p[0] * qt[1] + qt[0] * p[1] + p[2] * qt[3] - p[3] * qt[2],
+                                      p[0] * qt[2] + qt[0] * p[2] + p[3] * qt[1] - p[1] * qt[3],
+                                      p[0] * qt[3] + qt[0] * p[3] + p[1] * qt[2] - p[2] * qt[1]};
+                for (int k = 0; k < 4; ++k) qt[k] = r4[k];
+            }
+        }
+        s_R[0] = 1 - 2 * (qt[2] * qt[2] + qt[3] * qt[3]); s_R[1] = 2 * (qt[1] * qt[2] - qt[0] * qt[3]); s_R[2] = 2 * (qt[0] * qt[2] + qt[1] * qt[3]);
+        s_R[3] = 2 * (qt[1] * qt[2] + qt[0] * qt[3]); s_R[4] = 1 - 2 * (qt[1] * qt[1] + qt[3] * qt[3]); s_R[5] = 2 * (qt[2] * qt[3] - qt[0] * qt[1]);
+        s_R[6] = 2 * (qt[1] * qt[3] - qt[0] * qt[2]); s_R[7] = 2 * (qt[0] * qt[1] + qt[2] * qt[3]); s_R[8] = 1 - 2 * (qt[1] * qt[1] + qt[2] * qt[2]);
+    }
+    __syncthreads();
+    // node positions and bounding box, then the periodic remap of the centre of mass
+    double delta[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int n = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+        double x = s_rs[d];
+        if (g.per[d]) { const double L = (double)n; x = x - L * floor((x - (0.0 - 0.5)) * (1. / L)); }
+        delta[d] = x - s_rs[d];
+    }
+    double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
+    double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    const double scale = s_rs[22];
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        const double sv[3] = {scale * q.rest[3 * v], scale * q.rest[3 * v + 1], scale * q.rest[3 * v + 2]};
+        double r[3]; d_mat_vec(s_R, sv, r);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double x = s_rs[d] + r[d];
+            mn[d] = fmin(mn[d], x); mx[d] = fmax(mx[d], x);
+            vpos[d * q.cap + base + v] = x + delta[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o)); }
+        if ((threadIdx.x & 31) == 0) { s_red[2 * d][threadIdx.x >> 5] = mn[d]; s_red[2 * d + 1][threadIdx.x >> 5] = mx[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* st = pstate + (long long)(q.first_particle + pl) * 11;
+        for (int d = 0; d < 3; ++d) {
+            double lo = s_red[2 * d][0], hi = s_red[2 * d + 1][0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_red[2 * d][w]); hi = fmax(hi, s_red[2 * d + 1][w]); }
+            s_rs[d] = s_rs[d] + delta[d];
+            st[2 + d] = s_rs[d]; st[5 + 2 * d] = lo + delta[d]; st[5 + 2 * d + 1] = hi + delta[d];
+        }
+        for (int k = 0; k < RS; ++k) rsg[k] = s_rs[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ M4: wall / particle-particle forces
 // fsi/Potentials.h:29-71: type 1 = MorsePotential(r_min, beta, strength), 2 = SpringPotential(min_dist, strength); cutoff = r_min
 __device__ __forceinline__ double d_potential(const PotentialDev& q, double dist) {
@@ -1247,28 +1394,14 @@ __global__ void __launch_bounds__(256) k_band_reset(Geo g, double* force, const 
 // accumulated into a shared-memory tile covering its bounding box + 2 cells (the box k_band_velocity uses; a deflated RBC
 // touches ~1.6k cells, every one of them ~30 times), then each touched cell is added to the lattice force field ONCE with a
 // global fp64 reduction: 81 global atomics per vertex become ~8.
-// sm_100 has no native 64-bit shared-memory atomic add (fp64 and u64 both compile to ATOMS.CAST.SPIN loops, and a returning
-// atomic per stencil point makes the kernel latency-bound), so the tile accumulates in FIXED POINT spread over three 32-bit
-// limbs of 22 + 22 + 18 bits, each updated with a fire-and-forget native ATOMS.ADD; the limbs are summed independently (no
-// carries: |limb| < 2^21, at most 2^9 contributions per cell) and recombined in 64-bit integer arithmetic at flush time.
-// Integer addition commutes, so the per-particle sums do not depend on the order (deterministic). The scale is a power of
-// two chosen per particle from its largest force component (one unit = 2^-52 of it, i.e. fp64 resolution), so converting
-// back is exact.
+// Measured alternatives (782k vertices, B200; profiles/r1_ib_kernels.md): global fp64 atomics only 0.45 ms; this kernel (fp64
+// shared-memory atomicAdd = ATOMS.CAST.SPIN loops, sm_100 has no native 64-bit shared atomic) 0.38 ms and the best whole-IB time;
+// fixed-point limbs on native 32-bit ATOMS.ADD and an atomic-free binned gather were both slower end to end (0.38-0.44 ms).
 // Cells are addressed unwrapped inside the tile; periodic wrap, walls and slab ownership are applied at flush time
 // (d_band_cell), which is exactly where the reference's general kernel drops or wraps them. Boxes larger than the tile, or
 // stencil points outside it, fall back to direct global atomics.
-#define TILE_CELLS 2048
-__device__ __forceinline__ void d_tile_add(int* limb0, int* limb1, int* limb2, long long q) {
-    const long long b0 = ((q + (1LL << 21)) & ((1LL << 22) - 1)) - (1LL << 21);
-    const long long q1 = (q - b0) >> 22;
-    const long long b1 = ((q1 + (1LL << 21)) & ((1LL << 22) - 1)) - (1LL << 21);
-    const long long b2 = (q1 - b1) >> 22;
-    atomicAdd(limb0, (int)b0);
-    if (b1) atomicAdd(limb1, (int)b1);
-    if (b2) atomicAdd(limb2, (int)b2);
-}
-__device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int total, int* s_limb, double scale, double* force,
-                                            const double* p, bool th, const double* F) {
+#define TILE_CELLS 3072
+__device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int total, double* s_tile, double* force, const double* p, bool th, const double* F) {
     const int sup = th ? 2 : 3;
     const double hs = th ? 1.0 : 1.5;
     const int x0 = (int)ceil(p[0] - hs), y0 = (int)ceil(p[1] - hs), z0 = (int)ceil(p[2] - hs);
@@ -1284,7 +1417,7 @@ __device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int tot
                 if (tx >= 0 && tx < b.n[0] && ty >= 0 && ty < b.n[1] && tz >= 0 && tz < b.n[2]) {
                     const int t = (tx * b.n[1] + ty) * b.n[2] + tz;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) d_tile_add(&s_limb[c * total + t], &s_limb[(3 + c) * total + t], &s_limb[(6 + c) * total + t], __double2ll_rn((w * F[c]) * scale));
+                    for (int c = 0; c < 3; ++c) atomicAdd(&s_tile[c * total + t], w * F[c]);
                 } else {
                     const int i2 = d_remap(g, 0, i), j2 = d_remap(g, 1, j), k2 = d_remap(g, 2, k);
                     if (i2 < 0 || i2 > g.nx - 1 || !d_in_slab(g, i2) || j2 < 0 || j2 > g.ny - 1 || k2 < 0 || k2 > g.nz - 1) continue;
@@ -1298,30 +1431,16 @@ __device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int tot
 }
 __global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const double* __restrict__ pstate, const double* __restrict__ vpos,
                                                      const double* __restrict__ vfrc, long long cap, int nv, long long first_vertex, int first_particle) {
-    extern __shared__ int s_tile[];
-    __shared__ double s_max[8];
+    extern __shared__ double s_tile[];
     const int p = first_particle + blockIdx.x;
     if (g.role && g.role[p] == 0) return;
     const Band b = d_band(pstate + (long long)p * 11, 2);
     const long long total_ll = (long long)b.n[0] * b.n[1] * b.n[2];
-    const long long base = first_vertex + (long long)blockIdx.x * nv;
-    // largest force component of the particle -> power-of-two fixed-point scale
-    double m = 0.0;
-    for (int v = threadIdx.x; v < nv; v += blockDim.x)
-        m = fmax(m, fmax(fabs(vfrc[base + v]), fmax(fabs(vfrc[cap + base + v]), fabs(vfrc[2 * cap + base + v]))));
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
-    __syncthreads();
-    m = s_max[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, s_max[w]);
-    if (m == 0.0) return;                                       // nothing to spread (uniform across the CTA)
-    const bool finite = m <= 1.7976931348623157e308;            // false for inf / nan
-    const bool tiled = finite && total_ll > 0 && total_ll <= TILE_CELLS;
+    const bool tiled = total_ll > 0 && total_ll <= TILE_CELLS;
     const int total = tiled ? (int)total_ll : 0;
-    const int e = tiled ? ilogb(m) : 0;
-    const double scale = scalbn(1.0, 52 - e), inv_scale = scalbn(1.0, e - 52);       // |w F| < 2^(e+1)  ->  |q| < 2^53, sums of 2^9 stay below 2^62
-    for (int t = threadIdx.x; t < 9 * total; t += blockDim.x) s_tile[t] = 0;
+    for (int t = threadIdx.x; t < 3 * total; t += blockDim.x) s_tile[t] = 0.0;
     __syncthreads();
+    const long long base = first_vertex + (long long)blockIdx.x * nv;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) {
         const double pp[3] = {vpos[base + v], vpos[cap + base + v], vpos[2 * cap + base + v]};
         const double F[3] = {vfrc[base + v], vfrc[cap + base + v], vfrc[2 * cap + base + v]};
@@ -1331,27 +1450,23 @@ __global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const
         const double pr[3] = {pp[0] - (-1.0), pp[1] - (-1.0), pp[2] - (-1.0)};
         if (cls == 3) {
             const double weight = d_plates_distance(g, pp) - 1.5;
-            if (weight >= 1) d_tile_pass(g, b, total, s_tile, scale, force, pr, false, F);
-            else if (weight <= 0) d_tile_pass(g, b, total, s_tile, scale, force, pr, true, F);
+            if (weight >= 1) d_tile_pass(g, b, total, s_tile, force, pr, false, F);
+            else if (weight <= 0) d_tile_pass(g, b, total, s_tile, force, pr, true, F);
             else {
                 const double Fw[3] = {F[0] * weight, F[1] * weight, F[2] * weight};
                 const double Ft[3] = {F[0] * (1. - weight), F[1] * (1. - weight), F[2] * (1. - weight)};
-                d_tile_pass(g, b, total, s_tile, scale, force, pr, false, Fw);
-                d_tile_pass(g, b, total, s_tile, scale, force, pr, true, Ft);
+                d_tile_pass(g, b, total, s_tile, force, pr, false, Fw);
+                d_tile_pass(g, b, total, s_tile, force, pr, true, Ft);
             }
-        } else d_tile_pass(g, b, total, s_tile, scale, force, pr, false, F);
+        } else d_tile_pass(g, b, total, s_tile, force, pr, false, F);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        long long q[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            q[c] = (((long long)s_tile[(6 + c) * total + t] << 22) + (long long)s_tile[(3 + c) * total + t]) * (1LL << 22) + (long long)s_tile[c * total + t];
-        if (q[0] == 0 && q[1] == 0 && q[2] == 0) continue;
+        const double fx = s_tile[t], fy = s_tile[total + t], fz = s_tile[2 * total + t];
+        if (fx == 0.0 && fy == 0.0 && fz == 0.0) continue;
         long long idx;
         if (!d_band_cell(g, b, t, idx)) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) if (q[c] != 0) atomicAdd(force + c * g.vol + idx, (double)q[c] * inv_scale);
+        atomicAdd(force + idx, fx); atomicAdd(force + g.vol + idx, fy); atomicAdd(force + 2 * g.vol + idx, fz);
     }
 }
 
@@ -1535,6 +1650,17 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
 
 static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move, const uint8_t* skip_mask = nullptr) {
     const ShapeDev& s = d->shapes[gr.shape];
+    if (gr.type == 3) {
+        RigidParams c;
+        c.nv = s.nv; c.nt = s.nt; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
+        c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
+        for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
+        c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = 0;
+        k_rigid_move<<<gr.count, 256, 0, d->stream>>>(make_geo(d), c, d->vpos, d->vfrc, d->pstate, do_move);
+        d->launches++;
+        BIB_CHECK(cudaGetLastError());
+        return 1;
+    }
     k_move_update<<<gr.count, 256, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.first_particle,
                                                  d->vpos, d->vvel, d->pstate, do_move, skip_mask);
     d->launches++;
@@ -1603,7 +1729,7 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
 }
 
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
-    if (type < 0 || type > 2) { bib_set_error("particles_add: unknown particle type (BIB_PARTICLE_RBC, BIB_PARTICLE_CAPSULE, BIB_PARTICLE_SEMIRIGID)"); return 0; }
+    if (type < 0 || type > 2) { bib_set_error("particles_add: unknown particle type (BIB_PARTICLE_RBC, BIB_PARTICLE_CAPSULE, BIB_PARTICLE_SEMIRIGID; rigid particles: bib_ib_rigid_particles_add)"); return 0; }
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("particles_add: unknown shape"); return 0; }
     if (n <= 0) return 1;
     if (d->n_ranks > 1) return ib_particles_add_multislab(d, type, shape_id, params, n, positions);
@@ -1626,6 +1752,45 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
     d->n_particles += n; d->n_vertices += nvtot;
     // ParticleBase3D::update() at construction + add_particle's map_center_of_mass_to_periodic_grid (ImmersedBoundaryDynamics.hh:500-525)
     return launch_update(d, gr, 0);
+}
+
+// RigidParticle3D particles: state17 per particle = com[3], velocity[3], angular velocity[3], quaternion[4], density, damping,
+// relaxation factor, scale. Node positions follow from the state (RigidParticle3D::update).
+int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17) {
+    if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("rigid_particles_add: unknown shape"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("rigid particles: single-slab domains only (round 1)"); return 0; }
+    if (n <= 0) return 1;
+    const ShapeDev& s = d->shapes[shape_id];
+    const long long nvtot = (long long)n * s.nv;
+    if (!grow_particles(d, d->n_vertices + nvtot, d->n_particles + n)) return 0;
+    ParticleGroup gr;
+    gr.type = 3; gr.shape = shape_id; gr.first_particle = d->n_particles; gr.count = n; gr.first_vertex = d->n_vertices;
+    for (int k = 0; k < 9; ++k) gr.inertia[k] = inertia9[k];
+    gr.shape_volume = shape_volume;
+    std::vector<double> rs((size_t)n * RS, 0.0), st((size_t)n * 11, 0.0);
+    for (int p = 0; p < n; ++p) {
+        const double* in = state17 + (size_t)p * 17;
+        for (int k = 0; k < 13; ++k) rs[(size_t)p * RS + k] = in[k];
+        for (int k = 0; k < 4; ++k) rs[(size_t)p * RS + 19 + k] = in[13 + k];
+        st[(size_t)p * 11] = s.area; st[(size_t)p * 11 + 1] = s.volume;       // ParticleBase3D constructor: the shape's area and volume
+    }
+    if (!to_device(&gr.rigid, rs)) return 0;
+    BIB_CHECK(cudaMemcpyAsync(d->pstate + (size_t)gr.first_particle * 11, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    d->groups.push_back(gr);
+    d->n_particles += n; d->n_vertices += nvtot;
+    return launch_update(d, gr, 0);
+}
+int ib_rigid_download(bib_domain* d, int first, int count, double* state19) {
+    if (first < 0 || count < 0 || first + count > d->n_particles) { bib_set_error("rigid_state_download: range"); return 0; }
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    for (int p = first; p < first + count; ++p) {
+        const ParticleGroup* g = nullptr;
+        for (const ParticleGroup& gr : d->groups) if (p >= gr.first_particle && p < gr.first_particle + gr.count) g = &gr;
+        if (!g || g->type != 3) { bib_set_error("rigid_state_download: not a rigid particle"); return 0; }
+        BIB_CHECK(cudaMemcpy(state19 + (size_t)(p - first) * 19, g->rigid + (size_t)(p - g->first_particle) * RS, 19 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------ host: IB phases
@@ -1757,6 +1922,16 @@ int ib_forces_and_spread(bib_domain* d) {
     }
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
+        if (gr.type == 3) {
+            RigidParams c;
+            c.nv = s.nv; c.nt = s.nt; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
+            c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
+            for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
+            c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
+            k_rigid_forces<<<gr.count, 256, 0, d->stream>>>(c, d->vpos, d->vvel, d->vfrc);
+            d->launches++;
+            continue;
+        }
         if (gr.type == 2) {
             SemiParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
@@ -1809,7 +1984,7 @@ int ib_forces_and_spread(bib_domain* d) {
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
     else {
-        const size_t smem = (size_t)TILE_CELLS * 9 * sizeof(int);
+        const size_t smem = (size_t)TILE_CELLS * 3 * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(k_spread_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
         for (const ParticleGroup& gr : d->groups) {

@@ -105,6 +105,13 @@ int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* l
 /* params for BIB_PARTICLE_RBC: {shear_modulus, L0, k_area_global, k_area_local, k_volume, vol_desired, k_bend, theta0}
  * (RBCParameters, src/fsi/RBCParticle.h:23-60). positions: [n][nv][3]. Particles get ids in order of addition. */
 int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
+/* fsi::RigidParticle3D (src/fsi/RigidParticle.hh:31-120): direct-forcing coupling f_i += relaxation * M_i * (U_rigid(x_i) - u_i) and
+ * Newton-Euler integration with a quaternion exponential map. inertia9 / shape_volume: ParticleShape::get_moment_of_inertia() (row
+ * major) and get_volume() of the unscaled shape. state17 per particle: centre of mass[3], velocity[3], angular velocity[3] (world
+ * frame), orientation quaternion[4], density, damping, relaxation_factor, scale. Single-slab domains (round 1). */
+int bib_ib_rigid_particles_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
+/* state19 per particle: centre of mass, velocity, angular velocity, quaternion, total force, total torque */
+int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, double* state19);
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz);
 /* fsi.set_boundary(&ParallelPlatesBoundary(y0, y1)) (src/fsi/Boundary.h:300-365, progs/rbcs_in_shear/rbcs_in_shear.cpp:122-123): vertices
  * within 2.5 cells of a plate interpolate / spread with the Roma kernel blended into the 2-point kernel

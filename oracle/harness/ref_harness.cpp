@@ -265,6 +265,21 @@ static void dump_particles(FSI& fsi, i64 np, const std::string& vert_name, const
         pp.push_back(bb.x0); pp.push_back(bb.x1); pp.push_back(bb.y0); pp.push_back(bb.y1); pp.push_back(bb.z0); pp.push_back(bb.z1);
     }
     write_f64(vert_name, vv); write_f64(part_name, pp);
+    // rigid particles: com, velocity, angular velocity, orientation, force, torque (19 doubles each)
+    std::vector<double> rr;
+    for (i64 i = 0; i < np; ++i) {
+        const ParticleBase3D<double>* p;
+        fsi.get_particle(i, p);
+        const RigidParticle3D<double>* r = dynamic_cast<const RigidParticle3D<double>*>(p);
+        if (!r) continue;
+        for (int d = 0; d < 3; ++d) rr.push_back(r->center_of_mass()[d]);
+        for (int d = 0; d < 3; ++d) rr.push_back(r->velocity()[d]);
+        for (int d = 0; d < 3; ++d) rr.push_back(r->angular_velocity()[d]);
+        for (int d = 0; d < 4; ++d) rr.push_back(r->orientation()[d]);
+        for (int d = 0; d < 3; ++d) rr.push_back(r->force()[d]);
+        for (int d = 0; d < 3; ++d) rr.push_back(r->torque()[d]);
+    }
+    if (!rr.empty()) { std::string n = vert_name; n.replace(n.find("vert_"), 5, "rigid_"); write_f64(n, rr); }
 }
 
 template <class Periodicity>
@@ -359,8 +374,30 @@ static int run(const Config& cfg) {
         np = (i64)(pf.size() - 8) / (nv * 3);
         const ParticleShape<double>* shape = shape_library.get_by_tag("RBC");
         const bool capsule = cfg.str("particle_type", "rbc") == "capsule";     // params = {G, C, nu_s, kb, 0, 0, 0, 0}
+        const bool rigid = cfg.str("particle_type", "rbc") == "rigid";  // params = {density, damping, relaxation_factor, scale}; rigid_state file: [np][13] com, vel, angvel, quat
+        if (rigid) {
+            std::vector<double> rsf = read_f64(cfg.str("rigid_state"));
+            np = (i64)rsf.size() / 13;
+            for (i64 p = 0; p < np; ++p) {
+                const double* r = &rsf[p * 13];
+                RigidParticle3D<double> rp(shape);
+                rp.density() = pf[0]; rp.damping() = pf[1]; rp.relaxation_factor() = pf[2]; rp.scale() = pf[3];
+                rp.orientation() = Quaternion<double>(r[9], r[10], r[11], r[12]);
+                rp.update();
+                rp.set_center_of_mass(Array<double, 3>(r[0], r[1], r[2]));
+                rp.velocity() = Array<double, 3>(r[3], r[4], r[5]);
+                rp.angular_velocity() = Array<double, 3>(r[6], r[7], r[8]);
+                rp.update();
+                fsi->add_particle(&rp);
+            }
+            std::vector<double> sh;
+            Matrix<double, 3> I = shape->get_moment_of_inertia();
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) sh.push_back(I(a, b));
+            sh.push_back(shape->get_volume());
+            write_f64(out + "/rigid_shape.f64", sh);
+        }
         const bool semirigid = cfg.str("particle_type", "rbc") == "semirigid";  // params = {l0, k_in_plane, k_out_of_plane, k_bend, 0, 0, 0, 0}
-        for (i64 p = 0; p < np; ++p) {
+        for (i64 p = 0; p < (rigid ? 0 : np); ++p) {
             if (semirigid) {
                 SemiRigidParticleParams<double> sp; sp.l0 = pf[0]; sp.k_in_plane = pf[1]; sp.k_out_of_plane = pf[2]; sp.k_bend = pf[3];
                 SemiRigidParticle3D<double> plt(shape, sp);

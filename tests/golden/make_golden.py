@@ -200,6 +200,26 @@ def make_semirigid():
     print("semirigid golden ok, max |F| =", np.abs(out[f"vert_{steps}"][..., 6:]).max())
 
 
+def make_rigid():
+    """RigidParticle3D (M3): a rigid sphere (626-vertex mesh, scale 0.8) with initial translation, spin and tilt in a periodic box with
+    a sine flow: direct-forcing coupling + Newton-Euler integration with the quaternion exponential map, 8 steps."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    nx, ny, nz, steps = 24, 22, 20, 8
+    rp = np.array([1.0, 0.0, 0.45, 0.8, 0, 0, 0, 0])            # density, damping, relaxation_factor, scale
+    ang, ax = 0.7, np.array([0.3, -0.5, 0.8]); ax /= np.linalg.norm(ax)
+    q = np.array([np.cos(ang / 2), *(np.sin(ang / 2) * ax)])
+    rs13 = np.array([[11.3, 10.2, 9.6, 0.004, -0.002, 0.001, 0.002, 0.001, -0.003, *q]])
+    out = kit.run_reference(dict(nx=nx, ny=ny, nz=nz, steps=steps, dump_every=1, periodicity="ppp", omega=1.0, omega_inner=0.5, u0=0.02),
+                            verts=shape.verts, tris=shape.tris, params=rp, rigid_state=rs13)
+    keep = dict(pop_init=out["pop_init"], vert_init=out["vert_init"], part_init=out["part_init"], rigid_init=out["rigid_init"], rigid_shape=out["rigid_shape"],
+                pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(), omega=1.0, omega_inner=0.5, steps=steps, rparams=rp,
+                per=np.array([1, 1, 1], dtype=np.int32), body=np.zeros(3))
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]; keep[f"rigid_{s}"] = out[f"rigid_{s}"]
+    np.savez_compressed(HERE / "ib_rigid.npz", **keep)
+    print("rigid golden ok")
+
+
 def pipe_case():
     """rbc_in_pipe-type set-up in miniature (x periodic; PipeBoundary; Morse wall interaction and Morse particle-particle
     interaction with the parameters of progs/rbc_in_pipe/input.xml): RBC A almost touching the pipe wall with the fluid initially
@@ -291,6 +311,7 @@ if __name__ == "__main__":
     make_capsule()
     make_plates()
     make_semirigid()
+    make_rigid()
     make_pipe()
     make_guo()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

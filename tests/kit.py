@@ -213,6 +213,18 @@ class Oracle:
                                None if wv is None else _d(wv),
                                None if kind is None else np.ascontiguousarray(kind, dtype=np.uint8).ctypes.data_as(_u8p))
 
+    def set_rigid(self, rigid_state, inertia, shape_volume):
+        """RigidParticle3D model (particle model 3): rigid_state [np][24] is updated in place by ib_step / full_step."""
+        self._rs = rigid_state
+        self._inertia = np.ascontiguousarray(inertia, dtype=np.float64)
+        self.lib.orc_set_rigid(_d(self._rs), _d(self._inertia), C.c_double(shape_volume))
+
+    def rigid_place(self, rest_verts, rs):
+        rest = np.ascontiguousarray(rest_verts, dtype=np.float64)
+        pos = np.zeros_like(rest)
+        self.lib.orc_rigid_place(C.c_int(rest.shape[0]), _d(rest), _d(np.ascontiguousarray(rs, dtype=np.float64)), _d(pos))
+        return pos
+
     def reset_modes(self):
         self.set_parallel_plates(0); self.set_wall_interaction(0); self.set_pp_interaction(0); self.set_particle_model(0)
 
@@ -318,7 +330,7 @@ def write_mesh_bin(path, verts, tris):
 
 
 def run_reference(cfg: dict, workdir=None, verts=None, tris=None, params=None, particle_pos=None,
-                  externals=None, populations=None, timeout=600):
+                  externals=None, populations=None, timeout=600, rigid_state=None):
     """Run oracle/_ref/ref_harness `run` and load its dumps. Returns dict name -> ndarray (+ 'stdout')."""
     assert have_reference(), "oracle/_ref/ref_harness missing: run oracle/build_ref.sh (needs /root/reference)"
     tmp = None
@@ -340,6 +352,14 @@ def run_reference(cfg: dict, workdir=None, verts=None, tris=None, params=None, p
         n_p = pp.shape[0]
         np.concatenate([np.asarray(params, dtype=np.float64), pp.ravel()]).tofile(wd / "particles.f64")
         cfg["particles"] = str(wd / "particles.f64")
+    if rigid_state is not None:        # RigidParticle3D: params = {density, damping, relaxation, scale}; state [np][13] = com, vel, angvel, quaternion
+        rs = np.ascontiguousarray(rigid_state, dtype=np.float64).reshape(-1, 13)
+        n_p = rs.shape[0]
+        np.asarray(params, dtype=np.float64).tofile(wd / "particles.f64")
+        rs.tofile(wd / "rigid_state_in.f64")
+        cfg["particles"] = str(wd / "particles.f64")
+        cfg["rigid_state"] = str(wd / "rigid_state_in.f64")
+        cfg["particle_type"] = "rigid"
     if externals is not None:
         np.ascontiguousarray(externals, dtype=np.float64).tofile(wd / "externals.f64")
         cfg["externals"] = str(wd / "externals.f64")
@@ -356,7 +376,7 @@ def run_reference(cfg: dict, workdir=None, verts=None, tris=None, params=None, p
     out = {"stdout": r.stdout}
     for p in sorted(wd.glob("*.f64")):
         name = p.stem
-        if name in ("particles", "externals", "populations"):
+        if name in ("particles", "externals", "populations", "rigid_state_in"):
             continue
         a = np.fromfile(p)
         if name.startswith("pop_"):
@@ -367,6 +387,8 @@ def run_reference(cfg: dict, workdir=None, verts=None, tris=None, params=None, p
             a = a.reshape(n_p, nv, 9)
         elif name.startswith("part_"):
             a = a.reshape(n_p, 11)
+        elif name.startswith("rigid_") and name != "rigid_shape":
+            a = a.reshape(n_p, 19)
         out[name] = a
     if tmp is not None:
         tmp.cleanup()

@@ -182,6 +182,28 @@ def test_semirigid_particle_vs_golden(rbc):
     assert np.array_equal(lat.download()[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_rigid_particle_vs_golden(rbc):
+    """RigidParticle3D against the reference: 8 coupled steps, deterministic spread. sin / cos of the exponential map may
+    differ from the host libm in the last bit, hence 1e-13 instead of bit equality."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rigid.npz")
+    lat = make_lattice(g["pop_init"], g["per"], float(g["omega"]), float(g["omega_inner"]), {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    st17 = np.concatenate([g["rigid_init"][0, :13], g["rparams"][:4]])[None]
+    lat.add_rigid_particles(sid, g["rigid_shape"][:9], float(g["rigid_shape"][9]), st17)
+    assert np.array_equal(lat.vertices().reshape(1, -1, 9)[..., :3], g["vert_init"][..., :3])
+    assert np.array_equal(lat.particle_scalars(), g["part_init"])
+    for s in range(1, int(g["steps"]) + 1):
+        lat.step(g["body"])
+        v = lat.vertices().reshape(1, -1, 9)
+        assert kit.rel_err(v[..., :3], g[f"vert_{s}"][..., :3]) <= 1e-13, s
+        assert kit.rel_err(v[..., 3:], g[f"vert_{s}"][..., 3:]) <= 1e-11, s
+        assert kit.rel_err(lat.rigid_state(), g[f"rigid_{s}"]) <= 1e-13, s
+        assert kit.rel_err(lat.particle_scalars(), g[f"part_{s}"]) <= 1e-13
+    got = lat.download()[::2, ::2, ::2]
+    assert kit.rel_err(got[..., :19], g["pop_final_sample"][..., :19]) <= 1e-12
+
+
 def test_guo_pipe_wall_vs_golden():
     """GuoRigidWallBoundary (off-lattice pipe wall) + NoDynamics outside, LBM only: bit-identical to the reference."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")

@@ -244,6 +244,24 @@ def test_semirigid_particle_bit_exact(orc, rbc):
     assert np.abs(vert[..., 6:]).max() > 1e-5
 
 
+def test_rigid_particle_bit_exact(orc, rbc):
+    """RigidParticle3D: direct forcing, Newton-Euler, quaternion exponential map; oracle == reference bit for bit."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rigid.npz")
+    cells, vert, state = g["pop_init"].copy(), g["vert_init"].copy(), g["part_init"].copy()
+    rs = np.zeros((1, 24)); rs[0, :13] = g["rigid_init"][0, :13]; rs[0, 19:23] = g["rparams"][:4]
+    assert np.array_equal(orc.rigid_place(shape.verts, rs[0]), vert[0, :, :3])
+    orc.set_particle_model(3, shape.verts)
+    orc.set_rigid(rs, g["rigid_shape"][:9], float(g["rigid_shape"][9]))
+    try:
+        for s in range(1, int(g["steps"]) + 1):
+            orc.full_step(cells, g["per"], float(g["omega"]), float(g["omega_inner"]), g["body"], shape, g["rparams"], vert, state)
+            assert np.array_equal(vert, g[f"vert_{s}"]) and np.array_equal(state, g[f"part_{s}"]) and np.array_equal(rs[0, :19], g[f"rigid_{s}"][0]), s
+    finally:
+        orc.reset_modes()
+    assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
+
+
 def test_guo_pipe_wall_bit_exact(orc):
     """GuoRigidWallBoundary on a pipe + NoDynamics outside (rbc_in_pipe.cpp:285-343), LBM only: the wall-node list and 6 steps."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
