@@ -156,6 +156,36 @@ def run_reference_sample(steps, warmup, replicas, box=96, n_rbc=8):
                        f"{steps} timed steps after {warmup}; no MPI exchange cost included")
 
 
+def driver_speed():
+    """The reference's OWN driver progs/rbc_in_shear (97^3 Couette cell, 1 RBC, unchanged source) compiled against the C++ binding in
+    overlay/ vs against the pure reference: wall-clock per step from the difference of two run lengths (set-up and output cancel)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import kit
+    gpu, cpu = ROOT / "overlay" / "_build" / "rbc_in_shear_short_b200", ROOT / "oracle" / "_ref" / "rbc_in_shear_short_cpu"
+    if not gpu.exists() or not cpu.exists():
+        return None
+    shape, _, _, _ = kit.load_rbc_fixture()
+
+    def run(exe, nt):
+        with tempfile.TemporaryDirectory() as d:
+            kit.write_gmsh(os.path.join(d, "s.msh"), shape.verts, shape.tris)
+            env = dict(os.environ, BIB_NT=str(nt), BIB_OUTPUT_INTERVAL="1000000", BIB_NCASES="1", BIB_MESH=os.path.join(d, "s.msh"), BIB_SHRINK_ITERS="2000")
+            t0 = time.perf_counter()
+            r = subprocess.run([str(exe)], cwd=d, env=env, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr[-500:])
+            return time.perf_counter() - t0
+    try:
+        g = (run(gpu, 4500) - run(gpu, 500)) / 4000.0
+        c = (run(cpu, 35) - run(cpu, 5)) / 30.0
+    except Exception as e:      # reported, never fatal for the bench line
+        return {"error": str(e)[:200]}
+    cells = 97 ** 3
+    return {"workload": "progs/rbc_in_shear/rbc_in_shear.cpp unchanged (97^3 Couette cell, 1 RBC, regulator), linked against the binding vs the pure reference",
+            "binding_ms_per_step": g * 1e3, "binding_mlups": cells / g / 1e6, "reference_ms_per_step": c * 1e3, "reference_mlups": cells / c / 1e6,
+            "reference_cores": 1, "speedup": c / g}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -325,12 +355,13 @@ def ours(args):
             r = run_reference_sample(5, 1, 1)
             cpu = {"value": r["mlups"], "unit": "MLUPS", "cores": 1, "kind": "reference", "sample": r["sample"],
                    "lbm_only_mlups": r["lbm_only_mlups"], "ib_vertex_updates_per_s": r["vertex_updates_per_s"]}
+        drv = driver_speed() if (world == 1 and not args.no_cpu_baseline) else None
         cfg = workload_config(world) if (nx, ny, nz, args.rbcs) == (128, 1024, 1024, 1250) else {
             "workload": f"custom ({nx * world}x{ny}x{nz}) D3Q19 ForcedPhase lattice, {n_rbc * world} RBC meshes", "parallelism": f"x-slabs x{world}"}
         line = {"metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "ib": ib, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "device_bytes": lat.device_bytes()}
+                "e2e": e2e, "driver_e2e": drv, "gpu_launches": launches, "clocks": clocks, "device_bytes": lat.device_bytes()}
         print(json.dumps(line))
     lat.close()
     if world > 1:

@@ -30,6 +30,15 @@ int bib_device_count(int* count) {
     return 1;
 }
 
+// The halo exchange is issued while the interior-plane launch (a million CTAs) is still queued: without a higher priority the
+// block scheduler would drain that grid first and the exchange would run after it instead of underneath it.
+static cudaError_t create_comm_stream(cudaStream_t* st) {
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = greatest priority
+    if (e != cudaSuccess) return e;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
+}
+
 int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3], int device,
                       bib_domain** out) {
     if (!out || !periodic) { bib_set_error("domain_create: null argument"); return 0; }
@@ -60,7 +69,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
         bib_set_error(buf); delete d; return 0;
     }
     bool ok = bib_cuda_ok(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
-              bib_cuda_ok(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              bib_cuda_ok(create_comm_stream(&d->comm_stream), "cudaStreamCreate") &&
               bib_cuda_ok(cudaEventCreate(&d->ev0), "cudaEventCreate") && bib_cuda_ok(cudaEventCreate(&d->ev1), "cudaEventCreate") &&
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming), "cudaEventCreate") &&
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_compute, cudaEventDisableTiming), "cudaEventCreate");
