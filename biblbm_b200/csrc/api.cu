@@ -108,6 +108,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     if (d->results_dev) cudaFree(d->results_dev);
+    if (d->fflag) cudaFree(d->fflag);
     if (d->guo_nodes) cudaFree(d->guo_nodes);
     if (d->guo_delta) cudaFree(d->guo_delta);
     if (d->guo_vel) cudaFree(d->guo_vel);
@@ -145,6 +146,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_DETERMINISTIC_SPREAD: d->deterministic_spread = value != 0.0; return 1;
         case BIB_OPT_REGULATOR: d->regulator_p = value; return 1;
         case BIB_OPT_SPREAD_MODE: d->spread_mode = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
     bib_set_error("set_option: unknown key");
     return 0;
@@ -153,7 +155,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
 int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
     BIB_ENTER(d);
     if (!box || !cells) { bib_set_error("upload: null argument"); return 0; }
-    d->vel_full_valid = false; d->force_is_body = false;
+    d->vel_full_valid = false; d->force_is_body = false; d->fflag_valid = false;
     if (!lbm_launch_upload(d, box, cells)) return 0;
     return 1;
 }

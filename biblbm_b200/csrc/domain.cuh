@@ -93,6 +93,9 @@ struct bib_domain {
     int band_cap = 0, band_cur = 0;
     bool band_valid[2] = {false, false};
     bool force_is_body = false;           // every cell outside the particle bands holds force_body
+    unsigned* fflag = nullptr;            // 1 bit per cell (storage index): 0 => force == force_body exactly; only meaningful while fflag_valid && force_is_body
+    bool fflag_valid = false;
+    int sparse_force = 1;                 // BIB_OPT_SPARSE_FORCE
     bool interp_since_spread = false;     // the band masks of the last spread are in buffer 1 - band_cur (ib_interpolate ran since)
     double force_body[3] = {0, 0, 0};
     uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags

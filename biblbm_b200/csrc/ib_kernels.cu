@@ -37,6 +37,7 @@ struct Geo {
     const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
     int nv_slot;             // vertices per slot when role != NULL
     const uint8_t* kind;     // cell kinds (NULL = all bulk)
+    unsigned* fflag;         // force-differs-from-body flags (1 bit per cell), set by every atomic spread write; NULL = not maintained
     int plates;              // fsi::Boundary kind: 0 none, 1 ParallelPlatesBoundary (walls at y = py0, py1; src/fsi/Boundary.h:300-365),
     double py0, py1, prad;   //   2 PipeBoundary along x with axis (y, z) = (py0, py1) and radius prad (src/fsi/Boundary.h:131-253)
 };
@@ -265,6 +266,7 @@ __device__ __forceinline__ void d_general_spread(const Geo& g, double* force, co
                     const double val = dirac_xyz * F[c];
                     if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
                 }
+                if (atomic && g.fflag) atomicOr(&g.fflag[c0 >> 5], 1u << (c0 & 31));
             }
         }
     }
@@ -299,6 +301,7 @@ __device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, con
                 const double val = w * F[c];
                 if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
             }
+            if (atomic && g.fflag) atomicOr(&g.fflag[c0 >> 5], 1u << (c0 & 31));
         }
     } else {
         for (int i = x0; i <= x0 + 2; ++i) {
@@ -318,6 +321,7 @@ __device__ __forceinline__ void d_spread_vertex(const Geo& g, double* force, con
                         const double val = dirac_xyz * F[c];
                         if (atomic) atomicAdd(force + c * g.vol + c0, val); else force[c * g.vol + c0] += val;
                     }
+                    if (atomic && g.fflag) atomicOr(&g.fflag[c0 >> 5], 1u << (c0 & 31));
                 }
             }
         }
@@ -1424,6 +1428,7 @@ __device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int tot
                     const long long c0 = d_cell(g, i2, j2, k2);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) atomicAdd(force + c * g.vol + c0, w * F[c]);
+                    if (g.fflag) atomicOr(&g.fflag[c0 >> 5], 1u << (c0 & 31));
                 }
             }
         }
@@ -1461,12 +1466,24 @@ __global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const
         } else d_tile_pass(g, b, total, s_tile, force, pr, false, F);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        const double fx = s_tile[t], fy = s_tile[total + t], fz = s_tile[2 * total + t];
-        if (fx == 0.0 && fy == 0.0 && fz == 0.0) continue;
-        long long idx;
-        if (!d_band_cell(g, b, t, idx)) continue;
-        atomicAdd(force + idx, fx); atomicAdd(force + g.vol + idx, fy); atomicAdd(force + 2 * g.vol + idx, fz);
+    // flush: one global reduction per touched cell; the force flags of cells sharing a 32-cell word are OR-ed inside the warp first
+    for (int t0 = 0; t0 < total; t0 += blockDim.x) {
+        const int t = t0 + threadIdx.x;
+        long long idx = -1;
+        if (t < total) {
+            const double fx = s_tile[t], fy = s_tile[total + t], fz = s_tile[2 * total + t];
+            long long i2;
+            if (!(fx == 0.0 && fy == 0.0 && fz == 0.0) && d_band_cell(g, b, t, i2)) {
+                idx = i2;
+                atomicAdd(force + idx, fx); atomicAdd(force + g.vol + idx, fy); atomicAdd(force + 2 * g.vol + idx, fz);
+            }
+        }
+        if (g.fflag) {
+            const long long word = idx >= 0 ? (idx >> 5) : -1 - (long long)(threadIdx.x & 31);      // invalid lanes get unique keys
+            const unsigned grp = __match_any_sync(0xffffffffu, word);
+            const unsigned bits = __reduce_or_sync(grp, idx >= 0 ? (1u << (idx & 31)) : 0u);
+            if (idx >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) atomicOr(&g.fflag[word], bits);
+        }
     }
 }
 
@@ -1477,6 +1494,7 @@ Geo make_geo(const bib_domain* d) {
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
     g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
     g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1; g.prad = d->pipe_radius; g.kind = d->kind;
+    g.fflag = (d->sparse_force && d->fflag_valid && !d->deterministic_spread) ? d->fflag : nullptr;
     return g;
 }
 
@@ -1981,6 +1999,7 @@ int ib_forces_and_spread(bib_domain* d) {
     }
     if (d->pp_pot.type != 0 && !ib_pp_forces(d)) return 0;   // after every particle's own forces (_forces.hh:300-302)
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
+    if (d->deterministic_spread) d->fflag_valid = false;
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
     else {

@@ -25,6 +25,10 @@ struct LbmParams {
     const double* __restrict__ force;
     const uint8_t* __restrict__ phase;
     const uint8_t* __restrict__ kind;
+    // sparse force field: when fflag != NULL a cell whose bit is 0 carries exactly the uniform body force (bfx, bfy, bfz) and its
+    // three force components are NOT read (24 of the 329 compulsory bytes per cell; only the cells the IB spread touched are flagged)
+    const unsigned* __restrict__ fflag;
+    double bfx, bfy, bfz;
     int nx, ny, nz;
     long long plane, vol;
     double omega0, omega1;
@@ -200,7 +204,8 @@ __global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
     double f[BIB_Q];
 #pragma unroll
     for (int i = 0; i < BIB_Q; ++i) f[i] = __ldg(p.fin + (long long)i * p.vol + idx);
-    const double Fx = __ldg(p.force + idx), Fy = __ldg(p.force + p.vol + idx), Fz = __ldg(p.force + 2 * p.vol + idx);
+    double Fx = p.bfx, Fy = p.bfy, Fz = p.bfz;
+    if (!p.fflag || ((__ldg(p.fflag + (idx >> 5)) >> (idx & 31)) & 1u)) { Fx = __ldg(p.force + idx); Fy = __ldg(p.force + p.vol + idx); Fz = __ldg(p.force + 2 * p.vol + idx); }
     const double c = (double)(__ldg(p.phase + idx) & 1);
     const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
     d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega0, p.omega1);
@@ -262,7 +267,8 @@ __global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
     double f[BIB_Q];
 #pragma unroll
     for (int i = 0; i < BIB_Q; ++i) f[i] = __ldg(p.fin + (long long)i * p.vol + idx);
-    const double Fx = __ldg(p.force + idx), Fy = __ldg(p.force + p.vol + idx), Fz = __ldg(p.force + 2 * p.vol + idx);
+    double Fx = p.bfx, Fy = p.bfy, Fz = p.bfz;
+    if (!p.fflag || ((__ldg(p.fflag + (idx >> 5)) >> (idx & 31)) & 1u)) { Fx = __ldg(p.force + idx); Fy = __ldg(p.force + p.vol + idx); Fz = __ldg(p.force + 2 * p.vol + idx); }
     const double c = (double)(__ldg(p.phase + idx) & 1);
     const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
     d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega1, p.omega0);   // swapped
@@ -485,6 +491,9 @@ static LbmParams make_params(bib_domain* d) {
     LbmParams p;
     p.fin = d->f[d->cur]; p.fout = d->f[1 - d->cur];
     p.force = d->force; p.phase = d->phase; p.kind = d->kind;
+    const bool sparse = d->sparse_force && d->fflag && d->fflag_valid && d->force_is_body;
+    p.fflag = sparse ? d->fflag : nullptr;
+    p.bfx = d->force_body[0]; p.bfy = d->force_body[1]; p.bfz = d->force_body[2];
     p.nx = d->nx; p.ny = d->ny; p.nz = d->nz;
     p.plane = (long long)d->plane; p.vol = (long long)d->vol;
     p.omega0 = d->omega0; p.omega1 = d->omega1;
@@ -741,6 +750,13 @@ int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double f
                                                                                   (long long)d->plane, (long long)d->vol, d->nz, fx, fy, fz);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
+    const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    if (full && d->sparse_force) {          // every cell now holds the body force: all flags off
+        const size_t words = (d->vol + 31) / 32;
+        if (!d->fflag) { BIB_CHECK(cudaMalloc(&d->fflag, words * sizeof(unsigned))); d->bytes += (long long)(words * sizeof(unsigned)); }
+        BIB_CHECK(cudaMemsetAsync(d->fflag, 0, words * sizeof(unsigned), d->stream));
+        d->fflag_valid = true;
+    } else d->fflag_valid = false;
     return 1;
 }
 

@@ -44,8 +44,10 @@ enum {
     BIB_OPT_ENVELOPE_SWAP = 1,       /* 1 (default): reproduce the reference's periodic-envelope (omega,omega_inner) swap, see DESIGN.md */
     BIB_OPT_DETERMINISTIC_SPREAD = 2,/* 1: spread forces in the reference's vertex order (slow, bit-exact); 0 (default): fp64 atomics */
     BIB_OPT_REGULATOR = 3,           /* enable ParticlePositionRegulator (value = p, then target x,y,z via bib_ib_set_regulator) */
-    BIB_OPT_SPREAD_MODE = 4          /* 0 (default): per-particle shared-memory tile staging, one global fp64 reduction per touched cell;
+    BIB_OPT_SPREAD_MODE = 4,         /* 0 (default): per-particle shared-memory tile staging, one global fp64 reduction per touched cell;
                                         1: one global fp64 atomic per stencil point (81 per vertex) */
+    BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
+                                        force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
 };
 
 const char* bib_last_error(void);

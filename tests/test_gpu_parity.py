@@ -287,6 +287,28 @@ def test_particle_particle_force_vs_oracle(orc, rbc):
         assert np.abs((got - base) - want).max() <= 1e-12 * np.abs(want).max()
 
 
+def test_sparse_force_field_equals_dense(rbc):
+    """The lattice kernel skips the force read of cells flagged as 'still the uniform body force' (BIB_OPT_SPARSE_FORCE, default on).
+    On a real coupled state (production spread, band resets, particles across periodic faces) one collideAndStream in sparse mode
+    must give exactly the populations of a dense-mode step on the same state."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    body = np.array([1e-6, 0.0, -2e-6])
+    lat = run_ib_case(g, shape, params, deterministic=False)
+    lat.step(body, n=4)
+    state = lat.download()
+    assert np.count_nonzero(np.abs(state[..., 19:22] - body).max(-1) > 0) > 500          # the spread left its mark on the force field
+    lat.collideAndStream()
+    sparse = lat.download()
+    dense_lat = make_lattice(state, g["per"], float(g["omega"]), float(g["omega_inner"]), {bib.OPT_SPARSE_FORCE: 0.0})
+    dense_lat.collideAndStream()
+    assert np.array_equal(sparse[..., :19], dense_lat.download()[..., :19])
+    # and whole coupled runs agree within the spread's reordering noise
+    a = run_ib_case(g, shape, params, deterministic=False); a.step(body, n=6)
+    b = run_ib_case(g, shape, params, deterministic=False); b.set_option(bib.OPT_SPARSE_FORCE, 0.0); b.step(body, n=6)
+    assert kit.rel_err(a.download()[..., :19], b.download()[..., :19]) <= 1e-13
+
+
 def test_async_result_readback_matches_golden(rbc):
     """bib_ib_results_download_async: the read-back of step s overlaps step s+1 and still delivers step s, bit for bit."""
     import torch
