@@ -26,15 +26,29 @@ def main():
     centers = [(nxl - 0.4, 11.7, 10.6), (gx - 1.3, 12.4, 11.2), (10.2, 11.1, 10.9)]
     if world > 2:
         centers.append((2 * nxl + 3.1, 12.2, 11.0))
+    # IB_CHECK_CASE=channel: the rbcs_in_channel set-up (BASELINE configs[3]) in miniature -- no-slip velocity planes at y = 0 / ny-1,
+    # ParallelPlatesBoundary for the particles, body-force driven flow, a dense row of RBCs along x crossing every slab face
+    channel = os.environ.get("IB_CHECK_CASE", "periodic") == "channel"
+    per = (True, False, True) if channel else (True, True, True)
+    if channel:
+        centers = [(4.0 + 8.1 * k, 6.0 + 11.5 * (k % 2) + 0.3 * (k % 3), 10.4 + 0.5 * (k % 4)) for k in range(int(gx / 8.1))]
     pos = kit.place_particles(rbc_pos, centers, seed=9)
     body = (4e-5, 0.0, 1e-5)
-    u0 = (0.05, 0.0, 0.004)
+    u0 = (0.05, 0.0, 0.004) if not channel else (0.0, 0.0, 0.0)
 
-    lat = bib.Lattice(nxl, ny, nz, 1.0, 1 / 3, periodic=(True, True, True), device=local)
+    def configure(l, n_x):
+        if channel:
+            zero = np.zeros((n_x, nz, 3))
+            l.addVelocityBoundary((0, n_x - 1, 0, 0, 0, nz - 1), 1, -1, zero)
+            l.addVelocityBoundary((0, n_x - 1, ny - 1, ny - 1, 0, nz - 1), 1, +1, zero)
+            l.set_boundary(0.0, float(ny - 1))
+
+    lat = bib.Lattice(nxl, ny, nz, 1.0, 1 / 3, periodic=per, device=local)
     uid = [bib.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     lat.comm_init(rank, world, uid[0])
     lat.initializeAtEquilibrium(1.0, u0)
+    configure(lat, nxl)
     sid = lat.register_shape(shape.verts, shape.tris)
     lat.add_particles(sid, params, pos)          # same global list on every rank
     lat.step(body, n=steps)
@@ -55,8 +69,9 @@ def main():
                 assert g not in owned, f"particle {g} owned twice"
                 owned[g] = (r, v)
         assert sorted(owned) == list(range(len(centers))), f"owners: {sorted(owned)}"
-        ref = bib.Lattice(gx, ny, nz, 1.0, 1 / 3, periodic=(True, True, True), device=local)
+        ref = bib.Lattice(gx, ny, nz, 1.0, 1 / 3, periodic=per, device=local)
         ref.initializeAtEquilibrium(1.0, u0)
+        configure(ref, gx)
         rs = ref.register_shape(shape.verts, shape.tris)
         ref.add_particles(rs, params, pos)
         ref.step(body, n=steps)
@@ -69,7 +84,7 @@ def main():
         ph = np.array_equal(got[..., 22], rc[..., 22])
         owners = {g: owned[g][0] for g in sorted(owned)}
         com = {g: float(rv[g][:, 0].mean()) for g in sorted(owned)}
-        print(f"world={world} steps={steps}: pos {e_pos:.2e} vel {e_vel:.2e} pop {e_pop:.2e} phase_equal={ph} owners={owners} com_x={com}")
+        print(f"case={'channel' if channel else 'periodic'} particles={len(centers)} world={world} steps={steps}: pos {e_pos:.2e} vel {e_vel:.2e} pop {e_pop:.2e} phase_equal={ph} owners={owners} com_x={com}")
         ok = e_pos <= 1e-9 and e_pop <= 1e-9 and ph
         ref.close()
     lat.close()
