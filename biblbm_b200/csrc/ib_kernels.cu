@@ -1686,7 +1686,7 @@ static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move, co
     return 1;
 }
 
-int ms_create(bib_domain* d, int nv, int n_global);
+int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint);
 int ms_set_initial(bib_domain* d, const std::vector<int>& owned_gids);
 int ms_exchange_positions(bib_domain* d);
 int ms_exchange_velocities(bib_domain* d);
@@ -1704,14 +1704,14 @@ int ib_update_all(bib_domain* d, int do_move) {
 static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
     if (!d->groups.empty()) { bib_set_error("particles_add: multi-slab domains take one particle group (one call)"); return 0; }
     const ShapeDev& s = d->shapes[shape_id];
-    if (!ms_create(d, s.nv, n)) return 0;
-    MultiSlabIB* m = d->ms;
-    if (!grow_particles(d, (long long)m->cap * s.nv, m->cap)) return 0;
     // centre of mass exactly as DeformableParticle3D::update computes it (sequential, area weighted), then the periodic remap
     std::vector<int> owned;
+    double max_extent = 0.0;
     for (int p = 0; p < n; ++p) {
         const double* P = positions + (size_t)p * s.nv * 3;
-        double area = 0, cx = 0;
+        double area = 0, cx = 0, lo = P[0], hi = P[0];
+        for (int v = 0; v < s.nv; ++v) { lo = std::min(lo, P[3 * v]); hi = std::max(hi, P[3 * v]); }
+        max_extent = std::max(max_extent, hi - lo);
         for (int t = 0; t < s.nt; ++t) {
             const double *v0 = P + 3 * s.h_tris[3 * t], *v1 = P + 3 * s.h_tris[3 * t + 1], *v2 = P + 3 * s.h_tris[3 * t + 2];
             const double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
@@ -1725,6 +1725,16 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
         if (d->per[0]) { const double L = (double)d->gnx; x = x - L * std::floor((x - (0.0 - 0.5)) * (1. / L)); }
         if (x >= (double)d->x_offset - 0.5 && x < (double)(d->x_offset + d->nx) - 0.5) owned.push_back(p);
     }
+    // slot / exchange capacities from the geometry: a particle is mirrored on a neighbour while its box (+3 cells) reaches over the
+    // face, i.e. a fraction (extent + 6) / slab width of the owned ones per side; generous safety factors, overflow is detected
+    const double frac = std::min(1.0, (max_extent + 8.0) / (double)d->nx);
+    // (the exchange capacity fixes the NCCL message size, so it must come out identical on every rank: global quantities only)
+    const double base = 1.25 * (double)n / d->n_ranks;
+    const int xcap_hint = (int)(base * frac * 2.0) + 32;
+    const int cap_hint = std::max((int)(base * (1.0 + 2.0 * frac) * 1.3) + 64, (int)owned.size() + 2 * xcap_hint);
+    if (!ms_create(d, s.nv, n, cap_hint, xcap_hint)) return 0;
+    MultiSlabIB* m = d->ms;
+    if (!grow_particles(d, (long long)m->cap * s.nv, m->cap)) return 0;
     if ((int)owned.size() > m->cap) { bib_set_error("particles_add: more owned particles than slots"); return 0; }
     const long long capv = d->cap_vertices;
     std::vector<double> soa((size_t)owned.size() * s.nv * 3);

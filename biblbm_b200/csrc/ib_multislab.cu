@@ -161,11 +161,12 @@ int ms_exchange(bib_domain* d, int kind, const double* src, double* dst) {
 
 int ib_update_all(bib_domain* d, int do_move);
 
-int ms_create(bib_domain* d, int nv, int n_global) {
+int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint) {
     MultiSlabIB* m = new MultiSlabIB();
     m->nv = nv; m->n_global = n_global;
-    m->cap = n_global <= 4096 ? n_global : (int)std::min<long long>(n_global, (long long)(2.5 * n_global / d->n_ranks) + 256);
-    m->xcap = n_global <= 4096 ? m->cap : std::max(64, m->cap / 4);
+    // small problems: every slab can hold (and exchange) everything; otherwise the geometric estimates of the caller
+    m->cap = n_global <= 1024 ? n_global : std::min(n_global, std::max(cap_hint, 256));
+    m->xcap = n_global <= 1024 ? m->cap : std::min(m->cap, std::max(xcap_hint, 64));
     m->entry = 2 + 3 * (size_t)nv;
     const size_t nd = 1 + (size_t)m->xcap * m->entry;
     bool ok = bib_cuda_ok(cudaMalloc(&m->role, m->cap * sizeof(int)), "cudaMalloc") && bib_cuda_ok(cudaMalloc(&m->gid_of, m->cap * sizeof(int)), "cudaMalloc") &&
