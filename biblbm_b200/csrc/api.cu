@@ -108,6 +108,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     if (d->results_dev) cudaFree(d->results_dev);
+    if (d->step_graph) cudaGraphExecDestroy(d->step_graph);
     if (d->fflag) cudaFree(d->fflag);
     if (d->guo_nodes) cudaFree(d->guo_nodes);
     if (d->guo_delta) cudaFree(d->guo_delta);
@@ -137,7 +138,10 @@ int bib_domain_destroy(bib_domain* d) {
     return 1;
 }
 
-#define BIB_ENTER(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
+// BIB_ENTER: entry points that may change the configuration or the state outside the stepping loop (they invalidate the captured
+// step graph); BIB_ENTER_RO: stepping itself, synchronisation, timing and read-only downloads.
+#define BIB_ENTER_RO(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
+#define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; } while (0)
 
 int bib_domain_set_option(bib_domain* d, int key, double value) {
     BIB_ENTER(d);
@@ -146,6 +150,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_DETERMINISTIC_SPREAD: d->deterministic_spread = value != 0.0; return 1;
         case BIB_OPT_REGULATOR: d->regulator_p = value; return 1;
         case BIB_OPT_SPREAD_MODE: d->spread_mode = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_STEP_GRAPH: d->use_graph = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
     bib_set_error("set_option: unknown key");
@@ -160,7 +165,7 @@ int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
     return 1;
 }
 int bib_domain_download(bib_domain* d, const int box[6], double* cells) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!box || !cells) { bib_set_error("download: null argument"); return 0; }
     return lbm_launch_download(d, box, cells);
 }
@@ -266,7 +271,7 @@ int bib_ib_rigid_particles_add(bib_domain* d, int shape_id, const double* inerti
     return ib_rigid_add(d, shape_id, inertia9, shape_volume, n, state17);
 }
 int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, double* state19) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (count > 0 && !state19) { bib_set_error("rigid_state_download: null argument"); return 0; }
     return ib_rigid_download(d, first_particle, count, state19);
 }
@@ -307,7 +312,7 @@ int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta
     return set_potential(d->pp_pot, type, r_min, beta, strength, "set_pp_interaction");
 }
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (n_particles) *n_particles = d->n_particles;
     if (n_vertices) *n_vertices = d->n_vertices;
     return 1;
@@ -324,7 +329,7 @@ int bib_ib_step(bib_domain* d) {
     return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (count > 0 && !vertices9) { bib_set_error("vertices_download: null argument"); return 0; }
     return ib_vertices_download(d, first_vertex, count, vertices9);
 }
@@ -334,12 +339,12 @@ int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long coun
     return ib_vertices_upload(d, first_vertex, count, vertices9);
 }
 int bib_ib_local_slots(bib_domain* d, int* global_ids, int* roles, int capacity, int* n_slots) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!global_ids || !roles || !n_slots) { bib_set_error("local_slots: null argument"); return 0; }
     return ib_local_slots(d, global_ids, roles, capacity, n_slots);
 }
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (count > 0 && !scalars11) { bib_set_error("particle_scalars_download: null argument"); return 0; }
     return ib_scalars_download(d, first_particle, count, scalars11);
 }
@@ -350,32 +355,72 @@ int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count,
     return ib_scalars_upload(d, first_particle, count, scalars11);
 }
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!vertices9 || !scalars11) { bib_set_error("results_download_async: null argument"); return 0; }
     return ib_results_download_async(d, vertices9, scalars11);
 }
-int bib_ib_results_wait(bib_domain* d) { BIB_ENTER(d); return ib_results_wait(d); }
+int bib_ib_results_wait(bib_domain* d) { BIB_ENTER_RO(d); return ib_results_wait(d); }
 
 // One driver step: the velocity the IB interpolates is u = j(f^t)/rho + F^{t-1}/2 evaluated on demand from the current
 // populations and the force field still holding last step's total force, so the dense
 // computeVelocity pass of the reference is not needed; then F := body, IB, collide-and-stream.
-int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
-    BIB_ENTER(d);
+static int step_once(bib_domain* d, double body_fx, double body_fy, double body_fz) {
     const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
-    for (int s = 0; s < n_steps; ++s) {
-        if (!ib_interpolate(d)) return 0;
-        // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
-        if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {
-            if (!ib_band_reset(d, body_fx, body_fy, body_fz)) return 0;
-        } else {
-            if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
-            d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
-        }
-        if (!ib_forces_and_spread(d)) return 0;
-        if (!ib_move_and_voxelize(d)) return 0;
-        d->vel_full_valid = false;
-        if (!lbm_launch_collide_stream(d)) return 0;
+    if (!ib_interpolate(d)) return 0;
+    // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
+    if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {
+        if (!ib_band_reset(d, body_fx, body_fy, body_fz)) return 0;
+    } else {
+        if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
+        d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
     }
+    if (!ib_forces_and_spread(d)) return 0;
+    if (!ib_move_and_voxelize(d)) return 0;
+    d->vel_full_valid = false;
+    return lbm_launch_collide_stream(d);
+}
+
+// Small lattices (the reference's own driver configurations: 61^3 ... 97^3 cells, one to a few dozen particles) are launch-bound:
+// ~15 kernels of a few microseconds each per step. In steady state the kernel sequence of a step is fixed and all its arguments
+// repeat with period 2 (A/B population buffers, double-buffered band masks), so two consecutive steps are captured once into a CUDA
+// graph and replayed. Any configuration-changing entry point invalidates the graph (BIB_ENTER). Single-slab domains only (the
+// multi-slab step interleaves NCCL calls on two streams).
+int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
+    BIB_ENTER_RO(d);
+    int s = 0;
+    const bool same_body = d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz;
+    if (d->use_graph && d->n_ranks == 1 && n_steps >= 2 && (d->step_graph == nullptr || d->graph_dirty || !same_body) && n_steps >= 6) {
+        if (d->step_graph) { cudaGraphExecDestroy(d->step_graph); d->step_graph = nullptr; }
+        for (; s < 2; ++s) if (!step_once(d, body_fx, body_fy, body_fz)) return 0;      // reach the steady state (allocations, masks, flags)
+        const long long l0 = d->launches;
+        d->graph_cur = d->cur; d->graph_band_cur = d->band_cur;      // the buffers the captured pair of steps starts from
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const bool ok = step_once(d, body_fx, body_fy, body_fz) && step_once(d, body_fx, body_fy, body_fz);
+            const cudaError_t e = cudaStreamEndCapture(d->stream, &graph);
+            d->graph_launches = d->launches - l0;
+            d->launches = l0;                                  // captured, not executed
+            if (ok && e == cudaSuccess && graph && cudaGraphInstantiate(&d->step_graph, graph, 0) == cudaSuccess) {
+                d->graph_dirty = false;
+                d->graph_body[0] = body_fx; d->graph_body[1] = body_fy; d->graph_body[2] = body_fz;
+            } else {
+                d->step_graph = nullptr;
+                d->use_graph = 0;                              // something in this configuration is not capturable: plain launches from now on
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+        }
+    }
+    if (d->use_graph && d->n_ranks == 1 && d->step_graph && !d->graph_dirty &&
+        d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz) {
+        // the graph starts from fixed A/B buffers: after an odd number of steps one plain step realigns the parity
+        if (n_steps - s >= 3 && d->cur != d->graph_cur) { if (!step_once(d, body_fx, body_fy, body_fz)) return 0; ++s; }
+        for (; n_steps - s >= 2 && d->cur == d->graph_cur && d->band_cur == d->graph_band_cur; s += 2) {
+            BIB_CHECK(cudaGraphLaunch(d->step_graph, d->stream));
+            d->launches += d->graph_launches;
+        }
+    }
+    for (; s < n_steps; ++s) if (!step_once(d, body_fx, body_fy, body_fz)) return 0;
     return 1;
 }
 
@@ -391,14 +436,14 @@ int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_12
 }
 
 int bib_sync(bib_domain* d) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->comm_stream));
     return ms_check_overflow(d);
 }
-int bib_time_begin(bib_domain* d) { BIB_ENTER(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
+int bib_time_begin(bib_domain* d) { BIB_ENTER_RO(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
 int bib_time_end(bib_domain* d, float* milliseconds) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!milliseconds) { bib_set_error("time_end: null argument"); return 0; }
     BIB_CHECK(cudaEventRecord(d->ev1, d->stream));
     BIB_CHECK(cudaEventSynchronize(d->ev1));
@@ -406,13 +451,13 @@ int bib_time_end(bib_domain* d, float* milliseconds) {
     return 1;
 }
 int bib_kernel_launch_count(bib_domain* d, long long* launches) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!launches) { bib_set_error("kernel_launch_count: null argument"); return 0; }
     *launches = d->launches;
     return 1;
 }
 int bib_device_memory_bytes(bib_domain* d, long long* bytes) {
-    BIB_ENTER(d);
+    BIB_ENTER_RO(d);
     if (!bytes) { bib_set_error("device_memory_bytes: null argument"); return 0; }
     *bytes = d->bytes;
     return 1;

@@ -103,6 +103,8 @@ struct bib_domain {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
     long long launches = 0;
+    // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
+    cudaGraphExec_t step_graph = nullptr; bool graph_dirty = true; int use_graph = 1; long long graph_launches = 0; double graph_body[3] = {0, 0, 0}; int graph_cur = 0, graph_band_cur = 0;
     long long bytes = 0;
     // options
     int envelope_swap = 1;

@@ -1996,7 +1996,8 @@ int ib_forces_and_spread(bib_domain* d) {
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
         if (s.nv <= RF_THREADS * RF_VPT) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
-            cudaFuncSetAttribute(k_rbc_forces_elem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+            static size_t sm2_set = 0;
+            if (sm2_set != sm2) { cudaFuncSetAttribute(k_rbc_forces_elem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); sm2_set = sm2; }
             k_rbc_forces_elem<<<gr.count, RF_THREADS, sm2, d->stream>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np);
         } else if (smem <= 200 * 1024) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_rbc_forces_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

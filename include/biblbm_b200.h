@@ -46,6 +46,7 @@ enum {
     BIB_OPT_REGULATOR = 3,           /* enable ParticlePositionRegulator (value = p, then target x,y,z via bib_ib_set_regulator) */
     BIB_OPT_SPREAD_MODE = 4,         /* 0 (default): per-particle shared-memory tile staging, one global fp64 reduction per touched cell;
                                         1: one global fp64 atomic per stencil point (81 per vertex) */
+    BIB_OPT_STEP_GRAPH = 6,          /* 1 (default): bib_step replays a CUDA graph of two consecutive steps on single-slab domains (small lattices are launch-bound) */
     BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
                                         force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
 };

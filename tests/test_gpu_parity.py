@@ -309,6 +309,36 @@ def test_sparse_force_field_equals_dense(rbc):
     assert kit.rel_err(a.download()[..., :19], b.download()[..., :19]) <= 1e-13
 
 
+def test_step_graph_equals_plain_launches(rbc):
+    """bib_step replays a CUDA graph of two consecutive steps (BIB_OPT_STEP_GRAPH): bit-identical to plain launches, also when the call is
+    split, when the body force changes (graph rebuilt) and when a read-only download sits between calls; and faster on a small lattice."""
+    import time
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_in_shear.npz")
+
+    def build(graph, deterministic=1.0):
+        lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: deterministic, bib.OPT_STEP_GRAPH: float(graph)})
+        sid = lat.register_shape(shape.verts, shape.tris)
+        lat.add_particles(sid, params, g["vert_init"][..., :3])
+        lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
+        return lat
+    a, b = build(1), build(0)
+    for lat in (a, b):
+        lat.step((0.0, 0.0, 0.0), n=21)
+        lat.vertices()
+        lat.step((0.0, 0.0, 0.0), n=8)
+        lat.step((1e-6, 0.0, 0.0), n=11)
+    assert np.array_equal(a.vertices(), b.vertices())
+    assert np.array_equal(a.download(), b.download())
+    assert a.launches() == b.launches()
+    t = []
+    for lat in (build(1, 0.0), build(0, 0.0)):         # production spread: the step is launch-bound at this size
+        lat.step((1e-6, 0.0, 0.0), n=50)
+        lat.sync(); t0 = time.perf_counter(); lat.step((1e-6, 0.0, 0.0), n=2000); lat.sync(); t.append(time.perf_counter() - t0)
+    print(f"2000 steps of a 26x24x22 Couette cell + 1 RBC: graph {t[0] / 2:.3f} ms/step, plain launches {t[1] / 2:.3f} ms/step")
+    assert t[0] < t[1]
+
+
 def test_async_result_readback_matches_golden(rbc):
     """bib_ib_results_download_async: the read-back of step s overlaps step s+1 and still delivers step s, bit for bit."""
     import torch
