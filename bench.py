@@ -245,6 +245,7 @@ def ours(args):
         uid = [bib.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         lat.comm_init(rank, world, uid[0])
+    lat.set_option(bib.OPT_FUSED_FACE_SWAP, float(args.face_swap))
     lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
     body = (1e-6, 0.0, 0.0)
     n_rbc = args.rbcs                               # per GPU
@@ -286,7 +287,8 @@ def ours(args):
     mlups = cells_local * world / (ms_step * 1e-3) / 1e6
 
     # ---- dominant kernel alone (collide-and-stream), CUDA events on the launching stream
-    lat.set_option(bib.OPT_ENVELOPE_SWAP, 0.0)      # main kernel only (the periodic-face fix-up kernel is timed in the full step)
+    if args.face_swap != 1:                         # default (1): the periodic-face fix-up is part of k_collide_stream and is timed with it
+        lat.set_option(bib.OPT_ENVELOPE_SWAP, 0.0)  # main kernel only (the separate k_face_swap pass is timed in the full step)
     lat.collideAndStream(2)
     barrier()
     lat.time_begin()
@@ -380,6 +382,7 @@ def main():
     ap.add_argument("--nz", type=int, default=1024)
     ap.add_argument("--rbcs", type=int, default=1250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--face-swap", type=int, default=1, choices=[0, 1, 2], help="BIB_OPT_FUSED_FACE_SWAP (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

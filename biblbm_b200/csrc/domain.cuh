@@ -108,6 +108,7 @@ struct bib_domain {
     long long bytes = 0;
     // options
     int envelope_swap = 1;
+    int fused_face_swap = 1;              // BIB_OPT_FUSED_FACE_SWAP: 0 separate k_face_swap pass, 1 fused for all faces, 2 fused for x/y faces only
     int deterministic_spread = 0;
     int spread_mode = 0;                  // 0 shared-memory tile staging (default), 1 one global atomic per stencil point
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};

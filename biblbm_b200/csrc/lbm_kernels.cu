@@ -38,6 +38,8 @@ struct LbmParams {
     int x_lo_mode, x_hi_mode;
     // planes handled by this launch: x = x_first + blockIdx.z * x_stride (boundary launch: planes 0 and nx-1; interior: 1..nx-2)
     int x_first, x_stride;
+    // fused envelope quirk (SWAP != 0): is this slab's low / high x face a GLOBAL periodic face
+    int swap_x_lo, swap_x_hi;
 };
 
 __constant__ int c_cx[BIB_Q] = {0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0};
@@ -194,8 +196,28 @@ __device__ __forceinline__ void d_push(const LbmParams& p, const Nbr& n, long lo
     p.fout[(long long)I * p.vol + idx + off] = v;
 }
 
-template <bool HAS_KIND, bool HAS_WALLS>
-__global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
+// re-push of population I after the swapped-omega collision: only when it crosses a periodic face (a population that also
+// leaves through a non-periodic face stays bounced from the bulk collision)
+template <int I, bool HAS_WALLS, bool WITH_Z>
+__device__ __forceinline__ void d_push_crossing(const LbmParams& p, const Nbr& n, long long idx, double v, bool sxm, bool sxp, bool sym, bool syp, bool szm, bool szp) {
+    constexpr int cx = (I == 1 || I == 4 || I == 5 || I == 6 || I == 7) ? -1 : ((I == 10 || I == 13 || I == 14 || I == 15 || I == 16) ? 1 : 0);
+    constexpr int cy = (I == 2 || I == 4 || I == 8 || I == 9 || I == 14) ? -1 : ((I == 5 || I == 11 || I == 13 || I == 17 || I == 18) ? 1 : 0);
+    constexpr int cz = (I == 3 || I == 6 || I == 8 || I == 16 || I == 18) ? -1 : ((I == 7 || I == 9 || I == 12 || I == 15 || I == 17) ? 1 : 0);
+    const bool cross = (cx < 0 && sxm) || (cx > 0 && sxp) || (cy < 0 && sym) || (cy > 0 && syp) || (WITH_Z && ((cz < 0 && szm) || (cz > 0 && szp)));
+    if (!cross) return;
+    if (HAS_WALLS) {
+        const bool blocked = (cx < 0 && n.wxm) || (cx > 0 && n.wxp) || (cy < 0 && n.wym) || (cy > 0 && n.wyp) || (cz < 0 && n.wzm) || (cz > 0 && n.wzp);
+        if (blocked) return;
+    }
+    const int off = (cx < 0 ? n.oxm : (cx > 0 ? n.oxp : 0)) + (cy < 0 ? n.oym : (cy > 0 ? n.oyp : 0)) + (cz < 0 ? n.ozm : (cz > 0 ? n.ozp : 0));
+    p.fout[(long long)I * p.vol + idx + off] = v;
+}
+
+// SWAP: 0 = the periodic-face fix-up runs as a separate kernel (k_face_swap); 1 = fused for all faces; 2 = fused for the cells of the
+// x and y faces (whole planes / rows of threads take the tail; they also re-push what crosses z), the cells that lie on a z face only
+// (one lane of two warps per row) stay in k_face_swap.
+template <bool HAS_KIND, bool HAS_WALLS, int SWAP>
+__global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : 5) k_collide_stream(const LbmParams p) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nz) return;
     const int y = blockIdx.y, x = p.x_first + (int)blockIdx.z * p.x_stride;
@@ -208,6 +230,8 @@ __global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
     if (!p.fflag || ((__ldg(p.fflag + (idx >> 5)) >> (idx & 31)) & 1u)) { Fx = __ldg(p.force + idx); Fy = __ldg(p.force + p.vol + idx); Fz = __ldg(p.force + 2 * p.vol + idx); }
     const double c = (double)(__ldg(p.phase + idx) & 1);
     const int kind = HAS_KIND ? (int)__ldg(p.kind + idx) : 0;
+    const bool on_face = SWAP != 0 && (((x == 0) && p.swap_x_lo) || ((x == p.nx - 1) && p.swap_x_hi) || ((y == 0 || y == p.ny - 1) && p.per_y) ||
+                                       (SWAP == 1 && (z == 0 || z == p.nz - 1) && p.per_z));
     d_apply_kind(f, kind, Fx, Fy, Fz, c, p.omega0, p.omega1);
 
     const Nbr n = d_neighbours<HAS_WALLS>(p, x, y, z);
@@ -221,6 +245,65 @@ __global__ void __launch_bounds__(128) k_collide_stream(const LbmParams p) {
     d_push<7, HAS_WALLS>(p, n, idx, f[7]);   d_push<16, HAS_WALLS>(p, n, idx, f[16]);
     d_push<8, HAS_WALLS>(p, n, idx, f[8]);   d_push<17, HAS_WALLS>(p, n, idx, f[17]);
     d_push<9, HAS_WALLS>(p, n, idx, f[9]);   d_push<18, HAS_WALLS>(p, n, idx, f[18]);
+
+    if (SWAP != 0) {
+        // Envelope quirk fused (see k_face_swap below): a cell on a periodic face collides a second time with (omega, omega_inner)
+        // swapped and re-pushes only the populations that cross such a face. Same thread, same addresses as the pushes above, so
+        // program order makes the second value the one that stays.
+        // Everything in the tail is re-derived from re-read thread coordinates (loads hit L1/L2): keeping the pre-collision values, the
+        // force, the coordinates or the neighbour offsets alive across the pushes would cost EVERY thread registers for the sake of
+        // the few face cells.
+        if (on_face) {
+            unsigned tid, bx, by, bz;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+            asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+            asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+            asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+            const int z2 = (int)(bx * blockDim.x + tid), y2 = (int)by, x2 = p.x_first + (int)bz * p.x_stride;
+            const bool sxm = (x2 == 0) && p.swap_x_lo, sxp = (x2 == p.nx - 1) && p.swap_x_hi;
+            const bool sym = (y2 == 0) && p.per_y, syp = (y2 == p.ny - 1) && p.per_y;
+            const bool szm = (z2 == 0) && p.per_z, szp = (z2 == p.nz - 1) && p.per_z;
+            const long long idx2 = (long long)(x2 + 1) * p.plane + (long long)y2 * p.nz + z2;
+            double g[BIB_Q];
+#pragma unroll
+            for (int i = 0; i < BIB_Q; ++i) g[i] = __ldcg(p.fin + (long long)i * p.vol + idx2);
+            double Gx = p.bfx, Gy = p.bfy, Gz = p.bfz;
+            if (!p.fflag || ((__ldcg(p.fflag + (idx2 >> 5)) >> (idx2 & 31)) & 1u)) { Gx = __ldcg(p.force + idx2); Gy = __ldcg(p.force + p.vol + idx2); Gz = __ldcg(p.force + 2 * p.vol + idx2); }
+            const double c2 = (double)(__ldcg(p.phase + idx2) & 1);
+            const int kind2 = HAS_KIND ? (int)__ldcg(p.kind + idx2) : 0;
+            const Nbr m = d_neighbours<HAS_WALLS>(p, x2, y2, z2);
+            if (SWAP == 1 && !(sxm || sxp || sym || syp)) {
+                // z faces only (one lane of the first / last warp of every row): just the five populations that cross are needed, the
+                // rest of the second collision is dead code in these two branches
+                if (szm) {
+                    d_apply_kind(g, kind2, Gx, Gy, Gz, c2, p.omega1, p.omega0);
+                    d_push_crossing<3, HAS_WALLS, true>(p, m, idx2, g[3], false, false, false, false, true, false);
+                    d_push_crossing<6, HAS_WALLS, true>(p, m, idx2, g[6], false, false, false, false, true, false);
+                    d_push_crossing<8, HAS_WALLS, true>(p, m, idx2, g[8], false, false, false, false, true, false);
+                    d_push_crossing<16, HAS_WALLS, true>(p, m, idx2, g[16], false, false, false, false, true, false);
+                    d_push_crossing<18, HAS_WALLS, true>(p, m, idx2, g[18], false, false, false, false, true, false);
+                } else {
+                    d_apply_kind(g, kind2, Gx, Gy, Gz, c2, p.omega1, p.omega0);
+                    d_push_crossing<7, HAS_WALLS, true>(p, m, idx2, g[7], false, false, false, false, false, true);
+                    d_push_crossing<9, HAS_WALLS, true>(p, m, idx2, g[9], false, false, false, false, false, true);
+                    d_push_crossing<12, HAS_WALLS, true>(p, m, idx2, g[12], false, false, false, false, false, true);
+                    d_push_crossing<15, HAS_WALLS, true>(p, m, idx2, g[15], false, false, false, false, false, true);
+                    d_push_crossing<17, HAS_WALLS, true>(p, m, idx2, g[17], false, false, false, false, false, true);
+                }
+                return;
+            }
+            d_apply_kind(g, kind2, Gx, Gy, Gz, c2, p.omega1, p.omega0);
+            d_push_crossing<1, HAS_WALLS, true>(p, m, idx2, g[1], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<10, HAS_WALLS, true>(p, m, idx2, g[10], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<2, HAS_WALLS, true>(p, m, idx2, g[2], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<11, HAS_WALLS, true>(p, m, idx2, g[11], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<3, HAS_WALLS, true>(p, m, idx2, g[3], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<12, HAS_WALLS, true>(p, m, idx2, g[12], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<4, HAS_WALLS, true>(p, m, idx2, g[4], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<13, HAS_WALLS, true>(p, m, idx2, g[13], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<5, HAS_WALLS, true>(p, m, idx2, g[5], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<14, HAS_WALLS, true>(p, m, idx2, g[14], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<6, HAS_WALLS, true>(p, m, idx2, g[6], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<15, HAS_WALLS, true>(p, m, idx2, g[15], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<7, HAS_WALLS, true>(p, m, idx2, g[7], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<16, HAS_WALLS, true>(p, m, idx2, g[16], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<8, HAS_WALLS, true>(p, m, idx2, g[8], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<17, HAS_WALLS, true>(p, m, idx2, g[17], sxm, sxp, sym, syp, szm, szp);
+            d_push_crossing<9, HAS_WALLS, true>(p, m, idx2, g[9], sxm, sxp, sym, syp, szm, szp);   d_push_crossing<18, HAS_WALLS, true>(p, m, idx2, g[18], sxm, sxp, sym, syp, szm, szp);
+        }
+    }
 }
 
 // Envelope quirk: populations that cross a periodic face come from a collision with (omega, omega_inner) swapped
@@ -505,20 +588,34 @@ static LbmParams make_params(bib_domain* d) {
         p.x_hi_mode = (last && !d->per[0]) ? 2 : 0;
     }
     p.x_first = 0; p.x_stride = 1;
+    p.swap_x_lo = d->per[0] && first; p.swap_x_hi = d->per[0] && last;
     return p;
 }
 
+// 0: separate k_face_swap launches; 1: fused into k_collide_stream for all faces; 2: x and y faces fused, z faces separate
+static int fused_swap_mode(const bib_domain* d) {
+    if (!d->envelope_swap || d->omega0 == d->omega1) return 0;      // equal rates: the swap changes nothing, nothing to fuse
+    if (!(d->per[0] || d->per[1] || d->per[2])) return 0;
+    return d->fused_face_swap;
+}
 static void launch_main(bib_domain* d, const LbmParams& p, int n_planes, cudaStream_t st) {
     if (n_planes <= 0) return;
     int bs = d->nz >= 128 ? 128 : ((d->nz + 31) / 32) * 32;
     dim3 grid((d->nz + bs - 1) / bs, d->ny, n_planes);
     const bool walls = p.x_lo_mode == 2 || p.x_hi_mode == 2 || !p.per_y || !p.per_z;
-    if (d->kind) { if (walls) k_collide_stream<true, true><<<grid, bs, 0, st>>>(p); else k_collide_stream<true, false><<<grid, bs, 0, st>>>(p); }
-    else { if (walls) k_collide_stream<false, true><<<grid, bs, 0, st>>>(p); else k_collide_stream<false, false><<<grid, bs, 0, st>>>(p); }
+    const int swap = fused_swap_mode(d);
+#define BIB_LAUNCH_CS(K, W) do { if (swap == 1) k_collide_stream<K, W, 1><<<grid, bs, 0, st>>>(p); else if (swap == 2) k_collide_stream<K, W, 2><<<grid, bs, 0, st>>>(p); \
+                                 else k_collide_stream<K, W, 0><<<grid, bs, 0, st>>>(p); } while (0)
+    if (d->kind) { if (walls) BIB_LAUNCH_CS(true, true); else BIB_LAUNCH_CS(true, false); }
+    else { if (walls) BIB_LAUNCH_CS(false, true); else BIB_LAUNCH_CS(false, false); }
+#undef BIB_LAUNCH_CS
     d->launches++;
 }
 static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x_select, cudaStream_t st) {
-    if (!d->envelope_swap) return;
+    if (!d->envelope_swap || d->omega0 == d->omega1) return;        // equal rates: the swapped collision is the same collision
+    const int fused = fused_swap_mode(d);
+    if (fused == 1) return;
+    if (fused == 2) face_mask &= 48;                                // the z faces only
     FaceParams q; q.p = p; q.x_select = x_select;
     const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
     q.swap_x_lo = d->per[0] && first; q.swap_x_hi = d->per[0] && last;

@@ -55,15 +55,21 @@ def test_collide_and_stream_vs_golden(name):
 
 
 @pytest.mark.parametrize("per", [(1, 1, 1), (1, 0, 1), (0, 0, 0), (0, 1, 0)])
-@pytest.mark.parametrize("swap", [True, False])
+@pytest.mark.parametrize("swap", [True, False, "separate", "xy_fused"])
 def test_collide_and_stream_vs_oracle(orc, per, swap):
+    """swap=True is the default path (envelope quirk fused into k_collide_stream); "separate" / "xy_fused" run the quirk as a
+    separate k_face_swap pass over all / the z faces: all three must give the reference's bits."""
+    opts = {bib.OPT_ENVELOPE_SWAP: float(bool(swap))}
+    if swap == "separate": opts[bib.OPT_FUSED_FACE_SWAP] = 0.0
+    if swap == "xy_fused": opts[bib.OPT_FUSED_FACE_SWAP] = 2.0
+    swap = bool(swap)
     rng = np.random.default_rng(11)
     nx, ny, nz = 19, 9, 37            # ragged sizes: nz not a multiple of the warp size
     cells = np.zeros((nx, ny, nz, 23))
     cells[..., :19] = 0.01 * rng.normal(size=(nx, ny, nz, 19))
     cells[..., 19:22] = 1e-4 * rng.normal(size=(nx, ny, nz, 3))
     cells[..., 22] = rng.integers(0, 2, size=(nx, ny, nz))
-    lat = make_lattice(cells, per, 1.6, 0.7, {bib.OPT_ENVELOPE_SWAP: float(swap)})
+    lat = make_lattice(cells, per, 1.6, 0.7, opts)
     ref = cells
     for _ in range(4):
         lat.collideAndStream()
