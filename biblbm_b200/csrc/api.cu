@@ -72,7 +72,9 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
               bib_cuda_ok(create_comm_stream(&d->comm_stream), "cudaStreamCreate") &&
               bib_cuda_ok(cudaEventCreate(&d->ev0), "cudaEventCreate") && bib_cuda_ok(cudaEventCreate(&d->ev1), "cudaEventCreate") &&
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming), "cudaEventCreate") &&
-              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_compute, cudaEventDisableTiming), "cudaEventCreate");
+              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_compute, cudaEventDisableTiming), "cudaEventCreate") &&
+              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming), "cudaEventCreate") &&
+              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_forces, cudaEventDisableTiming), "cudaEventCreate");
     for (int b = 0; ok && b < 2; ++b) {
         ok = bib_cuda_ok(cudaMalloc(&d->f[b], d->vol * BIB_Q * sizeof(double)), "cudaMalloc(populations)") &&
              bib_cuda_ok(cudaMemsetAsync(d->f[b], 0, d->vol * BIB_Q * sizeof(double), d->stream), "cudaMemset");
@@ -132,6 +134,8 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->ev_compute) cudaEventDestroy(d->ev_compute);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_forces) cudaEventDestroy(d->ev_forces);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
     delete d;
@@ -152,6 +156,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_SPREAD_MODE: d->spread_mode = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_STEP_GRAPH: d->use_graph = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_FUSED_FACE_SWAP: d->fused_face_swap = value == 2.0 ? 2 : (value != 0.0 ? 1 : 0); return 1;
+        case BIB_OPT_OVERLAP_FORCES: d->overlap_forces = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
     bib_set_error("set_option: unknown key");
@@ -367,6 +372,15 @@ int bib_ib_results_wait(bib_domain* d) { BIB_ENTER_RO(d); return ib_results_wait
 // computeVelocity pass of the reference is not needed; then F := body, IB, collide-and-stream.
 static int step_once(bib_domain* d, double body_fx, double body_fy, double body_fz) {
     const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
+    // The vertex forces need the positions only: they are evaluated on a second stream (FP64-bound) beside the band velocity and
+    // the interpolation (HBM / L2-bound) and joined before the spread.
+    const bool fork = d->overlap_forces && ib_forces_independent_of_interpolation(d);
+    if (fork) {
+        BIB_CHECK(cudaEventRecord(d->ev_fork, d->stream));
+        BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_fork, 0));
+        if (!ib_forces(d, d->comm_stream)) return 0;
+        BIB_CHECK(cudaEventRecord(d->ev_forces, d->comm_stream));
+    }
     if (!ib_interpolate(d)) return 0;
     // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
     if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {
@@ -375,7 +389,10 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
         d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
     }
-    if (!ib_forces_and_spread(d)) return 0;
+    if (fork) {
+        BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_forces, 0));
+        if (!ib_spread(d)) return 0;
+    } else if (!ib_forces_and_spread(d)) return 0;
     if (!ib_move_and_voxelize(d)) return 0;
     d->vel_full_valid = false;
     return lbm_launch_collide_stream(d);

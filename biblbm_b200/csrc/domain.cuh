@@ -102,6 +102,8 @@ struct bib_domain {
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_forces = nullptr;   // bib_step: force evaluation on comm_stream beside the interpolation
+    int overlap_forces = 1;               // BIB_OPT_OVERLAP_FORCES
     long long launches = 0;
     // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
     cudaGraphExec_t step_graph = nullptr; bool graph_dirty = true; int use_graph = 1; long long graph_launches = 0; double graph_body[3] = {0, 0, 0}; int graph_cur = 0, graph_band_cur = 0;
@@ -176,6 +178,9 @@ int ib_rigid_download(bib_domain* d, int first, int count, double* state19);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
 int ib_forces_and_spread(bib_domain* d);
+int ib_forces(bib_domain* d, cudaStream_t st);
+int ib_spread(bib_domain* d);
+bool ib_forces_independent_of_interpolation(const bib_domain* d);
 int ib_move_and_voxelize(bib_domain* d);
 int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9);
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9);

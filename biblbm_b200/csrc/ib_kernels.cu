@@ -1902,14 +1902,14 @@ static PPGrid make_pp_grid(const bib_domain* d) {
     }
     return G;
 }
-static int ib_pp_forces(bib_domain* d) {
+static int ib_pp_forces(bib_domain* d, cudaStream_t st) {
     if (d->n_ranks > 1) { bib_set_error("particle-particle interaction forces: single-slab domains only (round 1)"); return 0; }
     if (d->pp_pot.r_min > 1.0) { bib_set_error("The interaction distance cannot be greater than the lattice spacing (1)"); return 0; }   // _forces.hh:347-350
     const PPGrid G = make_pp_grid(d);
     const size_t ncell = (size_t)G.nc[0] * G.nc[1] * G.nc[2];
     if (!d->pp_head) {
         BIB_CHECK(cudaMalloc(&d->pp_head, ncell * sizeof(int)));
-        BIB_CHECK(cudaMemsetAsync(d->pp_head, 0xff, ncell * sizeof(int), d->stream));
+        BIB_CHECK(cudaMemsetAsync(d->pp_head, 0xff, ncell * sizeof(int), st));
         d->bytes += (long long)(ncell * sizeof(int));
     }
     if (d->pp_cap < d->cap_vertices) {
@@ -1922,30 +1922,31 @@ static int ib_pp_forces(bib_domain* d) {
     if (d->pp_groups != (int)d->groups.size()) {
         for (const ParticleGroup& gr : d->groups) {
             const long long n = (long long)gr.count * d->shapes[gr.shape].nv;
-            k_fill_vobj<<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>(d->pp_vobj, gr.first_vertex, d->shapes[gr.shape].nv, gr.first_particle, n);
+            k_fill_vobj<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d->pp_vobj, gr.first_vertex, d->shapes[gr.shape].nv, gr.first_particle, n);
             d->launches++;
         }
         d->pp_groups = (int)d->groups.size();
     }
     const unsigned grid = (unsigned)((d->n_vertices + 255) / 256);
-    k_pp_build<<<grid, 256, 0, d->stream>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head, d->pp_next);
-    k_pp_forces<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(G, d->pp_pot, d->n_vertices, d->cap_vertices, d->vpos, d->pp_vobj,
+    k_pp_build<<<grid, 256, 0, st>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head, d->pp_next);
+    k_pp_forces<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, st>>>(G, d->pp_pot, d->n_vertices, d->cap_vertices, d->vpos, d->pp_vobj,
                                                                             d->pp_head, d->pp_next, d->vfrc);
-    k_pp_clear<<<grid, 256, 0, d->stream>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head);
+    k_pp_clear<<<grid, 256, 0, st>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head);
     d->launches += 3;
     BIB_CHECK(cudaGetLastError());
     return 1;
 }
 
-int ib_forces_and_spread(bib_domain* d) {
+// Vertex forces of every particle group (decorators first, then the particle models, then the particle-particle force), launched on `st`.
+// They depend on the vertex positions (and, for rigid particles, on the interpolated velocities) only, not on the lattice.
+int ib_forces(bib_domain* d, cudaStream_t st) {
     if (d->n_vertices == 0) return 1;
-    d->interp_since_spread = false;
     Geo wg = make_geo(d);
     if (d->wall_bkind >= 0) { wg.plates = d->wall_bkind; wg.py0 = d->wall_b[0]; wg.py1 = d->wall_b[1]; wg.prad = d->wall_b[2]; }
     const bool wall = d->wall_pot.type != 0 && wg.plates != 0;
     if (wall) {
         if (d->n_ranks > 1) { bib_set_error("wall interaction forces: single-slab domains only (round 1)"); return 0; }
-        k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, d->stream>>>(wg, d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+        k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, st>>>(wg, d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
         d->launches++;
     }
     for (const ParticleGroup& gr : d->groups) {
@@ -1956,7 +1957,7 @@ int ib_forces_and_spread(bib_domain* d) {
             c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
             for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
             c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
-            k_rigid_forces<<<gr.count, 256, 0, d->stream>>>(c, d->vpos, d->vvel, d->vfrc);
+            k_rigid_forces<<<gr.count, 256, 0, st>>>(c, d->vpos, d->vvel, d->vfrc);
             d->launches++;
             continue;
         }
@@ -1968,7 +1969,7 @@ int ib_forces_and_spread(bib_domain* d) {
             const size_t smem = (size_t)s.nv * 6 * sizeof(double);
             if (smem > 200 * 1024) { bib_set_error("semi-rigid particles: mesh too large for the shared-memory kernel"); return 0; }
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_semirigid_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_semirigid_forces<<<gr.count, 256, smem, d->stream>>>(c, d->vpos, d->vfrc, d->pstate);
+            k_semirigid_forces<<<gr.count, 256, smem, st>>>(c, d->vpos, d->vfrc, d->pstate);
             d->launches++;
             continue;
         }
@@ -1980,7 +1981,7 @@ int ib_forces_and_spread(bib_domain* d) {
             const size_t smem = (size_t)s.nv * 3 * sizeof(double);
             c.use_smem = smem <= 200 * 1024;
             if (c.use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_capsule_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_capsule_forces<<<gr.count, 256, c.use_smem ? smem : 0, d->stream>>>(c, d->vpos, d->vfrc);
+            k_capsule_forces<<<gr.count, 256, c.use_smem ? smem : 0, st>>>(c, d->vpos, d->vfrc);
             d->launches++;
             continue;
         }
@@ -1998,17 +1999,32 @@ int ib_forces_and_spread(bib_domain* d) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
             static size_t sm2_set = 0;
             if (sm2_set != sm2) { cudaFuncSetAttribute(k_rbc_forces_elem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); sm2_set = sm2; }
-            k_rbc_forces_elem<<<gr.count, RF_THREADS, sm2, d->stream>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np);
+            k_rbc_forces_elem<<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np);
         } else if (smem <= 200 * 1024) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_rbc_forces_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_rbc_forces_cta<<<gr.count, 256, smem, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+            k_rbc_forces_cta<<<gr.count, 256, smem, st>>>(q, d->vpos, d->vfrc, d->pstate);
         } else {
             const long long n = (long long)gr.count * s.nv;
-            k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(q, d->vpos, d->vfrc, d->pstate);
+            k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q, d->vpos, d->vfrc, d->pstate);
         }
         d->launches++;
     }
-    if (d->pp_pot.type != 0 && !ib_pp_forces(d)) return 0;   // after every particle's own forces (_forces.hh:300-302)
+    if (d->pp_pot.type != 0 && !ib_pp_forces(d, st)) return 0;   // after every particle's own forces (_forces.hh:300-302)
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// Can the force evaluation run beside the velocity interpolation of the same step (bib_step)? Not with rigid particles (their direct
+// forcing reads the interpolated velocities) and not on several slabs (the force exchange is ordered on the compute stream).
+bool ib_forces_independent_of_interpolation(const bib_domain* d) {
+    if (d->n_vertices == 0 || d->ms || d->n_ranks > 1) return false;
+    for (const ParticleGroup& gr : d->groups) if (gr.type == 3) return false;
+    return true;
+}
+
+int ib_spread(bib_domain* d) {
+    if (d->n_vertices == 0) return 1;
+    d->interp_since_spread = false;
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
     if (d->deterministic_spread) d->fflag_valid = false;
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
@@ -2028,6 +2044,8 @@ int ib_forces_and_spread(bib_domain* d) {
     BIB_CHECK(cudaGetLastError());
     return 1;
 }
+
+int ib_forces_and_spread(bib_domain* d) { return ib_forces(d, d->stream) && ib_spread(d); }
 
 int ib_move_and_voxelize(bib_domain* d) {
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;

@@ -49,6 +49,7 @@ enum {
     BIB_OPT_STEP_GRAPH = 6,          /* 1 (default): bib_step replays a CUDA graph of two consecutive steps on single-slab domains (small lattices are launch-bound) */
     BIB_OPT_FUSED_FACE_SWAP = 7,     /* envelope swap of the periodic faces: 1 (default) fused into the collide-and-stream kernel, 2 fused for the x / y faces with
                                         a separate pass over the z faces, 0 separate pass over all faces */
+    BIB_OPT_OVERLAP_FORCES = 8,      /* 1 (default): bib_step evaluates the vertex forces on a second stream beside the velocity interpolation (same results) */
     BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
                                         force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
 };

@@ -345,6 +345,23 @@ def test_step_graph_equals_plain_launches(rbc):
     assert t[0] < t[1]
 
 
+def test_overlapped_force_evaluation_equals_serial(rbc):
+    """BIB_OPT_OVERLAP_FORCES: bib_step evaluates the vertex forces on a second stream beside the velocity interpolation and joins
+    before the spread; results are bit-identical to the serial order, with and without the step graph."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc_in_shear.npz")
+    out = []
+    for overlap, graph in ((1.0, 1.0), (1.0, 0.0), (0.0, 0.0)):
+        lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0, bib.OPT_STEP_GRAPH: graph, bib.OPT_OVERLAP_FORCES: overlap})
+        sid = lat.register_shape(shape.verts, shape.tris)
+        lat.add_particles(sid, params, g["vert_init"][..., :3])
+        lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
+        lat.step((1e-6, 0.0, 0.0), n=40)
+        out.append((lat.vertices(), lat.download()))
+    for v, pop in out[1:]:
+        assert np.array_equal(v, out[0][0]) and np.array_equal(pop, out[0][1])
+
+
 def test_async_result_readback_matches_golden(rbc):
     """bib_ib_results_download_async: the read-back of step s overlaps step s+1 and still delivers step s, bit for bit."""
     import torch
