@@ -220,6 +220,25 @@ def make_rigid():
     print("rigid golden ok")
 
 
+def make_sphere_ext_flow():
+    """progs/sphere_in_ext_flow in miniature (oracle/harness/ref_sphere_harness.cpp includes the driver source in place): 25x27x16
+    ForcedD3Q19 lattice, GuoExternalForceBGKdynamics, extensionalFlowSetup (velocity planes normal to x and y + four z edges, z periodic),
+    one RigidParticle3D sphere (626 vertices, scale 0.6) advanced by the driver's MultiDirectForcingFunctional3D (4 sub-iterations), 10 steps."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    cfg = dict(geo_nx=24, geo_ny=26, geo_nz=15, tau=0.55, gamma=2e-3, relaxation_factor=0.3, relax_iterations=4, density=1.0, damping=0.0, scale=0.6,
+               pos_x=12.3, pos_y=17.9, pos_z=7.4, steps=10)
+    out = kit.run_reference_sphere(cfg, shape.verts, shape.tris)
+    steps = cfg["steps"]
+    keep = dict(pop_init=out["pop_init"], bvel=out["bvel"], vert_init=out["vert_init"], part_init=out["part_init"], rigid_init=out["rigid_init"],
+                rigid_shape=out["rigid_shape"], pop_1=out["pop_1"], pop_final_sample=out[f"pop_{steps}"][::2, ::2, ::2].copy(), omega=1.0 / cfg["tau"],
+                steps=steps, relax_iterations=cfg["relax_iterations"],
+                rparams=np.array([cfg["density"], cfg["damping"], cfg["relaxation_factor"], cfg["scale"], 0, 0, 0, 0]), per=np.array([0, 0, 1], dtype=np.int32))
+    for s in range(1, steps + 1):
+        keep[f"vert_{s}"] = out[f"vert_{s}"]; keep[f"part_{s}"] = out[f"part_{s}"]; keep[f"rigid_{s}"] = out[f"rigid_{s}"]
+    np.savez_compressed(HERE / "ib_sphere_ext_flow.npz", **keep)
+    print("sphere_in_ext_flow golden ok, |F|max =", np.abs(out[f"vert_{steps}"][..., 6:]).max())
+
+
 def pipe_case():
     """rbc_in_pipe-type set-up in miniature (x periodic; PipeBoundary; Morse wall interaction and Morse particle-particle
     interaction with the parameters of progs/rbc_in_pipe/input.xml): RBC A almost touching the pipe wall with the fluid initially
@@ -312,6 +331,7 @@ if __name__ == "__main__":
     make_plates()
     make_semirigid()
     make_rigid()
+    make_sphere_ext_flow()
     make_pipe()
     make_guo()
     make_ib("ib_rbc2_pfp.npz", (36, 22, 20), "pfp", [(34.6, 10.8, 9.2), (16.2, 11.1, 10.3)], steps=3, seed=2)

@@ -241,6 +241,39 @@ class Oracle:
         self.lib.orc_wall_plane(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(direction), C.c_int(orient), C.c_int(coord),
                                 _d(wallvel), C.c_double(omega))
 
+    # ---- sphere_in_ext_flow: partial velocity planes + z edges + multi-direct-forcing (cells carry a zero phase: 23 scalars per cell)
+    def wall_plane_box(self, cells, per, direction, orient, box, bvel, omega):
+        nx, ny, nz, _ = cells.shape
+        self.lib.orc_wall_plane_box(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(np.asarray(per, dtype=np.int32)), C.c_int(direction), C.c_int(orient),
+                                    _i(np.asarray(box, dtype=np.int32)), _d(bvel), C.c_double(omega))
+
+    def wall_edge(self, cells, per, plane, normal1, normal2, box, bvel, omega):
+        nx, ny, nz, _ = cells.shape
+        self.lib.orc_wall_edge(_d(cells), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(np.asarray(per, dtype=np.int32)), C.c_int(plane), C.c_int(normal1),
+                               C.c_int(normal2), _i(np.asarray(box, dtype=np.int32)), _d(bvel), C.c_double(omega))
+
+    def mdf_step(self, cells, per, bvel, bmask, n_iter, shape: Shape, vert, state):
+        """MultiDirectForcingFunctional3D::process for one rigid particle (set_rigid / set_particle_model(3, rest) beforehand)."""
+        nx, ny, nz, _ = cells.shape
+        vel = np.empty((nx, ny, nz, 3))
+        bm = np.ascontiguousarray(bmask, dtype=np.uint8)
+        self.lib.orc_mdf_step(_d(cells), _d(vel), C.c_int(nx), C.c_int(ny), C.c_int(nz), _i(np.asarray(per, dtype=np.int32)), _d(bvel), bm.ctypes.data_as(_u8p),
+                              C.c_int(n_iter), C.c_int(shape.nv), C.c_int(shape.nt), _i(shape.tris), _d(vert), _d(state))
+
+    def ext_flow_step(self, cells, bvel, omega, n_iter, shape, vert, state):
+        """One time step of progs/sphere_in_ext_flow (sphere_in_ext_flow.cpp:285-292) on the extensionalFlowSetup lattice: multi-direct
+        forcing, collideAndStream (x, y walls; z periodic; single relaxation rate), then the level-0 boundary functionals in their
+        order of insertion (extensional_flow_setup.h:78-88): planes 0N, 0P, 1N, 1P, edges 2NN, 2PN, 2NP, 2PP. Returns the new cells."""
+        per = (0, 0, 1)
+        planes, edges, bmask = ext_flow_boundaries(cells.shape[:3])
+        self.mdf_step(cells, per, bvel, bmask, n_iter, shape, vert, state)
+        out = self.collide_and_stream(cells, per, omega, 0.0, envelope_swap=False)
+        for (d, o, box) in planes:
+            self.wall_plane_box(out, per, d, o, box, bvel, omega)
+        for (n1, n2, box) in edges:
+            self.wall_edge(out, per, 2, n1, n2, box, bvel, omega)
+        return out
+
     def wall_velocity_fill(self, vel, direction, coord, wallvel):
         nx, ny, nz, _ = vel.shape
         wallvel = np.ascontiguousarray(wallvel, dtype=np.float64)
@@ -393,6 +426,54 @@ def run_reference(cfg: dict, workdir=None, verts=None, tris=None, params=None, p
     if tmp is not None:
         tmp.cleanup()
     return out
+
+
+REF_SPHERE_HARNESS = REF_HARNESS.parent / "ref_sphere_harness"
+
+
+def ext_flow_boundaries(dims):
+    """Boundary boxes of progs/common/extensional_flow_setup.h:66-88 for an (nx, ny, nz) lattice: [(dir, orient, box)] planes in their
+    order of insertion, [(normal1, normal2, box)] z-edges likewise, and the mask of boundary cells."""
+    nx, ny, nz = dims
+    gx, gy, gz = nx - 1, ny - 1, nz - 1
+    planes = [(0, -1, (0, 0, 1, gy - 1, 0, gz)), (0, 1, (gx, gx, 1, gy - 1, 0, gz)), (1, -1, (1, gx - 1, 0, 0, 0, gz)), (1, 1, (1, gx - 1, gy, gy, 0, gz))]
+    edges = [(-1, -1, (0, 0, 0, 0, 0, gz)), (1, -1, (gx, gx, 0, 0, 0, gz)), (-1, 1, (0, 0, gy, gy, 0, gz)), (1, 1, (gx, gx, gy, gy, 0, gz))]
+    bmask = np.zeros(dims, dtype=np.uint8)
+    bmask[0, :, :] = 1; bmask[gx, :, :] = 1; bmask[:, 0, :] = 1; bmask[:, gy, :] = 1
+    return planes, edges, bmask
+
+
+def run_reference_sphere(cfg: dict, verts, tris, timeout=600):
+    """Run oracle/_ref/ref_sphere_harness (miniature of progs/sphere_in_ext_flow on the unmodified reference) and load its dumps.
+    cfg: geo_nx, geo_ny, geo_nz, tau, gamma, relaxation_factor, relax_iterations, density, damping, scale, pos_x, pos_y, pos_z, steps."""
+    assert REF_SPHERE_HARNESS.exists(), "oracle/_ref/ref_sphere_harness missing: run oracle/build_ref.sh (needs /root/reference)"
+    with tempfile.TemporaryDirectory() as tmp:
+        wd = pathlib.Path(tmp)
+        cfg = dict(cfg, out=str(wd), mesh=str(wd / "shape.mesh"))
+        write_mesh_bin(wd / "shape.mesh", verts, tris)
+        with open(wd / "config.txt", "w") as f:
+            for k, v in cfg.items():
+                f.write(f"{k}={v}\n")
+        r = subprocess.run([str(REF_SPHERE_HARNESS), str(wd / "config.txt")], capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_sphere_harness failed: {r.stdout}\n{r.stderr}")
+        nx, ny, nz = int(cfg["geo_nx"]) + 1, int(cfg["geo_ny"]) + 1, int(cfg["geo_nz"]) + 1
+        out = {"stdout": r.stdout}
+        for p in sorted(wd.glob("*.f64")):
+            a = np.fromfile(p)
+            name = p.stem
+            if name.startswith("pop_") or name.startswith("mid_"):
+                a = a.reshape(nx, ny, nz, 22)
+            elif name == "bvel":
+                a = a.reshape(nx, ny, nz, 3)
+            elif name.startswith("vert_"):
+                a = a.reshape(1, verts.shape[0], 9)
+            elif name.startswith("part_"):
+                a = a.reshape(1, 11)
+            elif name.startswith("rigid_") and name != "rigid_shape":
+                a = a.reshape(1, 19)
+            out[name] = a
+        return out
 
 
 # ------------------------------------------------------------------------------------------- golden fixtures

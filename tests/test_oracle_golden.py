@@ -262,6 +262,31 @@ def test_rigid_particle_bit_exact(orc, rbc):
     assert np.array_equal(cells[::2, ::2, ::2], g["pop_final_sample"])
 
 
+def test_sphere_in_ext_flow_bit_exact(orc, rbc):
+    """progs/sphere_in_ext_flow in miniature: single-rate GuoExternalForceBGKdynamics on ForcedD3Q19, velocity planes
+    normal to x and y joined by OuterVelocityEdge cells, RigidParticle3D driven by the driver's own MultiDirectForcingFunctional3D
+    (4 sub-iterations); oracle == reference bit for bit over 10 steps (lattice, vertices, rigid-body state)."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_sphere_ext_flow.npz")
+    cells = np.zeros(g["pop_init"].shape[:3] + (23,)); cells[..., :22] = g["pop_init"]
+    bvel = np.ascontiguousarray(g["bvel"])
+    vert, state = g["vert_init"][0].copy(), g["part_init"][0].copy()
+    rs = np.zeros((1, 24)); rs[0, :13] = g["rigid_init"][0, :13]; rs[0, 19:23] = g["rparams"][:4]
+    assert np.array_equal(orc.rigid_place(shape.verts, rs[0]), vert[:, :3])
+    orc.set_particle_model(3, shape.verts)
+    orc.set_rigid(rs, g["rigid_shape"][:9], float(g["rigid_shape"][9]))
+    try:
+        for s in range(1, int(g["steps"]) + 1):
+            cells = orc.ext_flow_step(cells, bvel, float(g["omega"]), int(g["relax_iterations"]), shape, vert, state)
+            assert np.array_equal(vert, g[f"vert_{s}"][0]) and np.array_equal(state, g[f"part_{s}"][0]) and np.array_equal(rs[0, :19], g[f"rigid_{s}"][0]), s
+            if s == 1:
+                assert np.array_equal(cells[..., :22], g["pop_1"])
+    finally:
+        orc.reset_modes()
+    assert np.abs(vert[:, 6:]).max() > 1e-4, "the forcing must act"
+    assert np.array_equal(cells[::2, ::2, ::2, :22], g["pop_final_sample"])
+
+
 def test_guo_pipe_wall_bit_exact(orc):
     """GuoRigidWallBoundary on a pipe + NoDynamics outside (rbc_in_pipe.cpp:285-343), LBM only: the wall-node list and 6 steps."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
