@@ -22,7 +22,7 @@ SYMBOLS = [
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
-    "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_vertices_download", "bib_ib_vertices_upload",
+    "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
 ]
@@ -83,11 +83,14 @@ class Lattice:
     """One x-slab of a D3Q19 ForcedPhase lattice + its immersed particles, resident on one GPU."""
 
     def __init__(self, nx, ny, nz, omega, omega_inner, periodic=(True, True, True), device=0):
+        """omega_inner=None: ForcedD3Q19Descriptor cells (22 scalars) with the single-rate GuoExternalForceBGKdynamics(omega)."""
         self.lib = load_library()
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.h = C.c_void_p()
         per = (C.c_int * 3)(*[int(bool(p)) for p in periodic])
-        _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, 4, C.c_double(omega), C.c_double(omega_inner), per, int(device), C.byref(self.h)))
+        self.n_ext = 3 if omega_inner is None else 4
+        self.ncomp = 19 + self.n_ext
+        _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, self.n_ext, C.c_double(omega), C.c_double(omega_inner or 0.0), per, int(device), C.byref(self.h)))
         self.full = (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1)
         self.shape_nv = {}
 
@@ -110,12 +113,12 @@ class Lattice:
     def upload(self, cells, box=None):
         box = box or self.full
         cells = np.ascontiguousarray(cells, dtype=np.float64)
-        assert cells.size == (box[1] - box[0] + 1) * (box[3] - box[2] + 1) * (box[5] - box[4] + 1) * 23
+        assert cells.size == (box[1] - box[0] + 1) * (box[3] - box[2] + 1) * (box[5] - box[4] + 1) * self.ncomp
         _check(self.lib.bib_domain_upload(self.h, _box(box), _dptr(cells)))
 
     def download(self, box=None, out=None):
         box = box or self.full
-        shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 23)
+        shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, self.ncomp)
         if out is None:
             out = np.empty(shape, dtype=np.float64)
         _check(self.lib.bib_domain_download(self.h, _box(box), _dptr(out)))
@@ -132,6 +135,10 @@ class Lattice:
         _check(self.lib.bib_add_velocity_boundary(self.h, _box(box), int(direction), int(orientation)))
         if velocities is not None:
             self.setBoundaryVelocity(box, velocities)
+
+    def addExternalVelocityEdge(self, box, axis, normal1, normal2):
+        """boundaryCondition.addExternalVelocityEdge{axis}{N|P}{N|P}(box, lattice)."""
+        _check(self.lib.bib_add_velocity_edge(self.h, _box(box), int(axis), int(normal1), int(normal2)))
 
     def setBoundaryVelocity(self, box, velocities):
         v = np.ascontiguousarray(velocities, dtype=np.float64)
@@ -243,6 +250,9 @@ class Lattice:
 
     def move_vertices_and_revoxelize(self):
         _check(self.lib.bib_ib_move_vertices_and_revoxelize(self.h))
+
+    def multi_direct_forcing(self, relax_iterations):
+        _check(self.lib.bib_ib_multi_direct_forcing(self.h, int(relax_iterations)))
 
     def ib_step(self):
         _check(self.lib.bib_ib_step(self.h))

@@ -44,8 +44,9 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (!out || !periodic) { bib_set_error("domain_create: null argument"); return 0; }
     *out = nullptr;
     if (nx < 1 || ny < 1 || nz < 1) { bib_set_error("domain_create: empty lattice"); return 0; }
-    if (n_ext != 4) { bib_set_error("domain_create: only ForcedPhaseD3Q19Descriptor (4 external scalars) is implemented"); return 0; }
-    if (!(omega_outer > 0.0 && omega_outer < 2.0 && omega_inner > 0.0 && omega_inner < 2.0)) { bib_set_error("domain_create: omega must lie in (0,2)"); return 0; }
+    if (n_ext != 4 && n_ext != 3) { bib_set_error("domain_create: n_ext must be 4 (ForcedPhaseD3Q19Descriptor) or 3 (ForcedD3Q19Descriptor)"); return 0; }
+    if (n_ext == 3) omega_inner = 0.0;      // GuoExternalForceBGKdynamics: one relaxation rate (the kernels read omega1 == 0 as "use omega0 as it is")
+    if (!(omega_outer > 0.0 && omega_outer < 2.0) || (n_ext == 4 && !(omega_inner > 0.0 && omega_inner < 2.0))) { bib_set_error("domain_create: omega must lie in (0,2)"); return 0; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         bib_set_error("domain_create: no CUDA device available (this library has no CPU fallback)");
@@ -57,7 +58,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
     d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
     for (int k = 0; k < 3; ++k) d->per[k] = periodic[k] ? 1 : 0;
-    d->omega0 = omega_outer; d->omega1 = omega_inner;
+    d->omega0 = omega_outer; d->omega1 = omega_inner; d->n_ext = n_ext;
     d->plane = (size_t)ny * nz;
     d->vol = (size_t)(nx + 2) * d->plane;
     size_t free_b = 0, total_b = 0;
@@ -123,12 +124,14 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);
     if (d->vfrc) cudaFree(d->vfrc);
+    if (d->vfrc_sum) cudaFree(d->vfrc_sum);
     if (d->pstate) cudaFree(d->pstate);
     for (ShapeDev& s : d->shapes) {
         void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts, s.rest_radial};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
     for (WallPlane& w : d->walls) if (w.vel) cudaFree(w.vel);
+    for (WallEdge& e : d->edges) if (e.vel) cudaFree(e.vel);
     for (ParticleGroup& g : d->groups) { if (g.link_ks) cudaFree(g.link_ks); if (g.link_kp) cudaFree(g.link_kp); if (g.rigid) cudaFree(g.rigid); }
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -195,6 +198,11 @@ int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* vel
     BIB_ENTER(d);
     if (!box || !velocities) { bib_set_error("set_boundary_velocity: null argument"); return 0; }
     return lbm_set_wall_velocity(d, box, velocities);
+}
+int bib_add_velocity_edge(bib_domain* d, const int box[6], int axis, int normal1, int normal2) {
+    BIB_ENTER(d);
+    if (!box) { bib_set_error("add_velocity_edge: null argument"); return 0; }
+    return lbm_add_edge(d, box, axis, normal1, normal2);
 }
 int bib_set_guo_wall_nodes(bib_domain* d, int n, const int* location_direction6, const double* delta, const double* wall_velocity3) {
     BIB_ENTER(d);
@@ -333,6 +341,23 @@ int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib
 int bib_ib_step(bib_domain* d) {
     BIB_ENTER(d);
     return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
+}
+// MultiDirectForcingFunctional3D::process (progs/sphere_in_ext_flow/sphere_in_ext_flow.cpp:26-98; oracle/biblbm_oracle.c orc_mdf_step)
+int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations) {
+    BIB_ENTER(d);
+    if (relax_iterations < 0) { bib_set_error("multi_direct_forcing: negative iteration count"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("multi_direct_forcing: single-slab domains only"); return 0; }
+    const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
+    if (!lbm_launch_set_external(d, box, 0.0, 0.0, 0.0)) return 0;
+    d->force_is_body = true; d->force_body[0] = d->force_body[1] = d->force_body[2] = 0.0;
+    if (!ib_force_accumulate(d, 0)) return 0;
+    for (int it = 0; it < relax_iterations; ++it) {
+        if (!lbm_launch_velocity(d, box)) return 0;          // every cell, boundary cells report their stored velocity
+        d->vel_full_valid = true;
+        if (!ib_interpolate(d) || !ib_forces_and_spread(d) || !ib_force_accumulate(d, 1)) return 0;
+    }
+    d->vel_full_valid = false;
+    return ib_force_accumulate(d, 2) && ib_update_all(d, 1);   // node force := -sum, then move_vertices()
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
     BIB_ENTER_RO(d);

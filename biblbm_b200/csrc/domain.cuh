@@ -70,15 +70,26 @@ struct PotentialDev { int type = 0; double r_min = 0, beta = 0, strength = 0; };
 
 struct WallPlane {                 // one velocity boundary plane (VelocityDirichlet + PlaneFd)
     int dir = 1, orient = -1, coord = 0;
-    int na = 0, nb = 0;            // extent along the two in-plane axes (x,y,z order)
-    double* vel = nullptr;         // device [na][nb][3] stored boundary velocities
+    int na = 0, nb = 0;            // size of the whole lattice face along the two in-plane axes (x,y,z order)
+    int a0 = 0, a1 = -1, b0 = 0, b1 = -1;   // the cells of the face this boundary covers (extensional_flow_setup.h: planes stop short of the edges)
+    double* vel = nullptr;         // device [na][nb][3] stored boundary velocities of the WHOLE face (edge cells included: in-plane neighbours)
+    std::vector<double> h_vel;     // host mirror
+};
+struct WallEdge {                  // one external velocity edge (StoreVelocityDynamics + OuterVelocityEdgeFunctional3D<axis, n1, n2>)
+    int axis = 2, n1 = -1, n2 = -1;   // edge along `axis`; outward normals along direction1 = (axis+1)%3 and direction2 = (axis+2)%3
+    int c1 = 0, c2 = 0;            // position along direction1 / direction2
+    int e0 = 0, e1 = -1, n = 0;    // covered cells along the axis, lattice size along the axis
+    int plane1 = -1, plane2 = -1;  // walls[] index of the face normal to direction2 (holds the direction1 neighbours) / normal to direction1
+    double* vel = nullptr;         // device [n][3]
+    std::vector<double> h_vel;
 };
 
 struct bib_domain {
     int device = 0;
     int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
     int per[3] = {0, 0, 0};               // global periodicity
-    double omega0 = 1, omega1 = 1;        // outer, inner
+    double omega0 = 1, omega1 = 1;        // outer, inner (omega1 == 0: single relaxation rate, see n_ext)
+    int n_ext = 4;                        // external scalars per cell: 4 = ForcedPhaseD3Q19Descriptor (GuoExternalForceVOFDynamics), 3 = ForcedD3Q19Descriptor (GuoExternalForceBGKdynamics)
     size_t plane = 0;                     // ny*nz
     size_t vol = 0;                       // (nx+2)*ny*nz  (storage incl. ghost planes)
     int cur = 0;                          // which population buffer holds the current state
@@ -127,6 +138,7 @@ struct bib_domain {
     int gnx = 0;                          // global nx
     // IB
     std::vector<WallPlane> walls;
+    std::vector<WallEdge> edges;
     int n_guo = 0; int* guo_nodes = nullptr; double* guo_delta = nullptr; double* guo_vel = nullptr;   // Guo off-lattice wall nodes
     std::vector<ShapeDev> shapes;
     std::vector<ParticleGroup> groups;
@@ -137,6 +149,7 @@ struct bib_domain {
     double* vpos = nullptr;   // [3][cap_vertices]  SoA
     double* vvel = nullptr;
     double* vfrc = nullptr;
+    double* vfrc_sum = nullptr; long long vfrc_sum_cap = 0;   // multi-direct forcing: node forces summed over the sub-iterations
     double* pstate = nullptr; // [cap_particles][11] area, volume, com[3], bbox[6]
     int* p_first_vertex = nullptr;   // [cap_particles]
     void* scratch = nullptr; size_t scratch_bytes = 0;
@@ -164,6 +177,7 @@ int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity);
 int lbm_velocity_upload(bib_domain* d, const int box[6], const double* velocity);
 int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
 int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient);
+int lbm_add_edge(bib_domain* d, const int box[6], int axis, int normal1, int normal2);
 int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel);
 int lbm_apply_walls(bib_domain* d);
 int lbm_set_guo_nodes(bib_domain* d, int n, const int* loc_dir, const double* delta, const double* wall_velocity);
@@ -185,6 +199,7 @@ int ib_move_and_voxelize(bib_domain* d);
 int ib_vertices_download(bib_domain* d, long long first, long long count, double* v9);
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9);
 int ib_update_all(bib_domain* d, int do_move);
+int ib_force_accumulate(bib_domain* d, int mode);   // 0: sum := 0, 1: sum += vertex forces, 2: vertex forces := -sum
 int ib_scalars_download(bib_domain* d, int first, int count, double* s11);
 int ib_results_download_async(bib_domain* d, double* v9, double* s11);
 int ib_results_wait(bib_domain* d);

@@ -2047,6 +2047,27 @@ int ib_spread(bib_domain* d) {
 
 int ib_forces_and_spread(bib_domain* d) { return ib_forces(d, d->stream) && ib_spread(d); }
 
+__global__ void k_force_accumulate(double* __restrict__ sum, double* __restrict__ vfrc, long long n, int mode) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        if (mode == 0) sum[t] = 0.0;
+        else if (mode == 1) sum[t] += vfrc[t];
+        else vfrc[t] = -sum[t];
+    }
+}
+int ib_force_accumulate(bib_domain* d, int mode) {
+    if (d->n_vertices == 0) return 1;
+    if (d->vfrc_sum_cap < d->cap_vertices) {
+        if (d->vfrc_sum) cudaFree(d->vfrc_sum);
+        BIB_CHECK(cudaMalloc(&d->vfrc_sum, (size_t)d->cap_vertices * 3 * sizeof(double)));
+        d->vfrc_sum_cap = d->cap_vertices;
+    }
+    const long long n = d->cap_vertices * 3;
+    k_force_accumulate<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, d->stream>>>(d->vfrc_sum, d->vfrc, n, mode);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int ib_move_and_voxelize(bib_domain* d) {
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;
     if (d->ms && !ms_exchange_positions(d)) return 0;      // refresh ghosts / hand particles over before voxelizing

@@ -63,7 +63,8 @@ __device__ __forceinline__ void d_collide(double* f, double Fx, double Fy, doubl
     const double uz = jz * invRho2 + Fz / 2.0;
     const double rho = rhoBar + 1.0;
     jx = rho * ux; jy = rho * uy; jz = rho * uz;
-    const double omega = w0 * w1 / (c * w0 + (1. - c) * w1);
+    // w1 == 0: GuoExternalForceBGKdynamics (one relaxation rate, used as it is; basicDynamics/externalForceDynamics.hh:215-234)
+    const double omega = w1 == 0.0 ? w0 : w0 * w1 / (c * w0 + (1. - c) * w1);
 
     // bgk_ma2_collision_base
     const double invRho = 1.0 / (rhoBar + 1.0);
@@ -370,29 +371,29 @@ __global__ void __launch_bounds__(128) k_face_swap(const FaceParams q) {
 // ---------------------------------------------------------------------------------------------- transposes & side passes
 // host AoS [x][y][z][23] (staged in device memory) <-> device SoA. One thread per (cell, component).
 __global__ void k_unpack_cells(const double* __restrict__ aos, double* f, double* force, uint8_t* phase, int* bad_phase,
-                               int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+                               int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz, int ncomp) {
     const long long n = (long long)bnx * bny * bnz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
         const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
-        const double* c = aos + t * 23;
+        const double* c = aos + t * ncomp;
         for (int i = 0; i < BIB_Q; ++i) f[(long long)i * vol + idx] = c[i];
         for (int k = 0; k < 3; ++k) force[(long long)k * vol + idx] = c[BIB_Q + k];
-        const double ph = c[BIB_Q + 3];
+        const double ph = ncomp > BIB_Q + 3 ? c[BIB_Q + 3] : 0.0;
         if (ph != 0.0 && ph != 1.0) atomicAdd(bad_phase, 1);
         phase[idx] = (ph != 0.0) ? 1 : 0;
     }
 }
 __global__ void k_pack_cells(double* __restrict__ aos, const double* f, const double* force, const uint8_t* phase,
-                             int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz) {
+                             int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz, int ncomp) {
     const long long n = (long long)bnx * bny * bnz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(t % bnz), y = (int)((t / bnz) % bny), x = (int)(t / ((long long)bnz * bny));
         const long long idx = (long long)(x + bx0 + 1) * plane + (long long)(y + by0) * nz + (z + bz0);
-        double* c = aos + t * 23;
+        double* c = aos + t * ncomp;
         for (int i = 0; i < BIB_Q; ++i) c[i] = f[(long long)i * vol + idx];
         for (int k = 0; k < 3; ++k) c[BIB_Q + k] = force[(long long)k * vol + idx];
-        c[BIB_Q + 3] = (double)(phase[idx] & 1);
+        if (ncomp > BIB_Q + 3) c[BIB_Q + 3] = (double)(phase[idx] & 1);
     }
 }
 __global__ void k_set_external(double* force, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, long long vol, int nz,
@@ -467,11 +468,13 @@ struct WallParams {
     double* f; const double* force; const double* wallvel;
     int nx, ny, nz; long long plane, vol;
     int dir, orient, coord, na, nb;
+    int a0, b0, ca, cb;          // covered cells of the face: a = a0 .. a0+ca-1, b = b0 .. b0+cb-1
     double omega;
 };
 __global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= w.nb) return;
+    const int bb = blockIdx.x * blockDim.x + threadIdx.x, a = w.a0 + (int)blockIdx.y;
+    if (bb >= w.cb) return;
+    const int b = w.b0 + bb;
     const int ta = w.dir == 0 ? 1 : 0, tb = w.dir == 2 ? 1 : 2;
     int c[3]; c[w.dir] = w.coord; c[ta] = a; c[tb] = b;
     const long long idx = (long long)(c[0] + 1) * w.plane + (long long)c[1] * w.nz + c[2];
@@ -539,13 +542,110 @@ __global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
     }
 }
 // computeVelocity on a wall cell returns the stored boundary velocity (StoreVelocityDynamics::computeVelocity)
-__global__ void k_wall_velocity_fill(double* vel, const double* __restrict__ wallvel, int dir, int coord, int na, int nb, long long plane, long long vol, int nz) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= nb) return;
+__global__ void k_wall_velocity_fill(double* vel, const double* __restrict__ wallvel, int dir, int coord, int na, int nb, int a0, int b0, int cb,
+                                     long long plane, long long vol, int nz) {
+    const int bb = blockIdx.x * blockDim.x + threadIdx.x, a = a0 + (int)blockIdx.y;
+    if (bb >= cb) return;
+    const int b = b0 + bb;
     const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
     int c[3]; c[dir] = coord; c[ta] = a; c[tb] = b;
     const long long idx = (long long)(c[0] + 1) * plane + (long long)c[1] * nz + c[2];
     const double* v = wallvel + ((long long)a * nb + b) * 3;
+    vel[idx] = v[0]; vel[vol + idx] = v[1]; vel[2 * vol + idx] = v[2];
+}
+
+// VelocityDirichletBoundaryDynamics<dir,orient>::computeRhoBar of a wall-plane cell (the formula k_wall_plane evaluates for its own cell)
+__device__ __forceinline__ double d_wall_rhoBar(const double* f, double Fd, double vd, int dir, int orient) {
+    double rhoOnWall = 0.0, rhoNormal = 0.0;
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) { const int ci = dir == 0 ? c_cx[i] : (dir == 1 ? c_cy[i] : c_cz[i]); if (ci == 0) rhoOnWall += f[i]; }
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) { const int ci = dir == 0 ? c_cx[i] : (dir == 1 ? c_cy[i] : c_cz[i]); if (ci == orient) rhoNormal += f[i]; }
+    const double velNormal = (double)orient * (vd - 0.5 * Fd);
+    return (2.0 * rhoNormal + rhoOnWall - 1 * velNormal) / (1.0 + velNormal);
+}
+// OuterVelocityEdgeFunctional3D<axis,n1,n2>::processCell (citations and operation order: oracle/biblbm_oracle.c, orc_wall_edge). One thread
+// per edge cell. The density is extrapolated from the two wall cells next to the edge in each of the two directions (whose density is the
+// velocity-Dirichlet formula of the face they lie on), the velocity gradient comes from stored boundary velocities only.
+struct EdgeParams {
+    double* f; const double* force; const double* vel_e; const double* vel_p1; const double* vel_p2;   // edge [n][3]; faces normal to direction2 / direction1
+    int nx, ny, nz; long long plane, vol;
+    int axis, n1, n2, c1, c2, e0, count, n, per_axis;
+    int p1_na, p1_nb, p2_na, p2_nb;
+    double omega;
+};
+__device__ __forceinline__ const double* d_face_vel(const double* vel, int dir, int nb, const int* c) {
+    const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+    return vel + ((long long)c[ta] * nb + c[tb]) * 3;
+}
+__global__ void __launch_bounds__(128) k_wall_edge(const EdgeParams w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.count) return;
+    const int d1 = (w.axis + 1) % 3, d2 = (w.axis + 2) % 3;
+    int c[3]; c[w.axis] = w.e0 + t; c[d1] = w.c1; c[d2] = w.c2;
+    double rho_n[2][2];
+    for (int which = 0; which < 2; ++which) for (int step = 1; step <= 2; ++step) {
+        int m[3] = {c[0], c[1], c[2]};
+        if (which == 0) m[d1] += -w.n1 * step; else m[d2] += -w.n2 * step;
+        const long long mi = (long long)(m[0] + 1) * w.plane + (long long)m[1] * w.nz + m[2];
+        double g[BIB_Q];
+#pragma unroll
+        for (int i = 0; i < BIB_Q; ++i) g[i] = w.f[(long long)i * w.vol + mi];
+        const int fdir = which == 0 ? d2 : d1, forient = which == 0 ? w.n2 : w.n1;
+        const double* fv = which == 0 ? d_face_vel(w.vel_p1, d2, w.p1_nb, m) : d_face_vel(w.vel_p2, d1, w.p2_nb, m);
+        rho_n[which][step - 1] = d_wall_rhoBar(g, w.force[(long long)fdir * w.vol + mi], fv[fdir], fdir, forient) + 1.0;
+    }
+    const double rho10 = rho_n[0][0], rho01 = rho_n[1][0], rho20 = rho_n[0][1], rho02 = rho_n[1][1];
+    const double rho = 2.0 / 3.0 * (rho01 + rho10) - 1.0 / 6.0 * (rho02 + rho20);
+    const double* ve = w.vel_e + (long long)c[w.axis] * 3;
+    const double v[3] = {ve[0], ve[1], ve[2]};
+    double grad[3][3];
+    {
+        int ip = c[w.axis] + 1, im = c[w.axis] - 1;
+        if (w.per_axis) { ip = (ip + w.n) % w.n; im = (im + w.n) % w.n; }
+        const double* up = w.vel_e + (long long)ip * 3; const double* um = w.vel_e + (long long)im * 3;
+        for (int k = 0; k < 3; ++k) grad[w.axis][k] = (up[k] - um[k]) / 2.0;
+    }
+    for (int which = 0; which < 2; ++which) {
+        const int dd = which == 0 ? d1 : d2, orient = which == 0 ? w.n1 : w.n2;
+        int m[3] = {c[0], c[1], c[2]}; m[dd] -= orient;
+        const double* u1 = which == 0 ? d_face_vel(w.vel_p1, d2, w.p1_nb, m) : d_face_vel(w.vel_p2, d1, w.p2_nb, m);
+        for (int k = 0; k < 3; ++k) grad[dd][k] = -orient * (-v[k] + u1[k]);
+    }
+    const double sToPi = -rho / 3.0 / w.omega;
+    double pi[6];
+    pi[0] = 2.0 * grad[0][0] * sToPi; pi[3] = 2.0 * grad[1][1] * sToPi; pi[5] = 2.0 * grad[2][2] * sToPi;
+    pi[1] = (grad[0][1] + grad[1][0]) * sToPi; pi[2] = (grad[0][2] + grad[2][0]) * sToPi; pi[4] = (grad[1][2] + grad[2][1]) * sToPi;
+    const double j[3] = {rho * v[0], rho * v[1], rho * v[2]};
+    const double jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+    const double rhoBar = rho - 1.0;
+    const double invRho = 1.0 / (rhoBar + 1.0);
+    const long long idx = (long long)(c[0] + 1) * w.plane + (long long)c[1] * w.nz + c[2];
+#pragma unroll
+    for (int i = 0; i < BIB_Q; ++i) {
+        const int cc[3] = {c_cx[i], c_cy[i], c_cz[i]};
+        const double ti = i == 0 ? 1. / 3 : ((i >= 1 && i <= 3) || (i >= 10 && i <= 12) ? 1. / 18 : 1. / 36);
+        const double c_j = cc[0] * j[0] + cc[1] * j[1] + cc[2] * j[2];
+        const double eq = ti * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
+        double fNeq = 0.0; int iPi = 0;
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+            fNeq += pi[iPi] * (cc[al] * cc[al] - 1.0 / 3.0);
+            ++iPi;
+#pragma unroll
+            for (int be = al + 1; be < 3; ++be) { fNeq += pi[iPi] * 2.0 * cc[al] * cc[be]; ++iPi; }
+        }
+        fNeq *= ti * 3.0 * 3.0 / 2.0;
+        w.f[(long long)i * w.vol + idx] = eq + fNeq;
+    }
+}
+__global__ void k_edge_velocity_fill(double* vel, const double* __restrict__ vel_e, int axis, int c1, int c2, int e0, int count, long long plane, long long vol, int nz) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int d1 = (axis + 1) % 3, d2 = (axis + 2) % 3;
+    int c[3]; c[axis] = e0 + t; c[d1] = c1; c[d2] = c2;
+    const long long idx = (long long)(c[0] + 1) * plane + (long long)c[1] * nz + c[2];
+    const double* v = vel_e + (long long)c[axis] * 3;
     vel[idx] = v[0]; vel[vol + idx] = v[1]; vel[2 * vol + idx] = v[2];
 }
 
@@ -594,7 +694,7 @@ static LbmParams make_params(bib_domain* d) {
 
 // 0: separate k_face_swap launches; 1: fused into k_collide_stream for all faces; 2: x and y faces fused, z faces separate
 static int fused_swap_mode(const bib_domain* d) {
-    if (!d->envelope_swap || d->omega0 == d->omega1) return 0;      // equal rates: the swap changes nothing, nothing to fuse
+    if (!d->envelope_swap || d->omega0 == d->omega1 || d->omega1 == 0.0) return 0;      // equal rates / one rate: the swap changes nothing
     if (!(d->per[0] || d->per[1] || d->per[2])) return 0;
     return d->fused_face_swap;
 }
@@ -612,7 +712,7 @@ static void launch_main(bib_domain* d, const LbmParams& p, int n_planes, cudaStr
     d->launches++;
 }
 static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x_select, cudaStream_t st) {
-    if (!d->envelope_swap || d->omega0 == d->omega1) return;        // equal rates: the swapped collision is the same collision
+    if (!d->envelope_swap || d->omega0 == d->omega1 || d->omega1 == 0.0) return;        // equal rates / one rate: the swapped collision is the same collision
     const int fused = fused_swap_mode(d);
     if (fused == 1) return;
     if (fused == 2) face_mask &= 48;                                // the z faces only
@@ -669,33 +769,99 @@ int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient) {
     if (!wall_box(d, box, dir) || (orient != 1 && orient != -1)) { bib_set_error("add_velocity_boundary: box must be one plane normal to direction; orientation +-1"); return 0; }
     const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
     const int n[3] = {d->nx, d->ny, d->nz};
-    if (box[2 * ta] != 0 || box[2 * ta + 1] != n[ta] - 1 || box[2 * tb] != 0 || box[2 * tb + 1] != n[tb] - 1) {
-        bib_set_error("add_velocity_boundary: the plane must span the whole slab face"); return 0; }
-    if (!d->per[ta] || !d->per[tb]) { bib_set_error("add_velocity_boundary: in-plane directions must be periodic (edge/corner conditions are not implemented)"); return 0; }
+    // along a non-periodic in-plane axis the plane must stop short of the lattice border: its border cells differentiate the stored
+    // velocities of their in-plane neighbours (edge cells, extensional_flow_setup.h:66-88); along a periodic axis it spans the lattice
+    for (int k = 0; k < 2; ++k) {
+        const int t = k == 0 ? ta : tb;
+        if (d->per[t]) { if (box[2 * t] != 0 || box[2 * t + 1] != n[t] - 1) { bib_set_error("add_velocity_boundary: the plane must span every periodic in-plane direction"); return 0; } }
+        else if (box[2 * t] < 1 || box[2 * t + 1] > n[t] - 2) { bib_set_error("add_velocity_boundary: along a non-periodic in-plane direction the plane must leave the border cells to edge conditions"); return 0; }
+    }
+    if (d->n_ranks > 1 && (dir == 0 || !d->per[0])) { bib_set_error("add_velocity_boundary: on multi-slab domains only planes normal to y / z with periodic x"); return 0; }
+    for (const WallPlane& o : d->walls) if (o.dir == dir && o.coord == box[2 * dir]) { bib_set_error("add_velocity_boundary: a velocity boundary already exists on this plane"); return 0; }
     WallPlane w; w.dir = dir; w.orient = orient; w.coord = box[2 * dir]; w.na = n[ta]; w.nb = n[tb];
+    w.a0 = box[2 * ta]; w.a1 = box[2 * ta + 1]; w.b0 = box[2 * tb]; w.b1 = box[2 * tb + 1];
+    w.h_vel.assign((size_t)w.na * w.nb * 3, 0.0);
     BIB_CHECK(cudaMalloc(&w.vel, (size_t)w.na * w.nb * 3 * sizeof(double)));
     BIB_CHECK(cudaMemsetAsync(w.vel, 0, (size_t)w.na * w.nb * 3 * sizeof(double), d->stream));
     d->walls.push_back(w);
     return 1;
 }
-int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
-    for (WallPlane& w : d->walls) {
-        if (box[2 * w.dir] == w.coord && box[2 * w.dir + 1] == w.coord) {
-            BIB_CHECK(cudaMemcpyAsync(w.vel, vel, (size_t)w.na * w.nb * 3 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-            BIB_CHECK(cudaStreamSynchronize(d->stream));
-            return 1;
-        }
+// addExternalVelocityEdge{axis}{N|P}{N|P} (boundaryCondition/boundaryInstantiator3D.h:423-469 with the interp manager): the two faces the
+// edge joins must already carry velocity planes (their cells next to the edge provide density and velocity neighbours)
+int lbm_add_edge(bib_domain* d, const int box[6], int axis, int normal1, int normal2) {
+    if (!box_ok(d, box) || axis < 0 || axis > 2 || (normal1 != 1 && normal1 != -1) || (normal2 != 1 && normal2 != -1)) { bib_set_error("add_velocity_edge: bad arguments"); return 0; }
+    const int d1 = (axis + 1) % 3, d2 = (axis + 2) % 3;
+    const int n[3] = {d->nx, d->ny, d->nz};
+    if (box[2 * d1] != box[2 * d1 + 1] || box[2 * d2] != box[2 * d2 + 1]) { bib_set_error("add_velocity_edge: the box must be a line along the axis"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("add_velocity_edge: single-slab domains only"); return 0; }
+    WallEdge e; e.axis = axis; e.n1 = normal1; e.n2 = normal2; e.c1 = box[2 * d1]; e.c2 = box[2 * d2]; e.e0 = box[2 * axis]; e.e1 = box[2 * axis + 1]; e.n = n[axis];
+    if (e.c1 != (normal1 < 0 ? 0 : n[d1] - 1) || e.c2 != (normal2 < 0 ? 0 : n[d2] - 1)) { bib_set_error("add_velocity_edge: the edge must lie on the lattice border its normals point out of"); return 0; }
+    if (d->per[axis] ? (e.e0 != 0 || e.e1 != n[axis] - 1) : (e.e0 < 1 || e.e1 > n[axis] - 2)) { bib_set_error("add_velocity_edge: the edge must span a periodic axis / stop short of the corners of a non-periodic one"); return 0; }
+    for (size_t i = 0; i < d->walls.size(); ++i) {
+        const WallPlane& w = d->walls[i];
+        if (w.dir == d2 && w.coord == e.c2 && w.orient == normal2) e.plane1 = (int)i;
+        if (w.dir == d1 && w.coord == e.c1 && w.orient == normal1) e.plane2 = (int)i;
     }
-    bib_set_error("set_boundary_velocity: no velocity boundary registered on this plane");
-    return 0;
+    if (e.plane1 < 0 || e.plane2 < 0 || n[d1] < 4 || n[d2] < 4) { bib_set_error("add_velocity_edge: add the velocity planes of the two faces the edge joins first"); return 0; }
+    e.h_vel.assign((size_t)e.n * 3, 0.0);
+    BIB_CHECK(cudaMalloc(&e.vel, (size_t)e.n * 3 * sizeof(double)));
+    BIB_CHECK(cudaMemsetAsync(e.vel, 0, (size_t)e.n * 3 * sizeof(double), d->stream));
+    d->edges.push_back(e);
+    return 1;
+}
+// setBoundaryVelocity(lattice, box, u): every boundary cell inside the box stores its velocity; a face array also keeps the velocities
+// of the edge cells on its border (they are the in-plane neighbours of the plane's outermost cells)
+int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
+    if (!box_ok(d, box)) { bib_set_error("set_boundary_velocity: box outside the slab"); return 0; }
+    const int by = box[3] - box[2] + 1, bz = box[5] - box[4] + 1;
+    bool any = false;
+    for (WallPlane& w : d->walls) {
+        if (w.coord < box[2 * w.dir] || w.coord > box[2 * w.dir + 1]) continue;
+        const int ta = w.dir == 0 ? 1 : 0, tb = w.dir == 2 ? 1 : 2;
+        for (int a = std::max(0, box[2 * ta]); a <= std::min(w.na - 1, box[2 * ta + 1]); ++a)
+            for (int b = std::max(0, box[2 * tb]); b <= std::min(w.nb - 1, box[2 * tb + 1]); ++b) {
+                int c[3]; c[w.dir] = w.coord; c[ta] = a; c[tb] = b;
+                const double* src = vel + (((size_t)(c[0] - box[0]) * by + (c[1] - box[2])) * bz + (c[2] - box[4])) * 3;
+                double* dst = &w.h_vel[((size_t)a * w.nb + b) * 3];
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+            }
+        BIB_CHECK(cudaMemcpyAsync(w.vel, w.h_vel.data(), w.h_vel.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        any = true;
+    }
+    for (WallEdge& e : d->edges) {
+        const int d1 = (e.axis + 1) % 3, d2 = (e.axis + 2) % 3;
+        if (e.c1 < box[2 * d1] || e.c1 > box[2 * d1 + 1] || e.c2 < box[2 * d2] || e.c2 > box[2 * d2 + 1]) continue;
+        for (int t = std::max(0, box[2 * e.axis]); t <= std::min(e.n - 1, box[2 * e.axis + 1]); ++t) {
+            int c[3]; c[e.axis] = t; c[d1] = e.c1; c[d2] = e.c2;
+            const double* src = vel + (((size_t)(c[0] - box[0]) * by + (c[1] - box[2])) * bz + (c[2] - box[4])) * 3;
+            e.h_vel[(size_t)t * 3] = src[0]; e.h_vel[(size_t)t * 3 + 1] = src[1]; e.h_vel[(size_t)t * 3 + 2] = src[2];
+        }
+        BIB_CHECK(cudaMemcpyAsync(e.vel, e.h_vel.data(), e.h_vel.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        any = true;
+    }
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    if (!any) { bib_set_error("set_boundary_velocity: no velocity boundary registered inside this box"); return 0; }
+    return 1;
 }
 int lbm_apply_walls(bib_domain* d) {
     for (const WallPlane& wp : d->walls) {
         WallParams w;
         w.f = d->f[d->cur]; w.force = d->force; w.wallvel = wp.vel; w.nx = d->nx; w.ny = d->ny; w.nz = d->nz;
         w.plane = (long long)d->plane; w.vol = (long long)d->vol; w.dir = wp.dir; w.orient = wp.orient; w.coord = wp.coord; w.na = wp.na; w.nb = wp.nb;
+        w.a0 = wp.a0; w.b0 = wp.b0; w.ca = wp.a1 - wp.a0 + 1; w.cb = wp.b1 - wp.b0 + 1;
         w.omega = d->omega0;
-        k_wall_plane<<<dim3((wp.nb + 127) / 128, wp.na), 128, 0, d->stream>>>(w);
+        k_wall_plane<<<dim3((w.cb + 127) / 128, w.ca), 128, 0, d->stream>>>(w);
+        d->launches++;
+    }
+    for (const WallEdge& e : d->edges) {     // after the planes: order of insertion in every shipped set-up (extensional_flow_setup.h:78-88)
+        const WallPlane& p1 = d->walls[e.plane1]; const WallPlane& p2 = d->walls[e.plane2];
+        EdgeParams w;
+        w.f = d->f[d->cur]; w.force = d->force; w.vel_e = e.vel; w.vel_p1 = p1.vel; w.vel_p2 = p2.vel;
+        w.nx = d->nx; w.ny = d->ny; w.nz = d->nz; w.plane = (long long)d->plane; w.vol = (long long)d->vol;
+        w.axis = e.axis; w.n1 = e.n1; w.n2 = e.n2; w.c1 = e.c1; w.c2 = e.c2; w.e0 = e.e0; w.count = e.e1 - e.e0 + 1; w.n = e.n; w.per_axis = d->per[e.axis];
+        w.p1_na = p1.na; w.p1_nb = p1.nb; w.p2_na = p2.na; w.p2_nb = p2.nb;
+        w.omega = d->omega0;
+        k_wall_edge<<<(w.count + 127) / 128, 128, 0, d->stream>>>(w);
         d->launches++;
     }
     if (!d->walls.empty()) BIB_CHECK(cudaGetLastError());
@@ -792,7 +958,14 @@ int lbm_apply_guo(bib_domain* d) {
 int lbm_wall_velocity_fill(bib_domain* d) {
     if (!d->vel) return 1;
     for (const WallPlane& wp : d->walls) {
-        k_wall_velocity_fill<<<dim3((wp.nb + 127) / 128, wp.na), 128, 0, d->stream>>>(d->vel, wp.vel, wp.dir, wp.coord, wp.na, wp.nb, (long long)d->plane, (long long)d->vol, d->nz);
+        const int ca = wp.a1 - wp.a0 + 1, cb = wp.b1 - wp.b0 + 1;
+        k_wall_velocity_fill<<<dim3((cb + 127) / 128, ca), 128, 0, d->stream>>>(d->vel, wp.vel, wp.dir, wp.coord, wp.na, wp.nb, wp.a0, wp.b0, cb,
+                                                                              (long long)d->plane, (long long)d->vol, d->nz);
+        d->launches++;
+    }
+    for (const WallEdge& e : d->edges) {
+        const int count = e.e1 - e.e0 + 1;
+        k_edge_velocity_fill<<<(count + 127) / 128, 128, 0, d->stream>>>(d->vel, e.vel, e.axis, e.c1, e.c2, e.e0, count, (long long)d->plane, (long long)d->vol, d->nz);
         d->launches++;
     }
     return 1;
@@ -804,15 +977,16 @@ int lbm_launch_upload(bib_domain* d, const int box[6], const double* cells) {
     const long long n = (long long)bnx * bny * bnz;
     // staged in chunks of x-planes so that very large slabs do not need a second full copy in HBM
     const long long per_plane = (long long)bny * bnz;
-    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * 23 * 8) + 1));
-    if (!ensure_scratch(d, (size_t)chunk * per_plane * 23 * 8 + 16)) return 0;
-    int* bad = (int*)((char*)d->scratch + (size_t)chunk * per_plane * 23 * 8);
+    const int ncomp = BIB_Q + d->n_ext;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * ncomp * 8) + 1));
+    if (!ensure_scratch(d, (size_t)chunk * per_plane * ncomp * 8 + 16)) return 0;
+    int* bad = (int*)((char*)d->scratch + (size_t)chunk * per_plane * ncomp * 8);
     BIB_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), d->stream));
     for (int x0 = 0; x0 < bnx; x0 += chunk) {
         const int cn = std::min(chunk, bnx - x0);
-        BIB_CHECK(cudaMemcpyAsync(d->scratch, cells + (size_t)x0 * per_plane * 23, (size_t)cn * per_plane * 23 * 8, cudaMemcpyHostToDevice, d->stream));
+        BIB_CHECK(cudaMemcpyAsync(d->scratch, cells + (size_t)x0 * per_plane * ncomp, (size_t)cn * per_plane * ncomp * 8, cudaMemcpyHostToDevice, d->stream));
         k_unpack_cells<<<grid_for(cn * per_plane, 256), 256, 0, d->stream>>>((const double*)d->scratch, d->f[d->cur], d->force, d->phase, bad,
-                                                                          box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz);
+                                                                          box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz, ncomp);
         d->launches++;
     }
     int h_bad = 0;
@@ -827,14 +1001,15 @@ int lbm_launch_download(bib_domain* d, const int box[6], double* cells) {
     if (!box_ok(d, box)) { bib_set_error("download: box outside the slab"); return 0; }
     const int bnx = box[1] - box[0] + 1, bny = box[3] - box[2] + 1, bnz = box[5] - box[4] + 1;
     const long long per_plane = (long long)bny * bnz;
-    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * 23 * 8) + 1));
-    if (!ensure_scratch(d, (size_t)chunk * per_plane * 23 * 8 + 16)) return 0;
+    const int ncomp = BIB_Q + d->n_ext;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(bnx, (256LL << 20) / (per_plane * ncomp * 8) + 1));
+    if (!ensure_scratch(d, (size_t)chunk * per_plane * ncomp * 8 + 16)) return 0;
     for (int x0 = 0; x0 < bnx; x0 += chunk) {
         const int cn = std::min(chunk, bnx - x0);
         k_pack_cells<<<grid_for(cn * per_plane, 256), 256, 0, d->stream>>>((double*)d->scratch, d->f[d->cur], d->force, d->phase,
-                                                                        box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz);
+                                                                        box[0] + x0, box[2], box[4], cn, bny, bnz, (long long)d->plane, (long long)d->vol, d->nz, ncomp);
         d->launches++;
-        BIB_CHECK(cudaMemcpyAsync(cells + (size_t)x0 * per_plane * 23, d->scratch, (size_t)cn * per_plane * 23 * 8, cudaMemcpyDeviceToHost, d->stream));
+        BIB_CHECK(cudaMemcpyAsync(cells + (size_t)x0 * per_plane * ncomp, d->scratch, (size_t)cn * per_plane * ncomp * 8, cudaMemcpyDeviceToHost, d->stream));
     }
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     return 1;

@@ -81,6 +81,13 @@ int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, dou
  * to keep the current values (initially 0). The two in-plane directions must be periodic. */
 int bib_add_velocity_boundary(bib_domain* d, const int box[6], int direction, int orientation);
 int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* velocities);
+/* External velocity edge = boundaryCondition.addExternalVelocityEdge{axis}{N|P}{N|P}(box, lattice) with the "interp" boundary condition
+ * (src/boundaryCondition/boundaryInstantiator3D.h:423-469: StoreVelocityDynamics + OuterVelocityEdgeFunctional3D<axis,normal1,normal2>,
+ * finiteDifferenceBoundaryProcessor3D.hh:162-243), as progs/common/extensional_flow_setup.h:84-88 uses it: box is a line of cells along
+ * `axis` on the lattice border, normal1 / normal2 = outward normals (+-1) along (axis+1)%3 / (axis+2)%3. The velocity planes of the two
+ * faces it joins must have been added before; edges are applied after the planes (their order of insertion in the reference set-up).
+ * bib_set_boundary_velocity stores velocities for every boundary cell (plane or edge) inside its box. */
+int bib_add_velocity_edge(bib_domain* d, const int box[6], int axis, int normal1, int normal2);
 
 /* Off-lattice (curved) no-slip / moving wall = fsi::GuoRigidWallBoundary (src/fsi/GuoBoundaryCondition.hh:25-198; rbc_in_pipe.cpp:303-306):
  * a list of wall nodes {location x,y,z (global lattice coordinates), inward lattice direction dx,dy,dz}, the fraction `delta` of the link
@@ -150,6 +157,11 @@ int bib_ib_interpolate_velocity(bib_domain* d);
 int bib_ib_compute_and_spread_forces(bib_domain* d);
 int bib_ib_move_vertices_and_revoxelize(bib_domain* d);
 int bib_ib_step(bib_domain* d);
+/* MultiDirectForcingFunctional3D::process of progs/sphere_in_ext_flow/sphere_in_ext_flow.cpp:26-98 (rigid particles, direct forcing with
+ * sub-iterations): F := 0 on the whole lattice; relax_iterations times { velocity of every cell from the current populations and the
+ * force accumulated so far (boundary cells report their stored velocity), interpolate_velocity, compute_and_spread_forces, sum the node
+ * forces }; node force := -(sum); move_vertices() (no re-voxelization). Followed by bib_collide_and_stream in the driver's loop. */
+int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations);
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9);
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
 /* per particle {area, volume, com[3], bbox x0,x1,y0,y1,z0,z1} (ParticleBase3D::area/volume/center_of_mass/bounding_box) */

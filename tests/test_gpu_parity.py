@@ -210,6 +210,100 @@ def test_rigid_particle_vs_golden(rbc):
     assert kit.rel_err(got[..., :19], g["pop_final_sample"][..., :19]) <= 1e-12
 
 
+def _ext_flow_lattice(g, opts=None):
+    """extensionalFlowSetup (progs/common/extensional_flow_setup.h:53-101) through the C-ABI: ForcedD3Q19 cells, one relaxation rate,
+    velocity planes normal to x and y, four z edges, stored velocities from the reference's dump."""
+    nx, ny, nz = g["pop_init"].shape[:3]
+    lat = bib.Lattice(nx, ny, nz, float(g["omega"]), None, periodic=(False, False, True))
+    for k, v in (opts or {}).items():
+        lat.set_option(k, v)
+    lat.upload(g["pop_init"])
+    planes, edges, _ = kit.ext_flow_boundaries((nx, ny, nz))
+    for (d, o, box) in planes:
+        lat.addVelocityBoundary(box, d, o)
+    for (n1, n2, box) in edges:
+        lat.addExternalVelocityEdge(box, 2, n1, n2)
+    lat.setBoundaryVelocity(lat.full, g["bvel"])
+    return lat
+
+
+def test_sphere_in_ext_flow_vs_golden(rbc):
+    """progs/sphere_in_ext_flow in miniature against the reference: single-rate Guo BGK on ForcedD3Q19 cells, partial
+    velocity planes + OuterVelocityEdge cells, a rigid sphere advanced by multi-direct forcing (4 sub-iterations), 10 steps. The
+    lattice step without the particle is bit-identical; with it, device sin / cos and the order of the spread sums allow 1e-12."""
+    shape, _, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_sphere_ext_flow.npz")
+    lat = _ext_flow_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0})
+    sid = lat.register_shape(shape.verts, shape.tris)
+    st17 = np.concatenate([g["rigid_init"][0, :13], g["rparams"][:4]])[None]
+    lat.add_rigid_particles(sid, g["rigid_shape"][:9], float(g["rigid_shape"][9]), st17)
+    assert np.array_equal(lat.vertices().reshape(1, -1, 9)[..., :3], g["vert_init"][..., :3])
+    for s in range(1, int(g["steps"]) + 1):
+        lat.multi_direct_forcing(int(g["relax_iterations"]))
+        lat.collideAndStream()
+        v = lat.vertices().reshape(1, -1, 9)
+        assert kit.rel_err(v[..., :3], g[f"vert_{s}"][..., :3]) <= 1e-13, s
+        assert kit.rel_err(v[..., 3:6], g[f"vert_{s}"][..., 3:6]) <= 1e-11, s
+        assert kit.rel_err(v[..., 6:], g[f"vert_{s}"][..., 6:]) <= 1e-9, s
+        assert kit.rel_err(lat.rigid_state()[:, :13], g[f"rigid_{s}"][:, :13]) <= 1e-13, s
+        if s == 1:
+            assert kit.rel_err(lat.download(), g["pop_1"]) <= 1e-12
+    assert kit.rel_err(lat.download()[::2, ::2, ::2], g["pop_final_sample"]) <= 1e-12
+    assert np.abs(lat.vertices()[:, 6:]).max() > 1e-4
+
+
+@pytest.mark.skipif(not kit.REF_SPHERE_HARNESS.exists(), reason="compiled reference (oracle/_ref/ref_sphere_harness) not present")
+def test_sphere_in_ext_flow_full_size_vs_live_reference(rbc):
+    """The driver's own configuration (sphere_in_ext_flow.cpp:135-160: 97^3 lattice, tau 0.55, Re_p 1, radius-8 sphere at (0.5, 0.8, 0.5),
+    relaxation factor 0.3, 4 sub-iterations) for 12 steps, production (atomic) spread, against the unmodified reference run live."""
+    shape, _, _, _ = rbc
+    radius = float(np.linalg.norm(shape.verts - shape.verts.mean(0), axis=1).mean())
+    scale = 8.0 / radius
+    tau = 0.55; nu = (tau - 0.5) / 3.0
+    a_lb = scale * np.sqrt(float(shape.area) / (4 * np.pi))
+    cfg = dict(geo_nx=96, geo_ny=96, geo_nz=96, tau=tau, gamma=repr(1.0 * nu / a_lb ** 2), relaxation_factor=0.3, relax_iterations=4, density=1.0, damping=0.0,
+               scale=repr(scale), pos_x=48.0, pos_y=76.8, pos_z=48.0, steps=12)
+    out = kit.run_reference_sphere(cfg, shape.verts, shape.tris)
+    g = dict(pop_init=out["pop_init"], omega=1.0 / tau, bvel=out["bvel"])
+    lat = _ext_flow_lattice(g)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    st17 = np.concatenate([out["rigid_init"][0, :13], [1.0, 0.0, 0.3, scale]])[None]
+    lat.add_rigid_particles(sid, out["rigid_shape"][:9], float(out["rigid_shape"][9]), st17)
+    assert np.array_equal(lat.vertices().reshape(1, -1, 9)[..., :3], out["vert_init"][..., :3])
+    for s in range(1, 13):
+        lat.multi_direct_forcing(4)
+        lat.collideAndStream()
+    v = lat.vertices().reshape(1, -1, 9)
+    assert kit.rel_err(v[..., :3], out["vert_12"][..., :3]) <= 1e-12
+    assert kit.rel_err(lat.rigid_state()[:, :13], out["rigid_12"][:, :13]) <= 1e-11
+    assert kit.rel_err(v[..., 6:], out["vert_12"][..., 6:]) <= 1e-9
+    assert kit.rel_err(lat.download(), out["pop_12"]) <= 1e-12
+
+
+def test_ext_flow_boundaries_bit_exact_vs_oracle(orc):
+    """The lattice side of sphere_in_ext_flow alone (no particle): collide-and-stream with one relaxation rate, x / y walls, and the
+    eight boundary functionals, 6 steps from the reference's initial state with a synthetic force field: bit-identical to the oracle."""
+    g = np.load(kit.GOLDEN / "ib_sphere_ext_flow.npz")
+    rng = np.random.default_rng(5)
+    init = g["pop_init"].copy()
+    init[..., 19:22] = 1e-5 * rng.normal(size=init.shape[:3] + (3,))
+    g2 = dict(pop_init=init, omega=g["omega"], bvel=g["bvel"])
+    lat = _ext_flow_lattice(g2)
+    cells = np.zeros(init.shape[:3] + (23,)); cells[..., :22] = init
+    bvel = np.ascontiguousarray(g["bvel"]); omega = float(g["omega"])
+    planes, edges, _ = kit.ext_flow_boundaries(init.shape[:3])
+    for _ in range(6):
+        lat.collideAndStream()
+        cells = orc.collide_and_stream(cells, (0, 0, 1), omega, 0.0, envelope_swap=False)
+        for (d, o, box) in planes:
+            orc.wall_plane_box(cells, (0, 0, 1), d, o, box, bvel, omega)
+        for (n1, n2, box) in edges:
+            orc.wall_edge(cells, (0, 0, 1), 2, n1, n2, box, bvel, omega)
+    assert np.array_equal(lat.download(), cells[..., :22])
+    vel = lat.computeVelocity()
+    assert np.array_equal(vel[0, :, :], bvel[0, :, :]) and np.array_equal(vel[:, -1, :], bvel[:, -1, :]), "boundary cells report their stored velocity"
+
+
 def test_guo_pipe_wall_vs_golden():
     """GuoRigidWallBoundary (off-lattice pipe wall) + NoDynamics outside, LBM only: bit-identical to the reference."""
     g = np.load(kit.GOLDEN / "lbm_guo_pipe.npz")
