@@ -247,6 +247,7 @@ def ours(args):
         lat.comm_init(rank, world, uid[0])
     lat.set_option(bib.OPT_FUSED_FACE_SWAP, float(args.face_swap))
     lat.set_option(bib.OPT_OVERLAP_FORCES, float(args.overlap_forces))
+    lat.set_option(bib.OPT_PREFETCH_FORCES, float(args.prefetch_forces))
     lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
     body = (1e-6, 0.0, 0.0)
     n_rbc = args.rbcs                               # per GPU
@@ -384,6 +385,7 @@ def main():
     ap.add_argument("--rbcs", type=int, default=1250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_OVERLAP_FORCES (experiments)")
+    ap.add_argument("--prefetch-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_PREFETCH_FORCES (experiments)")
     ap.add_argument("--face-swap", type=int, default=1, choices=[0, 1, 2], help="BIB_OPT_FUSED_FACE_SWAP (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":

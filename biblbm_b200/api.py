@@ -21,13 +21,13 @@ SYMBOLS = [
     "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
-    "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
+    "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
 ]
 
-OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES, OPT_PREFETCH_FORCES = 1, 2, 3, 4, 5, 6, 7, 8, 9
 CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
 PARTICLE_RBC, PARTICLE_CAPSULE, PARTICLE_SEMIRIGID = 0, 1, 2
 POTENTIAL_NONE, POTENTIAL_MORSE, POTENTIAL_SPRING = 0, 1, 2
@@ -211,6 +211,10 @@ class Lattice:
         _check(self.lib.bib_ib_rigid_state_download(self.h, int(first), int(count), _dptr(out)))
         return out
 
+    def rigid_state_upload(self, state19, first=0):
+        st = np.ascontiguousarray(state19, dtype=np.float64).reshape(-1, 19)
+        _check(self.lib.bib_ib_rigid_state_upload(self.h, int(first), st.shape[0], _dptr(st)))
+
     def set_regulator(self, p, target):
         _check(self.lib.bib_ib_set_regulator(self.h, C.c_double(p), C.c_double(target[0]), C.c_double(target[1]), C.c_double(target[2])))
 
@@ -266,6 +270,10 @@ class Lattice:
         assert out.dtype == np.float64 and out.size >= count * 9 and out.flags["C_CONTIGUOUS"]
         _check(self.lib.bib_ib_vertices_download(self.h, C.c_longlong(first), C.c_longlong(count), _dptr(out)))
         return out
+
+    def upload_vertices(self, vertices9, first=0):
+        v = np.ascontiguousarray(vertices9, dtype=np.float64).reshape(-1, 9)
+        _check(self.lib.bib_ib_vertices_upload(self.h, C.c_longlong(first), C.c_longlong(v.shape[0]), _dptr(v)))
 
     def results_download_async(self, out_vertices, out_scalars):
         """Non-blocking read-back of all vertex records and particle scalars into page-locked arrays; see results_wait()."""

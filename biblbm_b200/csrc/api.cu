@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 
 static thread_local std::string g_last_error;
 
@@ -138,6 +139,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->ev_compute) cudaEventDestroy(d->ev_compute);
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->vfrc_next) cudaFree(d->vfrc_next);
     if (d->ev_forces) cudaEventDestroy(d->ev_forces);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
@@ -148,7 +150,7 @@ int bib_domain_destroy(bib_domain* d) {
 // BIB_ENTER: entry points that may change the configuration or the state outside the stepping loop (they invalidate the captured
 // step graph); BIB_ENTER_RO: stepping itself, synchronisation, timing and read-only downloads.
 #define BIB_ENTER_RO(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
-#define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; } while (0)
+#define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; (d)->forces_ready = false; } while (0)
 
 int bib_domain_set_option(bib_domain* d, int key, double value) {
     BIB_ENTER(d);
@@ -160,6 +162,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_STEP_GRAPH: d->use_graph = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_FUSED_FACE_SWAP: d->fused_face_swap = value == 2.0 ? 2 : (value != 0.0 ? 1 : 0); return 1;
         case BIB_OPT_OVERLAP_FORCES: d->overlap_forces = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_PREFETCH_FORCES: d->prefetch_forces = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
     bib_set_error("set_option: unknown key");
@@ -289,6 +292,11 @@ int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, do
     if (count > 0 && !state19) { bib_set_error("rigid_state_download: null argument"); return 0; }
     return ib_rigid_download(d, first_particle, count, state19);
 }
+int bib_ib_rigid_state_upload(bib_domain* d, int first_particle, int count, const double* state19) {
+    BIB_ENTER(d);
+    if (count > 0 && !state19) { bib_set_error("rigid_state_upload: null argument"); return 0; }
+    return ib_rigid_upload(d, first_particle, count, state19);
+}
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz) {
     BIB_ENTER(d);
     d->regulator_p = p; d->regulator_target[0] = tx; d->regulator_target[1] = ty; d->regulator_target[2] = tz;
@@ -397,9 +405,16 @@ int bib_ib_results_wait(bib_domain* d) { BIB_ENTER_RO(d); return ib_results_wait
 // computeVelocity pass of the reference is not needed; then F := body, IB, collide-and-stream.
 static int step_once(bib_domain* d, double body_fx, double body_fy, double body_fz) {
     const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
-    // The vertex forces need the positions only: they are evaluated on a second stream (FP64-bound) beside the band velocity and
-    // the interpolation (HBM / L2-bound) and joined before the spread.
-    const bool fork = d->overlap_forces && ib_forces_independent_of_interpolation(d);
+    // The vertex forces need the positions only. (a) BIB_OPT_PREFETCH_FORCES: those of step t+1 are evaluated on the second stream
+    // (FP64-bound) while the collide-and-stream of step t (HBM-bound) runs, into a second force array, so that vfrc keeps holding
+    // "the forces of the last completed step" for every reader. (b) Otherwise / for the first step: on the second stream beside the
+    // band velocity and the interpolation of the same step, joined before the spread.
+    const bool independent = ib_forces_independent_of_interpolation(d);
+    const bool prefetch = d->prefetch_forces && d->overlap_forces && independent;
+    const bool have = prefetch && d->forces_ready && d->vfrc_next && d->vfrc_next_cap == d->cap_vertices;
+    d->forces_ready = false;
+    if (have) std::swap(d->vfrc, d->vfrc_next);
+    const bool fork = !have && d->overlap_forces && independent;
     if (fork) {
         BIB_CHECK(cudaEventRecord(d->ev_fork, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_fork, 0));
@@ -414,12 +429,34 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
         d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
     }
-    if (fork) {
+    if (have) {
+        if (!ib_spread(d)) return 0;
+    } else if (fork) {
         BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_forces, 0));
         if (!ib_spread(d)) return 0;
     } else if (!ib_forces_and_spread(d)) return 0;
     if (!ib_move_and_voxelize(d)) return 0;
     d->vel_full_valid = false;
+    if (prefetch) {
+        if (d->vfrc_next_cap != d->cap_vertices) {
+            if (d->vfrc_next) { cudaFree(d->vfrc_next); d->vfrc_next = nullptr; d->vfrc_next_cap = 0; }
+            if (cudaMalloc(&d->vfrc_next, (size_t)d->cap_vertices * 3 * sizeof(double)) == cudaSuccess) d->vfrc_next_cap = d->cap_vertices;
+            else { cudaGetLastError(); d->vfrc_next = nullptr; }
+        }
+        if (d->vfrc_next) {
+            BIB_CHECK(cudaEventRecord(d->ev_fork, d->stream));
+            BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_fork, 0));
+            std::swap(d->vfrc, d->vfrc_next);                 // ib_forces writes d->vfrc: aim it at the second array for this call
+            const int ok = ib_forces(d, d->comm_stream);
+            std::swap(d->vfrc, d->vfrc_next);
+            if (!ok) return 0;
+            BIB_CHECK(cudaEventRecord(d->ev_forces, d->comm_stream));
+            if (!lbm_launch_collide_stream(d)) return 0;
+            BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_forces, 0));
+            d->forces_ready = true;
+            return 1;
+        }
+    }
     return lbm_launch_collide_stream(d);
 }
 
@@ -437,6 +474,7 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
         for (; s < 2; ++s) if (!step_once(d, body_fx, body_fy, body_fz)) return 0;      // reach the steady state (allocations, masks, flags)
         const long long l0 = d->launches;
         d->graph_cur = d->cur; d->graph_band_cur = d->band_cur;      // the buffers the captured pair of steps starts from
+        d->graph_vfrc = d->vfrc; d->graph_forces_ready = d->forces_ready;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             const bool ok = step_once(d, body_fx, body_fy, body_fz) && step_once(d, body_fx, body_fy, body_fz);
@@ -458,7 +496,7 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
         d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz) {
         // the graph starts from fixed A/B buffers: after an odd number of steps one plain step realigns the parity
         if (n_steps - s >= 3 && d->cur != d->graph_cur) { if (!step_once(d, body_fx, body_fy, body_fz)) return 0; ++s; }
-        for (; n_steps - s >= 2 && d->cur == d->graph_cur && d->band_cur == d->graph_band_cur; s += 2) {
+        for (; n_steps - s >= 2 && d->cur == d->graph_cur && d->band_cur == d->graph_band_cur && d->vfrc == d->graph_vfrc && d->forces_ready == d->graph_forces_ready; s += 2) {
             BIB_CHECK(cudaGraphLaunch(d->step_graph, d->stream));
             d->launches += d->graph_launches;
         }

@@ -115,6 +115,10 @@ struct bib_domain {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_forces = nullptr;   // bib_step: force evaluation on comm_stream beside the interpolation
     int overlap_forces = 1;               // BIB_OPT_OVERLAP_FORCES
+    int prefetch_forces = 1;              // BIB_OPT_PREFETCH_FORCES: bib_step evaluates the forces of step t+1 beside the collide-and-stream of step t
+    bool forces_ready = false;            // vfrc_next holds the forces of the current vertex positions (cleared by every mutating entry point)
+    double* vfrc_next = nullptr; long long vfrc_next_cap = 0;
+    const double* graph_vfrc = nullptr; bool graph_forces_ready = false;   // force-array parity the captured pair of steps starts from
     long long launches = 0;
     // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
     cudaGraphExec_t step_graph = nullptr; bool graph_dirty = true; int use_graph = 1; long long graph_launches = 0; double graph_body[3] = {0, 0, 0}; int graph_cur = 0, graph_band_cur = 0;
@@ -189,6 +193,7 @@ int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const 
 int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions);
 int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
 int ib_rigid_download(bib_domain* d, int first, int count, double* state19);
+int ib_rigid_upload(bib_domain* d, int first, int count, const double* state19);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
 int ib_forces_and_spread(bib_domain* d);

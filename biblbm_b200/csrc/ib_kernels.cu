@@ -1821,6 +1821,19 @@ int ib_rigid_download(bib_domain* d, int first, int count, double* state19) {
     return 1;
 }
 
+// the host mirror hands back the rigid-body state it holds (the node records travel through ib_vertices_upload)
+int ib_rigid_upload(bib_domain* d, int first, int count, const double* state19) {
+    if (first < 0 || count < 0 || first + count > d->n_particles) { bib_set_error("rigid_state_upload: range"); return 0; }
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    for (int p = first; p < first + count; ++p) {
+        const ParticleGroup* g = nullptr;
+        for (const ParticleGroup& gr : d->groups) if (p >= gr.first_particle && p < gr.first_particle + gr.count) g = &gr;
+        if (!g || g->type != 3) { bib_set_error("rigid_state_upload: not a rigid particle"); return 0; }
+        BIB_CHECK(cudaMemcpy(g->rigid + (size_t)(p - g->first_particle) * RS, state19 + (size_t)(p - first) * 19, 19 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------------ host: IB phases
 static int ensure_band_masks(bib_domain* d) {
     if (d->band_mask && d->band_cap >= d->n_particles) return 1;

@@ -50,6 +50,8 @@ enum {
     BIB_OPT_FUSED_FACE_SWAP = 7,     /* envelope swap of the periodic faces: 1 (default) fused into the collide-and-stream kernel, 2 fused for the x / y faces with
                                         a separate pass over the z faces, 0 separate pass over all faces */
     BIB_OPT_OVERLAP_FORCES = 8,      /* 1 (default): bib_step evaluates the vertex forces on a second stream beside the velocity interpolation (same results) */
+    BIB_OPT_PREFETCH_FORCES = 9,     /* 1 (default): bib_step evaluates the vertex forces of step t+1 on the second stream while the collide-and-stream of
+                                        step t runs (they depend on the advected positions only; same results; needs BIB_OPT_OVERLAP_FORCES) */
     BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
                                         force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
 };
@@ -125,6 +127,9 @@ int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* pa
 int bib_ib_rigid_particles_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
 /* state19 per particle: centre of mass, velocity, angular velocity, quaternion, total force, total torque */
 int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, double* state19);
+/* same layout; a host mirror that handed RigidParticle3D objects to its caller (fsi.get_particle) gives their state back with this call
+ * (node records: bib_ib_vertices_upload) */
+int bib_ib_rigid_state_upload(bib_domain* d, int first_particle, int count, const double* state19);
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz);
 /* fsi.set_boundary(&ParallelPlatesBoundary(y0, y1)) (src/fsi/Boundary.h:300-365, progs/rbcs_in_shear/rbcs_in_shear.cpp:122-123): vertices
  * within 2.5 cells of a plate interpolate / spread with the Roma kernel blended into the 2-point kernel

@@ -23,12 +23,13 @@ REFINC="-I$REF/src -I$REF/externalLibraries -I$REF/progs"
 B200="-I$HERE -I$ROOT/include"
 LINK_B200="$REFOUT/libplb_ref.a -L$ROOT/biblbm_b200 -lbiblbm_b200 -Wl,-rpath,\$ORIGIN/../../biblbm_b200"
 
-build() {   # build <out> <src> <driver dir> <b200|cpu>
-  local out="$1" src="$2" dir="$3" kind="$4"
+build() {   # build <out> <src> <driver dir> <b200|cpu> [extra flags]
+  local out="$1" src="$2" dir="$3" kind="$4" extra="${5:-}"
   if [ -f "$out" ] && [ "$out" -nt "$src" ] && [ "$out" -nt "$HERE/biblbm_overlay/impl.hh" ] && [ "$out" -nt "$HERE/biblbm_overlay/decl.h" ] \
+     && [ "$out" -nt "$HERE/biblbm_overlay/impl_desc.inc" ] && [ "$out" -nt "$HERE/biblbm_overlay/decl_desc.inc" ] \
      && [ "$out" -nt "$ROOT/include/biblbm_b200.h" ]; then return; fi
   echo "building $out"
-  if [ "$kind" = b200 ]; then g++ $BASE $B200 $REFINC -I"$dir" "$src" $LINK_B200 -o "$out"
+  if [ "$kind" = b200 ]; then g++ $BASE $extra $B200 $REFINC -I"$dir" "$src" $LINK_B200 -o "$out"
   else g++ $BASE $REFINC -I"$dir" "$src" "$REFOUT/libplb_ref.a" -o "$out"; fi
 }
 
@@ -39,6 +40,8 @@ patch_params() {  # patch_params <driver.cpp> <out.cpp>
     -e 's|^(\s*)plint output_interval = ([0-9]+);|\1plint output_interval = getenv("BIB_OUTPUT_INTERVAL") ? atol(getenv("BIB_OUTPUT_INTERVAL")) : \2;|' \
     -e 's|for\(int i = 0; i < 13; \+\+i\) \{|for(int i = 0; i < (getenv("BIB_NCASES") ? atoi(getenv("BIB_NCASES")) : 13); ++i) {|' \
     -e 's|^(\s*)const char \* mesh_file = "sphere_dx0_33.msh";|\1const char * mesh_file = getenv("BIB_MESH") ? getenv("BIB_MESH") : "sphere_dx0_33.msh";|' \
+    -e 's|^(\s*)const char \* mesh_file = "sphere_r8.gmsh";|\1const char * mesh_file = getenv("BIB_MESH") ? getenv("BIB_MESH") : "sphere_r8.gmsh";|' \
+    -e 's|^(\s*)plint geoNx = 96, geoNy = 96, geoNz = 96;|\1plint geoNx = getenv("BIB_GEO_N") ? atol(getenv("BIB_GEO_N")) : 96, geoNy = geoNx, geoNz = geoNx;|' \
     -e 's|^(\s*)plint Nt = std::ceil\(20 / gamma_lb\);|\1plint Nt = getenv("BIB_NT") ? atol(getenv("BIB_NT")) : (plint) std::ceil(20 / gamma_lb);|' \
     -e 's|^(\s*)plint output_interval = std::ceil\(1 /gamma_lb / 20\);|\1plint output_interval = getenv("BIB_OUTPUT_INTERVAL") ? atol(getenv("BIB_OUTPUT_INTERVAL")) : (plint) std::ceil(1 /gamma_lb / 20);|' \
     -e 's|get_volume\(\), 10000\);|get_volume(), getenv("BIB_SHRINK_ITERS") ? atol(getenv("BIB_SHRINK_ITERS")) : 10000);|' \
@@ -48,13 +51,17 @@ patch_params() {  # patch_params <driver.cpp> <out.cpp>
     "$1" > "$2"
 }
 
-DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe rigid_particle_in_shear}"
+DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe rigid_particle_in_shear sphere_in_ext_flow}"
 for drv in $DRIVERS; do
   dir="$REF/progs/$drv"
   src="$(ls "$dir"/*.cpp | head -1)"
-  build "$OUT/$drv" "$src" "$dir" b200                       # the unchanged driver
+  extra=""
+  # sphere_in_ext_flow defines its own data-processing functional with a private iteration count that the binding has to read
+  # (overlay/biblbm_overlay/decl_desc.inc): access control is switched off for this driver's build instead of editing its source
+  [ "$drv" = sphere_in_ext_flow ] && extra="-fno-access-control"
+  build "$OUT/$drv" "$src" "$dir" b200 "$extra"               # the unchanged driver
   patch_params "$src" "$OUT/src/${drv}_short.cpp.new"
   if ! cmp -s "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp" 2>/dev/null; then mv "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp"; else rm "$OUT/src/${drv}_short.cpp.new"; fi
-  build "$OUT/${drv}_short_b200" "$OUT/src/${drv}_short.cpp" "$dir" b200
+  build "$OUT/${drv}_short_b200" "$OUT/src/${drv}_short.cpp" "$dir" b200 "$extra"
   build "$REFOUT/${drv}_short_cpu" "$OUT/src/${drv}_short.cpp" "$dir" cpu
 done

@@ -216,3 +216,70 @@ def test_rbc_in_pipe_driver(tmp_path):
                 assert xa[k].shape == ya[k].shape and np.max(np.abs(xa[k] - ya[k])) <= 1e-7, (f, k)
             checked += 1
     assert checked >= 8
+
+
+def _vti_arrays(path):
+    import base64
+    out = {}
+    for m in re.finditer(r'<DataArray type="(\w+)" Name="(\w+)"[^>]*>\n([^<]*)\n</DataArray>', path.read_text()):
+        raw = m.group(3).strip()
+        n = np.frombuffer(base64.b64decode(raw[:8]), dtype=np.uint32)[0]
+        out[m.group(2)] = np.frombuffer(base64.b64decode(raw[8:])[:n], dtype=np.float32)
+    return out
+
+
+def test_sphere_in_ext_flow_driver(tmp_path):
+    """progs/sphere_in_ext_flow (BASELINE.json configs[1]) at the driver's own size: 97^3 ForcedD3Q19 lattice with the single-rate
+    GuoExternalForceBGKdynamics, extensionalFlowSetup (velocity planes on the x / y faces, four external velocity edges along z), a
+    rigid sphere of radius 8 (RigidParticle3D) coupled by the DRIVER'S OWN MultiDirectForcingFunctional3D (4 sub-iterations), which the
+    binding runs as one device call. 21 steps; particle csv every 10, velocity / particle VTK every 10, both checkpoints at the end.
+    The quaternion exponential map uses the device's sin / cos, so outputs are compared numerically (1e-9 relative)."""
+    _need(B200 / "sphere_in_ext_flow_short_b200", CPU / "sphere_in_ext_flow_short_cpu")
+    shape, _, _, _ = kit.load_rbc_fixture()
+    c = shape.verts.mean(0)
+    verts = (shape.verts - c) * (8.0 / float(np.linalg.norm(shape.verts - c, axis=1).mean()))
+    env = dict(BIB_NT="20", BIB_OUTPUT_INTERVAL="10", BIB_MESH="sphere626_r8.gmsh")
+    dirs = {}
+    for name, exe, extra in (("cpu", CPU / "sphere_in_ext_flow_short_cpu", {}), ("gpu", B200 / "sphere_in_ext_flow_short_b200", {"BIB_DETERMINISTIC_SPREAD": "1"})):
+        d = tmp_path / name
+        d.mkdir()
+        kit.write_gmsh(d / "sphere626_r8.gmsh", verts, shape.tris)
+        out = run_driver(exe, d, dict(env, **extra))
+        dirs[name] = (d, out)
+    x, y = numbers(dirs["cpu"][1]), numbers(dirs["gpu"][1])
+    assert x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x)))
+    files = [f for f in all_files(dirs["cpu"][0]) if not f.endswith(".gmsh")]
+    assert files == [f for f in all_files(dirs["gpu"][0]) if not f.endswith(".gmsh")] and len(files) >= 9, files
+    checked = 0
+    for f in files:
+        a, b = dirs["cpu"][0] / f, dirs["gpu"][0] / f
+        if f.endswith(".csv"):
+            x, y = numbers(a.read_text()), numbers(b.read_text())
+            assert x.size >= 3 * 13 and x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x))), f
+            assert np.abs(x.reshape(-1, 13)[-1, 7:10]).max() > 0          # the coupling force is not trivially zero
+            checked += 1
+        elif f.endswith("checkpoint_lbm.dat"):
+            x, y = np.fromfile(a), np.fromfile(b)
+            assert x.shape == y.shape and x.size == 97 ** 3 * 22 and np.max(np.abs(x - y)) <= 1e-9, f
+            checked += 1
+        elif f.endswith(".vti"):
+            xa, ya = _vti_arrays(a), _vti_arrays(b)
+            assert set(xa) == set(ya) and "velocity" in xa
+            for k in xa:
+                assert xa[k].shape == ya[k].shape and np.max(np.abs(xa[k] - ya[k])) <= 1e-7, (f, k)
+            checked += 1
+        elif f.endswith(".vtu"):
+            # appended raw data: [u32 length][626 x 3 float32] positions, the same for force_tot, then the (integer) cell arrays
+            ra, rb = a.read_bytes(), b.read_bytes()
+            ka, kb = ra.index(b"<AppendedData"), rb.index(b"<AppendedData")
+            assert ra[:ka] == rb[:kb]
+            da, db = ra[ra.index(b"_", ka) + 1:], rb[rb.index(b"_", kb) + 1:]
+            nb = 626 * 3 * 4
+            for off, tol in ((0, 1e-5), (4 + nb, 1e-9)):           # positions ~ 50 in float32; forces ~ 1e-6
+                x = np.frombuffer(da[off + 4:off + 4 + nb], dtype=np.float32); y = np.frombuffer(db[off + 4:off + 4 + nb], dtype=np.float32)
+                assert np.max(np.abs(x - y)) <= tol, (f, off)
+            assert da[2 * (4 + nb):] == db[2 * (4 + nb):], f
+            checked += 1
+        elif "checkpoint_fsi" in f:
+            assert a.stat().st_size == b.stat().st_size, f
+    assert checked >= 6, (checked, files)

@@ -440,20 +440,29 @@ def test_step_graph_equals_plain_launches(rbc):
 
 
 def test_overlapped_force_evaluation_equals_serial(rbc):
-    """BIB_OPT_OVERLAP_FORCES: bib_step evaluates the vertex forces on a second stream beside the velocity interpolation and joins
-    before the spread; results are bit-identical to the serial order, with and without the step graph."""
+    """BIB_OPT_OVERLAP_FORCES / BIB_OPT_PREFETCH_FORCES: bib_step evaluates the vertex forces on a second stream -- those of step t+1
+    beside the collide-and-stream of step t (prefetch, into a second force array), or beside the velocity interpolation of the same
+    step -- and joins before the spread; positions, velocities, FORCES and populations are bit-identical to the serial order, with
+    and without the step graph, across odd / even step counts and a host-side vertex upload in between."""
     shape, params, _, _ = rbc
     g = np.load(kit.GOLDEN / "ib_rbc_in_shear.npz")
     out = []
-    for overlap, graph in ((1.0, 1.0), (1.0, 0.0), (0.0, 0.0)):
-        lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0, bib.OPT_STEP_GRAPH: graph, bib.OPT_OVERLAP_FORCES: overlap})
+    for overlap, graph, prefetch in ((1.0, 1.0, 1.0), (1.0, 0.0, 1.0), (1.0, 1.0, 0.0), (1.0, 0.0, 0.0), (0.0, 0.0, 0.0)):
+        lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0, bib.OPT_STEP_GRAPH: graph, bib.OPT_OVERLAP_FORCES: overlap, bib.OPT_PREFETCH_FORCES: prefetch})
         sid = lat.register_shape(shape.verts, shape.tris)
         lat.add_particles(sid, params, g["vert_init"][..., :3])
         lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
-        lat.step((1e-6, 0.0, 0.0), n=40)
-        out.append((lat.vertices(), lat.download()))
-    for v, pop in out[1:]:
-        assert np.array_equal(v, out[0][0]) and np.array_equal(pop, out[0][1])
+        lat.step((1e-6, 0.0, 0.0), n=21)
+        mid = lat.vertices()
+        lat.step((1e-6, 0.0, 0.0), n=8)
+        v = lat.vertices()
+        v[:, 0] += 1e-3                      # the host moves the particle: prefetched forces must be dropped
+        lat.upload_vertices(v)
+        lat.step((1e-6, 0.0, 0.0), n=11)
+        out.append((mid, lat.vertices(), lat.download()))
+    for mid, v, pop in out[1:]:
+        assert np.array_equal(mid, out[0][0]) and np.array_equal(v, out[0][1]) and np.array_equal(pop, out[0][2])
+    assert np.abs(out[0][1][:, 6:]).max() > 0
 
 
 def test_async_result_readback_matches_golden(rbc):

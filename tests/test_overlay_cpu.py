@@ -27,6 +27,19 @@ def test_unchanged_driver_binds_to_the_cabi(driver):
     assert set(used) <= set(bib.SYMBOLS), "the binding uses symbols the header does not declare"
 
 
+def test_sphere_in_ext_flow_binds_to_the_cabi():
+    """The ForcedD3Q19Descriptor instance of the binding: the driver's own MultiDirectForcingFunctional3D resolves to one device call."""
+    exe = BUILD / "sphere_in_ext_flow"
+    if not exe.exists():
+        pytest.skip("overlay/build_drivers.sh has not run (needs the reference sources)")
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", str(exe)], capture_output=True, text=True, check=True).stdout
+    used = sorted({line.split()[-1] for line in undefined.splitlines() if " bib_" in line})
+    for sym in ("bib_domain_create", "bib_collide_and_stream", "bib_add_velocity_boundary", "bib_add_velocity_edge", "bib_ib_rigid_particles_add",
+                "bib_ib_rigid_state_download", "bib_ib_multi_direct_forcing", "bib_compute_velocity"):
+        assert sym in used, f"sphere_in_ext_flow does not call {sym}"
+    assert set(used) <= set(bib.SYMBOLS)
+
+
 def test_driver_fails_loudly_without_gpu(tmp_path):
     exe = BUILD / "rbc_in_shear_short_b200"
     if not exe.exists():
