@@ -22,7 +22,7 @@ SYMBOLS = [
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
-    "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload",
+    "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload", "bib_ib_vertex_forces_preload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
 ]
@@ -274,6 +274,10 @@ class Lattice:
     def upload_vertices(self, vertices9, first=0):
         v = np.ascontiguousarray(vertices9, dtype=np.float64).reshape(-1, 9)
         _check(self.lib.bib_ib_vertices_upload(self.h, C.c_longlong(first), C.c_longlong(v.shape[0]), _dptr(v)))
+
+    def preload_vertex_forces(self, forces3, first=0):
+        f = np.ascontiguousarray(forces3, dtype=np.float64).reshape(-1, 3)
+        _check(self.lib.bib_ib_vertex_forces_preload(self.h, C.c_longlong(first), C.c_longlong(f.shape[0]), _dptr(f)))
 
     def results_download_async(self, out_vertices, out_scalars):
         """Non-blocking read-back of all vertex records and particle scalars into page-locked arrays; see results_wait()."""

@@ -377,6 +377,12 @@ int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long coun
     if (count > 0 && !vertices9) { bib_set_error("vertices_upload: null argument"); return 0; }
     return ib_vertices_upload(d, first_vertex, count, vertices9);
 }
+int bib_ib_vertex_forces_preload(bib_domain* d, long long first_vertex, long long count, const double* forces3) {
+    BIB_ENTER(d);
+    if (count > 0 && !forces3) { bib_set_error("vertex_forces_preload: null argument"); return 0; }
+    if (d->n_ranks > 1) { bib_set_error("vertex_forces_preload: single-slab domains only"); return 0; }
+    return ib_forces_preload(d, first_vertex, count, forces3);
+}
 int bib_ib_local_slots(bib_domain* d, int* global_ids, int* roles, int capacity, int* n_slots) {
     BIB_ENTER_RO(d);
     if (!global_ids || !roles || !n_slots) { bib_set_error("local_slots: null argument"); return 0; }

@@ -118,6 +118,7 @@ struct bib_domain {
     int prefetch_forces = 1;              // BIB_OPT_PREFETCH_FORCES: bib_step evaluates the forces of step t+1 beside the collide-and-stream of step t
     bool forces_ready = false;            // vfrc_next holds the forces of the current vertex positions (cleared by every mutating entry point)
     double* vfrc_next = nullptr; long long vfrc_next_cap = 0;
+    bool vfrc_preloaded = false;          // bib_ib_vertex_forces_preload: the next force evaluation adds to vfrc instead of starting from zero
     const double* graph_vfrc = nullptr; bool graph_forces_ready = false;   // force-array parity the captured pair of steps starts from
     long long launches = 0;
     // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
@@ -194,6 +195,7 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
 int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
 int ib_rigid_download(bib_domain* d, int first, int count, double* state19);
 int ib_rigid_upload(bib_domain* d, int first, int count, const double* state19);
+int ib_forces_preload(bib_domain* d, long long first, long long count, const double* f3);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
 int ib_forces_and_spread(bib_domain* d);

@@ -1821,6 +1821,23 @@ int ib_rigid_download(bib_domain* d, int first, int count, double* state19) {
     return 1;
 }
 
+// Host-evaluated ForceDecorators (src/fsi/ForceDecorator.h:11-13; ImmersedBoundaryDynamics_forces.hh:293-297 applies them after reset_forces()
+// and before compute_forces()): the next force evaluation starts from these per-vertex values instead of zero.
+int ib_forces_preload(bib_domain* d, long long first, long long count, const double* f3) {
+    if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertex_forces_preload: range"); return 0; }
+    if (d->n_vertices == 0) return 1;
+    if (!d->vfrc_preloaded) BIB_CHECK(cudaMemsetAsync(d->vfrc, 0, (size_t)d->cap_vertices * 3 * sizeof(double), d->stream));
+    if (count > 0) {
+        std::vector<double> tmp((size_t)count * 3);
+        for (long long v = 0; v < count; ++v) for (int c = 0; c < 3; ++c) tmp[(size_t)c * count + v] = f3[(size_t)v * 3 + c];
+        for (int c = 0; c < 3; ++c)
+            BIB_CHECK(cudaMemcpyAsync(d->vfrc + (size_t)c * d->cap_vertices + first, tmp.data() + (size_t)c * count, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        BIB_CHECK(cudaStreamSynchronize(d->stream));
+    }
+    d->vfrc_preloaded = true;
+    return 1;
+}
+
 // the host mirror hands back the rigid-body state it holds (the node records travel through ib_vertices_upload)
 int ib_rigid_upload(bib_domain* d, int first, int count, const double* state19) {
     if (first < 0 || count < 0 || first + count > d->n_particles) { bib_set_error("rigid_state_upload: range"); return 0; }
@@ -1957,6 +1974,9 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
     Geo wg = make_geo(d);
     if (d->wall_bkind >= 0) { wg.plates = d->wall_bkind; wg.py0 = d->wall_b[0]; wg.py1 = d->wall_b[1]; wg.prad = d->wall_b[2]; }
     const bool wall = d->wall_pot.type != 0 && wg.plates != 0;
+    if (wall && d->vfrc_preloaded) { bib_set_error("vertex_forces_preload cannot be combined with a device-side wall interaction"); return 0; }
+    const bool init = wall || d->vfrc_preloaded;       // vfrc already holds the decorators' contribution
+    d->vfrc_preloaded = false;
     if (wall) {
         if (d->n_ranks > 1) { bib_set_error("wall interaction forces: single-slab domains only (round 1)"); return 0; }
         k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, st>>>(wg, d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
@@ -1969,7 +1989,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             c.nv = s.nv; c.nt = s.nt; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
             c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
             for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
-            c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
+            c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
             k_rigid_forces<<<gr.count, 256, 0, st>>>(c, d->vpos, d->vvel, d->vfrc);
             d->launches++;
             continue;
@@ -1978,7 +1998,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             SemiParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
             c.links = s.links; c.link_len = s.link_len; c.v_link_off = s.v_link_off; c.v_link = s.v_link; c.rest_radial = s.rest_radial;
-            c.k_in = gr.params[1]; c.k_out = gr.params[2]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
+            c.k_in = gr.params[1]; c.k_out = gr.params[2]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
             const size_t smem = (size_t)s.nv * 6 * sizeof(double);
             if (smem > 200 * 1024) { bib_set_error("semi-rigid particles: mesh too large for the shared-memory kernel"); return 0; }
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_semirigid_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1990,7 +2010,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             CapParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle; c.count = gr.count;
             c.tris = s.tris; c.tri_area = s.tri_area; c.rest = s.verts; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri;
-            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = wall ? 1 : 0;
+            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
             const size_t smem = (size_t)s.nv * 3 * sizeof(double);
             c.use_smem = smem <= 200 * 1024;
             if (c.use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_capsule_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2006,7 +2026,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
         q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
         q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
         q.role = d->ms ? d->ms->role : nullptr;
-        q.f_init = wall ? d->vfrc : nullptr;
+        q.f_init = init ? d->vfrc : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
         if (s.nv <= RF_THREADS * RF_VPT) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);

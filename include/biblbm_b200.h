@@ -169,6 +169,12 @@ int bib_ib_step(bib_domain* d);
 int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations);
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9);
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
+/* ForceDecorators the library does not implement itself (any user class derived from fsi::ForceDecorator, src/fsi/ForceDecorator.h:11-13,
+ * e.g. OpticalTweezerForce of progs/deformation_test/deformation_test.cpp:24-39): the host evaluates them and hands the per-vertex result
+ * ([count][3]) over; the NEXT force evaluation (bib_ib_compute_and_spread_forces / bib_ib_step) starts from these values instead of zero,
+ * exactly where the reference applies its decorators (ImmersedBoundaryDynamics_forces.hh:293-297). Vertices outside the range start from 0.
+ * One-shot: call it before every force evaluation that needs it. Single-slab domains. */
+int bib_ib_vertex_forces_preload(bib_domain* d, long long first_vertex, long long count, const double* forces3);
 /* per particle {area, volume, com[3], bbox x0,x1,y0,y1,z0,z1} (ParticleBase3D::area/volume/center_of_mass/bounding_box) */
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11);
 /* Non-blocking read-back of ALL vertex records and particle scalars of this slab (what write_lightweight_particle_data /

@@ -102,20 +102,22 @@ def test_rbc_in_shear_driver_atomic_spread(tmp_path, mesh):
         assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(a))), f
 
 
-def _compare_runs(tmp_path, driver, env, args=(), meshes=(), min_files=4):
+def _compare_runs(tmp_path, driver, env, args=(), meshes=(), min_files=4, texts=()):
     _need(B200 / f"{driver}_short_b200", CPU / f"{driver}_short_cpu")
     d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
     for d in (d_cpu, d_gpu):
         d.mkdir()
         for name, (verts, tris) in meshes:
             kit.write_gmsh(d / name, verts, tris)
+        for name, text in texts:
+            (d / name).write_text(text)
     out_cpu = run_driver(CPU / f"{driver}_short_cpu", d_cpu, env, args)
     out_gpu = run_driver(B200 / f"{driver}_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1"), args)
     assert out_gpu == out_cpu
     files = all_files(d_cpu)
     assert files == all_files(d_gpu) and len(files) >= min_files, files
     for f in files:
-        if f.endswith(".msh") or "profile" in f:      # inputs; wall-clock timer report
+        if f.endswith(".msh") or "profile" in f or f in [t[0] for t in texts]:      # inputs; wall-clock timer report
             continue
         assert same_file(d_cpu / f, d_gpu / f), f"{f} differs"
     return files
@@ -283,3 +285,24 @@ def test_sphere_in_ext_flow_driver(tmp_path):
         elif "checkpoint_fsi" in f:
             assert a.stat().st_size == b.stat().st_size, f
     assert checked >= 6, (checked, files)
+
+
+DEFORMATION_XML = """<?xml version="1.0" ?>
+<forcing><Nrelax>12</Nrelax><force_steps>2</force_steps><min_force>0</min_force><max_force>200e-12</max_force><node_fraction>0.02</node_fraction></forcing>
+<units><tau>4</tau><dx>0.5e-6</dx><nu_plasma>1.46e-6</nu_plasma><rho_plasma>1025</rho_plasma></units>
+<rbc><shear_modulus>6e-6</shear_modulus><bending_energy>4e-18</bending_energy><poisson_ratio>0.995</poisson_ratio><lambda>1</lambda>
+<mesh>sphere_TRImesh_626n_1248el.msh</mesh><deflation_factor>0.59</deflation_factor></rbc>
+<output><folder>out</folder></output>
+"""
+
+
+def test_deformation_test_driver_bit_identical(tmp_path):
+    """progs/deformation_test (optical-tweezers stretching of one RBC in a fully periodic box at negative coordinates): two features no
+    other driver uses -- a ForceDecorator class defined in the DRIVER (OpticalTweezerForce; evaluated by its own host code and handed
+    over with bib_ib_vertex_forces_preload) and the call order computeVelocity -> collideAndStream -> setExternalVector -> IB (the
+    binding evaluates the promised velocity field and interpolates before the collision). 26 steps, two force levels; the deformation
+    log, velocity VTK and particle VTK files are byte-identical to the CPU reference."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    files = _compare_runs(tmp_path, "deformation_test", dict(BIB_SHRINK_ITERS="2000"), args=("input.xml",),
+                          meshes=[("sphere_TRImesh_626n_1248el.msh", (shape.verts, shape.tris))], min_files=7, texts=[("input.xml", DEFORMATION_XML)])
+    assert any(f.endswith("deformation0.txt") for f in files) and sum(f.endswith(".vti") for f in files) == 2
