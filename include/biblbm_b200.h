@@ -63,7 +63,9 @@ int bib_device_count(int* count);
 /* ---- lattice (replaces CoProcessor3D::addDomain / send / receive / collideAndStream, coProcessor3D.h:71-109, and
  *      MultiBlockLattice3D<double,ForcedPhaseD3Q19Descriptor>::collideAndStream, src/multiBlock/multiBlockLattice3D.hh:306-348)
  * nx,ny,nz: size of THIS slab (x is the slab direction); periodic[3]: global periodicity (x periodicity of a multi-slab
- * domain is realised by the halo exchange, see bib_comm_*). n_ext must be 4 (ForcedPhaseD3Q19Descriptor). */
+ * domain is realised by the halo exchange, see bib_comm_*). n_ext = 4: ForcedPhaseD3Q19Descriptor cells (19 + {Fx,Fy,Fz,phase}),
+ * GuoExternalForceVOFDynamics with two relaxation rates; n_ext = 3: ForcedD3Q19Descriptor cells (19 + {Fx,Fy,Fz}), the single-rate
+ * GuoExternalForceBGKdynamics (omega_inner is ignored; 22 doubles per cell in upload / download). */
 int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner,
                       const int periodic[3], int device, bib_domain** out);
 int bib_domain_destroy(bib_domain* d);

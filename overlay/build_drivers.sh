@@ -51,17 +51,23 @@ patch_params() {  # patch_params <driver.cpp> <out.cpp>
     "$1" > "$2"
 }
 
-DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe rigid_particle_in_shear sphere_in_ext_flow}"
+DRIVERS="${@:-rbc_in_shear capsule_in_shear rbcs_in_shear rbc_in_pipe rigid_particle_in_shear sphere_in_ext_flow deformation_test}"
+JOBS="${BIB_BUILD_JOBS:-$(( $(nproc) > 6 ? 6 : $(nproc) ))}"      # one g++ per translation unit, ~2 GB each
+TASKS="$(mktemp)"
+trap 'rm -f "$TASKS"' EXIT
 for drv in $DRIVERS; do
   dir="$REF/progs/$drv"
   src="$(ls "$dir"/*.cpp | head -1)"
-  extra=""
+  extra="-"
   # sphere_in_ext_flow defines its own data-processing functional with a private iteration count that the binding has to read
   # (overlay/biblbm_overlay/decl_desc.inc): access control is switched off for this driver's build instead of editing its source
   [ "$drv" = sphere_in_ext_flow ] && extra="-fno-access-control"
-  build "$OUT/$drv" "$src" "$dir" b200 "$extra"               # the unchanged driver
   patch_params "$src" "$OUT/src/${drv}_short.cpp.new"
   if ! cmp -s "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp" 2>/dev/null; then mv "$OUT/src/${drv}_short.cpp.new" "$OUT/src/${drv}_short.cpp"; else rm "$OUT/src/${drv}_short.cpp.new"; fi
-  build "$OUT/${drv}_short_b200" "$OUT/src/${drv}_short.cpp" "$dir" b200 "$extra"
-  build "$REFOUT/${drv}_short_cpu" "$OUT/src/${drv}_short.cpp" "$dir" cpu
+  echo "$OUT/$drv $src $dir b200 $extra" >> "$TASKS"                                   # the unchanged driver
+  echo "$OUT/${drv}_short_b200 $OUT/src/${drv}_short.cpp $dir b200 $extra" >> "$TASKS"
+  echo "$REFOUT/${drv}_short_cpu $OUT/src/${drv}_short.cpp $dir cpu -" >> "$TASKS"
 done
+export -f build
+export HERE ROOT REF OUT REFOUT BASE REFINC B200 LINK_B200
+xargs -P "$JOBS" -L 1 bash -c 'e="$5"; [ "$e" = "-" ] && e=""; build "$1" "$2" "$3" "$4" "$e"' _ < "$TASKS"
