@@ -230,6 +230,46 @@ def _vti_arrays(path):
     return out
 
 
+def _compare_outputs_numeric(d_cpu, d_gpu, nv, min_checked, skip=()):
+    """File-by-file numeric comparison of two driver output trees: text tables 1e-9 relative, Palabos lattice checkpoints 1e-9 absolute,
+    velocity .vti (float32) 1e-7, particle .vtu (float32 appended data: positions 1e-5, forces 1e-9, connectivity byte-identical)."""
+    files = [f for f in all_files(d_cpu) if not f.endswith((".gmsh", ".msh")) and f not in skip]
+    assert files == [f for f in all_files(d_gpu) if not f.endswith((".gmsh", ".msh")) and f not in skip], files
+    checked = 0
+    for f in files:
+        a, b = d_cpu / f, d_gpu / f
+        if f.endswith((".csv", ".txt")):
+            x, y = numbers(a.read_text()), numbers(b.read_text())
+            assert x.size > 0 and x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x))), f
+            checked += 1
+        elif f.endswith("checkpoint_lbm.dat"):
+            x, y = np.fromfile(a), np.fromfile(b)
+            assert x.shape == y.shape and x.size > 0 and np.max(np.abs(x - y)) <= 1e-9, f
+            checked += 1
+        elif f.endswith(".vti"):
+            xa, ya = _vti_arrays(a), _vti_arrays(b)
+            assert set(xa) == set(ya) and "velocity" in xa
+            for k in xa:
+                assert xa[k].shape == ya[k].shape and np.max(np.abs(xa[k] - ya[k])) <= 1e-7, (f, k)
+            checked += 1
+        elif f.endswith(".vtu"):
+            # appended raw data: [u32 length][nv x 3 float32] positions, the same for force_tot, then the (integer) cell arrays
+            ra, rb = a.read_bytes(), b.read_bytes()
+            ka, kb = ra.index(b"<AppendedData"), rb.index(b"<AppendedData")
+            assert ra[:ka] == rb[:kb]
+            da, db = ra[ra.index(b"_", ka) + 1:], rb[rb.index(b"_", kb) + 1:]
+            nb = nv * 3 * 4
+            for off, tol in ((0, 1e-5), (4 + nb, 1e-9)):           # positions ~ 50 in float32; forces ~ 1e-4
+                x = np.frombuffer(da[off + 4:off + 4 + nb], dtype=np.float32); y = np.frombuffer(db[off + 4:off + 4 + nb], dtype=np.float32)
+                assert np.max(np.abs(x - y)) <= tol, (f, off)
+            assert da[2 * (4 + nb):] == db[2 * (4 + nb):], f
+            checked += 1
+        elif "checkpoint_fsi" in f and f.endswith("0.plb"):
+            assert a.stat().st_size == b.stat().st_size, f
+    assert checked >= min_checked, (checked, files)
+    return files
+
+
 def test_sphere_in_ext_flow_driver(tmp_path):
     """progs/sphere_in_ext_flow (BASELINE.json configs[1]) at the driver's own size: 97^3 ForcedD3Q19 lattice with the single-rate
     GuoExternalForceBGKdynamics, extensionalFlowSetup (velocity planes on the x / y faces, four external velocity edges along z), a
@@ -250,41 +290,13 @@ def test_sphere_in_ext_flow_driver(tmp_path):
         dirs[name] = (d, out)
     x, y = numbers(dirs["cpu"][1]), numbers(dirs["gpu"][1])
     assert x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x)))
-    files = [f for f in all_files(dirs["cpu"][0]) if not f.endswith(".gmsh")]
-    assert files == [f for f in all_files(dirs["gpu"][0]) if not f.endswith(".gmsh")] and len(files) >= 9, files
-    checked = 0
-    for f in files:
-        a, b = dirs["cpu"][0] / f, dirs["gpu"][0] / f
-        if f.endswith(".csv"):
-            x, y = numbers(a.read_text()), numbers(b.read_text())
-            assert x.size >= 3 * 13 and x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x))), f
-            assert np.abs(x.reshape(-1, 13)[-1, 7:10]).max() > 0          # the coupling force is not trivially zero
-            checked += 1
-        elif f.endswith("checkpoint_lbm.dat"):
-            x, y = np.fromfile(a), np.fromfile(b)
-            assert x.shape == y.shape and x.size == 97 ** 3 * 22 and np.max(np.abs(x - y)) <= 1e-9, f
-            checked += 1
-        elif f.endswith(".vti"):
-            xa, ya = _vti_arrays(a), _vti_arrays(b)
-            assert set(xa) == set(ya) and "velocity" in xa
-            for k in xa:
-                assert xa[k].shape == ya[k].shape and np.max(np.abs(xa[k] - ya[k])) <= 1e-7, (f, k)
-            checked += 1
-        elif f.endswith(".vtu"):
-            # appended raw data: [u32 length][626 x 3 float32] positions, the same for force_tot, then the (integer) cell arrays
-            ra, rb = a.read_bytes(), b.read_bytes()
-            ka, kb = ra.index(b"<AppendedData"), rb.index(b"<AppendedData")
-            assert ra[:ka] == rb[:kb]
-            da, db = ra[ra.index(b"_", ka) + 1:], rb[rb.index(b"_", kb) + 1:]
-            nb = 626 * 3 * 4
-            for off, tol in ((0, 1e-5), (4 + nb, 1e-9)):           # positions ~ 50 in float32; forces ~ 1e-6
-                x = np.frombuffer(da[off + 4:off + 4 + nb], dtype=np.float32); y = np.frombuffer(db[off + 4:off + 4 + nb], dtype=np.float32)
-                assert np.max(np.abs(x - y)) <= tol, (f, off)
-            assert da[2 * (4 + nb):] == db[2 * (4 + nb):], f
-            checked += 1
-        elif "checkpoint_fsi" in f:
-            assert a.stat().st_size == b.stat().st_size, f
-    assert checked >= 6, (checked, files)
+    files = _compare_outputs_numeric(dirs["cpu"][0], dirs["gpu"][0], 626, min_checked=8)
+    csv = [f for f in files if f.endswith(".csv")]
+    assert len(csv) == 1 and len(files) >= 9
+    rows = numbers((dirs["cpu"][0] / csv[0]).read_text()).reshape(-1, 13)
+    assert rows.shape[0] == 3 and np.abs(rows[-1, 7:10]).max() > 0           # the coupling force is not trivially zero
+    lbm = [f for f in files if f.endswith("checkpoint_lbm.dat")]
+    assert len(lbm) == 1 and (dirs["cpu"][0] / lbm[0]).stat().st_size == 97 ** 3 * 22 * 8
 
 
 DEFORMATION_XML = """<?xml version="1.0" ?>
@@ -296,13 +308,25 @@ DEFORMATION_XML = """<?xml version="1.0" ?>
 """
 
 
-def test_deformation_test_driver_bit_identical(tmp_path):
+def test_deformation_test_driver(tmp_path):
     """progs/deformation_test (optical-tweezers stretching of one RBC in a fully periodic box at negative coordinates): two features no
     other driver uses -- a ForceDecorator class defined in the DRIVER (OpticalTweezerForce; evaluated by its own host code and handed
     over with bib_ib_vertex_forces_preload) and the call order computeVelocity -> collideAndStream -> setExternalVector -> IB (the
-    binding evaluates the promised velocity field and interpolates before the collision). 26 steps, two force levels; the deformation
-    log, velocity VTK and particle VTK files are byte-identical to the CPU reference."""
+    binding evaluates the promised velocity field and interpolates before the collision). 26 steps, two force levels. stdout and the
+    deformation log are identical; the lattice starts at (-34, -17, -17), so device coordinates = global - origin round differently in
+    the last bit and the float32 VTK payloads are compared numerically (net vertex forces are sums of cancelling terms)."""
+    _need(B200 / "deformation_test_short_b200", CPU / "deformation_test_short_cpu")
     shape, _, _, _ = kit.load_rbc_fixture()
-    files = _compare_runs(tmp_path, "deformation_test", dict(BIB_SHRINK_ITERS="2000"), args=("input.xml",),
-                          meshes=[("sphere_TRImesh_626n_1248el.msh", (shape.verts, shape.tris))], min_files=7, texts=[("input.xml", DEFORMATION_XML)])
-    assert any(f.endswith("deformation0.txt") for f in files) and sum(f.endswith(".vti") for f in files) == 2
+    dirs = {}
+    for name, exe, extra in (("cpu", CPU / "deformation_test_short_cpu", {}), ("gpu", B200 / "deformation_test_short_b200", {"BIB_DETERMINISTIC_SPREAD": "1"})):
+        d = tmp_path / name
+        d.mkdir()
+        kit.write_gmsh(d / "sphere_TRImesh_626n_1248el.msh", shape.verts, shape.tris)
+        (d / "input.xml").write_text(DEFORMATION_XML)
+        dirs[name] = (d, run_driver(exe, d, dict(BIB_SHRINK_ITERS="2000", **extra), args=("input.xml",)))
+    assert dirs["cpu"][1] == dirs["gpu"][1]
+    files = _compare_outputs_numeric(dirs["cpu"][0], dirs["gpu"][0], 626, min_checked=5, skip=("input.xml",))
+    assert filecmp.cmp(dirs["cpu"][0] / "out" / "deformation0.txt", dirs["gpu"][0] / "out" / "deformation0.txt", shallow=False)
+    assert sum(f.endswith(".vti") for f in files) == 2 and sum(f.endswith(".vtu") for f in files) == 2
+    dx = numbers((dirs["cpu"][0] / "out" / "deformation0.txt").read_text()).reshape(-1, 4)
+    assert dx[-1, 2] > dx[0, 2]                          # the cell is being stretched along x
