@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -497,10 +498,12 @@ __global__ void __launch_bounds__(256) k_rbc_forces_cta(RbcParams q, const doubl
 // Element-parallel version: every link / triangle / adjacent-triangle pair is evaluated ONCE per particle (instead of once
 // per incident vertex) into a shared-memory chunk, and each thread then adds the chunk's contributions to its own
 // vertices in ascending element order -- the same per-vertex summation order as RBCParticle::compute_forces, hence the
-// same bits as the gather version, at ~1/3 of the fp64 divide/sqrt work. One CTA per particle, nv <= RF_THREADS*RF_VPT.
+// same bits as the gather version, at ~1/3 of the fp64 divide/sqrt work. One CTA per particle, nv <= RF_THREADS*RF_VPT (vertices per
+// thread: a template parameter so that the per-thread accumulators cost no more registers than the mesh needs).
 #define RF_THREADS 256
-#define RF_VPT 4
+#define RF_VPT_MAX 4
 #define RF_CHUNK 7488          // doubles per chunk (58.5 KB): 2496 links x3, 416 triangles x18, 624 pairs x12
+template <int RF_VPT>
 __global__ void __launch_bounds__(RF_THREADS) k_rbc_forces_elem(RbcParams q, const double* __restrict__ vpos, double* __restrict__ vfrc,
                                                                const double* __restrict__ pstate, int nt, int nl, int np) {
     extern __shared__ double s_mem[];
@@ -2028,11 +2031,13 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
         q.role = d->ms ? d->ms->role : nullptr;
         q.f_init = init ? d->vfrc : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
-        if (s.nv <= RF_THREADS * RF_VPT) {
+        if (s.nv <= RF_THREADS * RF_VPT_MAX) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
-            static size_t sm2_set = 0;
-            if (sm2_set != sm2) { cudaFuncSetAttribute(k_rbc_forces_elem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); sm2_set = sm2; }
-            k_rbc_forces_elem<<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np);
+            const int vpt = (s.nv + RF_THREADS - 1) / RF_THREADS;        // vertices per thread (measured: 3 instead of 4 for the 626-vertex RBC = -0.05 ms)
+#define BIB_RF_LAUNCH(V) do { static size_t set_ = 0; if (set_ != sm2) { cudaFuncSetAttribute(k_rbc_forces_elem<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); set_ = sm2; } \
+                              k_rbc_forces_elem<V><<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np); } while (0)
+            if (vpt <= 1) BIB_RF_LAUNCH(1); else if (vpt == 2) BIB_RF_LAUNCH(2); else if (vpt == 3) BIB_RF_LAUNCH(3); else BIB_RF_LAUNCH(4);
+#undef BIB_RF_LAUNCH
         } else if (smem <= 200 * 1024) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_rbc_forces_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_rbc_forces_cta<<<gr.count, 256, smem, st>>>(q, d->vpos, d->vfrc, d->pstate);
