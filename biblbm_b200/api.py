@@ -23,7 +23,7 @@ SYMBOLS = [
     "bib_velocity_download", "bib_velocity_upload", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload", "bib_ib_vertex_forces_preload",
-    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
+    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_ib_results_count", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
     "bib_kernel_launch_count", "bib_device_memory_bytes",
 ]
 
@@ -285,6 +285,12 @@ class Lattice:
 
     def results_wait(self):
         _check(self.lib.bib_ib_results_wait(self.h))
+
+    def results_count(self):
+        """Particles delivered by the last completed results_download_async (multi-slab: the owned ones, compacted)."""
+        n = C.c_int(0)
+        _check(self.lib.bib_ib_results_count(self.h, C.byref(n)))
+        return n.value
 
     def particle_scalars(self, first=0, count=None, out=None):
         if count is None:

@@ -112,6 +112,8 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
     if (d->results_dev) cudaFree(d->results_dev);
+    if (d->res_list) cudaFree(d->res_list);
+    if (d->res_count_host) cudaFreeHost(d->res_count_host);
     if (d->step_graph) cudaGraphExecDestroy(d->step_graph);
     if (d->fflag) cudaFree(d->fflag);
     if (d->guo_nodes) cudaFree(d->guo_nodes);
@@ -405,6 +407,11 @@ int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scal
     return ib_results_download_async(d, vertices9, scalars11);
 }
 int bib_ib_results_wait(bib_domain* d) { BIB_ENTER_RO(d); return ib_results_wait(d); }
+int bib_ib_results_count(bib_domain* d, int* n_particles) {
+    BIB_ENTER_RO(d);
+    if (!n_particles) { bib_set_error("results_count: null argument"); return 0; }
+    return ib_results_count(d, n_particles);
+}
 
 // One driver step: the velocity the IB interpolates is u = j(f^t)/rho + F^{t-1}/2 evaluated on demand from the current
 // populations and the force field still holding last step's total force, so the dense

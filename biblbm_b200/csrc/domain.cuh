@@ -164,6 +164,9 @@ struct bib_domain {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
     bool copy_in_flight = false;
+    int* res_list = nullptr;              // [1 + cap]: number and slot indices of the owned particles (multi-slab async read-back)
+    int* res_count_host = nullptr;        // page-locked: how many particles the last async read-back delivered
+    bool res_compact = false;
     MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 
@@ -195,6 +198,7 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
 int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17);
 int ib_rigid_download(bib_domain* d, int first, int count, double* state19);
 int ib_rigid_upload(bib_domain* d, int first, int count, const double* state19);
+int ib_results_count(bib_domain* d, int* n);
 int ib_forces_preload(bib_domain* d, long long first, long long count, const double* f3);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);

@@ -2174,6 +2174,53 @@ int ib_vertices_download(bib_domain* d, long long first, long long count, double
     std::memcpy(v9, d->pinned, bytes);
     return 1;
 }
+// Multi-slab domains deliver the particles this slab OWNS, compacted in slot order (what the reference's per-rank writers see,
+// ImmersedBoundaryDynamics.hh:232-246): the slot arrays are sized for the worst case, and a DMA of all of them (113 MB per step and rank
+// in the bench) does not fit under one step once the lattice kernel saturates HBM. The number of owned particles lives on the device,
+// so the copy is done by a small kernel on the copy stream that stores straight into the caller's page-locked (UVA-mapped) buffers.
+__global__ void __launch_bounds__(1024) k_results_list(const int* __restrict__ role, int cap, int* __restrict__ list, int* __restrict__ count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < cap; s0 += 1024) {
+        const int s = s0 + threadIdx.x;
+        const bool take = s < cap && role[s] == 1;
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int k = 0; k < w; ++k) before += s_warp[k];
+        if (take) list[before + __popc(m & ((1u << lane) - 1u))] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 32; ++k) t += s_warp[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = s_base;
+}
+__global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, double* __restrict__ out_s, const int* __restrict__ list, const int* __restrict__ count,
+                                                    int nv, const double* __restrict__ vpos, const double* __restrict__ vvel, const double* __restrict__ vfrc,
+                                                    const double* __restrict__ pstate, long long cap_v) {
+    const int j = blockIdx.x;
+    if (j >= *count) return;
+    const int s = list[j];
+    for (int t = threadIdx.x; t < nv * 9; t += blockDim.x) {
+        const int v = t / 9, k = t % 9;
+        const double* src = k < 3 ? vpos : (k < 6 ? vvel : vfrc);
+        out_v[(long long)j * nv * 9 + t] = src[(long long)(k % 3) * cap_v + (long long)s * nv + v];
+    }
+    if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_push_host(double* __restrict__ host_v, double* __restrict__ host_s, int* __restrict__ host_count,
+                                                   const double* __restrict__ stage_v, const double* __restrict__ stage_s, const int* __restrict__ count, int nv) {
+    const long long n = *count;
+    const long long nvd = n * nv * 9, nsd = n * 11;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nvd; t += (long long)gridDim.x * blockDim.x) host_v[t] = stage_v[t];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nsd; t += (long long)gridDim.x * blockDim.x) host_s[t] = stage_s[t];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *host_count = (int)n;
+}
+
 // Read-back that overlaps the following steps: the fsi::Vertex records of every slot and the particle scalars are packed on
 // the compute stream into a dedicated staging buffer; a second stream copies them to the caller's page-locked buffers while
 // the compute stream carries on. The next pack waits (on the device) for the previous copy, the host only in ib_results_wait.
@@ -2184,7 +2231,7 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
     cudaGetLastError();
     if (!pinned) { bib_set_error("results_download_async: both host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)"); return 0; }
     if (!d->copy_stream) {
-        BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));   // (a high-priority stream was measured: no difference)
         BIB_CHECK(cudaEventCreateWithFlags(&d->ev_packed, cudaEventDisableTiming));
         BIB_CHECK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
     }
@@ -2198,6 +2245,33 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         d->results_bytes = vb + sb; d->bytes += (long long)(vb + sb);
     }
     if (d->copy_in_flight) BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));      // staging buffer free again
+    double *dev_v = nullptr, *dev_s = nullptr;
+    if (d->ms && cudaHostGetDevicePointer((void**)&dev_v, v9, 0) == cudaSuccess && cudaHostGetDevicePointer((void**)&dev_s, s11, 0) == cudaSuccess) {
+        const MultiSlabIB* m = d->ms;
+        if (!d->res_list) {
+            BIB_CHECK(cudaMalloc(&d->res_list, ((size_t)m->cap + 1) * sizeof(int)));
+            BIB_CHECK(cudaHostAlloc((void**)&d->res_count_host, 64, cudaHostAllocMapped));
+            *d->res_count_host = 0;
+        }
+        int* dev_count_host = nullptr;
+        BIB_CHECK(cudaHostGetDevicePointer((void**)&dev_count_host, d->res_count_host, 0));
+        int* list = d->res_list + 1; int* count = d->res_list;
+        double* stage_v = (double*)d->results_dev; double* stage_s = (double*)((char*)d->results_dev + vb);
+        k_results_list<<<1, 1024, 0, d->stream>>>(m->role, m->cap, list, count);
+        k_pack_slots<<<m->cap, 128, 0, d->stream>>>(stage_v, stage_s, list, count, m->nv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
+        d->launches += 2;
+        BIB_CHECK(cudaEventRecord(d->ev_packed, d->stream));
+        BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_packed, 0));
+        k_push_host<<<32, 256, 0, d->copy_stream>>>(dev_v, dev_s, dev_count_host, stage_v, stage_s, count, m->nv);
+        d->launches++;
+        BIB_CHECK(cudaGetLastError());
+        BIB_CHECK(cudaEventRecord(d->ev_copied, d->copy_stream));
+        d->copy_in_flight = true;
+        d->res_compact = true;
+        return 1;
+    }
+    cudaGetLastError();
+    d->res_compact = false;
     if (vb) {
         const int grid = (int)std::min<long long>((d->n_vertices * 9 + 255) / 256, 148 * 16);
         k_pack_vertices<<<grid, 256, 0, d->stream>>>((double*)d->results_dev, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
@@ -2216,6 +2290,12 @@ int ib_results_wait(bib_domain* d) {
     if (!d->copy_in_flight) return 1;
     BIB_CHECK(cudaEventSynchronize(d->ev_copied));
     d->copy_in_flight = false;
+    return 1;
+}
+// number of particles the last completed bib_ib_results_download_async delivered (after ib_results_wait)
+int ib_results_count(bib_domain* d, int* n) {
+    if (d->copy_in_flight) { bib_set_error("results_count: call bib_ib_results_wait first"); return 0; }
+    *n = (d->res_compact && d->res_count_host) ? *d->res_count_host : d->n_particles;
     return 1;
 }
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {

@@ -185,6 +185,10 @@ int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int coun
  * before the wait is allowed with different buffers (the device serialises them). */
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11);
 int bib_ib_results_wait(bib_domain* d);
+/* On a multi-slab domain the slot arrays are sized for the worst case; the asynchronous read-back therefore delivers only the particles
+ * this slab OWNS (what a rank of the reference writes), compacted in ascending slot order (ids: bib_ib_local_slots, role 1), at the start
+ * of both buffers. n_particles = how many the last completed read-back delivered (single slab: all particles). Call after the wait. */
+int bib_ib_results_count(bib_domain* d, int* n_particles);
 /* The reference caches these per particle and refreshes them only in update() (after a move); a particle that was translated
  * or rotated on the host keeps the values computed before (ParticleBase3D::set_center_of_mass, src/fsi/ParticleBase.hh). A host
  * mirror hands its cached values over with this call so that the first force evaluation sees exactly what the reference sees;

@@ -56,6 +56,18 @@ def main():
     gids, roles = lat.local_slots()
     verts = lat.vertices().reshape(len(gids), shape.nv, 9)
     mine = {int(g): verts[s] for s, (g, r) in enumerate(zip(gids, roles)) if r == 1}
+    # asynchronous read-back on a multi-slab domain: the owned particles, compacted in slot order, bit for bit what vertices() holds
+    hv = torch.empty((len(gids) * shape.nv, 9), dtype=torch.float64, pin_memory=True).numpy()
+    hs = torch.empty((len(gids), 11), dtype=torch.float64, pin_memory=True).numpy()
+    lat.results_download_async(hv, hs)
+    lat.results_wait()
+    owned_slots = [s for s, r in enumerate(roles) if r == 1]
+    n_del = lat.results_count()
+    assert n_del == len(owned_slots), (n_del, len(owned_slots))
+    scal = lat.particle_scalars()
+    for j, s in enumerate(owned_slots):
+        assert np.array_equal(hv.reshape(-1, shape.nv, 9)[j], verts[s]), (rank, j, s)
+        assert np.array_equal(hs[j], scal[s]), (rank, j, s)
     cells = torch.from_numpy(lat.download()).cuda()
     parts = [torch.empty_like(cells) for _ in range(world)]
     dist.all_gather(parts, cells)

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Diagnostic (multi-GPU): where does the end-to-end loop of bench.py lose time relative to the device-timed step?
+   torchrun ... tools/e2e_probe.py   -- prints per-variant ms/step on rank 0."""
+import os, sys, time, pathlib
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np, torch, torch.distributed as dist
+import biblbm_b200 as bib
+import bench
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def barrier():
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+nx, ny, nz = 128, 1024, 1024
+lat = bib.Lattice(nx, ny, nz, 1.0, 1.0 / 3.0, periodic=(True, True, True), device=local)
+if world > 1:
+    uid = [bib.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    lat.comm_init(rank, world, uid[0])
+lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
+verts, tris, params, rbc_pos = bench.load_rbc()
+sid = lat.register_shape(verts, tris)
+lat.add_particles(sid, params, bench.rbc_positions(rbc_pos, 1250 * world, (nx * world, ny, nz), 0, seed=7))
+body = (1e-6, 0.0, 0.0)
+lat.step(body, n=5); lat.sync()
+n_slots, n_vert = lat.count()
+hv = [torch.empty((max(1, n_vert), 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+hs = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+K = 10
+lat.results_download_async(hv[0], hs[0]); lat.results_wait()     # first use allocates the staging buffer and the copy stream: not timed
+def run(name, fn):
+    barrier(); t0 = time.perf_counter(); fn(); barrier(); dt = (time.perf_counter() - t0) * 1e3 / K
+    if rank == 0: print(f"{name}: {dt:.3f} ms/step", flush=True)
+run("A  step(K) one call", lambda: lat.step(body, n=K))
+def b():
+    for _ in range(K): lat.step(body, n=1)
+run("B  K x step(1)", b)
+def c():
+    for it in range(K):
+        lat.step(body, n=1); lat.sync()
+run("C  K x (step(1); sync)", c)
+def d():
+    for it in range(K):
+        lat.step(body, n=1)
+        if it > 0: lat.results_wait()
+        lat.results_download_async(hv[it % 2], hs[it % 2])
+    lat.results_wait()
+run("D  bench e2e loop", d)
+def e():
+    for it in range(K):
+        lat.step(body, n=1)
+        lat.results_download_async(hv[it % 2], hs[it % 2])
+        lat.results_wait()
+run("E  step; download; wait (no overlap)", e)
+if rank == 0: print("slots", n_slots, "vertices", n_vert, "d2h MB/step", (n_vert * 72 + n_slots * 88) / 1e6)
+lat.close()
+if world > 1: dist.destroy_process_group()
