@@ -167,6 +167,8 @@ struct bib_domain {
     int* res_list = nullptr;              // [1 + cap]: number and slot indices of the owned particles (multi-slab async read-back)
     int* res_count_host = nullptr;        // page-locked: how many particles the last async read-back delivered
     bool res_compact = false;
+    int res_bound = 0, res_bound_used = 0;            // particles covered by the asynchronous prefix copy (last count + slack)
+    double* res_host_v = nullptr; double* res_host_s = nullptr;   // the caller's buffers of the read-back in flight
     MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 

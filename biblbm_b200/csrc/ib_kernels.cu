@@ -2176,8 +2176,9 @@ int ib_vertices_download(bib_domain* d, long long first, long long count, double
 }
 // Multi-slab domains deliver the particles this slab OWNS, compacted in slot order (what the reference's per-rank writers see,
 // ImmersedBoundaryDynamics.hh:232-246): the slot arrays are sized for the worst case, and a DMA of all of them (113 MB per step and rank
-// in the bench) does not fit under one step once the lattice kernel saturates HBM. The number of owned particles lives on the device,
-// so the copy is done by a small kernel on the copy stream that stores straight into the caller's page-locked (UVA-mapped) buffers.
+// in the bench) does not fit under one step once the lattice kernel saturates HBM. The number of owned particles lives on the device;
+// the host copies a prefix sized by the last count it saw plus slack, and ib_results_wait fetches the (rare) remainder synchronously.
+// (A copy-stream kernel storing straight into mapped host memory was measured too: it only ran after the following step had finished.)
 __global__ void __launch_bounds__(1024) k_results_list(const int* __restrict__ role, int cap, int* __restrict__ list, int* __restrict__ count) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
@@ -2212,15 +2213,6 @@ __global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, 
     }
     if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
 }
-__global__ void __launch_bounds__(256) k_push_host(double* __restrict__ host_v, double* __restrict__ host_s, int* __restrict__ host_count,
-                                                   const double* __restrict__ stage_v, const double* __restrict__ stage_s, const int* __restrict__ count, int nv) {
-    const long long n = *count;
-    const long long nvd = n * nv * 9, nsd = n * 11;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nvd; t += (long long)gridDim.x * blockDim.x) host_v[t] = stage_v[t];
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nsd; t += (long long)gridDim.x * blockDim.x) host_s[t] = stage_s[t];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *host_count = (int)n;
-}
-
 // Read-back that overlaps the following steps: the fsi::Vertex records of every slot and the particle scalars are packed on
 // the compute stream into a dedicated staging buffer; a second stream copies them to the caller's page-locked buffers while
 // the compute stream carries on. The next pack waits (on the device) for the previous copy, the host only in ib_results_wait.
@@ -2237,6 +2229,7 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
     }
     const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double), sb = (size_t)d->n_particles * 11 * sizeof(double);
     if (vb + sb == 0) return 1;
+    if (d->ms && d->copy_in_flight && !ib_results_wait(d)) return 0;     // a compact read-back is completed before its staging buffer is reused
     if (d->results_bytes < vb + sb) {
         if (d->copy_in_flight) BIB_CHECK(cudaEventSynchronize(d->ev_copied));
         if (d->results_dev) cudaFree(d->results_dev);
@@ -2245,29 +2238,30 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         d->results_bytes = vb + sb; d->bytes += (long long)(vb + sb);
     }
     if (d->copy_in_flight) BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));      // staging buffer free again
-    double *dev_v = nullptr, *dev_s = nullptr;
-    if (d->ms && cudaHostGetDevicePointer((void**)&dev_v, v9, 0) == cudaSuccess && cudaHostGetDevicePointer((void**)&dev_s, s11, 0) == cudaSuccess) {
+    if (d->ms) {
         const MultiSlabIB* m = d->ms;
         if (!d->res_list) {
             BIB_CHECK(cudaMalloc(&d->res_list, ((size_t)m->cap + 1) * sizeof(int)));
-            BIB_CHECK(cudaHostAlloc((void**)&d->res_count_host, 64, cudaHostAllocMapped));
+            BIB_CHECK(cudaHostAlloc((void**)&d->res_count_host, 64, cudaHostAllocDefault));
             *d->res_count_host = 0;
+            d->res_bound = m->cap;                       // first read-back: everything; afterwards the last count + slack
         }
-        int* dev_count_host = nullptr;
-        BIB_CHECK(cudaHostGetDevicePointer((void**)&dev_count_host, d->res_count_host, 0));
         int* list = d->res_list + 1; int* count = d->res_list;
         double* stage_v = (double*)d->results_dev; double* stage_s = (double*)((char*)d->results_dev + vb);
         k_results_list<<<1, 1024, 0, d->stream>>>(m->role, m->cap, list, count);
         k_pack_slots<<<m->cap, 128, 0, d->stream>>>(stage_v, stage_s, list, count, m->nv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
         d->launches += 2;
+        BIB_CHECK(cudaGetLastError());
         BIB_CHECK(cudaEventRecord(d->ev_packed, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_packed, 0));
-        k_push_host<<<32, 256, 0, d->copy_stream>>>(dev_v, dev_s, dev_count_host, stage_v, stage_s, count, m->nv);
-        d->launches++;
-        BIB_CHECK(cudaGetLastError());
+        size_t nb = (size_t)std::min(d->res_bound, m->cap);
+        if (const char* e = getenv("BIB_RESULTS_BOUND")) nb = (size_t)std::max(0, std::min(atoi(e), m->cap));     // tests: force the remainder path
+        BIB_CHECK(cudaMemcpyAsync(d->res_count_host, count, sizeof(int), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (nb) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, nb * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (nb) BIB_CHECK(cudaMemcpyAsync(s11, stage_s, nb * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
         BIB_CHECK(cudaEventRecord(d->ev_copied, d->copy_stream));
         d->copy_in_flight = true;
-        d->res_compact = true;
+        d->res_compact = true; d->res_bound_used = (int)nb; d->res_host_v = v9; d->res_host_s = s11;
         return 1;
     }
     cudaGetLastError();
@@ -2290,6 +2284,18 @@ int ib_results_wait(bib_domain* d) {
     if (!d->copy_in_flight) return 1;
     BIB_CHECK(cudaEventSynchronize(d->ev_copied));
     d->copy_in_flight = false;
+    if (d->res_compact && d->ms) {
+        const MultiSlabIB* m = d->ms;
+        const int n = *d->res_count_host, got = d->res_bound_used;
+        if (n > got) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
+            const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double);
+            const double* stage_v = (const double*)d->results_dev; const double* stage_s = (const double*)((const char*)d->results_dev + vb);
+            BIB_CHECK(cudaMemcpyAsync(d->res_host_v + (size_t)got * m->nv * 9, stage_v + (size_t)got * m->nv * 9, (size_t)(n - got) * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            BIB_CHECK(cudaMemcpyAsync(d->res_host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            BIB_CHECK(cudaStreamSynchronize(d->copy_stream));
+        }
+        d->res_bound = std::min(m->cap, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
+    }
     return 1;
 }
 // number of particles the last completed bib_ib_results_download_async delivered (after ib_results_wait)

@@ -186,8 +186,10 @@ int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int coun
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11);
 int bib_ib_results_wait(bib_domain* d);
 /* On a multi-slab domain the slot arrays are sized for the worst case; the asynchronous read-back therefore delivers only the particles
- * this slab OWNS (what a rank of the reference writes), compacted in ascending slot order (ids: bib_ib_local_slots, role 1), at the start
- * of both buffers. n_particles = how many the last completed read-back delivered (single slab: all particles). Call after the wait. */
+ * this slab OWNS (what a rank of the reference writes), compacted on the device in ascending slot order (ids: bib_ib_local_slots, role 1),
+ * at the start of both buffers. The asynchronous copy covers a prefix sized from the previous count plus slack; if more particles are
+ * owned by now, bib_ib_results_wait fetches the remainder before it returns. n_particles = how many the last completed read-back
+ * delivered (single slab: all particles). Call after the wait. */
 int bib_ib_results_count(bib_domain* d, int* n_particles);
 /* The reference caches these per particle and refreshes them only in update() (after a move); a particle that was translated
  * or rotated on the host keeps the values computed before (ParticleBase3D::set_center_of_mass, src/fsi/ParticleBase.hh). A host

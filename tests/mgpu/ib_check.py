@@ -68,6 +68,16 @@ def main():
     for j, s in enumerate(owned_slots):
         assert np.array_equal(hv.reshape(-1, shape.nv, 9)[j], verts[s]), (rank, j, s)
         assert np.array_equal(hs[j], scal[s]), (rank, j, s)
+    # the asynchronous copy covers a prefix sized from the last count; a particle count beyond it is completed by results_wait
+    os.environ["BIB_RESULTS_BOUND"] = "0" if len(owned_slots) < 2 else "1"
+    hv[:] = 0.0; hs[:] = 0.0
+    lat.results_download_async(hv, hs)
+    lat.results_wait()
+    del os.environ["BIB_RESULTS_BOUND"]
+    assert lat.results_count() == len(owned_slots)
+    for j, s in enumerate(owned_slots):
+        assert np.array_equal(hv.reshape(-1, shape.nv, 9)[j], verts[s]), (rank, j, s)
+        assert np.array_equal(hs[j], scal[s]), (rank, j, s)
     cells = torch.from_numpy(lat.download()).cuda()
     parts = [torch.empty_like(cells) for _ in range(world)]
     dist.all_gather(parts, cells)

@@ -56,6 +56,17 @@ def e():
         lat.results_download_async(hv[it % 2], hs[it % 2])
         lat.results_wait()
 run("E  step; download; wait (no overlap)", e)
+# where does the host wait? enqueue time of a step, and how long after it the copy of the PREVIOUS step has landed
+barrier()
+rows = []
+for it in range(K):
+    t0 = time.perf_counter(); lat.step(body, n=1); t1 = time.perf_counter()
+    if it > 0: lat.results_wait()
+    t2 = time.perf_counter(); lat.results_download_async(hv[it % 2], hs[it % 2]); t3 = time.perf_counter()
+    rows.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+lat.results_wait(); barrier()
+if rank == 0:
+    for r in rows: print("enqueue step %.2f ms | wait for previous copy %.2f ms | enqueue download %.2f ms" % r)
 if rank == 0: print("slots", n_slots, "vertices", n_vert, "d2h MB/step", (n_vert * 72 + n_slots * 88) / 1e6)
 lat.close()
 if world > 1: dist.destroy_process_group()
