@@ -111,10 +111,14 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->scratch) cudaFree(d->scratch);
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
-    if (d->results_dev) cudaFree(d->results_dev);
+    for (ResSlot& r : d->res) {
+        if (r.dev) cudaFree(r.dev);
+        if (r.packed) cudaEventDestroy(r.packed);
+        if (r.copied) cudaEventDestroy(r.copied);
+        if (r.count_host) cudaFreeHost(r.count_host);
+    }
     if (d->res_list) cudaFree(d->res_list);
-    if (d->res_count_host) cudaFreeHost(d->res_count_host);
-    if (d->step_graph) cudaGraphExecDestroy(d->step_graph);
+    for (StepGraph& g : d->sg) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (d->fflag) cudaFree(d->fflag);
     if (d->guo_nodes) cudaFree(d->guo_nodes);
     if (d->guo_delta) cudaFree(d->guo_delta);
@@ -122,8 +126,6 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pp_head) cudaFree(d->pp_head);
     if (d->pp_next) cudaFree(d->pp_next);
     if (d->pp_vobj) cudaFree(d->pp_vobj);
-    if (d->ev_packed) cudaEventDestroy(d->ev_packed);
-    if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->vpos) cudaFree(d->vpos);
     if (d->vvel) cudaFree(d->vvel);
     if (d->vfrc) cudaFree(d->vfrc);
@@ -152,7 +154,7 @@ int bib_domain_destroy(bib_domain* d) {
 // BIB_ENTER: entry points that may change the configuration or the state outside the stepping loop (they invalidate the captured
 // step graph); BIB_ENTER_RO: stepping itself, synchronisation, timing and read-only downloads.
 #define BIB_ENTER_RO(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
-#define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; (d)->forces_ready = false; } while (0)
+#define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; (d)->forces_ready = false; (d)->plain_steps_since_dirty = 0; } while (0)
 
 int bib_domain_set_option(bib_domain* d, int key, double value) {
     BIB_ENTER(d);
@@ -475,46 +477,74 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
 
 // Small lattices (the reference's own driver configurations: 61^3 ... 97^3 cells, one to a few dozen particles) are launch-bound:
 // ~15 kernels of a few microseconds each per step. In steady state the kernel sequence of a step is fixed and all its arguments
-// repeat with period 2 (A/B population buffers, double-buffered band masks), so two consecutive steps are captured once into a CUDA
-// graph and replayed. Any configuration-changing entry point invalidates the graph (BIB_ENTER). Single-slab domains only (the
-// multi-slab step interleaves NCCL calls on two streams).
+// repeat with period 2 (A/B population buffers, double-buffered band masks, the two vertex-force arrays of the prefetch), so the
+// two steps of a period are captured once, EACH into its own CUDA graph, and replayed alternately: a caller that issues one step
+// per call (a driver's time loop, bench.py's e2e leg) replays graphs as well. Any configuration-changing entry point invalidates
+// the graphs (BIB_ENTER). Single-slab domains only (the multi-slab step interleaves NCCL calls on two streams).
+static void step_graphs_destroy(bib_domain* d) {
+    for (StepGraph& g : d->sg) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+}
+static bool step_graph_matches(const bib_domain* d, const StepGraph& g) {
+    return g.exec && d->cur == g.cur && d->band_cur == g.band_cur && d->vfrc == g.vfrc && d->forces_ready == g.forces_ready;
+}
 int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
     BIB_ENTER_RO(d);
     int s = 0;
     const bool same_body = d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz;
-    if (d->use_graph && d->n_ranks == 1 && n_steps >= 2 && (d->step_graph == nullptr || d->graph_dirty || !same_body) && n_steps >= 6) {
-        if (d->step_graph) { cudaGraphExecDestroy(d->step_graph); d->step_graph = nullptr; }
-        for (; s < 2; ++s) if (!step_once(d, body_fx, body_fy, body_fz)) return 0;      // reach the steady state (allocations, masks, flags)
-        const long long l0 = d->launches;
-        d->graph_cur = d->cur; d->graph_band_cur = d->band_cur;      // the buffers the captured pair of steps starts from
-        d->graph_vfrc = d->vfrc; d->graph_forces_ready = d->forces_ready;
-        cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const bool ok = step_once(d, body_fx, body_fy, body_fz) && step_once(d, body_fx, body_fy, body_fz);
-            const cudaError_t e = cudaStreamEndCapture(d->stream, &graph);
-            d->graph_launches = d->launches - l0;
-            d->launches = l0;                                  // captured, not executed
-            if (ok && e == cudaSuccess && graph && cudaGraphInstantiate(&d->step_graph, graph, 0) == cudaSuccess) {
+    const bool have_graphs = d->sg[0].exec && d->sg[1].exec && !d->graph_dirty && same_body;
+    if (d->last_body[0] != body_fx || d->last_body[1] != body_fy || d->last_body[2] != body_fz) {
+        d->plain_steps_since_dirty = 0;
+        d->last_body[0] = body_fx; d->last_body[1] = body_fy; d->last_body[2] = body_fz;
+    }
+    // capture when this call is long enough to pay for it, or when a one-step-per-call caller has kept the configuration unchanged for a while
+    if (d->use_graph && d->n_ranks == 1 && !have_graphs && (n_steps >= 6 || d->plain_steps_since_dirty >= 4)) {
+        step_graphs_destroy(d);
+        for (; d->plain_steps_since_dirty < 2 && s < n_steps; ++s) {          // reach the steady state first (allocations, masks, flags)
+            if (!step_once(d, body_fx, body_fy, body_fz)) return 0;
+            d->plain_steps_since_dirty++;
+        }
+        if (d->plain_steps_since_dirty >= 2 && s < n_steps) {
+            bool ok = true;
+            for (int k = 0; k < 2 && ok; ++k) {
+                StepGraph& g = d->sg[k];
+                g.cur = d->cur; g.band_cur = d->band_cur; g.vfrc = d->vfrc; g.forces_ready = d->forces_ready;   // the state this step starts from
+                const long long l0 = d->launches;
+                cudaGraph_t graph = nullptr;
+                ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    const bool stepped = step_once(d, body_fx, body_fy, body_fz) != 0;
+                    const cudaError_t e = cudaStreamEndCapture(d->stream, &graph);
+                    g.launches = d->launches - l0;
+                    d->launches = l0;                              // captured, not executed
+                    ok = stepped && e == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            // period 2: after the two captured steps the host-side state must be the one the first graph starts from
+            if (ok && step_graph_matches(d, d->sg[0])) {
                 d->graph_dirty = false;
                 d->graph_body[0] = body_fx; d->graph_body[1] = body_fy; d->graph_body[2] = body_fz;
             } else {
-                d->step_graph = nullptr;
-                d->use_graph = 0;                              // something in this configuration is not capturable: plain launches from now on
+                step_graphs_destroy(d);
+                d->use_graph = 0;                                  // something in this configuration is not capturable: plain launches from now on
             }
-            if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
         }
     }
-    if (d->use_graph && d->n_ranks == 1 && d->step_graph && !d->graph_dirty &&
+    if (d->use_graph && d->n_ranks == 1 && d->sg[0].exec && d->sg[1].exec && !d->graph_dirty &&
         d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz) {
-        // the graph starts from fixed A/B buffers: after an odd number of steps one plain step realigns the parity
-        if (n_steps - s >= 3 && d->cur != d->graph_cur) { if (!step_once(d, body_fx, body_fy, body_fz)) return 0; ++s; }
-        for (; n_steps - s >= 2 && d->cur == d->graph_cur && d->band_cur == d->graph_band_cur && d->vfrc == d->graph_vfrc && d->forces_ready == d->graph_forces_ready; s += 2) {
-            BIB_CHECK(cudaGraphLaunch(d->step_graph, d->stream));
-            d->launches += d->graph_launches;
+        for (; s < n_steps; ++s) {
+            const int k = step_graph_matches(d, d->sg[0]) ? 0 : (step_graph_matches(d, d->sg[1]) ? 1 : -1);
+            if (k < 0) break;
+            BIB_CHECK(cudaGraphLaunch(d->sg[k].exec, d->stream));
+            d->launches += d->sg[k].launches;
+            // the host-side state one step later = the state the other graph starts from
+            const StepGraph& nx = d->sg[1 - k];
+            d->cur = nx.cur; d->band_cur = nx.band_cur; d->forces_ready = nx.forces_ready;
+            if (d->vfrc != nx.vfrc) std::swap(d->vfrc, d->vfrc_next);
         }
     }
-    for (; s < n_steps; ++s) if (!step_once(d, body_fx, body_fy, body_fz)) return 0;
+    for (; s < n_steps; ++s) { if (!step_once(d, body_fx, body_fy, body_fz)) return 0; d->plain_steps_since_dirty++; }
     return 1;
 }
 

@@ -84,6 +84,23 @@ struct WallEdge {                  // one external velocity edge (StoreVelocityD
     std::vector<double> h_vel;
 };
 
+// one captured driver step and the host-side state it starts from
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int cur = 0, band_cur = 0; const double* vfrc = nullptr; bool forces_ready = false;
+    long long launches = 0;
+};
+
+// one asynchronous read-back (bib_ib_results_download_async): staging buffer, events, the caller's buffers
+#define RES_DEPTH 2
+struct ResSlot {
+    void* dev = nullptr; size_t bytes = 0, vb = 0;
+    cudaEvent_t packed = nullptr, copied = nullptr;
+    double* host_v = nullptr; double* host_s = nullptr;
+    int* count_host = nullptr;            // page-locked: number of owned particles (multi-slab)
+    bool compact = false; int bound_used = 0;
+};
+
 struct bib_domain {
     int device = 0;
     int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
@@ -119,10 +136,12 @@ struct bib_domain {
     bool forces_ready = false;            // vfrc_next holds the forces of the current vertex positions (cleared by every mutating entry point)
     double* vfrc_next = nullptr; long long vfrc_next_cap = 0;
     bool vfrc_preloaded = false;          // bib_ib_vertex_forces_preload: the next force evaluation adds to vfrc instead of starting from zero
-    const double* graph_vfrc = nullptr; bool graph_forces_ready = false;   // force-array parity the captured pair of steps starts from
     long long launches = 0;
     // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
-    cudaGraphExec_t step_graph = nullptr; bool graph_dirty = true; int use_graph = 1; long long graph_launches = 0; double graph_body[3] = {0, 0, 0}; int graph_cur = 0, graph_band_cur = 0;
+    StepGraph sg[2];                      // the two steps of a period, one CUDA graph each (bib_step)
+    bool graph_dirty = true; int use_graph = 1; double graph_body[3] = {0, 0, 0};
+    double last_body[3] = {0, 0, 0};
+    int plain_steps_since_dirty = 0;      // steps issued with plain launches since the configuration last changed (one-step-per-call callers)
     long long bytes = 0;
     // options
     int envelope_swap = 1;
@@ -160,15 +179,12 @@ struct bib_domain {
     void* scratch = nullptr; size_t scratch_bytes = 0;
     void* pinned = nullptr; size_t pinned_bytes = 0;      // pinned host staging for device->host result reads
     // asynchronous result read-back (bib_ib_results_download_async): packed on the compute stream, copied on copy_stream
-    void* results_dev = nullptr; size_t results_bytes = 0;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
-    bool copy_in_flight = false;
-    int* res_list = nullptr;              // [1 + cap]: number and slot indices of the owned particles (multi-slab async read-back)
-    int* res_count_host = nullptr;        // page-locked: how many particles the last async read-back delivered
-    bool res_compact = false;
-    int res_bound = 0, res_bound_used = 0;            // particles covered by the asynchronous prefix copy (last count + slack)
-    double* res_host_v = nullptr; double* res_host_s = nullptr;   // the caller's buffers of the read-back in flight
+    ResSlot res[RES_DEPTH];               // asynchronous read-backs in flight (FIFO)
+    int res_head = 0, res_tail = 0, res_n = 0;
+    int* res_list = nullptr;              // per slot [1 + cap]: number and slot indices of the owned particles (multi-slab read-back)
+    int res_bound = 0;                    // particles covered by the asynchronous prefix copy (last count + slack)
+    int res_last_count = -1;              // particles delivered by the last completed read-back
     MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
 };
 

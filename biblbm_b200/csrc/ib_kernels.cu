@@ -2213,95 +2213,97 @@ __global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, 
     }
     if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
 }
-// Read-back that overlaps the following steps: the fsi::Vertex records of every slot and the particle scalars are packed on
-// the compute stream into a dedicated staging buffer; a second stream copies them to the caller's page-locked buffers while
-// the compute stream carries on. The next pack waits (on the device) for the previous copy, the host only in ib_results_wait.
+// Read-back that overlaps the following steps: the fsi::Vertex records and the particle scalars are packed on the compute stream into
+// a staging buffer; a second stream copies them to the caller's page-locked buffers while the compute stream carries on. Up to
+// RES_DEPTH read-backs are in flight (one staging buffer each); ib_results_wait completes the OLDEST one. Two in flight let a caller
+// keep one whole step queued ahead of the copy it is waiting for (bench.py e2e): the D2H DMA of 56 MB takes about as long as a step
+// while the lattice kernel saturates HBM.
+static int res_complete_oldest(bib_domain* d) {
+    if (d->res_n == 0) return 1;
+    ResSlot& r = d->res[d->res_tail];
+    BIB_CHECK(cudaEventSynchronize(r.copied));
+    int n = d->n_particles;
+    if (r.compact && d->ms) {
+        const MultiSlabIB* m = d->ms;
+        n = *r.count_host;
+        const int got = r.bound_used;
+        if (n > got) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
+            const double* stage_v = (const double*)r.dev; const double* stage_s = (const double*)((const char*)r.dev + r.vb);
+            BIB_CHECK(cudaMemcpyAsync(r.host_v + (size_t)got * m->nv * 9, stage_v + (size_t)got * m->nv * 9, (size_t)(n - got) * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            BIB_CHECK(cudaMemcpyAsync(r.host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            BIB_CHECK(cudaStreamSynchronize(d->copy_stream));
+        }
+        d->res_bound = std::min(m->cap, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
+    }
+    d->res_last_count = n;
+    d->res_tail = (d->res_tail + 1) % RES_DEPTH; d->res_n--;
+    return 1;
+}
 int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
     cudaPointerAttributes a0, a1;
     const bool pinned = cudaPointerGetAttributes(&a0, v9) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
                         cudaPointerGetAttributes(&a1, s11) == cudaSuccess && a1.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (!pinned) { bib_set_error("results_download_async: both host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)"); return 0; }
-    if (!d->copy_stream) {
-        BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));   // (a high-priority stream was measured: no difference)
-        BIB_CHECK(cudaEventCreateWithFlags(&d->ev_packed, cudaEventDisableTiming));
-        BIB_CHECK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
-    }
+    if (!d->copy_stream) BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));   // (a high-priority stream was measured: no difference)
     const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double), sb = (size_t)d->n_particles * 11 * sizeof(double);
     if (vb + sb == 0) return 1;
-    if (d->ms && d->copy_in_flight && !ib_results_wait(d)) return 0;     // a compact read-back is completed before its staging buffer is reused
-    if (d->results_bytes < vb + sb) {
-        if (d->copy_in_flight) BIB_CHECK(cudaEventSynchronize(d->ev_copied));
-        if (d->results_dev) cudaFree(d->results_dev);
-        d->results_dev = nullptr; d->results_bytes = 0;
-        BIB_CHECK(cudaMalloc(&d->results_dev, vb + sb));
-        d->results_bytes = vb + sb; d->bytes += (long long)(vb + sb);
+    if (d->res_n == RES_DEPTH && !res_complete_oldest(d)) return 0;        // every staging buffer is busy: finish the oldest read-back first
+    ResSlot& r = d->res[d->res_head];
+    if (!r.packed) {
+        BIB_CHECK(cudaEventCreateWithFlags(&r.packed, cudaEventDisableTiming));
+        BIB_CHECK(cudaEventCreateWithFlags(&r.copied, cudaEventDisableTiming));
+        BIB_CHECK(cudaHostAlloc((void**)&r.count_host, 64, cudaHostAllocDefault));
+        *r.count_host = 0;
     }
-    if (d->copy_in_flight) BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));      // staging buffer free again
+    if (r.bytes < vb + sb) {
+        if (r.dev) { cudaFree(r.dev); d->bytes -= (long long)r.bytes; }
+        r.dev = nullptr; r.bytes = 0;
+        BIB_CHECK(cudaMalloc(&r.dev, vb + sb));
+        r.bytes = vb + sb; d->bytes += (long long)(vb + sb);
+    }
+    r.vb = vb; r.host_v = v9; r.host_s = s11; r.compact = false; r.bound_used = 0;
+    double* stage_v = (double*)r.dev; double* stage_s = (double*)((char*)r.dev + vb);
     if (d->ms) {
+        // multi-slab: the owned particles, compacted in slot order
         const MultiSlabIB* m = d->ms;
         if (!d->res_list) {
-            BIB_CHECK(cudaMalloc(&d->res_list, ((size_t)m->cap + 1) * sizeof(int)));
-            BIB_CHECK(cudaHostAlloc((void**)&d->res_count_host, 64, cudaHostAllocDefault));
-            *d->res_count_host = 0;
+            BIB_CHECK(cudaMalloc(&d->res_list, (size_t)RES_DEPTH * ((size_t)m->cap + 1) * sizeof(int)));
             d->res_bound = m->cap;                       // first read-back: everything; afterwards the last count + slack
         }
-        int* list = d->res_list + 1; int* count = d->res_list;
-        double* stage_v = (double*)d->results_dev; double* stage_s = (double*)((char*)d->results_dev + vb);
+        int* count = d->res_list + (size_t)d->res_head * ((size_t)m->cap + 1); int* list = count + 1;
         k_results_list<<<1, 1024, 0, d->stream>>>(m->role, m->cap, list, count);
         k_pack_slots<<<m->cap, 128, 0, d->stream>>>(stage_v, stage_s, list, count, m->nv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
         d->launches += 2;
         BIB_CHECK(cudaGetLastError());
-        BIB_CHECK(cudaEventRecord(d->ev_packed, d->stream));
-        BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_packed, 0));
+        BIB_CHECK(cudaEventRecord(r.packed, d->stream));
+        BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));
         size_t nb = (size_t)std::min(d->res_bound, m->cap);
         if (const char* e = getenv("BIB_RESULTS_BOUND")) nb = (size_t)std::max(0, std::min(atoi(e), m->cap));     // tests: force the remainder path
-        BIB_CHECK(cudaMemcpyAsync(d->res_count_host, count, sizeof(int), cudaMemcpyDeviceToHost, d->copy_stream));
+        BIB_CHECK(cudaMemcpyAsync(r.count_host, count, sizeof(int), cudaMemcpyDeviceToHost, d->copy_stream));
         if (nb) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, nb * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
         if (nb) BIB_CHECK(cudaMemcpyAsync(s11, stage_s, nb * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
-        BIB_CHECK(cudaEventRecord(d->ev_copied, d->copy_stream));
-        d->copy_in_flight = true;
-        d->res_compact = true; d->res_bound_used = (int)nb; d->res_host_v = v9; d->res_host_s = s11;
-        return 1;
-    }
-    cudaGetLastError();
-    d->res_compact = false;
-    if (vb) {
-        const int grid = (int)std::min<long long>((d->n_vertices * 9 + 255) / 256, 148 * 16);
-        k_pack_vertices<<<grid, 256, 0, d->stream>>>((double*)d->results_dev, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
-        d->launches++;
-    }
-    if (sb) BIB_CHECK(cudaMemcpyAsync((char*)d->results_dev + vb, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
-    BIB_CHECK(cudaEventRecord(d->ev_packed, d->stream));
-    BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_packed, 0));
-    if (vb) BIB_CHECK(cudaMemcpyAsync(v9, d->results_dev, vb, cudaMemcpyDeviceToHost, d->copy_stream));
-    if (sb) BIB_CHECK(cudaMemcpyAsync(s11, (char*)d->results_dev + vb, sb, cudaMemcpyDeviceToHost, d->copy_stream));
-    BIB_CHECK(cudaEventRecord(d->ev_copied, d->copy_stream));
-    d->copy_in_flight = true;
-    return 1;
-}
-int ib_results_wait(bib_domain* d) {
-    if (!d->copy_in_flight) return 1;
-    BIB_CHECK(cudaEventSynchronize(d->ev_copied));
-    d->copy_in_flight = false;
-    if (d->res_compact && d->ms) {
-        const MultiSlabIB* m = d->ms;
-        const int n = *d->res_count_host, got = d->res_bound_used;
-        if (n > got) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
-            const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double);
-            const double* stage_v = (const double*)d->results_dev; const double* stage_s = (const double*)((const char*)d->results_dev + vb);
-            BIB_CHECK(cudaMemcpyAsync(d->res_host_v + (size_t)got * m->nv * 9, stage_v + (size_t)got * m->nv * 9, (size_t)(n - got) * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
-            BIB_CHECK(cudaMemcpyAsync(d->res_host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
-            BIB_CHECK(cudaStreamSynchronize(d->copy_stream));
+        r.compact = true; r.bound_used = (int)nb;
+    } else {
+        if (vb) {
+            const int grid = (int)std::min<long long>((d->n_vertices * 9 + 255) / 256, 148 * 16);
+            k_pack_vertices<<<grid, 256, 0, d->stream>>>(stage_v, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
+            d->launches++;
         }
-        d->res_bound = std::min(m->cap, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
+        if (sb) BIB_CHECK(cudaMemcpyAsync(stage_s, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
+        BIB_CHECK(cudaEventRecord(r.packed, d->stream));
+        BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));
+        if (vb) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, vb, cudaMemcpyDeviceToHost, d->copy_stream));
+        if (sb) BIB_CHECK(cudaMemcpyAsync(s11, stage_s, sb, cudaMemcpyDeviceToHost, d->copy_stream));
     }
+    BIB_CHECK(cudaEventRecord(r.copied, d->copy_stream));
+    d->res_head = (d->res_head + 1) % RES_DEPTH; d->res_n++;
     return 1;
 }
-// number of particles the last completed bib_ib_results_download_async delivered (after ib_results_wait)
+int ib_results_wait(bib_domain* d) { return res_complete_oldest(d); }
+// number of particles the last COMPLETED read-back delivered (single slab: all of them)
 int ib_results_count(bib_domain* d, int* n) {
-    if (d->copy_in_flight) { bib_set_error("results_count: call bib_ib_results_wait first"); return 0; }
-    *n = (d->res_compact && d->res_count_host) ? *d->res_count_host : d->n_particles;
+    *n = d->res_last_count >= 0 ? d->res_last_count : d->n_particles;
     return 1;
 }
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {

@@ -181,8 +181,8 @@ int bib_ib_vertex_forces_preload(bib_domain* d, long long first_vertex, long lon
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11);
 /* Non-blocking read-back of ALL vertex records and particle scalars of this slab (what write_lightweight_particle_data /
  * write_particles_as_vtk / the volume diagnostics of the drivers consume) into page-locked host buffers: the device->host copy
- * runs on its own stream while later steps execute. The buffers may be read after bib_ib_results_wait(); a second call
- * before the wait is allowed with different buffers (the device serialises them). */
+ * runs on its own stream while later steps execute. Up to two read-backs may be in flight (different host buffers); a third call
+ * first completes the oldest. bib_ib_results_wait() completes the OLDEST read-back in flight; its buffers may be read afterwards. */
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11);
 int bib_ib_results_wait(bib_domain* d);
 /* On a multi-slab domain the slot arrays are sized for the worst case; the asynchronous read-back therefore delivers only the particles

@@ -422,6 +422,15 @@ def test_step_graph_equals_plain_launches(rbc):
         lat.add_particles(sid, params, g["vert_init"][..., :3])
         lat.set_regulator(float(g["regulator_p"]), g["regulator_target"])
         return lat
+    # a caller that issues ONE step per call (a driver's time loop) gets the graphs too, after a few plain steps
+    c, e = build(1), build(0)
+    for lat in (c, e):
+        for k in range(13):
+            lat.step((2e-6, 0.0, 0.0), n=1)
+            if k == 8:
+                lat.vertices()                       # read-only calls in between keep the graphs
+        lat.step((2e-6, 0.0, 0.0), n=3)
+    assert np.array_equal(c.vertices(), e.vertices()) and np.array_equal(c.download(), e.download()) and c.launches() == e.launches()
     a, b = build(1), build(0)
     for lat in (a, b):
         lat.step((0.0, 0.0, 0.0), n=21)
@@ -483,12 +492,19 @@ def test_async_result_readback_matches_golden(rbc):
         lat.results_wait()
         assert np.array_equal(hv[s % 2].reshape(n_p, nv, 9), g[f"vert_{s}"]), s
         assert np.array_equal(hs[s % 2], g[f"part_{s}"])
-    # issue without waiting in between: both copies must land in order
+    # two read-backs in flight (FIFO): every wait completes the oldest one; a third request first completes the oldest itself
     lat2 = run_ib_case(g, shape, params, deterministic=True)
+    hv3 = torch.empty((n_p * nv, 9), dtype=torch.float64, pin_memory=True).numpy(); hs3 = torch.empty((n_p, 11), dtype=torch.float64, pin_memory=True).numpy()
     lat2.step(g["body"]); lat2.results_download_async(hv[0], hs[0])
     lat2.step(g["body"]); lat2.results_download_async(hv[1], hs[1])
+    lat2.step(g["body"]); lat2.results_download_async(hv3, hs3)              # a third request completes the oldest (step 1) itself
+    assert np.array_equal(hv[0].reshape(n_p, nv, 9), g["vert_1"]) and np.array_equal(hs[0], g["part_1"])
     lat2.results_wait()
-    assert np.array_equal(hv[0].reshape(n_p, nv, 9), g["vert_1"]) and np.array_equal(hv[1].reshape(n_p, nv, 9), g["vert_2"])
+    assert np.array_equal(hv[1].reshape(n_p, nv, 9), g["vert_2"]) and np.array_equal(hs[1], g["part_2"])
+    lat2.results_wait()
+    assert np.array_equal(hv3.reshape(n_p, nv, 9), g["vert_3"]) and np.array_equal(hs3, g["part_3"])
+    assert lat2.results_count() == n_p
+    lat2.results_wait()                                                      # nothing in flight: returns at once
     with pytest.raises(bib.BibError, match="page-locked"):
         lat2.results_download_async(np.empty((n_p * nv, 9)), np.empty((n_p, 11)))
 

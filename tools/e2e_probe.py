@@ -28,10 +28,10 @@ lat.add_particles(sid, params, bench.rbc_positions(rbc_pos, 1250 * world, (nx * 
 body = (1e-6, 0.0, 0.0)
 lat.step(body, n=5); lat.sync()
 n_slots, n_vert = lat.count()
-hv = [torch.empty((max(1, n_vert), 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
-hs = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+hv = [torch.empty((max(1, n_vert), 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
+hs = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
 K = 10
-lat.results_download_async(hv[0], hs[0]); lat.results_wait()     # first use allocates the staging buffer and the copy stream: not timed
+lat.results_download_async(hv[0], hs[0]); lat.results_download_async(hv[1], hs[1]); lat.results_wait(); lat.results_wait()     # first use allocates: not timed
 def run(name, fn):
     barrier(); t0 = time.perf_counter(); fn(); barrier(); dt = (time.perf_counter() - t0) * 1e3 / K
     if rank == 0: print(f"{name}: {dt:.3f} ms/step", flush=True)
@@ -49,7 +49,14 @@ def d():
         if it > 0: lat.results_wait()
         lat.results_download_async(hv[it % 2], hs[it % 2])
     lat.results_wait()
-run("D  bench e2e loop", d)
+run("D  one read-back in flight", d)
+def d2():
+    for it in range(K):
+        lat.step(body, n=1)
+        if it > 1: lat.results_wait()
+        lat.results_download_async(hv[it % 3], hs[it % 3])
+    lat.results_wait(); lat.results_wait()
+run("D2 two read-backs in flight (bench e2e loop)", d2)
 def e():
     for it in range(K):
         lat.step(body, n=1)
