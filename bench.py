@@ -176,7 +176,8 @@ def driver_speed():
                 raise RuntimeError(r.stderr[-500:])
             return time.perf_counter() - t0
     try:
-        g = (run(gpu, 4500) - run(gpu, 500)) / 4000.0
+        run(gpu, 500)                                               # warm-up (driver + CUDA context start-up on this box)
+        g = (run(gpu, 4500) - min(run(gpu, 500), run(gpu, 500))) / 4000.0
         c = (run(cpu, 35) - run(cpu, 5)) / 30.0
     except Exception as e:      # reported, never fatal for the bench line
         return {"error": str(e)[:200]}
