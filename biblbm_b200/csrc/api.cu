@@ -249,6 +249,10 @@ int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity)
     d->vel_full_valid = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
     return 1;
 }
+int bib_velocity_extrapolate_plane(bib_domain* d, int direction, int coord, int inward) {
+    BIB_ENTER(d);
+    return lbm_velocity_extrapolate(d, direction, coord, inward);
+}
 int bib_collide_and_stream(bib_domain* d) {
     BIB_ENTER(d);
     d->vel_full_valid = false;

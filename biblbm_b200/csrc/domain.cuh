@@ -200,6 +200,7 @@ int lbm_launch_download(bib_domain* d, const int box[6], double* cells);
 int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double fy, double fz);
 int lbm_launch_velocity(bib_domain* d, const int box[6]);
 int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity);
+int lbm_velocity_extrapolate(bib_domain* d, int dir, int coord, int inward);
 int lbm_velocity_upload(bib_domain* d, const int box[6], const double* velocity);
 int lbm_set_celltype(bib_domain* d, const int box[6], int kind);
 int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient);

@@ -442,6 +442,23 @@ __global__ void k_unpack_velocity(const double* __restrict__ in, double* vel, in
         vel[idx] = in[t * 3]; vel[vol + idx] = in[t * 3 + 1]; vel[2 * vol + idx] = in[t * 3 + 2];
     }
 }
+// CouetteVelocityExtrapolator (progs/common/shear_flow_setup.h:121-183): u[plane] = 2 u[plane + inward] - u[plane + 2 inward], per component
+__global__ void k_extrapolate_plane(double* vel, int dir, int coord, int inward, int nx, int ny, int nz, long long plane, long long vol) {
+    const int na = dir == 0 ? ny : nx, nb = dir == 2 ? ny : nz;
+    const long long n = (long long)na * nb;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(t / nb), b = (int)(t % nb);
+        int c[3], c1[3], c2[3];
+        c[dir] = coord; c1[dir] = coord + inward; c2[dir] = coord + 2 * inward;
+        const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+        c[ta] = c1[ta] = c2[ta] = a; c[tb] = c1[tb] = c2[tb] = b;
+        const long long i0 = (long long)(c[0] + 1) * plane + (long long)c[1] * nz + c[2];
+        const long long i1 = (long long)(c1[0] + 1) * plane + (long long)c1[1] * nz + c1[2];
+        const long long i2 = (long long)(c2[0] + 1) * plane + (long long)c2[1] * nz + c2[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vel[k * vol + i0] = 2.0 * vel[k * vol + i1] - vel[k * vol + i2];
+    }
+}
 __global__ void k_set_kind(uint8_t* kind, int bx0, int by0, int bz0, int bnx, int bny, int bnz, long long plane, int nz, uint8_t v) {
     const long long n = (long long)bnx * bny * bnz;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -1058,6 +1075,20 @@ int lbm_velocity_download(bib_domain* d, const int box[6], double* velocity) {
     d->launches++;
     BIB_CHECK(cudaMemcpyAsync(velocity, d->scratch, (size_t)n * 3 * 8, cudaMemcpyDeviceToHost, d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->stream));
+    return 1;
+}
+
+int lbm_velocity_extrapolate(bib_domain* d, int dir, int coord, int inward) {
+    const int n[3] = {d->nx, d->ny, d->nz};
+    if (dir < 0 || dir > 2 || (inward != 1 && inward != -1) || coord < 0 || coord >= n[dir] || coord + 2 * inward < 0 || coord + 2 * inward >= n[dir]) {
+        bib_set_error("velocity_extrapolate_plane: bad arguments"); return 0;
+    }
+    if (!d->vel) { bib_set_error("velocity_extrapolate_plane: call bib_compute_velocity / bib_velocity_upload first"); return 0; }
+    if (d->n_ranks > 1 && dir == 0) { bib_set_error("velocity_extrapolate_plane: planes normal to x on single-slab domains only"); return 0; }
+    const long long cells = (long long)(dir == 0 ? d->ny : d->nx) * (dir == 2 ? d->ny : d->nz);
+    k_extrapolate_plane<<<grid_for(cells, 256), 256, 0, d->stream>>>(d->vel, dir, coord, inward, d->nx, d->ny, d->nz, (long long)d->plane, (long long)d->vol);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
     return 1;
 }
 

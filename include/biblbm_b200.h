@@ -109,6 +109,9 @@ int bib_velocity_download(bib_domain* d, const int box[6], double* velocity);
  * src/fsi/ImmersedBoundaryDynamics_interpolation.hh:236-276); a driver that edits the field on the host after computeVelocity
  * (CouetteVelocityExtrapolator, progs/common/shear_flow_setup.h:121-183) hands the edited field back with this call */
 int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity);
+/* CouetteVelocityExtrapolator::process (progs/common/shear_flow_setup.h:121-183; rbcs_in_shear.cpp:184) on the device's velocity field:
+ * velocity[plane `coord` normal to `direction`] := 2 velocity[coord + inward] - velocity[coord + 2 inward], inward = +-1. */
+int bib_velocity_extrapolate_plane(bib_domain* d, int direction, int coord, int inward);
 /* F1-F5: one lattice.collideAndStream() */
 int bib_collide_and_stream(bib_domain* d);
 

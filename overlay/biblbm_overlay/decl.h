@@ -76,6 +76,11 @@ template<class P> struct BibHostPeriodicity : public P { };
 #undef BIB_GLUE
 #undef BIB_N_EXT
 
+// ---- applyProcessingFunctional(new CouetteVelocityExtrapolator<double>(geoNy, margin_y, uMax), domain, velocity)
+// (progs/rbcs_in_shear/rbcs_in_shear.cpp:184): exact-match overload; the two wall planes of the velocity field are extrapolated on the
+// device (bib_velocity_extrapolate_plane) instead of a download / host loop / upload of the whole field every step
+void applyProcessingFunctional(::CouetteVelocityExtrapolator<double>* functional, Box3D domain, MultiTensorField3D<double, 3>& velocity);
+
 // ---- the velocity field's coherence hook (shared by both descriptors)
 template<> TensorField3D<double, 3>& MultiTensorField3D<double, 3>::getComponent(plint blockId);
 template<> TensorField3D<double, 3> const& MultiTensorField3D<double, 3>::getComponent(plint blockId) const;

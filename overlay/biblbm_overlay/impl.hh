@@ -44,6 +44,16 @@ enum { BIB_PARTICLE_RIGID_ = 100 };      // binding-internal tag: RigidParticle3
 #undef BIB_GLUE
 #undef BIB_N_EXT
 
+// ================================================================================================ CouetteVelocityExtrapolator
+inline void applyProcessingFunctional(::CouetteVelocityExtrapolator<double>* functional, Box3D domain, MultiTensorField3D<double, 3>& velocity) {
+    if (bibglue::couette_on_device(*functional, domain, velocity) || bibglue3::couette_on_device(*functional, domain, velocity)) {
+        delete functional;
+        return;
+    }
+    // not a device-resident field: the reference's own path (host loop; the coherence hook hands an edited field back to the device)
+    applyProcessingFunctional(static_cast<BoxProcessingFunctional3D_T<double, 3>*>(functional), domain, velocity);
+}
+
 // ================================================================================================ velocity field hook
 template<>
 inline TensorField3D<double, 3>& MultiTensorField3D<double, 3>::getComponent(plint blockId) {

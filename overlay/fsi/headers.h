@@ -25,6 +25,7 @@
 #define protected public
 #include_next "fsi/headers.h"
 #include "fsi/GuoBoundaryCondition.h"      // not part of fsi/headers.h; rbc_in_pipe includes it itself (include-guarded)
+#include "common/shear_flow_setup.h"       // CouetteVelocityExtrapolator keeps geoNy / margin private; drivers include it later (include-guarded)
 #undef private
 #undef protected
 #include "biblbm_overlay/decl.h"
