@@ -246,6 +246,16 @@ class Lattice:
         _check(self.lib.bib_ib_local_slots(self.h, gids.ctypes.data_as(ip), roles.ctypes.data_as(ip), cap, C.byref(n)))
         return gids[:n.value], roles[:n.value]
 
+    def velocity_extrapolate_plane(self, direction, coord, inward):
+        """CouetteVelocityExtrapolator on the device's velocity field: u[coord] = 2 u[coord + inward] - u[coord + 2 inward]."""
+        _check(self.lib.bib_velocity_extrapolate_plane(self.h, int(direction), int(coord), int(inward)))
+
+    def velocity(self, box=None):
+        box = box or self.full
+        out = np.empty((box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 3), dtype=np.float64)
+        _check(self.lib.bib_velocity_download(self.h, _box(box), _dptr(out)))
+        return out
+
     def interpolate_velocity(self):
         _check(self.lib.bib_ib_interpolate_velocity(self.h))
 

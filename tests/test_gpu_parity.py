@@ -108,6 +108,45 @@ def test_velocity_and_external_vector(orc):
     assert np.array_equal(lat.download(), ref)
 
 
+def test_velocity_plane_extrapolation(orc):
+    """bib_velocity_extrapolate_plane = CouetteVelocityExtrapolator::process (progs/common/shear_flow_setup.h:121-183) on the device field."""
+    g = np.load(kit.GOLDEN / "lbm_periodic.npz")
+    lat = make_lattice(g["pop_1"], g["per"], 1.0, 0.5)
+    u = lat.computeVelocity()
+    ny = u.shape[1]
+    lat.velocity_extrapolate_plane(1, 0, +1)
+    lat.velocity_extrapolate_plane(1, ny - 1, -1)
+    ref = u.copy()
+    ref[:, 0] = 2.0 * u[:, 1] - u[:, 2]
+    ref[:, ny - 1] = 2.0 * u[:, ny - 2] - u[:, ny - 3]
+    assert np.array_equal(lat.velocity(), ref)
+    with pytest.raises(bib.BibError):
+        lat.velocity_extrapolate_plane(1, 1, -1)             # needs two planes on the inward side
+
+
+def test_vertex_force_preload(rbc):
+    """bib_ib_vertex_forces_preload (host-evaluated ForceDecorators): the next force evaluation starts from the given values, exactly once;
+    a zero preload changes nothing, bit for bit."""
+    shape, params, _, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc1.npz")
+    lats = [run_ib_case(g, shape, params, deterministic=True) for _ in range(3)]
+    rng = np.random.default_rng(3)
+    f0 = 1e-4 * rng.normal(size=(shape.nv, 3))
+    lats[1].preload_vertex_forces(np.zeros((shape.nv, 3)))
+    lats[2].preload_vertex_forces(f0)
+    for lat in lats:
+        lat.computeVelocity(download=False); lat.interpolate_velocity(); lat.compute_and_spread_forces()
+    base, zero, pre = (lat.vertices()[:, 6:] for lat in lats)
+    assert np.array_equal(base, zero)
+    assert np.abs(pre - (base + f0)).max() <= 1e-12 * max(1.0, np.abs(base).max()) and np.abs(pre - base).max() > 1e-5
+    lats[2].move_vertices_and_revoxelize(); lats[0].move_vertices_and_revoxelize()
+    # one-shot: the following evaluation starts from zero again (positions differ by now, so compare against a fresh preload-free sum)
+    lats[2].upload_vertices(lats[0].vertices())
+    for lat in (lats[0], lats[2]):
+        lat.computeVelocity(download=False); lat.interpolate_velocity(); lat.compute_and_spread_forces()
+    assert np.array_equal(lats[0].vertices()[:, 6:], lats[2].vertices()[:, 6:])
+
+
 def test_shape_connectivity_matches_reference(rbc):
     shape, _, _, z = rbc
     lat = bib.Lattice(4, 4, 4, 1.0, 1.0)
