@@ -11,7 +11,7 @@ import kit
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 BUILD = ROOT / "overlay" / "_build"
-DRIVERS = ["rbc_in_shear", "capsule_in_shear", "rbcs_in_shear"]
+DRIVERS = ["rbc_in_shear", "capsule_in_shear", "rbcs_in_shear", "rbc_in_pipe", "rigid_particle_in_shear", "deformation_test"]
 
 
 @pytest.mark.parametrize("driver", DRIVERS)
@@ -25,6 +25,12 @@ def test_unchanged_driver_binds_to_the_cabi(driver):
                 "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces", "bib_ib_move_vertices_and_revoxelize"):
         assert sym in used, f"{driver} does not call {sym}"
     assert set(used) <= set(bib.SYMBOLS), "the binding uses symbols the header does not declare"
+    if driver == "rbcs_in_shear":
+        assert "bib_velocity_extrapolate_plane" in used          # CouetteVelocityExtrapolator runs on the device
+    if driver == "deformation_test":
+        assert "bib_ib_vertex_forces_preload" in used            # the driver's own OpticalTweezerForce is evaluated on the host and handed over
+    if driver == "rbc_in_pipe":
+        assert "bib_set_guo_wall_nodes" in used and "bib_ib_set_pp_interaction" in used
 
 
 def test_sphere_in_ext_flow_binds_to_the_cabi():
