@@ -37,9 +37,28 @@ def test_bad_arguments_return_zero():
     h = C.c_void_p()
     per = (C.c_int * 3)(1, 1, 1)
     assert lib.bib_domain_create(0, 4, 4, 4, C.c_double(1.0), C.c_double(1.0), per, 0, C.byref(h)) == 0
-    assert lib.bib_domain_create(4, 4, 4, 3, C.c_double(1.0), C.c_double(1.0), per, 0, C.byref(h)) == 0
+    assert lib.bib_domain_create(4, 4, 4, 5, C.c_double(1.0), C.c_double(1.0), per, 0, C.byref(h)) == 0      # n_ext is 3 or 4
     assert lib.bib_domain_create(4, 4, 4, 4, C.c_double(2.5), C.c_double(1.0), per, 0, C.byref(h)) == 0
     assert not h
+
+
+def test_null_handle_is_rejected_by_every_entry_point():
+    """Every entry point that takes a domain handle returns 0 (never crashes) for a NULL handle and names the problem."""
+    lib = bib.load_library()
+    text = (ROOT / "include" / "biblbm_b200.h").read_text()
+    protos = re.findall(r"^int (bib_[a-z0-9_]+)\(bib_domain\* d([^)]*)\);", text, flags=re.M)
+    assert len(protos) >= 45
+    for name, rest in protos:
+        if name == "bib_domain_destroy":          # like free(NULL): nothing to do, succeeds
+            assert lib.bib_domain_destroy(None) == 1
+            continue
+        n_args = 0 if not rest.strip() else rest.count(",")
+        args = []
+        for a in [x.strip() for x in rest.split(",")[1:]]:
+            args.append(C.c_double(0.0) if a.startswith("double ") else (C.c_longlong(0) if a.startswith("long long ") else (C.c_void_p(None) if "*" in a or "[" in a else C.c_int(0))))
+        assert len(args) == n_args
+        assert getattr(lib, name)(None, *args) == 0, name
+        assert b"null domain" in lib.bib_last_error(), name
 
 
 def test_no_cpu_fallback():
