@@ -177,7 +177,7 @@ def driver_speed():
             return time.perf_counter() - t0
     try:
         run(gpu, 500)                                               # warm-up (driver + CUDA context start-up on this box)
-        g = (run(gpu, 4500) - min(run(gpu, 500), run(gpu, 500))) / 4000.0
+        g = (run(gpu, 12500) - min(run(gpu, 500), run(gpu, 500))) / 12000.0       # start-up jitter of +-1 s -> +-0.08 ms per step
         c = (run(cpu, 35) - run(cpu, 5)) / 30.0
     except Exception as e:      # reported, never fatal for the bench line
         return {"error": str(e)[:200]}
