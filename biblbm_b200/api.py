@@ -18,7 +18,7 @@ LIB_PATH = _HERE / "libbiblbm_b200.so"
 
 # every symbol include/biblbm_b200.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
-    "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_destroy", "bib_domain_set_option",
+    "bib_last_error", "bib_version", "bib_device_count", "bib_domain_create", "bib_domain_create_multi", "bib_domain_slab_count", "bib_domain_slab", "bib_domain_destroy", "bib_domain_set_option",
     "bib_domain_upload", "bib_domain_download", "bib_domain_set_celltype", "bib_domain_init_equilibrium", "bib_add_velocity_boundary", "bib_set_boundary_velocity", "bib_set_guo_wall_nodes", "bib_set_external_vector", "bib_compute_velocity",
     "bib_velocity_download", "bib_velocity_upload", "bib_velocity_extrapolate_plane", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
@@ -82,15 +82,22 @@ def comm_unique_id() -> bytes:
 class Lattice:
     """One x-slab of a D3Q19 ForcedPhase lattice + its immersed particles, resident on one GPU."""
 
-    def __init__(self, nx, ny, nz, omega, omega_inner, periodic=(True, True, True), device=0):
-        """omega_inner=None: ForcedD3Q19Descriptor cells (22 scalars) with the single-rate GuoExternalForceBGKdynamics(omega)."""
+    def __init__(self, nx, ny, nz, omega, omega_inner, periodic=(True, True, True), device=0, slabs=1, devices=None):
+        """omega_inner=None: ForcedD3Q19Descriptor cells (22 scalars) with the single-rate GuoExternalForceBGKdynamics(omega).
+        slabs > 1: the lattice is split into equal x-slabs owned by this process (bib_domain_create_multi), on `devices` (default:
+        every slab on `device`); the object is then used exactly like a single-slab one (global boxes and particle ids)."""
         self.lib = load_library()
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.h = C.c_void_p()
         per = (C.c_int * 3)(*[int(bool(p)) for p in periodic])
         self.n_ext = 3 if omega_inner is None else 4
         self.ncomp = 19 + self.n_ext
-        _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, self.n_ext, C.c_double(omega), C.c_double(omega_inner or 0.0), per, int(device), C.byref(self.h)))
+        self.slabs = int(slabs)
+        if self.slabs > 1:
+            devs = (C.c_int * self.slabs)(*[int(v) for v in (devices if devices is not None else [device] * self.slabs)])
+            _check(self.lib.bib_domain_create_multi(self.nx, self.ny, self.nz, self.n_ext, C.c_double(omega), C.c_double(omega_inner or 0.0), per, self.slabs, devs, C.byref(self.h)))
+        else:
+            _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, self.n_ext, C.c_double(omega), C.c_double(omega_inner or 0.0), per, int(device), C.byref(self.h)))
         self.full = (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1)
         self.shape_nv = {}
 

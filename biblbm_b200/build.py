@@ -14,7 +14,7 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbiblbm_b200.so"
-SOURCES = ["api.cu", "lbm_kernels.cu", "ib_kernels.cu", "ib_multislab.cu", "comm.cu"]
+SOURCES = ["api.cu", "lbm_kernels.cu", "ib_kernels.cu", "ib_multislab.cu", "comm.cu", "group.cu"]
 HEADERS = [CSRC / "domain.cuh", HERE.parent / "include" / "biblbm_b200.h"]
 
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-           "-Xcompiler", "-fPIC", "-shared", *nccl_include_flags(), "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl"]
+           "-Xcompiler", "-fPIC", "-shared", *nccl_include_flags(), "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

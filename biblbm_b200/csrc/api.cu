@@ -20,6 +20,52 @@ bool bib_cuda_ok(cudaError_t e, const char* what) {
 void ms_destroy(bib_domain* d);
 int ms_check_overflow(bib_domain* d);
 
+// in-process slab groups (group.cu): the head handle's version of each entry point
+int group_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3], int n_slabs, const int* devices, bib_domain** out);
+int group_destroy(bib_domain* head);
+int group_set_option(bib_domain* h, int key, double value);
+int group_upload(bib_domain* h, const int box[6], const double* cells);
+int group_download(bib_domain* h, const int box[6], double* cells);
+int group_set_celltype(bib_domain* h, const int box[6], int kind);
+int group_init_equilibrium(bib_domain* h, const int box[6], double rho, double ux, double uy, double uz);
+int group_add_velocity_boundary(bib_domain* h, const int box[6], int direction, int orientation);
+int group_set_boundary_velocity(bib_domain* h, const int box[6], const double* velocities);
+int group_set_guo_wall_nodes(bib_domain* h, int n, const int* location_direction6, const double* delta, const double* wall_velocity3);
+int group_set_external_vector(bib_domain* h, const int box[6], double fx, double fy, double fz);
+int group_compute_velocity(bib_domain* h, const int box[6]);
+int group_velocity_download(bib_domain* h, const int box[6], double* velocity);
+int group_velocity_upload(bib_domain* h, const int box[6], const double* velocity);
+int group_velocity_extrapolate_plane(bib_domain* h, int direction, int coord, int inward);
+int group_collide_and_stream(bib_domain* h);
+int group_shape_register(bib_domain* h, int nv, int nt, const double* vertices, const int* triangles, int* shape_id);
+int group_particles_add(bib_domain* h, int type, int shape_id, const double* params, int n, const double* positions);
+int group_count(bib_domain* h, int* n_particles, long long* n_vertices);
+int group_vertices_download(bib_domain* h, long long first, long long count, double* v9);
+int group_vertices_upload(bib_domain* h, long long first, long long count, const double* v9);
+int group_scalars_download(bib_domain* h, int first, int count, double* s11);
+int group_scalars_upload(bib_domain* h, int first, int count, const double* s11);
+int group_local_slots(bib_domain* h, int* global_ids, int* roles, int capacity, int* n_slots);
+int group_set_regulator(bib_domain* h, double p, double tx, double ty, double tz);
+int group_set_parallel_plates(bib_domain* h, int enabled, double y0, double y1);
+int group_set_pipe(bib_domain* h, int enabled, double y0, double z0, double radius);
+int group_set_wall_interaction(bib_domain* h, int type, double r_min, double beta, double strength);
+int group_set_wall_interaction_boundary(bib_domain* h, int kind, double p0, double p1, double p2);
+int group_set_pp_interaction(bib_domain* h, int type, double r_min, double beta, double strength);
+int group_ib_interpolate(bib_domain* h);
+int group_ib_forces_spread(bib_domain* h);
+int group_ib_move(bib_domain* h);
+int group_ib_step(bib_domain* h);
+int group_step(bib_domain* h, double fx, double fy, double fz, int n_steps);
+int group_sync(bib_domain* h);
+int group_time_begin(bib_domain* h);
+int group_time_end(bib_domain* h, float* ms);
+int group_launch_count(bib_domain* h, long long* launches);
+int group_memory_bytes(bib_domain* h, long long* bytes);
+bib_domain* group_slab_of(bib_domain* h, int r);
+int group_size(bib_domain* h);
+#define BIB_HEAD(d, call) do { if ((d) && (d)->is_head) return (call); } while (0)
+#define BIB_HEAD_UNSUPPORTED(d, what) do { if ((d) && (d)->is_head) { bib_set_error(what ": not available on a multi-slab (bib_domain_create_multi) handle"); return 0; } } while (0)
+
 extern "C" {
 
 const char* bib_last_error(void) { return g_last_error.c_str(); }
@@ -55,6 +101,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     }
     if (device < 0 || device >= ndev) { bib_set_error("domain_create: device index out of range"); return 0; }
     BIB_CHECK(cudaSetDevice(device));
+    if (!ib_set_kernel_attributes()) return 0;          // function attributes are per device: set for every device a domain is created on
     bib_domain* d = new (std::nothrow) bib_domain();
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
     d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
@@ -93,8 +140,31 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     return 1;
 }
 
+int bib_domain_create_multi(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3],
+                            int n_slabs, const int* devices, bib_domain** out) {
+    if (!out || !periodic) { bib_set_error("domain_create_multi: null argument"); return 0; }
+    *out = nullptr;
+    if (n_slabs == 1) return bib_domain_create(nx, ny, nz, n_ext, omega_outer, omega_inner, periodic, devices ? devices[0] : 0, out);
+    return group_create(nx, ny, nz, n_ext, omega_outer, omega_inner, periodic, n_slabs, devices, out);
+}
+int bib_domain_slab_count(bib_domain* d, int* n_slabs) {
+    if (!d) { bib_set_error("null domain handle"); return 0; }
+    if (!n_slabs) { bib_set_error("slab_count: null argument"); return 0; }
+    *n_slabs = d->is_head ? group_size(d) : 1;
+    return 1;
+}
+int bib_domain_slab(bib_domain* d, int slab, bib_domain** out) {
+    if (!d) { bib_set_error("null domain handle"); return 0; }
+    if (!out) { bib_set_error("domain_slab: null argument"); return 0; }
+    *out = d->is_head ? group_slab_of(d, slab) : (slab == 0 ? d : nullptr);
+    if (!*out) { bib_set_error("domain_slab: slab index out of range"); return 0; }
+    return 1;
+}
+
 int bib_domain_destroy(bib_domain* d) {
     if (!d) return 1;
+    if (d->is_head) return group_destroy(d);
+    if (d->group) { bib_set_error("domain_destroy: this slab belongs to a multi-slab handle; destroy that handle"); return 0; }
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     comm_destroy(d);
@@ -157,6 +227,7 @@ int bib_domain_destroy(bib_domain* d) {
 #define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; (d)->forces_ready = false; (d)->plain_steps_since_dirty = 0; } while (0)
 
 int bib_domain_set_option(bib_domain* d, int key, double value) {
+    BIB_HEAD(d, group_set_option(d, key, value));
     BIB_ENTER(d);
     switch (key) {
         case BIB_OPT_ENVELOPE_SWAP: d->envelope_swap = value != 0.0; return 1;
@@ -174,6 +245,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
 }
 
 int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
+    if (d && d->is_head && box && cells) return group_upload(d, box, cells);
     BIB_ENTER(d);
     if (!box || !cells) { bib_set_error("upload: null argument"); return 0; }
     d->vel_full_valid = false; d->force_is_body = false; d->fflag_valid = false;
@@ -181,56 +253,63 @@ int bib_domain_upload(bib_domain* d, const int box[6], const double* cells) {
     return 1;
 }
 int bib_domain_download(bib_domain* d, const int box[6], double* cells) {
+    if (d && d->is_head && box && cells) return group_download(d, box, cells);
     BIB_ENTER_RO(d);
     if (!box || !cells) { bib_set_error("download: null argument"); return 0; }
     return lbm_launch_download(d, box, cells);
 }
 int bib_domain_set_celltype(bib_domain* d, const int box[6], int kind) {
+    if (d && d->is_head && box) return group_set_celltype(d, box, kind);
     BIB_ENTER(d);
     if (!box) { bib_set_error("set_celltype: null argument"); return 0; }
     return lbm_set_celltype(d, box, kind);
 }
 int bib_domain_init_equilibrium(bib_domain* d, const int box[6], double rho, double ux, double uy, double uz) {
+    if (d && d->is_head && box) return group_init_equilibrium(d, box, rho, ux, uy, uz);
     BIB_ENTER(d);
     if (!box) { bib_set_error("init_equilibrium: null argument"); return 0; }
     if (!(rho > 0.0)) { bib_set_error("init_equilibrium: density must be positive"); return 0; }
     return lbm_init_equilibrium(d, box, rho, ux, uy, uz);
 }
 int bib_add_velocity_boundary(bib_domain* d, const int box[6], int direction, int orientation) {
+    if (d && d->is_head && box) return group_add_velocity_boundary(d, box, direction, orientation);
     BIB_ENTER(d);
     if (!box) { bib_set_error("add_velocity_boundary: null argument"); return 0; }
     return lbm_add_wall(d, box, direction, orientation);
 }
 int bib_set_boundary_velocity(bib_domain* d, const int box[6], const double* velocities) {
+    if (d && d->is_head && box && velocities) return group_set_boundary_velocity(d, box, velocities);
     BIB_ENTER(d);
     if (!box || !velocities) { bib_set_error("set_boundary_velocity: null argument"); return 0; }
     return lbm_set_wall_velocity(d, box, velocities);
 }
 int bib_add_velocity_edge(bib_domain* d, const int box[6], int axis, int normal1, int normal2) {
+    BIB_HEAD_UNSUPPORTED(d, "add_velocity_edge");
     BIB_ENTER(d);
     if (!box) { bib_set_error("add_velocity_edge: null argument"); return 0; }
     return lbm_add_edge(d, box, axis, normal1, normal2);
 }
 int bib_set_guo_wall_nodes(bib_domain* d, int n, const int* location_direction6, const double* delta, const double* wall_velocity3) {
+    BIB_HEAD(d, group_set_guo_wall_nodes(d, n, location_direction6, delta, wall_velocity3));
     BIB_ENTER(d);
     if (n > 0 && (!location_direction6 || !delta)) { bib_set_error("set_guo_wall_nodes: null argument"); return 0; }
     return lbm_set_guo_nodes(d, n, location_direction6, delta, wall_velocity3);
 }
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
+    if (d && d->is_head && box) return group_set_external_vector(d, box, fx, fy, fz);
     BIB_ENTER(d);
     if (!box) { bib_set_error("set_external_vector: null argument"); return 0; }
     const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
-    // Every cell outside the bands the last spread touched still holds the same body force: reset the bands only. Needs this
-    // step's interpolation to have run already (it rotates the band masks), i.e. the calling order of bib_step.
-    if (full && d->force_is_body && d->force_body[0] == fx && d->force_body[1] == fy && d->force_body[2] == fz) {
-        if (d->n_particles == 0) return 1;
-        if (d->interp_since_spread) return ib_band_reset(d, fx, fy, fz);
-    }
+    // Every cell outside the bands the last spread touched still holds the same body force: reset those bands only (ib_band_reset
+    // knows which mask buffer the spread used and falls back to the whole lattice when it does not).
+    if (full && d->force_is_body && d->force_body[0] == fx && d->force_body[1] == fy && d->force_body[2] == fz)
+        return ib_band_reset(d, fx, fy, fz);
     d->force_is_body = full;
     if (full) { d->force_body[0] = fx; d->force_body[1] = fy; d->force_body[2] = fz; }
     return lbm_launch_set_external(d, box, fx, fy, fz);
 }
 int bib_compute_velocity(bib_domain* d, const int box[6]) {
+    if (d && d->is_head && box) return group_compute_velocity(d, box);
     BIB_ENTER(d);
     if (!box) { bib_set_error("compute_velocity: null argument"); return 0; }
     if (!lbm_launch_velocity(d, box)) return 0;
@@ -238,11 +317,13 @@ int bib_compute_velocity(bib_domain* d, const int box[6]) {
     return 1;
 }
 int bib_velocity_download(bib_domain* d, const int box[6], double* velocity) {
+    if (d && d->is_head && box && velocity) return group_velocity_download(d, box, velocity);
     BIB_ENTER(d);
     if (!box || !velocity) { bib_set_error("velocity_download: null argument"); return 0; }
     return lbm_velocity_download(d, box, velocity);
 }
 int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity) {
+    if (d && d->is_head && box && velocity) return group_velocity_upload(d, box, velocity);
     BIB_ENTER(d);
     if (!box || !velocity) { bib_set_error("velocity_upload: null argument"); return 0; }
     if (!lbm_velocity_upload(d, box, velocity)) return 0;
@@ -250,21 +331,25 @@ int bib_velocity_upload(bib_domain* d, const int box[6], const double* velocity)
     return 1;
 }
 int bib_velocity_extrapolate_plane(bib_domain* d, int direction, int coord, int inward) {
+    BIB_HEAD(d, group_velocity_extrapolate_plane(d, direction, coord, inward));
     BIB_ENTER(d);
     return lbm_velocity_extrapolate(d, direction, coord, inward);
 }
 int bib_collide_and_stream(bib_domain* d) {
+    BIB_HEAD(d, group_collide_and_stream(d));
     BIB_ENTER(d);
     d->vel_full_valid = false;
     return lbm_launch_collide_stream(d);
 }
 
 int bib_ib_shape_register(bib_domain* d, int nv, int nt, const double* vertices, const int* triangles, int* shape_id) {
+    if (d && d->is_head && shape_id) return group_shape_register(d, nv, nt, vertices, triangles, shape_id);
     BIB_ENTER(d);
     if (!shape_id) { bib_set_error("shape_register: null argument"); return 0; }
     return ib_shape_register(d, nv, nt, vertices, triangles, shape_id);
 }
 int bib_ib_shape_info(bib_domain* d, int shape_id, int* n_links, int* n_pairs, double* area, double* volume) {
+    if (d && d->is_head) return bib_ib_shape_info(group_slab_of(d, 0), shape_id, n_links, n_pairs, area, volume);
     BIB_ENTER(d);
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("shape_info: unknown shape"); return 0; }
     const ShapeDev& s = d->shapes[shape_id];
@@ -275,6 +360,7 @@ int bib_ib_shape_info(bib_domain* d, int shape_id, int* n_links, int* n_pairs, d
     return 1;
 }
 int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* link_len, int* pairs, double* pair_cos_sin, double* tri_area) {
+    if (d && d->is_head) return bib_ib_shape_connectivity(group_slab_of(d, 0), shape_id, links, link_len, pairs, pair_cos_sin, tri_area);
     BIB_ENTER(d);
     if (shape_id < 0 || shape_id >= (int)d->shapes.size()) { bib_set_error("shape_connectivity: unknown shape"); return 0; }
     const ShapeDev& s = d->shapes[shape_id];
@@ -286,37 +372,44 @@ int bib_ib_shape_connectivity(bib_domain* d, int shape_id, int* links, double* l
     return 1;
 }
 int bib_ib_particles_add(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
+    if (d && d->is_head && params && (n <= 0 || positions)) return group_particles_add(d, type, shape_id, params, n, positions);
     BIB_ENTER(d);
     if (!params || (n > 0 && !positions)) { bib_set_error("particles_add: null argument"); return 0; }
     return ib_particles_add(d, type, shape_id, params, n, positions);
 }
 int bib_ib_rigid_particles_add(bib_domain* d, int shape_id, const double* inertia9, double shape_volume, int n, const double* state17) {
+    BIB_HEAD_UNSUPPORTED(d, "rigid_particles_add");
     BIB_ENTER(d);
     if (!inertia9 || (n > 0 && !state17)) { bib_set_error("rigid_particles_add: null argument"); return 0; }
     return ib_rigid_add(d, shape_id, inertia9, shape_volume, n, state17);
 }
 int bib_ib_rigid_state_download(bib_domain* d, int first_particle, int count, double* state19) {
+    BIB_HEAD_UNSUPPORTED(d, "rigid_state_download");
     BIB_ENTER_RO(d);
     if (count > 0 && !state19) { bib_set_error("rigid_state_download: null argument"); return 0; }
     return ib_rigid_download(d, first_particle, count, state19);
 }
 int bib_ib_rigid_state_upload(bib_domain* d, int first_particle, int count, const double* state19) {
+    BIB_HEAD_UNSUPPORTED(d, "rigid_state_upload");
     BIB_ENTER(d);
     if (count > 0 && !state19) { bib_set_error("rigid_state_upload: null argument"); return 0; }
     return ib_rigid_upload(d, first_particle, count, state19);
 }
 int bib_ib_set_regulator(bib_domain* d, double p, double tx, double ty, double tz) {
+    BIB_HEAD(d, group_set_regulator(d, p, tx, ty, tz));
     BIB_ENTER(d);
     d->regulator_p = p; d->regulator_target[0] = tx; d->regulator_target[1] = ty; d->regulator_target[2] = tz;
     return 1;
 }
 int bib_ib_set_parallel_plates(bib_domain* d, int enabled, double y0, double y1) {
+    BIB_HEAD(d, group_set_parallel_plates(d, enabled, y0, y1));
     BIB_ENTER(d);
     if (enabled && !(y1 > y0)) { bib_set_error("set_parallel_plates: need y1 > y0"); return 0; }
     d->plates = enabled ? 1 : 0; d->plate_y0 = y0; d->plate_y1 = y1;
     return 1;
 }
 int bib_ib_set_pipe(bib_domain* d, int enabled, double y0, double z0, double radius) {
+    BIB_HEAD(d, group_set_pipe(d, enabled, y0, z0, radius));
     BIB_ENTER(d);
     if (enabled && !(radius > 0)) { bib_set_error("set_pipe: need radius > 0"); return 0; }
     d->plates = enabled ? 2 : 0; d->plate_y0 = y0; d->plate_y1 = z0; d->pipe_radius = radius;
@@ -328,38 +421,45 @@ static int set_potential(PotentialDev& q, int type, double r_min, double beta, d
     return 1;
 }
 int bib_ib_set_wall_interaction(bib_domain* d, int type, double r_min, double beta, double strength) {
+    BIB_HEAD(d, group_set_wall_interaction(d, type, r_min, beta, strength));
     BIB_ENTER(d);
     return set_potential(d->wall_pot, type, r_min, beta, strength, "set_wall_interaction");
 }
 int bib_ib_set_wall_interaction_boundary(bib_domain* d, int kind, double p0, double p1, double p2) {
+    BIB_HEAD(d, group_set_wall_interaction_boundary(d, kind, p0, p1, p2));
     BIB_ENTER(d);
     if (kind < -1 || kind > 2) { bib_set_error("set_wall_interaction_boundary: kind must be -1 (boundary of set_boundary), 0, 1 (plates y0,y1) or 2 (pipe y0,z0,radius)"); return 0; }
     d->wall_bkind = kind; d->wall_b[0] = p0; d->wall_b[1] = p1; d->wall_b[2] = p2;
     return 1;
 }
 int bib_ib_set_pp_interaction(bib_domain* d, int type, double r_min, double beta, double strength) {
+    BIB_HEAD(d, group_set_pp_interaction(d, type, r_min, beta, strength));
     BIB_ENTER(d);
     return set_potential(d->pp_pot, type, r_min, beta, strength, "set_pp_interaction");
 }
 int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
+    BIB_HEAD(d, group_count(d, n_particles, n_vertices));
     BIB_ENTER_RO(d);
     if (n_particles) *n_particles = d->n_particles;
     if (n_vertices) *n_vertices = d->n_vertices;
     return 1;
 }
 int bib_ib_interpolate_velocity(bib_domain* d) {
+    BIB_HEAD(d, group_ib_interpolate(d));
     BIB_ENTER(d);
     // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
     return ib_interpolate(d);
 }
-int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_ENTER(d); return ib_forces_and_spread(d); }
-int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_ENTER(d); return ib_move_and_voxelize(d); }
+int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_HEAD(d, group_ib_forces_spread(d)); BIB_ENTER(d); return ib_forces_and_spread(d); }
+int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_HEAD(d, group_ib_move(d)); BIB_ENTER(d); return ib_move_and_voxelize(d); }
 int bib_ib_step(bib_domain* d) {
+    BIB_HEAD(d, group_ib_step(d));
     BIB_ENTER(d);
     return ib_interpolate(d) && ib_forces_and_spread(d) && ib_move_and_voxelize(d);
 }
 // MultiDirectForcingFunctional3D::process (progs/sphere_in_ext_flow/sphere_in_ext_flow.cpp:26-98; oracle/biblbm_oracle.c orc_mdf_step)
 int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations) {
+    BIB_HEAD_UNSUPPORTED(d, "multi_direct_forcing");
     BIB_ENTER(d);
     if (relax_iterations < 0) { bib_set_error("multi_direct_forcing: negative iteration count"); return 0; }
     if (d->n_ranks > 1) { bib_set_error("multi_direct_forcing: single-slab domains only"); return 0; }
@@ -376,44 +476,52 @@ int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations) {
     return ib_force_accumulate(d, 2) && ib_update_all(d, 1);   // node force := -sum, then move_vertices()
 }
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9) {
+    if (d && d->is_head && (count <= 0 || vertices9)) return group_vertices_download(d, first_vertex, count, vertices9);
     BIB_ENTER_RO(d);
     if (count > 0 && !vertices9) { bib_set_error("vertices_download: null argument"); return 0; }
     return ib_vertices_download(d, first_vertex, count, vertices9);
 }
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9) {
+    if (d && d->is_head && (count <= 0 || vertices9)) return group_vertices_upload(d, first_vertex, count, vertices9);
     BIB_ENTER(d);
     if (count > 0 && !vertices9) { bib_set_error("vertices_upload: null argument"); return 0; }
     return ib_vertices_upload(d, first_vertex, count, vertices9);
 }
 int bib_ib_vertex_forces_preload(bib_domain* d, long long first_vertex, long long count, const double* forces3) {
+    BIB_HEAD_UNSUPPORTED(d, "vertex_forces_preload");
     BIB_ENTER(d);
     if (count > 0 && !forces3) { bib_set_error("vertex_forces_preload: null argument"); return 0; }
     if (d->n_ranks > 1) { bib_set_error("vertex_forces_preload: single-slab domains only"); return 0; }
     return ib_forces_preload(d, first_vertex, count, forces3);
 }
 int bib_ib_local_slots(bib_domain* d, int* global_ids, int* roles, int capacity, int* n_slots) {
+    if (d && d->is_head && global_ids && roles && n_slots) return group_local_slots(d, global_ids, roles, capacity, n_slots);
     BIB_ENTER_RO(d);
     if (!global_ids || !roles || !n_slots) { bib_set_error("local_slots: null argument"); return 0; }
     return ib_local_slots(d, global_ids, roles, capacity, n_slots);
 }
 int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int count, double* scalars11) {
+    if (d && d->is_head && (count <= 0 || scalars11)) return group_scalars_download(d, first_particle, count, scalars11);
     BIB_ENTER_RO(d);
     if (count > 0 && !scalars11) { bib_set_error("particle_scalars_download: null argument"); return 0; }
     return ib_scalars_download(d, first_particle, count, scalars11);
 }
 int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count, const double* scalars11) {
+    if (d && d->is_head && (count <= 0 || scalars11)) return group_scalars_upload(d, first_particle, count, scalars11);
     BIB_ENTER(d);
     if (count > 0 && !scalars11) { bib_set_error("particle_scalars_upload: null argument"); return 0; }
     if (d->n_ranks > 1) { bib_set_error("particle_scalars_upload: single-slab domains only"); return 0; }
     return ib_scalars_upload(d, first_particle, count, scalars11);
 }
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11) {
+    BIB_HEAD_UNSUPPORTED(d, "results_download_async (use bib_ib_vertices_download / bib_ib_particle_scalars_download, or the per-slab handles of bib_domain_slab)");
     BIB_ENTER_RO(d);
     if (!vertices9 || !scalars11) { bib_set_error("results_download_async: null argument"); return 0; }
     return ib_results_download_async(d, vertices9, scalars11);
 }
-int bib_ib_results_wait(bib_domain* d) { BIB_ENTER_RO(d); return ib_results_wait(d); }
+int bib_ib_results_wait(bib_domain* d) { BIB_HEAD_UNSUPPORTED(d, "results_wait"); BIB_ENTER_RO(d); return ib_results_wait(d); }
 int bib_ib_results_count(bib_domain* d, int* n_particles) {
+    BIB_HEAD_UNSUPPORTED(d, "results_count");
     BIB_ENTER_RO(d);
     if (!n_particles) { bib_set_error("results_count: null argument"); return 0; }
     return ib_results_count(d, n_particles);
@@ -457,12 +565,14 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
     if (!ib_move_and_voxelize(d)) return 0;
     d->vel_full_valid = false;
     if (prefetch) {
-        if (d->vfrc_next_cap != d->cap_vertices) {
+        cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(d->stream, &cap_status);
+        if (d->vfrc_next_cap != d->cap_vertices && cap_status == cudaStreamCaptureStatusNone) {      // never allocate inside a capture
             if (d->vfrc_next) { cudaFree(d->vfrc_next); d->vfrc_next = nullptr; d->vfrc_next_cap = 0; }
             if (cudaMalloc(&d->vfrc_next, (size_t)d->cap_vertices * 3 * sizeof(double)) == cudaSuccess) d->vfrc_next_cap = d->cap_vertices;
             else { cudaGetLastError(); d->vfrc_next = nullptr; }
         }
-        if (d->vfrc_next) {
+        if (d->vfrc_next && d->vfrc_next_cap == d->cap_vertices) {
             BIB_CHECK(cudaEventRecord(d->ev_fork, d->stream));
             BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_fork, 0));
             std::swap(d->vfrc, d->vfrc_next);                 // ib_forces writes d->vfrc: aim it at the second array for this call
@@ -489,9 +599,10 @@ static void step_graphs_destroy(bib_domain* d) {
     for (StepGraph& g : d->sg) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
 }
 static bool step_graph_matches(const bib_domain* d, const StepGraph& g) {
-    return g.exec && d->cur == g.cur && d->band_cur == g.band_cur && d->vfrc == g.vfrc && d->forces_ready == g.forces_ready;
+    return g.exec && d->cur == g.cur && d->band_cur == g.band_cur && d->spread_band == g.spread_band && d->vfrc == g.vfrc && d->forces_ready == g.forces_ready;
 }
 int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
+    BIB_HEAD(d, group_step(d, body_fx, body_fy, body_fz, n_steps));
     BIB_ENTER_RO(d);
     int s = 0;
     const bool same_body = d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz;
@@ -508,10 +619,13 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
             d->plain_steps_since_dirty++;
         }
         if (d->plain_steps_since_dirty >= 2 && s < n_steps) {
+            // host-side state the captured (not executed) steps advance: restored if the capture does not succeed
+            struct { int cur, band_cur, spread_band; bool band_valid[2], band_pos_valid, forces_ready, vel_full_valid, force_is_body, fflag_valid; double* vfrc; double* vfrc_next; long long launches; } snap =
+                {d->cur, d->band_cur, d->spread_band, {d->band_valid[0], d->band_valid[1]}, d->band_pos_valid, d->forces_ready, d->vel_full_valid, d->force_is_body, d->fflag_valid, d->vfrc, d->vfrc_next, d->launches};
             bool ok = true;
             for (int k = 0; k < 2 && ok; ++k) {
                 StepGraph& g = d->sg[k];
-                g.cur = d->cur; g.band_cur = d->band_cur; g.vfrc = d->vfrc; g.forces_ready = d->forces_ready;   // the state this step starts from
+                g.cur = d->cur; g.band_cur = d->band_cur; g.spread_band = d->spread_band; g.vfrc = d->vfrc; g.forces_ready = d->forces_ready;   // the state this step starts from
                 const long long l0 = d->launches;
                 cudaGraph_t graph = nullptr;
                 ok = cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
@@ -531,6 +645,9 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
             } else {
                 step_graphs_destroy(d);
                 d->use_graph = 0;                                  // something in this configuration is not capturable: plain launches from now on
+                d->cur = snap.cur; d->band_cur = snap.band_cur; d->spread_band = snap.spread_band; d->band_valid[0] = snap.band_valid[0]; d->band_valid[1] = snap.band_valid[1];
+                d->band_pos_valid = snap.band_pos_valid; d->forces_ready = snap.forces_ready; d->vel_full_valid = snap.vel_full_valid;
+                d->force_is_body = snap.force_is_body; d->fflag_valid = snap.fflag_valid; d->vfrc = snap.vfrc; d->vfrc_next = snap.vfrc_next; d->launches = snap.launches;
             }
             cudaGetLastError();
         }
@@ -544,7 +661,7 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
             d->launches += d->sg[k].launches;
             // the host-side state one step later = the state the other graph starts from
             const StepGraph& nx = d->sg[1 - k];
-            d->cur = nx.cur; d->band_cur = nx.band_cur; d->forces_ready = nx.forces_ready;
+            d->cur = nx.cur; d->band_cur = nx.band_cur; d->spread_band = nx.spread_band; d->forces_ready = nx.forces_ready;
             if (d->vfrc != nx.vfrc) std::swap(d->vfrc, d->vfrc_next);
         }
     }
@@ -557,6 +674,7 @@ int bib_comm_unique_id(void* unique_id_128) {
     return comm_unique_id(unique_id_128);
 }
 int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128) {
+    BIB_HEAD_UNSUPPORTED(d, "comm_init");
     BIB_ENTER(d);
     if (!unique_id_128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) { bib_set_error("comm_init: bad arguments"); return 0; }
     if (d->n_particles > 0) { bib_set_error("comm_init: call bib_comm_init before adding particles"); return 0; }
@@ -564,13 +682,15 @@ int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_12
 }
 
 int bib_sync(bib_domain* d) {
+    BIB_HEAD(d, group_sync(d));
     BIB_ENTER_RO(d);
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->comm_stream));
     return ms_check_overflow(d);
 }
-int bib_time_begin(bib_domain* d) { BIB_ENTER_RO(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
+int bib_time_begin(bib_domain* d) { BIB_HEAD(d, group_time_begin(d)); BIB_ENTER_RO(d); BIB_CHECK(cudaEventRecord(d->ev0, d->stream)); return 1; }
 int bib_time_end(bib_domain* d, float* milliseconds) {
+    if (d && d->is_head && milliseconds) return group_time_end(d, milliseconds);
     BIB_ENTER_RO(d);
     if (!milliseconds) { bib_set_error("time_end: null argument"); return 0; }
     BIB_CHECK(cudaEventRecord(d->ev1, d->stream));
@@ -579,12 +699,14 @@ int bib_time_end(bib_domain* d, float* milliseconds) {
     return 1;
 }
 int bib_kernel_launch_count(bib_domain* d, long long* launches) {
+    if (d && d->is_head && launches) return group_launch_count(d, launches);
     BIB_ENTER_RO(d);
     if (!launches) { bib_set_error("kernel_launch_count: null argument"); return 0; }
     *launches = d->launches;
     return 1;
 }
 int bib_device_memory_bytes(bib_domain* d, long long* bytes) {
+    if (d && d->is_head && bytes) return group_memory_bytes(d, bytes);
     BIB_ENTER_RO(d);
     if (!bytes) { bib_set_error("device_memory_bytes: null argument"); return 0; }
     *bytes = d->bytes;

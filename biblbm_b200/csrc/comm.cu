@@ -96,8 +96,57 @@ void comm_destroy(bib_domain* d) {
 
 // Runs on the compute stream right after the push kernel: ghost plane nx+1 (populations with c_x=+1) goes to the right
 // neighbour's plane 1, ghost plane 0 (c_x=-1) to the left neighbour's plane nx.
+// In-process slab group: the same exchange as a PULL over peer memory. Order: (1) my ghost planes are written (event on st),
+// host barrier, (2) wait for the neighbours' events and copy their ghost planes into my boundary planes, (3) event "pulled",
+// host barrier, the neighbours' compute streams wait for it before they overwrite their ghost planes in the next step.
+static int local_halo_exchange(bib_domain* d, cudaStream_t st) {
+    bib_group* g = d->group;
+    double* f = d->f[d->cur];
+    const size_t n = d->plane;
+    const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+    const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    const bool has_left = d->per[0] || d->rank > 0;
+    const bool staged = !d->per[1] || !d->per[2];
+    if (staged && !d->halo_stage) {
+        BIB_CHECK(cudaMalloc(&d->halo_stage, 10 * n * sizeof(double)));
+        d->bytes += (long long)(10 * n * sizeof(double));
+    }
+    BIB_CHECK(cudaEventRecord(d->ev_h_ready, st));
+    group_barrier(g);
+    bib_domain* L = group_slab(g, left); bib_domain* R = group_slab(g, right);
+    const double* fl = L->f[L->cur]; const double* fr = R->f[R->cur];      // every slab flipped `cur` before the exchange
+    if (has_left) {
+        BIB_CHECK(cudaStreamWaitEvent(st, L->ev_h_ready, 0));
+        for (int k = 0; k < 5; ++k)
+            BIB_CHECK(cudaMemcpyPeerAsync(staged ? d->halo_stage + (size_t)k * n : f + (size_t)kPlusX[k] * d->vol + (size_t)1 * n, d->device,
+                                          fl + (size_t)kPlusX[k] * L->vol + (size_t)(L->nx + 1) * n, L->device, n * sizeof(double), st));
+    }
+    if (has_right) {
+        BIB_CHECK(cudaStreamWaitEvent(st, R->ev_h_ready, 0));
+        for (int k = 0; k < 5; ++k)
+            BIB_CHECK(cudaMemcpyPeerAsync(staged ? d->halo_stage + (size_t)(5 + k) * n : f + (size_t)kMinusX[k] * d->vol + (size_t)d->nx * n, d->device,
+                                          fr + (size_t)kMinusX[k] * R->vol + (size_t)0 * n, R->device, n * sizeof(double), st));
+    }
+    BIB_CHECK(cudaEventRecord(d->ev_h_done, st));
+    d->launches++;
+    group_barrier(g);
+    // my ghost planes may be overwritten (next step's boundary launch on the compute stream) only after the neighbours pulled them
+    if (has_left) BIB_CHECK(cudaStreamWaitEvent(d->stream, L->ev_h_done, 0));
+    if (has_right) BIB_CHECK(cudaStreamWaitEvent(d->stream, R->ev_h_done, 0));
+    if (staged) {
+        const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+        for (int k = 0; k < 5; ++k) {
+            if (has_left) { k_halo_merge<<<grid, 256, 0, st>>>(f + (size_t)kPlusX[k] * d->vol + (size_t)1 * n, d->halo_stage + (size_t)k * n, d->ny, d->nz, kCy[kPlusX[k]], kCz[kPlusX[k]], d->per[1], d->per[2]); d->launches++; }
+            if (has_right) { k_halo_merge<<<grid, 256, 0, st>>>(f + (size_t)kMinusX[k] * d->vol + (size_t)d->nx * n, d->halo_stage + (size_t)(5 + k) * n, d->ny, d->nz, kCy[kMinusX[k]], kCz[kMinusX[k]], d->per[1], d->per[2]); d->launches++; }
+        }
+        BIB_CHECK(cudaGetLastError());
+    }
+    return 1;
+}
+
 int comm_halo_exchange(bib_domain* d, cudaStream_t st) {
     if (d->n_ranks == 1) return 1;
+    if (d->group) return local_halo_exchange(d, st);
     ncclComm_t comm = (ncclComm_t)d->nccl_comm;
     if (!comm) { bib_set_error("halo exchange: bib_comm_init has not been called"); return 0; }
     double* f = d->f[d->cur];           // the buffer just written
@@ -136,6 +185,30 @@ int comm_halo_exchange(bib_domain* d, cudaStream_t st) {
 
 // Symmetric neighbour exchange of two fixed-size buffers (used by the multi-slab immersed-boundary protocol).
 int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles) {
+    if (d->group) {                       // in-process slab group: pull the neighbours' send buffers over peer memory
+        bib_group* g = d->group;
+        const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+        const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+        const bool has_left = d->per[0] || d->rank > 0;
+        d->x_send[0] = send_left; d->x_send[1] = send_right;
+        BIB_CHECK(cudaEventRecord(d->ev_x_ready, d->stream));
+        group_barrier(g);
+        bib_domain* L = group_slab(g, left); bib_domain* R = group_slab(g, right);
+        if (has_left) {
+            BIB_CHECK(cudaStreamWaitEvent(d->stream, L->ev_x_ready, 0));
+            BIB_CHECK(cudaMemcpyPeerAsync(recv_left, d->device, L->x_send[1], L->device, n_doubles * sizeof(double), d->stream));
+        } else BIB_CHECK(cudaMemsetAsync(recv_left, 0, sizeof(double), d->stream));
+        if (has_right) {
+            BIB_CHECK(cudaStreamWaitEvent(d->stream, R->ev_x_ready, 0));
+            BIB_CHECK(cudaMemcpyPeerAsync(recv_right, d->device, R->x_send[0], R->device, n_doubles * sizeof(double), d->stream));
+        } else BIB_CHECK(cudaMemsetAsync(recv_right, 0, sizeof(double), d->stream));
+        BIB_CHECK(cudaEventRecord(d->ev_x_done, d->stream));
+        d->launches++;
+        group_barrier(g);
+        if (has_left) BIB_CHECK(cudaStreamWaitEvent(d->stream, L->ev_x_done, 0));      // my send buffers are free again once both neighbours pulled them
+        if (has_right) BIB_CHECK(cudaStreamWaitEvent(d->stream, R->ev_x_done, 0));
+        return 1;
+    }
     ncclComm_t comm = (ncclComm_t)d->nccl_comm;
     if (!comm) { bib_set_error("exchange: bib_comm_init has not been called"); return 0; }
     const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;

@@ -52,18 +52,17 @@ struct ParticleGroup {            // particles of one (type, shape, params) adde
 // particles that reach into its slab. Per step three fixed-capacity neighbour exchanges keyed by global particle id:
 // positions (owner -> ghost holders, carries ownership hand-off), partial interpolated velocities (ghost holder -> owner,
 // summed there) and vertex forces (owner -> ghost holders, each slab spreads into its own cells only).
-struct MultiSlabIB {
+struct MultiSlabIB {                        // one per particle group of a multi-slab domain
     int nv = 0, cap = 0, n_global = 0, xcap = 0;
+    int first_slot = 0;                    // the group's slots are [first_slot, first_slot + cap) of the domain-wide slot arrays
+    long long first_vertex = 0;            // slot s holds vertices [first_vertex + (s - first_slot) * nv, + nv)
+    int gid_base = 0;                      // global particle id of the group's particle 0 (ids are global over all groups, in order of addition)
     size_t entry = 0;                      // doubles per exchanged particle: gid, flag, 3*nv payload
-    int* role = nullptr;                   // [cap] 0 dead, 1 owned, 2 ghost (owner = left neighbour), 3 ghost (owner = right)
-    int* gid_of = nullptr;                 // [cap]
-    int* slot_of = nullptr;                // [n_global] -1 when not resident
+    int* slot_of = nullptr;                // [n_global] -1 when not resident (slot index is domain-wide)
     int* free_stack = nullptr;             // [cap]
     int* counters = nullptr;               // [0] free_top, [1] overflow flag
-    uint8_t* seen = nullptr;               // [cap]
     double* send[2] = {nullptr, nullptr};  // [1 + xcap*entry]; element 0 holds the entry count (uint64)
     double* recv[2] = {nullptr, nullptr};
-    bool ghosts_dirty = true;
 };
 
 struct PotentialDev { int type = 0; double r_min = 0, beta = 0, strength = 0; };   // fsi/Potentials.h: 1 Morse, 2 spring
@@ -71,6 +70,7 @@ struct PotentialDev { int type = 0; double r_min = 0, beta = 0, strength = 0; };
 struct WallPlane {                 // one velocity boundary plane (VelocityDirichlet + PlaneFd)
     int dir = 1, orient = -1, coord = 0;
     int na = 0, nb = 0;            // size of the whole lattice face along the two in-plane axes (x,y,z order)
+    int gx = 0;                    // multi-slab: ghost columns on either side along x (the stored velocities of the neighbouring slabs' wall cells); rows = na + 2 gx
     int a0 = 0, a1 = -1, b0 = 0, b1 = -1;   // the cells of the face this boundary covers (extensional_flow_setup.h: planes stop short of the edges)
     double* vel = nullptr;         // device [na][nb][3] stored boundary velocities of the WHOLE face (edge cells included: in-plane neighbours)
     std::vector<double> h_vel;     // host mirror
@@ -87,7 +87,7 @@ struct WallEdge {                  // one external velocity edge (StoreVelocityD
 // one captured driver step and the host-side state it starts from
 struct StepGraph {
     cudaGraphExec_t exec = nullptr;
-    int cur = 0, band_cur = 0; const double* vfrc = nullptr; bool forces_ready = false;
+    int cur = 0, band_cur = 0, spread_band = -1; const double* vfrc = nullptr; bool forces_ready = false;
     long long launches = 0;
 };
 
@@ -98,11 +98,21 @@ struct ResSlot {
     cudaEvent_t packed = nullptr, copied = nullptr;
     double* host_v = nullptr; double* host_s = nullptr;
     int* count_host = nullptr;            // page-locked: number of owned particles (multi-slab)
-    bool compact = false; int bound_used = 0;
+    bool compact = false; int bound_used = 0; long long bound_used_v = 0;
 };
+
+// Several slabs owned by ONE host process (bib_domain_create_multi): the slabs are stepped by one worker thread each, SPMD like the
+// ranks of a multi-process run, and the neighbour exchanges use peer memory (cudaMemcpyPeer / kernels reading the neighbour's
+// buffers over NVLink) ordered by CUDA events + a host barrier instead of NCCL. Defined in group.cu.
+struct bib_group;
 
 struct bib_domain {
     int device = 0;
+    bib_group* group = nullptr;           // non-null: slab `rank` of an in-process slab group (n_ranks slabs)
+    bool is_head = false;                 // the handle bib_domain_create_multi returned: every entry point dispatches to the group's slabs
+    cudaEvent_t ev_x_ready = nullptr, ev_x_done = nullptr;      // in-process exchanges: my buffers are packed / I have pulled my neighbours' buffers
+    cudaEvent_t ev_h_ready = nullptr, ev_h_done = nullptr;      // same for the population halo (runs on the communication stream)
+    const double* x_send[2] = {nullptr, nullptr};               // buffers published for the neighbours of the exchange in flight
     int nx = 0, ny = 0, nz = 0;           // slab size (without ghost planes)
     int per[3] = {0, 0, 0};               // global periodicity
     double omega0 = 1, omega1 = 1;        // outer, inner (omega1 == 0: single relaxation rate, see n_ext)
@@ -124,7 +134,11 @@ struct bib_domain {
     unsigned* fflag = nullptr;            // 1 bit per cell (storage index): 0 => force == force_body exactly; only meaningful while fflag_valid && force_is_body
     bool fflag_valid = false;
     int sparse_force = 1;                 // BIB_OPT_SPARSE_FORCE
-    bool interp_since_spread = false;     // the band masks of the last spread are in buffer 1 - band_cur (ib_interpolate ran since)
+    // Which mask buffer describes the cells the last NOT YET RESET spread wrote: 0 / 1 = that buffer (the masks ib_interpolate took at
+    // the positions the spread used); -1 = nothing to reset (no spread since the force field was last set); -2 = unknown (a spread
+    // without matching masks, or two spreads since the last reset) -> the next reset runs over the whole lattice.
+    int spread_band = -1;
+    bool band_pos_valid = false;          // the masks in buffer band_cur were taken at the CURRENT vertex positions
     double force_body[3] = {0, 0, 0};
     uint8_t* col_flags = nullptr;         // [nx+2][ny] voxelizer per-column flags
     cudaStream_t stream = nullptr;
@@ -184,8 +198,18 @@ struct bib_domain {
     int res_head = 0, res_tail = 0, res_n = 0;
     int* res_list = nullptr;              // per slot [1 + cap]: number and slot indices of the owned particles (multi-slab read-back)
     int res_bound = 0;                    // particles covered by the asynchronous prefix copy (last count + slack)
+    long long res_bound_v = 0; int res_list_cap = 0;
     int res_last_count = -1;              // particles delivered by the last completed read-back
-    MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles
+    // multi-slab domains: domain-wide slot arrays (one slot per resident particle, owned or ghost) + one exchange context per particle group
+    MultiSlabIB* ms = nullptr;       // non-null on multi-slab domains with particles (= msv[0])
+    std::vector<MultiSlabIB*> msv;   // per particle group (same index as groups[])
+    int* role_all = nullptr;         // [cap_particles] 0 dead, 1 owned, 2 ghost (owner = left neighbour), 3 ghost (owner = right)
+    int* gid_all = nullptr;          // [cap_particles] global particle id of the slot
+    uint8_t* seen_all = nullptr;     // [2][cap_particles] refreshed-by-this-exchange marks, owner snapshot
+    int* vslot = nullptr;            // [cap_vertices] slot of each vertex
+    int* slot_nv = nullptr;          // [cap_particles] vertices per slot
+    long long* slot_fv = nullptr;    // [cap_particles] first vertex of the slot
+    bool ghosts_dirty = true;        // ghost copies do not reflect the owners' positions (particles added / uploaded): POS exchange before the next use
 };
 
 void bib_set_error(const std::string& msg);
@@ -221,6 +245,7 @@ int ib_results_count(bib_domain* d, int* n);
 int ib_forces_preload(bib_domain* d, long long first, long long count, const double* f3);
 int ib_interpolate(bib_domain* d);
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz);
+int ib_set_kernel_attributes();     // per device: opt-in dynamic shared memory sizes (called by bib_domain_create after cudaSetDevice)
 int ib_forces_and_spread(bib_domain* d);
 int ib_forces(bib_domain* d, cudaStream_t st);
 int ib_spread(bib_domain* d);
@@ -240,6 +265,11 @@ int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);
 int comm_halo_exchange(bib_domain* d, cudaStream_t st);
 void comm_destroy(bib_domain* d);
 int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles);
+// in-process slab groups (group.cu)
+bib_domain* group_slab(bib_group* g, int rank);
+void group_barrier(bib_group* g);
+bool group_same_device(bib_group* g);
+inline bool bib_multi(const bib_domain* d) { return d->n_ranks > 1; }
 int ib_local_slots(bib_domain* d, int* gids, int* roles, int capacity, int* n_slots);
 
 // ---- device helpers shared by the LBM and IB kernels

@@ -36,7 +36,7 @@ struct Geo {
     int x_offset;            // global x of storage plane 1
     int nxl;                 // planes owned by this slab (== nx on a single slab)
     const int* role;         // per particle slot: 0 dead, 1 owned, 2/3 ghost of the left/right neighbour; NULL = all owned
-    int nv_slot;             // vertices per slot when role != NULL
+    const int* vslot;        // slot of each vertex (used when role != NULL)
     const uint8_t* kind;     // cell kinds (NULL = all bulk)
     unsigned* fflag;         // force-differs-from-body flags (1 bit per cell), set by every atomic spread write; NULL = not maintained
     int plates;              // fsi::Boundary kind: 0 none, 1 ParallelPlatesBoundary (walls at y = py0, py1; src/fsi/Boundary.h:300-365),
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
                                                      const double* __restrict__ vpos, double* __restrict__ vvel) {
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= nvert) return;
-    if (g.role && g.role[v / g.nv_slot] == 0) return;
+    if (g.role && g.role[g.vslot[v]] == 0) return;
     const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     double o[3] = {0.0, 0.0, 0.0};
     int cls = d_classify(g, pp);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) k_spread_atomic(Geo g, double* force, lon
                                                        const double* __restrict__ vpos, const double* __restrict__ vfrc) {
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= nvert) return;
-    if (g.role && g.role[v / g.nv_slot] == 0) return;
+    if (g.role && g.role[g.vslot[v]] == 0) return;
     const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
     const int cls = d_classify(g, pp);
@@ -346,7 +346,7 @@ __global__ void k_spread_sequential(Geo g, double* force, long long nvert, long 
         for (long long v = 0; v < nvert; ++v) {
             const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
             const double F[3] = {vfrc[v], vfrc[cap + v], vfrc[2 * cap + v]};
-            if (g.role && g.role[v / g.nv_slot] == 0) continue;
+            if (g.role && g.role[g.vslot[v]] == 0) continue;
             if (d_classify(g, pp) == pass) d_spread_vertex(g, force, pp, F, pass, false);
         }
 }
@@ -969,7 +969,13 @@ __global__ void __launch_bounds__(256) k_wall_interaction(Geo g, PotentialDev po
 // paired with the vertex's cell, including what the reference leaves out -- only the 7 neighbours with non-negative
 // offsets are visited from a bulk cell (so a pair is seen iff its cell offset is one of those 7 or their negatives), and
 // periodic images are only paired between directly opposite boundary cells.
-struct PPGrid { int nc[3]; double g0[3], cs[3], lo[3], hi[3]; int per[3]; double L[3]; };
+struct PPGrid {
+    int nc[3]; double g0[3], cs[3], lo[3], hi[3]; int per[3]; double L[3];
+    // multi-slab: dead slots are not binned; a slab evaluates the vertices that lie in ITS x-range [x_lo, x_hi) (positions clamped into
+    // the lattice), whoever owns them -- every partner within the cut-off is resident there -- and ghost holders return their part to the owner
+    const int* role; const int* vslot; double x_lo, x_hi, x_min, x_max;
+};
+__device__ __forceinline__ bool d_pp_live(const PPGrid& G, long long v) { return !G.role || G.role[G.vslot[v]] != 0; }
 __device__ __forceinline__ bool d_pp_cell(const PPGrid& G, const double* p, int* c) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -983,7 +989,7 @@ __global__ void __launch_bounds__(256) k_pp_build(PPGrid G, long long nvert, lon
     if (v >= nvert) return;
     const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     int c[3];
-    if (!d_pp_cell(G, p, c)) { next[v] = -2; return; }
+    if (!d_pp_live(G, v) || !d_pp_cell(G, p, c)) { next[v] = -2; return; }
     const long long cell = (long long)c[2] + (long long)G.nc[2] * ((long long)c[1] + (long long)G.nc[1] * c[0]);
     next[v] = atomicExch(&head[cell], (int)v);
 }
@@ -992,7 +998,7 @@ __global__ void __launch_bounds__(256) k_pp_clear(PPGrid G, long long nvert, lon
     if (v >= nvert) return;
     const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
     int c[3];
-    if (!d_pp_cell(G, p, c)) return;
+    if (!d_pp_live(G, v) || !d_pp_cell(G, p, c)) return;
     head[(long long)c[2] + (long long)G.nc[2] * ((long long)c[1] + (long long)G.nc[1] * c[0])] = -1;
 }
 __device__ __forceinline__ void d_pp_cell_sum(const PPGrid& G, const PotentialDev& pot, double cut_sqr, const int* __restrict__ head, const int* __restrict__ next,
@@ -1018,6 +1024,7 @@ __global__ void __launch_bounds__(128) k_pp_forces(PPGrid G, PotentialDev pot, l
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= nvert || next[v] == -2) return;
     const double p[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    if (G.role) { const double xc = fmin(fmax(p[0], G.x_min), G.x_max); if (!(xc >= G.x_lo && xc < G.x_hi)) return; }
     int c[3];
     d_pp_cell(G, p, c);
     const int obj = vobj[v];
@@ -1059,6 +1066,13 @@ __global__ void __launch_bounds__(128) k_pp_forces(PPGrid G, PotentialDev pot, l
         }
     }
     vfrc[v] += f[0]; vfrc[cap + v] += f[1]; vfrc[2 * cap + v] += f[2];
+}
+// multi-slab: the vertex forces of ghost copies start from zero before the pair forces are gathered (they only carry the partial pair
+// force of the vertices inside this slab back to the owner)
+__global__ void k_zero_ghost_forces(const int* __restrict__ role, const int* __restrict__ vslot, long long nvert, long long cap, double* __restrict__ vfrc) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvert || role[vslot[v]] == 1) return;
+    vfrc[v] = 0.0; vfrc[cap + v] = 0.0; vfrc[2 * cap + v] = 0.0;
 }
 __global__ void k_fill_vobj(int* vobj, long long first_vertex, int nv, int first_particle, long long n) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1180,11 +1194,11 @@ __device__ __forceinline__ void d_toggle_mark(uint8_t* phase, long long idx) {
 // One thread per (particle, triangle): Moeller-Trumbore against the +z rays through the integer (x,y) of the triangle's
 // bounding box (RayTracer.hh:19-39,80-108). A hit at height h toggles the mark bit of cell ceil(h) in column (x,y).
 __global__ void __launch_bounds__(128) k_raycast(Geo g, int nv, int nt, const int* __restrict__ tris, long long first_vertex, long long cap,
-                                                 int count, const double* __restrict__ vpos, uint8_t* phase, uint8_t* col_flags) {
+                                                 int count, int first_particle, const double* __restrict__ vpos, uint8_t* phase, uint8_t* col_flags) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= (long long)count * nt) return;
     const int pl = (int)(t / nt), tr = (int)(t % nt);
-    if (g.role && g.role[pl] == 0) return;
+    if (g.role && g.role[first_particle + pl] == 0) return;
     const long long base = first_vertex + (long long)pl * nv;
     const V3 p0 = ld3(vpos, cap, base + tris[3 * tr]), p1 = ld3(vpos, cap, base + tris[3 * tr + 1]), p2 = ld3(vpos, cap, base + tris[3 * tr + 2]);
     const int iXmin = (int)ceil(fmin(p0.x, fmin(p1.x, p2.x))), iXmax = (int)floor(fmax(p0.x, fmax(p1.x, p2.x)));
@@ -1495,7 +1509,7 @@ Geo make_geo(const bib_domain* d) {
     g.nx = d->gnx; g.ny = d->ny; g.nz = d->nz;
     g.per[0] = d->per[0]; g.per[1] = d->per[1]; g.per[2] = d->per[2];
     g.plane = (long long)d->plane; g.vol = (long long)d->vol; g.x_offset = d->x_offset;
-    g.nxl = d->nx; g.role = d->ms ? d->ms->role : nullptr; g.nv_slot = d->ms ? d->ms->nv : 1;
+    g.nxl = d->nx; g.role = d->ms ? d->role_all : nullptr; g.vslot = d->vslot;
     g.plates = d->plates; g.py0 = d->plate_y0; g.py1 = d->plate_y1; g.prad = d->pipe_radius; g.kind = d->kind;
     g.fflag = (d->sparse_force && d->fflag_valid && !d->deterministic_spread) ? d->fflag : nullptr;
     return g;
@@ -1653,6 +1667,13 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
         }
         BIB_CHECK(cudaStreamSynchronize(d->stream));
         for (int k = 0; k < 3; ++k) { if (*old[k]) cudaFree(*old[k]); *old[k] = np[k]; }
+        if (d->n_ranks > 1) {
+            int* nvs;
+            BIB_CHECK(cudaMalloc(&nvs, (size_t)cap * sizeof(int)));
+            BIB_CHECK(cudaMemset(nvs, 0, (size_t)cap * sizeof(int)));
+            if (d->vslot) { BIB_CHECK(cudaMemcpy(nvs, d->vslot, (size_t)d->n_vertices * sizeof(int), cudaMemcpyDeviceToDevice)); cudaFree(d->vslot); }
+            d->vslot = nvs;
+        }
         d->bytes += (cap - d->cap_vertices) * 9 * 8;
         d->cap_vertices = cap;
     }
@@ -1664,6 +1685,20 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
         if (d->pstate) BIB_CHECK(cudaMemcpyAsync(ns, d->pstate, (size_t)d->n_particles * 11 * sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
         BIB_CHECK(cudaStreamSynchronize(d->stream));
         if (d->pstate) cudaFree(d->pstate);
+        if (d->n_ranks > 1) {          // multi-slab slot tables
+            int *nr, *ng, *nn; long long* nf; uint8_t* nsn;
+            BIB_CHECK(cudaMalloc(&nr, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMalloc(&ng, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMalloc(&nn, (size_t)cap * sizeof(int)));
+            BIB_CHECK(cudaMalloc(&nf, (size_t)cap * sizeof(long long))); BIB_CHECK(cudaMalloc(&nsn, 2 * (size_t)cap));
+            BIB_CHECK(cudaMemset(nr, 0, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMemset(ng, 0xff, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMemset(nn, 0, (size_t)cap * sizeof(int)));
+            BIB_CHECK(cudaMemset(nf, 0, (size_t)cap * sizeof(long long))); BIB_CHECK(cudaMemset(nsn, 0, 2 * (size_t)cap));
+            if (d->role_all) {
+                const size_t n = (size_t)d->n_particles;
+                BIB_CHECK(cudaMemcpy(nr, d->role_all, n * sizeof(int), cudaMemcpyDeviceToDevice)); BIB_CHECK(cudaMemcpy(ng, d->gid_all, n * sizeof(int), cudaMemcpyDeviceToDevice));
+                BIB_CHECK(cudaMemcpy(nn, d->slot_nv, n * sizeof(int), cudaMemcpyDeviceToDevice)); BIB_CHECK(cudaMemcpy(nf, d->slot_fv, n * sizeof(long long), cudaMemcpyDeviceToDevice));
+                cudaFree(d->role_all); cudaFree(d->gid_all); cudaFree(d->slot_nv); cudaFree(d->slot_fv); cudaFree(d->seen_all);
+            }
+            d->role_all = nr; d->gid_all = ng; d->slot_nv = nn; d->slot_fv = nf; d->seen_all = nsn;
+        }
         d->pstate = ns; d->cap_particles = cap;
     }
     return 1;
@@ -1671,12 +1706,13 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
 
 static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move, const uint8_t* skip_mask = nullptr) {
     const ShapeDev& s = d->shapes[gr.shape];
+    if (do_move) d->band_pos_valid = false;      // the band masks were taken at the positions before this move
     if (gr.type == 3) {
         RigidParams c;
         c.nv = s.nv; c.nt = s.nt; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
         c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
         for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
-        c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = 0;
+        c.shape_volume = gr.shape_volume; c.role = d->ms ? d->role_all : nullptr; c.f_init = 0;
         k_rigid_move<<<gr.count, 256, 0, d->stream>>>(make_geo(d), c, d->vpos, d->vfrc, d->pstate, do_move);
         d->launches++;
         BIB_CHECK(cudaGetLastError());
@@ -1689,23 +1725,24 @@ static int launch_update(bib_domain* d, const ParticleGroup& gr, int do_move, co
     return 1;
 }
 
-int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint);
-int ms_set_initial(bib_domain* d, const std::vector<int>& owned_gids);
+int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint, int first_slot, long long first_vertex, int gid_base, MultiSlabIB** out);
+int ms_set_initial(bib_domain* d, MultiSlabIB* m, const std::vector<int>& owned_lids);
 int ms_exchange_positions(bib_domain* d);
 int ms_exchange_velocities(bib_domain* d);
 int ms_exchange_forces(bib_domain* d);
+int ms_exchange_pair_forces(bib_domain* d);
 
 // update (and optionally advect) every live particle slot; skip_mask[slot] != 0 leaves a slot alone
 int ib_update_all(bib_domain* d, int do_move) {
-    const uint8_t* skip = (d->ms && do_move == 0) ? d->ms->seen + d->ms->cap : nullptr;   // POS exchange: owners keep their cached scalars
+    const uint8_t* skip = (d->ms && do_move == 0) ? d->seen_all + d->cap_particles : nullptr;   // POS exchange: owners keep their cached scalars
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, do_move, skip)) return 0;
     return 1;
 }
 
 // Multi-slab domains: every rank is given the same global particle list (like the reference's add_particle, which keeps
 // only what it owns, src/fsi/ImmersedBoundaryDynamics.hh:500-525); ownership = slab containing the centre of mass.
+// Every call adds one particle group with its own slot range and exchange context; global particle ids continue across groups.
 static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, const double* params, int n, const double* positions) {
-    if (!d->groups.empty()) { bib_set_error("particles_add: multi-slab domains take one particle group (one call)"); return 0; }
     const ShapeDev& s = d->shapes[shape_id];
     // centre of mass exactly as DeformableParticle3D::update computes it (sequential, area weighted), then the periodic remap
     std::vector<int> owned;
@@ -1728,34 +1765,43 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
         if (d->per[0]) { const double L = (double)d->gnx; x = x - L * std::floor((x - (0.0 - 0.5)) * (1. / L)); }
         if (x >= (double)d->x_offset - 0.5 && x < (double)(d->x_offset + d->nx) - 0.5) owned.push_back(p);
     }
+    if (max_extent + 6.0 >= (double)d->nx) { bib_set_error("particles_add: the slab width must exceed the particle extent + 6 cells (a particle may only reach the two neighbouring slabs)"); return 0; }
     // slot / exchange capacities from the geometry: a particle is mirrored on a neighbour while its box (+3 cells) reaches over the
     // face, i.e. a fraction (extent + 6) / slab width of the owned ones per side; generous safety factors, overflow is detected
     const double frac = std::min(1.0, (max_extent + 8.0) / (double)d->nx);
-    // (the exchange capacity fixes the NCCL message size, so it must come out identical on every rank: global quantities only)
+    // (the exchange capacity fixes the message size, so it must come out identical on every rank: global quantities only)
     const double base = 1.25 * (double)n / d->n_ranks;
     const int xcap_hint = (int)(base * frac * 2.0) + 32;
     const int cap_hint = std::max((int)(base * (1.0 + 2.0 * frac) * 1.3) + 64, (int)owned.size() + 2 * xcap_hint);
-    if (!ms_create(d, s.nv, n, cap_hint, xcap_hint)) return 0;
-    MultiSlabIB* m = d->ms;
-    if (!grow_particles(d, (long long)m->cap * s.nv, m->cap)) return 0;
+    int gid_base = 0;
+    for (MultiSlabIB* m : d->msv) if (m) gid_base += m->n_global;
+    MultiSlabIB* m = nullptr;
+    if (!ms_create(d, s.nv, n, cap_hint, xcap_hint, d->n_particles, d->n_vertices, gid_base, &m)) return 0;
     if ((int)owned.size() > m->cap) { bib_set_error("particles_add: more owned particles than slots"); return 0; }
+    if (!grow_particles(d, d->n_vertices + (long long)m->cap * s.nv, d->n_particles + m->cap)) return 0;
     const long long capv = d->cap_vertices;
     std::vector<double> soa((size_t)owned.size() * s.nv * 3);
     const size_t no = owned.size() * (size_t)s.nv;
     for (size_t k = 0; k < owned.size(); ++k) for (int v = 0; v < s.nv; ++v) for (int c = 0; c < 3; ++c)
         soa[(size_t)c * no + k * s.nv + v] = positions[((size_t)owned[k] * s.nv + v) * 3 + c];
     for (int c = 0; c < 3 && no > 0; ++c)
-        BIB_CHECK(cudaMemcpyAsync(d->vpos + (size_t)c * capv, soa.data() + (size_t)c * no, no * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        BIB_CHECK(cudaMemcpyAsync(d->vpos + (size_t)c * capv + m->first_vertex, soa.data() + (size_t)c * no, no * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->stream));
-    if (!ms_set_initial(d, owned)) return 0;
+    if (!ms_set_initial(d, m, owned)) return 0;
     ParticleGroup gr;
-    gr.type = type; gr.shape = shape_id; gr.first_particle = 0; gr.count = m->cap; gr.first_vertex = 0;
+    gr.type = type; gr.shape = shape_id; gr.first_particle = m->first_slot; gr.count = m->cap; gr.first_vertex = m->first_vertex;
     std::memcpy(gr.params, params, 8 * sizeof(double));
     std::vector<double> ks(s.nl), kp(s.nl);
     for (int l = 0; l < s.nl; ++l) rbc_ks_kp(s.h_link_len[l], params[0], ks[l], kp[l]);
     if (!to_device(&gr.link_ks, ks) || !to_device(&gr.link_kp, kp)) return 0;
     d->groups.push_back(gr);
-    d->n_particles = m->cap; d->n_vertices = (long long)m->cap * s.nv;
+    d->msv.push_back(m);
+    d->ms = d->msv[0];
+    d->n_particles += m->cap; d->n_vertices += (long long)m->cap * s.nv;
+    d->band_pos_valid = false;
+    const long long nvg = (long long)m->cap * s.nv;
+    k_fill_vobj<<<(unsigned)((nvg + 255) / 256), 256, 0, d->stream>>>(d->vslot, gr.first_vertex, s.nv, gr.first_particle, nvg);
+    d->launches++;
     return launch_update(d, gr, 0);
 }
 
@@ -1781,6 +1827,7 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     d->groups.push_back(gr);
     d->n_particles += n; d->n_vertices += nvtot;
+    d->band_pos_valid = false;
     // ParticleBase3D::update() at construction + add_particle's map_center_of_mass_to_periodic_grid (ImmersedBoundaryDynamics.hh:500-525)
     return launch_update(d, gr, 0);
 }
@@ -1879,10 +1926,11 @@ static int ensure_velocity_field(bib_domain* d) {
 int ib_interpolate(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
     if (!ensure_velocity_field(d)) return 0;
-    if (d->ms && d->ms->ghosts_dirty && !ms_exchange_positions(d)) return 0;
+    if (d->ms && d->ghosts_dirty && !ms_exchange_positions(d)) return 0;
     if (!d->vel_full_valid) {
         if (!ensure_band_masks(d)) return 0;
-        d->band_cur = 1 - d->band_cur;
+        // never overwrite the masks of a spread that has not been reset yet (ib_band_reset reads them)
+        d->band_cur = d->spread_band >= 0 ? 1 - d->spread_band : 1 - d->band_cur;
         unsigned* ms = d->band_mask + (size_t)d->band_cur * d->band_cap * BAND_WORDS;
         int* bs = d->band_box + (size_t)d->band_cur * d->band_cap * 6;
         for (const ParticleGroup& gr : d->groups) {
@@ -1892,11 +1940,11 @@ int ib_interpolate(bib_domain* d) {
             d->launches++;
         }
         d->band_valid[d->band_cur] = true;
+        d->band_pos_valid = true;
         if (!lbm_wall_velocity_fill(d)) return 0;      // wall cells report their stored boundary velocity
     } else {
-        d->band_valid[0] = d->band_valid[1] = false;
+        d->band_pos_valid = false;                     // the caller's full velocity field is used: no masks were taken at these positions
     }
-    d->interp_since_spread = true;
     const int bs = 128;
     const unsigned grid = (unsigned)((d->n_vertices + bs - 1) / bs);
     k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
@@ -1908,15 +1956,19 @@ int ib_interpolate(bib_domain* d) {
 
 // F := body inside the particles' bands (everywhere else the force already equals the body force)
 int ib_band_reset(bib_domain* d, double fx, double fy, double fz) {
-    if (d->n_particles == 0) return 1;
-    // the masks of the previous step's interpolation (taken at the positions its spread used) are in buffer 1 - band_cur
-    const int prev = 1 - d->band_cur;
-    const bool use_masks = d->band_mask && d->band_valid[prev];
+    if (d->n_particles == 0 || d->spread_band == -1) return 1;        // no spread has written since the force field was last set
+    // the masks ib_interpolate took at the positions the last spread used are in buffer spread_band (recorded by ib_spread; any
+    // number of interpolations may have run since, they write the other buffer). Unknown -> the whole lattice.
+    const int prev = d->spread_band;
+    if (prev < 0 || !d->band_mask || !d->band_valid[prev] || d->band_cap < d->n_particles) {
+        const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
+        return lbm_launch_set_external(d, box, fx, fy, fz);
+    }
     k_band_reset<<<d->n_particles, 256, 0, d->stream>>>(make_geo(d), d->force, d->pstate, fx, fy, fz,
-                                                      use_masks ? d->band_mask + (size_t)prev * d->band_cap * BAND_WORDS : d->band_mask,
-                                                      use_masks ? d->band_box + (size_t)prev * d->band_cap * 6 : nullptr);
+                                                      d->band_mask + (size_t)prev * d->band_cap * BAND_WORDS, d->band_box + (size_t)prev * d->band_cap * 6);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
+    d->spread_band = -1;
     return 1;
 }
 
@@ -1933,10 +1985,12 @@ static PPGrid make_pp_grid(const bib_domain* d) {
         G.lo[k] = dom0 - d->pp_pot.r_min; G.hi[k] = dom1 + d->pp_pot.r_min;
         G.per[k] = d->per[k]; G.L[k] = (double)n[k];
     }
+    G.role = d->ms ? d->role_all : nullptr; G.vslot = d->vslot;
+    G.x_lo = (double)d->x_offset - 0.5; G.x_hi = (double)(d->x_offset + d->nx) - 0.5;
+    G.x_min = -0.5; G.x_max = std::nextafter((double)d->gnx - 0.5, 0.0);
     return G;
 }
 static int ib_pp_forces(bib_domain* d, cudaStream_t st) {
-    if (d->n_ranks > 1) { bib_set_error("particle-particle interaction forces: single-slab domains only (round 1)"); return 0; }
     if (d->pp_pot.r_min > 1.0) { bib_set_error("The interaction distance cannot be greater than the lattice spacing (1)"); return 0; }   // _forces.hh:347-350
     const PPGrid G = make_pp_grid(d);
     const size_t ncell = (size_t)G.nc[0] * G.nc[1] * G.nc[2];
@@ -1951,6 +2005,10 @@ static int ib_pp_forces(bib_domain* d, cudaStream_t st) {
         BIB_CHECK(cudaMalloc(&d->pp_next, (size_t)d->cap_vertices * sizeof(int)));
         BIB_CHECK(cudaMalloc(&d->pp_vobj, (size_t)d->cap_vertices * sizeof(int)));
         d->pp_cap = d->cap_vertices; d->pp_groups = 0;
+    }
+    if (d->ms) {          // ghost copies carry only their partial pair force
+        k_zero_ghost_forces<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, st>>>(d->role_all, d->vslot, d->n_vertices, d->cap_vertices, d->vfrc);
+        d->launches++;
     }
     if (d->pp_groups != (int)d->groups.size()) {
         for (const ParticleGroup& gr : d->groups) {
@@ -1967,6 +2025,7 @@ static int ib_pp_forces(bib_domain* d, cudaStream_t st) {
     k_pp_clear<<<grid, 256, 0, st>>>(G, d->n_vertices, d->cap_vertices, d->vpos, d->pp_head);
     d->launches += 3;
     BIB_CHECK(cudaGetLastError());
+    if (d->ms && !ms_exchange_pair_forces(d)) return 0;      // ghost holders -> owner (added there): src/fsi/ImmersedBoundaryDynamics_forces.hh:378-456
     return 1;
 }
 
@@ -1981,7 +2040,6 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
     const bool init = wall || d->vfrc_preloaded;       // vfrc already holds the decorators' contribution
     d->vfrc_preloaded = false;
     if (wall) {
-        if (d->n_ranks > 1) { bib_set_error("wall interaction forces: single-slab domains only (round 1)"); return 0; }
         k_wall_interaction<<<(unsigned)((d->n_vertices + 255) / 256), 256, 0, st>>>(wg, d->wall_pot, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
         d->launches++;
     }
@@ -1992,7 +2050,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             c.nv = s.nv; c.nt = s.nt; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
             c.tris = s.tris; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri; c.rest = s.verts; c.rigid = gr.rigid;
             for (int k = 0; k < 9; ++k) c.inertia[k] = gr.inertia[k];
-            c.shape_volume = gr.shape_volume; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
+            c.shape_volume = gr.shape_volume; c.role = d->ms ? d->role_all : nullptr; c.f_init = init ? 1 : 0;
             k_rigid_forces<<<gr.count, 256, 0, st>>>(c, d->vpos, d->vvel, d->vfrc);
             d->launches++;
             continue;
@@ -2001,7 +2059,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             SemiParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle;
             c.links = s.links; c.link_len = s.link_len; c.v_link_off = s.v_link_off; c.v_link = s.v_link; c.rest_radial = s.rest_radial;
-            c.k_in = gr.params[1]; c.k_out = gr.params[2]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
+            c.k_in = gr.params[1]; c.k_out = gr.params[2]; c.role = d->ms ? d->role_all : nullptr; c.f_init = init ? 1 : 0;
             const size_t smem = (size_t)s.nv * 6 * sizeof(double);
             if (smem > 200 * 1024) { bib_set_error("semi-rigid particles: mesh too large for the shared-memory kernel"); return 0; }
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_semirigid_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2013,7 +2071,7 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
             CapParams c;
             c.nv = s.nv; c.first_vertex = gr.first_vertex; c.cap = d->cap_vertices; c.first_particle = gr.first_particle; c.count = gr.count;
             c.tris = s.tris; c.tri_area = s.tri_area; c.rest = s.verts; c.v_tri_off = s.v_tri_off; c.v_tri = s.v_tri;
-            c.G = gr.params[0]; c.role = d->ms ? d->ms->role : nullptr; c.f_init = init ? 1 : 0;
+            c.G = gr.params[0]; c.role = d->ms ? d->role_all : nullptr; c.f_init = init ? 1 : 0;
             const size_t smem = (size_t)s.nv * 3 * sizeof(double);
             c.use_smem = smem <= 200 * 1024;
             if (c.use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_capsule_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2028,14 +2086,13 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
         q.v_link_off = s.v_link_off; q.v_link = s.v_link; q.v_tri_off = s.v_tri_off; q.v_tri = s.v_tri; q.v_pair_off = s.v_pair_off; q.v_pair = s.v_pair;
         q.shape_area = s.area; q.k_ag = gr.params[2]; q.k_al = gr.params[3]; q.k_v = gr.params[4]; q.vol_desired = gr.params[5]; q.k_b = gr.params[6];
         q.reg_p = d->regulator_p; for (int k = 0; k < 3; ++k) q.reg_t[k] = d->regulator_target[k];
-        q.role = d->ms ? d->ms->role : nullptr;
+        q.role = d->ms ? d->role_all : nullptr;
         q.f_init = init ? d->vfrc : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
         if (s.nv <= RF_THREADS * RF_VPT_MAX) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
             const int vpt = (s.nv + RF_THREADS - 1) / RF_THREADS;        // vertices per thread (measured: 3 instead of 4 for the 626-vertex RBC = -0.05 ms)
-#define BIB_RF_LAUNCH(V) do { static size_t set_ = 0; if (set_ != sm2) { cudaFuncSetAttribute(k_rbc_forces_elem<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); set_ = sm2; } \
-                              k_rbc_forces_elem<V><<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np); } while (0)
+#define BIB_RF_LAUNCH(V) k_rbc_forces_elem<V><<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np)      /* shared-memory opt-in: ib_set_kernel_attributes */
             if (vpt <= 1) BIB_RF_LAUNCH(1); else if (vpt == 2) BIB_RF_LAUNCH(2); else if (vpt == 3) BIB_RF_LAUNCH(3); else BIB_RF_LAUNCH(4);
 #undef BIB_RF_LAUNCH
         } else if (smem <= 200 * 1024) {
@@ -2062,15 +2119,14 @@ bool ib_forces_independent_of_interpolation(const bib_domain* d) {
 
 int ib_spread(bib_domain* d) {
     if (d->n_vertices == 0) return 1;
-    d->interp_since_spread = false;
+    // remember which masks describe the cells written now; a second spread before any reset, or one without masks of the current positions: unknown
+    d->spread_band = (d->spread_band == -1 && d->band_pos_valid && d->band_mask && d->band_valid[d->band_cur]) ? d->band_cur : -2;
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
     if (d->deterministic_spread) d->fflag_valid = false;
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
     else {
         const size_t smem = (size_t)TILE_CELLS * 3 * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k_spread_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
         for (const ParticleGroup& gr : d->groups) {
             k_spread_tile<<<gr.count, 256, smem, d->stream>>>(make_geo(d), d->force, d->pstate, d->vpos, d->vfrc, d->cap_vertices, d->shapes[gr.shape].nv,
                                                          gr.first_vertex, gr.first_particle);
@@ -2084,6 +2140,19 @@ int ib_spread(bib_domain* d) {
 }
 
 int ib_forces_and_spread(bib_domain* d) { return ib_forces(d, d->stream) && ib_spread(d); }
+
+// Function attributes belong to the CURRENT device: every device a domain lives on needs the opt-in above 48 KB of dynamic shared
+// memory (k_spread_tile: 72 KB tile; k_rbc_forces_elem: vertex positions of up to RF_THREADS*RF_VPT_MAX vertices + one element chunk).
+int ib_set_kernel_attributes() {
+    const int tile = (int)((size_t)TILE_CELLS * 3 * sizeof(double));
+    const int rf = (int)((size_t)RF_THREADS * RF_VPT_MAX * 3 * sizeof(double) + RF_CHUNK * sizeof(double));
+    BIB_CHECK(cudaFuncSetAttribute(k_spread_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, tile));
+    BIB_CHECK(cudaFuncSetAttribute(k_rbc_forces_elem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf));
+    BIB_CHECK(cudaFuncSetAttribute(k_rbc_forces_elem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf));
+    BIB_CHECK(cudaFuncSetAttribute(k_rbc_forces_elem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf));
+    BIB_CHECK(cudaFuncSetAttribute(k_rbc_forces_elem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rf));
+    return 1;
+}
 
 __global__ void k_force_accumulate(double* __restrict__ sum, double* __restrict__ vfrc, long long n, int mode) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -2112,7 +2181,7 @@ int ib_move_and_voxelize(bib_domain* d) {
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
         const long long n = (long long)gr.count * s.nt;
-        k_raycast<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.count, d->vpos, d->phase, d->col_flags);
+        k_raycast<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(make_geo(d), s.nv, s.nt, s.tris, gr.first_vertex, d->cap_vertices, gr.count, gr.first_particle, d->vpos, d->phase, d->col_flags);
         d->launches++;
     }
     // apply_voxelization rewrites the phase of every cell of the block each step, also without any particle
@@ -2179,37 +2248,45 @@ int ib_vertices_download(bib_domain* d, long long first, long long count, double
 // in the bench) does not fit under one step once the lattice kernel saturates HBM. The number of owned particles lives on the device;
 // the host copies a prefix sized by the last count it saw plus slack, and ib_results_wait fetches the (rare) remainder synchronously.
 // (A copy-stream kernel storing straight into mapped host memory was measured too: it only ran after the following step had finished.)
-__global__ void __launch_bounds__(1024) k_results_list(const int* __restrict__ role, int cap, int* __restrict__ list, int* __restrict__ count) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
+__global__ void __launch_bounds__(1024) k_results_list(const int* __restrict__ role, const int* __restrict__ slot_nv, int cap, int* __restrict__ list,
+                                                       int* __restrict__ voff, int* __restrict__ count) {
+    __shared__ int s_warp[32], s_wv[32];
+    __shared__ int s_base, s_vbase;
+    if (threadIdx.x == 0) { s_base = 0; s_vbase = 0; }
     __syncthreads();
     for (int s0 = 0; s0 < cap; s0 += 1024) {
         const int s = s0 + threadIdx.x;
         const bool take = s < cap && role[s] == 1;
+        const int nv = take ? slot_nv[s] : 0;
         const unsigned m = __ballot_sync(0xffffffffu, take);
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int incl = nv;                                    // inclusive warp scan of the vertex counts
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_wv[w] = incl;
         if (lane == 0) s_warp[w] = __popc(m);
         __syncthreads();
-        int before = s_base;
-        for (int k = 0; k < w; ++k) before += s_warp[k];
-        if (take) list[before + __popc(m & ((1u << lane) - 1u))] = s;
+        int before = s_base, vbefore = s_vbase;
+        for (int k = 0; k < w; ++k) { before += s_warp[k]; vbefore += s_wv[k]; }
+        if (take) { const int j = before + __popc(m & ((1u << lane) - 1u)); list[j] = s; voff[j] = vbefore + incl - nv; }
         __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 32; ++k) t += s_warp[k]; s_base += t; }
+        if (threadIdx.x == 0) { int t = 0, tv = 0; for (int k = 0; k < 32; ++k) { t += s_warp[k]; tv += s_wv[k]; } s_base += t; s_vbase += tv; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *count = s_base;
+    if (threadIdx.x == 0) { count[0] = s_base; count[1] = s_vbase; }
 }
-__global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, double* __restrict__ out_s, const int* __restrict__ list, const int* __restrict__ count,
-                                                    int nv, const double* __restrict__ vpos, const double* __restrict__ vvel, const double* __restrict__ vfrc,
+__global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, double* __restrict__ out_s, const int* __restrict__ list, const int* __restrict__ voff,
+                                                    const int* __restrict__ count, const int* __restrict__ slot_nv, const long long* __restrict__ slot_fv,
+                                                    const double* __restrict__ vpos, const double* __restrict__ vvel, const double* __restrict__ vfrc,
                                                     const double* __restrict__ pstate, long long cap_v) {
     const int j = blockIdx.x;
     if (j >= *count) return;
     const int s = list[j];
+    const int nv = slot_nv[s];
+    const long long fv = slot_fv[s];
     for (int t = threadIdx.x; t < nv * 9; t += blockDim.x) {
         const int v = t / 9, k = t % 9;
         const double* src = k < 3 ? vpos : (k < 6 ? vvel : vfrc);
-        out_v[(long long)j * nv * 9 + t] = src[(long long)(k % 3) * cap_v + (long long)s * nv + v];
+        out_v[(long long)voff[j] * 9 + t] = src[(long long)(k % 3) * cap_v + fv + v];
     }
     if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
 }
@@ -2224,16 +2301,17 @@ static int res_complete_oldest(bib_domain* d) {
     BIB_CHECK(cudaEventSynchronize(r.copied));
     int n = d->n_particles;
     if (r.compact && d->ms) {
-        const MultiSlabIB* m = d->ms;
-        n = *r.count_host;
-        const int got = r.bound_used;
-        if (n > got) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
+        n = r.count_host[0];
+        const long long nvert = r.count_host[1];
+        const int got = r.bound_used; const long long got_v = r.bound_used_v;
+        if (n > got || nvert > got_v) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
             const double* stage_v = (const double*)r.dev; const double* stage_s = (const double*)((const char*)r.dev + r.vb);
-            BIB_CHECK(cudaMemcpyAsync(r.host_v + (size_t)got * m->nv * 9, stage_v + (size_t)got * m->nv * 9, (size_t)(n - got) * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
-            BIB_CHECK(cudaMemcpyAsync(r.host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            if (nvert > got_v) BIB_CHECK(cudaMemcpyAsync(r.host_v + (size_t)got_v * 9, stage_v + (size_t)got_v * 9, (size_t)(nvert - got_v) * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            if (n > got) BIB_CHECK(cudaMemcpyAsync(r.host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
             BIB_CHECK(cudaStreamSynchronize(d->copy_stream));
         }
-        d->res_bound = std::min(m->cap, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
+        d->res_bound = std::min(d->n_particles, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
+        d->res_bound_v = std::min(d->n_vertices, nvert + std::max<long long>(8 * 1024, nvert / 64));
     }
     d->res_last_count = n;
     d->res_tail = (d->res_tail + 1) % RES_DEPTH; d->res_n--;
@@ -2262,28 +2340,34 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         BIB_CHECK(cudaMalloc(&r.dev, vb + sb));
         r.bytes = vb + sb; d->bytes += (long long)(vb + sb);
     }
-    r.vb = vb; r.host_v = v9; r.host_s = s11; r.compact = false; r.bound_used = 0;
+    r.vb = vb; r.host_v = v9; r.host_s = s11; r.compact = false; r.bound_used = 0; r.bound_used_v = 0;
     double* stage_v = (double*)r.dev; double* stage_s = (double*)((char*)r.dev + vb);
     if (d->ms) {
-        // multi-slab: the owned particles, compacted in slot order
-        const MultiSlabIB* m = d->ms;
-        if (!d->res_list) {
-            BIB_CHECK(cudaMalloc(&d->res_list, (size_t)RES_DEPTH * ((size_t)m->cap + 1) * sizeof(int)));
-            d->res_bound = m->cap;                       // first read-back: everything; afterwards the last count + slack
+        // multi-slab: the owned particles, compacted in slot order (vertex records back to back, whatever the particles' vertex counts)
+        const int cap = d->n_particles;
+        if (!d->res_list || d->res_list_cap < cap) {
+            if (d->res_list) cudaFree(d->res_list);
+            BIB_CHECK(cudaMalloc(&d->res_list, (size_t)RES_DEPTH * (2 * (size_t)cap + 2) * sizeof(int)));
+            d->res_list_cap = cap;
+            d->res_bound = cap; d->res_bound_v = d->n_vertices;    // first read-back: everything; afterwards the last count + slack
         }
-        int* count = d->res_list + (size_t)d->res_head * ((size_t)m->cap + 1); int* list = count + 1;
-        k_results_list<<<1, 1024, 0, d->stream>>>(m->role, m->cap, list, count);
-        k_pack_slots<<<m->cap, 128, 0, d->stream>>>(stage_v, stage_s, list, count, m->nv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
+        int* count = d->res_list + (size_t)d->res_head * (2 * (size_t)cap + 2); int* list = count + 2; int* voff = list + cap;
+        k_results_list<<<1, 1024, 0, d->stream>>>(d->role_all, d->slot_nv, cap, list, voff, count);
+        k_pack_slots<<<cap, 128, 0, d->stream>>>(stage_v, stage_s, list, voff, count, d->slot_nv, d->slot_fv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
         d->launches += 2;
         BIB_CHECK(cudaGetLastError());
         BIB_CHECK(cudaEventRecord(r.packed, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));
-        size_t nb = (size_t)std::min(d->res_bound, m->cap);
-        if (const char* e = getenv("BIB_RESULTS_BOUND")) nb = (size_t)std::max(0, std::min(atoi(e), m->cap));     // tests: force the remainder path
-        BIB_CHECK(cudaMemcpyAsync(r.count_host, count, sizeof(int), cudaMemcpyDeviceToHost, d->copy_stream));
-        if (nb) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, nb * m->nv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+        size_t nb = (size_t)std::min(d->res_bound, cap);
+        size_t nbv = (size_t)std::min(d->res_bound_v, d->n_vertices);
+        if (const char* e = getenv("BIB_RESULTS_BOUND")) {     // tests: force the remainder path
+            nb = (size_t)std::max(0, std::min(atoi(e), cap));
+            nbv = std::min<size_t>(nbv, nb * (size_t)(d->msv[0] ? d->msv[0]->nv : 0));
+        }
+        BIB_CHECK(cudaMemcpyAsync(r.count_host, count, 2 * sizeof(int), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (nbv) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, nbv * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
         if (nb) BIB_CHECK(cudaMemcpyAsync(s11, stage_s, nb * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
-        r.compact = true; r.bound_used = (int)nb;
+        r.compact = true; r.bound_used = (int)nb; r.bound_used_v = (long long)nbv;
     } else {
         if (vb) {
             const int grid = (int)std::min<long long>((d->n_vertices * 9 + 255) / 256, 148 * 16);
@@ -2307,6 +2391,7 @@ int ib_results_count(bib_domain* d, int* n) {
     return 1;
 }
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {
+    d->band_pos_valid = false;
     if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_upload: range"); return 0; }
     if (count == 0) return 1;
     std::vector<double> tmp((size_t)count * 9);
@@ -2315,7 +2400,7 @@ int ib_vertices_upload(bib_domain* d, long long first, long long count, const do
     for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
         BIB_CHECK(cudaMemcpyAsync(dst[a] + (size_t)c * d->cap_vertices + first, tmp.data() + (size_t)(a * 3 + c) * count, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     BIB_CHECK(cudaStreamSynchronize(d->stream));
-    if (d->ms) d->ms->ghosts_dirty = true;
+    if (d->ms) d->ghosts_dirty = true;
     return ib_update_all(d, 0);        // area, volume, centre of mass, bounding box follow the new positions (ParticleBase3D::update)
 }
 int ib_scalars_upload(bib_domain* d, int first, int count, const double* s11) {

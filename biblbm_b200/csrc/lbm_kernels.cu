@@ -484,7 +484,7 @@ __global__ void k_fill_populations(double* f, Eq19 eq, int bx0, int by0, int bz0
 struct WallParams {
     double* f; const double* force; const double* wallvel;
     int nx, ny, nz; long long plane, vol;
-    int dir, orient, coord, na, nb;
+    int dir, orient, coord, na, nb, gx;
     int a0, b0, ca, cb;          // covered cells of the face: a = a0 .. a0+ca-1, b = b0 .. b0+cb-1
     double omega;
 };
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
     double f[BIB_Q];
 #pragma unroll
     for (int i = 0; i < BIB_Q; ++i) f[i] = w.f[(long long)i * w.vol + idx];
-    const double* vel = w.wallvel + ((long long)a * w.nb + b) * 3;
+    const double* vel = w.wallvel + ((long long)(a + w.gx) * w.nb + b) * 3;
     const double v[3] = {vel[0], vel[1], vel[2]};
     const double Fd = w.force[(long long)w.dir * w.vol + idx];
     double rhoOnWall = 0.0, rhoNormal = 0.0;
@@ -526,9 +526,10 @@ __global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
             for (int k = 0; k < 3; ++k) grad[dd][k] = -w.orient * (-v[k] + u1[k]);
         } else {
             int p[3] = {c[0], c[1], c[2]}, q[3] = {c[0], c[1], c[2]};
-            p[dd] = (c[dd] + 1) % n[dd]; q[dd] = (c[dd] + n[dd] - 1) % n[dd];
-            const double* up = w.wallvel + ((long long)p[ta] * w.nb + p[tb]) * 3;
-            const double* um = w.wallvel + ((long long)q[ta] * w.nb + q[tb]) * 3;
+            if (dd == 0 && w.gx) { p[0] = c[0] + 1; q[0] = c[0] - 1; }      // multi-slab: the neighbouring slabs' columns are stored as ghost columns
+            else { p[dd] = (c[dd] + 1) % n[dd]; q[dd] = (c[dd] + n[dd] - 1) % n[dd]; }
+            const double* up = w.wallvel + ((long long)(p[ta] + w.gx) * w.nb + p[tb]) * 3;
+            const double* um = w.wallvel + ((long long)(q[ta] + w.gx) * w.nb + q[tb]) * 3;
             for (int k = 0; k < 3; ++k) grad[dd][k] = (up[k] - um[k]) / 2.0;
         }
     }
@@ -560,14 +561,14 @@ __global__ void __launch_bounds__(128) k_wall_plane(const WallParams w) {
 }
 // computeVelocity on a wall cell returns the stored boundary velocity (StoreVelocityDynamics::computeVelocity)
 __global__ void k_wall_velocity_fill(double* vel, const double* __restrict__ wallvel, int dir, int coord, int na, int nb, int a0, int b0, int cb,
-                                     long long plane, long long vol, int nz) {
+                                     long long plane, long long vol, int nz, int gx) {
     const int bb = blockIdx.x * blockDim.x + threadIdx.x, a = a0 + (int)blockIdx.y;
     if (bb >= cb) return;
     const int b = b0 + bb;
     const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
     int c[3]; c[dir] = coord; c[ta] = a; c[tb] = b;
     const long long idx = (long long)(c[0] + 1) * plane + (long long)c[1] * nz + c[2];
-    const double* v = wallvel + ((long long)a * nb + b) * 3;
+    const double* v = wallvel + ((long long)(a + gx) * nb + b) * 3;
     vel[idx] = v[0]; vel[vol + idx] = v[1]; vel[2 * vol + idx] = v[2];
 }
 
@@ -794,12 +795,14 @@ int lbm_add_wall(bib_domain* d, const int box[6], int dir, int orient) {
         else if (box[2 * t] < 1 || box[2 * t + 1] > n[t] - 2) { bib_set_error("add_velocity_boundary: along a non-periodic in-plane direction the plane must leave the border cells to edge conditions"); return 0; }
     }
     if (d->n_ranks > 1 && (dir == 0 || !d->per[0])) { bib_set_error("add_velocity_boundary: on multi-slab domains only planes normal to y / z with periodic x"); return 0; }
+    const int gxc = d->n_ranks > 1 ? 1 : 0;
     for (const WallPlane& o : d->walls) if (o.dir == dir && o.coord == box[2 * dir]) { bib_set_error("add_velocity_boundary: a velocity boundary already exists on this plane"); return 0; }
     WallPlane w; w.dir = dir; w.orient = orient; w.coord = box[2 * dir]; w.na = n[ta]; w.nb = n[tb];
     w.a0 = box[2 * ta]; w.a1 = box[2 * ta + 1]; w.b0 = box[2 * tb]; w.b1 = box[2 * tb + 1];
-    w.h_vel.assign((size_t)w.na * w.nb * 3, 0.0);
-    BIB_CHECK(cudaMalloc(&w.vel, (size_t)w.na * w.nb * 3 * sizeof(double)));
-    BIB_CHECK(cudaMemsetAsync(w.vel, 0, (size_t)w.na * w.nb * 3 * sizeof(double), d->stream));
+    w.gx = gxc;
+    w.h_vel.assign((size_t)(w.na + 2 * w.gx) * w.nb * 3, 0.0);
+    BIB_CHECK(cudaMalloc(&w.vel, w.h_vel.size() * sizeof(double)));
+    BIB_CHECK(cudaMemsetAsync(w.vel, 0, w.h_vel.size() * sizeof(double), d->stream));
     d->walls.push_back(w);
     return 1;
 }
@@ -828,22 +831,45 @@ int lbm_add_edge(bib_domain* d, const int box[6], int axis, int normal1, int nor
 }
 // setBoundaryVelocity(lattice, box, u): every boundary cell inside the box stores its velocity; a face array also keeps the velocities
 // of the edge cells on its border (they are the in-plane neighbours of the plane's outermost cells)
-int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
-    if (!box_ok(d, box)) { bib_set_error("set_boundary_velocity: box outside the slab"); return 0; }
+// `box` / `vel` in coordinates whose x = 0 is global plane gx0 of this slab's frame shifted by -gx0 (gx0 = 0: slab-local coordinates).
+// On a multi-slab domain the box may reach one column beyond either x-end of the slab (x = -1, x = nx): the stored velocities of the
+// neighbouring slabs' wall cells, which the plane functional differentiates along x; columns never supplied copy the nearest own column
+// (exact for a wall velocity that does not depend on x). gnx_wrap != 0: x of the box is global and periodic with that period.
+int lbm_set_wall_velocity_ext(bib_domain* d, const int box[6], const double* vel, int gx0, int gnx_wrap) {
     const int by = box[3] - box[2] + 1, bz = box[5] - box[4] + 1;
+    if (box[0] > box[1] || box[2] < 0 || box[3] >= d->ny || box[2] > box[3] || box[4] < 0 || box[5] >= d->nz || box[4] > box[5]) { bib_set_error("set_boundary_velocity: box outside the lattice"); return 0; }
     bool any = false;
     for (WallPlane& w : d->walls) {
         if (w.coord < box[2 * w.dir] || w.coord > box[2 * w.dir + 1]) continue;
         const int ta = w.dir == 0 ? 1 : 0, tb = w.dir == 2 ? 1 : 2;
-        for (int a = std::max(0, box[2 * ta]); a <= std::min(w.na - 1, box[2 * ta + 1]); ++a)
+        std::vector<char> have(w.na + 2 * w.gx, 0);
+        const int alo = ta == 0 ? -w.gx : 0, ahi = ta == 0 ? w.na - 1 + w.gx : w.na - 1;
+        for (int a = alo; a <= ahi; ++a) {
+            int ga = a;                                    // coordinate of row a in the box's frame
+            if (ta == 0) {
+                ga = a + gx0;
+                if (gnx_wrap) ga = ((ga % gnx_wrap) + gnx_wrap) % gnx_wrap;
+            }
+            if (ga < box[2 * ta] || ga > box[2 * ta + 1]) continue;
             for (int b = std::max(0, box[2 * tb]); b <= std::min(w.nb - 1, box[2 * tb + 1]); ++b) {
-                int c[3]; c[w.dir] = w.coord; c[ta] = a; c[tb] = b;
+                int c[3]; c[w.dir] = w.coord; c[ta] = ga; c[tb] = b;
                 const double* src = vel + (((size_t)(c[0] - box[0]) * by + (c[1] - box[2])) * bz + (c[2] - box[4])) * 3;
-                double* dst = &w.h_vel[((size_t)a * w.nb + b) * 3];
+                double* dst = &w.h_vel[((size_t)(a + (ta == 0 ? w.gx : 0)) * w.nb + b) * 3];
                 dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
             }
+            if (ta == 0) have[a + w.gx] = 1;
+            any = true;
+        }
+        if (w.gx) {
+            if (!have[0]) std::copy(w.h_vel.begin() + (size_t)1 * w.nb * 3, w.h_vel.begin() + (size_t)2 * w.nb * 3, w.h_vel.begin());
+            if (!have[w.na + 1]) std::copy(w.h_vel.begin() + (size_t)w.na * w.nb * 3, w.h_vel.begin() + (size_t)(w.na + 1) * w.nb * 3, w.h_vel.begin() + (size_t)(w.na + 1) * w.nb * 3);
+        }
         BIB_CHECK(cudaMemcpyAsync(w.vel, w.h_vel.data(), w.h_vel.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-        any = true;
+    }
+    if (gx0 != 0 || gnx_wrap != 0) {        // called by the slab group with the global box: edges do not exist on multi-slab domains
+        BIB_CHECK(cudaStreamSynchronize(d->stream));
+        if (!any) { bib_set_error("set_boundary_velocity: no velocity boundary registered inside this box"); return 0; }
+        return 1;
     }
     for (WallEdge& e : d->edges) {
         const int d1 = (e.axis + 1) % 3, d2 = (e.axis + 2) % 3;
@@ -860,11 +886,16 @@ int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
     if (!any) { bib_set_error("set_boundary_velocity: no velocity boundary registered inside this box"); return 0; }
     return 1;
 }
+int lbm_set_wall_velocity(bib_domain* d, const int box[6], const double* vel) {
+    const int xlo = d->n_ranks > 1 ? -1 : 0, xhi = d->n_ranks > 1 ? d->nx : d->nx - 1;
+    if (box[0] < xlo || box[1] > xhi) { bib_set_error("set_boundary_velocity: box outside the slab"); return 0; }
+    return lbm_set_wall_velocity_ext(d, box, vel, 0, 0);
+}
 int lbm_apply_walls(bib_domain* d) {
     for (const WallPlane& wp : d->walls) {
         WallParams w;
         w.f = d->f[d->cur]; w.force = d->force; w.wallvel = wp.vel; w.nx = d->nx; w.ny = d->ny; w.nz = d->nz;
-        w.plane = (long long)d->plane; w.vol = (long long)d->vol; w.dir = wp.dir; w.orient = wp.orient; w.coord = wp.coord; w.na = wp.na; w.nb = wp.nb;
+        w.plane = (long long)d->plane; w.vol = (long long)d->vol; w.dir = wp.dir; w.orient = wp.orient; w.coord = wp.coord; w.na = wp.na; w.nb = wp.nb; w.gx = wp.gx;
         w.a0 = wp.a0; w.b0 = wp.b0; w.ca = wp.a1 - wp.a0 + 1; w.cb = wp.b1 - wp.b0 + 1;
         w.omega = d->omega0;
         k_wall_plane<<<dim3((w.cb + 127) / 128, w.ca), 128, 0, d->stream>>>(w);
@@ -977,7 +1008,7 @@ int lbm_wall_velocity_fill(bib_domain* d) {
     for (const WallPlane& wp : d->walls) {
         const int ca = wp.a1 - wp.a0 + 1, cb = wp.b1 - wp.b0 + 1;
         k_wall_velocity_fill<<<dim3((cb + 127) / 128, ca), 128, 0, d->stream>>>(d->vel, wp.vel, wp.dir, wp.coord, wp.na, wp.nb, wp.a0, wp.b0, cb,
-                                                                              (long long)d->plane, (long long)d->vol, d->nz);
+                                                                              (long long)d->plane, (long long)d->vol, d->nz, wp.gx);
         d->launches++;
     }
     for (const WallEdge& e : d->edges) {
@@ -1040,6 +1071,7 @@ int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double f
     d->launches++;
     BIB_CHECK(cudaGetLastError());
     const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
+    if (full) d->spread_band = -1;          // nothing left to reset
     if (full && d->sparse_force) {          // every cell now holds the body force: all flags off
         const size_t words = (d->vol + 31) / 32;
         if (!d->fflag) { BIB_CHECK(cudaMalloc(&d->fflag, words * sizeof(unsigned))); d->bytes += (long long)(words * sizeof(unsigned)); }

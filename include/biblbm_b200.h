@@ -68,6 +68,17 @@ int bib_device_count(int* count);
  * GuoExternalForceBGKdynamics (omega_inner is ignored; 22 doubles per cell in upload / download). */
 int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner,
                       const int periodic[3], int device, bib_domain** out);
+/* The same lattice as x-slabs on SEVERAL GPUs owned by ONE host process: what `mpirun -np N ./driver` is to the reference
+ * (one block per rank: src/fsi/ImmersedBoundaryDynamics.hh:49-54, src/multiBlock/multiBlockLattice3D.hh:306-348, progs/rbc_in_pipe/batch.sh).
+ * nx is the GLOBAL size (a multiple of n_slabs); devices[n_slabs] = CUDA ordinal of every slab (NULL: 0..n_slabs-1; slabs may share
+ * a device). The returned handle is used like any other: boxes, particle ids and vertex ranges are global, every entry point is split
+ * over / broadcast to the slabs, collective work runs on one worker thread per slab with peer-to-peer (NVLink) halo and particle
+ * exchanges. Not available on such a handle: rigid particles, velocity edges, vertex_forces_preload, multi_direct_forcing, the
+ * asynchronous results read-back (bib_domain_slab gives the per-slab handles for that), planes normal to x. n_slabs == 1 is bib_domain_create. */
+int bib_domain_create_multi(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3],
+                            int n_slabs, const int* devices, bib_domain** out);
+int bib_domain_slab_count(bib_domain* d, int* n_slabs);
+int bib_domain_slab(bib_domain* d, int slab, bib_domain** out);      /* the handle of one slab (owned by the multi-slab handle) */
 int bib_domain_destroy(bib_domain* d);
 int bib_domain_set_option(bib_domain* d, int key, double value);
 int bib_domain_upload(bib_domain* d, const int box[6], const double* cells);
@@ -205,7 +216,7 @@ int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count,
  *      collideAndStream, repeated n_steps times without host synchronisation. */
 int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps);
 
-/* ---- multi-GPU: x-slab ring over NCCL (replaces ParallelBlockCommunicator3D::duplicateOverlaps,
+/* ---- multi-GPU, one process per GPU: x-slab ring over NCCL (replaces ParallelBlockCommunicator3D::duplicateOverlaps,
  *      src/parallelism/parallelBlockCommunicator3D.cpp:144-233). unique_id: the 128 bytes of an ncclUniqueId. */
 int bib_comm_unique_id(void* unique_id_128);
 int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128);

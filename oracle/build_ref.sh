@@ -21,7 +21,7 @@ HARNESSES=("$@")
 if [ ${#HARNESSES[@]} -eq 0 ]; then HARNESSES=($(ls "$HERE"/harness/*.cpp 2>/dev/null | xargs -n1 basename | sed 's/\.cpp$//')); fi
 for h in "${HARNESSES[@]}"; do
   src="$HERE/harness/$h.cpp"
-  if [ ! -f "$OUT/$h" ] || [ "$src" -nt "$OUT/$h" ] || [ "$HERE/harness/harness_common.h" -nt "$OUT/$h" ]; then
+  if [ ! -f "$OUT/$h" ] || [ "$src" -nt "$OUT/$h" ]; then
     echo "building oracle/_ref/$h"
     g++ $FLAGS -O3 -I"$REF/progs" -I"$HERE/harness" "$src" "$OUT/libplb_ref.a" -o "$OUT/$h"
   fi

@@ -5,7 +5,7 @@
 // and dumps raw state so that the C restatement (oracle/biblbm_oracle.c) and the CUDA path can be compared
 // with it. This file is our own harness code: it contains no reference source, only calls into its API.
 //
-// Sub-commands (all file formats are raw little-endian, documented in oracle/README.md):
+// Sub-commands (all file formats are raw little-endian, documented at the readers/writers in tests/kit.py and tests/golden/make_golden.py):
 //   ref_harness mesh2bin <in.msh> <out.mesh>        gmsh -> {i64 nv, i64 nt, f64 xyz[nv*3], i64 tri[nt*3]}
 //   ref_harness shape    <in.mesh> <out_prefix>     connectivity as built by ParticleShape::compute_connectivity
 //   ref_harness deflate  <in.mesh> <out.f64> G K_area K_bend vol_frac N_it     shrink_rbc_volume (setup-time host loop)

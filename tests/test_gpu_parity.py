@@ -688,6 +688,55 @@ def test_band_passes_equal_full_passes(rbc):
     assert np.array_equal(a.download(), b.download())
 
 
+def test_band_reset_survives_extra_interpolations(rbc):
+    """Extra public bib_ib_interpolate_velocity calls between two steps (and a move without a spread) must not change which cells the
+    next step's band reset clears: the reset uses the masks recorded at the spread, not "the other buffer" (ADVICE r1)."""
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    a = run_ib_case(g, shape, params, deterministic=True)
+    b = run_ib_case(g, shape, params, deterministic=True)
+    for it in range(6):
+        a.step(g["body"])
+        b.step(g["body"])
+        b.interpolate_velocity()                   # once, twice: each rotates / rewrites the band masks
+        if it % 2:
+            b.interpolate_velocity()
+    # interpolation only changes vertex velocities (overwritten by the next step's own interpolation): everything else is identical
+    assert np.array_equal(a.vertices()[..., :3], b.vertices()[..., :3])
+    assert np.array_equal(a.download(), b.download())
+    # a move between spread and reset (positions no longer those of the masks): the reset falls back to the whole lattice
+    a.step(g["body"]); b.step(g["body"])
+    va = a.vertices(); b.upload_vertices(va.copy())
+    a.upload_vertices(va.copy())
+    a.step(g["body"]); b.step(g["body"])
+    assert np.array_equal(a.download(), b.download())
+    # the force field outside the current stencils equals the body force exactly (no stale IB force anywhere)
+    for lat in (a, b):
+        F = lat.download()[..., 19:22]
+        lat.setExternalVector(g["body"])
+        lat.sync()
+        assert np.array_equal(lat.download()[..., 19:22], np.broadcast_to(np.asarray(g["body"], dtype=float), F.shape))
+
+
+def test_two_devices_in_one_process(rbc):
+    """Function attributes (dynamic shared memory opt-in of k_spread_tile / k_rbc_forces_elem) are per device: a second domain on
+    another GPU of the same process must step like the first. Needs 2 GPUs."""
+    if bib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc1.npz")
+    out = []
+    for dev in (0, 1):
+        lat = bib.Lattice(*g["pop_init"].shape[:3], float(g["omega"]), float(g["omega_inner"]), periodic=tuple(bool(p) for p in g["per"]), device=dev)
+        lat.upload(g["pop_init"])
+        sid = lat.register_shape(shape.verts, shape.tris)
+        lat.add_particles(sid, params, g["vert_init"][..., :3])
+        lat.step(g["body"], n=3)
+        out.append((lat.vertices(), lat.download()))
+    assert np.array_equal(out[0][1], out[1][1])
+    assert kit.rel_err(out[0][0][..., :3], out[1][0][..., :3]) <= 1e-12
+
+
 def _shear_lattice(g, opts=None):
     nx, ny, nz, _ = g["pop_init"].shape
     uw = float(g["u_wall"])
