@@ -3,16 +3,25 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --gpus N --scaling strong                 (fixed global lattice instead of a fixed slab per GPU)
 
 Workload (BASELINE.json configs[4], weak scaling along x): every GPU owns a 128 x 1024 x 1024 slab of a
 (128*N) x 1024 x 1024 fp64 D3Q19 ForcedPhase lattice (N = 8 is the named 1024^3 lattice) carrying 1250 RBC meshes
 (626 vertices each; N = 8: 10 000 RBCs). A step is one full driver step: velocity interpolation, membrane forces,
 force spreading, vertex advection, voxelization and the fused collide-and-stream.
+
+Measurement: W warm-up steps, then one untimed priming block of K steps issued exactly like the timed ones (CUDA graphs are
+captured there, every buffer is allocated), then R back-to-back blocks of EXACTLY K steps, each bracketed by CUDA events on the
+compute stream (barrier + synchronize on both sides, max over ranks per block); R is chosen so that the blocks cover >= 2 s.
+`value` / `ms_per_step` are the MEDIAN block; `repeats` carries min / max / all blocks. Before anything is timed a multi-slab
+parity gate runs small cases through the same multi-GPU path and compares them with the CPU oracle (`parity_check`); a failing
+gate makes the process exit non-zero.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import pathlib
 import subprocess
@@ -28,6 +37,7 @@ sys.path.insert(0, str(ROOT))
 REF_HARNESS = ROOT / "oracle" / "_ref" / "ref_harness"
 LBM_BYTES_PER_CELL = 304.0          # 19 populations x 8 B x (read + write): BASELINE.json / SURVEY.md section 8(d)
 IB_BYTES_PER_VERTEX = 330.0
+REF_BOX, REF_RBCS = 96, 8           # the bounded sample the reference arm / cpu_baseline times (per host core)
 
 
 def measured_peaks():
@@ -61,27 +71,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def mark(self):
-        return time.time()
-
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         for t, line in self.rows:
             if t < t0 - 0.1 or t > t1 + 0.3:
                 continue
             parts = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(parts[1])); smax = float(parts[2])
+                sm.append(float(parts[1])); smax = float(parts[2]); power.append(float(parts[3]))
             except Exception:
                 continue
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": float(np.median(power)) if power else None}
 
 
 # ----------------------------------------------------------------------------------------------------- inputs
@@ -120,7 +128,13 @@ def write_mesh(path, verts, tris):
         np.ascontiguousarray(tris, dtype=np.int64).tofile(f)
 
 
-def run_reference_sample(steps, warmup, replicas, box=96, n_rbc=8):
+def reference_sample_text(replicas=None):
+    who = f"{replicas}" if replicas else "one per host core (<= 32)"
+    return (f"reference arm / cpu_baseline time the UNMODIFIED reference on {who} concurrent single-rank replicas of a {REF_BOX}^3 periodic box with "
+            f"{REF_RBCS} RBCs each (the bench's hematocrit; a bounded sample: the full lattice needs 27 GB of host RAM per 512^3); no MPI exchange cost included")
+
+
+def run_reference_sample(steps, warmup, replicas, box=REF_BOX, n_rbc=REF_RBCS):
     """Times the UNMODIFIED reference (oracle/_ref/ref_harness) on `replicas` concurrent single-rank copies of a bounded
     sample of the workload: a box^3 periodic lattice with n_rbc RBCs at the bench's hematocrit. Returns aggregate numbers."""
     verts, tris, params, rbc_pos = load_rbc()
@@ -199,18 +213,196 @@ def reference_arm(args):
     r = run_reference_sample(args.steps, args.warmup, replicas)
     line = {"impl": "reference", "metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": r["mlups"], "unit": "MLUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
             "lbm_only_mlups": r["lbm_only_mlups"], "ib_vertex_updates_per_s": r["vertex_updates_per_s"],
             "cpu_baseline": {"value": r["mlups"], "unit": "MLUPS", "cores": replicas, "kind": "reference", "sample": r["sample"]},
             "e2e": {"value": r["mlups"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n):
-    return {"workload": f"synthetic ({128 * n}x1024x1024) D3Q19 ForcedPhase lattice, {1250 * n} RBC meshes (626 vertices), x-slab per GPU 128x1024x1024",
-            "global_cells": 128 * n * 1024 * 1024, "rbcs": 1250 * n, "vertices": 1250 * n * 626, "parallelism": f"x-slabs x{n}",
-            "l2_policy": "inputs (41 GB of populations per GPU) exceed the 126 MB L2; no flush needed"}
+def slab_of(args, n):
+    """(local nx, ny, nz, RBCs per GPU) of one of n GPUs."""
+    if args.scaling == "strong":
+        if args.global_nx % n:
+            raise SystemExit(f"--scaling strong: global nx {args.global_nx} is not a multiple of {n} GPUs")
+        return args.global_nx // n, args.ny, args.nz, args.global_rbcs / n
+    return args.nx, args.ny, args.nz, args.rbcs
+
+
+def workload_config(args, n):
+    nxl, ny, nz, rb = slab_of(args, n)
+    gx, rbcs = nxl * n, int(round(rb * n))
+    kind = "weak scaling: fixed x-slab per GPU" if args.scaling == "weak" else "strong scaling: fixed global lattice"
+    return {"workload": f"synthetic ({gx}x{ny}x{nz}) D3Q19 ForcedPhase lattice, {rbcs} RBC meshes (626 vertices), x-slab per GPU {nxl}x{ny}x{nz} ({kind})",
+            "global_cells": gx * ny * nz, "rbcs": rbcs, "vertices": rbcs * 626, "parallelism": f"x-slabs x{n}",
+            "l2_policy": "inputs (>= 10 GB of populations per GPU) exceed the 126 MB L2; no flush needed",
+            "reference_sample": reference_sample_text()}
+
+
+# ----------------------------------------------------------------------------------------------------- multi-slab parity gate
+def flat_rbc(rbc_pos, thin_axis):
+    base = rbc_pos - rbc_pos.mean(0)
+    _, _, vt = np.linalg.svd(base, full_matrices=False)
+    R = np.roll(vt[::-1], thin_axis, axis=0)
+    if np.linalg.det(R) < 0:
+        R[(thin_axis + 1) % 3] *= -1.0
+    return base @ R.T
+
+
+def channel_positions(rbc_pos, gx):
+    disk = flat_rbc(rbc_pos, 0)
+    thick = disk[:, 0].max() - disk[:, 0].min()
+    n = int(gx / (thick + 0.55))
+    pitch = gx / n
+    return np.array([disk + np.array([(k + 0.5) * pitch, 9.05 + 5.0 * (k % 2), 10.4 + 0.7 * (k % 3)]) for k in range(n)])
+
+
+def parity_gate(bib, dist, torch, rank, world, local):
+    """Small cases through THIS run's multi-GPU path (one slab per rank, NCCL halo + particle exchanges; world == 1: the single-slab
+    path) against the CPU oracle stepping the undivided lattice on rank 0: (a) populations on random lattices for three periodicity
+    patterns (bit-identical), (b) RBCs across slab faces / the periodic seam in a periodic box, (c) the rbcs_in_channel-class case:
+    wall planes with x-dependent velocity, ParallelPlatesBoundary, body force, Morse wall force, Morse particle-particle force."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import kit
+    orc = kit.oracle() if rank == 0 else None
+    shape, params, rbc_pos, _ = kit.load_rbc_fixture()
+    cases, worst = [], 0.0
+
+    def make(nxl, ny, nz, w0, w1, per):
+        lat = bib.Lattice(nxl, ny, nz, w0, w1, periodic=per, device=local)
+        if world > 1:
+            uid = [bib.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            lat.comm_init(rank, world, uid[0])
+        return lat
+
+    def gather_cells(lat):
+        mine = torch.from_numpy(lat.download()).cuda()
+        if world == 1:
+            return mine.cpu().numpy()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts, 0).cpu().numpy()
+
+    def gather_particles(lat, n_p, nv):
+        gids, roles = lat.local_slots()
+        verts = lat.vertices().reshape(len(gids), nv, 9)
+        scal = lat.particle_scalars()
+        mine = {int(g): (verts[s], scal[s]) for s, (g, r) in enumerate(zip(gids, roles)) if r == 1}
+        allv = [mine]
+        if world > 1:
+            allv = [None] * world
+            dist.all_gather_object(allv, mine)
+        out_v, out_s, owners = np.zeros((n_p, nv, 9)), np.zeros((n_p, 11)), np.zeros(n_p, dtype=int)
+        for m in allv:
+            for g, (v, s) in m.items():
+                out_v[g] = v; out_s[g] = s; owners[g] += 1
+        return out_v, out_s, owners
+
+    # (a) populations
+    for per in [(1, 1, 1), (0, 1, 0), (1, 0, 1)]:
+        nxl, ny, nz = 6, 9, 20
+        gx = nxl * world
+        rng = np.random.default_rng(21)
+        cells = np.zeros((gx, ny, nz, 23))
+        cells[..., :19] = 0.01 * rng.normal(size=(gx, ny, nz, 19))
+        cells[..., 19:22] = 1e-4 * rng.normal(size=(gx, ny, nz, 3))
+        cells[..., 22] = rng.integers(0, 2, size=(gx, ny, nz))
+        lat = make(nxl, ny, nz, 1.5, 0.6, per)
+        lat.upload(cells[rank * nxl:(rank + 1) * nxl])
+        lat.collideAndStream(5)
+        got = gather_cells(lat)
+        lat.close()
+        if rank == 0:
+            ref = cells
+            for _ in range(5):
+                ref = orc.collide_and_stream(ref, per, 1.5, 0.6)
+            err = 0.0 if np.array_equal(got, ref) else max(kit.rel_err(got[..., :19], ref[..., :19]), 1e-300)
+            cases.append({"case": f"lattice per={per}", "steps": 5, "rel_err": err, "pass": err == 0.0})
+            worst = max(worst, err)
+
+    # (b) RBCs across faces and the periodic seam
+    nxl, ny, nz, steps = 24, 24, 22, 100
+    gx = nxl * world
+    per = (1, 1, 1)
+    centers = [(nxl - 0.4, 11.7, 10.6), (gx - 1.3, 12.4, 11.2), (10.2, 11.1, 10.9)] + ([(2 * nxl + 3.1, 12.2, 11.0)] if world > 2 else [])
+    pos = kit.place_particles(rbc_pos, centers, seed=9)
+    body, u0 = (4e-5, 0.0, 1e-5), (0.05, 0.0, 0.004)
+    lat = make(nxl, ny, nz, 1.0, 1 / 3, per)
+    lat.initializeAtEquilibrium(1.0, u0)
+    cells0 = gather_cells(lat)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    lat.step(body, n=steps)
+    lat.sync()
+    got_v, got_s, owners = gather_particles(lat, len(centers), shape.nv)
+    got = gather_cells(lat)
+    lat.close()
+    if rank == 0:
+        vert = np.zeros((len(centers), shape.nv, 9)); vert[..., :3] = pos
+        state = np.array([orc.particle_update(shape, p) for p in pos])
+        ref = cells0.copy()
+        for _ in range(steps):
+            orc.full_step(ref, per, 1.0, 1 / 3, body, shape, params, vert, state)
+        err = max(kit.rel_err(got_v[..., :3], vert[..., :3]), kit.rel_err(got_v[..., 3:6], vert[..., 3:6]), kit.rel_err(got[..., :19], ref[..., :19]))
+        ok = err <= 1e-9 and np.array_equal(got[..., 22], ref[..., 22]) and bool((owners == 1).all())
+        cases.append({"case": f"{len(centers)} RBCs across slab faces / periodic seam, {gx}x{ny}x{nz}", "steps": steps, "rel_err": err, "pass": bool(ok)})
+        worst = max(worst, err)
+
+    # (c) rbcs_in_channel class
+    nxl, ny, nz, steps = 26, 27, 22, 60
+    gx = nxl * world
+    pos = channel_positions(rbc_pos, gx)
+    n_p = pos.shape[0]
+    wall_morse, pp_morse = (1.0, 2.0, 2e-4), (1.0, 1.5, 3e-4)
+    x = np.arange(gx)
+    lo = np.zeros((gx, nz, 3)); hi = np.zeros((gx, nz, 3))
+    lo[..., 0] = -0.01 * (1.0 + 0.3 * np.sin(2 * np.pi * x / gx))[:, None]
+    hi[..., 0] = 0.012 * (1.0 + 0.2 * np.cos(2 * np.pi * x / gx))[:, None]
+    lat = make(nxl, ny, nz, 1.0, 1 / 3, (1, 0, 1))
+    lat.initializeAtEquilibrium(1.0, (0.0, 0.0, 0.0))
+    cells0 = gather_cells(lat)
+    sl = slice(rank * nxl, (rank + 1) * nxl)
+    lat.addVelocityBoundary((0, nxl - 1, 0, 0, 0, nz - 1), 1, -1)
+    lat.addVelocityBoundary((0, nxl - 1, ny - 1, ny - 1, 0, nz - 1), 1, +1)
+    if world > 1:      # own columns + one ghost column on either side (the neighbours' wall cells: differentiated along x by the plane functional)
+        idx = np.arange(rank * nxl - 1, (rank + 1) * nxl + 1) % gx
+        lat.setBoundaryVelocity((-1, nxl, 0, 0, 0, nz - 1), lo[idx][:, None])
+        lat.setBoundaryVelocity((-1, nxl, ny - 1, ny - 1, 0, nz - 1), hi[idx][:, None])
+    else:
+        lat.setBoundaryVelocity((0, nxl - 1, 0, 0, 0, nz - 1), lo[sl][:, None])
+        lat.setBoundaryVelocity((0, nxl - 1, ny - 1, ny - 1, 0, nz - 1), hi[sl][:, None])
+    lat.set_boundary(0.0, float(ny - 1))
+    lat.set_wall_interaction(bib.POTENTIAL_MORSE, *wall_morse)
+    lat.set_pp_interaction(bib.POTENTIAL_MORSE, *pp_morse)
+    sid = lat.register_shape(shape.verts, shape.tris)
+    lat.add_particles(sid, params, pos)
+    lat.step(body, n=steps)
+    lat.sync()
+    got_v, got_s, owners = gather_particles(lat, n_p, shape.nv)
+    got = gather_cells(lat)
+    lat.close()
+    if rank == 0:
+        vert = np.zeros((n_p, shape.nv, 9)); vert[..., :3] = pos
+        state = np.array([orc.particle_update(shape, p) for p in pos])
+        ref = cells0.copy()
+        orc.set_parallel_plates(1, 0.0, float(ny - 1))
+        orc.set_wall_interaction(bib.POTENTIAL_MORSE, *wall_morse)
+        orc.set_pp_interaction(bib.POTENTIAL_MORSE, *pp_morse)
+        try:
+            for _ in range(steps):
+                ref, _v = orc.shear_step(ref, 1.0, 1 / 3, body, lo, hi, shape, params, vert, state)
+        finally:
+            orc.reset_modes()
+        err = max(kit.rel_err(got_v[..., :3], vert[..., :3]), kit.rel_err(got[..., :19], ref[..., :19]))
+        ok = err <= 1e-9 and np.array_equal(got[..., 22], ref[..., 22]) and bool((owners == 1).all())
+        cases.append({"case": f"rbcs_in_channel class: {n_p} RBCs, wall planes (x-dependent velocity), plates, body force, Morse wall + particle-particle forces, {gx}x{ny}x{nz}",
+                      "steps": steps, "rel_err": err, "pass": bool(ok)})
+        worst = max(worst, err)
+    res = {"against": "CPU oracle (oracle/biblbm_oracle.c) on the undivided lattice", "n_slabs": world, "cases": cases, "max_rel_err": worst,
+           "tolerance": 1e-9, "pass": bool(all(c["pass"] for c in cases))} if rank == 0 else None
+    return res
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
@@ -235,12 +427,25 @@ def ours(args):
     def max_over_ranks(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        out = t.cpu().numpy()
+        return float(out[0]) if np.ndim(x) == 0 else out
 
-    nx, ny, nz = args.nx, args.ny, args.nz
+    # clocks are sampled from well before the timed region (>= 2 s) to its end
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_sampler = time.time()
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(bib, dist, torch, rank, world, local)
+        barrier()
+
+    nx, ny, nz, rb = slab_of(args, world)
     cells_local = nx * ny * nz
+    n_rbc_global = int(round(rb * world))
     lat = bib.Lattice(nx, ny, nz, 1.0, 1.0 / 3.0, periodic=(True, True, True), device=local)
     if world > 1:
         uid = [bib.comm_unique_id() if rank == 0 else None]
@@ -251,56 +456,82 @@ def ours(args):
     lat.set_option(bib.OPT_PREFETCH_FORCES, float(args.prefetch_forces))
     lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
     body = (1e-6, 0.0, 0.0)
-    n_rbc = args.rbcs                               # per GPU
-    nvert = 0
-    if n_rbc > 0:
+    nvert_global = 0
+    if n_rbc_global > 0:
         verts, tris, params, rbc_pos = load_rbc()
         sid = lat.register_shape(verts, tris)
         # every rank passes the same global particle list; the library keeps what the slab owns (+ ghosts of its neighbours)
-        lat.add_particles(sid, params, rbc_positions(rbc_pos, n_rbc * world, (nx * world, ny, nz), 0, seed=7))
-        nvert = n_rbc * verts.shape[0]
+        lat.add_particles(sid, params, rbc_positions(rbc_pos, n_rbc_global, (nx * world, ny, nz), 0, seed=7))
+        nvert_global = n_rbc_global * verts.shape[0]
     lat.sync()
 
     def step(n=1):
-        if n_rbc > 0:
+        if n_rbc_global > 0:
             lat.step(body, n=n)
         else:
             lat.collideAndStream(n)
 
-    # ---- headline: K full steps, state resident in HBM
+    K = args.steps
+
+    def timed_blocks(fn, target_s=2.0, max_blocks=60):
+        """Priming block (untimed, same call pattern), then R >= 3 back-to-back blocks of exactly K steps covering >= target_s."""
+        barrier()
+        lat.time_begin(); fn(K); est = max_over_ranks(lat.time_end())
+        reps = int(min(max_blocks, max(3, math.ceil(target_s * 1e3 / max(est, 1e-3)))))
+        out = []
+        for _ in range(reps):
+            barrier()
+            lat.time_begin()
+            fn(K)
+            ms = lat.time_end()
+            barrier()
+            out.append(max_over_ranks(ms) / K)
+        return out
+
+    # ---- headline: full steps, state resident in HBM
     step(args.warmup)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
+    while time.time() - t_sampler < 2.2:
+        time.sleep(0.05)
     l0 = lat.launches()
     t_mark0 = time.time()
-    lat.time_begin()
     w0 = time.perf_counter()
-    step(args.steps)
-    ms_dev = lat.time_end()
-    barrier()
+    blocks = timed_blocks(step, target_s=args.min_seconds)
     w1 = time.perf_counter()
     t_mark1 = time.time()
-    launches = lat.launches() - l0
-    ms_step = max_over_ranks(ms_dev) / args.steps
-    wall_ms_step = max_over_ranks((w1 - w0) * 1e3) / args.steps
+    launches_per_block = (lat.launches() - l0) / (len(blocks) + 1)
+    ms_step = float(np.median(blocks))
     clocks = sampler.stop(t_mark0, t_mark1) if rank == 0 else None
     mlups = cells_local * world / (ms_step * 1e-3) / 1e6
+    repeats = {"blocks": len(blocks), "steps_per_block": K, "ms_per_step_min": float(np.min(blocks)), "ms_per_step_max": float(np.max(blocks)),
+               "ms_per_step_median": ms_step, "spread_rel": float((np.max(blocks) - np.min(blocks)) / ms_step), "timed_seconds": float(np.sum(blocks) * K / 1e3),
+               "ms_per_step_blocks": [round(float(b), 4) for b in blocks]}
+
+    # ---- per-phase device times (phases serialised on the compute stream: an upper bound of the production step)
+    phases = None
+    if n_rbc_global > 0:
+        lat.phase_timing(True)
+        step(K)
+        lat.phase_times()                        # discard the first block (allocation of the timing events)
+        step(K)
+        pt = lat.phase_times()
+        lat.phase_timing(False)
+        names = list(pt.keys())
+        vals = max_over_ranks(np.array([pt[k] for k in names])) / K
+        phases = {k: round(float(v), 4) for k, v in zip(names, np.atleast_1d(vals))}
+        phases["note"] = ("ms per step, max over ranks, phases serialised (no force prefetch, no graphs): lattice = collide-and-stream (interior planes on "
+                          "several slabs), halo = the exchange on the communication stream beside it, halo_wait = what the compute stream still waited")
+        step(args.warmup)                        # back to the production configuration (graphs are re-captured here)
 
     # ---- dominant kernel alone (collide-and-stream), CUDA events on the launching stream
     if args.face_swap != 1:                         # default (1): the periodic-face fix-up is part of k_collide_stream and is timed with it
         lat.set_option(bib.OPT_ENVELOPE_SWAP, 0.0)  # main kernel only (the separate k_face_swap pass is timed in the full step)
-    lat.collideAndStream(2)
-    barrier()
-    lat.time_begin()
-    lat.collideAndStream(args.steps)
-    ms_kernel = max_over_ranks(lat.time_end()) / args.steps
+    lat.collideAndStream(3)
+    kblocks = timed_blocks(lambda n: lat.collideAndStream(n), target_s=min(1.0, args.min_seconds), max_blocks=20)
+    ms_kernel = float(np.median(kblocks))
     lat.set_option(bib.OPT_ENVELOPE_SWAP, 1.0)
     peak, peak_kind = measured_peaks()
     traffic = None
-    tj = ROOT / "profiles" / "r1_k_collide_stream_traffic.json"
+    tj = ROOT / "profiles" / "k_collide_stream_traffic.json"
     if tj.exists():
         t = json.loads(tj.read_text())
         if t["workload"] == [nx, ny, nz]:
@@ -308,61 +539,77 @@ def ours(args):
     achieved = LBM_BYTES_PER_CELL * cells_local / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_collide_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}; burst figure, kernel timed alone)",
-                "ms_per_launch": ms_kernel, "lbm_only_mlups": cells_local * world / (ms_kernel * 1e-3) / 1e6,
+                "ms_per_launch": ms_kernel, "ms_per_launch_min": float(np.min(kblocks)), "ms_per_launch_max": float(np.max(kblocks)),
+                "lbm_only_mlups": cells_local * world / (ms_kernel * 1e-3) / 1e6,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
+                "full_step_gbs_at_304B": LBM_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9,
+                "full_step_frac_of_measured": LBM_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9 / peak,
+                "full_step_frac_of_nominal_8TBs": LBM_BYTES_PER_CELL * cells_local / (ms_step * 1e-3) / 1e9 / 8000.0,
                 "algorithmic_bytes_per_cell": LBM_BYTES_PER_CELL, "true_bytes_per_cell": 306.0,
                 "true_bytes_note": "19 populations read + written, 1 phase byte, force-flag word; the 24 B/cell force field is read only in flagged (particle-band) cells"}
 
     # ---- IB phases alone (vertex-updates/s)
     ib = None
-    if n_rbc > 0:
-        barrier()
-        lat.time_begin()
-        for _ in range(args.steps):
-            lat.ib_step()
-        ms_ib = lat.time_end() / args.steps
-        ms_ib = max_over_ranks(ms_ib)
-        ib = {"vertex_updates_per_s": nvert * world / (ms_ib * 1e-3), "ms_per_step": ms_ib, "vertices": nvert * world,
-              "achieved_gbs_at_330B_per_vertex": IB_BYTES_PER_VERTEX * nvert * world / (ms_ib * 1e-3) / 1e9}
+    if n_rbc_global > 0:
+        lat.ib_step()
+        iblocks = timed_blocks(lambda n: [lat.ib_step() for _ in range(n)], target_s=min(0.5, args.min_seconds), max_blocks=20)
+        ms_ib = float(np.median(iblocks))
+        ib = {"vertex_updates_per_s": nvert_global / (ms_ib * 1e-3), "ms_per_step": ms_ib, "vertices": nvert_global,
+              "achieved_gbs_at_330B_per_vertex": IB_BYTES_PER_VERTEX * nvert_global / world / (ms_ib * 1e-3) / 1e9}
 
-    # ---- end to end through the C-ABI with host buffers: every step the host reads back what the reference drivers read
-    #      (vertex state for write_lightweight_particle_data / VTK, particle scalars for the volume diagnostics)
-    n_slots = lat.count()[0]
-    d2h = lat.count()[1] * 72 + n_slots * 88
-    # three sets of page-locked result buffers: two read-backs are in flight while the host consumes a third, so that the host always has
-    # one whole step queued ahead of the copy it waits for (bib_ib_results_download_async / _wait: FIFO of depth 2)
-    host_v = [torch.empty((max(1, lat.count()[1]), 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
-    host_s = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
-    checksum = 0.0
-    if n_rbc > 0:                                   # first use allocates the staging buffers and the copy stream: not part of a step
-        for k in range(2):
-            lat.results_download_async(host_v[k], host_s[k])
-        lat.results_wait(); lat.results_wait()
-    barrier()
-    e0 = time.perf_counter()
-    for it in range(args.steps):
-        step(1)
-        if n_rbc > 0:
-            if it >= 2:
-                lat.results_wait()                              # results of step it-2 are now on the host ...
-                checksum += float(host_s[(it - 2) % 3][0, 1])    # ... and are consumed (a particle volume, like the drivers print)
-            lat.results_download_async(host_v[it % 3], host_s[it % 3])
-        else:
-            lat.sync()
-    if n_rbc > 0:
-        for it in range(max(0, args.steps - 2), args.steps):
-            lat.results_wait()
-            checksum += float(host_s[it % 3][0, 1])
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - e0) * 1e3) / args.steps
-    if n_rbc > 0:                                   # bytes actually delivered per step (multi-slab: the owned particles, compacted)
-        n_del = lat.results_count()
-        d2h = n_del * (nvert // n_rbc * 72 + 88)
-    e2e = {"value": cells_local * world / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms,
-           "note": "state stays resident in HBM (the point of the design); per step the host passes the body force (24 B, by value) and "
-                   "reads all vertex states + particle scalars back into page-locked buffers (the data the reference drivers consume between steps); "
-                   "the read-backs of steps t-1 and t overlap step t+1 on a copy stream (two in flight)", "checksum": checksum}
+    # ---- end to end through the C-ABI with host buffers.
+    # e2e (headline): every step the host passes the body force and reads back the record the reference drivers write every output
+    # interval (write_lightweight_particle_data: id, centre of mass, gyration tensor, volume of every particle), evaluated on the device.
+    # e2e_all_vertices (labelled worst case): ALL vertex records + particle scalars every step (VTK / check-point data, which the
+    # drivers need every 500 - 1000 steps).
+    n_slots, n_vslots = lat.count()
+    e2e = e2e_all = None
+    step(args.warmup)
+    if n_rbc_global > 0:
+        host_l = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
+        host_v = [torch.empty((max(1, n_vslots), 9), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
+        host_s = [torch.empty((max(1, n_slots), 11), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
+
+        def e2e_run(light, total_steps):
+            chk = 0.0
+            for k in range(2):                       # first use allocates the staging buffers and the copy stream: not part of a step
+                lat.lightweight_download_async(host_l[k]) if light else lat.results_download_async(host_v[k], host_s[k])
+            lat.results_wait(); lat.results_wait()
+            step(K)                                  # priming block (graphs)
+            barrier()
+            t0 = time.perf_counter()
+            for it in range(total_steps):
+                step(1)
+                if it >= 2:
+                    lat.results_wait()                                   # results of step it-2 are now on the host ...
+                    chk += float((host_l if light else host_s)[(it - 2) % 3][0, 10 if light else 1])   # ... and are consumed (a particle volume, like the drivers print)
+                lat.lightweight_download_async(host_l[it % 3]) if light else lat.results_download_async(host_v[it % 3], host_s[it % 3])
+            for it in range(max(0, total_steps - 2), total_steps):
+                lat.results_wait()
+                chk += float((host_l if light else host_s)[it % 3][0, 10 if light else 1])
+            barrier()
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / total_steps
+            return ms, chk, lat.results_count()
+
+        n_e2e = int(max(K, min(400, math.ceil(args.min_seconds * 1e3 / ms_step))))
+        ms_l, chk_l, n_del = e2e_run(True, n_e2e)
+        e2e = {"value": cells_local * world / (ms_l * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": n_del * 88,
+               "ms_per_step": ms_l, "steps": n_e2e, "checksum": chk_l,
+               "note": "state stays resident in HBM (the point of the design); per step the host passes the body force (24 B, by value) and reads back, into "
+                       "page-locked buffers, the lightweight record of every particle this rank owns (id, centre of mass, gyration tensor, volume = what "
+                       "write_lightweight_particle_data writes; evaluated on the device), two read-backs in flight on a copy stream; wall-clock, max over ranks"}
+        ms_a, chk_a, n_del = e2e_run(False, max(K, n_e2e // 4))
+        e2e_all = {"value": cells_local * world / (ms_a * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 24,
+                   "d2h_bytes_per_step": n_del * (nvert_global // n_rbc_global * 72 + 88), "ms_per_step": ms_a, "checksum": chk_a,
+                   "note": "labelled worst case: ALL vertex records (pos, vel, force) + particle scalars of the owned particles every step (the drivers need "
+                           "these for VTK output / check-points every 500 - 1000 steps)"}
+    else:
+        barrier(); t0 = time.perf_counter()
+        for _ in range(K):
+            step(1); lat.sync()
+        barrier()
+        ms_l = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+        e2e = {"value": cells_local * world / (ms_l * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": ms_l}
 
     if rank == 0:
         cpu = None
@@ -375,29 +622,36 @@ def ours(args):
                    "lbm_only_mlups": r["lbm_only_mlups"], "ib_vertex_updates_per_s": r["vertex_updates_per_s"],
                    "single_core": {"value": r1["mlups"], "lbm_only_mlups": r1["lbm_only_mlups"], "ib_vertex_updates_per_s": r1["vertex_updates_per_s"]}}
         drv = driver_speed() if (world == 1 and not args.no_cpu_baseline) else None
-        cfg = workload_config(world) if (nx, ny, nz, args.rbcs) == (128, 1024, 1024, 1250) else {
-            "workload": f"custom ({nx * world}x{ny}x{nz}) D3Q19 ForcedPhase lattice, {n_rbc * world} RBC meshes", "parallelism": f"x-slabs x{world}"}
-        line = {"metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "ib": ib, "cpu_baseline": cpu,
-                "e2e": e2e, "driver_e2e": drv, "gpu_launches": launches, "clocks": clocks, "device_bytes": lat.device_bytes()}
+        line = {"metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K,
+                "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": (w1 - w0) * 1e3 / ((len(blocks) + 1) * K), "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "repeats": repeats, "roofline": roofline, "ib": ib, "phases_ms": phases, "parity_check": parity, "cpu_baseline": cpu,
+                "e2e": e2e, "e2e_all_vertices": e2e_all, "driver_e2e": drv, "gpu_launches": int(round(launches_per_block)), "clocks": clocks,
+                "device_bytes": lat.device_bytes()}
         print(json.dumps(line))
     lat.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["pass"]:
+        sys.exit(3)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nx", type=int, default=128)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--nx", type=int, default=128, help="weak scaling: slab width per GPU")
     ap.add_argument("--ny", type=int, default=1024)
     ap.add_argument("--nz", type=int, default=1024)
-    ap.add_argument("--rbcs", type=int, default=1250)
+    ap.add_argument("--rbcs", type=float, default=1250, help="weak scaling: RBCs per GPU")
+    ap.add_argument("--global-nx", type=int, default=256, help="strong scaling: global lattice width (split over the GPUs)")
+    ap.add_argument("--global-rbcs", type=float, default=2500, help="strong scaling: RBCs in the global lattice")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="the timed blocks of K steps are repeated until they cover this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-slab parity gate")
     ap.add_argument("--overlap-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_OVERLAP_FORCES (experiments)")
     ap.add_argument("--prefetch-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_PREFETCH_FORCES (experiments)")
     ap.add_argument("--face-swap", type=int, default=1, choices=[0, 1, 2], help="BIB_OPT_FUSED_FACE_SWAP (experiments)")

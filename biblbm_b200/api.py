@@ -23,8 +23,8 @@ SYMBOLS = [
     "bib_velocity_download", "bib_velocity_upload", "bib_velocity_extrapolate_plane", "bib_collide_and_stream", "bib_ib_shape_register", "bib_ib_shape_info", "bib_ib_shape_connectivity",
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload", "bib_ib_vertex_forces_preload",
-    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_results_wait", "bib_ib_results_count", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
-    "bib_kernel_launch_count", "bib_device_memory_bytes",
+    "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_lightweight_download_async", "bib_ib_results_wait", "bib_ib_results_count", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
+    "bib_kernel_launch_count", "bib_device_memory_bytes", "bib_phase_timing", "bib_phase_times",
 ]
 
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES, OPT_PREFETCH_FORCES = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -300,6 +300,10 @@ class Lattice:
         """Non-blocking read-back of all vertex records and particle scalars into page-locked arrays; see results_wait()."""
         _check(self.lib.bib_ib_results_download_async(self.h, _dptr(out_vertices), _dptr(out_scalars)))
 
+    def lightweight_download_async(self, out_records):
+        """Non-blocking read-back of the lightweight record {id, com, gyration tensor, volume} of every owned particle ([n][11], page-locked)."""
+        _check(self.lib.bib_ib_lightweight_download_async(self.h, _dptr(out_records)))
+
     def results_wait(self):
         _check(self.lib.bib_ib_results_wait(self.h))
 
@@ -336,6 +340,18 @@ class Lattice:
         ms = C.c_float(0)
         _check(self.lib.bib_time_end(self.h, C.byref(ms)))
         return ms.value
+
+    PHASES = ["interpolate", "exchange_vel", "force_reset", "forces", "exchange_force", "spread", "move", "exchange_pos", "voxelize",
+              "lattice_boundary", "lattice", "halo_wait", "halo", "walls"]
+
+    def phase_timing(self, enable=True):
+        _check(self.lib.bib_phase_timing(self.h, int(bool(enable))))
+
+    def phase_times(self) -> dict:
+        """Device milliseconds per phase, summed over the steps since the last call (see include/biblbm_b200.h, BIB_PHASE_*)."""
+        ms = (C.c_double * 14)()
+        _check(self.lib.bib_phase_times(self.h, ms, 14))
+        return dict(zip(self.PHASES, [float(v) for v in ms]))
 
     def launches(self) -> int:
         n = C.c_longlong(0)

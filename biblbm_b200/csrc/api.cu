@@ -20,6 +20,17 @@ bool bib_cuda_ok(cudaError_t e, const char* what) {
 void ms_destroy(bib_domain* d);
 int ms_check_overflow(bib_domain* d);
 
+// Per-phase timing: an event at the END of every phase; the time since the previous mark on the same stream belongs to that phase.
+void pt_mark(bib_domain* d, int phase, cudaStream_t st) {
+    if (!d->pt_on) return;
+    cudaEvent_t e = nullptr;
+    if (!d->pt_pool.empty()) { e = d->pt_pool.back(); d->pt_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+    const bool comm = st != nullptr && st == d->comm_stream;
+    cudaEventRecord(e, comm ? d->comm_stream : d->stream);
+    (comm ? d->pt_comm_marks : d->pt_marks).emplace_back(phase, e);
+}
+
 // in-process slab groups (group.cu): the head handle's version of each entry point
 int group_create(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3], int n_slabs, const int* devices, bib_domain** out);
 int group_destroy(bib_domain* head);
@@ -201,6 +212,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->vfrc) cudaFree(d->vfrc);
     if (d->vfrc_sum) cudaFree(d->vfrc_sum);
     if (d->pstate) cudaFree(d->pstate);
+    for (void* q : {(void*)d->role_all, (void*)d->gid_all, (void*)d->seen_all, (void*)d->vslot, (void*)d->slot_nv, (void*)d->slot_fv}) if (q) cudaFree(q);
     for (ShapeDev& s : d->shapes) {
         void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts, s.rest_radial};
         for (void* p : ptrs) if (p) cudaFree(p);
@@ -519,6 +531,12 @@ int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scal
     if (!vertices9 || !scalars11) { bib_set_error("results_download_async: null argument"); return 0; }
     return ib_results_download_async(d, vertices9, scalars11);
 }
+int bib_ib_lightweight_download_async(bib_domain* d, double* records11) {
+    BIB_HEAD_UNSUPPORTED(d, "lightweight_download_async (use the per-slab handles of bib_domain_slab)");
+    BIB_ENTER_RO(d);
+    if (!records11) { bib_set_error("lightweight_download_async: null argument"); return 0; }
+    return ib_results_download_async(d, nullptr, records11);
+}
 int bib_ib_results_wait(bib_domain* d) { BIB_HEAD_UNSUPPORTED(d, "results_wait"); BIB_ENTER_RO(d); return ib_results_wait(d); }
 int bib_ib_results_count(bib_domain* d, int* n_particles) {
     BIB_HEAD_UNSUPPORTED(d, "results_count");
@@ -536,8 +554,9 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
     // (FP64-bound) while the collide-and-stream of step t (HBM-bound) runs, into a second force array, so that vfrc keeps holding
     // "the forces of the last completed step" for every reader. (b) Otherwise / for the first step: on the second stream beside the
     // band velocity and the interpolation of the same step, joined before the spread.
-    const bool independent = ib_forces_independent_of_interpolation(d);
+    const bool independent = ib_forces_independent_of_interpolation(d) && !d->pt_on;      // phase timing: every phase on the compute stream
     const bool prefetch = d->prefetch_forces && d->overlap_forces && independent;
+    pt_mark(d, PT_BEGIN);
     const bool have = prefetch && d->forces_ready && d->vfrc_next && d->vfrc_next_cap == d->cap_vertices;
     d->forces_ready = false;
     if (have) std::swap(d->vfrc, d->vfrc_next);
@@ -549,6 +568,7 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         BIB_CHECK(cudaEventRecord(d->ev_forces, d->comm_stream));
     }
     if (!ib_interpolate(d)) return 0;
+    pt_mark(d, PT_X_VEL);
     // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
     if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {
         if (!ib_band_reset(d, body_fx, body_fy, body_fz)) return 0;
@@ -556,6 +576,7 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         if (!lbm_launch_set_external(d, box, body_fx, body_fy, body_fz)) return 0;
         d->force_is_body = true; d->force_body[0] = body_fx; d->force_body[1] = body_fy; d->force_body[2] = body_fz;
     }
+    pt_mark(d, PT_RESET);
     if (have) {
         if (!ib_spread(d)) return 0;
     } else if (fork) {
@@ -563,6 +584,7 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         if (!ib_spread(d)) return 0;
     } else if (!ib_forces_and_spread(d)) return 0;
     if (!ib_move_and_voxelize(d)) return 0;
+    pt_mark(d, PT_VOXELIZE);
     d->vel_full_valid = false;
     if (prefetch) {
         cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
@@ -612,7 +634,7 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
         d->last_body[0] = body_fx; d->last_body[1] = body_fy; d->last_body[2] = body_fz;
     }
     // capture when this call is long enough to pay for it, or when a one-step-per-call caller has kept the configuration unchanged for a while
-    if (d->use_graph && d->n_ranks == 1 && !have_graphs && (n_steps >= 6 || d->plain_steps_since_dirty >= 4)) {
+    if (d->use_graph && !d->pt_on && d->n_ranks == 1 && !have_graphs && (n_steps >= 6 || d->plain_steps_since_dirty >= 4)) {
         step_graphs_destroy(d);
         for (; d->plain_steps_since_dirty < 2 && s < n_steps; ++s) {          // reach the steady state first (allocations, masks, flags)
             if (!step_once(d, body_fx, body_fy, body_fz)) return 0;
@@ -652,7 +674,7 @@ int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int 
             cudaGetLastError();
         }
     }
-    if (d->use_graph && d->n_ranks == 1 && d->sg[0].exec && d->sg[1].exec && !d->graph_dirty &&
+    if (d->use_graph && !d->pt_on && d->n_ranks == 1 && d->sg[0].exec && d->sg[1].exec && !d->graph_dirty &&
         d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz) {
         for (; s < n_steps; ++s) {
             const int k = step_graph_matches(d, d->sg[0]) ? 0 : (step_graph_matches(d, d->sg[1]) ? 1 : -1);
@@ -696,6 +718,35 @@ int bib_time_end(bib_domain* d, float* milliseconds) {
     BIB_CHECK(cudaEventRecord(d->ev1, d->stream));
     BIB_CHECK(cudaEventSynchronize(d->ev1));
     BIB_CHECK(cudaEventElapsedTime(milliseconds, d->ev0, d->ev1));
+    return 1;
+}
+int group_phase_timing(bib_domain* h, int enable);
+int group_phase_times(bib_domain* h, double* ms, int n);
+int bib_phase_timing(bib_domain* d, int enable) {
+    if (d && d->is_head) return group_phase_timing(d, enable);
+    BIB_ENTER(d);
+    d->pt_on = enable != 0;
+    for (auto* v : {&d->pt_marks, &d->pt_comm_marks}) { for (auto& m : *v) d->pt_pool.push_back(m.second); v->clear(); }
+    return 1;
+}
+int bib_phase_times(bib_domain* d, double* milliseconds, int n) {
+    if (d && d->is_head && milliseconds) return group_phase_times(d, milliseconds, n);
+    BIB_ENTER_RO(d);
+    if (!milliseconds || n < PT_COUNT) { bib_set_error("phase_times: need room for 14 doubles"); return 0; }
+    for (int k = 0; k < n; ++k) milliseconds[k] = 0.0;
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    BIB_CHECK(cudaStreamSynchronize(d->comm_stream));
+    for (auto* v : {&d->pt_marks, &d->pt_comm_marks}) {
+        for (size_t k = 1; k < v->size(); ++k) {
+            const int ph = (*v)[k].first;
+            if (ph < 0) continue;                       // a BEGIN mark: nothing is attributed to the gap before it
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, (*v)[k - 1].second, (*v)[k].second) == cudaSuccess) milliseconds[ph] += t;
+        }
+        for (auto& m : *v) d->pt_pool.push_back(m.second);
+        v->clear();
+    }
+    cudaGetLastError();
     return 1;
 }
 int bib_kernel_launch_count(bib_domain* d, long long* launches) {

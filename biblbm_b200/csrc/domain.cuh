@@ -98,7 +98,7 @@ struct ResSlot {
     cudaEvent_t packed = nullptr, copied = nullptr;
     double* host_v = nullptr; double* host_s = nullptr;
     int* count_host = nullptr;            // page-locked: number of owned particles (multi-slab)
-    bool compact = false; int bound_used = 0; long long bound_used_v = 0;
+    bool compact = false, light = false; int bound_used = 0; long long bound_used_v = 0;
 };
 
 // Several slabs owned by ONE host process (bib_domain_create_multi): the slabs are stepped by one worker thread each, SPMD like the
@@ -151,6 +151,10 @@ struct bib_domain {
     double* vfrc_next = nullptr; long long vfrc_next_cap = 0;
     bool vfrc_preloaded = false;          // bib_ib_vertex_forces_preload: the next force evaluation adds to vfrc instead of starting from zero
     long long launches = 0;
+    // per-phase device timing (bib_phase_timing): CUDA events recorded at the END of each phase of a step; read back by bib_phase_times
+    bool pt_on = false;
+    std::vector<std::pair<int, cudaEvent_t>> pt_marks, pt_comm_marks;      // compute stream / communication stream
+    std::vector<cudaEvent_t> pt_pool;
     // CUDA graph of two consecutive whole steps (bib_step; the A/B population buffers and the band masks alternate with period 2)
     StepGraph sg[2];                      // the two steps of a period, one CUDA graph each (bib_step)
     bool graph_dirty = true; int use_graph = 1; double graph_body[3] = {0, 0, 0};
@@ -213,6 +217,10 @@ struct bib_domain {
 };
 
 void bib_set_error(const std::string& msg);
+// phase ids of bib_phase_times (include/biblbm_b200.h)
+enum { PT_BEGIN = -1, PT_INTERPOLATE = 0, PT_X_VEL = 1, PT_RESET = 2, PT_FORCES = 3, PT_X_FORCE = 4, PT_SPREAD = 5, PT_MOVE = 6, PT_X_POS = 7, PT_VOXELIZE = 8,
+       PT_LBM_BOUNDARY = 9, PT_LBM = 10, PT_HALO_WAIT = 11, PT_HALO = 12, PT_WALLS = 13, PT_COUNT = 14 };
+void pt_mark(bib_domain* d, int phase, cudaStream_t st = nullptr);
 bool bib_cuda_ok(cudaError_t e, const char* what);
 
 #define BIB_CHECK(call) do { if (!bib_cuda_ok((call), #call)) return 0; } while (0)

@@ -387,3 +387,10 @@ int group_memory_bytes(bib_domain* h, long long* bytes) {
 }
 bib_domain* group_slab_of(bib_domain* h, int r) { G(h); return (r >= 0 && r < g->n) ? g->slab[r] : nullptr; }
 int group_size(bib_domain* h) { return h->group->n; }
+int group_phase_timing(bib_domain* h, int enable) { G(h); return group_each(g, [&](int r) { return bib_phase_timing(g->slab[r], enable); }); }
+int group_phase_times(bib_domain* h, double* ms, int n) {      // max over the slabs, phase by phase
+    G(h);
+    if (n < PT_COUNT) { bib_set_error("phase_times: need room for 14 doubles"); return 0; }
+    for (int k = 0; k < n; ++k) ms[k] = 0.0;
+    return group_each(g, [&](int r) { double t[PT_COUNT]; if (!bib_phase_times(g->slab[r], t, PT_COUNT)) return 0; for (int k = 0; k < PT_COUNT; ++k) ms[k] = std::max(ms[k], t[k]); return 1; });
+}

@@ -1074,6 +1074,12 @@ __global__ void k_zero_ghost_forces(const int* __restrict__ role, const int* __r
     if (v >= nvert || role[vslot[v]] == 1) return;
     vfrc[v] = 0.0; vfrc[cap + v] = 0.0; vfrc[2 * cap + v] = 0.0;
 }
+__global__ void k_fill_slots(int first_particle, int count, int nv, long long first_vertex, int* role, int* gid, int* slot_nv, long long* slot_fv) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int s = first_particle + k;
+    role[s] = 1; gid[s] = s; slot_nv[s] = nv; slot_fv[s] = first_vertex + (long long)k * nv;
+}
 __global__ void k_fill_vobj(int* vobj, long long first_vertex, int nv, int first_particle, long long n) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t < n) vobj[first_vertex + t] = first_particle + (int)(t / nv);
@@ -1685,7 +1691,7 @@ static int grow_particles(bib_domain* d, long long need_v, int need_p) {
         if (d->pstate) BIB_CHECK(cudaMemcpyAsync(ns, d->pstate, (size_t)d->n_particles * 11 * sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
         BIB_CHECK(cudaStreamSynchronize(d->stream));
         if (d->pstate) cudaFree(d->pstate);
-        if (d->n_ranks > 1) {          // multi-slab slot tables
+        {                              // slot tables (one slot per resident particle; on a single slab slot == particle, all owned)
             int *nr, *ng, *nn; long long* nf; uint8_t* nsn;
             BIB_CHECK(cudaMalloc(&nr, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMalloc(&ng, (size_t)cap * sizeof(int))); BIB_CHECK(cudaMalloc(&nn, (size_t)cap * sizeof(int)));
             BIB_CHECK(cudaMalloc(&nf, (size_t)cap * sizeof(long long))); BIB_CHECK(cudaMalloc(&nsn, 2 * (size_t)cap));
@@ -1828,6 +1834,8 @@ int ib_particles_add(bib_domain* d, int type, int shape_id, const double* params
     d->groups.push_back(gr);
     d->n_particles += n; d->n_vertices += nvtot;
     d->band_pos_valid = false;
+    k_fill_slots<<<(n + 255) / 256, 256, 0, d->stream>>>(gr.first_particle, n, s.nv, gr.first_vertex, d->role_all, d->gid_all, d->slot_nv, d->slot_fv);
+    d->launches++;
     // ParticleBase3D::update() at construction + add_particle's map_center_of_mass_to_periodic_grid (ImmersedBoundaryDynamics.hh:500-525)
     return launch_update(d, gr, 0);
 }
@@ -1857,6 +1865,8 @@ int ib_rigid_add(bib_domain* d, int shape_id, const double* inertia9, double sha
     BIB_CHECK(cudaStreamSynchronize(d->stream));
     d->groups.push_back(gr);
     d->n_particles += n; d->n_vertices += nvtot;
+    k_fill_slots<<<(n + 255) / 256, 256, 0, d->stream>>>(gr.first_particle, n, s.nv, gr.first_vertex, d->role_all, d->gid_all, d->slot_nv, d->slot_fv);
+    d->launches++;
     return launch_update(d, gr, 0);
 }
 int ib_rigid_download(bib_domain* d, int first, int count, double* state19) {
@@ -1950,6 +1960,7 @@ int ib_interpolate(bib_domain* d) {
     k_interpolate<true><<<grid, bs, 0, d->stream>>>(make_geo(d), d->f[d->cur], d->force, d->vel, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
     d->launches++;
     BIB_CHECK(cudaGetLastError());
+    pt_mark(d, PT_INTERPOLATE);
     if (d->ms && !ms_exchange_velocities(d)) return 0;     // owners add the partial sums of the neighbouring slabs
     return 1;
 }
@@ -2122,6 +2133,7 @@ int ib_spread(bib_domain* d) {
     // remember which masks describe the cells written now; a second spread before any reset, or one without masks of the current positions: unknown
     d->spread_band = (d->spread_band == -1 && d->band_pos_valid && d->band_mask && d->band_valid[d->band_cur]) ? d->band_cur : -2;
     if (d->ms && !ms_exchange_forces(d)) return 0;         // ghost copies receive the owner's vertex forces
+    pt_mark(d, PT_X_FORCE);
     if (d->deterministic_spread) d->fflag_valid = false;
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
     else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
@@ -2136,10 +2148,15 @@ int ib_spread(bib_domain* d) {
     }
     d->launches++;
     BIB_CHECK(cudaGetLastError());
+    pt_mark(d, PT_SPREAD);
     return 1;
 }
 
-int ib_forces_and_spread(bib_domain* d) { return ib_forces(d, d->stream) && ib_spread(d); }
+int ib_forces_and_spread(bib_domain* d) {
+    if (!ib_forces(d, d->stream)) return 0;
+    pt_mark(d, PT_FORCES);
+    return ib_spread(d);
+}
 
 // Function attributes belong to the CURRENT device: every device a domain lives on needs the opt-in above 48 KB of dynamic shared
 // memory (k_spread_tile: 72 KB tile; k_rbc_forces_elem: vertex positions of up to RF_THREADS*RF_VPT_MAX vertices + one element chunk).
@@ -2177,7 +2194,9 @@ int ib_force_accumulate(bib_domain* d, int mode) {
 
 int ib_move_and_voxelize(bib_domain* d) {
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;
+    pt_mark(d, PT_MOVE);
     if (d->ms && !ms_exchange_positions(d)) return 0;      // refresh ghosts / hand particles over before voxelizing
+    pt_mark(d, PT_X_POS);
     for (const ParticleGroup& gr : d->groups) {
         const ShapeDev& s = d->shapes[gr.shape];
         const long long n = (long long)gr.count * s.nt;
@@ -2290,6 +2309,28 @@ __global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, 
     }
     if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
 }
+// write_lightweight_particle_data (src/fsi/DeformableParticle3D.hh:318-333, compute_tensor_of_gyration :110-125): per particle
+// {global id, centre of mass[3], gyration tensor xx xy xz yy yz zz, volume}. One thread per listed slot, vertices summed in order
+// (the reference's sequential sum, bit for bit).
+__global__ void __launch_bounds__(64) k_lightweight(double* __restrict__ out, const int* __restrict__ list, const int* __restrict__ count, int n_slots,
+                                                    const int* __restrict__ gid, const int* __restrict__ slot_nv, const long long* __restrict__ slot_fv,
+                                                    const double* __restrict__ vpos, const double* __restrict__ pstate, long long cap_v) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (count ? *count : n_slots)) return;
+    const int s = list ? list[j] : j;
+    const double* st = pstate + (long long)s * 11;
+    const int nv = slot_nv[s];
+    const long long fv = slot_fv[s];
+    double A[6] = {0, 0, 0, 0, 0, 0};
+    for (int v = 0; v < nv; ++v) {
+        const double r[3] = {vpos[fv + v] - st[2], vpos[cap_v + fv + v] - st[3], vpos[2 * cap_v + fv + v] - st[4]};
+        A[0] += r[0] * r[0]; A[1] += r[0] * r[1]; A[2] += r[0] * r[2]; A[3] += r[1] * r[1]; A[4] += r[1] * r[2]; A[5] += r[2] * r[2];
+    }
+    double* o = out + (long long)j * 11;
+    o[0] = (double)gid[s]; o[1] = st[2]; o[2] = st[3]; o[3] = st[4];
+    for (int k = 0; k < 6; ++k) o[4 + k] = A[k] / (double)nv;
+    o[10] = st[1];
+}
 // Read-back that overlaps the following steps: the fsi::Vertex records and the particle scalars are packed on the compute stream into
 // a staging buffer; a second stream copies them to the caller's page-locked buffers while the compute stream carries on. Up to
 // RES_DEPTH read-backs are in flight (one staging buffer each); ib_results_wait completes the OLDEST one. Two in flight let a caller
@@ -2304,27 +2345,29 @@ static int res_complete_oldest(bib_domain* d) {
         n = r.count_host[0];
         const long long nvert = r.count_host[1];
         const int got = r.bound_used; const long long got_v = r.bound_used_v;
-        if (n > got || nvert > got_v) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
+        if (n > got || (!r.light && nvert > got_v)) {       // more particles are owned than the prefix covered (ownership moved towards this slab): fetch the rest now
             const double* stage_v = (const double*)r.dev; const double* stage_s = (const double*)((const char*)r.dev + r.vb);
-            if (nvert > got_v) BIB_CHECK(cudaMemcpyAsync(r.host_v + (size_t)got_v * 9, stage_v + (size_t)got_v * 9, (size_t)(nvert - got_v) * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
+            if (!r.light && nvert > got_v) BIB_CHECK(cudaMemcpyAsync(r.host_v + (size_t)got_v * 9, stage_v + (size_t)got_v * 9, (size_t)(nvert - got_v) * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
             if (n > got) BIB_CHECK(cudaMemcpyAsync(r.host_s + (size_t)got * 11, stage_s + (size_t)got * 11, (size_t)(n - got) * 11 * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
             BIB_CHECK(cudaStreamSynchronize(d->copy_stream));
         }
         d->res_bound = std::min(d->n_particles, n + std::max(8, n / 64));     // ownership changes by a few particles per step at most
-        d->res_bound_v = std::min(d->n_vertices, nvert + std::max<long long>(8 * 1024, nvert / 64));
+        if (!r.light) d->res_bound_v = std::min(d->n_vertices, nvert + std::max<long long>(8 * 1024, nvert / 64));
     }
     d->res_last_count = n;
     d->res_tail = (d->res_tail + 1) % RES_DEPTH; d->res_n--;
     return 1;
 }
+// v9 == NULL: the lightweight records only (s11 then receives {id, com, gyration, volume} per owned particle instead of the cached scalars)
 int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
+    const bool light = v9 == nullptr;
     cudaPointerAttributes a0, a1;
-    const bool pinned = cudaPointerGetAttributes(&a0, v9) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+    const bool pinned = (light || (cudaPointerGetAttributes(&a0, v9) == cudaSuccess && a0.type == cudaMemoryTypeHost)) &&
                         cudaPointerGetAttributes(&a1, s11) == cudaSuccess && a1.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (!pinned) { bib_set_error("results_download_async: both host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)"); return 0; }
+    if (!pinned) { bib_set_error("results_download_async: the host buffers must be page-locked (cudaHostAlloc / cudaHostRegister)"); return 0; }
     if (!d->copy_stream) BIB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));   // (a high-priority stream was measured: no difference)
-    const size_t vb = (size_t)d->n_vertices * 9 * sizeof(double), sb = (size_t)d->n_particles * 11 * sizeof(double);
+    const size_t vb = light ? 0 : (size_t)d->n_vertices * 9 * sizeof(double), sb = (size_t)d->n_particles * 11 * sizeof(double);
     if (vb + sb == 0) return 1;
     if (d->res_n == RES_DEPTH && !res_complete_oldest(d)) return 0;        // every staging buffer is busy: finish the oldest read-back first
     ResSlot& r = d->res[d->res_head];
@@ -2340,7 +2383,7 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         BIB_CHECK(cudaMalloc(&r.dev, vb + sb));
         r.bytes = vb + sb; d->bytes += (long long)(vb + sb);
     }
-    r.vb = vb; r.host_v = v9; r.host_s = s11; r.compact = false; r.bound_used = 0; r.bound_used_v = 0;
+    r.vb = vb; r.host_v = v9; r.host_s = s11; r.compact = false; r.light = light; r.bound_used = 0; r.bound_used_v = 0;
     double* stage_v = (double*)r.dev; double* stage_s = (double*)((char*)r.dev + vb);
     if (d->ms) {
         // multi-slab: the owned particles, compacted in slot order (vertex records back to back, whatever the particles' vertex counts)
@@ -2353,13 +2396,14 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         }
         int* count = d->res_list + (size_t)d->res_head * (2 * (size_t)cap + 2); int* list = count + 2; int* voff = list + cap;
         k_results_list<<<1, 1024, 0, d->stream>>>(d->role_all, d->slot_nv, cap, list, voff, count);
-        k_pack_slots<<<cap, 128, 0, d->stream>>>(stage_v, stage_s, list, voff, count, d->slot_nv, d->slot_fv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
+        if (light) k_lightweight<<<(cap + 63) / 64, 64, 0, d->stream>>>(stage_s, list, count, cap, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices);
+        else k_pack_slots<<<cap, 128, 0, d->stream>>>(stage_v, stage_s, list, voff, count, d->slot_nv, d->slot_fv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
         d->launches += 2;
         BIB_CHECK(cudaGetLastError());
         BIB_CHECK(cudaEventRecord(r.packed, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));
         size_t nb = (size_t)std::min(d->res_bound, cap);
-        size_t nbv = (size_t)std::min(d->res_bound_v, d->n_vertices);
+        size_t nbv = light ? 0 : (size_t)std::min(d->res_bound_v, d->n_vertices);
         if (const char* e = getenv("BIB_RESULTS_BOUND")) {     // tests: force the remainder path
             nb = (size_t)std::max(0, std::min(atoi(e), cap));
             nbv = std::min<size_t>(nbv, nb * (size_t)(d->msv[0] ? d->msv[0]->nv : 0));
@@ -2374,7 +2418,8 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
             k_pack_vertices<<<grid, 256, 0, d->stream>>>(stage_v, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
             d->launches++;
         }
-        if (sb) BIB_CHECK(cudaMemcpyAsync(stage_s, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
+        if (sb && light) { k_lightweight<<<(d->n_particles + 63) / 64, 64, 0, d->stream>>>(stage_s, nullptr, nullptr, d->n_particles, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices); d->launches++; }
+        else if (sb) BIB_CHECK(cudaMemcpyAsync(stage_s, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
         BIB_CHECK(cudaEventRecord(r.packed, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));
         if (vb) BIB_CHECK(cudaMemcpyAsync(v9, stage_v, vb, cudaMemcpyDeviceToHost, d->copy_stream));

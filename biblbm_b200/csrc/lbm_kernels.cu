@@ -758,26 +758,37 @@ int lbm_launch_collide_stream(bib_domain* d) {
         launch_main(d, p, d->nx, d->stream);
         launch_faces(d, p, 63, 0, d->stream);
         BIB_CHECK(cudaGetLastError());
+        pt_mark(d, PT_LBM);
         d->cur = 1 - d->cur;
         if (d->n_ranks > 1 && !comm_halo_exchange(d, d->stream)) return 0;
-        return lbm_apply_walls(d) && lbm_apply_guo(d);      // level-0, then level-1 internal processors run after streaming (and after the halo is in place)
+        if (d->n_ranks > 1) pt_mark(d, PT_HALO_WAIT);
+        const int okw = lbm_apply_walls(d) && lbm_apply_guo(d);
+        pt_mark(d, PT_WALLS);
+        return okw;      // level-0, then level-1 internal processors run after streaming (and after the halo is in place)
     }
     LbmParams pb = p; pb.x_first = 0; pb.x_stride = d->nx - 1;
     launch_main(d, pb, 2, d->stream);
     launch_faces(d, p, 63, 1, d->stream);                   // every periodic-face fix-up of the boundary planes precedes the exchange
+    pt_mark(d, PT_LBM_BOUNDARY);
     BIB_CHECK(cudaEventRecord(d->ev_compute, d->stream));
     BIB_CHECK(cudaStreamWaitEvent(d->comm_stream, d->ev_compute, 0));
     d->cur = 1 - d->cur;
+    pt_mark(d, PT_BEGIN, d->comm_stream);
     if (!comm_halo_exchange(d, d->comm_stream)) return 0;
+    pt_mark(d, PT_HALO, d->comm_stream);
     BIB_CHECK(cudaEventRecord(d->ev_halo, d->comm_stream));
     d->cur = 1 - d->cur;
     LbmParams pi = p; pi.x_first = 1; pi.x_stride = 1;
     launch_main(d, pi, d->nx - 2, d->stream);
     launch_faces(d, p, 60, 2, d->stream);                   // y and z faces of the interior planes
     BIB_CHECK(cudaGetLastError());
+    pt_mark(d, PT_LBM);
     d->cur = 1 - d->cur;
     BIB_CHECK(cudaStreamWaitEvent(d->stream, d->ev_halo, 0));
-    return lbm_apply_walls(d) && lbm_apply_guo(d);
+    pt_mark(d, PT_HALO_WAIT);
+    const int okw = lbm_apply_walls(d) && lbm_apply_guo(d);
+    pt_mark(d, PT_WALLS);
+    return okw;
 }
 
 static bool wall_box(const bib_domain* d, const int box[6], int dir) {

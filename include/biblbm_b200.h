@@ -198,6 +198,12 @@ int bib_ib_particle_scalars_download(bib_domain* d, int first_particle, int coun
  * runs on its own stream while later steps execute. Up to two read-backs may be in flight (different host buffers); a third call
  * first completes the oldest. bib_ib_results_wait() completes the OLDEST read-back in flight; its buffers may be read afterwards. */
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11);
+/* The record write_lightweight_particle_data writes per particle (src/fsi/DeformableParticle3D.hh:318-333): records11 = {global particle
+ * id, centre of mass[3], tensor of gyration xx xy xz yy yz zz (:110-125), volume}, evaluated on the device for every particle this slab
+ * owns, delivered through the same FIFO as bib_ib_results_download_async (bib_ib_results_wait / _count apply): 88 B per particle instead
+ * of the 56 kB of its vertex records -- what a driver needs every output interval; full vertex records are needed for VTK output and
+ * check-points only (progs/rbc_in_shear/rbc_in_shear.cpp:157-181). */
+int bib_ib_lightweight_download_async(bib_domain* d, double* records11);
 int bib_ib_results_wait(bib_domain* d);
 /* On a multi-slab domain the slot arrays are sized for the worst case; the asynchronous read-back therefore delivers only the particles
  * this slab OWNS (what a rank of the reference writes), compacted on the device in ascending slot order (ids: bib_ib_local_slots, role 1),
@@ -225,6 +231,15 @@ int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_12
 int bib_sync(bib_domain* d);
 int bib_time_begin(bib_domain* d);                 /* records a CUDA event on the domain's stream */
 int bib_time_end(bib_domain* d, float* milliseconds);  /* records a second event, waits, returns elapsed device time */
+/* Per-phase device times of the steps issued since the last call (or since bib_phase_timing(d, 1)): milliseconds[14], summed over those
+ * steps, indexed by the BIB_PHASE_* ids. While enabled every phase runs on the compute stream (no force prefetch / overlap, no step graph),
+ * so the sum is an upper bound of the production step; the halo exchange itself (BIB_PHASE_HALO) runs beside BIB_PHASE_LATTICE on the
+ * communication stream, BIB_PHASE_HALO_WAIT is what the compute stream still had to wait for it. */
+enum { BIB_PHASE_INTERPOLATE = 0, BIB_PHASE_EXCHANGE_VEL = 1, BIB_PHASE_FORCE_RESET = 2, BIB_PHASE_FORCES = 3, BIB_PHASE_EXCHANGE_FORCE = 4,
+       BIB_PHASE_SPREAD = 5, BIB_PHASE_MOVE = 6, BIB_PHASE_EXCHANGE_POS = 7, BIB_PHASE_VOXELIZE = 8, BIB_PHASE_LATTICE_BOUNDARY = 9,
+       BIB_PHASE_LATTICE = 10, BIB_PHASE_HALO_WAIT = 11, BIB_PHASE_HALO = 12, BIB_PHASE_WALLS = 13, BIB_PHASE_COUNT = 14 };
+int bib_phase_timing(bib_domain* d, int enable);
+int bib_phase_times(bib_domain* d, double* milliseconds, int n);
 int bib_kernel_launch_count(bib_domain* d, long long* launches);   /* kernels launched by this library on this domain so far */
 int bib_device_memory_bytes(bib_domain* d, long long* bytes);
 

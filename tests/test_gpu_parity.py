@@ -718,6 +718,32 @@ def test_band_reset_survives_extra_interpolations(rbc):
         assert np.array_equal(lat.download()[..., 19:22], np.broadcast_to(np.asarray(g["body"], dtype=float), F.shape))
 
 
+def test_lightweight_record_matches_reference_formula(rbc):
+    """bib_ib_lightweight_download_async: {id, centre of mass, tensor of gyration, volume} per particle as write_lightweight computes them
+    (src/fsi/DeformableParticle3D.hh:110-125,318-333: sequential sums over the vertices, divided by the vertex count)."""
+    import torch
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    lat = run_ib_case(g, shape, params, deterministic=False)
+    lat.step(g["body"], n=7)
+    n_p, nv = g["vert_init"].shape[:2]
+    rec = torch.empty((n_p, 11), dtype=torch.float64, pin_memory=True).numpy()
+    lat.lightweight_download_async(rec)
+    lat.results_wait()
+    assert lat.results_count() == n_p
+    v = lat.vertices().reshape(n_p, nv, 9)
+    st = lat.particle_scalars()
+    for p in range(n_p):
+        com = st[p, 2:5]
+        A = np.zeros(6)
+        for k in range(nv):                    # the reference's order of summation
+            r = v[p, k, :3] - com
+            A += np.array([r[0] * r[0], r[0] * r[1], r[0] * r[2], r[1] * r[1], r[1] * r[2], r[2] * r[2]])
+        want = np.concatenate([[p], com, A / nv, [st[p, 1]]])
+        assert np.array_equal(rec[p, :4], want[:4]) and rec[p, 10] == want[10]
+        assert np.allclose(rec[p, 4:10], want[4:10], rtol=1e-13, atol=0)
+
+
 def test_two_devices_in_one_process(rbc):
     """Function attributes (dynamic shared memory opt-in of k_spread_tile / k_rbc_forces_elem) are per device: a second domain on
     another GPU of the same process must step like the first. Needs 2 GPUs."""
