@@ -14,7 +14,8 @@ import pathlib
 import numpy as np
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libbiblbm_b200.so"
+import os as _os
+LIB_PATH = pathlib.Path(_os.environ["BIB_LIB"]) if _os.environ.get("BIB_LIB") else _HERE / "libbiblbm_b200.so"      # BIB_LIB: experiments with alternative builds
 
 # every symbol include/biblbm_b200.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
@@ -45,7 +46,8 @@ def load_library():
     if _lib is not None:
         return _lib
     from . import build as _build
-    _build.build()
+    if not _os.environ.get("BIB_LIB"):
+        _build.build()
     lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
     lib.bib_last_error.restype = C.c_char_p
     for name in SYMBOLS:

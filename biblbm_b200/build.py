@@ -45,11 +45,11 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in [CSRC / s for s in SOURCES] + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, fmad: bool = False, out: pathlib.Path | None = None) -> pathlib.Path:
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-           "-Xcompiler", "-fPIC", "-shared", *nccl_include_flags(), "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl", "-lpthread"]
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=true" if fmad else "-fmad=false",
+           "-Xcompiler", "-fPIC", "-shared", *nccl_include_flags(), "-o", str(out or LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl", "-lpthread", "-Xlinker", "--no-undefined"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout, r.stderr, file=sys.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -74,6 +74,8 @@ int group_launch_count(bib_domain* h, long long* launches);
 int group_memory_bytes(bib_domain* h, long long* bytes);
 bib_domain* group_slab_of(bib_domain* h, int r);
 int group_size(bib_domain* h);
+int group_phase_timing(bib_domain* h, int enable);
+int group_phase_times(bib_domain* h, double* ms, int n);
 #define BIB_HEAD(d, call) do { if ((d) && (d)->is_head) return (call); } while (0)
 #define BIB_HEAD_UNSUPPORTED(d, what) do { if ((d) && (d)->is_head) { bib_set_error(what ": not available on a multi-slab (bib_domain_create_multi) handle"); return 0; } } while (0)
 
@@ -226,6 +228,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->ev_compute) cudaEventDestroy(d->ev_compute);
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
     if (d->vfrc_next) cudaFree(d->vfrc_next);
+    if (d->token) cudaFree(d->token);
     if (d->ev_forces) cudaEventDestroy(d->ev_forces);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
@@ -720,8 +723,6 @@ int bib_time_end(bib_domain* d, float* milliseconds) {
     BIB_CHECK(cudaEventElapsedTime(milliseconds, d->ev0, d->ev1));
     return 1;
 }
-int group_phase_timing(bib_domain* h, int enable);
-int group_phase_times(bib_domain* h, double* ms, int n);
 int bib_phase_timing(bib_domain* d, int enable) {
     if (d && d->is_head) return group_phase_timing(d, enable);
     BIB_ENTER(d);

@@ -11,6 +11,7 @@
 #include "domain.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -221,5 +222,63 @@ int comm_exchange_pair(bib_domain* d, const double* send_left, const double* sen
     if (has_right) { NCCL_CHECK(g_nccl.Send(send_right, n_doubles, ncclDouble, right, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(recv_right, n_doubles, ncclDouble, right, comm, d->stream)); }
     NCCL_CHECK(g_nccl.GroupEnd());
     d->launches++;
+    return 1;
+}
+
+// Stream-ordered neighbour synchronisation: work issued on d->stream after this call runs after everything the two neighbours issued on
+// their streams before THEIR matching call. In-process group: CUDA events + the host barrier; one process per GPU: a grouped
+// ncclSend / ncclRecv of one element with each neighbour (NCCL's own flag exchange over NVLink).
+int comm_neighbour_sync(bib_domain* d) {
+    const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+    const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    const bool has_left = d->per[0] || d->rank > 0;
+    if (d->group) {
+        bib_group* g = d->group;
+        BIB_CHECK(cudaEventRecord(d->ev_x_ready, d->stream));
+        group_barrier(g);
+        if (has_left) BIB_CHECK(cudaStreamWaitEvent(d->stream, group_slab(g, left)->ev_x_ready, 0));
+        if (has_right) BIB_CHECK(cudaStreamWaitEvent(d->stream, group_slab(g, right)->ev_x_ready, 0));
+        group_barrier(g);                      // nobody re-records its event before every neighbour has enqueued its wait
+        return 1;
+    }
+    ncclComm_t comm = (ncclComm_t)d->nccl_comm;
+    if (!comm) { bib_set_error("neighbour sync: bib_comm_init has not been called"); return 0; }
+    if (!d->token) { BIB_CHECK(cudaMalloc(&d->token, 4 * sizeof(double))); BIB_CHECK(cudaMemset(d->token, 0, 4 * sizeof(double))); }
+    NCCL_CHECK(g_nccl.GroupStart());
+    if (has_left) { NCCL_CHECK(g_nccl.Send(d->token, 1, ncclDouble, left, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(d->token + 2, 1, ncclDouble, left, comm, d->stream)); }
+    if (has_right) { NCCL_CHECK(g_nccl.Send(d->token + 1, 1, ncclDouble, right, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(d->token + 3, 1, ncclDouble, right, comm, d->stream)); }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    d->launches++;
+    return 1;
+}
+
+// Make the neighbours' exchange buffers readable from this slab's kernels (NVLink peer loads). One process per GPU: every rank exports
+// its two buffers with cudaIpcGetMemHandle, the 64-byte handles travel over NCCL, cudaIpcOpenMemHandle maps them. COLLECTIVE.
+int comm_map_peer_buffers(bib_domain* d, double* mine_for_left, double* mine_for_right, const double** from_left, const double** from_right) {
+    const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+    const bool has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    const bool has_left = d->per[0] || d->rank > 0;
+    *from_left = nullptr; *from_right = nullptr;
+    if (d->group) return 1;                    // in-process: the caller reads the neighbour's pointers directly
+    ncclComm_t comm = (ncclComm_t)d->nccl_comm;
+    if (!comm) { bib_set_error("map peer buffers: bib_comm_init has not been called"); return 0; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h[4];                   // [0] mine for left, [1] mine for right, [2] left's for me, [3] right's for me
+    memset(h, 0, sizeof h);
+    BIB_CHECK(cudaIpcGetMemHandle(&h[0], mine_for_left));
+    BIB_CHECK(cudaIpcGetMemHandle(&h[1], mine_for_right));
+    char* dev = nullptr;
+    BIB_CHECK(cudaMalloc(&dev, sizeof h));
+    BIB_CHECK(cudaMemcpy(dev, h, sizeof h, cudaMemcpyHostToDevice));
+    NCCL_CHECK(g_nccl.GroupStart());
+    if (has_left) { NCCL_CHECK(g_nccl.Send(dev, 64, ncclChar, left, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(dev + 128, 64, ncclChar, left, comm, d->stream)); }
+    if (has_right) { NCCL_CHECK(g_nccl.Send(dev + 64, 64, ncclChar, right, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(dev + 192, 64, ncclChar, right, comm, d->stream)); }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    BIB_CHECK(cudaStreamSynchronize(d->stream));
+    BIB_CHECK(cudaMemcpy(h, dev, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    void* p = nullptr;
+    if (has_left) { BIB_CHECK(cudaIpcOpenMemHandle(&p, h[2], cudaIpcMemLazyEnablePeerAccess)); *from_left = (const double*)p; }
+    if (has_right) { BIB_CHECK(cudaIpcOpenMemHandle(&p, h[3], cudaIpcMemLazyEnablePeerAccess)); *from_right = (const double*)p; }
     return 1;
 }

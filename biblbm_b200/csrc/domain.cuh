@@ -61,8 +61,16 @@ struct MultiSlabIB {                        // one per particle group of a multi
     int* slot_of = nullptr;                // [n_global] -1 when not resident (slot index is domain-wide)
     int* free_stack = nullptr;             // [cap]
     int* counters = nullptr;               // [0] free_top, [1] overflow flag
-    double* send[2] = {nullptr, nullptr};  // [1 + xcap*entry]; element 0 holds the entry count (uint64)
-    double* recv[2] = {nullptr, nullptr};
+    // Exchange buffers [parity][side] (side 0 = packed for the left neighbour, 1 = for the right), [1 + xcap*entry] doubles, element 0
+    // holds the entry count (uint64). Consecutive exchanges alternate the parity, so a neighbour may still be reading exchange n while
+    // exchange n+1 is packed (the sync of exchange n+1 orders pack n+2 after its unpack n).
+    double* send[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    // PULL transport: the neighbours' send buffers mapped into this process / device (in-process group: plain pointers; one process per
+    // GPU: cudaIpcOpenMemHandle). peer[parity][side] = what the neighbour on `side` packed for me. NULL: copy transport (recv buffers).
+    const double* peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool pull = false;
+    unsigned xseq = 0;                     // exchanges issued so far (parity = xseq & 1)
+    double* recv[2] = {nullptr, nullptr};  // copy transport only
 };
 
 struct PotentialDev { int type = 0; double r_min = 0, beta = 0, strength = 0; };   // fsi/Potentials.h: 1 Morse, 2 spring
@@ -175,6 +183,7 @@ struct bib_domain {
     // multi-GPU ring
     int rank = 0, n_ranks = 1;
     void* nccl_comm = nullptr;
+    double* token = nullptr;              // 4 doubles: neighbour-sync tokens (comm_neighbour_sync)
     double* halo_stage = nullptr;         // [10][ny*nz] received ghost planes when y or z has walls
     int x_offset = 0;                     // global x of local plane 0
     int gnx = 0;                          // global nx
@@ -273,6 +282,8 @@ int comm_init(bib_domain* d, int rank, int n_ranks, const void* id128);
 int comm_halo_exchange(bib_domain* d, cudaStream_t st);
 void comm_destroy(bib_domain* d);
 int comm_exchange_pair(bib_domain* d, const double* send_left, const double* send_right, double* recv_left, double* recv_right, size_t n_doubles);
+int comm_neighbour_sync(bib_domain* d);        // stream-ordered: returns (on d->stream) after both neighbours' streams reached the same call
+int comm_map_peer_buffers(bib_domain* d, double* mine_for_left, double* mine_for_right, const double** from_left, const double** from_right);
 // in-process slab groups (group.cu)
 bib_domain* group_slab(bib_group* g, int rank);
 void group_barrier(bib_group* g);

@@ -2310,26 +2310,30 @@ __global__ void __launch_bounds__(128) k_pack_slots(double* __restrict__ out_v, 
     if (threadIdx.x < 11) out_s[(long long)j * 11 + threadIdx.x] = pstate[(long long)s * 11 + threadIdx.x];
 }
 // write_lightweight_particle_data (src/fsi/DeformableParticle3D.hh:318-333, compute_tensor_of_gyration :110-125): per particle
-// {global id, centre of mass[3], gyration tensor xx xy xz yy yz zz, volume}. One thread per listed slot, vertices summed in order
-// (the reference's sequential sum, bit for bit).
-__global__ void __launch_bounds__(64) k_lightweight(double* __restrict__ out, const int* __restrict__ list, const int* __restrict__ count, int n_slots,
-                                                    const int* __restrict__ gid, const int* __restrict__ slot_nv, const long long* __restrict__ slot_fv,
-                                                    const double* __restrict__ vpos, const double* __restrict__ pstate, long long cap_v) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// {global id, centre of mass[3], gyration tensor xx xy xz yy yz zz, volume}. One warp per listed slot: every lane sums a strided
+// subset of the vertices, the lanes are combined by a shuffle tree (the reference sums sequentially: equal to ~1e-16 relative).
+__global__ void __launch_bounds__(128) k_lightweight(double* __restrict__ out, const int* __restrict__ list, const int* __restrict__ count, int n_slots,
+                                                     const int* __restrict__ gid, const int* __restrict__ slot_nv, const long long* __restrict__ slot_fv,
+                                                     const double* __restrict__ vpos, const double* __restrict__ pstate, long long cap_v) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= (count ? *count : n_slots)) return;
     const int s = list ? list[j] : j;
     const double* st = pstate + (long long)s * 11;
     const int nv = slot_nv[s];
     const long long fv = slot_fv[s];
     double A[6] = {0, 0, 0, 0, 0, 0};
-    for (int v = 0; v < nv; ++v) {
+    for (int v = lane; v < nv; v += 32) {
         const double r[3] = {vpos[fv + v] - st[2], vpos[cap_v + fv + v] - st[3], vpos[2 * cap_v + fv + v] - st[4]};
         A[0] += r[0] * r[0]; A[1] += r[0] * r[1]; A[2] += r[0] * r[2]; A[3] += r[1] * r[1]; A[4] += r[1] * r[2]; A[5] += r[2] * r[2];
     }
-    double* o = out + (long long)j * 11;
-    o[0] = (double)gid[s]; o[1] = st[2]; o[2] = st[3]; o[3] = st[4];
-    for (int k = 0; k < 6; ++k) o[4 + k] = A[k] / (double)nv;
-    o[10] = st[1];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) for (int o = 16; o > 0; o >>= 1) A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
+    if (lane == 0) {
+        double* o = out + (long long)j * 11;
+        o[0] = (double)gid[s]; o[1] = st[2]; o[2] = st[3]; o[3] = st[4];
+        for (int k = 0; k < 6; ++k) o[4 + k] = A[k] / (double)nv;
+        o[10] = st[1];
+    }
 }
 // Read-back that overlaps the following steps: the fsi::Vertex records and the particle scalars are packed on the compute stream into
 // a staging buffer; a second stream copies them to the caller's page-locked buffers while the compute stream carries on. Up to
@@ -2396,7 +2400,7 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
         }
         int* count = d->res_list + (size_t)d->res_head * (2 * (size_t)cap + 2); int* list = count + 2; int* voff = list + cap;
         k_results_list<<<1, 1024, 0, d->stream>>>(d->role_all, d->slot_nv, cap, list, voff, count);
-        if (light) k_lightweight<<<(cap + 63) / 64, 64, 0, d->stream>>>(stage_s, list, count, cap, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices);
+        if (light) k_lightweight<<<(cap + 3) / 4, 128, 0, d->stream>>>(stage_s, list, count, cap, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices);
         else k_pack_slots<<<cap, 128, 0, d->stream>>>(stage_v, stage_s, list, voff, count, d->slot_nv, d->slot_fv, d->vpos, d->vvel, d->vfrc, d->pstate, d->cap_vertices);
         d->launches += 2;
         BIB_CHECK(cudaGetLastError());
@@ -2418,7 +2422,7 @@ int ib_results_download_async(bib_domain* d, double* v9, double* s11) {
             k_pack_vertices<<<grid, 256, 0, d->stream>>>(stage_v, d->vpos, d->vvel, d->vfrc, d->cap_vertices, 0, d->n_vertices);
             d->launches++;
         }
-        if (sb && light) { k_lightweight<<<(d->n_particles + 63) / 64, 64, 0, d->stream>>>(stage_s, nullptr, nullptr, d->n_particles, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices); d->launches++; }
+        if (sb && light) { k_lightweight<<<(d->n_particles + 3) / 4, 128, 0, d->stream>>>(stage_s, nullptr, nullptr, d->n_particles, d->gid_all, d->slot_nv, d->slot_fv, d->vpos, d->pstate, d->cap_vertices); d->launches++; }
         else if (sb) BIB_CHECK(cudaMemcpyAsync(stage_s, d->pstate, sb, cudaMemcpyDeviceToDevice, d->stream));
         BIB_CHECK(cudaEventRecord(r.packed, d->stream));
         BIB_CHECK(cudaStreamWaitEvent(d->copy_stream, r.packed, 0));

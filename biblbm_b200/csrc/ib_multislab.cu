@@ -16,6 +16,8 @@
 #include "domain.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace {
@@ -153,28 +155,49 @@ MsGeo make_ms_geo(const bib_domain* d, const MultiSlabIB* m) {
     return g;
 }
 
-// one neighbour exchange of every particle group: pack (2 launches per group incl. the counter reset), transfer, unpack (1 launch per group)
+// One neighbour exchange of every particle group. PULL transport (default): pack into this slab's send buffers (counter reset + one
+// launch for both sides), one stream-ordered neighbour sync for all groups, then the unpack kernel READS THE NEIGHBOURS' BUFFERS over
+// NVLink peer memory (both sides in one launch): only the entries actually packed cross the link, no staging copy, no NCCL data
+// transfer. COPY transport (BIB_IB_EXCHANGE=copy): the whole fixed-capacity buffers travel by ncclSend/ncclRecv / cudaMemcpyPeer.
 int ms_exchange(bib_domain* d, int kind, const double* src, double* dst) {
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
         const MsGeo g = make_ms_geo(d, m);
-        k_ms_clear_counts<<<1, 1, 0, d->stream>>>(m->send[0], m->send[1]);
-        k_ms_pack<<<dim3(m->cap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, d->pstate, src, d->cap_vertices, m->send[0], m->send[1], m->counters);
+        const int par = m->xseq & 1;
+        k_ms_clear_counts<<<1, 1, 0, d->stream>>>(m->send[par][0], m->send[par][1]);
+        k_ms_pack<<<dim3(m->cap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, d->pstate, src, d->cap_vertices, m->send[par][0], m->send[par][1], m->counters);
         d->launches += 2;
     }
     BIB_CHECK(cudaGetLastError());
+    bool any_pull = false;
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
+        if (m->pull) { any_pull = true; continue; }
         const size_t nd = 1 + (size_t)m->xcap * m->entry;
-        if (!comm_exchange_pair(d, m->send[0], m->send[1], m->recv[0], m->recv[1], nd)) return 0;
+        const int par = m->xseq & 1;
+        if (!comm_exchange_pair(d, m->send[par][0], m->send[par][1], m->recv[0], m->recv[1], nd)) return 0;
     }
-    uint8_t* seen = d->seen_all;
-    for (MultiSlabIB* m : d->msv) {
+    if (any_pull && !comm_neighbour_sync(d)) return 0;
+    const bool has_left = d->per[0] || d->rank > 0, has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    for (size_t gi = 0; gi < d->msv.size(); ++gi) {
+        MultiSlabIB* m = d->msv[gi];
         if (!m) continue;
         const MsGeo g = make_ms_geo(d, m);
-        k_ms_unpack<<<dim3(m->xcap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, m->slot_of, m->free_stack, m->counters, seen,
-                                                            m->recv[0], m->recv[1], dst, d->cap_vertices, m->gid_base);
+        const int par = m->xseq & 1;
+        const double *b0 = m->recv[0], *b1 = m->recv[1];
+        if (m->pull) {
+            if (d->group) {           // in-process: the neighbours' buffers are plain pointers (same device or peer access enabled)
+                const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
+                b0 = group_slab(d->group, left)->msv[gi]->send[par][1];
+                b1 = group_slab(d->group, right)->msv[gi]->send[par][0];
+            } else { b0 = m->peer[par][0]; b1 = m->peer[par][1]; }
+            if (!has_left) b0 = nullptr;
+            if (!has_right) b1 = nullptr;
+        }
+        k_ms_unpack<<<dim3(m->xcap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, m->slot_of, m->free_stack, m->counters, d->seen_all,
+                                                            b0, b1, dst, d->cap_vertices, m->gid_base);
         d->launches++;
+        m->xseq++;
     }
     BIB_CHECK(cudaGetLastError());
     return 1;
@@ -193,11 +216,17 @@ int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint, 
     m->xcap = n_global <= 1024 ? m->cap : std::min(m->cap, std::max(xcap_hint, 64));
     m->entry = 2 + 3 * (size_t)nv;
     const size_t nd = 1 + (size_t)m->xcap * m->entry;
+    const char* mode = getenv("BIB_IB_EXCHANGE");
+    m->pull = !(mode && std::string(mode) == "copy");
     bool ok = bib_cuda_ok(cudaMalloc(&m->slot_of, std::max(1, n_global) * sizeof(int)), "cudaMalloc") &&
               bib_cuda_ok(cudaMalloc(&m->free_stack, std::max(1, m->cap) * sizeof(int)), "cudaMalloc") && bib_cuda_ok(cudaMalloc(&m->counters, 2 * sizeof(int)), "cudaMalloc");
-    for (int s = 0; ok && s < 2; ++s)
-        ok = bib_cuda_ok(cudaMalloc(&m->send[s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMalloc(&m->recv[s], nd * sizeof(double)), "cudaMalloc") &&
-             bib_cuda_ok(cudaMemset(m->recv[s], 0, sizeof(double)), "cudaMemset");
+    for (int par = 0; ok && par < 2; ++par) for (int s = 0; ok && s < 2; ++s)
+        ok = bib_cuda_ok(cudaMalloc(&m->send[par][s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMemset(m->send[par][s], 0, sizeof(double)), "cudaMemset");
+    for (int s = 0; ok && !m->pull && s < 2; ++s)
+        ok = bib_cuda_ok(cudaMalloc(&m->recv[s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMemset(m->recv[s], 0, sizeof(double)), "cudaMemset");
+    // pull transport, one process per GPU: map the neighbours' send buffers (collective: every rank adds its particle groups in the same order)
+    for (int par = 0; ok && m->pull && !d->group && par < 2; ++par)
+        ok = comm_map_peer_buffers(d, m->send[par][0], m->send[par][1], &m->peer[par][0], &m->peer[par][1]) != 0;
     if (!ok) { delete m; return 0; }
     d->bytes += (long long)(4 * nd * sizeof(double));
     *out = m;
@@ -228,7 +257,8 @@ int ms_set_initial(bib_domain* d, MultiSlabIB* m, const std::vector<int>& owned_
 void ms_destroy(bib_domain* d) {
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
-        void* ptrs[] = {m->slot_of, m->free_stack, m->counters, m->send[0], m->send[1], m->recv[0], m->recv[1]};
+        for (int par = 0; par < 2; ++par) for (int s = 0; s < 2; ++s) if (m->peer[par][s]) cudaIpcCloseMemHandle((void*)m->peer[par][s]);
+        void* ptrs[] = {m->slot_of, m->free_stack, m->counters, m->send[0][0], m->send[0][1], m->send[1][0], m->send[1][1], m->recv[0], m->recv[1]};
         for (void* p : ptrs) if (p) cudaFree(p);
         delete m;
     }
