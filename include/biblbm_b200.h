@@ -52,6 +52,8 @@ enum {
     BIB_OPT_OVERLAP_FORCES = 8,      /* 1 (default): bib_step evaluates the vertex forces on a second stream beside the velocity interpolation (same results) */
     BIB_OPT_PREFETCH_FORCES = 9,     /* 1 (default): bib_step evaluates the vertex forces of step t+1 on the second stream while the collide-and-stream of
                                         step t runs (they depend on the advected positions only; same results; needs BIB_OPT_OVERLAP_FORCES) */
+    BIB_OPT_FUSED_INTERPOLATION = 10,/* 1 (default): the band velocities are evaluated into a per-particle shared-memory tile and interpolated from there (one kernel,
+                                        no dense velocity field); 0: k_band_velocity into the dense field + k_interpolate (same results, bit for bit) */
     BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
                                         force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
 };

@@ -718,6 +718,28 @@ def test_band_reset_survives_extra_interpolations(rbc):
         assert np.array_equal(lat.download()[..., 19:22], np.broadcast_to(np.asarray(g["body"], dtype=float), F.shape))
 
 
+@pytest.mark.parametrize("name", ["ib_rbc2_pfp", "ib_rbc_plates"])
+def test_fused_interpolation_equals_two_kernel_path(rbc, name):
+    """BIB_OPT_FUSED_INTERPOLATION: band velocities in a shared-memory tile + interpolation in one kernel == k_band_velocity into the dense
+    field + k_interpolate, bit for bit (periodic faces; wall planes + ParallelPlatesBoundary near-wall blending)."""
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    out = []
+    for fused in (1.0, 0.0):
+        if name == "ib_rbc_plates":
+            lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0, bib.OPT_FUSED_INTERPOLATION: fused})
+            sid = lat.register_shape(shape.verts, shape.tris)
+            lat.add_particles(sid, params, g["vert_init"][..., :3])
+            lat.set_boundary(float(g["plates"][0]), float(g["plates"][1]))
+        else:
+            lat = run_ib_case(g, shape, params, deterministic=True)
+            lat.set_option(bib.OPT_FUSED_INTERPOLATION, fused)
+        lat.step(g["body"], n=12)
+        out.append((lat.vertices(), lat.download()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+
+
 def test_lightweight_record_matches_reference_formula(rbc):
     """bib_ib_lightweight_download_async: {id, centre of mass, tensor of gyration, volume} per particle as write_lightweight computes them
     (src/fsi/DeformableParticle3D.hh:110-125,318-333: sequential sums over the vertices, divided by the vertex count)."""
