@@ -117,6 +117,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (!ib_set_kernel_attributes()) return 0;          // function attributes are per device: set for every device a domain is created on
     bib_domain* d = new (std::nothrow) bib_domain();
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) d->n_sms = sms; }
     d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
     for (int k = 0; k < 3; ++k) d->per[k] = periodic[k] ? 1 : 0;
     d->omega0 = omega_outer; d->omega1 = omega_inner; d->n_ext = n_ext;
@@ -526,7 +527,7 @@ int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count,
     if (d && d->is_head && (count <= 0 || scalars11)) return group_scalars_upload(d, first_particle, count, scalars11);
     BIB_ENTER(d);
     if (count > 0 && !scalars11) { bib_set_error("particle_scalars_upload: null argument"); return 0; }
-    if (d->n_ranks > 1) { bib_set_error("particle_scalars_upload: single-slab domains only"); return 0; }
+    if (d->n_ranks > 1 && !d->group) { bib_set_error("particle_scalars_upload: single-slab domains only"); return 0; }
     return ib_scalars_upload(d, first_particle, count, scalars11);
 }
 int bib_ib_results_download_async(bib_domain* d, double* vertices9, double* scalars11) {

@@ -116,6 +116,7 @@ struct bib_group;
 
 struct bib_domain {
     int device = 0;
+    int n_sms = 148;                      // multiprocessors of the device (kernel-variant heuristics)
     bib_group* group = nullptr;           // non-null: slab `rank` of an in-process slab group (n_ranks slabs)
     bool is_head = false;                 // the handle bib_domain_create_multi returned: every entry point dispatches to the group's slabs
     cudaEvent_t ev_x_ready = nullptr, ev_x_done = nullptr;      // in-process exchanges: my buffers are packed / I have pulled my neighbours' buffers

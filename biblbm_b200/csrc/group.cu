@@ -21,7 +21,8 @@
 struct bib_group {
     int n = 0;
     std::vector<bib_domain*> slab;
-    int gnx = 0, nxl = 0, ny = 0, nz = 0, n_ext = 4;
+    int gnx = 0, ny = 0, nz = 0, n_ext = 4;
+    std::vector<int> x0;                   // [n + 1] first global plane of every slab (widths differ by at most one plane)
     bool same_device = true;
     // worker threads (one per slab) + job hand-over
     std::vector<std::thread> workers;
@@ -100,7 +101,7 @@ int group_each(bib_group* g, const std::function<int(int)>& fn) {
 
 // the part of a global inclusive box that lies in slab r, in slab-local coordinates; false if empty
 bool split_box(const bib_group* g, const int box[6], int r, int local[6], int* x_skip) {
-    const int lo = r * g->nxl, hi = lo + g->nxl - 1;
+    const int lo = g->x0[r], hi = g->x0[r + 1] - 1;
     const int x0 = std::max(box[0], lo), x1 = std::min(box[1], hi);
     if (x0 > x1) return false;
     local[0] = x0 - lo; local[1] = x1 - lo;
@@ -120,18 +121,19 @@ int group_create(int nx, int ny, int nz, int n_ext, double omega_outer, double o
                  bib_domain** out) {
     *out = nullptr;
     if (n_slabs < 1 || n_slabs > 64) { bib_set_error("domain_create_multi: 1 .. 64 slabs"); return 0; }
-    if (nx % n_slabs != 0) { bib_set_error("domain_create_multi: nx must be a multiple of the number of slabs (equal x-slabs)"); return 0; }
+    if (nx / n_slabs < 3) { bib_set_error("domain_create_multi: fewer than 3 planes per slab"); return 0; }
     bib_group* g = new bib_group();
-    g->n = n_slabs; g->gnx = nx; g->nxl = nx / n_slabs; g->ny = ny; g->nz = nz; g->n_ext = n_ext;
+    g->n = n_slabs; g->gnx = nx; g->ny = ny; g->nz = nz; g->n_ext = n_ext;
+    for (int r = 0; r <= n_slabs; ++r) g->x0.push_back((int)((long long)r * nx / n_slabs));
     g->slab.assign(n_slabs, nullptr); g->result.assign(n_slabs, 0); g->error.assign(n_slabs, std::string());
     bool ok = true;
     for (int r = 0; ok && r < n_slabs; ++r) {
         const int dev = devices ? devices[r] : r;
         if (dev != (devices ? devices[0] : 0)) g->same_device = false;
-        ok = bib_domain_create(g->nxl, ny, nz, n_ext, omega_outer, omega_inner, periodic, dev, &g->slab[r]) != 0;
+        ok = bib_domain_create(g->x0[r + 1] - g->x0[r], ny, nz, n_ext, omega_outer, omega_inner, periodic, dev, &g->slab[r]) != 0;
         if (!ok) break;
         bib_domain* d = g->slab[r];
-        d->group = g; d->rank = r; d->n_ranks = n_slabs; d->gnx = nx; d->x_offset = r * g->nxl;
+        d->group = g; d->rank = r; d->n_ranks = n_slabs; d->gnx = nx; d->x_offset = g->x0[r];
         ok = bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_x_ready, cudaEventDisableTiming), "cudaEventCreate") &&
              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_x_done, cudaEventDisableTiming), "cudaEventCreate") &&
              bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_h_ready, cudaEventDisableTiming), "cudaEventCreate") &&
@@ -226,7 +228,7 @@ int group_set_boundary_velocity(bib_domain* h, const int box[6], const double* v
     if (!box_in_lattice(g, box)) { bib_set_error("set_boundary_velocity: box outside the lattice"); return 0; }
     // every slab also stores the velocities of the wall cells just outside its x-range (ghost columns): the plane functional
     // differentiates the stored velocities along x (PlaneFdBoundaryFunctional3D, finiteDifferenceBoundaryProcessor3D.hh:52-115)
-    return group_each(g, [&](int r) { return lbm_set_wall_velocity_ext(g->slab[r], box, velocities, r * g->nxl, h->per[0] ? g->gnx : 0); });
+    return group_each(g, [&](int r) { return lbm_set_wall_velocity_ext(g->slab[r], box, velocities, g->x0[r], h->per[0] ? g->gnx : 0); });
 }
 int group_set_guo_wall_nodes(bib_domain* h, int n, const int* location_direction6, const double* delta, const double* wall_velocity3) {
     G(h);

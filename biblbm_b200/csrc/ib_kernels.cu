@@ -1879,10 +1879,11 @@ static int ib_particles_add_multislab(bib_domain* d, int type, int shape_id, con
         if (d->per[0]) { const double L = (double)d->gnx; x = x - L * std::floor((x - (0.0 - 0.5)) * (1. / L)); }
         if (x >= (double)d->x_offset - 0.5 && x < (double)(d->x_offset + d->nx) - 0.5) owned.push_back(p);
     }
-    if (max_extent + 6.0 >= (double)d->nx) { bib_set_error("particles_add: the slab width must exceed the particle extent + 6 cells (a particle may only reach the two neighbouring slabs)"); return 0; }
+    const double slab_w = (double)(d->gnx / d->n_ranks);            // narrowest slab: a global quantity (capacities must agree on every rank)
+    if (max_extent + 6.0 >= slab_w) { bib_set_error("particles_add: the slab width must exceed the particle extent + 6 cells (a particle may only reach the two neighbouring slabs)"); return 0; }
     // slot / exchange capacities from the geometry: a particle is mirrored on a neighbour while its box (+3 cells) reaches over the
     // face, i.e. a fraction (extent + 6) / slab width of the owned ones per side; generous safety factors, overflow is detected
-    const double frac = std::min(1.0, (max_extent + 8.0) / (double)d->nx);
+    const double frac = std::min(1.0, (max_extent + 8.0) / slab_w);
     // (the exchange capacity fixes the message size, so it must come out identical on every rank: global quantities only)
     const double base = 1.25 * (double)n / d->n_ranks;
     const int xcap_hint = (int)(base * frac * 2.0) + 32;
@@ -2233,7 +2234,13 @@ int ib_forces(bib_domain* d, cudaStream_t st) {
         q.role = d->ms ? d->role_all : nullptr;
         q.f_init = init ? d->vfrc : nullptr;
         const size_t smem = (size_t)s.nv * 3 * sizeof(double);
-        if (s.nv <= RF_THREADS * RF_VPT_MAX) {
+        // A handful of particles (the reference's own driver set-ups: 1 .. 28 RBCs) cannot fill 148 SMs with one CTA per particle: there the
+        // vertex-parallel gather kernel runs (one thread per vertex, 3x the arithmetic, nv / 128 CTAs per particle; the same bits).
+        const bool few = gr.count * 4 < d->n_sms && !d->ms;
+        if (few) {
+            const long long n = (long long)gr.count * s.nv;
+            k_rbc_forces<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q, d->vpos, d->vfrc, d->pstate);
+        } else if (s.nv <= RF_THREADS * RF_VPT_MAX) {
             const size_t sm2 = smem + RF_CHUNK * sizeof(double);
             const int vpt = (s.nv + RF_THREADS - 1) / RF_THREADS;        // vertices per thread (measured: 3 instead of 4 for the 626-vertex RBC = -0.05 ms)
 #define BIB_RF_LAUNCH(V) k_rbc_forces_elem<V><<<gr.count, RF_THREADS, sm2, st>>>(q, d->vpos, d->vfrc, d->pstate, s.nt, s.nl, s.np)      /* shared-memory opt-in: ib_set_kernel_attributes */
@@ -2269,8 +2276,9 @@ int ib_spread(bib_domain* d) {
     pt_mark(d, PT_X_FORCE);
     if (d->deterministic_spread) d->fflag_valid = false;
     if (d->deterministic_spread) k_spread_sequential<<<1, 32, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
-    else if (d->spread_mode == 1) { k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc); }
-    else {
+    else if (d->spread_mode == 1 || (d->n_particles * 4 < d->n_sms && !d->ms)) {      // few particles: one thread per vertex instead of one CTA per particle
+        k_spread_atomic<<<(unsigned)((d->n_vertices + 127) / 128), 128, 0, d->stream>>>(make_geo(d), d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vfrc);
+    } else {
         const size_t smem = (size_t)TILE_CELLS * 3 * sizeof(double);
         for (const ParticleGroup& gr : d->groups) {
             k_spread_tile<<<gr.count, 256, smem, d->stream>>>(make_geo(d), d->force, d->pstate, d->vpos, d->vfrc, d->cap_vertices, d->shapes[gr.shape].nv,

@@ -72,7 +72,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
                       const int periodic[3], int device, bib_domain** out);
 /* The same lattice as x-slabs on SEVERAL GPUs owned by ONE host process: what `mpirun -np N ./driver` is to the reference
  * (one block per rank: src/fsi/ImmersedBoundaryDynamics.hh:49-54, src/multiBlock/multiBlockLattice3D.hh:306-348, progs/rbc_in_pipe/batch.sh).
- * nx is the GLOBAL size (a multiple of n_slabs); devices[n_slabs] = CUDA ordinal of every slab (NULL: 0..n_slabs-1; slabs may share
+ * nx is the GLOBAL size (slab widths differ by at most one plane: slab r starts at plane floor(r nx / n_slabs)); devices[n_slabs] = CUDA ordinal of every slab (NULL: 0..n_slabs-1; slabs may share
  * a device). The returned handle is used like any other: boxes, particle ids and vertex ranges are global, every entry point is split
  * over / broadcast to the slabs, collective work runs on one worker thread per slab with peer-to-peer (NVLink) halo and particle
  * exchanges. Not available on such a handle: rigid particles, velocity edges, vertex_forces_preload, multi_direct_forcing, the

@@ -102,6 +102,64 @@ def test_rbc_in_shear_driver_atomic_spread(tmp_path, mesh):
         assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(a))), f
 
 
+def _multi_env(n):
+    """BIB_GPUS=n: one process, n x-slabs (overlay/biblbm_overlay/impl_desc.inc); one slab per GPU when the box has n GPUs, otherwise the
+    slabs share GPU 0 (same multi-slab protocol, peer copies on one device)."""
+    import biblbm_b200 as bib
+    have = bib.device_count()
+    return dict(BIB_GPUS=str(n), BIB_DEVICES=",".join(str(k if have >= n else 0) for k in range(n)))
+
+
+def _numeric_files_close(d_ref, d_got, files, tol):
+    for f in files:
+        ta, tb = (d_ref / f).read_bytes(), (d_got / f).read_bytes()
+        if ta == tb:
+            continue
+        if not ("objsP" in f or f.endswith(".txt") or f.endswith(".csv")):     # VTK (base64 float32) / check-points (raw doubles): last bits may differ
+            assert len(ta) == len(tb), f
+            continue
+        a, b = numbers(ta.decode()), numbers(tb.decode())
+        assert a.shape == b.shape, f
+        assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(a))), f
+
+
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_rbc_in_shear_driver_on_several_slabs(tmp_path, mesh, n_slabs):
+    """The UNCHANGED driver on a lattice split into x-slabs (BIB_GPUS=n; the RBC sits on the slab face of the 97-plane lattice: 48 | 49)
+    against the CPU reference: the reference's `mpirun -np n` use (progs/rbc_in_pipe/batch.sh). Interpolation sums are split between
+    the slabs (different association), so text output agrees to its printed digits and numerically to 1e-9."""
+    _need(B200 / "rbc_in_shear_short_b200", CPU / "rbc_in_shear_short_cpu")
+    env = dict(BIB_NT="30", BIB_OUTPUT_INTERVAL="10", BIB_NCASES="1", BIB_MESH=str(mesh), BIB_SHRINK_ITERS="2000")
+    d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
+    d_cpu.mkdir(); d_gpu.mkdir()
+    out_cpu = run_driver(CPU / "rbc_in_shear_short_cpu", d_cpu, env)
+    out_gpu = run_driver(B200 / "rbc_in_shear_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1", **_multi_env(n_slabs)))
+    a, b = numbers(out_cpu), numbers(out_gpu)
+    assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(a)))
+    files = all_files(d_cpu)
+    assert files == all_files(d_gpu) and len(files) >= 8
+    _numeric_files_close(d_cpu, d_gpu, files, 1e-9)
+
+
+def test_rbcs_in_shear_driver_on_two_slabs(tmp_path):
+    """progs/rbcs_in_shear (28 RBCs between plates, wall planes inside the box, NoDynamics margins, velocity extrapolation on the device
+    field every step) on two x-slabs against the CPU reference."""
+    shape, _, _, _ = kit.load_rbc_fixture()
+    _need(B200 / "rbcs_in_shear_short_b200", CPU / "rbcs_in_shear_short_cpu")
+    env = dict(BIB_NT="20", BIB_OUTPUT_INTERVAL="10", BIB_SHRINK_ITERS="2000")
+    d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
+    for d in (d_cpu, d_gpu):
+        d.mkdir()
+        kit.write_gmsh(d / "sphere_TRImesh_626n_1248el.msh", shape.verts, shape.tris)
+    out_cpu = run_driver(CPU / "rbcs_in_shear_short_cpu", d_cpu, env)
+    out_gpu = run_driver(B200 / "rbcs_in_shear_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1", **_multi_env(2)))
+    a, b = numbers(out_cpu), numbers(out_gpu)
+    assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(a)))
+    files = [f for f in all_files(d_cpu) if not f.endswith(".msh") and "profile" not in f]
+    assert files == [f for f in all_files(d_gpu) if not f.endswith(".msh") and "profile" not in f]
+    _numeric_files_close(d_cpu, d_gpu, files, 1e-9)
+
+
 def _compare_runs(tmp_path, driver, env, args=(), meshes=(), min_files=4, texts=()):
     _need(B200 / f"{driver}_short_b200", CPU / f"{driver}_short_cpu")
     d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
