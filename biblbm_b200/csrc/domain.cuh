@@ -192,6 +192,7 @@ struct bib_domain {
     // IB
     std::vector<WallPlane> walls;
     std::vector<WallEdge> edges;
+    std::vector<int> guo_levels;          // node ranges [guo_levels[l], guo_levels[l+1]) that can be updated concurrently (see lbm_set_guo_nodes)
     int n_guo = 0; int* guo_nodes = nullptr; double* guo_delta = nullptr; double* guo_vel = nullptr;   // Guo off-lattice wall nodes
     std::vector<ShapeDev> shapes;
     std::vector<ParticleGroup> groups;

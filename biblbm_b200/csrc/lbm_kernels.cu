@@ -17,6 +17,10 @@
 // Bound: HBM. Algorithmic traffic 19*8*2 = 304 B/cell (+24 B force +1 B phase actually read).
 #include "domain.cuh"
 
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
 namespace {
 
 struct LbmParams {
@@ -936,11 +940,11 @@ __device__ __forceinline__ double d_ma2_equilibrium(int i, double rhoBar, double
     return t * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
 }
 __global__ void __launch_bounds__(128) k_guo_wall(double* __restrict__ f, const uint8_t* __restrict__ kind, const int* __restrict__ nodes,
-                                                  const double* __restrict__ delta_arr, const double* __restrict__ wall_vel, int n_nodes,
+                                                  const double* __restrict__ delta_arr, const double* __restrict__ wall_vel, int first_node, int n_nodes,
                                                   int nxl, int gnx, int ny, int nz, int x_offset, int per_x, int per_y, int per_z,
                                                   long long plane, long long vol) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_nodes) return;
+    const int w = first_node + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= first_node + n_nodes) return;
     const int* nd = nodes + 6 * w;
     const int lx = nd[0] - x_offset;
     if (lx < 0 || lx >= nxl) return;                       // another slab owns this node
@@ -957,6 +961,11 @@ __global__ void __launch_bounds__(128) k_guo_wall(double* __restrict__ f, const 
     double rhoBar1, rhoBar2, j1[3], j2[3];
     d_rhoBar_j(f1, rhoBar1, j1[0], j1[1], j1[2]);
     d_rhoBar_j(f2, rhoBar2, j2[0], j2[1], j2[2]);
+    // a neighbour that is itself NoDynamics / BounceBack answers through ITS dynamics: NoDynamics: rhoBar = 0 (rho = 1), j = 0, equilibrium = 0
+    // (src/core/dynamics.hh:773-777,852-857,946-950,1027-1032)
+    const bool dead1 = kind && kind[i1] != 0, dead2 = kind && kind[i2] != 0;
+    if (dead1) { rhoBar1 = kind[i1] == 2 ? -1.0 : 0.0; j1[0] = j1[1] = j1[2] = 0.0; }      // BounceBack(rho = T()) reports rhoBar(0) = -1
+    if (dead2) { rhoBar2 = kind[i2] == 2 ? -1.0 : 0.0; j2[0] = j2[1] = j2[2] = 0.0; }
     const double j1sqr = j1[0] * j1[0] + j1[1] * j1[1] + j1[2] * j1[2];
     const double j2sqr = j2[0] * j2[0] + j2[1] * j2[1] + j2[2] * j2[2];
     const double inv1 = 1. / (rhoBar1 + 1.), inv2 = 1. / (rhoBar2 + 1.);
@@ -974,8 +983,8 @@ __global__ void __launch_bounds__(128) k_guo_wall(double* __restrict__ f, const 
     const bool no_eq = kind && kind[i0] != 0;
 #pragma unroll
     for (int i = 0; i < BIB_Q; ++i) {
-        const double n1 = f1[i] - d_ma2_equilibrium(i, rhoBar1, inv1, j1, j1sqr);
-        const double n2 = f2[i] - d_ma2_equilibrium(i, rhoBar2, inv2, j2, j2sqr);
+        const double n1 = f1[i] - (dead1 ? 0.0 : d_ma2_equilibrium(i, rhoBar1, inv1, j1, j1sqr));
+        const double n2 = f2[i] - (dead2 ? 0.0 : d_ma2_equilibrium(i, rhoBar2, inv2, j2, j2sqr));
         const double neq = near ? delta * n1 + (1. - delta) * n2 : n1;
         f[(long long)i * vol + i0] = (no_eq ? 0.0 : d_ma2_equilibrium(i, rhoBar_w, 1. / (rhoBar_w + 1.), j_w, jSqr_w)) + neq;
     }
@@ -995,22 +1004,72 @@ int lbm_set_guo_nodes(bib_domain* d, int n, const int* loc_dir, const double* de
         if (!ok) { bib_set_error("set_guo_wall_nodes: node or its two fluid neighbours outside the lattice"); return 0; }
         if (d->n_ranks > 1 && q[3] != 0) { bib_set_error("set_guo_wall_nodes: on multi-slab domains the node direction must not have an x component"); return 0; }
     }
+    // The reference updates the nodes one after the other, in place (GuoRigidWallBoundaryFunctional::process): a node whose first or second
+    // neighbour is itself a wall node (narrow gaps, staircase corners) reads that node's NEW value if it comes earlier in the list and its
+    // OLD value if it comes later. One thread per node reproduces that when the list is processed in LEVELS: level(w) = 1 + the highest
+    // level among the earlier nodes w depends on (read-after-write) or that depend on w's old value (write-after-read); every such
+    // dependence points from a lower to a higher list index, so one forward pass assigns the levels. Typical lists have one level.
+    std::vector<int> level(n, 0);
+    {
+        std::unordered_map<long long, int> at;      // cell -> node index
+        const auto key = [&](long long x, long long y, long long z) { return (x * d->ny + y) * d->nz + z; };
+        for (int w = 0; w < n; ++w) at[key(loc_dir[6 * w], loc_dir[6 * w + 1], loc_dir[6 * w + 2])] = w;
+        const int nn[3] = {d->gnx, d->ny, d->nz};
+        std::vector<std::vector<int>> readers(n);   // readers[v] = nodes that read cell v
+        for (int w = 0; w < n; ++w)
+            for (int m = 1; m <= 2; ++m) {
+                long long c[3];
+                for (int k = 0; k < 3; ++k) { c[k] = loc_dir[6 * w + k] + (long long)m * loc_dir[6 * w + 3 + k]; if (d->per[k]) c[k] = ((c[k] % nn[k]) + nn[k]) % nn[k]; }
+                const auto it = at.find(key(c[0], c[1], c[2]));
+                if (it != at.end() && it->second != w) readers[it->second].push_back(w);
+            }
+        for (int v = 0; v < n; ++v)
+            for (int w : readers[v]) {
+                if (v < w) level[w] = std::max(level[w], level[v] + 1);          // w reads v's new value: after v
+            }
+        // write-after-read: v (later in the list) must not overwrite its cell before the earlier reader w has run; forward pass in index order
+        bool changed = true;
+        for (int pass = 0; changed && pass < 64; ++pass) {
+            changed = false;
+            for (int v = 0; v < n; ++v)
+                for (int w : readers[v]) {
+                    if (w < v && level[v] < level[w] + 1) { level[v] = level[w] + 1; changed = true; }
+                    if (v < w && level[w] < level[v] + 1) { level[w] = level[v] + 1; changed = true; }
+                }
+        }
+    }
+    std::vector<int> order(n);
+    for (int w = 0; w < n; ++w) order[w] = w;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+    std::vector<int> ld((size_t)n * 6); std::vector<double> dl(n), wv(wall_velocity ? (size_t)n * 3 : 0);
+    d->guo_levels.clear();
+    for (int k = 0; k < n; ++k) {
+        const int w = order[k];
+        for (int c = 0; c < 6; ++c) ld[(size_t)k * 6 + c] = loc_dir[6 * w + c];
+        dl[k] = delta[w];
+        if (wall_velocity) for (int c = 0; c < 3; ++c) wv[(size_t)k * 3 + c] = wall_velocity[3 * w + c];
+        if (k == 0 || level[w] != level[order[k - 1]]) d->guo_levels.push_back(k);
+    }
+    d->guo_levels.push_back(n);
     BIB_CHECK(cudaMalloc(&d->guo_nodes, (size_t)n * 6 * sizeof(int)));
     BIB_CHECK(cudaMalloc(&d->guo_delta, (size_t)n * sizeof(double)));
-    BIB_CHECK(cudaMemcpy(d->guo_nodes, loc_dir, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice));
-    BIB_CHECK(cudaMemcpy(d->guo_delta, delta, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    BIB_CHECK(cudaMemcpy(d->guo_nodes, ld.data(), (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice));
+    BIB_CHECK(cudaMemcpy(d->guo_delta, dl.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     if (wall_velocity) {
         BIB_CHECK(cudaMalloc(&d->guo_vel, (size_t)n * 3 * sizeof(double)));
-        BIB_CHECK(cudaMemcpy(d->guo_vel, wall_velocity, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        BIB_CHECK(cudaMemcpy(d->guo_vel, wv.data(), (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
     }
     d->n_guo = n;
     return 1;
 }
 int lbm_apply_guo(bib_domain* d) {
     if (d->n_guo == 0) return 1;
-    k_guo_wall<<<(d->n_guo + 127) / 128, 128, 0, d->stream>>>(d->f[d->cur], d->kind, d->guo_nodes, d->guo_delta, d->guo_vel, d->n_guo, d->nx, d->gnx, d->ny, d->nz,
-                                                           d->x_offset, d->n_ranks == 1 ? d->per[0] : 0, d->per[1], d->per[2], (long long)d->plane, (long long)d->vol);
-    d->launches++;
+    for (size_t l = 0; l + 1 < d->guo_levels.size(); ++l) {          // one launch per dependence level (normally one)
+        const int first = d->guo_levels[l], cnt = d->guo_levels[l + 1] - first;
+        k_guo_wall<<<(cnt + 127) / 128, 128, 0, d->stream>>>(d->f[d->cur], d->kind, d->guo_nodes, d->guo_delta, d->guo_vel, first, cnt, d->nx, d->gnx, d->ny, d->nz,
+                                                          d->x_offset, d->n_ranks == 1 ? d->per[0] : 0, d->per[1], d->per[2], (long long)d->plane, (long long)d->vol);
+        d->launches++;
+    }
     BIB_CHECK(cudaGetLastError());
     return 1;
 }

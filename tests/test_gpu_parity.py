@@ -359,6 +359,41 @@ def test_guo_pipe_wall_vs_golden():
             assert np.array_equal(got[..., :19], g[f"pop_{s}"][..., :19]), s
 
 
+def test_guo_wall_chained_nodes_follow_the_reference_order(orc):
+    """Wall nodes whose first / second neighbour is itself a wall node (narrow gaps, staircase corners): the reference updates the list
+    sequentially in place, so a node sees the NEW value of an earlier node and the OLD value of a later one; neighbours that are
+    NoDynamics cells answer rhoBar = 0, j = 0, equilibrium 0. The device processes the list in dependence levels: bit-identical to the
+    sequential oracle."""
+    rng = np.random.default_rng(8)
+    nx, ny, nz = 8, 12, 9
+    cells = np.zeros((nx, ny, nz, 23))
+    cells[..., :19] = 0.01 * rng.normal(size=(nx, ny, nz, 19))
+    kind = np.zeros((nx, ny, nz), dtype=np.uint8)
+    kind[:, 0, :] = bib.CELL_NODYNAMICS
+    nodes = []
+    for x in range(1, 7):
+        for z in range(1, 8):
+            # a chain along +y: node at y reads y+1 and y+2; (y = 1, 2, 3) are all wall nodes in mixed list order
+            for y in ((2, 1, 3) if (x + z) % 2 else (1, 3, 2)):
+                nodes.append([x, y, z, 0, 1, 0, 0.3 + 0.1 * ((x + y + z) % 5)])
+            nodes.append([x, 10, z, 0, -1, 0, 0.8])                         # delta >= 0.75 branch, unchained
+            nodes.append([x, 2 + 9 * 0, z, 0, 0, 0, 0.5]) if False else None
+    nodes = np.array([n for n in nodes if n is not None], dtype=np.float64)
+    # a node next to the NoDynamics layer looking INTO it: its neighbours are dead cells
+    extra = np.array([[x, 2, 0, 0, -1, 0, 0.4] for x in range(1, 7)], dtype=np.float64)
+    nodes = np.concatenate([nodes, extra])
+    wv = 0.01 * rng.normal(size=(nodes.shape[0], 3))
+    lat = make_lattice(cells, (1, 0, 1), 1.1, 0.8)
+    lat.defineDynamics((0, nx - 1, 0, 0, 0, nz - 1), bib.CELL_NODYNAMICS)
+    lat.set_guo_wall_nodes(nodes, wv)
+    ref = cells
+    for _ in range(3):
+        lat.collideAndStream()
+        ref = orc.collide_and_stream(ref, (1, 0, 1), 1.1, 0.8, kind=kind)
+        orc.guo_apply(ref, (1, 0, 1), nodes, wv, kind=kind)
+    assert np.array_equal(lat.download()[..., :19], ref[..., :19])
+
+
 def _set_kinds(lat, kind):
     nx, ny, nz = kind.shape
     for y in range(ny):
