@@ -278,6 +278,36 @@ def test_rbc_in_pipe_driver(tmp_path):
     assert checked >= 8
 
 
+def test_rbc_in_pipe_driver_on_two_slabs(tmp_path):
+    """progs/rbc_in_pipe on two x-slabs (BIB_GPUS=2; the reference runs this driver with `mpirun -np 6`, progs/rbc_in_pipe/batch.sh): RBC +
+    platelet particle groups, Guo wall nodes, Morse wall and particle-particle forces evaluated across the slab face. A 60-long pipe so
+    that a slab (30 / 31 planes) is wider than a particle + 6 cells. Particle tables against the CPU reference to 1e-9."""
+    _need(B200 / "rbc_in_pipe_short_b200", CPU / "rbc_in_pipe_short_cpu")
+    shape, _, _, _ = kit.load_rbc_fixture()
+    plt = np.load(kit.GOLDEN / "platelet54.npz")
+    xml = PIPE_XML.replace("<length>24</length>", "<length>60</length>").replace("<max_iterations>40</max_iterations>", "<max_iterations>30</max_iterations>")
+    env = dict(BIB_SHRINK_ITERS="2000", BIB_GROW_ITERS="2000")
+    dirs = {}
+    for name, exe, extra in (("cpu", CPU / "rbc_in_pipe_short_cpu", {}),
+                             ("gpu", B200 / "rbc_in_pipe_short_b200", dict(BIB_DETERMINISTIC_SPREAD="1", **_multi_env(2)))):
+        d = tmp_path / name
+        d.mkdir()
+        kit.write_gmsh(d / "sphere_TRImesh_626n_1248el.msh", shape.verts, shape.tris)
+        kit.write_gmsh(d / "sphere_2_2_2_TRImesh_54n_104el.msh", plt["verts"], plt["tris"])
+        (d / "input.xml").write_text(xml)
+        run_driver(exe, d, dict(env, **extra), args=("input.xml",), timeout=1500)
+        dirs[name] = d
+    files = [f for f in all_files(dirs["cpu"] / "out")]
+    assert files == all_files(dirs["gpu"] / "out")
+    checked = 0
+    for f in files:
+        if "objsP" in f:
+            x, y = numbers((dirs["cpu"] / "out" / f).read_text()), numbers((dirs["gpu"] / "out" / f).read_text())
+            assert x.shape == y.shape and np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(x))), f
+            checked += 1
+    assert checked >= 2
+
+
 def _vti_arrays(path):
     import base64
     out = {}

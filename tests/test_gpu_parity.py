@@ -377,8 +377,7 @@ def test_guo_wall_chained_nodes_follow_the_reference_order(orc):
             for y in ((2, 1, 3) if (x + z) % 2 else (1, 3, 2)):
                 nodes.append([x, y, z, 0, 1, 0, 0.3 + 0.1 * ((x + y + z) % 5)])
             nodes.append([x, 10, z, 0, -1, 0, 0.8])                         # delta >= 0.75 branch, unchained
-            nodes.append([x, 2 + 9 * 0, z, 0, 0, 0, 0.5]) if False else None
-    nodes = np.array([n for n in nodes if n is not None], dtype=np.float64)
+    nodes = np.array(nodes, dtype=np.float64)
     # a node next to the NoDynamics layer looking INTO it: its neighbours are dead cells
     extra = np.array([[x, 2, 0, 0, -1, 0, 0.4] for x in range(1, 7)], dtype=np.float64)
     nodes = np.concatenate([nodes, extra])
