@@ -45,11 +45,11 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in [CSRC / s for s in SOURCES] + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False, fmad: bool = False, out: pathlib.Path | None = None) -> pathlib.Path:
+def build(force: bool = False, verbose: bool = False, fmad: bool = False, out: pathlib.Path | None = None, defines: tuple = ()) -> pathlib.Path:
     if out is None and not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=true" if fmad else "-fmad=false",
-           "-Xcompiler", "-fPIC", "-shared", *nccl_include_flags(), "-o", str(out or LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl", "-lpthread", "-Xlinker", "--no-undefined"]
+           "-Xcompiler", "-fPIC", "-shared", *[f"-D{x}" for x in defines], *nccl_include_flags(), "-o", str(out or LIB)] + [str(CSRC / s) for s in SOURCES] + ["-ldl", "-lpthread", "-Xlinker", "--no-undefined"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

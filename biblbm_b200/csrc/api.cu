@@ -3,6 +3,7 @@
 #include "domain.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -115,6 +116,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (device < 0 || device >= ndev) { bib_set_error("domain_create: device index out of range"); return 0; }
     BIB_CHECK(cudaSetDevice(device));
     if (!ib_set_kernel_attributes()) return 0;          // function attributes are per device: set for every device a domain is created on
+    if (const char* g = std::getenv("BIB_L2_FETCH")) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)); cudaGetLastError(); }   // experiments: 32 / 64 / 128
     bib_domain* d = new (std::nothrow) bib_domain();
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) d->n_sms = sms; }

@@ -1400,7 +1400,10 @@ __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __re
 // Wall-plane cells report their stored boundary velocity (StoreVelocityDynamics), NoDynamics / BounceBack cells zero.
 #define TILE_SLOTS 3072
 struct WallsDev { int n; int dir[6], coord[6], nb[6], gx[6], a0[6], a1[6], b0[6], b1[6]; const double* vel[6]; };
-__global__ void __launch_bounds__(256, 2) k_interp_tile(Geo g, WallsDev W, const double* __restrict__ f, const double* __restrict__ force,
+#ifndef BIB_INTERP_MINB
+#define BIB_INTERP_MINB 2
+#endif
+__global__ void __launch_bounds__(256, BIB_INTERP_MINB) k_interp_tile(Geo g, WallsDev W, const double* __restrict__ f, const double* __restrict__ force,
                                                      const double* __restrict__ pstate, const double* __restrict__ vpos, double* __restrict__ vvel,
                                                      long long cap_v, int nv, long long first_vertex, int first_particle, unsigned* mask_store, int* band_store) {
     __shared__ unsigned s_mask[BAND_WORDS];

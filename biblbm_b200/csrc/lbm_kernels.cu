@@ -46,6 +46,33 @@ struct LbmParams {
     int swap_x_lo, swap_x_hi;
 };
 
+// Cache-policy variants of the streaming accesses of k_collide_stream (experiments: build with -DBIB_LBM_LD=1/2, -DBIB_LBM_ST=1/2):
+// loads  0 = ld.global.nc (read-only path, default), 1 = ld.global.cs (streaming, evict first), 2 = ld.global.lu (last use)
+// stores 0 = st.global (default), 1 = st.global.cs (streaming), 2 = st.global.wt (write through)
+#ifndef BIB_LBM_LD
+#define BIB_LBM_LD 0
+#endif
+#ifndef BIB_LBM_ST
+#define BIB_LBM_ST 0
+#endif
+__device__ __forceinline__ double d_ld_pop(const double* p) {
+#if BIB_LBM_LD == 1
+    return __ldcs(p);
+#elif BIB_LBM_LD == 2
+    return __ldlu(p);
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void d_st_pop(double* p, double v) {
+#if BIB_LBM_ST == 1
+    __stcs(p, v);
+#elif BIB_LBM_ST == 2
+    __stwt(p, v);
+#else
+    *p = v;
+#endif
+}
 __constant__ int c_cx[BIB_Q] = {0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0};
 __constant__ int c_cy[BIB_Q] = {0, 0, -1, 0, -1, 1, 0, 0, -1, -1, 0, 1, 0, 1, -1, 0, 0, 1, 1};
 __constant__ int c_cz[BIB_Q] = {0, 0, 0, -1, 0, 0, -1, 1, -1, 1, 0, 0, 1, 0, 0, 1, -1, 1, -1};
@@ -195,10 +222,10 @@ __device__ __forceinline__ void d_push(const LbmParams& p, const Nbr& n, long lo
     constexpr int OPP = I == 0 ? 0 : (I <= 9 ? I + 9 : I - 9);
     if (HAS_WALLS) {
         const bool blocked = (cx < 0 && n.wxm) || (cx > 0 && n.wxp) || (cy < 0 && n.wym) || (cy > 0 && n.wyp) || (cz < 0 && n.wzm) || (cz > 0 && n.wzp);
-        if (blocked) { p.fout[(long long)OPP * p.vol + idx] = v; return; }
+        if (blocked) { d_st_pop(p.fout + (long long)OPP * p.vol + idx, v); return; }
     }
     const int off = (cx < 0 ? n.oxm : (cx > 0 ? n.oxp : 0)) + (cy < 0 ? n.oym : (cy > 0 ? n.oyp : 0)) + (cz < 0 ? n.ozm : (cz > 0 ? n.ozp : 0));
-    p.fout[(long long)I * p.vol + idx + off] = v;
+    d_st_pop(p.fout + (long long)I * p.vol + idx + off, v);
 }
 
 // re-push of population I after the swapped-omega collision: only when it crosses a periodic face (a population that also
@@ -222,7 +249,10 @@ __device__ __forceinline__ void d_push_crossing(const LbmParams& p, const Nbr& n
 // x and y faces (whole planes / rows of threads take the tail; they also re-push what crosses z), the cells that lie on a z face only
 // (one lane of two warps per row) stay in k_face_swap.
 template <bool HAS_KIND, bool HAS_WALLS, int SWAP>
-__global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : 5) k_collide_stream(const LbmParams p) {
+#ifndef BIB_LBM_MINB
+#define BIB_LBM_MINB 5
+#endif
+__global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : BIB_LBM_MINB) k_collide_stream(const LbmParams p) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nz) return;
     const int y = blockIdx.y, x = p.x_first + (int)blockIdx.z * p.x_stride;
@@ -230,7 +260,7 @@ __global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : 5) k_collid
 
     double f[BIB_Q];
 #pragma unroll
-    for (int i = 0; i < BIB_Q; ++i) f[i] = __ldg(p.fin + (long long)i * p.vol + idx);
+    for (int i = 0; i < BIB_Q; ++i) f[i] = d_ld_pop(p.fin + (long long)i * p.vol + idx);
     double Fx = p.bfx, Fy = p.bfy, Fz = p.bfz;
     if (!p.fflag || ((__ldg(p.fflag + (idx >> 5)) >> (idx & 31)) & 1u)) { Fx = __ldg(p.force + idx); Fy = __ldg(p.force + p.vol + idx); Fz = __ldg(p.force + 2 * p.vol + idx); }
     const double c = (double)(__ldg(p.phase + idx) & 1);

@@ -24,6 +24,7 @@ if a.rbcs:
     verts, tris, params, rbc_pos = bench.load_rbc()
     sid = lat.register_shape(verts, tris)
     lat.add_particles(sid, params, bench.rbc_positions(rbc_pos, a.rbcs, (a.nx, 1024, 1024), 0, seed=7))
+lat.setExternalVector(body)      # production state: every cell holds the body force, force flags valid (sparse force reads)
 lat.sync()
 def timed(fn, K=20):
     fn(K); lat.sync()
