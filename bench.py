@@ -532,6 +532,8 @@ def ours(args):
     peak, peak_kind = measured_peaks()
     traffic = None
     tj = ROOT / "profiles" / "k_collide_stream_traffic.json"
+    if not tj.exists():
+        tj = ROOT / "profiles" / "r1_k_collide_stream_traffic.json"
     if tj.exists():
         t = json.loads(tj.read_text())
         if t["workload"] == [nx, ny, nz]:
