@@ -2,11 +2,14 @@
 #include "../../include/biblbm_b200.h"
 #include "domain.cuh"
 
+#include <algorithm>
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
+#include <vector>
 
 static thread_local std::string g_last_error;
 
@@ -241,8 +244,32 @@ int bib_domain_destroy(bib_domain* d) {
 
 // BIB_ENTER: entry points that may change the configuration or the state outside the stepping loop (they invalidate the captured
 // step graph); BIB_ENTER_RO: stepping itself, synchronisation, timing and read-only downloads.
-#define BIB_ENTER_RO(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); } while (0)
+// Call fusion (BIB_OPT_FUSE_CALLS): a driver issues the IB phases, the force reset and collideAndStream as separate calls
+// (progs/rbc_in_shear/rbc_in_shear.cpp:154-186 through the binding: interpolate, setExternalVector, forces + spread, move, collideAndStream).
+// On a single slab these five calls are DEFERRED: when the sequence completes in exactly that order it is executed as one bib_step, i.e. by
+// replaying the captured step graph (one launch instead of ~16); any other entry point first executes what is pending, call by call, so
+// nothing observable changes. Errors of deferred calls surface at the call that executes them.
+static int fuse_flush(bib_domain* d);
+#define BIB_ENTER_RO(d) do { if (!(d)) { bib_set_error("null domain handle"); return 0; } BIB_CHECK(cudaSetDevice((d)->device)); \
+                             if ((d)->fuse_stage && !fuse_flush(d)) return 0; } while (0)
 #define BIB_ENTER(d) do { BIB_ENTER_RO(d); (d)->graph_dirty = true; (d)->forces_ready = false; (d)->plain_steps_since_dirty = 0; } while (0)
+
+static int set_external_full_or_band(bib_domain* d, const int box[6], double fx, double fy, double fz);
+static int step_n(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps);
+static bool fusable(const bib_domain* d) {
+    return d->fuse_calls && d->use_graph && d->n_ranks == 1 && !d->is_head && !d->pt_on && !d->vel_full_valid && d->n_vertices > 0 && !d->vfrc_preloaded;
+}
+static int fuse_flush(bib_domain* d) {
+    const int stage = d->fuse_stage;
+    d->fuse_stage = 0;
+    d->graph_dirty = true; d->forces_ready = false; d->plain_steps_since_dirty = 0;      // what BIB_ENTER of the deferred calls would have done
+    const int box[6] = {0, d->nx - 1, 0, d->ny - 1, 0, d->nz - 1};
+    if (stage >= 1 && !ib_interpolate(d)) return 0;
+    if (stage >= 2 && !set_external_full_or_band(d, box, d->fuse_body[0], d->fuse_body[1], d->fuse_body[2])) return 0;
+    if (stage >= 3 && !ib_forces_and_spread(d)) return 0;
+    if (stage >= 4 && !ib_move_and_voxelize(d)) return 0;
+    return 1;
+}
 
 int bib_domain_set_option(bib_domain* d, int key, double value) {
     BIB_HEAD(d, group_set_option(d, key, value));
@@ -256,6 +283,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_FUSED_FACE_SWAP: d->fused_face_swap = value == 2.0 ? 2 : (value != 0.0 ? 1 : 0); return 1;
         case BIB_OPT_OVERLAP_FORCES: d->overlap_forces = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_PREFETCH_FORCES: d->prefetch_forces = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_FUSE_CALLS: d->fuse_calls = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_FUSED_INTERPOLATION: d->fused_interp = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
@@ -316,8 +344,15 @@ int bib_set_guo_wall_nodes(bib_domain* d, int n, const int* location_direction6,
 }
 int bib_set_external_vector(bib_domain* d, const int box[6], double fx, double fy, double fz) {
     if (d && d->is_head && box) return group_set_external_vector(d, box, fx, fy, fz);
+    if (d && box && d->fuse_stage == 1 && box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1) {
+        d->fuse_stage = 2; d->fuse_body[0] = fx; d->fuse_body[1] = fy; d->fuse_body[2] = fz;      // deferred (call fusion)
+        return 1;
+    }
     BIB_ENTER(d);
     if (!box) { bib_set_error("set_external_vector: null argument"); return 0; }
+    return set_external_full_or_band(d, box, fx, fy, fz);
+}
+static int set_external_full_or_band(bib_domain* d, const int box[6], double fx, double fy, double fz) {
     const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
     // Every cell outside the bands the last spread touched still holds the same body force: reset those bands only (ib_band_reset
     // knows which mask buffer the spread used and falls back to the whole lattice when it does not).
@@ -354,10 +389,37 @@ int bib_velocity_extrapolate_plane(bib_domain* d, int direction, int coord, int 
     BIB_ENTER(d);
     return lbm_velocity_extrapolate(d, direction, coord, inward);
 }
+// BIB_STEP_WALL_REPORT=<file>: wall-clock time between successive bib_collide_and_stream calls (= one driver step when a driver's time
+// loop calls it once per step), written every 500 calls as "<calls> <mean ms per step since call 100> <median ms per step>". The mean
+// includes whatever the driver does between steps (its output cadence: VTK / particle dumps every 500 - 1000 steps); the median is the
+// cost of an ordinary step. Measures a driver run without differencing whole-process run times (start-up jitter of +-1 s).
+static void step_wall_report(bib_domain* d) {
+    static const char* path = std::getenv("BIB_STEP_WALL_REPORT");
+    if (!path) return;
+    static std::vector<double> deltas;
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    d->wall_calls++;
+    if (d->wall_calls == 100) d->wall_t100 = now;
+    if (d->wall_calls > 100) deltas.push_back(now - d->wall_tprev);
+    d->wall_tprev = now;
+    if (d->wall_calls % 500 == 0 && d->wall_calls >= 1000) {
+        std::vector<double> sorted(deltas);
+        std::nth_element(sorted.begin(), sorted.begin() + sorted.size() / 2, sorted.end());
+        if (FILE* f = std::fopen(path, "w")) { std::fprintf(f, "%lld %.6f %.6f\n", d->wall_calls, (now - d->wall_t100) / (double)(d->wall_calls - 100), sorted[sorted.size() / 2]); std::fclose(f); }
+    }
+}
 int bib_collide_and_stream(bib_domain* d) {
     BIB_HEAD(d, group_collide_and_stream(d));
+    if (d && d->fuse_stage == 4) {            // the deferred calls of one driver step are complete: execute them as ONE step (graph replay)
+        BIB_CHECK(cudaSetDevice(d->device));
+        d->fuse_stage = 0;
+        step_wall_report(d);
+        return step_n(d, d->fuse_body[0], d->fuse_body[1], d->fuse_body[2], 1);
+    }
     BIB_ENTER(d);
     d->vel_full_valid = false;
+    step_wall_report(d);
     return lbm_launch_collide_stream(d);
 }
 
@@ -465,12 +527,23 @@ int bib_ib_count(bib_domain* d, int* n_particles, long long* n_vertices) {
 }
 int bib_ib_interpolate_velocity(bib_domain* d) {
     BIB_HEAD(d, group_ib_interpolate(d));
+    if (d && d->fuse_stage == 0 && fusable(d)) { d->fuse_stage = 1; return 1; }       // deferred (call fusion)
     BIB_ENTER(d);
     // the reference interpolates from the TensorField the driver computed (and may have edited); use it when it exists
     return ib_interpolate(d);
 }
-int bib_ib_compute_and_spread_forces(bib_domain* d) { BIB_HEAD(d, group_ib_forces_spread(d)); BIB_ENTER(d); return ib_forces_and_spread(d); }
-int bib_ib_move_vertices_and_revoxelize(bib_domain* d) { BIB_HEAD(d, group_ib_move(d)); BIB_ENTER(d); return ib_move_and_voxelize(d); }
+int bib_ib_compute_and_spread_forces(bib_domain* d) {
+    BIB_HEAD(d, group_ib_forces_spread(d));
+    if (d && d->fuse_stage == 2) { d->fuse_stage = 3; return 1; }
+    BIB_ENTER(d);
+    return ib_forces_and_spread(d);
+}
+int bib_ib_move_vertices_and_revoxelize(bib_domain* d) {
+    BIB_HEAD(d, group_ib_move(d));
+    if (d && d->fuse_stage == 3) { d->fuse_stage = 4; return 1; }
+    BIB_ENTER(d);
+    return ib_move_and_voxelize(d);
+}
 int bib_ib_step(bib_domain* d) {
     BIB_HEAD(d, group_ib_step(d));
     BIB_ENTER(d);
@@ -633,6 +706,9 @@ static bool step_graph_matches(const bib_domain* d, const StepGraph& g) {
 int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
     BIB_HEAD(d, group_step(d, body_fx, body_fy, body_fz, n_steps));
     BIB_ENTER_RO(d);
+    return step_n(d, body_fx, body_fy, body_fz, n_steps);
+}
+static int step_n(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps) {
     int s = 0;
     const bool same_body = d->graph_body[0] == body_fx && d->graph_body[1] == body_fy && d->graph_body[2] == body_fz;
     const bool have_graphs = d->sg[0].exec && d->sg[1].exec && !d->graph_dirty && same_body;

@@ -160,6 +160,8 @@ struct bib_domain {
     double* vfrc_next = nullptr; long long vfrc_next_cap = 0;
     bool vfrc_preloaded = false;          // bib_ib_vertex_forces_preload: the next force evaluation adds to vfrc instead of starting from zero
     long long launches = 0;
+    int fuse_calls = 1, fuse_stage = 0; double fuse_body[3] = {0, 0, 0};     // call fusion (api.cu): deferred interpolate / reset / forces+spread / move
+    long long wall_calls = 0; double wall_t100 = 0, wall_tprev = 0;      // BIB_STEP_WALL_REPORT (api.cu)
     // per-phase device timing (bib_phase_timing): CUDA events recorded at the END of each phase of a step; read back by bib_phase_times
     bool pt_on = false;
     std::vector<std::pair<int, cudaEvent_t>> pt_marks, pt_comm_marks;      // compute stream / communication stream

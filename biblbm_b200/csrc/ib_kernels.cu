@@ -144,6 +144,31 @@ struct SrcDense {                 // the dense velocity field (bib_compute_veloc
     const double* __restrict__ vel; long long vol;
     __device__ __forceinline__ void load(int, int, int, long long c0, double* u) const { u[0] = vel[c0]; u[1] = vel[vol + c0]; u[2] = vel[2 * vol + c0]; }
 };
+struct WallsDev { int n; int dir[6], coord[6], nb[6], gx[6], a0[6], a1[6], b0[6], b1[6]; const double* vel[6]; };
+// stored boundary velocity of a wall-plane cell (slab-local x, global y / z); false if the cell lies on no wall plane
+__device__ __forceinline__ bool d_wall_velocity(const WallsDev& W, int lx, int y, int z, double* u) {
+    const int c[3] = {lx, y, z};
+    for (int q = 0; q < W.n; ++q) {
+        const int dir = W.dir[q], ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+        if (c[dir] == W.coord[q] && c[ta] >= W.a0[q] && c[ta] <= W.a1[q] && c[tb] >= W.b0[q] && c[tb] <= W.b1[q]) {
+            const double* wv = W.vel[q] + ((long long)(c[ta] + W.gx[q]) * W.nb[q] + c[tb]) * 3;
+            u[0] = wv[0]; u[1] = wv[1]; u[2] = wv[2];
+            return true;
+        }
+    }
+    return false;
+}
+struct SrcPopW {                  // from the populations, honouring wall planes (stored velocity) and cell kinds (zero): the few-particle path
+    const double* __restrict__ f; const double* __restrict__ force; const uint8_t* __restrict__ kind; long long vol, plane; int nz; WallsDev W;
+    __device__ __forceinline__ void load(int, int, int, long long c0, double* u) const {
+        if (W.n > 0) {
+            const int lx = (int)(c0 / plane) - 1; const long long r = c0 % plane;
+            if (d_wall_velocity(W, lx, (int)(r / nz), (int)(r % nz), u)) return;
+        }
+        if (kind && kind[c0] != 0) { u[0] = u[1] = u[2] = 0.0; return; }
+        d_cell_velocity(f, force, vol, c0, u);
+    }
+};
 struct SrcPop {                   // straight from the populations: u = j/rho + F/2
     const double* __restrict__ f; const double* __restrict__ force; long long vol;
     __device__ __forceinline__ void load(int, int, int, long long c0, double* u) const { d_cell_velocity(f, force, vol, c0, u); }
@@ -244,6 +269,37 @@ __global__ void __launch_bounds__(128) k_interpolate(Geo g, const double* __rest
     if (DENSE) { const SrcDense src = {vel, g.vol}; d_interp_vertex(g, src, pp, o); }
     else { const SrcPop src = {f, force, g.vol}; d_interp_vertex(g, src, pp, o); }
     vvel[v] = o[0]; vvel[cap + v] = o[1]; vvel[2 * cap + v] = o[2];
+}
+
+// Few particles: one WARP per vertex. Lane l < 27 evaluates the velocity of stencil cell l = (i*3 + j)*3 + k straight from the populations
+// (22 independent loads per lane, all in flight at once); the interpolation sum is then formed by every lane in lockstep, in the
+// reference's order, fetching cell values with warp shuffles (same bits as the tile / dense paths).
+struct SrcWarp {
+    double u[3]; int x0, y0, z0;
+    __device__ __forceinline__ void load(int i, int j, int k, long long, double* o) const {
+        const int m = ((i - x0) * 3 + (j - y0)) * 3 + (k - z0);
+        o[0] = __shfl_sync(0xffffffffu, u[0], m); o[1] = __shfl_sync(0xffffffffu, u[1], m); o[2] = __shfl_sync(0xffffffffu, u[2], m);
+    }
+};
+__global__ void __launch_bounds__(128) k_interpolate_warp(Geo g, WallsDev W, const double* __restrict__ f, const double* __restrict__ force,
+                                                          long long nvert, long long cap, const double* __restrict__ vpos, double* __restrict__ vvel) {
+    const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= nvert) return;                                   // whole warps leave together
+    const double pp[3] = {vpos[v], vpos[cap + v], vpos[2 * cap + v]};
+    SrcWarp src;
+    src.x0 = (int)ceil((pp[0] - (-1.0)) - 1.5); src.y0 = (int)ceil((pp[1] - (-1.0)) - 1.5); src.z0 = (int)ceil((pp[2] - (-1.0)) - 1.5);
+    src.u[0] = src.u[1] = src.u[2] = 0.0;
+    if (lane < 27) {
+        const int i2 = d_remap(g, 0, src.x0 + lane / 9), j2 = d_remap(g, 1, src.y0 + (lane / 3) % 3), k2 = d_remap(g, 2, src.z0 + lane % 3);
+        if (i2 >= 0 && i2 <= g.nx - 1 && d_in_slab(g, i2) && j2 >= 0 && j2 <= g.ny - 1 && k2 >= 0 && k2 <= g.nz - 1) {
+            const SrcPopW cell = {f, force, g.kind, g.vol, g.plane, g.nz, W};
+            cell.load(0, 0, 0, d_cell(g, i2, j2, k2), src.u);
+        }
+    }
+    double o[3];
+    d_interp_vertex<SrcWarp, true>(g, src, pp, o);
+    if (lane == 0) { vvel[v] = o[0]; vvel[cap + v] = o[1]; vvel[2 * cap + v] = o[2]; }
 }
 
 // ------------------------------------------------------------------------------------------------ I3: spreading
@@ -1399,7 +1455,6 @@ __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __re
 // Same arithmetic in the same order as the reference (_interpolation.hh:43-153): bit-identical to the two-kernel path.
 // Wall-plane cells report their stored boundary velocity (StoreVelocityDynamics), NoDynamics / BounceBack cells zero.
 #define TILE_SLOTS 3072
-struct WallsDev { int n; int dir[6], coord[6], nb[6], gx[6], a0[6], a1[6], b0[6], b1[6]; const double* vel[6]; };
 #ifndef BIB_INTERP_MINB
 #define BIB_INTERP_MINB 2
 #endif
@@ -1468,15 +1523,7 @@ __global__ void __launch_bounds__(256, BIB_INTERP_MINB) k_interp_tile(Geo g, Wal
                     const int nn[3] = {g.nx, g.ny, g.nz};
 #pragma unroll
                     for (int d = 0; d < 3; ++d) if (g.per[d]) c[d] = ((c[d] % nn[d]) + nn[d]) % nn[d];
-                    c[0] -= g.x_offset;                                           // wall arrays are slab-local along x
-                    for (int q = 0; q < W.n && !wall; ++q) {
-                        const int dir = W.dir[q], ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
-                        if (c[dir] == W.coord[q] && c[ta] >= W.a0[q] && c[ta] <= W.a1[q] && c[tb] >= W.b0[q] && c[tb] <= W.b1[q]) {
-                            const double* wv = W.vel[q] + ((long long)(c[ta] + W.gx[q]) * W.nb[q] + c[tb]) * 3;
-                            u[0] = wv[0]; u[1] = wv[1]; u[2] = wv[2];
-                            wall = true;
-                        }
-                    }
+                    wall = d_wall_velocity(W, c[0] - g.x_offset, c[1], c[2], u);          // wall arrays are slab-local along x
                 }
                 if (!wall && !(g.kind && g.kind[idx] != 0)) d_cell_velocity(f, force, g.vol, idx, u);
             }
@@ -2058,12 +2105,23 @@ int ib_interpolate(bib_domain* d) {
         bool fused = d->fused_interp && d->edges.empty() && d->walls.size() <= 6;
         // particles larger than the tile read the populations directly: not valid next to wall planes / cell kinds (they need the stored velocities)
         if (fused && (!d->walls.empty() || d->kind)) for (const ParticleGroup& gr : d->groups) if (d->shapes[gr.shape].nv > 2048) fused = false;
+        WallsDev W; W.n = fused ? (int)d->walls.size() : 0;
+        for (int q = 0; q < W.n; ++q) {
+            const WallPlane& w = d->walls[q];
+            W.dir[q] = w.dir; W.coord[q] = w.coord; W.nb[q] = w.nb; W.gx[q] = w.gx; W.a0[q] = w.a0; W.a1[q] = w.a1; W.b0[q] = w.b0; W.b1[q] = w.b1; W.vel[q] = w.vel;
+        }
+        // A handful of particles on a small lattice (the reference's own driver set-ups): one CTA per particle leaves the GPU idle. One warp per
+        // vertex reads the populations directly (k_interpolate_warp); no band masks are taken, so the next force reset runs over the whole (small) lattice.
+        if (fused && !d->ms && d->n_particles * 4 < d->n_sms && d->n_vertices <= 8192 && d->vol <= (size_t)4 << 20) {      // (27 RBCs: the tile kernel is faster again)
+            k_interpolate_warp<<<(unsigned)((d->n_vertices * 32 + 127) / 128), 128, 0, d->stream>>>(make_geo(d), W, d->f[d->cur], d->force, d->n_vertices, d->cap_vertices, d->vpos, d->vvel);
+            d->launches++;
+            d->band_valid[d->band_cur] = false;     // no masks were written into this buffer
+            d->band_pos_valid = false;
+            BIB_CHECK(cudaGetLastError());
+            pt_mark(d, PT_INTERPOLATE);
+            return 1;
+        }
         if (fused) {
-            WallsDev W; W.n = (int)d->walls.size();
-            for (int q = 0; q < W.n; ++q) {
-                const WallPlane& w = d->walls[q];
-                W.dir[q] = w.dir; W.coord[q] = w.coord; W.nb[q] = w.nb; W.gx[q] = w.gx; W.a0[q] = w.a0; W.a1[q] = w.a1; W.b0[q] = w.b0; W.b1[q] = w.b1; W.vel[q] = w.vel;
-            }
             const size_t smem = (size_t)3 * TILE_SLOTS * sizeof(double);
             for (const ParticleGroup& gr : d->groups) {
                 const ShapeDev& s = d->shapes[gr.shape];

@@ -752,6 +752,33 @@ def test_band_reset_survives_extra_interpolations(rbc):
         assert np.array_equal(lat.download()[..., 19:22], np.broadcast_to(np.asarray(g["body"], dtype=float), F.shape))
 
 
+def test_call_fusion_equals_separate_calls(rbc):
+    """BIB_OPT_FUSE_CALLS: the five calls of a driver step (interpolate, setExternalVector, forces + spread, move, collideAndStream) are deferred and run
+    as one bib_step (graph replay after a few steps); a read in the middle of the sequence executes the pending calls one by one. Bit-identical to
+    the same calls with fusion off, and to bib_step."""
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / "ib_rbc2_pfp.npz")
+    lats = [run_ib_case(g, shape, params, deterministic=True) for _ in range(3)]
+    lats[1].set_option(bib.OPT_FUSE_CALLS, 0.0)
+    mid = None
+    for it in range(14):
+        for k in (0, 1):
+            lat = lats[k]
+            lat.interpolate_velocity()
+            lat.setExternalVector(g["body"])
+            if it == 9 and k == 0:
+                mid = lat.vertices().copy()           # a read between the deferred calls: forces the pending ones to run now
+            if it == 9 and k == 1:
+                assert np.array_equal(mid, lat.vertices())
+            lat.compute_and_spread_forces()
+            lat.move_vertices_and_revoxelize()
+            lat.collideAndStream()
+        lats[2].step(g["body"])
+    for k in (1, 2):
+        assert np.array_equal(lats[0].vertices(), lats[k].vertices()), k
+        assert np.array_equal(lats[0].download(), lats[k].download()), k
+
+
 @pytest.mark.parametrize("name", ["ib_rbc2_pfp", "ib_rbc_plates"])
 def test_fused_interpolation_equals_two_kernel_path(rbc, name):
     """BIB_OPT_FUSED_INTERPOLATION: band velocities in a shared-memory tile + interpolation in one kernel == k_band_velocity into the dense

@@ -29,5 +29,14 @@ if __name__ == "__main__":
     if "--cpu" not in sys.argv:
         s, t1, t2 = per_step(gpu, 500, 4500)
         print(f"binding (GPU): {s * 1e3:.4f} ms/step  (runs {t1:.2f} s, {t2:.2f} s)")
+        with tempfile.TemporaryDirectory() as d:
+            rep = str(pathlib.Path(d) / "wall.txt")
+            run(gpu, 8000, {"BIB_STEP_WALL_REPORT": rep})
+            print("binding (GPU), BIB_STEP_WALL_REPORT after 8000 steps [calls, mean ms/step since step 100, median ms/step]:", open(rep).read().strip())
+        if "--long" in sys.argv:
+            s, t1, t2 = per_step(gpu, 500, 12500)
+            print(f"binding (GPU), 12 000 steps: {s * 1e3:.4f} ms/step  (runs {t1:.2f} s, {t2:.2f} s)")
+            s, t1, t2 = per_step(gpu, 4500, 12500)
+            print(f"binding (GPU), steps 4500 .. 12500: {s * 1e3:.4f} ms/step  (runs {t1:.2f} s, {t2:.2f} s)")
     s, t1, t2 = per_step(cpu, 5, 35)
     print(f"reference (1 core): {s * 1e3:.2f} ms/step  (runs {t1:.2f} s, {t2:.2f} s)")
