@@ -31,6 +31,7 @@ SYMBOLS = [
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES, OPT_PREFETCH_FORCES = 1, 2, 3, 4, 5, 6, 7, 8, 9
 OPT_FUSED_INTERPOLATION = 10
 OPT_FUSE_CALLS = 11
+OPT_LBM_PREFETCH = 12
 CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
 PARTICLE_RBC, PARTICLE_CAPSULE, PARTICLE_SEMIRIGID = 0, 1, 2
 POTENTIAL_NONE, POTENTIAL_MORSE, POTENTIAL_SPRING = 0, 1, 2

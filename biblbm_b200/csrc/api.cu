@@ -283,6 +283,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_FUSED_FACE_SWAP: d->fused_face_swap = value == 2.0 ? 2 : (value != 0.0 ? 1 : 0); return 1;
         case BIB_OPT_OVERLAP_FORCES: d->overlap_forces = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_PREFETCH_FORCES: d->prefetch_forces = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_LBM_PREFETCH: d->lbm_prefetch = value > 0.0 ? (long long)value : 0; return 1;
         case BIB_OPT_FUSE_CALLS: d->fuse_calls = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_FUSED_INTERPOLATION: d->fused_interp = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;

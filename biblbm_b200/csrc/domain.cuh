@@ -177,6 +177,7 @@ struct bib_domain {
     int fused_face_swap = 1;              // BIB_OPT_FUSED_FACE_SWAP: 0 separate k_face_swap pass, 1 fused for all faces, 2 fused for x/y faces only
     int deterministic_spread = 0;
     int spread_mode = 0;                  // 0 shared-memory tile staging (default), 1 one global atomic per stencil point
+    long long lbm_prefetch = 32768;       // BIB_OPT_LBM_PREFETCH: L2 prefetch distance of k_collide_stream in cells (0 = off)
     int fused_interp = 1;                 // BIB_OPT_FUSED_INTERPOLATION: band velocity + interpolation in one per-particle tile kernel
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
     int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),

@@ -14,10 +14,13 @@ ap.add_argument("--envelope", type=int, default=1)
 ap.add_argument("--rbcs", type=int, default=1250)
 ap.add_argument("--seconds", type=float, default=1.5)
 ap.add_argument("--nx", type=int, default=128)
+ap.add_argument("--prefetch", type=int, default=-1)
 a = ap.parse_args()
 lat = bib.Lattice(a.nx, 1024, 1024, 1.0, 1 / 3)
 lat.set_option(bib.OPT_FUSED_FACE_SWAP, float(a.face_swap))
 lat.set_option(bib.OPT_ENVELOPE_SWAP, float(a.envelope))
+if a.prefetch >= 0:
+    lat.set_option(bib.OPT_LBM_PREFETCH, float(a.prefetch))
 lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
 body = (1e-6, 0.0, 0.0)
 if a.rbcs:
@@ -34,7 +37,7 @@ def timed(fn, K=20):
         lat.time_begin(); fn(K); out.append(lat.time_end() / K)
     return out
 k = timed(lambda n: lat.collideAndStream(n))
-res = {"tag": a.tag, "lib": os.environ.get("BIB_LIB", "default"), "face_swap": a.face_swap, "envelope": a.envelope,
+res = {"tag": a.tag, "lib": os.environ.get("BIB_LIB", "default"), "prefetch": a.prefetch, "face_swap": a.face_swap, "envelope": a.envelope,
        "lbm_ms_first": k[0], "lbm_ms_median": float(np.median(k)), "lbm_ms_min": float(np.min(k))}
 if a.rbcs:
     s = timed(lambda n: lat.step(body, n=n))
