@@ -45,6 +45,7 @@ struct LbmParams {
     // fused envelope quirk (SWAP != 0): is this slab's low / high x face a GLOBAL periodic face
     int swap_x_lo, swap_x_hi;
     long long prefetch_cells;     // L2 prefetch distance of the main body (cells ahead in memory order; 0 = off)
+    int flat;                     // thread index runs over the flattened (y, z) plane (grid.y == 1)
 };
 
 // Cache-policy variants of the streaming accesses of k_collide_stream (experiments: build with -DBIB_LBM_LD=1/2, -DBIB_LBM_ST=1/2):
@@ -255,9 +256,19 @@ template <bool HAS_KIND, bool HAS_WALLS, int SWAP>
 #define BIB_LBM_MINB 5
 #endif
 __global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : BIB_LBM_MINB) k_collide_stream(const LbmParams p) {
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    if (z >= p.nz) return;
-    const int y = blockIdx.y, x = p.x_first + (int)blockIdx.z * p.x_stride;
+    // threads along z (the contiguous axis), one row per blockIdx.y; p.flat: threads along the flattened (y, z) plane instead, so that a
+    // row length that is not a multiple of the CTA size (the reference's 97 / 61 / 121-cell lattices) leaves no idle lanes
+    int y, z;
+    if (p.flat) {
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= (int)p.plane) return;
+        y = t / p.nz; z = t - y * p.nz;
+    } else {
+        z = blockIdx.x * blockDim.x + threadIdx.x;
+        if (z >= p.nz) return;
+        y = blockIdx.y;
+    }
+    const int x = p.x_first + (int)blockIdx.z * p.x_stride;
     const long long idx = (long long)(x + 1) * p.plane + (long long)y * p.nz + z;
 
     if (p.prefetch_cells > 0) {
@@ -306,7 +317,9 @@ __global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : BIB_LBM_MIN
             asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
             asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
             asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
-            const int z2 = (int)(bx * blockDim.x + tid), y2 = (int)by, x2 = p.x_first + (int)bz * p.x_stride;
+            int z2 = (int)(bx * blockDim.x + tid), y2 = (int)by;
+            if (p.flat) { y2 = z2 / p.nz; z2 -= y2 * p.nz; }
+            const int x2 = p.x_first + (int)bz * p.x_stride;
             const bool sxm = (x2 == 0) && p.swap_x_lo, sxp = (x2 == p.nx - 1) && p.swap_x_hi;
             const bool sym = (y2 == 0) && p.per_y, syp = (y2 == p.ny - 1) && p.per_y;
             const bool szm = (z2 == 0) && p.per_z, szp = (z2 == p.nz - 1) && p.per_z;
@@ -755,6 +768,7 @@ static LbmParams make_params(bib_domain* d) {
     p.swap_x_lo = d->per[0] && first; p.swap_x_hi = d->per[0] && last;
     // only worth it when the lattice does not fit the 126 MB L2 anyway (A + B populations of 400 k cells)
     p.prefetch_cells = (d->lbm_prefetch > 0 && d->vol > (size_t)400000) ? d->lbm_prefetch : 0;
+    p.flat = (d->nz % 128 != 0 && d->plane < ((size_t)1 << 30)) ? 1 : 0;
     return p;
 }
 
@@ -768,6 +782,7 @@ static void launch_main(bib_domain* d, const LbmParams& p, int n_planes, cudaStr
     if (n_planes <= 0) return;
     int bs = d->nz >= 128 ? 128 : ((d->nz + 31) / 32) * 32;
     dim3 grid((d->nz + bs - 1) / bs, d->ny, n_planes);
+    if (p.flat) { bs = 128; grid = dim3((unsigned)((d->plane + bs - 1) / bs), 1, n_planes); }
     const bool walls = p.x_lo_mode == 2 || p.x_hi_mode == 2 || !p.per_y || !p.per_z;
     const int swap = fused_swap_mode(d);
 #define BIB_LAUNCH_CS(K, W) do { if (swap == 1) k_collide_stream<K, W, 1><<<grid, bs, 0, st>>>(p); else if (swap == 2) k_collide_stream<K, W, 2><<<grid, bs, 0, st>>>(p); \
