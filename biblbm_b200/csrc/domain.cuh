@@ -142,6 +142,7 @@ struct bib_domain {
     bool force_is_body = false;           // every cell outside the particle bands holds force_body
     unsigned* fflag = nullptr;            // 1 bit per cell (storage index): 0 => force == force_body exactly; only meaningful while fflag_valid && force_is_body
     bool fflag_valid = false;
+    bool flags_by_masks = false;          // the last k_interp_tile raised the force flags of every cell its masks cover (the spread of the same positions need not)
     int sparse_force = 1;                 // BIB_OPT_SPARSE_FORCE
     // Which mask buffer describes the cells the last NOT YET RESET spread wrote: 0 / 1 = that buffer (the masks ib_interpolate took at
     // the positions the spread used); -1 = nothing to reset (no spread since the force field was last set); -2 = unknown (a spread

@@ -1201,6 +1201,7 @@ int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double f
     BIB_CHECK(cudaGetLastError());
     const bool full = box[0] == 0 && box[1] == d->nx - 1 && box[2] == 0 && box[3] == d->ny - 1 && box[4] == 0 && box[5] == d->nz - 1;
     if (full) d->spread_band = -1;          // nothing left to reset
+    d->flags_by_masks = false;              // (a full reset clears the force flags an earlier interpolation may have raised)
     if (full && d->sparse_force) {          // every cell now holds the body force: all flags off
         const size_t words = (d->vol + 31) / 32;
         if (!d->fflag) { BIB_CHECK(cudaMalloc(&d->fflag, words * sizeof(unsigned))); d->bytes += (long long)(words * sizeof(unsigned)); }
