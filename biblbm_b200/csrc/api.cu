@@ -12,6 +12,7 @@
 #include <vector>
 
 static thread_local std::string g_last_error;
+static int d_spread_sorted_env = -1;
 
 void bib_set_error(const std::string& msg) { g_last_error = msg; }
 bool bib_cuda_ok(cudaError_t e, const char* what) {
@@ -119,10 +120,12 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (device < 0 || device >= ndev) { bib_set_error("domain_create: device index out of range"); return 0; }
     BIB_CHECK(cudaSetDevice(device));
     if (!ib_set_kernel_attributes()) return 0;          // function attributes are per device: set for every device a domain is created on
+    if (const char* so = std::getenv("BIB_SPREAD_SORTED")) d_spread_sorted_env = std::atoi(so);
     if (const char* g = std::getenv("BIB_L2_FETCH")) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)); cudaGetLastError(); }   // experiments: 32 / 64 / 128
     bib_domain* d = new (std::nothrow) bib_domain();
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) d->n_sms = sms; }
+    if (d_spread_sorted_env >= 0) d->spread_sorted = d_spread_sorted_env;
     d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
     for (int k = 0; k < 3; ++k) d->per[k] = periodic[k] ? 1 : 0;
     d->omega0 = omega_outer; d->omega1 = omega_inner; d->n_ext = n_ext;
@@ -222,7 +225,7 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->pstate) cudaFree(d->pstate);
     for (void* q : {(void*)d->role_all, (void*)d->gid_all, (void*)d->seen_all, (void*)d->vslot, (void*)d->slot_nv, (void*)d->slot_fv}) if (q) cudaFree(q);
     for (ShapeDev& s : d->shapes) {
-        void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts, s.rest_radial};
+        void* ptrs[] = {s.tris, s.tri_area, s.links, s.link_len, s.pairs, s.pair_cs, s.v_link_off, s.v_link, s.v_tri_off, s.v_tri, s.v_pair_off, s.v_pair, s.verts, s.rest_radial, s.spread_perm};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
     for (WallPlane& w : d->walls) if (w.vel) cudaFree(w.vel);

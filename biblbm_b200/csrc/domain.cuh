@@ -31,6 +31,7 @@ struct ShapeDev {
     int* v_link_off = nullptr; int* v_link = nullptr;      // entry = link*2 + end
     int* v_tri_off = nullptr;  int* v_tri = nullptr;       // entry = tri*3 + corner
     int* v_pair_off = nullptr; int* v_pair = nullptr;      // entry = pair*4 + corner
+    int* spread_perm = nullptr;   // [nv] vertices along a Morton curve through the rest shape (spread: neighbouring lanes = neighbouring vertices)
     // host copies
     std::vector<int> h_tris, h_links, h_pairs;
     std::vector<double> h_tri_area, h_link_len, h_pair_cs, h_verts;
@@ -179,6 +180,7 @@ struct bib_domain {
     int deterministic_spread = 0;
     int spread_mode = 0;                  // 0 shared-memory tile staging (default), 1 one global atomic per stencil point
     long long lbm_prefetch = 32768;       // BIB_OPT_LBM_PREFETCH: L2 prefetch distance of k_collide_stream in cells (0 = off)
+    int spread_sorted = 1;                // BIB_SPREAD_SORTED (experiments): spread the vertices in space-filling-curve order
     int fused_interp = 1;                 // BIB_OPT_FUSED_INTERPOLATION: band velocity + interpolation in one per-particle tile kernel
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
     int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),

@@ -1629,7 +1629,8 @@ __device__ __forceinline__ void d_tile_pass(const Geo& g, const Band& b, int tot
     }
 }
 __global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const double* __restrict__ pstate, const double* __restrict__ vpos,
-                                                     const double* __restrict__ vfrc, long long cap, int nv, long long first_vertex, int first_particle) {
+                                                     const double* __restrict__ vfrc, long long cap, int nv, long long first_vertex, int first_particle,
+                                                     const int* __restrict__ perm) {
     extern __shared__ double s_tile[];
     const int p = first_particle + blockIdx.x;
     if (g.role && g.role[p] == 0) return;
@@ -1640,7 +1641,10 @@ __global__ void __launch_bounds__(256) k_spread_tile(Geo g, double* force, const
     for (int t = threadIdx.x; t < 3 * total; t += blockDim.x) s_tile[t] = 0.0;
     __syncthreads();
     const long long base = first_vertex + (long long)blockIdx.x * nv;
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    for (int kk = threadIdx.x; kk < nv; kk += blockDim.x) {
+        // lanes of a warp take vertices that are NEIGHBOURS ON THE SURFACE (perm: the shape's vertices along a space-filling curve), so that the
+        // 32 reductions of one instruction fall into few 32-byte sectors of the force field
+        const int v = perm ? perm[kk] : kk;
         const double pp[3] = {vpos[base + v], vpos[cap + base + v], vpos[2 * cap + base + v]};
         const double F[3] = {vfrc[base + v], vfrc[cap + base + v], vfrc[2 * cap + base + v]};
         const int cls = d_classify(g, pp);
@@ -1808,6 +1812,22 @@ int ib_shape_register(bib_domain* d, int nv, int nt, const double* verts, const 
         !to_device(&s.link_len, s.h_link_len) || !to_device(&s.pairs, s.h_pairs) || !to_device(&s.pair_cs, s.h_pair_cs) ||
         !to_device(&s.v_link_off, lo) || !to_device(&s.v_link, ll) || !to_device(&s.v_tri_off, to) || !to_device(&s.v_tri, tl) ||
         !to_device(&s.v_pair_off, po) || !to_device(&s.v_pair, pl) || !to_device(&s.verts, s.h_verts)) return 0;
+    {   // vertices along a Morton curve through the rest shape: consecutive entries are neighbours on the surface (k_spread_tile)
+        double lo[3] = {verts[0], verts[1], verts[2]}, hi[3] = {verts[0], verts[1], verts[2]};
+        for (int v = 0; v < nv; ++v) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], verts[3 * v + c]); hi[c] = std::max(hi[c], verts[3 * v + c]); }
+        std::vector<std::pair<unsigned long long, int>> key(nv);
+        for (int v = 0; v < nv; ++v) {
+            unsigned long long m = 0;
+            unsigned q[3];
+            for (int c = 0; c < 3; ++c) q[c] = (unsigned)(1023.0 * (verts[3 * v + c] - lo[c]) / std::max(hi[c] - lo[c], 1e-300));
+            for (int b = 9; b >= 0; --b) for (int c = 0; c < 3; ++c) m = (m << 1) | ((q[c] >> b) & 1u);
+            key[v] = std::make_pair(m, v);
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> perm(nv);
+        for (int v = 0; v < nv; ++v) perm[v] = key[v].second;
+        if (!to_device(&s.spread_perm, perm)) return 0;
+    }
     d->shapes.push_back(s);
     *shape_id = (int)d->shapes.size() - 1;
     return 1;
@@ -2363,7 +2383,7 @@ int ib_spread(bib_domain* d) {
             Geo sg = make_geo(d);
             if (flags_done) sg.fflag = nullptr;
             k_spread_tile<<<gr.count, 256, smem, d->stream>>>(sg, d->force, d->pstate, d->vpos, d->vfrc, d->cap_vertices, d->shapes[gr.shape].nv,
-                                                         gr.first_vertex, gr.first_particle);
+                                                         gr.first_vertex, gr.first_particle, d->spread_sorted ? d->shapes[gr.shape].spread_perm : nullptr);
             d->launches++;
         }
         d->launches--;
