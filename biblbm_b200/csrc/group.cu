@@ -341,7 +341,12 @@ static int group_particle_io(bib_domain* h, int which, bool upload, long long fi
     return 1;
 }
 int group_vertices_download(bib_domain* h, long long first, long long count, double* v9) { return group_particle_io(h, 0, false, first, count, v9); }
-int group_vertices_upload(bib_domain* h, long long first, long long count, const double* v9) { return group_particle_io(h, 0, true, first, count, const_cast<double*>(v9)); }
+int group_vertices_upload(bib_domain* h, long long first, long long count, const double* v9) {
+    if (!group_particle_io(h, 0, true, first, count, const_cast<double*>(v9))) return 0;
+    // the POS exchange that refreshes the ghost copies is collective: every slab must take part, not only those that hold the particle
+    for (bib_domain* d : h->group->slab) d->ghosts_dirty = true;
+    return 1;
+}
 int group_scalars_download(bib_domain* h, int first, int count, double* s11) { return group_particle_io(h, 1, false, first, count, s11); }
 int group_scalars_upload(bib_domain* h, int first, int count, const double* s11) { return group_particle_io(h, 1, true, first, count, const_cast<double*>(s11)); }
 

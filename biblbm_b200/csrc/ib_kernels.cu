@@ -2685,7 +2685,7 @@ int ib_results_count(bib_domain* d, int* n) {
 int ib_vertices_upload(bib_domain* d, long long first, long long count, const double* v9) {
     d->band_pos_valid = false;
     if (first < 0 || count < 0 || first + count > d->n_vertices) { bib_set_error("vertices_upload: range"); return 0; }
-    if (count == 0) return 1;
+    if (count == 0) { if (d->ms) d->ghosts_dirty = true; return 1; }
     std::vector<double> tmp((size_t)count * 9);
     for (long long v = 0; v < count; ++v) for (int k = 0; k < 9; ++k) tmp[(size_t)k * count + v] = v9[(size_t)v * 9 + k];
     double* dst[3] = {d->vpos, d->vvel, d->vfrc};

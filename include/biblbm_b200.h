@@ -190,6 +190,8 @@ int bib_ib_step(bib_domain* d);
  * forces }; node force := -(sum); move_vertices() (no re-voxelization). Followed by bib_collide_and_stream in the driver's loop. */
 int bib_ib_multi_direct_forcing(bib_domain* d, int relax_iterations);
 int bib_ib_vertices_download(bib_domain* d, long long first_vertex, long long count, double* vertices9);
+/* (one process per GPU: collective - every rank must call it, with count = 0 if it has nothing to upload, because the next interpolation
+ * refreshes the neighbours' ghost copies with a neighbour exchange) */
 int bib_ib_vertices_upload(bib_domain* d, long long first_vertex, long long count, const double* vertices9);
 /* ForceDecorators the library does not implement itself (any user class derived from fsi::ForceDecorator, src/fsi/ForceDecorator.h:11-13,
  * e.g. OpticalTweezerForce of progs/deformation_test/deformation_test.cpp:24-39): the host evaluates them and hands the per-vertex result
