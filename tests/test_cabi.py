@@ -69,6 +69,14 @@ def test_no_cpu_fallback():
         bib.Lattice(8, 8, 8, 1.0, 0.5)
 
 
+def test_no_cpu_fallback_multi_slab():
+    """The multi-slab handle (bib_domain_create_multi, what the overlay's BIB_GPUS=N uses) fails just as loudly without a GPU."""
+    if bib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(bib.BibError, match="no CUDA device"):
+        bib.Lattice(48, 8, 8, 1.0, 0.5, slabs=2, devices=[0, 0])
+
+
 def test_built_for_sm100a():
     import shutil
     import subprocess

@@ -646,6 +646,28 @@ def test_1000_steps_vs_oracle(orc, rbc):
     assert np.array_equal(got[..., 22], ref[..., 22])
 
 
+def test_lattice_kernel_hints_do_not_change_results():
+    """BIB_OPT_LBM_PREFETCH (L2 prefetch ahead of the loads) and the flattened (y, z) thread indexing of ragged row lengths are pure
+    scheduling choices: identical bits on a lattice large enough for the prefetch to be active (> 400 k cells), row length 70."""
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 90, 80, 70
+    cells = np.zeros((nx, ny, nz, 23))
+    cells[..., :19] = 1e-3 * rng.standard_normal((nx, ny, nz, 19))
+    cells[..., 19:22] = 1e-5 * rng.standard_normal((nx, ny, nz, 3))
+    cells[..., 22] = (rng.random((nx, ny, nz)) < 0.3)
+    out = []
+    for pf in (32768.0, 0.0, 1000.0):
+        lat = make_lattice(cells, (1, 0, 1), 1.3, 0.5, {bib.OPT_LBM_PREFETCH: pf})
+        lat.collideAndStream(3)
+        out.append(lat.download())
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+    ref = cells
+    orc = kit.oracle()
+    for _ in range(3):
+        ref = orc.collide_and_stream(ref, (1, 0, 1), 1.3, 0.5)
+    assert np.array_equal(out[0], ref)
+
+
 def test_mass_conservation_large():
     """Size-independent property at a size the oracle is not run at: 192^3 periodic, no force, quirk off => sum(f) and
     sum(c f) conserved to round-off over 20 steps."""
