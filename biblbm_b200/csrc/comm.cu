@@ -274,9 +274,9 @@ int comm_map_peer_buffers(bib_domain* d, double* mine_for_left, double* mine_for
     if (has_left) { NCCL_CHECK(g_nccl.Send(dev, 64, ncclChar, left, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(dev + 128, 64, ncclChar, left, comm, d->stream)); }
     if (has_right) { NCCL_CHECK(g_nccl.Send(dev + 64, 64, ncclChar, right, comm, d->stream)); NCCL_CHECK(g_nccl.Recv(dev + 192, 64, ncclChar, right, comm, d->stream)); }
     NCCL_CHECK(g_nccl.GroupEnd());
-    BIB_CHECK(cudaStreamSynchronize(d->stream));
-    BIB_CHECK(cudaMemcpy(h, dev, sizeof h, cudaMemcpyDeviceToHost));
+    const bool copied = bib_cuda_ok(cudaStreamSynchronize(d->stream), "cudaStreamSynchronize") && bib_cuda_ok(cudaMemcpy(h, dev, sizeof h, cudaMemcpyDeviceToHost), "cudaMemcpy");
     cudaFree(dev);
+    if (!copied) return 0;
     void* p = nullptr;
     if (has_left) { BIB_CHECK(cudaIpcOpenMemHandle(&p, h[2], cudaIpcMemLazyEnablePeerAccess)); *from_left = (const double*)p; }
     if (has_right) { BIB_CHECK(cudaIpcOpenMemHandle(&p, h[3], cudaIpcMemLazyEnablePeerAccess)); *from_right = (const double*)p; }

@@ -296,7 +296,6 @@ int comm_map_peer_buffers(bib_domain* d, double* mine_for_left, double* mine_for
 // in-process slab groups (group.cu)
 bib_domain* group_slab(bib_group* g, int rank);
 void group_barrier(bib_group* g);
-bool group_same_device(bib_group* g);
 inline bool bib_multi(const bib_domain* d) { return d->n_ranks > 1; }
 int ib_local_slots(bib_domain* d, int* gids, int* roles, int capacity, int* n_slots);
 

@@ -45,7 +45,6 @@ struct bib_group {
 };
 
 bib_domain* group_slab(bib_group* g, int rank) { return g->slab[rank]; }
-bool group_same_device(bib_group* g) { return g->same_device; }
 
 void group_barrier(bib_group* g) {
     const int sense = g->bar_sense.load(std::memory_order_acquire);
@@ -273,10 +272,8 @@ int group_shape_register(bib_domain* h, int nv, int nt, const double* vertices, 
 int group_particles_add(bib_domain* h, int type, int shape_id, const double* params, int n, const double* positions) {
     G(h);
     if (n <= 0) return 1;
-    int nl, np; double a, v;
     // every slab is given the same global list and keeps what it owns (+ ghosts), like the ranks of the reference (add_particle)
     if (!group_each(g, [&](int r) { return bib_ib_particles_add(g->slab[r], type, shape_id, params, n, positions); })) return 0;
-    (void)nl; (void)np; (void)a; (void)v;
     const ShapeDev& s = g->slab[0]->shapes[shape_id];
     g->group_nv.push_back(s.nv); g->group_first.push_back(g->n_particles); g->group_count.push_back(n); g->group_first_vertex.push_back(g->n_vertices);
     g->n_particles += n; g->n_vertices += (long long)n * s.nv;
