@@ -651,7 +651,10 @@ static int step_once(bib_domain* d, double body_fx, double body_fy, double body_
         if (!ib_forces(d, d->comm_stream)) return 0;
         BIB_CHECK(cudaEventRecord(d->ev_forces, d->comm_stream));
     }
-    if (!ib_interpolate(d)) return 0;
+    d->defer_vel = d->ms != nullptr;           // multi-slab: one neighbour sync for VEL + FORCE (the forces in between do not read the velocities)
+    const int ok_interp = ib_interpolate(d);
+    d->defer_vel = false;
+    if (!ok_interp) return 0;
     pt_mark(d, PT_X_VEL);
     // setExternalVector(body): the only cells that differ from the body force are those the last spread touched
     if (d->force_is_body && d->force_body[0] == body_fx && d->force_body[1] == body_fy && d->force_body[2] == body_fz) {

@@ -62,15 +62,16 @@ struct MultiSlabIB {                        // one per particle group of a multi
     int* slot_of = nullptr;                // [n_global] -1 when not resident (slot index is domain-wide)
     int* free_stack = nullptr;             // [cap]
     int* counters = nullptr;               // [0] free_top, [1] overflow flag
-    // Exchange buffers [parity][side] (side 0 = packed for the left neighbour, 1 = for the right), [1 + xcap*entry] doubles, element 0
-    // holds the entry count (uint64). Consecutive exchanges alternate the parity, so a neighbour may still be reading exchange n while
-    // exchange n+1 is packed (the sync of exchange n+1 orders pack n+2 after its unpack n).
-    double* send[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    // Exchange buffers [channel][parity][side] (side 0 = packed for the left neighbour, 1 = for the right), [1 + xcap*entry] doubles, element 0
+    // holds the entry count (uint64). Channel 0 carries POS / FORCE / PPF, channel 1 VEL (so that the VEL entries can stay packed while the
+    // forces are evaluated and ONE neighbour sync serves VEL + FORCE). Consecutive exchanges of a channel alternate the parity, so a neighbour
+    // may still be reading exchange n while exchange n+1 is packed (a later sync orders pack n+2 after its unpack n).
+    double* send[2][2][2] = {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}};
     // PULL transport: the neighbours' send buffers mapped into this process / device (in-process group: plain pointers; one process per
-    // GPU: cudaIpcOpenMemHandle). peer[parity][side] = what the neighbour on `side` packed for me. NULL: copy transport (recv buffers).
-    const double* peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    // GPU: cudaIpcOpenMemHandle). peer[channel][parity][side] = what the neighbour on `side` packed for me. NULL: copy transport (recv buffers).
+    const double* peer[2][2][2] = {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}};
     bool pull = false;
-    unsigned xseq = 0;                     // exchanges issued so far (parity = xseq & 1)
+    unsigned xseq[2] = {0, 0};             // exchanges issued so far per channel (parity = xseq & 1)
     double* recv[2] = {nullptr, nullptr};  // copy transport only
 };
 
@@ -231,6 +232,8 @@ struct bib_domain {
     int* vslot = nullptr;            // [cap_vertices] slot of each vertex
     int* slot_nv = nullptr;          // [cap_particles] vertices per slot
     long long* slot_fv = nullptr;    // [cap_particles] first vertex of the slot
+    bool defer_vel = false;          // bib_step: the VEL entries stay packed after the interpolation, their sync is shared with the FORCE exchange
+    bool vel_packed = false;         // ... and are waiting to be unpacked
     bool ghosts_dirty = true;        // ghost copies do not reflect the owners' positions (particles added / uploaded): POS exchange before the next use
 };
 

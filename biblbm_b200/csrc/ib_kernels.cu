@@ -1928,6 +1928,7 @@ int ms_exchange_positions(bib_domain* d);
 int ms_exchange_velocities(bib_domain* d);
 int ms_exchange_forces(bib_domain* d);
 int ms_exchange_pair_forces(bib_domain* d);
+int ms_finish_velocities(bib_domain* d);
 
 // update (and optionally advect) every live particle slot; skip_mask[slot] != 0 leaves a slot alone
 int ib_update_all(bib_domain* d, int do_move) {
@@ -2436,6 +2437,7 @@ int ib_force_accumulate(bib_domain* d, int mode) {
 }
 
 int ib_move_and_voxelize(bib_domain* d) {
+    if (d->ms && !ms_finish_velocities(d)) return 0;       // (a VEL exchange whose sync was deferred and that no FORCE exchange completed)
     for (const ParticleGroup& gr : d->groups) if (!launch_update(d, gr, 1)) return 0;
     pt_mark(d, PT_MOVE);
     if (d->ms && !ms_exchange_positions(d)) return 0;      // refresh ghosts / hand particles over before voxelizing

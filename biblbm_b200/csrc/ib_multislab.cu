@@ -27,7 +27,7 @@ struct MsGeo {
     long long first_vertex;
     size_t entry;
     double my_lo, my_hi, center, GX;    // owned x-range [my_lo, my_hi) in global lattice coordinates
-    int per_x, has_left, has_right;
+    int per_x, has_left, has_right, two_periodic;
 };
 
 __device__ __forceinline__ int d_direction(const MsGeo& g, double com_x) {
@@ -38,6 +38,19 @@ __device__ __forceinline__ int d_direction(const MsGeo& g, double com_x) {
 }
 
 enum { MS_POS = 0, MS_VEL = 1, MS_FORCE = 2, MS_PPF = 3 };
+
+// Does the particle's box (+3 cells) reach into the neighbouring slab on `side` (0 = left, 1 = right)? Periodic images are tested: after
+// a periodic remap of the centre of mass (all vertices shifted by the lattice length) the unwrapped box lies on the far side of the seam.
+__device__ __forceinline__ bool d_reaches(const MsGeo& g, double blo, double bhi, int side) {
+    const double W = g.my_hi - g.my_lo;
+    const double t_lo = side == 0 ? g.my_lo - W : g.my_hi, t_hi = side == 0 ? g.my_lo : g.my_hi + W;
+    for (int k = -1; k <= 1; ++k) {
+        if (k != 0 && !g.per_x) continue;
+        const double a = blo - 3.0 + k * g.GX, b = bhi + 3.0 + k * g.GX;
+        if (b > t_lo && a < t_hi) return true;
+    }
+    return false;
+}
 
 // one CTA per slot of the group: append {gid, flag, payload[3][nv]} to the buffer of `side` (0 = left neighbour, 1 = right)
 __global__ void __launch_bounds__(128) k_ms_pack(MsGeo g, int kind, const int* __restrict__ role, const int* __restrict__ gid_of,
@@ -55,10 +68,16 @@ __global__ void __launch_bounds__(128) k_ms_pack(MsGeo g, int kind, const int* _
     } else if (r == 1) {
         const double* st = pstate + (long long)s * 11;
         const int dirn = d_direction(g, st[2]);
-        const bool reach = side == 0 ? (st[5] - 3.0 < g.my_lo) : (st[6] + 3.0 > g.my_hi);
         const bool handoff = (side == 0 && dirn < 0) || (side == 1 && dirn > 0);
-        take = reach || handoff;
+        take = handoff || d_reaches(g, st[5], st[6], side);
         flag = handoff ? 1.0 : 0.0;
+        // Two slabs on a periodic axis: the left and the right neighbour are the SAME slab. One entry per particle, not one per side (two
+        // entries of one particle would be unpacked concurrently there: an ownership hand-off could be overwritten by the plain ghost entry).
+        if (g.two_periodic) {
+            const bool other_handoff = (side == 0 && dirn > 0) || (side == 1 && dirn < 0);
+            const bool other_take = other_handoff || d_reaches(g, st[5], st[6], 1 - side);
+            if (other_take && (other_handoff || (!handoff && side == 0))) take = false;      // the hand-off side wins, else side 1
+        }
     }
     if (side == 0 ? !g.has_left : !g.has_right) take = false;
     if (!take) return;
@@ -152,6 +171,7 @@ MsGeo make_ms_geo(const bib_domain* d, const MultiSlabIB* m) {
     g.my_lo = (double)d->x_offset - 0.5; g.my_hi = (double)(d->x_offset + d->nx) - 0.5;
     g.center = 0.5 * (g.my_lo + g.my_hi); g.GX = (double)d->gnx; g.per_x = d->per[0];
     g.has_left = d->per[0] || d->rank > 0; g.has_right = d->per[0] || d->rank < d->n_ranks - 1;
+    g.two_periodic = d->per[0] && d->n_ranks == 2;
     return g;
 }
 
@@ -159,49 +179,64 @@ MsGeo make_ms_geo(const bib_domain* d, const MultiSlabIB* m) {
 // launch for both sides), one stream-ordered neighbour sync for all groups, then the unpack kernel READS THE NEIGHBOURS' BUFFERS over
 // NVLink peer memory (both sides in one launch): only the entries actually packed cross the link, no staging copy, no NCCL data
 // transfer. COPY transport (BIB_IB_EXCHANGE=copy): the whole fixed-capacity buffers travel by ncclSend/ncclRecv / cudaMemcpyPeer.
-int ms_exchange(bib_domain* d, int kind, const double* src, double* dst) {
+int channel_of(int kind) { return kind == MS_VEL ? 1 : 0; }
+int ms_pack(bib_domain* d, int kind, const double* src) {
+    const int ch = channel_of(kind);
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
         const MsGeo g = make_ms_geo(d, m);
-        const int par = m->xseq & 1;
-        k_ms_clear_counts<<<1, 1, 0, d->stream>>>(m->send[par][0], m->send[par][1]);
-        k_ms_pack<<<dim3(m->cap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, d->pstate, src, d->cap_vertices, m->send[par][0], m->send[par][1], m->counters);
+        const int par = m->xseq[ch] & 1;
+        k_ms_clear_counts<<<1, 1, 0, d->stream>>>(m->send[ch][par][0], m->send[ch][par][1]);
+        k_ms_pack<<<dim3(m->cap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, d->pstate, src, d->cap_vertices, m->send[ch][par][0], m->send[ch][par][1], m->counters);
         d->launches += 2;
     }
     BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+// the transfer step: copy transport moves the buffers, pull transport only orders the streams
+int ms_transfer(bib_domain* d, int kind) {
+    const int ch = channel_of(kind);
     bool any_pull = false;
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
         if (m->pull) { any_pull = true; continue; }
         const size_t nd = 1 + (size_t)m->xcap * m->entry;
-        const int par = m->xseq & 1;
-        if (!comm_exchange_pair(d, m->send[par][0], m->send[par][1], m->recv[0], m->recv[1], nd)) return 0;
+        const int par = m->xseq[ch] & 1;
+        if (!comm_exchange_pair(d, m->send[ch][par][0], m->send[ch][par][1], m->recv[0], m->recv[1], nd)) return 0;
     }
     if (any_pull && !comm_neighbour_sync(d)) return 0;
+    return 1;
+}
+int ms_unpack(bib_domain* d, int kind, double* dst) {
+    const int ch = channel_of(kind);
     const bool has_left = d->per[0] || d->rank > 0, has_right = d->per[0] || d->rank < d->n_ranks - 1;
     for (size_t gi = 0; gi < d->msv.size(); ++gi) {
         MultiSlabIB* m = d->msv[gi];
         if (!m) continue;
         const MsGeo g = make_ms_geo(d, m);
-        const int par = m->xseq & 1;
+        const int par = m->xseq[ch] & 1;
         const double *b0 = m->recv[0], *b1 = m->recv[1];
         if (m->pull) {
             if (d->group) {           // in-process: the neighbours' buffers are plain pointers (same device or peer access enabled)
                 const int right = (d->rank + 1) % d->n_ranks, left = (d->rank + d->n_ranks - 1) % d->n_ranks;
-                b0 = group_slab(d->group, left)->msv[gi]->send[par][1];
-                b1 = group_slab(d->group, right)->msv[gi]->send[par][0];
-            } else { b0 = m->peer[par][0]; b1 = m->peer[par][1]; }
+                b0 = group_slab(d->group, left)->msv[gi]->send[ch][par][1];
+                b1 = group_slab(d->group, right)->msv[gi]->send[ch][par][0];
+            } else { b0 = m->peer[ch][par][0]; b1 = m->peer[ch][par][1]; }
             if (!has_left) b0 = nullptr;
             if (!has_right) b1 = nullptr;
         }
         k_ms_unpack<<<dim3(m->xcap, 2), 128, 0, d->stream>>>(g, kind, d->role_all, d->gid_all, m->slot_of, m->free_stack, m->counters, d->seen_all,
                                                             b0, b1, dst, d->cap_vertices, m->gid_base);
         d->launches++;
-        m->xseq++;
+        m->xseq[ch]++;
     }
     BIB_CHECK(cudaGetLastError());
     return 1;
 }
+int ms_exchange(bib_domain* d, int kind, const double* src, double* dst) {
+    return ms_pack(d, kind, src) && ms_transfer(d, kind) && ms_unpack(d, kind, dst);
+}
+bool all_pull(const bib_domain* d) { for (const MultiSlabIB* m : d->msv) if (m && !m->pull) return false; return true; }
 
 }  // namespace
 
@@ -220,15 +255,15 @@ int ms_create(bib_domain* d, int nv, int n_global, int cap_hint, int xcap_hint, 
     m->pull = !(mode && std::string(mode) == "copy");
     bool ok = bib_cuda_ok(cudaMalloc(&m->slot_of, std::max(1, n_global) * sizeof(int)), "cudaMalloc") &&
               bib_cuda_ok(cudaMalloc(&m->free_stack, std::max(1, m->cap) * sizeof(int)), "cudaMalloc") && bib_cuda_ok(cudaMalloc(&m->counters, 2 * sizeof(int)), "cudaMalloc");
-    for (int par = 0; ok && par < 2; ++par) for (int s = 0; ok && s < 2; ++s)
-        ok = bib_cuda_ok(cudaMalloc(&m->send[par][s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMemset(m->send[par][s], 0, sizeof(double)), "cudaMemset");
+    for (int ch = 0; ok && ch < 2; ++ch) for (int par = 0; ok && par < 2; ++par) for (int s = 0; ok && s < 2; ++s)
+        ok = bib_cuda_ok(cudaMalloc(&m->send[ch][par][s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMemset(m->send[ch][par][s], 0, sizeof(double)), "cudaMemset");
     for (int s = 0; ok && !m->pull && s < 2; ++s)
         ok = bib_cuda_ok(cudaMalloc(&m->recv[s], nd * sizeof(double)), "cudaMalloc") && bib_cuda_ok(cudaMemset(m->recv[s], 0, sizeof(double)), "cudaMemset");
     // pull transport, one process per GPU: map the neighbours' send buffers (collective: every rank adds its particle groups in the same order)
-    for (int par = 0; ok && m->pull && !d->group && par < 2; ++par)
-        ok = comm_map_peer_buffers(d, m->send[par][0], m->send[par][1], &m->peer[par][0], &m->peer[par][1]) != 0;
+    for (int ch = 0; ok && m->pull && !d->group && ch < 2; ++ch) for (int par = 0; ok && par < 2; ++par)
+        ok = comm_map_peer_buffers(d, m->send[ch][par][0], m->send[ch][par][1], &m->peer[ch][par][0], &m->peer[ch][par][1]) != 0;
     if (!ok) { delete m; return 0; }
-    d->bytes += (long long)(4 * nd * sizeof(double));
+    d->bytes += (long long)(8 * nd * sizeof(double));
     *out = m;
     return 1;
 }
@@ -257,8 +292,11 @@ int ms_set_initial(bib_domain* d, MultiSlabIB* m, const std::vector<int>& owned_
 void ms_destroy(bib_domain* d) {
     for (MultiSlabIB* m : d->msv) {
         if (!m) continue;
-        for (int par = 0; par < 2; ++par) for (int s = 0; s < 2; ++s) if (m->peer[par][s]) cudaIpcCloseMemHandle((void*)m->peer[par][s]);
-        void* ptrs[] = {m->slot_of, m->free_stack, m->counters, m->send[0][0], m->send[0][1], m->send[1][0], m->send[1][1], m->recv[0], m->recv[1]};
+        for (int ch = 0; ch < 2; ++ch) for (int par = 0; par < 2; ++par) for (int s = 0; s < 2; ++s) {
+            if (m->peer[ch][par][s]) cudaIpcCloseMemHandle((void*)m->peer[ch][par][s]);
+            if (m->send[ch][par][s]) cudaFree(m->send[ch][par][s]);
+        }
+        void* ptrs[] = {m->slot_of, m->free_stack, m->counters, m->recv[0], m->recv[1]};
         for (void* p : ptrs) if (p) cudaFree(p);
         delete m;
     }
@@ -282,8 +320,22 @@ int ms_exchange_positions(bib_domain* d) {
     d->ghosts_dirty = false;
     return ib_update_all(d, 0);      // recompute the cached scalars of ghost / newly owned slots (owners are masked out), nothing moves
 }
-int ms_exchange_velocities(bib_domain* d) { return ms_exchange(d, MS_VEL, d->vvel, d->vvel); }
-int ms_exchange_forces(bib_domain* d) { return ms_exchange(d, MS_FORCE, d->vfrc, d->vfrc); }
+// VEL: bib_step defers the sync (d->defer_vel): the entries are packed right after the interpolation and unpacked together with the FORCE
+// entries, behind ONE neighbour sync (the membrane forces in between do not read the vertex velocities). Pull transport only.
+int ms_exchange_velocities(bib_domain* d) {
+    if (d->defer_vel && all_pull(d)) { d->vel_packed = true; return ms_pack(d, MS_VEL, d->vvel); }
+    return ms_exchange(d, MS_VEL, d->vvel, d->vvel);
+}
+int ms_finish_velocities(bib_domain* d) {          // stand-alone completion (no FORCE exchange follows)
+    if (!d->vel_packed) return 1;
+    d->vel_packed = false;
+    return ms_transfer(d, MS_VEL) && ms_unpack(d, MS_VEL, d->vvel);
+}
+int ms_exchange_forces(bib_domain* d) {
+    if (!d->vel_packed) return ms_exchange(d, MS_FORCE, d->vfrc, d->vfrc);
+    d->vel_packed = false;
+    return ms_pack(d, MS_FORCE, d->vfrc) && ms_transfer(d, MS_FORCE) && ms_unpack(d, MS_VEL, d->vvel) && ms_unpack(d, MS_FORCE, d->vfrc);
+}
 int ms_exchange_pair_forces(bib_domain* d) { return ms_exchange(d, MS_PPF, d->vfrc, d->vfrc); }
 
 int ms_check_overflow(bib_domain* d) {
