@@ -431,6 +431,61 @@ def parity_gate(bib, dist, torch, rank, world, local):
         cases.append({"case": f"rbcs_in_channel class: {n_p} RBCs, wall planes (x-dependent velocity), plates, body force, Morse wall + particle-particle forces, {gx}x{ny}x{nz}",
                       "steps": steps, "rel_err": err, "pass": bool(ok)})
         worst = max(worst, err)
+    # (d) a dense suspension at size: the rbcs_in_channel arrangement (progs/rbcs_in_channel/rbcs_in_channel.cpp:161-184: flat RBCs, minor axis along x,
+    #     pitch 5.3 along x (near contacts: the pair force is active), five rows across the channel, staggered along z) on a (32 N) x 83 x 81 lattice, 90 RBCs per slab (N = 8: 480 RBCs,
+    #     300 k vertices), plates, wall planes, body force, Morse wall + particle-particle forces, 100 steps
+    if not os.environ.get("BIB_GATE_SKIP_SUSPENSION"):
+        nxl, ny, nz, steps = 32, 83, 81, 100
+        gx = nxl * world
+        disk = flat_rbc(rbc_pos, 0)
+        npx, npy = int(gx // 5.3), 5
+        npz = 3 if npx * npy * 3 <= 450 else 2             # 90 RBCs per slab up to 4 slabs, 480 RBCs on 8 (bounds the oracle's run to about a minute)
+        dx, dy, dz = gx / npx, (ny - 1 - 4) / npy, nz / npz
+        rng = np.random.default_rng(3)
+        pos = []
+        for i in range(npx):
+            for j in range(npy):
+                for k in range(npz):
+                    r = rng.uniform(-0.5, 0.5, 3)
+                    c = np.array([(i + 0.5) * dx + 1.0 * r[0], 2.0 + (j + 0.5) * dy + 0.5 * r[1], (k + 0.25 + (0.0 if j % 2 == 0 else 0.5)) * dz + r[2]])
+                    pos.append(disk + c)
+        pos = np.array(pos)
+        n_p = pos.shape[0]
+        body_s = (2e-5, 0.0, 0.0)
+        zero = np.zeros((gx, nz, 3))
+        lat = make(nxl, ny, nz, 1.0, 1 / 3, (1, 0, 1))
+        lat.initializeAtEquilibrium(1.0, (0.02, 0.0, 0.004))        # a moving start: populations of O(1e-2), so that the relative error is not an artefact of |fBar| ~ 1e-5
+        cells0 = gather_cells(lat)
+        lat.addVelocityBoundary((0, nxl - 1, 0, 0, 0, nz - 1), 1, -1, zero[:nxl][:, None])
+        lat.addVelocityBoundary((0, nxl - 1, ny - 1, ny - 1, 0, nz - 1), 1, +1, zero[:nxl][:, None])
+        lat.set_boundary(0.0, float(ny - 1))
+        lat.set_wall_interaction(bib.POTENTIAL_MORSE, *wall_morse)
+        lat.set_pp_interaction(bib.POTENTIAL_MORSE, *pp_morse)
+        sid = lat.register_shape(shape.verts, shape.tris)
+        lat.add_particles(sid, params, pos)
+        lat.step(body_s, n=steps)
+        lat.sync()
+        got_v, got_s, owners = gather_particles(lat, n_p, shape.nv)
+        got = gather_cells(lat)
+        lat.close()
+        if rank == 0:
+            t_or = time.time()
+            vert = np.zeros((n_p, shape.nv, 9)); vert[..., :3] = pos
+            state = np.array([orc.particle_update(shape, p) for p in pos])
+            ref = cells0.copy()
+            orc.set_parallel_plates(1, 0.0, float(ny - 1))
+            orc.set_wall_interaction(bib.POTENTIAL_MORSE, *wall_morse)
+            orc.set_pp_interaction(bib.POTENTIAL_MORSE, *pp_morse)
+            try:
+                for _ in range(steps):
+                    ref, _v = orc.shear_step(ref, 1.0, 1 / 3, body_s, zero, zero, shape, params, vert, state)
+            finally:
+                orc.reset_modes()
+            err = max(kit.rel_err(got_v[..., :3], vert[..., :3]), kit.rel_err(got[..., :19], ref[..., :19]))
+            ok = err <= 1e-9 and np.array_equal(got[..., 22], ref[..., 22]) and bool((owners == 1).all())
+            cases.append({"case": f"dense suspension in the rbcs_in_channel arrangement: {n_p} RBCs ({n_p * shape.nv} vertices), plates, wall planes, body force, Morse wall + "
+                                  f"particle-particle forces, {gx}x{ny}x{nz}", "steps": steps, "rel_err": err, "pass": bool(ok), "oracle_seconds": round(time.time() - t_or, 1)})
+            worst = max(worst, err)
     res = {"against": "CPU oracle (oracle/biblbm_oracle.c) on the undivided lattice", "n_slabs": world, "cases": cases, "max_rel_err": worst,
            "tolerance": 1e-9, "pass": bool(all(c["pass"] for c in cases))} if rank == 0 else None
     return res
