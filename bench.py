@@ -432,14 +432,15 @@ def parity_gate(bib, dist, torch, rank, world, local):
                       "steps": steps, "rel_err": err, "pass": bool(ok)})
         worst = max(worst, err)
     # (d) a dense suspension at size: the rbcs_in_channel arrangement (progs/rbcs_in_channel/rbcs_in_channel.cpp:161-184: flat RBCs, minor axis along x,
-    #     pitch 5.3 along x (near contacts: the pair force is active), five rows across the channel, staggered along z) on a (32 N) x 83 x 81 lattice, 90 RBCs per slab (N = 8: 480 RBCs,
-    #     300 k vertices), plates, wall planes, body force, Morse wall + particle-particle forces, 100 steps
+    #     pitch 5.3 along x (near contacts: the pair force is active), five rows across the channel, staggered along z) on a (32 N) x 83 x 81 lattice, 90 RBCs per slab (N = 8: 384 RBCs,
+    #     240 k vertices), plates, wall planes, body force, Morse wall + particle-particle forces, 100 steps
     if not os.environ.get("BIB_GATE_SKIP_SUSPENSION"):
         nxl, ny, nz, steps = 32, 83, 81, 100
         gx = nxl * world
         disk = flat_rbc(rbc_pos, 0)
-        npx, npy = int(gx // 5.3), 5
-        npz = 3 if npx * npy * 3 <= 450 else 2             # 90 RBCs per slab up to 4 slabs, 480 RBCs on 8 (bounds the oracle's run to about a minute)
+        npx, npy, npz = int(gx // 5.3), 5, 3
+        if npx * npy * npz > 450:                          # 90 RBCs per slab up to 4 slabs, 384 RBCs on 8 (bounds the oracle's run to about a minute)
+            npy, npz = 4, 2
         dx, dy, dz = gx / npx, (ny - 1 - 4) / npy, nz / npz
         rng = np.random.default_rng(3)
         pos = []
