@@ -525,6 +525,7 @@ def ours(args):
         sampler.start()
     t_sampler = time.time()
 
+    bib.set_default_inplace(args.inplace)       # before the parity gate: its lattices use the layout the timed lattice uses
     parity = None
     if not args.no_parity:
         parity = parity_gate(bib, dist, torch, rank, world, local)
@@ -551,6 +552,7 @@ def ours(args):
         lat.add_particles(sid, params, rbc_positions(rbc_pos, n_rbc_global, (nx * world, ny, nz), 0, seed=7))
         nvert_global = n_rbc_global * verts.shape[0]
     lat.sync()
+    inplace_shift = lat.inplace_shift()
 
     def step(n=1):
         if n_rbc_global > 0:
@@ -733,7 +735,8 @@ def ours(args):
             drv = driver_speed()
         line = {"metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K,
                 "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": (w1 - w0) * 1e3 / ((len(blocks) + 1) * K), "higher_is_better": True,
-                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(workload_config(args, world), population_storage=(f"in place, shift {inplace_shift} planes" if inplace_shift else "two buffers (A/B)")),
                 "repeats": repeats, "roofline": roofline, "ib": ib, "phases_ms": phases, "parity_check": parity, "cpu_baseline": cpu,
                 "e2e": e2e, "e2e_all_vertices": e2e_all, "driver_e2e": drv, "gpu_launches": int(round(launches_per_block)), "clocks": clocks,
                 "device_bytes": dev_bytes if drv is not None else lat.device_bytes()}
@@ -763,6 +766,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-slab parity gate")
     ap.add_argument("--overlap-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_OVERLAP_FORCES (experiments)")
     ap.add_argument("--prefetch-forces", type=int, default=1, choices=[0, 1], help="BIB_OPT_PREFETCH_FORCES (experiments)")
+    ap.add_argument("--inplace", type=int, default=-1, help="population storage: 0 two buffers (A/B), >= 2 in-place streaming with that shift (planes), "
+                    "-1 A/B when it fits the device and in place otherwise (bib_set_default_inplace)")
     ap.add_argument("--face-swap", type=int, default=1, choices=[0, 1, 2], help="BIB_OPT_FUSED_FACE_SWAP (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -25,7 +25,7 @@ SYMBOLS = [
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload", "bib_ib_vertex_forces_preload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_lightweight_download_async", "bib_ib_results_wait", "bib_ib_results_count", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
-    "bib_kernel_launch_count", "bib_device_memory_bytes", "bib_phase_timing", "bib_phase_times",
+    "bib_kernel_launch_count", "bib_device_memory_bytes", "bib_phase_timing", "bib_phase_times", "bib_set_default_inplace", "bib_domain_inplace_shift",
 ]
 
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES, OPT_PREFETCH_FORCES = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -78,6 +78,11 @@ def device_count() -> int:
     return n.value if ok else 0
 
 
+def set_default_inplace(shift_planes: int) -> None:
+    """Population storage of the lattices created from now on: 0 two buffers, >= 2 in place with that shift, -1 automatic."""
+    _check(load_library().bib_set_default_inplace(int(shift_planes)))
+
+
 def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(load_library().bib_comm_unique_id(buf))
@@ -105,6 +110,11 @@ class Lattice:
             _check(self.lib.bib_domain_create(self.nx, self.ny, self.nz, self.n_ext, C.c_double(omega), C.c_double(omega_inner or 0.0), per, int(device), C.byref(self.h)))
         self.full = (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1)
         self.shape_nv = {}
+
+    def inplace_shift(self) -> int:
+        n = C.c_int(0)
+        _check(self.lib.bib_domain_inplace_shift(self.h, C.byref(n)))
+        return n.value
 
     def close(self):
         if self.h:

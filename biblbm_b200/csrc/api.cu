@@ -95,6 +95,29 @@ int bib_device_count(int* count) {
     return 1;
 }
 
+// Population storage of the domains created from now on: 0 = two buffers (A/B), > 0 = in-place streaming with that many planes of
+// shift (section 4a of DESIGN.md), -1 (default) = A/B when it fits the device, in-place otherwise. BIB_INPLACE in the environment sets
+// the initial value (tests run the whole parity suite in both layouts that way).
+static int g_default_inplace = -2;
+static int default_inplace() {
+    if (g_default_inplace == -2) {
+        g_default_inplace = -1;
+        if (const char* e = std::getenv("BIB_INPLACE")) g_default_inplace = std::atoi(e);
+    }
+    return g_default_inplace;
+}
+int bib_set_default_inplace(int shift_planes) {
+    if (shift_planes < -1 || shift_planes == 1) { bib_set_error("set_default_inplace: -1 (automatic), 0 (two buffers) or a shift of >= 2 planes"); return 0; }
+    g_default_inplace = shift_planes;
+    return 1;
+}
+int bib_domain_inplace_shift(bib_domain* d, int* shift_planes) {
+    if (!d) { bib_set_error("null domain handle"); return 0; }
+    if (!shift_planes) { bib_set_error("domain_inplace_shift: null argument"); return 0; }
+    *shift_planes = d->is_head ? group_slab_of(d, 0)->inplace_shift : d->inplace_shift;
+    return 1;
+}
+
 // The halo exchange is issued while the interior-plane launch (a million CTAs) is still queued: without a higher priority the
 // block scheduler would drain that grid first and the exchange would run after it instead of underneath it.
 static cudaError_t create_comm_stream(cudaStream_t* st) {
@@ -133,10 +156,18 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     d->vol = (size_t)(nx + 2) * d->plane;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t need = d->vol * (2 * BIB_Q + 3) * sizeof(double) + d->vol + (size_t)(nx + 2) * ny + (64 << 20);
+    size_t need = d->vol * (2 * BIB_Q + 3) * sizeof(double) + d->vol + (size_t)(nx + 2) * ny + (64 << 20);
+    // In-place streaming: forced (shift > 0), or chosen when the two-buffer layout does not fit this device (auto)
+    const int inplace_req = default_inplace();
+    if (inplace_req > 0 || (inplace_req < 0 && need > free_b)) {
+        d->inplace_shift = inplace_req > 0 ? std::max(2, inplace_req) : 17;
+        d->vol = (size_t)(nx + 2 + d->inplace_shift) * d->plane;
+        need = d->vol * (BIB_Q + 3) * sizeof(double) + d->vol + (size_t)(nx + 2) * ny + (64 << 20);
+    }
     if (need > free_b) {
         char buf[256];
-        std::snprintf(buf, sizeof buf, "domain_create: lattice needs %.1f GB of HBM, %.1f GB free", need / 1e9, free_b / 1e9);
+        std::snprintf(buf, sizeof buf, "domain_create: lattice needs %.1f GB of HBM%s, %.1f GB free", need / 1e9,
+                      d->inplace_shift ? " (in-place streaming)" : "", free_b / 1e9);
         bib_set_error(buf); delete d; return 0;
     }
     bool ok = bib_cuda_ok(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
@@ -146,9 +177,15 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_compute, cudaEventDisableTiming), "cudaEventCreate") &&
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming), "cudaEventCreate") &&
               bib_cuda_ok(cudaEventCreateWithFlags(&d->ev_forces, cudaEventDisableTiming), "cudaEventCreate");
-    for (int b = 0; ok && b < 2; ++b) {
-        ok = bib_cuda_ok(cudaMalloc(&d->f[b], d->vol * BIB_Q * sizeof(double)), "cudaMalloc(populations)") &&
-             bib_cuda_ok(cudaMemsetAsync(d->f[b], 0, d->vol * BIB_Q * sizeof(double), d->stream), "cudaMemset");
+    if (d->inplace_shift) {
+        ok = ok && bib_cuda_ok(cudaMalloc(&d->f_base, d->vol * BIB_Q * sizeof(double)), "cudaMalloc(populations)") &&
+             bib_cuda_ok(cudaMemsetAsync(d->f_base, 0, d->vol * BIB_Q * sizeof(double), d->stream), "cudaMemset");
+        if (ok) { d->f[1] = d->f_base; d->f[0] = d->f_base + (size_t)d->inplace_shift * d->plane; }
+    } else {
+        for (int b = 0; ok && b < 2; ++b) {
+            ok = bib_cuda_ok(cudaMalloc(&d->f[b], d->vol * BIB_Q * sizeof(double)), "cudaMalloc(populations)") &&
+                 bib_cuda_ok(cudaMemsetAsync(d->f[b], 0, d->vol * BIB_Q * sizeof(double), d->stream), "cudaMemset");
+        }
     }
     ok = ok && bib_cuda_ok(cudaMalloc(&d->force, d->vol * 3 * sizeof(double)), "cudaMalloc(force)") &&
          bib_cuda_ok(cudaMemsetAsync(d->force, 0, d->vol * 3 * sizeof(double), d->stream), "cudaMemset") &&
@@ -157,7 +194,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
          bib_cuda_ok(cudaMemsetAsync(d->col_flags, 0, (size_t)(nx + 2) * ny + 4, d->stream), "cudaMemset") &&
          bib_cuda_ok(cudaStreamSynchronize(d->stream), "cudaStreamSynchronize");
     if (!ok) { bib_domain_destroy(d); return 0; }
-    d->bytes = (long long)(d->vol * (2 * BIB_Q + 3) * sizeof(double) + d->vol);
+    d->bytes = (long long)(d->vol * ((d->inplace_shift ? 1 : 2) * BIB_Q + 3) * sizeof(double) + d->vol);
     *out = d;
     return 1;
 }
@@ -191,7 +228,8 @@ int bib_domain_destroy(bib_domain* d) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     comm_destroy(d);
     ms_destroy(d);
-    for (int b = 0; b < 2; ++b) if (d->f[b]) cudaFree(d->f[b]);
+    if (d->f_base) cudaFree(d->f_base);
+    else for (int b = 0; b < 2; ++b) if (d->f[b]) cudaFree(d->f[b]);
     if (d->force) cudaFree(d->force);
     if (d->phase) cudaFree(d->phase);
     if (d->kind) cudaFree(d->kind);

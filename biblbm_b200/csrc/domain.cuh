@@ -3,6 +3,7 @@
 // HBM layout (all fp64 unless stated; z fastest, then y, then x; x carries one ghost plane on each side so that a slab's
 // x-faces are contiguous ny*nz planes that can be sent/received without packing):
 //   f[2][19][nx+2][ny][nz]   population buffers A/B holding PRE-collision fBar (= what the reference's cells hold)
+//                            (in-place mode: one allocation [19][nx+2+S][ny][nz] seen through two frames S planes apart, see bib_domain)
 //   force[3][nx+2][ny][nz]   total external force (body + spread IB force), the reference's external scalars 0..2
 //   phase[nx+2][ny][nz] u8   bit0 = inside/outside phase (reference external scalar 3, exactly 0.0/1.0), bit1 = voxelizer toggle mark
 //   kind[nx+2][ny][nz]  u8   optional cell kinds (allocated on first bib_domain_set_celltype)
@@ -132,6 +133,13 @@ struct bib_domain {
     size_t vol = 0;                       // (nx+2)*ny*nz  (storage incl. ghost planes)
     int cur = 0;                          // which population buffer holds the current state
     double* f[2] = {nullptr, nullptr};
+    // In-place streaming (BIB_INPLACE / bib_set_default_inplace): ONE population allocation of nx+2+shift planes per
+    // direction; the two "buffers" are the same memory seen through two frames shifted by `inplace_shift` planes along x
+    // (f[1] = f_base, f[0] = f_base + inplace_shift*plane) and `vol` (the component stride of every field) is (nx+2+shift)*plane.
+    // A step pushes from one frame into the other in launches of at most shift-1 planes, ordered so that no launch writes a plane
+    // a later launch still has to read. 0 = two separate buffers (A/B).
+    int inplace_shift = 0;
+    double* f_base = nullptr;
     double* force = nullptr;
     uint8_t* phase = nullptr;
     uint8_t* kind = nullptr;

@@ -45,6 +45,7 @@ struct LbmParams {
     // fused envelope quirk (SWAP != 0): is this slab's low / high x face a GLOBAL periodic face
     int swap_x_lo, swap_x_hi;
     long long prefetch_cells;     // L2 prefetch distance of the main body (cells ahead in memory order; 0 = off)
+    long long pf_end;             // first cell index the prefetch must not reach (the high ghost plane)
     int flat;                     // thread index runs over the flattened (y, z) plane (grid.y == 1)
 };
 
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(128, (HAS_KIND && HAS_WALLS) ? 4 : BIB_LBM_MIN
         // cells = 256 KB per population stream; the hint holds no register): the kernel is latency-bound at 5 CTAs / SM, an L2 hit shortens
         // the wait of those warps. Measured on the bench slab: 6.82 -> 6.66 ms (16 / 64 rows: 6.70; 128 rows: 7.04; 256 rows: 8.67, evicted before use).
         const long long pf = idx + p.prefetch_cells;
-        if (pf < p.vol - p.plane) {
+        if (pf < p.pf_end) {
 #pragma unroll
             for (int i = 0; i < BIB_Q; ++i) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.fin + (long long)i * p.vol + pf));
         }
@@ -726,6 +727,24 @@ __global__ void k_edge_velocity_fill(double* vel, const double* __restrict__ vel
     vel[idx] = v[0]; vel[vol + idx] = v[1]; vel[2 * vol + idx] = v[2];
 }
 
+// In-place streaming on one slab with periodic x: the populations pushed into the ghost planes re-enter on the other side. A slot whose
+// upstream cell lies beyond a y / z wall was filled by the local bounce and is left alone (same rule as k_halo_merge between slabs).
+__global__ void k_ghost_wrap(double* f, long long vol, long long plane, int nx, int ny, int nz, int per_y, int per_z) {
+    const int plus_x[5] = {10, 13, 14, 15, 16}, minus_x[5] = {1, 4, 5, 6, 7};
+    const long long n = 10 * plane;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / plane);
+        const long long c = t - (long long)k * plane;
+        const int y = (int)(c / nz), z = (int)(c - (long long)y * nz);
+        const int i = k < 5 ? plus_x[k] : minus_x[k - 5];
+        const int sy = y - c_cy[i], sz = z - c_cz[i];
+        if ((!per_y && (sy < 0 || sy >= ny)) || (!per_z && (sz < 0 || sz >= nz))) continue;
+        double* pop = f + (long long)i * vol;
+        if (k < 5) pop[plane + c] = pop[(long long)(nx + 1) * plane + c];
+        else pop[(long long)nx * plane + c] = pop[c];
+    }
+}
+
 bool box_ok(const bib_domain* d, const int box[6]) {
     return box[0] >= 0 && box[1] < d->nx && box[0] <= box[1] && box[2] >= 0 && box[3] < d->ny && box[2] <= box[3] &&
            box[4] >= 0 && box[5] < d->nz && box[4] <= box[5];
@@ -759,7 +778,9 @@ static LbmParams make_params(bib_domain* d) {
     p.omega0 = d->omega0; p.omega1 = d->omega1;
     p.per_y = d->per[1]; p.per_z = d->per[2];
     const bool first = d->rank == 0, last = d->rank == d->n_ranks - 1;
-    if (d->n_ranks == 1) { p.x_lo_mode = p.x_hi_mode = d->per[0] ? 1 : 2; }
+    // (in place: a periodic x of a single slab goes through the ghost planes like a slab face - a push wrapped inside the array would land
+    // on planes the later launches of the step still have to read - and lbm_ghost_wrap carries the ghost planes over afterwards)
+    if (d->n_ranks == 1) { p.x_lo_mode = p.x_hi_mode = d->per[0] ? (d->inplace_shift ? 0 : 1) : 2; }
     else {
         p.x_lo_mode = (first && !d->per[0]) ? 2 : 0;
         p.x_hi_mode = (last && !d->per[0]) ? 2 : 0;
@@ -768,6 +789,7 @@ static LbmParams make_params(bib_domain* d) {
     p.swap_x_lo = d->per[0] && first; p.swap_x_hi = d->per[0] && last;
     // only worth it when the lattice does not fit the 126 MB L2 anyway (A + B populations of 400 k cells)
     p.prefetch_cells = (d->lbm_prefetch > 0 && d->vol > (size_t)400000) ? d->lbm_prefetch : 0;
+    p.pf_end = (long long)(d->nx + 1) * (long long)d->plane;
     p.flat = (d->nz % 128 != 0 && d->plane < ((size_t)1 << 30)) ? 1 : 0;
     return p;
 }
@@ -776,6 +798,7 @@ static LbmParams make_params(bib_domain* d) {
 static int fused_swap_mode(const bib_domain* d) {
     if (!d->envelope_swap || d->omega0 == d->omega1 || d->omega1 == 0.0) return 0;      // equal rates / one rate: the swap changes nothing
     if (!(d->per[0] || d->per[1] || d->per[2])) return 0;
+    if (d->inplace_shift) return 1;      // a separate fix-up pass would re-read source planes the step has already overwritten
     return d->fused_face_swap;
 }
 static void launch_main(bib_domain* d, const LbmParams& p, int n_planes, cudaStream_t st) {
@@ -815,8 +838,47 @@ static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x
 // planes go first, their ghost planes are exchanged over NCCL on the communication stream WHILE the interior planes are
 // processed on the compute stream (the exchange writes populations c_x=+-1 of planes 1 / nx, the interior launch writes
 // the other populations of those planes: disjoint arrays).
+// In-place streaming. The source frame f[cur] and the destination frame f[1 - cur] are the same allocation
+// displaced by S = inplace_shift planes: storage plane of (frame 0, x) = x + 1 + S, of (frame 1, x) = x + 1. A launch over the planes
+// [a, a + C) reads storage planes a + 1 + S .. a + C + S and pushes into a .. a + C + 1 (frame 0 -> 1; mirrored for 1 -> 0), so with
+// C <= S - 1 it never writes a plane it reads, and taking the launches in ascending x (frame 0 -> 1; descending for 1 -> 0) every plane a
+// launch overwrites has been read by an earlier launch of the same stream. Every destination slot is still written exactly once.
+static int launch_inplace(bib_domain* d, const LbmParams& p) {
+    const int C = d->inplace_shift - 1;
+    const bool ascending = d->cur == 0;
+    for (int done = 0; done < d->nx; done += C) {
+        const int n = std::min(C, d->nx - done);
+        LbmParams pc = p;
+        pc.x_first = ascending ? done : d->nx - done - n;
+        pc.x_stride = 1;
+        launch_main(d, pc, n, d->stream);
+    }
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+// single slab, periodic x, in place: what the halo exchange does between slabs (ghost plane nx+1 -> plane 1, ghost plane 0 -> plane nx)
+static int lbm_ghost_wrap(bib_domain* d) {
+    const long long n = 10 * (long long)d->plane;
+    k_ghost_wrap<<<grid_for(n, 256), 256, 0, d->stream>>>(d->f[d->cur], (long long)d->vol, (long long)d->plane, d->nx, d->ny, d->nz, d->per[1], d->per[2]);
+    d->launches++;
+    BIB_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int lbm_launch_collide_stream(bib_domain* d) {
     LbmParams p = make_params(d);
+    if (d->inplace_shift) {
+        // the halo of several slabs is not hidden in this mode (the plane that feeds one of the two ghost planes is processed last); it is
+        // meant for slabs too large for two buffers, where the exchange is ~1 % of the step
+        if (!launch_inplace(d, p)) return 0;
+        pt_mark(d, PT_LBM);
+        d->cur = 1 - d->cur;
+        if (d->n_ranks > 1) { if (!comm_halo_exchange(d, d->stream)) return 0; pt_mark(d, PT_HALO_WAIT); }
+        else if (d->per[0] && !lbm_ghost_wrap(d)) return 0;
+        const int okw = lbm_apply_walls(d) && lbm_apply_guo(d);
+        pt_mark(d, PT_WALLS);
+        return okw;
+    }
     if (d->n_ranks == 1 || d->nx < 3) {
         launch_main(d, p, d->nx, d->stream);
         launch_faces(d, p, 63, 0, d->stream);

@@ -83,6 +83,15 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
  * asynchronous results read-back (bib_domain_slab gives the per-slab handles for that), planes normal to x. n_slabs == 1 is bib_domain_create. */
 int bib_domain_create_multi(int nx, int ny, int nz, int n_ext, double omega_outer, double omega_inner, const int periodic[3],
                             int n_slabs, const int* devices, bib_domain** out);
+/* In-place streaming (the reference streams in place too: BlockLattice3D::bulkStream swaps populations with the neighbours inside one
+ * array, src/atomicBlock/blockLattice3D.hh:500-551). Population storage of the domains created AFTER this call:
+ *   0  two buffers A/B (304 B of HBM per cell for the populations),
+ *  >=2 ONE buffer of nx + 2 + shift planes (152 B per cell + shift planes): a step pushes into the same memory displaced by `shift`
+ *      planes along x, in launches of shift - 1 planes ordered so that nothing unread is overwritten; results are bit-identical,
+ *  -1  (default) A/B when it fits the device, in place (shift 17) when it does not.
+ * The environment variable BIB_INPLACE gives the initial value. bib_domain_inplace_shift reports what a domain uses (0 = A/B). */
+int bib_set_default_inplace(int shift_planes);
+int bib_domain_inplace_shift(bib_domain* d, int* shift_planes);
 int bib_domain_slab_count(bib_domain* d, int* n_slabs);
 int bib_domain_slab(bib_domain* d, int slab, bib_domain** out);      /* the handle of one slab (owned by the multi-slab handle) */
 int bib_domain_destroy(bib_domain* d);

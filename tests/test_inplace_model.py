@@ -1,0 +1,136 @@
+"""CPU model of the in-place streaming schedule (biblbm_b200/csrc/lbm_kernels.cu: launch_inplace, k_ghost_wrap).
+
+One population buffer of nx + 2 + S planes is seen through two frames S planes apart; a step pushes from one frame into the other in
+launches of at most S - 1 planes, ascending in x for frame 0 -> 1 and descending for 1 -> 0. The model replays exactly that address
+arithmetic with numpy on a small lattice (pure streaming, every population value unique) and checks, for every launch, that
+ (1) no launch writes a storage location that it or a LATER launch of the step still has to read (the threads of a launch run in
+     any order, launches of a stream run in order),
+ (2) every destination slot is written exactly once,
+ (3) after the ghost-plane wrap the lattice equals plain two-buffer push streaming with the reference's boundary rule (a population
+     that would leave through a non-periodic face stays in the cell's opposite slot: src/atomicBlock/blockLattice3D.hh:402-427)."""
+import itertools
+
+import numpy as np
+import pytest
+
+CX = [0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0]
+CY = [0, 0, -1, 0, -1, 1, 0, 0, -1, -1, 0, 1, 0, 1, -1, 0, 0, 1, 1]
+CZ = [0, 0, 0, -1, 0, 0, -1, 1, -1, 1, 0, 0, 1, 0, 0, 1, -1, 1, -1]
+OPP = [0] + [i + 9 for i in range(1, 10)] + [i - 9 for i in range(10, 19)]
+
+
+def stream_two_buffers(f, per):
+    """f[19][nx][ny][nz] -> streamed copy (push; wrap on periodic axes, stay in the opposite slot at non-periodic faces)."""
+    n = f.shape[1:]
+    out = np.full_like(f, np.nan)
+    for i in range(19):
+        for x, y, z in itertools.product(range(n[0]), range(n[1]), range(n[2])):
+            t = [x + CX[i], y + CY[i], z + CZ[i]]
+            blocked = False
+            for k in range(3):
+                if t[k] < 0 or t[k] >= n[k]:
+                    if per[k]:
+                        t[k] %= n[k]
+                    else:
+                        blocked = True
+            if blocked:
+                out[OPP[i], x, y, z] = f[i, x, y, z]
+            else:
+                out[i, t[0], t[1], t[2]] = f[i, x, y, z]
+    return out
+
+
+class InPlace:
+    def __init__(self, f, per, shift):
+        self.nx, self.ny, self.nz = f.shape[1:]
+        self.per, self.S = per, shift
+        self.mem = np.full((19, self.nx + 2 + shift, self.ny, self.nz), np.nan)
+        self.cur = 0
+        self.mem[:, self.base(0) + 1:self.base(0) + 1 + self.nx] = f
+
+    def base(self, frame):                  # f[0] = f_base + shift planes, f[1] = f_base
+        return self.S if frame == 0 else 0
+
+    def state(self):
+        b = self.base(self.cur)
+        return self.mem[:, b + 1:b + 1 + self.nx].copy()
+
+    def step(self):
+        nx, ny, nz, S = self.nx, self.ny, self.nz, self.S
+        src, dst = self.base(self.cur), self.base(1 - self.cur)
+        C = S - 1
+        ascending = self.cur == 0
+        chunks = []
+        done = 0
+        while done < nx:
+            n = min(C, nx - done)
+            a = done if ascending else nx - done - n
+            chunks.append((a, a + n))
+            done += C
+        unread = np.zeros(self.mem.shape[1], dtype=bool)
+        unread[src + 1:src + 1 + nx] = True
+        written = np.zeros(self.mem.shape, dtype=np.int32)
+        for a, b in chunks:
+            writes = []
+            for x in range(a, b):
+                for i, y, z in itertools.product(range(19), range(ny), range(nz)):
+                    v = self.mem[i, src + 1 + x, y, z]
+                    tx, ty, tz = x + CX[i], y + CY[i], z + CZ[i]          # x: always into the ghost planes (x mode 0) unless a wall
+                    blocked = False
+                    if (tx < 0 or tx >= nx) and not self.per[0]:
+                        blocked = True
+                    if ty < 0 or ty >= ny:
+                        if self.per[1]: ty %= ny
+                        else: blocked = True
+                    if tz < 0 or tz >= nz:
+                        if self.per[2]: tz %= nz
+                        else: blocked = True
+                    writes.append((OPP[i], dst + 1 + x, y, z, v) if blocked else (i, dst + 1 + tx, ty, tz, v))
+            for i, p, y, z, v in writes:
+                assert not unread[p], f"launch [{a},{b}) overwrites storage plane {p}, which is still to be read"
+            for i, p, y, z, v in writes:
+                self.mem[i, p, y, z] = v
+                written[i, p, y, z] += 1
+            unread[src + 1 + a:src + 1 + b] = False
+        assert not unread.any()
+        self.cur = 1 - self.cur
+        if self.per[0]:                     # k_ghost_wrap
+            b0 = self.base(self.cur)
+            for i in range(19):
+                if CX[i] == 0:
+                    continue
+                for y, z in itertools.product(range(ny), range(nz)):
+                    sy, sz = y - CY[i], z - CZ[i]
+                    if (not self.per[1] and (sy < 0 or sy >= ny)) or (not self.per[2] and (sz < 0 or sz >= nz)):
+                        continue
+                    if CX[i] > 0:
+                        self.mem[i, b0 + 1, y, z] = self.mem[i, b0 + nx + 1, y, z]; written[i, b0 + 1, y, z] += 1
+                    else:
+                        self.mem[i, b0 + nx, y, z] = self.mem[i, b0, y, z]; written[i, b0 + nx, y, z] += 1
+        b0 = self.base(self.cur)
+        assert (written[:, b0 + 1:b0 + 1 + nx] == 1).all(), "every slot of the new state is written exactly once"
+
+
+@pytest.mark.parametrize("shift", [2, 3, 4, 9])
+@pytest.mark.parametrize("per", [(1, 1, 1), (0, 1, 0), (1, 0, 1), (0, 0, 0)])
+def test_inplace_schedule_equals_two_buffer_streaming(per, shift):
+    nx, ny, nz = 7, 3, 4
+    f = np.arange(19 * nx * ny * nz, dtype=np.float64).reshape(19, nx, ny, nz) + 1.0
+    model = InPlace(f, per, shift)
+    ref = f
+    for step in range(5):
+        model.step()
+        ref = stream_two_buffers(ref, per)
+        assert np.array_equal(model.state(), ref), f"step {step + 1}"
+
+
+def test_launches_wider_than_the_shift_would_clobber():
+    """The bound the schedule relies on: with launches of S planes (instead of S - 1) a launch writes into planes it reads itself."""
+    nx, ny, nz, S = 7, 2, 2, 3
+    src, dst = S, 0
+    a, b = 0, S                              # a launch of S planes, frame 0 -> 1
+    read = set(range(src + 1 + a, src + 1 + b))
+    wrote = set(range(dst + 1 + a - 1, dst + 1 + b + 1))
+    assert read & wrote
+    b = S - 1
+    assert not (set(range(src + 1 + a, src + 1 + b)) & set(range(dst + 1 + a - 1, dst + 1 + b + 1)))
