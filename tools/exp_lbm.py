@@ -15,8 +15,12 @@ ap.add_argument("--rbcs", type=int, default=1250)
 ap.add_argument("--seconds", type=float, default=1.5)
 ap.add_argument("--nx", type=int, default=128)
 ap.add_argument("--prefetch", type=int, default=-1)
+ap.add_argument("--inplace", type=int, default=-1)
+ap.add_argument("--ny", type=int, default=1024)
+ap.add_argument("--nz", type=int, default=1024)
 a = ap.parse_args()
-lat = bib.Lattice(a.nx, 1024, 1024, 1.0, 1 / 3)
+bib.set_default_inplace(a.inplace)
+lat = bib.Lattice(a.nx, a.ny, a.nz, 1.0, 1 / 3)
 lat.set_option(bib.OPT_FUSED_FACE_SWAP, float(a.face_swap))
 lat.set_option(bib.OPT_ENVELOPE_SWAP, float(a.envelope))
 if a.prefetch >= 0:
@@ -26,7 +30,7 @@ body = (1e-6, 0.0, 0.0)
 if a.rbcs:
     verts, tris, params, rbc_pos = bench.load_rbc()
     sid = lat.register_shape(verts, tris)
-    lat.add_particles(sid, params, bench.rbc_positions(rbc_pos, a.rbcs, (a.nx, 1024, 1024), 0, seed=7))
+    lat.add_particles(sid, params, bench.rbc_positions(rbc_pos, a.rbcs, (a.nx, a.ny, a.nz), 0, seed=7))
 lat.setExternalVector(body)      # production state: every cell holds the body force, force flags valid (sparse force reads)
 lat.sync()
 def timed(fn, K=20):
@@ -37,7 +41,7 @@ def timed(fn, K=20):
         lat.time_begin(); fn(K); out.append(lat.time_end() / K)
     return out
 k = timed(lambda n: lat.collideAndStream(n))
-res = {"tag": a.tag, "lib": os.environ.get("BIB_LIB", "default"), "prefetch": a.prefetch, "face_swap": a.face_swap, "envelope": a.envelope,
+res = {"tag": a.tag, "inplace_shift": lat.inplace_shift(), "dims": [a.nx, a.ny, a.nz], "device_bytes": lat.device_bytes(), "lib": os.environ.get("BIB_LIB", "default"), "prefetch": a.prefetch, "face_swap": a.face_swap, "envelope": a.envelope,
        "lbm_ms_first": k[0], "lbm_ms_median": float(np.median(k)), "lbm_ms_min": float(np.min(k))}
 if a.rbcs:
     s = timed(lambda n: lat.step(body, n=n))
