@@ -202,6 +202,13 @@ struct bib_domain {
     void* nccl_comm = nullptr;
     double* token = nullptr;              // 4 doubles: neighbour-sync tokens (comm_neighbour_sync)
     double* halo_stage = nullptr;         // [10][ny*nz] received ghost planes when y or z has walls
+    // Population halo as a PULL (comm.cu): one kernel reads the neighbours' ghost planes over peer memory (NVLink) straight into this slab's
+    // boundary planes. One process per GPU: the neighbours' population allocations are mapped with cudaIpcOpenMemHandle at the first exchange.
+    bool halo_peer_ok = true;             // in-process slab group: both neighbours' memory can be read by this device's kernels
+    int halo_pull = -1;                   // -1 not decided yet, 0 ncclSend / ncclRecv of the planes (BIB_HALO=nccl), 1 pull kernel
+    const double* peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side 0 left / 1 right][frame]: the neighbour's f[frame]
+    long long peer_vol[2] = {0, 0}; int peer_nx[2] = {0, 0};
+    void* peer_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};         // what cudaIpcOpenMemHandle returned (closed by comm_destroy)
     int x_offset = 0;                     // global x of local plane 0
     int gnx = 0;                          // global nx
     // IB

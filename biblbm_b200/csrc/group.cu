@@ -147,6 +147,7 @@ int group_create(int nx, int ny, int nz, int n_ext, double omega_outer, double o
             int can = 0;
             cudaDeviceCanAccessPeer(&can, a, b);
             if (can) { cudaSetDevice(a); const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = bib_cuda_ok(e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
+            else g->slab[r]->halo_peer_ok = false;      // the population halo falls back to cudaMemcpyPeerAsync (staged through the host by the driver)
         }
     }
     if (!ok) {
