@@ -41,9 +41,14 @@ def stream_two_buffers(f, per):
 
 
 class InPlace:
-    def __init__(self, f, per, shift):
+    def __init__(self, f, per, shift, x_lo_wall=None, x_hi_wall=None, self_wrap=True):
+        """x_lo_wall / x_hi_wall: is the low / high x face of THIS slab a wall (default: the lattice is one slab, walls iff x is not periodic);
+        self_wrap: the slab is its own x-neighbour (k_ghost_wrap); False: halo_pull() fills the boundary planes from the neighbours."""
         self.nx, self.ny, self.nz = f.shape[1:]
         self.per, self.S = per, shift
+        self.x_lo_wall = (not per[0]) if x_lo_wall is None else x_lo_wall
+        self.x_hi_wall = (not per[0]) if x_hi_wall is None else x_hi_wall
+        self.self_wrap = self_wrap
         self.mem = np.full((19, self.nx + 2 + shift, self.ny, self.nz), np.nan)
         self.cur = 0
         self.mem[:, self.base(0) + 1:self.base(0) + 1 + self.nx] = f
@@ -77,7 +82,7 @@ class InPlace:
                     v = self.mem[i, src + 1 + x, y, z]
                     tx, ty, tz = x + CX[i], y + CY[i], z + CZ[i]          # x: always into the ghost planes (x mode 0) unless a wall
                     blocked = False
-                    if (tx < 0 or tx >= nx) and not self.per[0]:
+                    if (tx < 0 and self.x_lo_wall) or (tx >= nx and self.x_hi_wall):
                         blocked = True
                     if ty < 0 or ty >= ny:
                         if self.per[1]: ty %= ny
@@ -94,7 +99,8 @@ class InPlace:
             unread[src + 1 + a:src + 1 + b] = False
         assert not unread.any()
         self.cur = 1 - self.cur
-        if self.per[0]:                     # k_ghost_wrap
+        self.written = written
+        if self.per[0] and self.self_wrap:  # k_ghost_wrap
             b0 = self.base(self.cur)
             for i in range(19):
                 if CX[i] == 0:
@@ -107,8 +113,29 @@ class InPlace:
                         self.mem[i, b0 + 1, y, z] = self.mem[i, b0 + nx + 1, y, z]; written[i, b0 + 1, y, z] += 1
                     else:
                         self.mem[i, b0 + nx, y, z] = self.mem[i, b0, y, z]; written[i, b0 + nx, y, z] += 1
+        if self.self_wrap:
+            self.check_written_once()
+
+    def check_written_once(self):
         b0 = self.base(self.cur)
-        assert (written[:, b0 + 1:b0 + 1 + nx] == 1).all(), "every slot of the new state is written exactly once"
+        assert (self.written[:, b0 + 1:b0 + 1 + self.nx] == 1).all(), "every slot of the new state is written exactly once"
+
+    def halo_pull(self, left, right):
+        """k_halo_pull (comm.cu): c_x = +1 populations from the left neighbour's ghost plane nx_l + 1 into my plane 1, c_x = -1 populations
+        from the right neighbour's ghost plane 0 into my plane nx; holes behind y / z walls are skipped."""
+        ny, nz = self.ny, self.nz
+        b0 = self.base(self.cur)
+        for i in range(19):
+            if CX[i] == 0:
+                continue
+            for y, z in itertools.product(range(ny), range(nz)):
+                sy, sz = y - CY[i], z - CZ[i]
+                if (not self.per[1] and (sy < 0 or sy >= ny)) or (not self.per[2] and (sz < 0 or sz >= nz)):
+                    continue
+                if CX[i] > 0 and left is not None:
+                    self.mem[i, b0 + 1, y, z] = left.mem[i, left.base(left.cur) + left.nx + 1, y, z]; self.written[i, b0 + 1, y, z] += 1
+                if CX[i] < 0 and right is not None:
+                    self.mem[i, b0 + self.nx, y, z] = right.mem[i, right.base(right.cur), y, z]; self.written[i, b0 + self.nx, y, z] += 1
 
 
 @pytest.mark.parametrize("shift", [2, 3, 4, 9])
@@ -134,3 +161,29 @@ def test_launches_wider_than_the_shift_would_clobber():
     assert read & wrote
     b = S - 1
     assert not (set(range(src + 1 + a, src + 1 + b)) & set(range(dst + 1 + a - 1, dst + 1 + b + 1)))
+
+
+@pytest.mark.parametrize("per", [(1, 1, 1), (0, 1, 0), (1, 0, 1)])
+@pytest.mark.parametrize("widths,shifts", [((4, 3), (3, 3)), ((3, 4, 3), (2, 4, 0 + 5))])
+def test_inplace_slabs_with_pulled_halo_equal_the_undivided_lattice(per, widths, shifts):
+    """Several x-slabs of unequal width, every slab in place with its OWN shift (the layouts of the ranks may differ), halo as a pull from the
+    neighbours' ghost planes after all launches of the step: equal to two-buffer streaming of the undivided lattice."""
+    gx, ny, nz = sum(widths), 3, 4
+    f = np.arange(19 * gx * ny * nz, dtype=np.float64).reshape(19, gx, ny, nz) + 1.0
+    x0 = np.concatenate([[0], np.cumsum(widths)])
+    n = len(widths)
+    slabs = [InPlace(f[:, x0[r]:x0[r + 1]], per, shifts[r], x_lo_wall=(r == 0 and not per[0]), x_hi_wall=(r == n - 1 and not per[0]), self_wrap=False)
+             for r in range(n)]
+    ref = f
+    for step in range(4):
+        for s in slabs:
+            s.step()
+        for r, s in enumerate(slabs):              # every slab has finished its launches ("ghost planes written") before anybody pulls
+            left = slabs[(r - 1) % n] if (per[0] or r > 0) else None
+            right = slabs[(r + 1) % n] if (per[0] or r < n - 1) else None
+            s.halo_pull(left, right)
+        for s in slabs:
+            s.check_written_once()
+        ref = stream_two_buffers(ref, per)
+        got = np.concatenate([s.state() for s in slabs], axis=1)
+        assert np.array_equal(got, ref), f"step {step + 1}"
