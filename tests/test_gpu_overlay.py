@@ -70,15 +70,17 @@ def _need(*exes):
             pytest.skip(f"{e} not built (overlay/build_drivers.sh needs the reference sources)")
 
 
-def test_rbc_in_shear_driver_bit_identical(tmp_path, mesh):
+@pytest.mark.parametrize("inplace", ["0", "17"])
+def test_rbc_in_shear_driver_bit_identical(tmp_path, mesh, inplace):
     """progs/rbc_in_shear (BASELINE.json configs[0]) at the driver's own size (97^3, lambda = 8.48, Couette walls, position
-    regulator): 31 steps, outputs every 10."""
+    regulator): 31 steps, outputs every 10. With two population buffers and with in-place streaming (BIB_INPLACE: one buffer, a step
+    in 7 launches of 16 planes): the layout must be invisible in every output file."""
     _need(B200 / "rbc_in_shear_short_b200", CPU / "rbc_in_shear_short_cpu")
     env = dict(BIB_NT="30", BIB_OUTPUT_INTERVAL="10", BIB_NCASES="1", BIB_MESH=str(mesh), BIB_SHRINK_ITERS="2000")
     d_cpu = tmp_path / "cpu"; d_gpu = tmp_path / "gpu"
     d_cpu.mkdir(); d_gpu.mkdir()
     out_cpu = run_driver(CPU / "rbc_in_shear_short_cpu", d_cpu, env)
-    out_gpu = run_driver(B200 / "rbc_in_shear_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1"))
+    out_gpu = run_driver(B200 / "rbc_in_shear_short_b200", d_gpu, dict(env, BIB_DETERMINISTIC_SPREAD="1", BIB_INPLACE=inplace))
     assert out_gpu == out_cpu
     files = all_files(d_cpu)
     assert files == all_files(d_gpu) and len(files) >= 8
