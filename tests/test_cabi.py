@@ -42,6 +42,19 @@ def test_bad_arguments_return_zero():
     assert not h
 
 
+def test_default_inplace_argument_checking():
+    """bib_set_default_inplace: -1 (automatic), 0 (two buffers) or a shift of >= 2 planes; nothing else (a shift of 1 leaves no plane per launch)."""
+    lib = bib.load_library()
+    try:
+        for ok in (-1, 0, 2, 17, 1000):
+            assert lib.bib_set_default_inplace(ok) == 1
+        for bad in (1, -2, -100):
+            assert lib.bib_set_default_inplace(bad) == 0
+            assert b"set_default_inplace" in lib.bib_last_error()
+    finally:
+        lib.bib_set_default_inplace(-1)
+
+
 def test_null_handle_is_rejected_by_every_entry_point():
     """Every entry point that takes a domain handle returns 0 (never crashes) for a NULL handle and names the problem."""
     lib = bib.load_library()
