@@ -19,15 +19,16 @@ PLUS_X = [10, 13, 14, 15, 16]
 MINUS_X = [1, 4, 5, 6, 7]
 
 
-def push_step(orc, slab, omega0, omega1, rank, world, per):
-    """slab: [nx][ny][nz][23] -> (new slab, ghost_lo[5][ny][nz], ghost_hi[5][ny][nz]) before the halo exchange."""
+def push_planes(orc, chunk, a, nx, dest, dest_plane0, omega0, omega1, rank, world, per):
+    """chunk: the cells of the slab's planes [a, a + n) as [n][ny][nz][23]; their post-collision populations are pushed into
+    dest[19][planes][ny][nz], where plane x of the slab is stored at dest_plane0 + x (the ghost planes at dest_plane0 - 1 and
+    dest_plane0 + nx): periodic wrap in y / z, ghost planes in x, the envelope quirk only at the GLOBAL periodic faces."""
     import ctypes as C
-    nx, ny, nz, _ = slab.shape
-    post = slab.copy()
-    orc.lib.orc_collide_cells(post.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(nx * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(0))
-    env = slab.copy()
-    orc.lib.orc_collide_cells(env.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(nx * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(1))
-    f = np.zeros((19, nx + 2, ny, nz))            # destination buffer with ghost planes
+    n, ny, nz, _ = chunk.shape
+    post = chunk.copy()
+    orc.lib.orc_collide_cells(post.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(n * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(0))
+    env = chunk.copy()
+    orc.lib.orc_collide_cells(env.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(n * ny * nz), C.c_double(omega0), C.c_double(omega1), C.c_int(1))
     first, last = rank == 0, rank == world - 1
     for i in range(19):
         cx, cy, cz = kit.C19[i]
@@ -42,12 +43,51 @@ def push_step(orc, slab, omega0, omega1, rank, world, per):
             if cz == 1: val[:, :, -1] = src_e[:, :, -1]
             if cz == -1: val[:, :, 0] = src_e[:, :, 0]
         if per[0]:
-            if cx == 1 and last: val[-1] = src_e[-1]
-            if cx == -1 and first: val[0] = src_e[0]
+            if cx == 1 and last and a + n == nx: val[-1] = src_e[-1]
+            if cx == -1 and first and a == 0: val[0] = src_e[0]
         assert per[1] and per[2], "model covers periodic y/z"
         shifted = np.roll(val, (cy, cz), axis=(1, 2))
-        f[i, 1 + cx:1 + cx + nx] = shifted        # x: into the ghost planes, no wrap
+        dest[i, dest_plane0 + a + cx:dest_plane0 + a + cx + n] = shifted        # x: into the ghost planes, no wrap
+
+
+def push_step(orc, slab, omega0, omega1, rank, world, per):
+    """Two buffers: slab [nx][ny][nz][23] -> fresh destination buffer f[19][nx + 2][ny][nz] (ghost planes 0 and nx + 1) before the halo exchange."""
+    nx, ny, nz, _ = slab.shape
+    f = np.zeros((19, nx + 2, ny, nz))
+    push_planes(orc, slab, 0, nx, f, 1, omega0, omega1, rank, world, per)
     return f
+
+
+class InPlaceSlab:
+    """In-place streaming (biblbm_b200/csrc/lbm_kernels.cu: launch_inplace): ONE buffer of nx + 2 + S planes seen through two
+    frames S planes apart (frame 1 at plane 0, frame 0 at plane S); a step pushes from frame `cur` into the other one in launches of S - 1 planes,
+    ascending in x for 0 -> 1 and descending for 1 -> 0, so that no launch overwrites a plane that it or a later launch still reads."""
+
+    def __init__(self, slab, shift):
+        self.nx, self.ny, self.nz, _ = slab.shape
+        self.S, self.cur = shift, 0
+        self.mem = np.full((19, self.nx + 2 + shift, self.ny, self.nz), np.nan)
+        self.ext = slab[..., 19:].copy()                      # force + phase (not streamed)
+        self.mem[:, shift + 1:shift + 1 + self.nx] = np.moveaxis(slab[..., :19], -1, 0)
+
+    def base(self, frame):
+        return self.S if frame == 0 else 0
+
+    def frame(self):                                          # the current frame incl. its two ghost planes: [19][nx + 2][ny][nz] (a view)
+        b = self.base(self.cur)
+        return self.mem[:, b:b + self.nx + 2]
+
+    def step(self, orc, omega0, omega1, rank, world, per):
+        nx, C = self.nx, self.S - 1
+        src, dst = self.base(self.cur), self.base(1 - self.cur)
+        for done in range(0, nx, C):
+            n = min(C, nx - done)
+            a = done if self.cur == 0 else nx - done - n
+            chunk = np.concatenate([np.moveaxis(self.mem[:, src + 1 + a:src + 1 + a + n], 0, -1), self.ext[a:a + n]], axis=-1)
+            assert not np.isnan(chunk).any(), "a launch read a plane that an earlier launch of the step had overwritten with nothing valid"
+            push_planes(orc, np.ascontiguousarray(chunk), a, nx, self.mem, dst + 1, omega0, omega1, rank, world, per)
+        self.cur = 1 - self.cur
+        return self.frame()
 
 
 def main():
@@ -65,8 +105,10 @@ def main():
     slab = cells[rank * nxl:(rank + 1) * nxl].copy()
     right, left = (rank + 1) % world, (rank - 1) % world
     steps = 4
+    shift = int(os.environ.get("SLAB_MODEL_INPLACE", "0"))    # 0: two buffers; S >= 2: every rank streams in place with shift S + rank (layouts may differ)
+    inplace = InPlaceSlab(slab, shift + rank) if shift else None
     for _ in range(steps):
-        f = push_step(orc, slab, 1.5, 0.6, rank, world, per)
+        f = inplace.step(orc, 1.5, 0.6, rank, world, per) if inplace else push_step(orc, slab, 1.5, 0.6, rank, world, per)
         # halo: ghost plane nx+1 (c_x=+1 pops) -> right neighbour's plane 1; ghost plane 0 (c_x=-1) -> left neighbour's plane nx
         send_r = torch.from_numpy(np.ascontiguousarray(f[PLUS_X, nxl + 1]))
         send_l = torch.from_numpy(np.ascontiguousarray(f[MINUS_X, 0]))
@@ -86,7 +128,7 @@ def main():
         for _ in range(steps):
             ref = orc.collide_and_stream(ref, per, 1.5, 0.6)
         ok = bool(np.array_equal(got, ref))
-        print(f"gloo slab model world={world}: bit-identical={ok}")
+        print(f"gloo slab model world={world} inplace_shift={shift}: bit-identical={ok}")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
