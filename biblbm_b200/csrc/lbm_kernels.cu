@@ -834,10 +834,6 @@ static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x
     d->launches++;
 }
 
-// One lattice step. Single slab: one launch over all planes (+ the periodic-face fix-up). Several slabs: the two boundary
-// planes go first, their ghost planes are exchanged over NCCL on the communication stream WHILE the interior planes are
-// processed on the compute stream (the exchange writes populations c_x=+-1 of planes 1 / nx, the interior launch writes
-// the other populations of those planes: disjoint arrays).
 // In-place streaming. The source frame f[cur] and the destination frame f[1 - cur] are the same allocation
 // displaced by S = inplace_shift planes: storage plane of (frame 0, x) = x + 1 + S, of (frame 1, x) = x + 1. A launch over the planes
 // [a, a + C) reads storage planes a + 1 + S .. a + C + S and pushes into a .. a + C + 1 (frame 0 -> 1; mirrored for 1 -> 0), so with
@@ -865,6 +861,10 @@ static int lbm_ghost_wrap(bib_domain* d) {
     return 1;
 }
 
+// One lattice step. Single slab: one launch over all planes (+ the periodic-face fix-up). Several slabs: the two boundary
+// planes go first, their ghost planes are exchanged over NCCL on the communication stream WHILE the interior planes are
+// processed on the compute stream (the exchange writes populations c_x=+-1 of planes 1 / nx, the interior launch writes
+// the other populations of those planes: disjoint arrays).
 int lbm_launch_collide_stream(bib_domain* d) {
     LbmParams p = make_params(d);
     if (d->inplace_shift) {
