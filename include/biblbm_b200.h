@@ -240,7 +240,11 @@ int bib_ib_particle_scalars_upload(bib_domain* d, int first_particle, int count,
 int bib_step(bib_domain* d, double body_fx, double body_fy, double body_fz, int n_steps);
 
 /* ---- multi-GPU, one process per GPU: x-slab ring over NCCL (replaces ParallelBlockCommunicator3D::duplicateOverlaps,
- *      src/parallelism/parallelBlockCommunicator3D.cpp:144-233). unique_id: the 128 bytes of an ncclUniqueId. */
+ *      src/parallelism/parallelBlockCommunicator3D.cpp:144-233). unique_id: the 128 bytes of an ncclUniqueId.
+ *      NCCL carries set-up data and 1-element synchronisation tokens; the payloads (the 5 populations crossing each slab face, the
+ *      particle records) are read by this library's kernels from the neighbours' buffers over NVLink peer memory (cudaIpc mappings made at
+ *      the first exchange). Environment: BIB_HALO=nccl moves the population planes with ncclSend / ncclRecv instead, BIB_IB_EXCHANGE=copy
+ *      the particle buffers (same value on every rank). */
 int bib_comm_unique_id(void* unique_id_128);
 int bib_comm_init(bib_domain* d, int rank, int n_ranks, const void* unique_id_128);
 
