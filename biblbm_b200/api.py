@@ -32,6 +32,7 @@ OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT
 OPT_FUSED_INTERPOLATION = 10
 OPT_FUSE_CALLS = 11
 OPT_LBM_PREFETCH = 12
+OPT_INTERP_COMPACT = 13
 CELL_BULK, CELL_NODYNAMICS, CELL_BOUNCEBACK = 0, 1, 2
 PARTICLE_RBC, PARTICLE_CAPSULE, PARTICLE_SEMIRIGID = 0, 1, 2
 POTENTIAL_NONE, POTENTIAL_MORSE, POTENTIAL_SPRING = 0, 1, 2

@@ -149,6 +149,7 @@ int bib_domain_create(int nx, int ny, int nz, int n_ext, double omega_outer, dou
     if (!d) { bib_set_error("domain_create: out of host memory"); return 0; }
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) d->n_sms = sms; }
     if (d_spread_sorted_env >= 0) d->spread_sorted = d_spread_sorted_env;
+    if (const char* ic = std::getenv("BIB_INTERP_COMPACT")) d->interp_compact = std::atoi(ic) != 0;      // experiments / tests: initial value of BIB_OPT_INTERP_COMPACT
     d->device = device; d->nx = nx; d->ny = ny; d->nz = nz; d->gnx = nx; d->x_offset = 0;
     for (int k = 0; k < 3; ++k) d->per[k] = periodic[k] ? 1 : 0;
     d->omega0 = omega_outer; d->omega1 = omega_inner; d->n_ext = n_ext;
@@ -327,6 +328,7 @@ int bib_domain_set_option(bib_domain* d, int key, double value) {
         case BIB_OPT_LBM_PREFETCH: d->lbm_prefetch = value > 0.0 ? (long long)value : 0; return 1;
         case BIB_OPT_FUSE_CALLS: d->fuse_calls = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_FUSED_INTERPOLATION: d->fused_interp = value != 0.0 ? 1 : 0; return 1;
+        case BIB_OPT_INTERP_COMPACT: d->interp_compact = value != 0.0 ? 1 : 0; return 1;
         case BIB_OPT_SPARSE_FORCE: d->sparse_force = value != 0.0 ? 1 : 0; d->fflag_valid = false; return 1;
     }
     bib_set_error("set_option: unknown key");

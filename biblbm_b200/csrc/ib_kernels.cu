@@ -1461,7 +1461,7 @@ __global__ void __launch_bounds__(256) k_band_velocity(Geo g, const double* __re
 __global__ void __launch_bounds__(256, BIB_INTERP_MINB) k_interp_tile(Geo g, WallsDev W, const double* __restrict__ f, const double* __restrict__ force,
                                                      const double* __restrict__ pstate, const double* __restrict__ vpos, double* __restrict__ vvel,
                                                      long long cap_v, int nv, long long first_vertex, int first_particle, unsigned* mask_store, int* band_store,
-                                                     unsigned* fflag) {
+                                                     unsigned* fflag, int compact) {
     __shared__ unsigned s_mask[BAND_WORDS];
     __shared__ int s_pre[BAND_WORDS];
     __shared__ int s_wsum[8];
@@ -1509,11 +1509,24 @@ __global__ void __launch_bounds__(256, BIB_INTERP_MINB) k_interp_tile(Geo g, Wal
         tiled = s_total <= TILE_SLOTS;
     }
     if (tiled) {
-        // velocities of the touched cells
-        for (int t = threadIdx.x; t < total; t += blockDim.x) {
-            const unsigned mw = s_mask[t >> 5];
-            if (!((mw >> (t & 31)) & 1u)) continue;
-            const int slot = s_pre[t >> 5] + __popc(mw & ((1u << (t & 31)) - 1u));
+        // velocities of the touched cells. compact == 0: the threads walk the cells of the box and skip the untouched ones (40 - 60 % of the
+        // lanes idle while the others wait for their 22 loads); compact != 0: the threads walk the SLOTS, i.e. the touched cells only
+        // (slot -> cell: binary search of the word in the prefix counts, then the (slot - prefix)-th set bit of its mask) - every lane has a
+        // cell, more loads in flight per warp, fewer trips. Same cells, same arithmetic per cell.
+        const int n_iter = compact ? s_total : total;
+        for (int it = threadIdx.x; it < n_iter; it += blockDim.x) {
+            int t, slot;
+            if (compact) {
+                slot = it;
+                int lo = 0, hi = BAND_WORDS - 1;                       // last word w with s_pre[w] <= slot (it holds the slot: empty words repeat the prefix of their successor)
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[mid] <= slot) lo = mid; else hi = mid - 1; }
+                t = (lo << 5) + (int)__fns(s_mask[lo], 0u, slot - s_pre[lo] + 1);
+            } else {
+                t = it;
+                const unsigned mw0 = s_mask[t >> 5];
+                if (!((mw0 >> (t & 31)) & 1u)) continue;
+                slot = s_pre[t >> 5] + __popc(mw0 & ((1u << (t & 31)) - 1u));
+            }
             double u[3] = {0.0, 0.0, 0.0};
             long long idx;
             if (d_band_cell(g, b, t, idx)) {
@@ -2162,7 +2175,7 @@ int ib_interpolate(bib_domain* d) {
             for (const ParticleGroup& gr : d->groups) {
                 const ShapeDev& s = d->shapes[gr.shape];
                 k_interp_tile<<<gr.count, 256, smem, d->stream>>>(make_geo(d), W, d->f[d->cur], d->force, d->pstate, d->vpos, d->vvel, d->cap_vertices,
-                                                                  s.nv, gr.first_vertex, gr.first_particle, ms, bs, flags);
+                                                                  s.nv, gr.first_vertex, gr.first_particle, ms, bs, flags, d->interp_compact);
                 d->launches++;
             }
             d->flags_by_masks = flags != nullptr;

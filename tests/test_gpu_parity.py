@@ -823,6 +823,29 @@ def test_fused_interpolation_equals_two_kernel_path(rbc, name):
     assert np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("name", ["ib_rbc2_pfp", "ib_rbc_plates"])
+def test_compact_interpolation_equals_box_walk(rbc, name):
+    """BIB_OPT_INTERP_COMPACT: the fused interpolation kernel evaluates the band velocities slot by slot (touched cells only; slot -> cell through
+    the prefix counts and the n-th set bit of a mask word) instead of walking the particle's box: same cells, same arithmetic, bit for bit -
+    also against the golden dump of the reference (deterministic spread)."""
+    shape, params, rbc_pos, _ = rbc
+    g = np.load(kit.GOLDEN / f"{name}.npz")
+    out = []
+    for compact in (1.0, 0.0):
+        if name == "ib_rbc_plates":
+            lat = _shear_lattice(g, {bib.OPT_DETERMINISTIC_SPREAD: 1.0, bib.OPT_INTERP_COMPACT: compact})
+            sid = lat.register_shape(shape.verts, shape.tris)
+            lat.add_particles(sid, params, g["vert_init"][..., :3])
+            lat.set_boundary(float(g["plates"][0]), float(g["plates"][1]))
+        else:
+            lat = run_ib_case(g, shape, params, deterministic=True)
+            lat.set_option(bib.OPT_INTERP_COMPACT, compact)
+        lat.step(g["body"], n=12)
+        out.append((lat.vertices(), lat.download()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+
+
 def test_lightweight_record_matches_reference_formula(rbc):
     """bib_ib_lightweight_download_async: {id, centre of mass, tensor of gyration, volume} per particle as write_lightweight computes them
     (src/fsi/DeformableParticle3D.hh:110-125,318-333: sequential sums over the vertices, divided by the vertex count)."""

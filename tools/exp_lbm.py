@@ -16,6 +16,7 @@ ap.add_argument("--seconds", type=float, default=1.5)
 ap.add_argument("--nx", type=int, default=128)
 ap.add_argument("--prefetch", type=int, default=-1)
 ap.add_argument("--inplace", type=int, default=-1)
+ap.add_argument("--interp-compact", type=int, default=0)
 ap.add_argument("--ny", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=1024)
 a = ap.parse_args()
@@ -23,6 +24,7 @@ bib.set_default_inplace(a.inplace)
 lat = bib.Lattice(a.nx, a.ny, a.nz, 1.0, 1 / 3)
 lat.set_option(bib.OPT_FUSED_FACE_SWAP, float(a.face_swap))
 lat.set_option(bib.OPT_ENVELOPE_SWAP, float(a.envelope))
+lat.set_option(bib.OPT_INTERP_COMPACT, float(a.interp_compact))
 if a.prefetch >= 0:
     lat.set_option(bib.OPT_LBM_PREFETCH, float(a.prefetch))
 lat.initializeAtEquilibrium(1.0, (0.02, 0.01, -0.01))
@@ -41,7 +43,7 @@ def timed(fn, K=20):
         lat.time_begin(); fn(K); out.append(lat.time_end() / K)
     return out
 k = timed(lambda n: lat.collideAndStream(n))
-res = {"tag": a.tag, "inplace_shift": lat.inplace_shift(), "dims": [a.nx, a.ny, a.nz], "device_bytes": lat.device_bytes(), "lib": os.environ.get("BIB_LIB", "default"), "prefetch": a.prefetch, "face_swap": a.face_swap, "envelope": a.envelope,
+res = {"tag": a.tag, "interp_compact": a.interp_compact, "inplace_shift": lat.inplace_shift(), "dims": [a.nx, a.ny, a.nz], "device_bytes": lat.device_bytes(), "lib": os.environ.get("BIB_LIB", "default"), "prefetch": a.prefetch, "face_swap": a.face_swap, "envelope": a.envelope,
        "lbm_ms_first": k[0], "lbm_ms_median": float(np.median(k)), "lbm_ms_min": float(np.min(k))}
 if a.rbcs:
     s = timed(lambda n: lat.step(body, n=n))
