@@ -191,7 +191,7 @@ struct bib_domain {
     long long lbm_prefetch = 32768;       // BIB_OPT_LBM_PREFETCH: L2 prefetch distance of k_collide_stream in cells (0 = off)
     int spread_sorted = 1;                // BIB_SPREAD_SORTED (experiments): spread the vertices in space-filling-curve order
     int fused_interp = 1;                 // BIB_OPT_FUSED_INTERPOLATION: band velocity + interpolation in one per-particle tile kernel
-    int interp_compact = 0;               // BIB_OPT_INTERP_COMPACT: k_interp_tile evaluates the band velocities slot by slot (touched cells only) instead of cell by cell
+    int interp_compact = 1;               // BIB_OPT_INTERP_COMPACT (default on): k_interp_tile evaluates the band velocities slot by slot (touched cells only) instead of cell by cell
     double regulator_p = 0, regulator_target[3] = {0, 0, 0};
     int plates = 0; double plate_y0 = 0, plate_y1 = 0;      // ImmersedBoundaryDynamics3D::set_boundary: 1 ParallelPlatesBoundary(y0, y1),
     double pipe_radius = 0;                                 //   2 PipeBoundary (axis y = plate_y0, z = plate_y1, radius)

@@ -57,8 +57,8 @@ enum {
     BIB_OPT_FUSE_CALLS = 11,         /* 1 (default): on a single slab the call sequence of one driver step - bib_ib_interpolate_velocity, bib_set_external_vector(whole lattice),
                                         bib_ib_compute_and_spread_forces, bib_ib_move_vertices_and_revoxelize, bib_collide_and_stream - is deferred and executed as one
                                         bib_step (CUDA-graph replay); any other call first executes what is pending, so results are unchanged */
-    BIB_OPT_INTERP_COMPACT = 13,     /* 1: the fused interpolation kernel evaluates the band velocities slot by slot (only the touched cells, every lane busy) instead of
-                                        walking the particle's box; same results bit for bit; 0 (default) */
+    BIB_OPT_INTERP_COMPACT = 13,     /* 1 (default): the fused interpolation kernel evaluates the band velocities slot by slot (only the touched cells, every lane busy);
+                                        0: it walks the particle's box and skips the untouched cells; same results bit for bit */
     BIB_OPT_LBM_PREFETCH = 12,       /* L2 prefetch distance of the collide-and-stream kernel, in cells ahead in memory order (default 32768; 0 = off); results unaffected */
     BIB_OPT_SPARSE_FORCE = 5         /* 1 (default): the lattice kernel skips the force read of every cell that still holds the uniform body
                                         force (1 flag bit per cell, set by the spread, cleared by the band reset); 0: always read it */
