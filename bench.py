@@ -735,8 +735,8 @@ def ours(args):
             drv = driver_speed()
         line = {"metric": "D3Q19+IB MLUPS (fp64, full driver step)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K,
                 "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": (w1 - w0) * 1e3 / ((len(blocks) + 1) * K), "higher_is_better": True,
-                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(args, world), population_storage=(f"in place, shift {inplace_shift} planes" if inplace_shift else "two buffers (A/B)")),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "population_storage": f"in place, shift {inplace_shift} planes" if inplace_shift else "two buffers (A/B)",
                 "repeats": repeats, "roofline": roofline, "ib": ib, "phases_ms": phases, "parity_check": parity, "cpu_baseline": cpu,
                 "e2e": e2e, "e2e_all_vertices": e2e_all, "driver_e2e": drv, "gpu_launches": int(round(launches_per_block)), "clocks": clocks,
                 "device_bytes": dev_bytes if drv is not None else lat.device_bytes()}

@@ -8,7 +8,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/r2q_bench_inplace_n1.json").read().strip().splitlines()[-1])
-    print("inplace n1:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["roofline"]["sustained"]["ms_per_launch"], d["config"]["population_storage"], d["device_bytes"], d["parity_check"])
+    print("inplace n1:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["roofline"]["sustained"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["device_bytes"], d["parity_check"])
 except Exception as e:
     print("no bench line", e)
 PY
@@ -17,7 +17,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/r2q_bench_768.json").read().strip().splitlines()[-1])
-    print("768^3:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["config"]["population_storage"], d["device_bytes"], d["e2e"]["ms_per_step"])
+    print("768^3:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["device_bytes"], d["e2e"]["ms_per_step"])
 except Exception as e:
     print("no bench line", e)
 PY

@@ -16,7 +16,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/r2r_bench_768x1024x1024.json").read().strip().splitlines()[-1])
-    print("768x1024x1024:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["config"]["population_storage"], d["device_bytes"], d["e2e"]["ms_per_step"])
+    print("768x1024x1024:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["device_bytes"], d["e2e"]["ms_per_step"])
 except Exception as e:
     print("no bench line", e)
 PY

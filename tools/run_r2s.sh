@@ -8,7 +8,7 @@ python - <<PY
 import json
 try:
     d = json.loads(open("gpurun_out/r2s_1024cubed_n$N.json").read().strip().splitlines()[-1])
-    print("1024^3:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["config"]["population_storage"], d["device_bytes"], d["e2e"]["ms_per_step"], d["phases_ms"], d["parity_check"]["max_rel_err"], d["parity_check"]["pass"])
+    print("1024^3:", d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["device_bytes"], d["e2e"]["ms_per_step"], d["phases_ms"], d["parity_check"]["max_rel_err"], d["parity_check"]["pass"])
 except Exception as e:
     print("no bench line", e)
 PY

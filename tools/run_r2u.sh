@@ -11,7 +11,7 @@ import json
 for f in ["gpurun_out/r2u_weak_n$N.json", "gpurun_out/r2u_1024cubed_n$N.json"]:
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d["config"]["population_storage"], d["e2e"]["ms_per_step"], d["phases_ms"], d["parity_check"] and (d["parity_check"]["max_rel_err"], d["parity_check"]["pass"]))
+        print(f, d["ms_per_step"], d["value"], d["roofline"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["e2e"]["ms_per_step"], d["phases_ms"], d["parity_check"] and (d["parity_check"]["max_rel_err"], d["parity_check"]["pass"]))
     except Exception as e:
         print("no bench line", f, e)
 PY

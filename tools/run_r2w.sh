@@ -9,7 +9,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/r2w_bench_n1.json").read().strip().splitlines()[-1])
-    print("n1:", d["ms_per_step"], d["value"], d["roofline"]["frac"], d["roofline"]["ms_per_launch"], d["config"]["population_storage"], d["e2e"]["ms_per_step"], d["parity_check"]["pass"], d["cpu_baseline"] and d["cpu_baseline"]["value"], d["clocks"])
+    print("n1:", d["ms_per_step"], d["value"], d["roofline"]["frac"], d["roofline"]["ms_per_launch"], d.get("population_storage", d["config"].get("population_storage")), d["e2e"]["ms_per_step"], d["parity_check"]["pass"], d["cpu_baseline"] and d["cpu_baseline"]["value"], d["clocks"])
 except Exception as e:
     print("no bench line", e)
 PY
