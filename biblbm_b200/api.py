@@ -25,7 +25,7 @@ SYMBOLS = [
     "bib_ib_particles_add", "bib_ib_rigid_particles_add", "bib_ib_rigid_state_download", "bib_ib_rigid_state_upload", "bib_ib_set_regulator", "bib_ib_set_parallel_plates", "bib_ib_set_pipe", "bib_ib_set_wall_interaction", "bib_ib_set_wall_interaction_boundary", "bib_ib_set_pp_interaction", "bib_ib_count", "bib_ib_local_slots", "bib_ib_interpolate_velocity", "bib_ib_compute_and_spread_forces",
     "bib_ib_move_vertices_and_revoxelize", "bib_ib_step", "bib_ib_multi_direct_forcing", "bib_add_velocity_edge", "bib_ib_vertices_download", "bib_ib_vertices_upload", "bib_ib_vertex_forces_preload",
     "bib_ib_particle_scalars_download", "bib_ib_particle_scalars_upload", "bib_ib_results_download_async", "bib_ib_lightweight_download_async", "bib_ib_results_wait", "bib_ib_results_count", "bib_step", "bib_comm_unique_id", "bib_comm_init", "bib_sync", "bib_time_begin", "bib_time_end",
-    "bib_kernel_launch_count", "bib_device_memory_bytes", "bib_phase_timing", "bib_phase_times", "bib_set_default_inplace", "bib_domain_inplace_shift",
+    "bib_kernel_launch_count", "bib_device_memory_bytes", "bib_phase_timing", "bib_phase_times", "bib_set_default_inplace", "bib_domain_inplace_shift", "bib_inplace_schedule",
 ]
 
 OPT_ENVELOPE_SWAP, OPT_DETERMINISTIC_SPREAD, OPT_REGULATOR, OPT_SPREAD_MODE, OPT_SPARSE_FORCE, OPT_STEP_GRAPH, OPT_FUSED_FACE_SWAP, OPT_OVERLAP_FORCES, OPT_PREFETCH_FORCES = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -82,6 +82,14 @@ def device_count() -> int:
 def set_default_inplace(shift_planes: int) -> None:
     """Population storage of the lattices created from now on: 0 two buffers, >= 2 in place with that shift, -1 automatic."""
     _check(load_library().bib_set_default_inplace(int(shift_planes)))
+
+
+def inplace_schedule(nx: int, shift_planes: int, frame: int):
+    """[(first plane, planes)] of the launches of one in-place step, as the library issues them (host-side; no device needed)."""
+    cap = int(nx) + 1
+    first, count, n = (C.c_int * cap)(), (C.c_int * cap)(), C.c_int(0)
+    _check(load_library().bib_inplace_schedule(int(nx), int(shift_planes), int(frame), cap, first, count, C.byref(n)))
+    return [(first[i], count[i]) for i in range(n.value)]
 
 
 def comm_unique_id() -> bytes:

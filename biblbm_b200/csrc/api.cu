@@ -111,6 +111,16 @@ int bib_set_default_inplace(int shift_planes) {
     g_default_inplace = shift_planes;
     return 1;
 }
+int bib_inplace_schedule(int nx, int shift_planes, int frame, int capacity, int* first_plane, int* n_planes, int* n_launches) {
+    if (!first_plane || !n_planes || !n_launches) { bib_set_error("inplace_schedule: null argument"); return 0; }
+    if (nx < 1 || shift_planes < 2 || (frame != 0 && frame != 1)) { bib_set_error("inplace_schedule: nx >= 1, shift >= 2, frame 0 or 1"); return 0; }
+    std::vector<std::pair<int, int>> launches;
+    lbm_inplace_schedule(nx, shift_planes, frame, launches);
+    *n_launches = (int)launches.size();
+    if ((int)launches.size() > capacity) { bib_set_error("inplace_schedule: capacity too small"); return 0; }
+    for (size_t i = 0; i < launches.size(); ++i) { first_plane[i] = launches[i].first; n_planes[i] = launches[i].second; }
+    return 1;
+}
 int bib_domain_inplace_shift(bib_domain* d, int* shift_planes) {
     if (!d) { bib_set_error("null domain handle"); return 0; }
     if (!shift_planes) { bib_set_error("domain_inplace_shift: null argument"); return 0; }

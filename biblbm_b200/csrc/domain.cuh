@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #define BIB_Q 19
@@ -264,6 +265,7 @@ bool bib_cuda_ok(cudaError_t e, const char* what);
 
 // ---- kernels / host launchers implemented in the .cu files
 int lbm_launch_collide_stream(bib_domain* d);
+void lbm_inplace_schedule(int nx, int shift, int cur, std::vector<std::pair<int, int>>& launches);
 int lbm_launch_upload(bib_domain* d, const int box[6], const double* cells);
 int lbm_launch_download(bib_domain* d, const int box[6], double* cells);
 int lbm_launch_set_external(bib_domain* d, const int box[6], double fx, double fy, double fz);

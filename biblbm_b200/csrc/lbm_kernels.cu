@@ -839,15 +839,24 @@ static void launch_faces(bib_domain* d, const LbmParams& p, int face_mask, int x
 // [a, a + C) reads storage planes a + 1 + S .. a + C + S and pushes into a .. a + C + 1 (frame 0 -> 1; mirrored for 1 -> 0), so with
 // C <= S - 1 it never writes a plane it reads, and taking the launches in ascending x (frame 0 -> 1; descending for 1 -> 0) every plane a
 // launch overwrites has been read by an earlier launch of the same stream. Every destination slot is still written exactly once.
+// (host only; exported as bib_inplace_schedule so that the CPU tests check the invariants on the launch list the library really uses)
+void lbm_inplace_schedule(int nx, int shift, int cur, std::vector<std::pair<int, int>>& launches) {
+    launches.clear();
+    const int C = shift - 1;
+    const bool ascending = cur == 0;
+    for (int done = 0; done < nx; done += C) {
+        const int n = std::min(C, nx - done);
+        launches.emplace_back(ascending ? done : nx - done - n, n);      // (first plane, planes)
+    }
+}
 static int launch_inplace(bib_domain* d, const LbmParams& p) {
-    const int C = d->inplace_shift - 1;
-    const bool ascending = d->cur == 0;
-    for (int done = 0; done < d->nx; done += C) {
-        const int n = std::min(C, d->nx - done);
+    std::vector<std::pair<int, int>> launches;
+    lbm_inplace_schedule(d->nx, d->inplace_shift, d->cur, launches);
+    for (const std::pair<int, int>& l : launches) {
         LbmParams pc = p;
-        pc.x_first = ascending ? done : d->nx - done - n;
+        pc.x_first = l.first;
         pc.x_stride = 1;
-        launch_main(d, pc, n, d->stream);
+        launch_main(d, pc, l.second, d->stream);
     }
     BIB_CHECK(cudaGetLastError());
     return 1;

@@ -94,6 +94,10 @@ int bib_domain_create_multi(int nx, int ny, int nz, int n_ext, double omega_oute
  * The environment variable BIB_INPLACE gives the initial value. bib_domain_inplace_shift reports what a domain uses (0 = A/B). */
 int bib_set_default_inplace(int shift_planes);
 int bib_domain_inplace_shift(bib_domain* d, int* shift_planes);
+/* The launches of ONE in-place step of an nx-plane slab whose current state is frame `frame` (0 / 1), in issue order: launch i covers the planes
+ * [first_plane[i], first_plane[i] + n_planes[i]). Host-side arithmetic only (no device needed): what the library itself iterates over; the CPU
+ * tests check on it that no launch overwrites a plane that it or a later launch still reads (tests/test_inplace_model.py). */
+int bib_inplace_schedule(int nx, int shift_planes, int frame, int capacity, int* first_plane, int* n_planes, int* n_launches);
 int bib_domain_slab_count(bib_domain* d, int* n_slabs);
 int bib_domain_slab(bib_domain* d, int slab, bib_domain** out);      /* the handle of one slab (owned by the multi-slab handle) */
 int bib_domain_destroy(bib_domain* d);

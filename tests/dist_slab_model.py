@@ -13,6 +13,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent))
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import kit  # noqa: E402
 
 PLUS_X = [10, 13, 14, 15, 16]
@@ -78,11 +79,10 @@ class InPlaceSlab:
         return self.mem[:, b:b + self.nx + 2]
 
     def step(self, orc, omega0, omega1, rank, world, per):
-        nx, C = self.nx, self.S - 1
+        import biblbm_b200 as bib
+        nx = self.nx
         src, dst = self.base(self.cur), self.base(1 - self.cur)
-        for done in range(0, nx, C):
-            n = min(C, nx - done)
-            a = done if self.cur == 0 else nx - done - n
+        for a, n in bib.inplace_schedule(nx, self.S, self.cur):       # the library's own launch list (host-side)
             chunk = np.concatenate([np.moveaxis(self.mem[:, src + 1 + a:src + 1 + a + n], 0, -1), self.ext[a:a + n]], axis=-1)
             assert not np.isnan(chunk).any(), "a launch read a plane that an earlier launch of the step had overwritten with nothing valid"
             push_planes(orc, np.ascontiguousarray(chunk), a, nx, self.mem, dst + 1, omega0, omega1, rank, world, per)

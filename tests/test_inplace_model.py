@@ -1,8 +1,8 @@
 """CPU model of the in-place streaming schedule (biblbm_b200/csrc/lbm_kernels.cu: launch_inplace, k_ghost_wrap).
 
 One population buffer of nx + 2 + S planes is seen through two frames S planes apart; a step pushes from one frame into the other in
-launches of at most S - 1 planes, ascending in x for frame 0 -> 1 and descending for 1 -> 0. The model replays exactly that address
-arithmetic with numpy on a small lattice (pure streaming, every population value unique) and checks, for every launch, that
+launches of at most S - 1 planes, ascending in x for frame 0 -> 1 and descending for 1 -> 0. The launch list is the library's own
+(bib_inplace_schedule, host-side); the model replays the address arithmetic with numpy on a small lattice (pure streaming, every population value unique) and checks, for every launch, that
  (1) no launch writes a storage location that it or a LATER launch of the step still has to read (the threads of a launch run in
      any order, launches of a stream run in order),
  (2) every destination slot is written exactly once,
@@ -12,6 +12,8 @@ import itertools
 
 import numpy as np
 import pytest
+
+import biblbm_b200 as bib
 
 CX = [0, -1, 0, 0, -1, -1, -1, -1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 0]
 CY = [0, 0, -1, 0, -1, 1, 0, 0, -1, -1, 0, 1, 0, 1, -1, 0, 0, 1, 1]
@@ -63,15 +65,8 @@ class InPlace:
     def step(self):
         nx, ny, nz, S = self.nx, self.ny, self.nz, self.S
         src, dst = self.base(self.cur), self.base(1 - self.cur)
-        C = S - 1
-        ascending = self.cur == 0
-        chunks = []
-        done = 0
-        while done < nx:
-            n = min(C, nx - done)
-            a = done if ascending else nx - done - n
-            chunks.append((a, a + n))
-            done += C
+        # the launch list comes from the LIBRARY (bib_inplace_schedule = what launch_inplace iterates over; host-side, no device needed)
+        chunks = [(a, a + n) for a, n in bib.inplace_schedule(nx, S, self.cur)]
         unread = np.zeros(self.mem.shape[1], dtype=bool)
         unread[src + 1:src + 1 + nx] = True
         written = np.zeros(self.mem.shape, dtype=np.int32)
@@ -187,3 +182,34 @@ def test_inplace_slabs_with_pulled_halo_equal_the_undivided_lattice(per, widths,
         ref = stream_two_buffers(ref, per)
         got = np.concatenate([s.state() for s in slabs], axis=1)
         assert np.array_equal(got, ref), f"step {step + 1}"
+
+
+def test_library_schedule_invariants_for_many_sizes():
+    """For every (nx, shift, frame) of a sweep - including the bench slab (128, 17), the drivers' 97-plane lattices and shifts wider than the
+    slab - the library's launch list covers every plane exactly once and no launch writes a storage plane that it or a LATER launch reads
+    (storage plane of (frame 0, x) = x + 1 + S, of (frame 1, x) = x + 1; a launch over [a, b) writes the planes a - 1 .. b of the other frame)."""
+    checked = 0
+    for nx in list(range(1, 40)) + [61, 97, 121, 128, 241, 512, 768]:
+        for S in [2, 3, 4, 5, 8, 9, 16, 17, 33, 64, 65, 129, 1000]:
+            for frame in (0, 1):
+                launches = bib.inplace_schedule(nx, S, frame)
+                src, dst = (S, 0) if frame == 0 else (0, S)
+                covered = sorted(x for a, n in launches for x in range(a, a + n))
+                assert covered == list(range(nx)), (nx, S, frame)
+                assert all(1 <= n <= S - 1 for _, n in launches)
+                reads = [set(range(src + 1 + a, src + 1 + a + n)) for a, n in launches]
+                for i, (a, n) in enumerate(launches):
+                    writes = set(range(dst + 1 + a - 1, dst + 1 + a + n + 1))
+                    still_needed = set().union(*reads[i:])
+                    assert not (writes & still_needed), (nx, S, frame, i)
+                checked += 1
+    assert checked > 1000
+
+
+def test_schedule_argument_checking():
+    with pytest.raises(bib.BibError, match="inplace_schedule"):
+        bib.inplace_schedule(10, 1, 0)
+    with pytest.raises(bib.BibError, match="inplace_schedule"):
+        bib.inplace_schedule(0, 5, 0)
+    with pytest.raises(bib.BibError, match="inplace_schedule"):
+        bib.inplace_schedule(10, 5, 2)
